@@ -1,0 +1,234 @@
+/* fwb200.h — C ABI of the B200-native batched fixed-wing simulator (libfwb200.so).
+ *
+ * Drop-in boundary for the hot path named by BASELINE.json:north_star: everything below the SB3 `VecEnv`
+ * contract of the reference (magpie/libs/stable-baselines3/stable_baselines3/common/vec_env/base_vec_env.py:48-224)
+ * for the `FixedWingAircraft` env (magpie/libs/fixed-wing-gym/gym_fixed_wing/fixed_wing.py:13-1736) on top of the
+ * `PyFly` simulator (magpie/libs/pyfly/pyfly/pyfly.py:1030-1881, dryden.py:6-261), plus the GAE pass of the
+ * forked SB3 RolloutBuffer (stable_baselines3/common/buffers.py:304-333).
+ *
+ * Conventions
+ *  - Plain C: pointers, sizes, PODs.  No torch / C++ types.
+ *  - Every `*_dev` pointer is a DEVICE pointer owned by the caller (e.g. a torch CUDA tensor's data_ptr()).
+ *    Env state (structure-of-arrays in HBM) is owned by the handle.
+ *  - All compute entry points are asynchronous on the `stream` argument (a cudaStream_t passed as void*;
+ *    NULL = legacy default stream).  Nothing here synchronises except fw_create / fw_destroy / the host getters.
+ *  - Return value: 0 on success, negative FW_E* on USAGE errors only.  Simulation failures (constraint violations,
+ *    pyfly's ConstraintException pyfly.py:11-16) are DATA: they set done=1 and term_code, never an error.
+ *  - One handle per GPU; a handle is not thread-safe.  There is no CPU fallback: without a CUDA device
+ *    fw_create returns FW_ENODEVICE.
+ */
+#ifndef FWB200_H
+#define FWB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FW_ABI_VERSION 1
+
+#define FW_NY 19        /* ODE state: quat[4] omega[3] pos[3] vel[3] act_value[3] act_rate[3]  (pyfly.py:1372-1389) */
+#define FW_NOBS 14      /* default observation vector (fixed_wing_config.json "observation.states")               */
+#define FW_NACT 3       /* elevator, aileron, throttle (fixed_wing_config.json "action.states")                   */
+#define FW_NSTATE_INJECT 21 /* roll pitch yaw p q r pn pe pd u v w | er el thr | er_dot el_dot thr_dot | wind n e d */
+#define FW_NMETRIC 28   /* see FwMetricIndex                                                                      */
+#define FW_ACT_WINDOW_MAX 8
+#define FW_END_ERR_WINDOW 50   /* fixed_wing.py:1666 */
+
+enum FwError {
+    FW_OK = 0,
+    FW_EINVAL = -1,      /* bad argument / shape / config */
+    FW_ENODEVICE = -2,   /* no CUDA device or wrong architecture */
+    FW_ECUDA = -3,       /* CUDA runtime error (see fw_last_error) */
+    FW_ENOMEM = -4
+};
+
+/* term_code[n] written on done (fixed_wing.py:521,550,595): */
+enum FwTermCode {
+    FW_TERM_NONE = 0,
+    FW_TERM_STEPS = 1,
+    FW_TERM_SUCCESS = 2,
+    FW_TERM_OMEGA_P = 10,   /* ConstraintException variable (pyfly.py:121-125) */
+    FW_TERM_OMEGA_Q = 11,
+    FW_TERM_OMEGA_R = 12,
+    FW_TERM_VA = 13
+};
+
+enum FwIntegrator {
+    FW_INT_RK45_SCIPY = 0,  /* bit-for-logic replica of scipy solve_ivp RK45 as called at pyfly.py:1393-1395 */
+    FW_INT_RK4_FIXED = 1    /* fixed-step classical RK4 x substeps (throughput mode, graded at its own tolerance) */
+};
+
+enum FwPrecision { FW_F64 = 0, FW_F32 = 1 };
+
+enum FwTargetClass { FW_TGT_CONSTANT = 0, FW_TGT_COMPENSATE = 1 };   /* fixed_wing.py:1375-1431 */
+enum FwOnSuccess { FW_SUCCESS_NONE = 0, FW_SUCCESS_DONE = 1, FW_SUCCESS_NEW = 2 }; /* fixed_wing.py:548-553 */
+
+/* Layout of the per-env metric row written when an episode ends (fixed_wing.py:1644-1736). NaN = numpy nan. */
+enum FwMetricIndex {
+    FW_M_RISE_TIME = 0,        /* [3] roll pitch Va            */
+    FW_M_SETTLING_TIME = 3,    /* [4] roll pitch Va all        */
+    FW_M_OVERSHOOT = 7,        /* [3]                          */
+    FW_M_TOTAL_ERROR = 10,     /* [3]                          */
+    FW_M_AVG_ERROR = 13,       /* [3]                          */
+    FW_M_CONTROL_VARIATION = 16, /* [1]                        */
+    FW_M_SUCCESS = 17,         /* [4] 0/1                      */
+    FW_M_SUCCESS_TIME_FRAC = 21, /* [4]                        */
+    FW_M_END_ERROR = 25        /* [3]                          */
+};
+
+/* One Dryden shaping filter in lsim form (dryden.py:22-39 -> scipy.signal.lsim):
+ *   x_i = Ad x_{i-1} + Bd0 u_{i-1} + Bd1 u_i ;  y_i = C x_i + D u_i ;  x_0 = 0.
+ * Matrices are computed on the host at init from the reference's (mis-ordered) parameters. */
+typedef struct FwFilter {
+    int32_t order;        /* 1..3 */
+    int32_t noise_row;    /* which of the 4 white-noise rows drives it (dryden.py:238-252: u0 v1 w2 p3 q1 r2) */
+    double Ad[9];         /* row-major order x order */
+    double Bd0[3];
+    double Bd1[3];
+    double C[3];
+    double D;
+} FwFilter;
+
+typedef struct FwConfig {
+    int32_t abi_version;      /* FW_ABI_VERSION */
+    int32_t precision;        /* FwPrecision: arithmetic type of the step kernel */
+    int32_t integrator;       /* FwIntegrator */
+    int32_t rk4_substeps;     /* for FW_INT_RK4_FIXED */
+    double rtol, atol;        /* for FW_INT_RK45_SCIPY (scipy defaults 1e-3 / 1e-6) */
+
+    /* ---- aircraft parameters (x8_param.mat, pyfly.py:1076-1119) ---- */
+    double mass, Jx, Jy, Jz, Jxz, S_wing, b, c, S_prop, C_prop, k_motor, k_T_P, k_Omega, e_oswald, M, a_0;
+    double C_L_0, C_L_alpha, C_L_q, C_L_delta_e;
+    double C_D_p, C_D_q, C_D_beta1, C_D_beta2, C_D_delta_e;
+    double C_m_0, C_m_alpha, C_m_q, C_m_delta_e, C_m_fp;
+    double C_Y_0, C_Y_beta, C_Y_p, C_Y_r, C_Y_delta_a, C_Y_delta_r;
+    double C_l_0, C_l_beta, C_l_p, C_l_r, C_l_delta_a, C_l_delta_r;
+    double C_n_0, C_n_beta, C_n_p, C_n_r, C_n_delta_a, C_n_delta_r;
+
+    /* ---- simulator (pyfly_config.json + the gym config's "simulator.states" overrides) ---- */
+    double dt, rho, g;
+    double elevon_min, elevon_max;        /* value clip, rad (pyfly_config.json elevon_*: -30..35 deg) */
+    double elevon_dot_max;                /* rate clip 3.4907 (NOT degree-converted: SURVEY App. E-6) */
+    double elevon_omega0, elevon_zeta;    /* 2nd-order actuator (pyfly.py:299-304) */
+    double throttle_min, throttle_max, throttle_tau; /* 1st-order actuator (pyfly.py:296-298) */
+    double omega_con_min[3], omega_con_max[3];   /* ConstraintException limits on p,q,r (rad/s) */
+    double va_value_min;                  /* Va clip floor 1e-6 */
+    double va_con_max;                    /* Va constraint (70); <=0 disables */
+    double init_lo[12], init_hi[12];      /* uniform init ranges: roll pitch yaw p q r pn pe pd u v w (pyfly.py:94) */
+    double wind_mag_min, wind_mag_max;    /* steady wind sampling (pyfly.py:816-823) */
+    int32_t turbulence;                   /* 0/1 */
+    int32_t _pad0;
+    double turb_noise_scale;              /* sqrt(pi/dt_dryden) (dryden.py:172,187) */
+    FwFilter filt[6];                     /* H_u H_v H_w H_p H_q H_r */
+
+    /* ---- gym env (fixed_wing_config.json) ---- */
+    int32_t steps_max;
+    int32_t scale_actions;                /* action.scale_space */
+    double scale_low, scale_high;         /* action.scale_low/high (-1, 1) */
+    double act_lo[3], act_hi[3];          /* actuator ranges used by linear_action_scaling (fixed_wing.py:250-251) */
+    int32_t has_action_bounds;            /* action.bounds_multiplier present */
+    int32_t _pad1;
+    double action_bounds_min[3], action_bounds_max[3];  /* fixed_wing.py:264-276 */
+    double tgt_low[3], tgt_high[3];       /* roll pitch Va, radians where applicable */
+    double tgt_delta[3];                  /* NaN = no delta */
+    double tgt_bound[3];                  /* goal bounds */
+    int32_t tgt_class[3];                 /* FwTargetClass */
+    int32_t on_success;                   /* FwOnSuccess */
+    int32_t streak_req;                   /* target.success_streak_req (<=128) */
+    int32_t resample_every;
+    double streak_fraction;
+    double rew_err_scaling[3], rew_err_max[3];   /* linear error factors; max = +inf when absent */
+    double rew_delta_scaling, rew_delta_max;     /* action-delta factor; scaling<=0 disables */
+    double rew_bound_scaling, rew_bound_max;     /* action-bound factor; scaling<=0 disables */
+    int32_t rew_delta_window;             /* 5 */
+    int32_t obs_act_window;               /* 5 (observation "window_size") */
+    int32_t step_fail_timesteps;          /* reward.step_fail == "timesteps" */
+    int32_t _pad2;
+    double step_fail_value;
+    double rise_low, rise_high;           /* rise_time metric limits (0.1, 0.9) */
+
+    /* ---- counter-based RNG (Philox4x32-10) for auto-reset and turbulence noise ---- */
+    uint64_t seed;
+    int64_t env_id_offset;                /* global id of env 0 of this handle (sharding: rank*n_envs) */
+} FwConfig;
+
+typedef struct FwHandle FwHandle;
+
+/* Replaces: FixedWingAircraft.__init__ (fixed_wing.py:14-306) + PyFly.__init__ (pyfly.py:1054-1249) for n_envs envs.
+ * `device` is the CUDA ordinal.  All envs start un-reset (call fw_reset with mask=NULL). */
+int fw_create(const FwConfig* cfg, int32_t n_envs, int32_t device, FwHandle** out);
+int fw_destroy(FwHandle* h);
+const char* fw_last_error(void);
+int fw_abi_version(void);
+
+/* Replaces: FixedWingAircraft.reset(state, target, turbulence_noise) (fixed_wing.py:414-481 -> pyfly.py:1262-1311).
+ *  mask_dev        [n] uint8, nullable (NULL = all envs): which envs to reset.
+ *  state_dev       [n, FW_NSTATE_INJECT] f64, nullable: injected initial state (NaN entries = sample that entry).
+ *  target_dev      [n, 3] f64, nullable: injected targets (roll, pitch, Va).
+ *  noise_dev       [n, 4, noise_len] f64, nullable: injected unit white noise (pyfly.py:1294, dryden.py:184-188);
+ *                  when NULL turbulence noise is generated from Philox. The buffer must stay alive while in use.
+ *  obs_dev         [n, FW_NOBS] f32, nullable: reset observation for the masked envs (others untouched).
+ *  obs64_dev       [n, FW_NOBS] f64, nullable.
+ */
+int fw_reset(FwHandle* h, const uint8_t* mask_dev, const double* state_dev, const double* target_dev,
+             const double* noise_dev, int32_t noise_len, float* obs_dev, double* obs64_dev, void* stream);
+
+/* Replaces: VecEnv.step_async/step_wait over FixedWingAircraft.step (fixed_wing.py:483-628 -> pyfly.py:1358-1420),
+ * including the VecEnv auto-reset contract (subproc_vec_env.py:26-31 / dummy_vec_env.py:46-50).
+ *  actions_dev     [n, 3]; f32 when actions_f64==0, f64 otherwise.  Raw agent actions (pre-clip, pre-scale).
+ *  obs_dev         [n, FW_NOBS] f32: next observation (the RESET observation for envs that finished).
+ *  rew_dev         [n] f32;  done_dev [n] uint8.
+ *  term_obs_dev    [n, FW_NOBS] f32, nullable: info["terminal_observation"] rows (written only where done).
+ *  obs64_dev, rew64_dev   nullable f64 copies (parity tests / PID harness that consumes f64 obs).
+ *  auto_reset      0: leave finished envs in their terminal state (caller resets, e.g. evaluate_controller.py:174).
+ */
+int fw_step(FwHandle* h, const void* actions_dev, int32_t actions_f64, float* obs_dev, float* rew_dev,
+            uint8_t* done_dev, float* term_obs_dev, double* obs64_dev, double* rew64_dev, int32_t auto_reset,
+            void* stream);
+
+/* K fused steps per launch with Philox U(-1,1)^3 actions generated in-kernel (random-action throughput workloads
+ * C2/C3 of BASELINE.json; the policy-free analogue of collect_rollouts, on_policy_algorithm.py:123-191).
+ * Accumulates per-env reward sums / done counts into the episode-statistics arrays. */
+int fw_step_random(FwHandle* h, int32_t k_steps, uint64_t action_seed, float* obs_dev, float* rew_dev,
+                   uint8_t* done_dev, void* stream);
+
+/* Per-env info on done: term_code [n] int32, metrics [n, FW_NMETRIC] f64, episode return/length (Monitor,
+ * common/monitor.py:99-113).  Valid for envs whose done flag was set by the most recent fw_step. */
+int fw_get_episode_info(FwHandle* h, int32_t* term_code_dev, double* metrics_dev, double* ep_return_dev,
+                        int32_t* ep_length_dev, void* stream);
+
+/* State access for parity tests and checkpointing (SoA -> [n, width] row-major f64 / int32).
+ * field ids: see FwField. */
+enum FwField {
+    FW_FIELD_Y = 0,          /* [n,19] f64 ODE state                                          */
+    FW_FIELD_EULER = 1,      /* [n,3]  roll pitch yaw (state .value)                          */
+    FW_FIELD_VAB = 2,        /* [n,3]  Va alpha beta                                          */
+    FW_FIELD_WIND = 3,       /* [n,3]  steady wind NED                                        */
+    FW_FIELD_TARGET = 4,     /* [n,3]  roll pitch Va targets                                  */
+    FW_FIELD_CMD = 5,        /* [n,3]  constrained elevator/aileron/throttle commands         */
+    FW_FIELD_TURB = 6,       /* [n,6]  turbulence sample used by the NEXT step (lin3, ang3)   */
+    FW_FIELD_COUNTERS = 7,   /* [n,4]  int32: steps_count, steps_for_target, sim_step, episode*/
+    FW_FIELD_NFEV = 8,       /* [n,2]  int32: RHS evaluations, RK attempts of the last step   */
+    FW_FIELD_COUNT = 9
+};
+int fw_get_field(FwHandle* h, int32_t field, void* out_dev, void* stream);
+int fw_set_field(FwHandle* h, int32_t field, const void* in_dev, void* stream);
+
+/* Replaces: RolloutBuffer.compute_returns_and_advantage (buffers.py:304-333), time-major [T, N] f32 arrays.
+ * dones[t] is the "episode ended before obs[t]" flag stored by RolloutBuffer.add (on_policy_algorithm.py:178);
+ * last_done is the done vector returned by the final env.step (uint8).  Bit-exact with the reference's mixed
+ * f32-delta / f64-carry arithmetic. */
+int fw_gae(const float* rew_dev, const float* val_dev, const float* done_dev, const float* last_val_dev,
+           const uint8_t* last_done_dev, float* adv_dev, float* ret_dev, int32_t T, int32_t N, float gamma,
+           float gae_lambda, void* stream);
+
+/* Vector-pipe peak micro-benchmarks (dependent-chain-free FMA loops) used as roofline denominators by bench.py:
+ * returns achieved TFLOP/s (2 flop per FMA) measured with CUDA events on `device`. */
+int fw_measure_fma_peak(int32_t device, int32_t precision, double* tflops_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FWB200_H */

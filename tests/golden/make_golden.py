@@ -1,0 +1,384 @@
+"""Generate the golden fixtures in this directory by running the UNMODIFIED reference where it lies.
+
+TEST INFRASTRUCTURE — run here (the build container, where /root/reference is mounted), never on the
+GPU box.  Usage:  python tests/golden/make_golden.py [params|traj|turb|fail|full|pid|gae|dryden|all]
+
+Everything is recorded through the reference's public surface:
+  FixedWingAircraft.reset(state=, target=, turbulence_noise=) / .step(action)
+      (magpie/libs/fixed-wing-gym/gym_fixed_wing/fixed_wing.py:414, :483)
+  PyFly state objects (magpie/libs/pyfly/pyfly/pyfly.py:1129-1221)
+  RolloutBuffer.compute_returns_and_advantage (magpie/libs/stable-baselines3/stable_baselines3/common/buffers.py:304)
+Per-step RHS-evaluation counts are taken by wrapping PyFly._dynamics (pyfly.py:1450) with a counter.
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from oracle import refshim  # noqa: E402
+
+refshim.install()
+from gym_fixed_wing.fixed_wing import FixedWingAircraft  # noqa: E402
+from pyfly.pid_controller import PIDController  # noqa: E402
+
+STATE_KEYS = ["roll", "pitch", "yaw", "omega_p", "omega_q", "omega_r", "position_n", "position_e", "position_d",
+              "velocity_u", "velocity_v", "velocity_w"]
+TARGET_KEYS = ["roll", "pitch", "Va"]
+
+
+def make_env(turbulence, config_kw=None, intensity="light"):
+    env = FixedWingAircraft(refshim.GYM_CONFIG, config_kw=config_kw,
+                            sim_config_kw={"turbulence": turbulence, "turbulence_intensity": intensity})
+    env.seed(0)
+    sim = env.simulator
+    sim._nfev = 0
+    inner = sim._dynamics
+
+    def counted(t, y, control_sp=None):
+        sim._nfev += 1
+        return inner(t, y, control_sp)
+
+    sim._dynamics = counted
+    return env
+
+
+def term_code(term):
+    """0 none, 1 steps, 2 success, 10+k constraint on (omega_p, omega_q, omega_r, Va)[k]."""
+    if term in ("", None):
+        return 0
+    if term in ("steps", "success"):
+        return 1 if term == "steps" else 2
+    return 10 + ["omega_p", "omega_q", "omega_r", "Va"].index(term)
+
+
+def snapshot(env):
+    sim = env.simulator
+    y = list(sim.state["attitude"].value)
+    y += sim.get_states_vector(["omega_p", "omega_q", "omega_r", "position_n", "position_e", "position_d",
+                                "velocity_u", "velocity_v", "velocity_w"])
+    y += sim.actuation.get_values()
+    euler = sim.get_states_vector(["roll", "pitch", "yaw"])
+    vab = sim.get_states_vector(["Va", "alpha", "beta"])
+    cmd = [sim.state[k].command for k in ("elevator", "aileron", "throttle")]
+    cmd = [np.nan if c is None else c for c in cmd]
+    tgt = [env.target[k] for k in TARGET_KEYS]
+    return (np.array(y, dtype=np.float64), np.array(euler, dtype=np.float64), np.array(vab, dtype=np.float64),
+            np.array(cmd, dtype=np.float64), np.array(tgt, dtype=np.float64))
+
+
+def random_scenario(rs, wind_mag=0.0, hard=False):
+    """Initial state drawn from the default-task init ranges, as an injectable dict."""
+    d = np.radians
+    om = 60 if not hard else 600
+    st = {
+        "roll": rs.uniform(d(-110), d(110)), "pitch": rs.uniform(d(-45), d(45)), "yaw": rs.uniform(d(-30), d(30)),
+        "omega_p": rs.uniform(d(-om), d(om)), "omega_q": rs.uniform(d(-om), d(om)), "omega_r": rs.uniform(d(-om), d(om)),
+        "position_n": rs.uniform(-100, 100), "position_e": rs.uniform(-100, 100), "position_d": rs.uniform(-100, -20),
+        "velocity_u": rs.uniform(10, 23) if not hard else rs.uniform(40, 60),
+        "velocity_v": rs.uniform(-5, 5), "velocity_w": rs.uniform(-5, 5),
+        "elevon_right": (rs.uniform(d(-20), d(20)), rs.uniform(-1, 1)),
+        "elevon_left": (rs.uniform(d(-20), d(20)), rs.uniform(-1, 1)),
+        "throttle": (rs.uniform(0, 1), 0.0),
+    }
+    if wind_mag > 0:
+        w = rs.uniform(-wind_mag, wind_mag, 3)
+    else:
+        w = np.zeros(3)
+    st["wind"] = [float(w[0]), float(w[1]), float(w[2])]
+    tgt = {"roll": rs.uniform(d(-60), d(60)), "pitch": rs.uniform(d(-25), d(25)), "Va": rs.uniform(15, 28)}
+    return st, tgt
+
+
+def scenario_arrays(st, tgt):
+    s = [st[k] for k in STATE_KEYS]
+    s += [st["elevon_right"][0], st["elevon_left"][0], st["throttle"][0],
+          st["elevon_right"][1], st["elevon_left"][1], st["throttle"][1]]
+    s += list(st["wind"])
+    return np.array(s, dtype=np.float64), np.array([tgt[k] for k in TARGET_KEYS], dtype=np.float64)
+
+
+def run_episodes(env, n_ep, n_steps, rs, turbulence, wind_mag, action_amp, hard=False, noise_len=None,
+                 metrics=False, f32_actions=False):
+    """Roll `n_ep` injected episodes; every record has a leading [episode, step] shape."""
+    rec = {k: [] for k in ("init_state", "init_target", "actions", "y", "euler", "vab", "cmd", "target", "obs",
+                           "reward", "done", "nfev", "term", "obs0", "y0", "euler0", "vab0", "n_valid")}
+    if turbulence:
+        rec.update({"noise": [], "turb_lin": [], "turb_ang": []})
+    mrec = []
+    L = env.steps_max if noise_len is None else noise_len
+    for ep in range(n_ep):
+        st, tgt = random_scenario(rs, wind_mag, hard)
+        kw = {}
+        if turbulence:
+            noise = rs.standard_normal((4, L))
+            kw["turbulence_noise"] = noise
+        obs0 = env.reset(state=dict(st), target=dict(tgt), **kw)
+        s_arr, t_arr = scenario_arrays(st, tgt)
+        rec["init_state"].append(s_arr)
+        rec["init_target"].append(t_arr)
+        rec["obs0"].append(np.array(obs0, dtype=np.float64))
+        y0, e0, v0, _, _ = snapshot(env)
+        rec["y0"].append(y0), rec["euler0"].append(e0), rec["vab0"].append(v0)
+        if turbulence:
+            rec["noise"].append(noise)
+            rec["turb_lin"].append(np.array(env.simulator.wind.dryden.vel_lin))
+            rec["turb_ang"].append(np.array(env.simulator.wind.dryden.vel_ang))
+        ep_rec = {k: [] for k in ("actions", "y", "euler", "vab", "cmd", "target", "obs", "reward", "done", "nfev",
+                                  "term")}
+        n_valid = n_steps
+        for t in range(n_steps):
+            a = rs.uniform(-action_amp, action_amp, 3)
+            if f32_actions:
+                a = a.astype(np.float32)
+            env.simulator._nfev = 0
+            obs, rew, done, info = env.step(a)
+            y, e, v, c, tg = snapshot(env)
+            ep_rec["actions"].append(np.asarray(a, dtype=np.float64))
+            ep_rec["y"].append(y), ep_rec["euler"].append(e), ep_rec["vab"].append(v), ep_rec["cmd"].append(c)
+            ep_rec["target"].append(tg), ep_rec["obs"].append(np.array(obs, dtype=np.float64))
+            ep_rec["reward"].append(float(rew)), ep_rec["done"].append(bool(done))
+            ep_rec["nfev"].append(env.simulator._nfev)
+            ep_rec["term"].append(term_code(info.get("termination", "")))
+            if done:
+                n_valid = t + 1
+                if metrics:
+                    mrec.append({k: info[k] for k in ("rise_time", "settling_time", "overshoot", "total_error",
+                                                      "avg_error", "control_variation", "success",
+                                                      "success_time_frac", "end_error")})
+                break
+        rec["n_valid"].append(n_valid)
+        for k, v in ep_rec.items():
+            arr = np.array(v)
+            pad = [(0, n_steps - arr.shape[0])] + [(0, 0)] * (arr.ndim - 1)
+            rec[k].append(np.pad(arr, pad))
+    out = {k: np.array(v) for k, v in rec.items()}
+    if metrics:
+        out.update(pack_metrics(mrec))
+    return out
+
+
+def pack_metrics(mrec):
+    def f(x):
+        return np.nan if x is None else float(x)
+
+    out = {}
+    for name, keys in (("rise_time", TARGET_KEYS), ("settling_time", TARGET_KEYS + ["all"]),
+                       ("overshoot", TARGET_KEYS), ("total_error", TARGET_KEYS), ("avg_error", TARGET_KEYS),
+                       ("control_variation", ["all"]), ("success", TARGET_KEYS + ["all"]),
+                       ("success_time_frac", TARGET_KEYS + ["all"]), ("end_error", TARGET_KEYS)):
+        out["m_" + name] = np.array([[f(m[name][k]) for k in keys] for m in mrec], dtype=np.float64)
+    return out
+
+
+def gen_params():
+    import scipy.io
+    p = scipy.io.loadmat(refshim.X8_PARAMS, squeeze_me=True)
+    params = {k: float(v) for k, v in p.items() if not k.startswith("__") and np.size(v) == 1}
+    dst = os.path.join(ROOT, "tum_adlr_deep_reinforcement_learning_b200", "data", "x8_params.json")
+    with open(dst, "w") as f:
+        json.dump(params, f, indent=1, sort_keys=True)
+    print("wrote", dst, len(params), "scalars")
+
+
+def gen_traj():
+    rs = np.random.RandomState(1234)
+    env = make_env(False)
+    out = run_episodes(env, 6, 250, rs, False, wind_mag=0.0, action_amp=1.3)
+    np.savez_compressed(os.path.join(HERE, "traj_calm.npz"), **out)
+    rs = np.random.RandomState(99)
+    out = run_episodes(env, 4, 250, rs, False, wind_mag=6.0, action_amp=2.0)
+    np.savez_compressed(os.path.join(HERE, "traj_wind.npz"), **out)
+    rs = np.random.RandomState(5)
+    out = run_episodes(env, 3, 120, rs, False, wind_mag=3.0, action_amp=1.2, f32_actions=True)
+    np.savez_compressed(os.path.join(HERE, "traj_f32act.npz"), **out)
+
+
+def gen_turb():
+    rs = np.random.RandomState(4321)
+    env = make_env(True)
+    out = run_episodes(env, 5, 250, rs, True, wind_mag=6.0, action_amp=1.3)
+    np.savez_compressed(os.path.join(HERE, "traj_turb.npz"), **out)
+    env = make_env(True, intensity="severe")
+    rs = np.random.RandomState(777)
+    out = run_episodes(env, 2, 200, rs, True, wind_mag=4.0, action_amp=1.0)
+    np.savez_compressed(os.path.join(HERE, "traj_turb_severe.npz"), **out)
+
+
+def gen_fail():
+    """Episodes started near/over the constraint envelope so that ConstraintException paths fire."""
+    rs = np.random.RandomState(31337)
+    env = make_env(False)
+    out = run_episodes(env, 24, 150, rs, False, wind_mag=5.0, action_amp=3.0, hard=True, metrics=True)
+    print("fail terms:", out["term"].max(axis=1), "n_valid", out["n_valid"])
+    np.savez_compressed(os.path.join(HERE, "traj_fail.npz"), **out)
+
+
+def gen_full():
+    """Whole episodes to the step limit (done by 'steps') with the 9 end-of-episode metrics."""
+    rs = np.random.RandomState(2024)
+    env = make_env(False, config_kw={"steps_max": 400})
+    out = run_episodes(env, 4, 400, rs, False, wind_mag=3.0, action_amp=1.0, metrics=True)
+    np.savez_compressed(os.path.join(HERE, "traj_full400.npz"), **out)
+    env = make_env(True, config_kw={"steps_max": 300})
+    rs = np.random.RandomState(2025)
+    out = run_episodes(env, 3, 300, rs, True, wind_mag=3.0, action_amp=0.6, metrics=True, noise_len=300)
+    np.savez_compressed(os.path.join(HERE, "traj_full300_turb.npz"), **out)
+
+
+def gen_pid(max_scen=100, num_envs=6):
+    """Lock-step emulation of examples/evaluate_controller.py:57-232 (use_pid=True) with `num_envs` env slots.
+
+    The reference's golden file was produced with 6 parallel envs (the metric completion order in the file is only reproduced by 6 slots; scenarios 0-5 start with `info is None`,
+    every later scenario's FIRST action is computed with the PID reference still set to the final target of the
+    episode that previously ran in the same slot, evaluate_controller.py:203-208).  We record that stale
+    reference per scenario (`first_ref`) so each scenario can be replayed on its own.
+    """
+    scenarios = list(np.load(refshim.PID_TEST_SET, allow_pickle=True))[:max_scen]
+    golden = np.load(refshim.PID_GOLDEN, allow_pickle=True).item()
+    config_kw = {"steps_max": 1500,
+                 "target": {"on_success": "done", "success_streak_fraction": 1, "success_streak_req": 100,
+                            "states": {0: {"bound": 5}, 1: {"bound": 5}, 2: {"bound": 2}}},
+                 "action": {"scale_space": False}}
+    envs = [make_env(False, config_kw=config_kw) for _ in range(num_envs)]
+    pids = [PIDController(envs[0].simulator.dt) for _ in range(num_envs)]
+    obs_states = [v["name"] for v in envs[0].cfg["observation"]["states"]]
+    i_phi, i_th, i_va = obs_states.index("roll"), obs_states.index("pitch"), obs_states.index("Va")
+    i_om = [obs_states.index(k) for k in ("omega_p", "omega_q", "omega_r")]
+    S = len(scenarios)
+    skeys = STATE_KEYS + ["Va", "alpha", "beta", "elevator", "aileron", "throttle", "wind_n", "wind_e", "wind_d"]
+    init_state = np.array([[float(sc["state"][k]) for k in skeys] for sc in scenarios])
+    init_target = np.array([[float(sc["target"][k]) for k in TARGET_KEYS] for sc in scenarios])
+    first_ref = np.full((S, 3), np.nan)
+    live_rewards = np.zeros((S, 1500))
+    live_len = np.zeros(S, dtype=np.int64)
+    live_final_y = np.zeros((S, 19))
+    live_metrics = [None] * S
+    gold_len = np.array([len(golden["rewards"][i]) for i in range(S)], dtype=np.int64)
+    gold_rewards = np.zeros((S, int(gold_len.max())))
+    for i in range(S):
+        gold_rewards[i, :gold_len[i]] = golden["rewards"][i]
+
+    queue = list(range(S))
+    slot_scen = [-1] * num_envs
+    slot_t = [0] * num_envs
+    active = [False] * num_envs
+    done = [True] * num_envs
+    obs = [None] * num_envs
+    info = None
+    t0 = time.time()
+    while True:
+        for i in range(num_envs):
+            if done[i]:
+                if queue:
+                    si = queue.pop(0)
+                    slot_scen[i], slot_t[i], active[i] = si, 0, True
+                    sc = scenarios[si]
+                    obs[i] = envs[i].reset(state=dict(sc["state"]), target=dict(sc["target"]))
+                    pids[i].reset()
+                    pids[i].set_reference(sc["target"]["roll"], sc["target"]["pitch"], sc["target"]["Va"])
+                    if info is not None and info[i] is not None:
+                        first_ref[si] = [info[i]["target"][k] for k in TARGET_KEYS]
+                else:
+                    active[i] = False
+                done[i] = False
+        if not queue and not any(active):
+            break
+        new_info = [None] * num_envs
+        for i in range(num_envs):
+            if not active[i]:
+                continue
+            if info is not None and info[i] is not None:
+                pids[i].set_reference(phi=info[i]["target"]["roll"], theta=info[i]["target"]["pitch"],
+                                      va=info[i]["target"]["Va"])
+            a = pids[i].get_action(obs[i][i_phi], obs[i][i_th], obs[i][i_va], obs[i][i_om])
+            o, rew, d, inf = envs[i].step(a)
+            si = slot_scen[i]
+            live_rewards[si, slot_t[i]] = rew
+            slot_t[i] += 1
+            obs[i] = o
+            inf = dict(inf)
+            inf["target"] = dict(inf["target"])   # SubprocVecEnv pickles info through the pipe: a snapshot
+            new_info[i] = inf
+            if d:
+                done[i] = True
+                live_len[si] = slot_t[i]
+                live_final_y[si] = snapshot(envs[i])[0]
+                live_metrics[si] = {k: inf[k] for k in ("rise_time", "settling_time", "overshoot", "total_error",
+                                                        "avg_error", "control_variation", "success",
+                                                        "success_time_frac", "end_error")}
+                n = min(live_len[si], gold_len[si])
+                print("scenario %3d len live %4d golden %4d  max|dr| %.2e  (%.0fs)" % (
+                    si, live_len[si], gold_len[si],
+                    np.abs(live_rewards[si, :n] - gold_rewards[si, :n]).max(), time.time() - t0), flush=True)
+        # envs that are inactive keep their last info (the harness keeps stepping them; irrelevant here)
+        info = [new_info[i] if new_info[i] is not None else (info[i] if info is not None else None)
+                for i in range(num_envs)]
+    out = dict(init_state=init_state, init_target=init_target, first_ref=first_ref, live_rewards=live_rewards,
+               live_len=live_len, live_final_y=live_final_y, gold_rewards=gold_rewards, gold_len=gold_len)
+    out.update(pack_metrics(live_metrics))
+    for name in ("success", "rise_time", "overshoot", "settling_time", "control_variation"):
+        keys = list(golden[name].keys())
+        out["gold_" + name] = np.array([[np.nan if v is None else float(v) for v in golden[name][k]] for k in keys],
+                                       dtype=np.float64).T
+        out["gold_" + name + "_keys"] = np.array(keys)
+    np.savez_compressed(os.path.join(HERE, "pid_none.npz"), **out)
+
+
+def gen_gae():
+    """Reference RolloutBuffer GAE on seeded data (buffers.py:304-333), incl. the mixed f32/f64 quirk."""
+    import torch
+    from stable_baselines3.common.buffers import RolloutBuffer
+    out = {}
+    for tag, (T, N, p_done) in {"a": (64, 16, 0.05), "b": (256, 8, 0.01), "c": (5, 3, 0.3)}.items():
+        rs = np.random.RandomState(T * 1000 + N)
+        obs_space = refshim.Box(-np.ones(14), np.ones(14), dtype=np.float32)
+        act_space = refshim.Box(-np.ones(3), np.ones(3), dtype=np.float32)
+        buf = RolloutBuffer(T, obs_space, act_space, device="cpu", gae_lambda=0.95, gamma=0.99, n_envs=N)
+        rew = rs.standard_normal((T, N)).astype(np.float32)
+        val = rs.standard_normal((T, N)).astype(np.float32)
+        dones = (rs.uniform(size=(T, N)) < p_done)
+        last_val = rs.standard_normal(N).astype(np.float32)
+        last_done = (rs.uniform(size=N) < 0.2)
+        for t in range(T):
+            buf.add(np.zeros((N, 14), np.float32), np.zeros((N, 3), np.float32), rew[t], dones[t].astype(np.float32),
+                    torch.as_tensor(val[t]), torch.zeros(N))
+        buf.compute_returns_and_advantage(torch.as_tensor(last_val), dones=last_done)
+        out.update({tag + "_rew": rew, tag + "_val": val, tag + "_done": dones.astype(np.float32),
+                    tag + "_last_val": last_val, tag + "_last_done": last_done,
+                    tag + "_adv": buf.advantages.copy(), tag + "_ret": buf.returns.copy()})
+    np.savez_compressed(os.path.join(HERE, "gae.npz"), **out)
+
+
+def gen_dryden():
+    """Reference Dryden output for injected noise, for the gym parameterisation (dt<-2000, b<-0.01, h<-2.1;
+    pyfly.py:781-783 vs dryden.py:52) and for raw pyfly (sim_length 300), all three intensities."""
+    from pyfly.pyfly import Wind
+    out = {}
+    for L in (2000, 300):
+        for inten in ("light", "moderate", "severe"):
+            w = Wind(turbulence=True, mag_min=-8, mag_max=8, b=2.1, turbulence_intensity=inten, sim_length=L, dt=0.01)
+            rs = np.random.RandomState(L + len(inten))
+            noise = rs.standard_normal((4, L))
+            w.reset([0.0, 0.0, 0.0], noise)
+            w.get_turbulence_linear(0)
+            tag = "L%d_%s" % (L, inten)
+            out[tag + "_noise"] = noise
+            out[tag + "_lin"] = np.array(w.dryden.vel_lin)
+            out[tag + "_ang"] = np.array(w.dryden.vel_ang)
+    np.savez_compressed(os.path.join(HERE, "dryden.npz"), **out)
+
+
+if __name__ == "__main__":
+    what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    jobs = {"params": gen_params, "traj": gen_traj, "turb": gen_turb, "fail": gen_fail, "full": gen_full,
+            "pid": gen_pid, "gae": gen_gae, "dryden": gen_dryden}
+    for name, fn in jobs.items():
+        if what in (name, "all"):
+            t0 = time.time()
+            fn()
+            print("[%s] done in %.1fs" % (name, time.time() - t0), flush=True)

@@ -1,0 +1,459 @@
+"""Host-side configuration: reference-format JSON / dict configs -> the POD `FwConfig` of include/fwb200.h.
+
+Mirrors what the reference does at construction time:
+  * PyFly.__init__ (magpie/libs/pyfly/pyfly/pyfly.py:1054-1249): aircraft parameters, pyfly_config.json,
+    recursive `config_kw` overrides (:1067-1073, :1125-1126), Actuation.finalize limits (:584-623);
+  * FixedWingAircraft.__init__ / set_curriculum_level (magpie/libs/fixed-wing-gym/gym_fixed_wing/fixed_wing.py:14-306,
+    :334-412): the gym JSON, `config_kw` / `sim_config_kw` overrides (:34-62), simulator-state overrides and the
+    curriculum scaling of init ranges and target ranges;
+  * Wind.__init__ -> DrydenGustModel.__init__ (pyfly.py:780-783, dryden.py:52-143) including the reference's
+    mis-ordered constructor arguments, and scipy.signal.lsim's discretisation.
+The numbers of the default configs below are those of pyfly_config.json / fixed_wing_config.json.
+"""
+import copy
+import ctypes
+import json
+import math
+import os
+
+import numpy as np
+
+_DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
+
+FW_ABI_VERSION = 1
+FW_NY, FW_NOBS, FW_NACT, FW_NSTATE_INJECT, FW_NMETRIC = 19, 14, 3, 21, 28
+FW_F64, FW_F32 = 0, 1
+FW_INT_RK45_SCIPY, FW_INT_RK4_FIXED = 0, 1
+TERM_NAMES = {0: None, 1: "steps", 2: "success", 10: "omega_p", 11: "omega_q", 12: "omega_r", 13: "Va"}
+TARGET_STATES = ("roll", "pitch", "Va")
+GOAL_STATES = ("roll", "pitch", "Va", "all")
+INIT_STATES = ("roll", "pitch", "yaw", "omega_p", "omega_q", "omega_r", "position_n", "position_e", "position_d",
+               "velocity_u", "velocity_v", "velocity_w")
+METRIC_LAYOUT = (("rise_time", 0, TARGET_STATES), ("settling_time", 3, GOAL_STATES), ("overshoot", 7, TARGET_STATES),
+                 ("total_error", 10, TARGET_STATES), ("avg_error", 13, TARGET_STATES),
+                 ("control_variation", 16, ("all",)), ("success", 17, GOAL_STATES),
+                 ("success_time_frac", 21, GOAL_STATES), ("end_error", 25, TARGET_STATES))
+
+
+class FwFilter(ctypes.Structure):
+    _fields_ = [("order", ctypes.c_int32), ("noise_row", ctypes.c_int32), ("Ad", ctypes.c_double * 9),
+                ("Bd0", ctypes.c_double * 3), ("Bd1", ctypes.c_double * 3), ("C", ctypes.c_double * 3),
+                ("D", ctypes.c_double)]
+
+
+_AERO = ("mass Jx Jy Jz Jxz S_wing b c S_prop C_prop k_motor k_T_P k_Omega e_oswald M a_0 "
+         "C_L_0 C_L_alpha C_L_q C_L_delta_e C_D_p C_D_q C_D_beta1 C_D_beta2 C_D_delta_e "
+         "C_m_0 C_m_alpha C_m_q C_m_delta_e C_m_fp C_Y_0 C_Y_beta C_Y_p C_Y_r C_Y_delta_a C_Y_delta_r "
+         "C_l_0 C_l_beta C_l_p C_l_r C_l_delta_a C_l_delta_r C_n_0 C_n_beta C_n_p C_n_r C_n_delta_a C_n_delta_r").split()
+
+_d, _i = ctypes.c_double, ctypes.c_int32
+
+
+class FwConfig(ctypes.Structure):
+    """ctypes mirror of `struct FwConfig` (include/fwb200.h) — field order and types must match exactly;
+    tests/test_capi.py compares sizeof with the value both shared libraries report."""
+    _fields_ = (
+        [("abi_version", _i), ("precision", _i), ("integrator", _i), ("rk4_substeps", _i), ("rtol", _d), ("atol", _d)]
+        + [(n, _d) for n in _AERO]
+        + [("dt", _d), ("rho", _d), ("g", _d),
+           ("elevon_min", _d), ("elevon_max", _d), ("elevon_dot_max", _d), ("elevon_omega0", _d), ("elevon_zeta", _d),
+           ("throttle_min", _d), ("throttle_max", _d), ("throttle_tau", _d),
+           ("omega_con_min", _d * 3), ("omega_con_max", _d * 3), ("va_value_min", _d), ("va_con_max", _d),
+           ("init_lo", _d * 12), ("init_hi", _d * 12), ("wind_mag_min", _d), ("wind_mag_max", _d),
+           ("turbulence", _i), ("_pad0", _i), ("turb_noise_scale", _d), ("filt", FwFilter * 6),
+           ("steps_max", _i), ("scale_actions", _i), ("scale_low", _d), ("scale_high", _d),
+           ("act_lo", _d * 3), ("act_hi", _d * 3), ("has_action_bounds", _i), ("_pad1", _i),
+           ("action_bounds_min", _d * 3), ("action_bounds_max", _d * 3),
+           ("tgt_low", _d * 3), ("tgt_high", _d * 3), ("tgt_delta", _d * 3), ("tgt_bound", _d * 3),
+           ("tgt_class", _i * 3), ("on_success", _i), ("streak_req", _i), ("resample_every", _i),
+           ("streak_fraction", _d),
+           ("rew_err_scaling", _d * 3), ("rew_err_max", _d * 3), ("rew_delta_scaling", _d), ("rew_delta_max", _d),
+           ("rew_bound_scaling", _d), ("rew_bound_max", _d), ("rew_delta_window", _i), ("obs_act_window", _i),
+           ("step_fail_timesteps", _i), ("_pad2", _i), ("step_fail_value", _d), ("rise_low", _d), ("rise_high", _d),
+           ("seed", ctypes.c_uint64), ("env_id_offset", ctypes.c_int64)])
+
+
+def _var(name, **kw):
+    kw["name"] = name
+    return kw
+
+
+def default_sim_config():
+    """The reference's pyfly_config.json, restated (plots omitted: rendering is out of scope)."""
+    elevon = dict(value_min=-30, value_max=35, init_min=0, init_max=0, convert_to_radians=True, order=2,
+                  dot_max=3.4907, omega_0=100, zeta=1.71)
+    ang = dict(convert_to_radians=True, init_min=-30, init_max=30)
+    rate = dict(convert_to_radians=True, init_min=-40, init_max=40, constraint_min=-180, constraint_max=180)
+    return {
+        "dt": 0.01, "rho": 1.225, "g": 9.81, "wind_magnitude_min": -8, "wind_magnitude_max": 8,
+        "turbulence": True, "turbulence_intensity": "light", "turbulence_sim_length": 300,
+        "actuation": {"dynamics": ["elevon_right", "elevon_left", "throttle"],
+                      "inputs": ["elevator", "aileron", "throttle"]},
+        "variables": [
+            _var("roll", wrap=True, **ang), _var("pitch", **ang), _var("yaw", wrap=True, **ang),
+            _var("omega_p", **rate), _var("omega_q", **rate), _var("omega_r", **rate),
+            _var("position_n", init_min=-100, init_max=100), _var("position_e", init_min=-100, init_max=100),
+            _var("position_d", init_min=-20, init_max=-100),
+            _var("velocity_u", init_min=13, init_max=22), _var("velocity_v", init_min=-5, init_max=5),
+            _var("velocity_w", init_min=-5, init_max=5),
+            _var("alpha"), _var("beta", convert_to_radians=True), _var("Va", value_min=1e-6),
+            _var("elevon_left", **elevon), _var("elevon_right", **elevon),
+            _var("throttle", value_min=0, value_max=1, init_min=0, init_max=0, order=1, tau=0.2),
+        ],
+    }
+
+
+def default_env_config():
+    """The reference's fixed_wing_config.json, restated (render block omitted)."""
+    def st(name, lo=None, hi=None, rad=False, **kw):
+        d = {"name": name, "type": "state"}
+        if lo is not None:
+            d.update(low=lo, high=hi)
+        if rad:
+            d["convert_to_radians"] = True
+        d.update(kw)
+        return d
+
+    rate = dict(init_min=-60, init_max=60, constraint_min=-720, constraint_max=720, convert_to_radians=True)
+    return {
+        "steps_max": 2000, "integration_window": 0,
+        "observation": {
+            "length": 1, "step": 1, "shape": "vector", "normalize": False, "noise": {"mean": 0, "var": 0},
+            "states": [st("roll", -180, 180, True), st("pitch", -85, 85, True), st("Va", 0, 70),
+                       st("omega_p", -720, 720, True), st("omega_q", -720, 720, True), st("omega_r", -720, 720, True),
+                       {"name": "roll", "type": "target", "value": "absolute"},
+                       {"name": "pitch", "type": "target", "value": "absolute"},
+                       {"name": "Va", "type": "target", "value": "absolute"},
+                       st("alpha"), st("beta"),
+                       {"name": "elevator", "type": "action", "window_size": 5},
+                       {"name": "aileron", "type": "action", "window_size": 5},
+                       {"name": "throttle", "type": "action", "window_size": 5}]},
+        "action": {"scale_space": True, "scale_low": -1, "scale_high": 1, "bounds_multiplier": 1.5,
+                   "states": [{"name": n, "low": "max", "high": "max"} for n in ("elevator", "aileron", "throttle")]},
+        "target": {
+            "resample_every": 0, "success_streak_req": 100, "success_streak_fraction": 0.95, "on_success": "none",
+            "states": [
+                {"name": "roll", "convert_to_radians": True, "low": -60, "high": 60, "delta": 180,
+                 "class": "constant", "bound": 5},
+                {"name": "pitch", "convert_to_radians": True, "low": -25, "high": 25, "delta": 45,
+                 "class": "constant", "bound": 5},
+                {"name": "Va", "low": 15, "high": 28, "delta": 6, "class": "compensate", "bound": 2}]},
+        "reward": {
+            "form": "absolute", "randomize_scaling": False, "step_fail": "timesteps",
+            "terms": [{"function_class": "linear", "weight": 1}],
+            "factors": [
+                {"name": "roll", "class": "state", "type": "error", "function_class": "linear", "scaling": 3.2,
+                 "shaping": True, "max": 0.3, "sign": -1},
+                {"name": "pitch", "class": "state", "type": "error", "function_class": "linear", "scaling": 3.2,
+                 "shaping": True, "max": 0.3, "sign": -1},
+                {"name": "Va", "class": "state", "type": "error", "function_class": "linear", "scaling": 25,
+                 "shaping": True, "max": 0.3, "sign": -1},
+                {"name": "action", "class": "action", "type": "delta", "function_class": "linear", "window_size": 5,
+                 "scaling": 60, "shaping": False, "sign": -1},
+                {"name": "action_bound", "class": "action", "type": "bound", "function_class": "linear",
+                 "scaling": 1, "shaping": False, "sign": -1}]},
+        "simulator": {"states": [
+            {"name": "roll", "init_min": -110, "init_max": 110, "convert_to_radians": True},
+            {"name": "pitch", "init_min": -45, "init_max": 45, "convert_to_radians": True},
+            {"name": "velocity_u", "init_min": 10, "init_max": 23},
+            {"name": "velocity_v", "init_min": -5, "init_max": 5},
+            {"name": "velocity_w", "init_min": -5, "init_max": 5},
+            {"name": "Va", "constraint_max": 70},
+            dict(name="omega_p", **rate), dict(name="omega_q", **rate), dict(name="omega_r", **rate)]},
+        "metrics": [{"name": "rise_time", "high": 0.9, "low": 0.1}, {"name": "settling_time"}, {"name": "overshoot"},
+                    {"name": "total_error"}, {"name": "avg_error"}, {"name": "control_variation"},
+                    {"name": "success"}, {"name": "success_time_frac"}, {"name": "end_error"}],
+    }
+
+
+def load_aircraft_parameters(path=None):
+    """x8_param.mat scalars (pyfly.py:1076-1078); shipped as JSON printed to 17 digits by tests/golden/make_golden.py.
+    A `.mat` path is read with scipy.io like the reference does."""
+    if path is None:
+        path = os.path.join(_DATA, "x8_params.json")
+    if path.endswith(".mat"):
+        import scipy.io
+        raw = scipy.io.loadmat(path, squeeze_me=True)
+        return {k: float(v) for k, v in raw.items() if not k.startswith("__") and np.size(v) == 1}
+    with open(path) as f:
+        return json.load(f)
+
+
+def apply_overrides(parent, kws):
+    """Recursive override, same semantics as fixed_wing.py:34-40 (dict keys, or int keys into lists)."""
+    for attr, val in kws.items():
+        if isinstance(val, dict):
+            apply_overrides(parent[attr], val)
+        else:
+            parent[attr] = val
+
+
+def _tf2ss(num, den):
+    """Controller-canonical realisation as produced by scipy.signal.tf2ss for a strictly proper SISO system."""
+    num = np.atleast_1d(np.asarray(num, dtype=np.float64))
+    den = np.atleast_1d(np.asarray(den, dtype=np.float64))
+    num = num / den[0]
+    den = den / den[0]
+    n = len(den) - 1
+    num = np.concatenate([np.zeros(n + 1 - len(num)), num])
+    A = np.zeros((n, n))
+    A[0, :] = -den[1:]
+    if n > 1:
+        A[1:, :-1] = np.eye(n - 1)
+    B = np.zeros((n, 1))
+    B[0, 0] = 1.0
+    D = num[0]
+    C = (num[1:] - num[0] * den[1:]).reshape(1, n)
+    return A, B, C, D
+
+
+def dryden_filters(sim_length, sim_dt, wingspan, intensity="light", spec=False):
+    """Discretised Dryden shaping filters in scipy.signal.lsim's linear-interpolation form.
+
+    Reference parameterisation (default): `Wind` calls DrydenGustModel(sim_length, dt, b, intensity=...)
+    (pyfly.py:781-783) against the signature (dt, b, h=100, V_a=25, intensity) (dryden.py:52), hence inside the
+    model dt = sim_length, b = sim dt, h = wingspan.  `spec=True` gives the intended MIL-F-8785C parameters
+    (dt = sim dt, b = wingspan, h = 100 m) — a labelled deviation from the reference, never used for parity.
+    Returns (filters [(order, noise_row, Ad, Bd0, Bd1, C, D)], noise_scale).
+    """
+    from scipy.linalg import expm
+    if spec:
+        dt_d, b, h = sim_dt, wingspan, 100.0
+    else:
+        dt_d, b, h = float(sim_length), sim_dt, wingspan
+    V_a = 25.0
+    meters2feet = 3.281
+    feet2meters = 1 / meters2feet
+    knots2mpers = 0.5144
+    W_20 = {"light": 15, "moderate": 30, "severe": 45, None: 15}[intensity] * knots2mpers
+    h, b, V_a, W_20 = h * meters2feet, b * meters2feet, V_a * meters2feet, W_20 * meters2feet
+    sigma_w = 0.1 * W_20
+    sigma_u = sigma_w / (0.177 + 0.000823 * h) ** 0.4
+    sigma_v = sigma_u
+    L_u = h / (0.177 + 0.000823 * h) ** 1.2
+    L_v, L_w = L_u, h
+    K_u = sigma_u * math.sqrt((2 * L_u) / (math.pi * V_a))
+    K_v = sigma_v * math.sqrt(L_v / (math.pi * V_a))
+    K_w = sigma_w * math.sqrt(L_w / (math.pi * V_a))
+    T_u = L_u / V_a
+    T_v1, T_v2 = math.sqrt(3.0) * L_v / V_a, L_v / V_a
+    T_w1, T_w2 = math.sqrt(3.0) * L_w / V_a, L_w / V_a
+    K_p = sigma_w * math.sqrt(0.8 / V_a) * ((math.pi / (4 * b)) ** (1 / 6)) / (L_w ** (1 / 3))
+    K_q = K_r = 1 / V_a
+    T_p = 4 * b / (math.pi * V_a)
+    T_q, T_r = T_p, 3 * b / (math.pi * V_a)
+    tfs = [([feet2meters * K_u], [T_u, 1], 0),
+           ([feet2meters * K_v * T_v1, feet2meters * K_v], [T_v2 ** 2, 2 * T_v2, 1], 1),
+           ([feet2meters * K_w * T_w1, feet2meters * K_w], [T_w2 ** 2, 2 * T_w2, 1], 2),
+           ([K_p], [T_p, 1], 3),
+           ([-K_w * K_q * T_w1, -K_w * K_q, 0], [T_q * T_w2 ** 2, T_w2 ** 2 + 2 * T_q * T_w2, T_q + 2 * T_w2, 1], 1),
+           ([K_v * K_r * T_v1, K_v * K_r, 0], [T_r * T_v2 ** 2, T_v2 ** 2 + 2 * T_r * T_v2, T_r + 2 * T_v2, 1], 2)]
+    # lsim time grid: np.linspace(0, L*dt_d, L) (dryden.py:205) -> step L*dt_d/(L-1)
+    step = sim_length * dt_d / (sim_length - 1)
+    out = []
+    for num, den, row in tfs:
+        A, B, C, D = _tf2ss(num, den)
+        n = A.shape[0]
+        M = np.zeros((n + 2, n + 2))
+        M[:n, :n] = A * step
+        M[:n, n:n + 1] = B * step
+        M[n, n + 1] = 1.0
+        eM = expm(M.T)
+        Ad = eM[:n, :n]
+        Bd1 = eM[n + 1:, :n]
+        Bd0 = eM[n:n + 1, :n] - Bd1
+        out.append((n, row, Ad, Bd0.ravel(), Bd1.ravel(), C.ravel(), float(D)))
+    return out, math.sqrt(math.pi / dt_d)
+
+
+def build_config(env_cfg=None, sim_cfg=None, config_kw=None, sim_config_kw=None, params=None,
+                 curriculum_level=1.0, precision="f64", integrator="rk45", rk4_substeps=4, rtol=1e-3, atol=1e-6,
+                 seed=0, env_id_offset=0, dryden_spec=False):
+    """Flatten reference-format configs into an `FwConfig`.  `env_cfg` / `sim_cfg`: dict or JSON path (defaults above)."""
+    def load(x, default):
+        if x is None:
+            return default()
+        if isinstance(x, str):
+            with open(x) as f:
+                return json.load(f)
+        return copy.deepcopy(x)
+
+    env = load(env_cfg, default_env_config)
+    sim = load(sim_cfg, default_sim_config)
+    if config_kw:
+        apply_overrides(env, copy.deepcopy(config_kw))
+    sim_kw = copy.deepcopy(sim_config_kw) if sim_config_kw else {}
+    sim_kw["turbulence_sim_length"] = env["steps_max"]        # fixed_wing.py:62
+    apply_overrides(sim, sim_kw)
+    P = load_aircraft_parameters() if params is None else dict(params)
+
+    c = FwConfig()
+    c.abi_version = FW_ABI_VERSION
+    c.precision = {"f64": FW_F64, "f32": FW_F32}[precision]
+    c.integrator = {"rk45": FW_INT_RK45_SCIPY, "rk4": FW_INT_RK4_FIXED}[integrator]
+    c.rk4_substeps, c.rtol, c.atol = int(rk4_substeps), float(rtol), float(atol)
+    for name in _AERO:
+        setattr(c, name, float(P["e" if name == "e_oswald" else name]))
+    c.dt, c.rho, c.g = float(sim["dt"]), float(sim["rho"]), float(sim["g"])
+
+    # ---- simulator variables (Variable.__init__ radians conversion pyfly.py:61-64) ----
+    var = {}
+    for v in sim["variables"]:
+        v = dict(v)
+        if v.get("convert_to_radians"):
+            for k in ("value_min", "value_max", "init_min", "init_max", "constraint_min", "constraint_max"):
+                if v.get(k) is not None:
+                    v[k] = float(np.radians(v[k]))
+        var[v["name"]] = v
+    # gym "simulator.states" overrides with curriculum scaling (fixed_wing.py:343-362)
+    for s in env.get("simulator", {}).get("states", []):
+        s = dict(s)
+        name = s.pop("name")
+        rad = s.pop("convert_to_radians", False)
+        for prop, val in s.items():
+            if val is not None:
+                if "constraint" not in prop and any(m in prop for m in ("min", "max")):
+                    mid = (s[prop[:-3] + "max"] + s[prop[:-3] + "min"]) / 2
+                    val = mid - curriculum_level * (mid - val)
+                if rad:
+                    val = float(np.radians(val))
+            var[name][prop] = val
+    el = var["elevon_right"]
+    c.elevon_min, c.elevon_max = el["value_min"], el["value_max"]
+    c.elevon_dot_max = el["dot_max"]            # not degree-converted in the reference
+    c.elevon_omega0, c.elevon_zeta = el["omega_0"], el["zeta"]
+    th = var["throttle"]
+    c.throttle_min, c.throttle_max, c.throttle_tau = th["value_min"], th["value_max"], th["tau"]
+    for i, n in enumerate(("omega_p", "omega_q", "omega_r")):
+        c.omega_con_min[i] = var[n].get("constraint_min") if var[n].get("constraint_min") is not None else -np.inf
+        c.omega_con_max[i] = var[n].get("constraint_max") if var[n].get("constraint_max") is not None else np.inf
+    c.va_value_min = var["Va"].get("value_min") or 0.0
+    c.va_con_max = var["Va"].get("constraint_max") or 0.0
+    for i, n in enumerate(INIT_STATES):
+        c.init_lo[i], c.init_hi[i] = var[n]["init_min"], var[n]["init_max"]
+    c.wind_mag_min, c.wind_mag_max = sim["wind_magnitude_min"], sim["wind_magnitude_max"]
+    c.turbulence = int(bool(sim["turbulence"]))
+    intensity = sim.get("turbulence_intensity")
+    if intensity in ("None", "none"):
+        intensity = None
+    L = int(sim["turbulence_sim_length"])
+    filters, scale = dryden_filters(L, c.dt, c.b, intensity, spec=dryden_spec)
+    c.turb_noise_scale = scale
+    for fi, (n, row, Ad, Bd0, Bd1, C, D) in enumerate(filters):
+        f = c.filt[fi]
+        f.order, f.noise_row, f.D = n, row, D
+        for a in range(n):
+            f.Bd0[a], f.Bd1[a], f.C[a] = Bd0[a], Bd1[a], C[a]
+            for b_ in range(n):
+                f.Ad[a * n + b_] = Ad[a, b_]
+
+    # ---- gym env ----
+    c.steps_max = int(env["steps_max"])
+    act = env["action"]
+    c.scale_actions = int(bool(act.get("scale_space", False)))
+    c.scale_low, c.scale_high = float(act.get("scale_low", -1)), float(act.get("scale_high", 1))
+    # Actuation.finalize (pyfly.py:599-623): elevator/aileron limits from the elevon limits
+    lo = [(c.elevon_min + c.elevon_min) / 2, (-c.elevon_max + c.elevon_min) / 2, c.throttle_min]
+    hi = [(c.elevon_max + c.elevon_max) / 2, (-c.elevon_min + c.elevon_max) / 2, c.throttle_max]
+    for j in range(3):
+        c.act_lo[j], c.act_hi[j] = lo[j], hi[j]
+    mult = act.get("bounds_multiplier")
+    c.has_action_bounds = int(mult is not None)
+    for j in range(3):
+        c.action_bounds_max[j] = act.get("scale_high", 1) * (mult or 0)
+        c.action_bounds_min[j] = act.get("scale_low", -1) * (mult or 0)
+    tgt = env["target"]
+    tstates = {s["name"]: s for s in tgt["states"]}
+    for k, name in enumerate(TARGET_STATES):
+        s = tstates[name]
+        rad = s.get("convert_to_radians", False)
+
+        def cur(key, v):       # set_curriculum_level target scaling (fixed_wing.py:371-387)
+            if key == "low":
+                mid = (s["high"] + v) / 2
+            elif key == "high":
+                mid = (v + s["low"]) / 2
+            else:
+                mid = 0
+            return mid - curriculum_level * (mid - v)
+
+        low, high = cur("low", s["low"]), cur("high", s["high"])
+        delta = s.get("delta")
+        delta = cur("delta", delta) if delta is not None else None
+        bound = s.get("bound")
+        if rad:
+            low, high = float(np.radians(low)), float(np.radians(high))
+            delta = float(np.radians(delta)) if delta is not None else None
+            bound = float(np.radians(bound)) if bound is not None else None
+        c.tgt_low[k], c.tgt_high[k] = low, high
+        c.tgt_delta[k] = np.nan if delta is None else delta
+        c.tgt_bound[k] = np.inf if bound is None else bound
+        cls = s.get("class", "constant")
+        if cls not in ("constant", "compensate"):
+            raise NotImplementedError("target class %r (SURVEY §8f 'next' row 1)" % cls)
+        c.tgt_class[k] = 1 if cls == "compensate" else 0
+    c.on_success = {"none": 0, "done": 1, "new": 2}[tgt.get("on_success", "none")]
+    c.streak_req = int(tgt["success_streak_req"])
+    if c.streak_req > 128:
+        raise NotImplementedError("success_streak_req > 128")
+    c.streak_fraction = float(tgt["success_streak_fraction"])
+    c.resample_every = int(tgt.get("resample_every", 0) or 0)
+    rew = env["reward"]
+    if rew.get("form", "absolute") != "absolute" or len(rew["terms"]) != 1 or rew["terms"][0]["weight"] != 1 \
+            or rew["terms"][0]["function_class"] != "linear":
+        raise NotImplementedError("reward form/terms other than one absolute linear term (SURVEY §8f row 1)")
+    for k in range(3):
+        c.rew_err_scaling[k], c.rew_err_max[k] = 0.0, np.inf
+    c.rew_delta_scaling = c.rew_bound_scaling = 0.0
+    c.rew_delta_max = c.rew_bound_max = np.inf
+    c.rew_delta_window = 5
+    for f in rew["factors"]:
+        if f["function_class"] != "linear" or f.get("sign", -1) >= 0:
+            raise NotImplementedError("reward factor %r" % (f,))
+        mx = f.get("max")
+        mx = np.inf if mx is None else float(mx)
+        if f["class"] == "state" and f["type"] == "error":
+            k = TARGET_STATES.index(f["name"])
+            c.rew_err_scaling[k], c.rew_err_max[k] = float(f["scaling"]), mx
+        elif f["class"] == "action" and f["type"] == "delta":
+            c.rew_delta_scaling, c.rew_delta_max, c.rew_delta_window = float(f["scaling"]), mx, int(f["window_size"])
+        elif f["class"] == "action" and f["type"] == "bound":
+            c.rew_bound_scaling, c.rew_bound_max = float(f["scaling"]), mx
+        else:
+            raise NotImplementedError("reward factor %r" % (f,))
+    fail = rew.get("step_fail", 0)
+    c.step_fail_timesteps = int(fail == "timesteps")
+    c.step_fail_value = 0.0 if fail == "timesteps" else float(fail)
+    obs = env["observation"]
+    if obs.get("length", 1) != 1 or obs.get("normalize", False) or (obs.get("noise") or {}).get("var", 0) != 0:
+        raise NotImplementedError("observation history / normalisation / noise (SURVEY §8f row 1)")
+    names = [(s["name"], s["type"]) for s in obs["states"]]
+    expect = [("roll", "state"), ("pitch", "state"), ("Va", "state"), ("omega_p", "state"), ("omega_q", "state"),
+              ("omega_r", "state"), ("roll", "target"), ("pitch", "target"), ("Va", "target"), ("alpha", "state"),
+              ("beta", "state"), ("elevator", "action"), ("aileron", "action"), ("throttle", "action")]
+    if names != expect:
+        raise NotImplementedError("observation layout other than the default 14-vector")
+    c.obs_act_window = int([s for s in obs["states"] if s["type"] == "action"][0].get("window_size", 1))
+    if max(c.obs_act_window, c.rew_delta_window) > 8:
+        raise NotImplementedError("action windows > 8")
+    c.rise_low, c.rise_high = 0.1, 0.9
+    for m in env.get("metrics", []):
+        if m["name"] == "rise_time":
+            c.rise_low, c.rise_high = m.get("low", 0.1), m.get("high", 0.9)
+    c.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    c.env_id_offset = int(env_id_offset)
+    return c
+
+
+def observation_bounds(env_cfg=None, cfg=None):
+    """observation_space low/high (fixed_wing.py:92-140) for the default 14-vector."""
+    f32max = float(np.finfo(np.float32).max)
+    d = np.radians
+    lo = [d(-180), d(-85), 0, d(-720), d(-720), d(-720)]
+    hi = [d(180), d(85), 70, d(720), d(720), d(720)]
+    # targets: pyfly state limits -> none for roll/pitch; Va has value_min 1e-6
+    lo += [-f32max, -f32max, 1e-6, -f32max, -f32max]
+    hi += [f32max, f32max, f32max, f32max, f32max]
+    a_lo = [cfg.act_lo[j] for j in range(3)] if cfg is not None else [d(-30), d(-32.5), 0]
+    a_hi = [cfg.act_hi[j] for j in range(3)] if cfg is not None else [d(35), d(32.5), 1]
+    return (np.array(lo + a_lo, dtype=np.float32), np.array(hi + a_hi, dtype=np.float32))
