@@ -1,0 +1,132 @@
+"""GPU parity tests proper: libfwb200.so (through the C ABI) against
+  (1) fixtures recorded from the live reference (tests/golden/*.npz, made by tests/golden/make_golden.py), and
+  (2) the C oracle (oracle/fw_oracle.c) on seeded inputs.
+Bars: fp64 exact mode within 1e-9 relative per step (north_star); done / termination codes / RHS-evaluation
+counts / integer metrics bit-exact."""
+import numpy as np
+import pytest
+
+from conftest import TRAJ_CASES, close_or_both_nan, golden_metric_rows, load_golden
+
+pytestmark = pytest.mark.gpu
+
+RTOL_F64 = 1e-9
+
+
+def _rel(a, b):
+    return np.abs(a - b) / np.maximum(1.0, np.abs(b))
+
+
+def _run_golden(name, cfg_kw, sim_kw, f32, torch, B):
+    from tum_adlr_deep_reinforcement_learning_b200 import batched as bt
+    from tum_adlr_deep_reinforcement_learning_b200.config import build_config
+    g = load_golden(name)
+    E, T = g["actions"].shape[:2]
+    cfg = build_config(config_kw=cfg_kw, sim_config_kw=sim_kw)
+    env = B(E, cfg=cfg)
+    env.enable_f64_outputs()
+    noise = torch.as_tensor(g["noise"]) if "noise" in g.files else None
+    env.reset(state=g["init_state"], target=g["init_target"], noise=noise)
+    out = dict(obs0=env.obs64.cpu().numpy(), y0=env.get_field(bt.FIELD_Y).cpu().numpy())
+    rec = {k: [] for k in ("y", "obs", "rew", "done", "term", "nfev", "vab", "tgt", "cmd")}
+    metrics = {}
+    alive = np.ones(E, bool)
+    for t in range(T):
+        a = torch.as_tensor(g["actions"][:, t], dtype=torch.float32 if f32 else torch.float64).cuda().contiguous()
+        env.step(a, auto_reset=False)
+        term, m, ret, ln = env.episode_info()
+        rec["y"].append(env.get_field(bt.FIELD_Y).cpu().numpy())
+        rec["obs"].append(env.obs64.cpu().numpy())
+        rec["rew"].append(env.rew64.cpu().numpy())
+        rec["done"].append(env.done.cpu().numpy().astype(bool))
+        rec["term"].append(term.cpu().numpy())
+        rec["nfev"].append(env.get_field(bt.FIELD_NFEV).cpu().numpy()[:, 0])
+        rec["vab"].append(env.get_field(bt.FIELD_VAB).cpu().numpy())
+        rec["tgt"].append(env.get_field(bt.FIELD_TARGET).cpu().numpy())
+        rec["cmd"].append(env.get_field(bt.FIELD_CMD).cpu().numpy())
+        d = rec["done"][-1]
+        for ep in np.where(d & alive)[0]:
+            metrics[int(ep)] = m[ep].cpu().numpy()
+        alive &= ~d
+    env.close()
+    out.update({k: np.stack(v, axis=1) for k, v in rec.items()})
+    out["metrics"] = metrics
+    return g, out
+
+
+@pytest.mark.parametrize("name,cfg_kw,sim_kw,f32", TRAJ_CASES, ids=[c[0] for c in TRAJ_CASES])
+def test_reference_fixture_trajectories(name, cfg_kw, sim_kw, f32, cuda_device):
+    import torch
+    from tum_adlr_deep_reinforcement_learning_b200.batched import BatchedFixedWing
+    g, o = _run_golden(name, cfg_kw, sim_kw, f32, torch, BatchedFixedWing)
+    E, T = g["actions"].shape[:2]
+    assert np.abs(o["y0"] - g["y0"]).max() < 1e-14
+    assert np.abs(o["obs0"] - g["obs0"]).max() < 1e-12
+    worst = {}
+    n_steps = n_same_nfev = 0
+    for ep in range(E):
+        nv = int(g["n_valid"][ep])
+        sl = slice(0, nv)
+        ok = g["term"][ep, sl] < 10          # steps where the simulator step succeeded
+        # flags: bit exact
+        assert np.array_equal(o["done"][ep, sl], g["done"][ep, sl].astype(bool)), (name, ep)
+        assert np.array_equal(o["term"][ep, sl], g["term"][ep, sl]), (name, ep)
+        for key, ref, got in (("y", g["y"][ep, sl][ok], o["y"][ep, sl][ok]),
+                              ("vab", g["vab"][ep, sl][ok], o["vab"][ep, sl][ok]),
+                              ("obs", g["obs"][ep, sl], o["obs"][ep, sl]),
+                              ("rew", g["reward"][ep, sl], o["rew"][ep, sl]),
+                              ("tgt", g["target"][ep, sl], o["tgt"][ep, sl]),
+                              ("cmd", g["cmd"][ep, sl], o["cmd"][ep, sl])):
+            if ref.size:
+                worst[key] = max(worst.get(key, 0.0), float(_rel(got, ref).max()))
+        n_steps += nv
+        n_same_nfev += int((o["nfev"][ep, sl] == g["nfev"][ep, sl]).sum())
+    print("\n[%s] worst rel err %s ; identical RHS-evaluation counts %d/%d" % (
+        name, {k: "%.2e" % v for k, v in worst.items()}, n_same_nfev, n_steps))
+    for k, v in worst.items():
+        assert v < RTOL_F64, (name, k, v)
+    assert n_same_nfev == n_steps, "adaptive step-size decisions diverged from the reference"
+    if "m_success" in g.files:
+        rows, eps = golden_metric_rows(g)
+        for row, ep in zip(rows, eps):
+            got = o["metrics"][ep]
+            assert close_or_both_nan(got, row, 1e-7, 1e-9).all(), (name, ep, got, row)
+            for lo, hi in ((0, 7), (17, 21)):     # rise/settling times and success flags are integers: exact
+                assert np.array_equal(np.nan_to_num(got[lo:hi], nan=-1), np.nan_to_num(row[lo:hi], nan=-1))
+
+
+def test_batch_against_oracle_random_policy(cuda_device):
+    """2048 envs x 40 steps, Philox resets, turbulence on, float32 actions: CUDA vs C oracle, state-for-state."""
+    import torch
+    from oracle import fw_oracle as O
+    from tum_adlr_deep_reinforcement_learning_b200 import batched as bt
+    from tum_adlr_deep_reinforcement_learning_b200.config import build_config
+    n, T = 2048, 40
+    cfg = build_config(sim_config_kw={"turbulence": True}, seed=1234)
+    env = bt.BatchedFixedWing(n, cfg=cfg)
+    env.enable_f64_outputs()
+    env.reset()
+    ob = O.OracleBatch(cfg, n)
+    obs_ref = ob.reset().copy()
+    assert _rel(env.obs64.cpu().numpy(), obs_ref).max() < 1e-12
+    rs = np.random.RandomState(0)
+    for t in range(T):
+        a = rs.uniform(-1.5, 1.5, (n, 3)).astype(np.float32)
+        env.step(torch.as_tensor(a).cuda(), auto_reset=True)
+        o_ref, r_ref, d_ref = ob.step(a)
+        assert np.array_equal(env.done.cpu().numpy(), d_ref)
+        assert _rel(env.obs64.cpu().numpy(), o_ref).max() < RTOL_F64, t
+        assert _rel(env.rew64.cpu().numpy(), r_ref).max() < RTOL_F64, t
+    env.close()
+
+
+def test_gae_bit_exact_vs_reference_fixture(cuda_device):
+    import torch
+    from tum_adlr_deep_reinforcement_learning_b200.batched import gae
+    g = load_golden("gae")
+    for tag in ("a", "b", "c"):
+        dev = lambda x: torch.as_tensor(np.ascontiguousarray(x)).cuda()
+        adv, ret = gae(dev(g[tag + "_rew"]), dev(g[tag + "_val"]), dev(g[tag + "_done"]), dev(g[tag + "_last_val"]),
+                       dev(g[tag + "_last_done"].astype(np.uint8)))
+        assert np.array_equal(adv.cpu().numpy(), g[tag + "_adv"]), tag
+        assert np.array_equal(ret.cpu().numpy(), g[tag + "_ret"]), tag

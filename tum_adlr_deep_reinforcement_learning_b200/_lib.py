@@ -1,0 +1,51 @@
+"""ctypes binding of libfwb200.so — the only way host code reaches the kernels.  Fails loudly when the library
+is missing or cannot be loaded: there is no CPU / PyTorch fallback for the env step."""
+import ctypes
+import os
+
+from .build import LIB_PATH
+from .config import FwConfig
+
+_lib = None
+_vp = ctypes.c_void_p
+
+
+class FwError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FwError("%s is missing — run `python -c 'import __graft_entry__ as g; g.build()'` "
+                      "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    L.fw_last_error.restype = ctypes.c_char_p
+    L.fw_create.argtypes = [ctypes.POINTER(FwConfig), ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(_vp)]
+    L.fw_destroy.argtypes = [_vp]
+    L.fw_reset.argtypes = [_vp, _vp, _vp, _vp, _vp, ctypes.c_int32, _vp, _vp, _vp]
+    L.fw_step.argtypes = [_vp, _vp, ctypes.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_int32, _vp]
+    L.fw_step_random.argtypes = [_vp, ctypes.c_int32, ctypes.c_uint64, _vp, _vp, _vp, _vp]
+    L.fw_get_episode_info.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp]
+    L.fw_get_field.argtypes = [_vp, ctypes.c_int32, _vp, _vp]
+    L.fw_set_field.argtypes = [_vp, ctypes.c_int32, _vp, _vp]
+    L.fw_gae.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_float,
+                         ctypes.c_float, _vp]
+    L.fw_measure_fma_peak.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(ctypes.c_double)]
+    L.fw_config_size.restype = ctypes.c_int
+    L.fw_abi_version.restype = ctypes.c_int
+    if L.fw_config_size() != ctypes.sizeof(FwConfig):
+        raise FwError("FwConfig layout mismatch between config.py and include/fwb200.h")
+    _lib = L
+    return L
+
+
+def check(rc, what):
+    if rc != 0:
+        raise FwError("%s failed (%d): %s" % (what, rc, lib().fw_last_error().decode()))
+
+
+EXPORTS = ("fw_create", "fw_destroy", "fw_last_error", "fw_abi_version", "fw_reset", "fw_step", "fw_step_random",
+           "fw_get_episode_info", "fw_get_field", "fw_set_field", "fw_gae", "fw_measure_fma_peak")

@@ -1,0 +1,143 @@
+"""BatchedFixedWing — thin tensor-level front-end over the C ABI (one handle = n envs on one GPU).
+
+This is the fast path: every argument and result is a torch CUDA tensor, nothing is copied to the host and no
+per-env Python object is created.  `FixedWingVecEnv` (vec_env.py) layers the SB3 VecEnv contract on top.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from .config import (FW_NMETRIC, FW_NOBS, FW_NSTATE_INJECT, FW_NY, build_config)
+
+FIELD_Y, FIELD_EULER, FIELD_VAB, FIELD_WIND, FIELD_TARGET, FIELD_CMD, FIELD_TURB, FIELD_COUNTERS, FIELD_NFEV = range(9)
+_FIELD_SHAPE = {FIELD_Y: (FW_NY, torch.float64), FIELD_EULER: (3, torch.float64), FIELD_VAB: (3, torch.float64),
+                FIELD_WIND: (3, torch.float64), FIELD_TARGET: (3, torch.float64), FIELD_CMD: (3, torch.float64),
+                FIELD_TURB: (6, torch.float64), FIELD_COUNTERS: (4, torch.int32), FIELD_NFEV: (2, torch.int32)}
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+class BatchedFixedWing:
+    def __init__(self, n_envs, cfg=None, device=0, **cfg_kw):
+        if not torch.cuda.is_available():
+            raise _lib.FwError("BatchedFixedWing needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.cfg = cfg if cfg is not None else build_config(**cfg_kw)
+        self.n = int(n_envs)
+        self.device = torch.device("cuda", device)
+        self._h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().fw_create(ctypes.byref(self.cfg), self.n, device, ctypes.byref(self._h)), "fw_create")
+        n, dev = self.n, self.device
+        self.obs = torch.zeros(n, FW_NOBS, dtype=torch.float32, device=dev)
+        self.rew = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.done = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self.term_obs = torch.zeros(n, FW_NOBS, dtype=torch.float32, device=dev)
+        self.obs64 = None
+        self.rew64 = None
+        self._noise = None   # keeps an injected noise buffer alive
+
+    def close(self):
+        if self._h:
+            _lib.lib().fw_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def enable_f64_outputs(self):
+        self.obs64 = torch.zeros(self.n, FW_NOBS, dtype=torch.float64, device=self.device)
+        self.rew64 = torch.zeros(self.n, dtype=torch.float64, device=self.device)
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def reset(self, mask=None, state=None, target=None, noise=None):
+        """mask [n] uint8/bool, state [n,21] f64 (NaN = sample), target [n,3] f64, noise [n,4,L] f64 — all optional."""
+        dev = self.device
+
+        def prep(x, dtype, shape):
+            if x is None:
+                return None
+            x = torch.as_tensor(x, dtype=dtype, device=dev).contiguous()
+            assert tuple(x.shape) == shape, (tuple(x.shape), shape)
+            return x
+
+        mask = prep(mask, torch.uint8, (self.n,))
+        state = prep(state, torch.float64, (self.n, FW_NSTATE_INJECT))
+        target = prep(target, torch.float64, (self.n, 3))
+        nlen = 0
+        if noise is not None:
+            noise = torch.as_tensor(noise, dtype=torch.float64, device=dev).contiguous()
+            assert noise.shape[:2] == (self.n, 4)
+            nlen = noise.shape[2]
+        self._noise = noise
+        self._keep = (mask, state, target)
+        _lib.check(_lib.lib().fw_reset(self._h, _ptr(mask), _ptr(state), _ptr(target), _ptr(noise), nlen,
+                                       _ptr(self.obs), _ptr(self.obs64), self._stream()), "fw_reset")
+        return self.obs
+
+    def step(self, actions, auto_reset=True):
+        """actions [n,3] float32 or float64 CUDA tensor (raw agent actions).  Returns (obs, rew, done) tensors that
+        are overwritten by the next call."""
+        assert actions.is_cuda and actions.is_contiguous() and tuple(actions.shape) == (self.n, 3)
+        f64 = actions.dtype == torch.float64
+        assert f64 or actions.dtype == torch.float32
+        _lib.check(_lib.lib().fw_step(self._h, _ptr(actions), int(f64), _ptr(self.obs), _ptr(self.rew),
+                                      _ptr(self.done), _ptr(self.term_obs), _ptr(self.obs64), _ptr(self.rew64),
+                                      int(auto_reset), self._stream()), "fw_step")
+        return self.obs, self.rew, self.done
+
+    def step_random(self, k_steps, action_seed=1):
+        _lib.check(_lib.lib().fw_step_random(self._h, int(k_steps), int(action_seed), _ptr(self.obs), _ptr(self.rew),
+                                             _ptr(self.done), self._stream()), "fw_step_random")
+        return self.obs, self.rew, self.done
+
+    def episode_info(self):
+        dev = self.device
+        term = torch.zeros(self.n, dtype=torch.int32, device=dev)
+        metrics = torch.zeros(self.n, FW_NMETRIC, dtype=torch.float64, device=dev)
+        ret = torch.zeros(self.n, dtype=torch.float64, device=dev)
+        length = torch.zeros(self.n, dtype=torch.int32, device=dev)
+        _lib.check(_lib.lib().fw_get_episode_info(self._h, _ptr(term), _ptr(metrics), _ptr(ret), _ptr(length),
+                                                  self._stream()), "fw_get_episode_info")
+        return term, metrics, ret, length
+
+    def get_field(self, field):
+        width, dtype = _FIELD_SHAPE[field]
+        out = torch.zeros(self.n, width, dtype=dtype, device=self.device)
+        _lib.check(_lib.lib().fw_get_field(self._h, field, _ptr(out), self._stream()), "fw_get_field")
+        return out
+
+    def set_field(self, field, value):
+        width, dtype = _FIELD_SHAPE[field]
+        value = torch.as_tensor(value, dtype=dtype, device=self.device).contiguous()
+        assert tuple(value.shape) == (self.n, width)
+        _lib.check(_lib.lib().fw_set_field(self._h, field, _ptr(value), self._stream()), "fw_set_field")
+        torch.cuda.current_stream(self.device).synchronize()
+
+
+def gae(rew, val, done, last_val, last_done, gamma=0.99, gae_lambda=0.95):
+    """Time-major [T, N] float32 CUDA tensors -> (advantages, returns); RolloutBuffer semantics (buffers.py:304-333)."""
+    T, N = rew.shape
+    for t in (rew, val, done):
+        assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == (T, N)
+    last_val = last_val.to(torch.float32).contiguous().view(-1)
+    last_done = last_done.to(torch.uint8).contiguous().view(-1)
+    adv, ret = torch.empty_like(rew), torch.empty_like(rew)
+    st = ctypes.c_void_p(torch.cuda.current_stream(rew.device).cuda_stream)
+    _lib.check(_lib.lib().fw_gae(_ptr(rew), _ptr(val), _ptr(done), _ptr(last_val), _ptr(last_done), _ptr(adv),
+                                 _ptr(ret), T, N, float(gamma), float(gae_lambda), st), "fw_gae")
+    return adv, ret
+
+
+def measure_fma_peak(device=0, precision="f64"):
+    out = ctypes.c_double()
+    _lib.check(_lib.lib().fw_measure_fma_peak(device, 0 if precision == "f64" else 1, ctypes.byref(out)),
+               "fw_measure_fma_peak")
+    return out.value

@@ -1,0 +1,713 @@
+// fw_device.cuh — device code of the batched fixed-wing env step (sm_100a).
+//
+// One thread owns one env.  All persistent env state lives structure-of-arrays in HBM (`S.r[field * n + env]`,
+// `S.i[field * n + env]`), so every load/store of a warp is one fully coalesced 128/256-byte transaction.
+// The step is compute bound on the FP64 (exact mode) or FP32 (fast mode) CUDA-core pipe: ~24 RHS evaluations of
+// ~900 FP instructions per env-step against ~1.6 KB of state traffic (DESIGN.md "roofline").
+//
+// Reference semantics followed (paths under magpie/libs/ of the reference; see DESIGN.md for the full map):
+//   pyfly/pyfly/pyfly.py   PyFly.step :1358-1420, _dynamics :1450-1482, _forces :1484-1643, _f_*_dot :1645-1747,
+//                          _rot_b_v :1749-1803, _calculate_airspeed_factors :1830-1850,
+//                          _set_states_from_ode_solution :1852-1881, Actuation :453-655, reset :1262-1311
+//   pyfly/pyfly/dryden.py  simulate :193-261 (streamed here: one lsim recurrence step per env-step)
+//   fixed-wing-gym/gym_fixed_wing/fixed_wing.py   reset :414-481, step :483-628, sample_target :654-746,
+//                          get_reward :941-1111, get_observation :1113-1262, _get_next_target :1363-1471,
+//                          get_metric :1644-1736 (streamed: rings + running accumulators)
+//   scipy.integrate.solve_ivp RK45 (un-vendored dependency; rk.py / common.py) for the exact integrator.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "../../include/fwb200.h"
+
+namespace fw {
+
+// ---------------------------------------------------------------------------------------------------------------
+// math wrappers: one spelling for float / double
+template <typename T> struct M;
+template <> struct M<double> {
+    static __device__ __forceinline__ double sin(double x) { return ::sin(x); }
+    static __device__ __forceinline__ double cos(double x) { return ::cos(x); }
+    static __device__ __forceinline__ void sincos(double x, double* s, double* c) { ::sincos(x, s, c); }
+    static __device__ __forceinline__ double exp(double x) { return ::exp(x); }
+    static __device__ __forceinline__ double log(double x) { return ::log(x); }
+    static __device__ __forceinline__ double sqrt(double x) { return ::sqrt(x); }
+    static __device__ __forceinline__ double atan2(double y, double x) { return ::atan2(y, x); }
+    static __device__ __forceinline__ double asin(double x) { return ::asin(x); }
+    static __device__ __forceinline__ double pow(double x, double y) { return ::pow(x, y); }
+    static __device__ __forceinline__ double fabs(double x) { return ::fabs(x); }
+    static __device__ __forceinline__ double fmin(double a, double b) { return ::fmin(a, b); }
+    static __device__ __forceinline__ double fmax(double a, double b) { return ::fmax(a, b); }
+    static __device__ __forceinline__ double fmod(double a, double b) { return ::fmod(a, b); }
+    static __device__ __forceinline__ double nan() { return CUDART_NAN; }
+    static __device__ __forceinline__ double inf() { return CUDART_INF; }
+    static __device__ __forceinline__ bool isnan(double x) { return ::isnan(x); }
+};
+template <> struct M<float> {
+    static __device__ __forceinline__ float sin(float x) { return ::sinf(x); }
+    static __device__ __forceinline__ float cos(float x) { return ::cosf(x); }
+    static __device__ __forceinline__ void sincos(float x, float* s, float* c) { ::sincosf(x, s, c); }
+    static __device__ __forceinline__ float exp(float x) { return ::expf(x); }
+    static __device__ __forceinline__ float log(float x) { return ::logf(x); }
+    static __device__ __forceinline__ float sqrt(float x) { return ::sqrtf(x); }
+    static __device__ __forceinline__ float atan2(float y, float x) { return ::atan2f(y, x); }
+    static __device__ __forceinline__ float asin(float x) { return ::asinf(x); }
+    static __device__ __forceinline__ float pow(float x, float y) { return ::powf(x, y); }
+    static __device__ __forceinline__ float fabs(float x) { return ::fabsf(x); }
+    static __device__ __forceinline__ float fmin(float a, float b) { return ::fminf(a, b); }
+    static __device__ __forceinline__ float fmax(float a, float b) { return ::fmaxf(a, b); }
+    static __device__ __forceinline__ float fmod(float a, float b) { return ::fmodf(a, b); }
+    static __device__ __forceinline__ float nan() { return CUDART_NAN_F; }
+    static __device__ __forceinline__ float inf() { return CUDART_INF_F; }
+    static __device__ __forceinline__ bool isnan(float x) { return ::isnan(x); }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// device-side config: FwConfig converted once on the host to the arithmetic type of the kernel and passed to every
+// launch as a __grid_constant__ kernel parameter (constant bank, warp-uniform broadcast reads).
+template <typename T> struct DFilter {
+    int order, noise_row;
+    T Ad[9], Bd0[3], Bd1[3], C[3], D;
+};
+
+template <typename T> struct DCfg {
+    int integrator, rk4_substeps, turbulence, steps_max, scale_actions, has_action_bounds;
+    int tgt_class[3], on_success, streak_req, resample_every, rew_delta_window, obs_act_window, step_fail_timesteps;
+    T rtol, atol;
+    T mass, Jy, S_wing, b, c, k_motor, k_T_P, k_Omega, M_, a_0, ar;
+    T C_L_0, C_L_alpha, C_L_q, C_L_delta_e, C_D_p, C_D_q, C_D_beta1, C_D_beta2, C_D_delta_e;
+    T C_m_0, C_m_alpha, C_m_q, C_m_delta_e, C_m_fp;
+    T C_Y_0, C_Y_beta, C_Y_p, C_Y_r, C_Y_delta_a, C_Y_delta_r;
+    T C_l_0, C_l_beta, C_l_p, C_l_r, C_l_delta_a, C_l_delta_r;
+    T C_n_0, C_n_beta, C_n_p, C_n_r, C_n_delta_a, C_n_delta_r;
+    T gam[9];
+    T half_rho, mg, prop_k /* 0.5 rho S_prop C_prop */, pi_e_ar;
+    T dt, elevon_min, elevon_max, elevon_dot_max, w0sq, two_zeta_w0, inv_tau, throttle_min, throttle_max;
+    T omega_con_min[3], omega_con_max[3], va_value_min, va_con_max;
+    T init_lo[12], init_hi[12], wind_mag_min, wind_mag_max, turb_noise_scale;
+    DFilter<T> filt[6];
+    T scale_low, scale_high, act_lo[3], act_hi[3], action_bounds_min[3], action_bounds_max[3];
+    T tgt_low[3], tgt_high[3], tgt_delta[3], tgt_bound[3], streak_fraction;
+    T rew_err_scaling[3], rew_err_max[3], rew_delta_scaling, rew_delta_max, rew_bound_scaling, rew_bound_max;
+    T step_fail_value, rise_low, rise_high;
+    unsigned long long seed;
+    long long env_id_offset;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// SoA field ids
+enum RField {
+    RF_Y = 0,                 // 19: quat4 omega3 pos3 vel3 act_val3 act_dot3
+    RF_ROLL = 19, RF_PITCH, RF_VA, RF_ALPHA, RF_BETA,   // last committed (= .history[-1]) values
+    RF_WIND = 24,             // 3
+    RF_TGT = 27,              // 3
+    RF_FX = 30,               // 12 filter states (filter f uses slots 3*? see FX_OFF)
+    RF_FU = 42,               // 4 current (scaled) noise sample u_k
+    RF_ACT_RING = 46,         // 4 x 3 previous raw actions, slot (age-1)*3 + j, age 1 = most recent
+    RF_CMD_RING = 58,         // 4 x 3 previous constrained commands (same layout); slot 0..2 doubles as cmd_prev
+    RF_CV_SUM = 70,           // sum |delta cmd|
+    RF_E0 = 71,               // 3 initial errors
+    RF_ESUM = 74, RF_EABS = 77, RF_EMIN = 80, RF_EMAX = 83, RF_EPREV = 86,   // 3 each
+    RF_EP_RET = 89,
+    RF_COUNT = 90
+};
+enum IField {
+    IF_STEPS = 0, IF_STEPS_TGT, IF_EPISODE, IF_SIM_STEP,
+    IF_GOAL_RING = 4,         // 4 states x 4 words (128-bit rings)
+    IF_GOAL_CNT = 20,         // 4 window counts
+    IF_GOAL_TOTAL = 24,       // 4
+    IF_SETTLE = 28,           // 4 (-1 = never)
+    IF_RISE_LO = 32,          // 3 first index t with |e_t| >= low_lim and |e_{t+1}| < low_lim (-1 = none)
+    IF_RISE_HI = 35,          // 3
+    IF_NFEV = 38, IF_NATT = 39, IF_TERM = 40, IF_EP_LEN = 41, IF_ACT_F32 = 42,
+    IF_COUNT = 43
+};
+__device__ __constant__ const int FX_OFF[6] = {0, 1, 3, 5, 6, 9};   // orders 1 2 2 1 3 3
+
+template <typename T> struct Soa {
+    T* r;              // [RF_COUNT][n]
+    int32_t* i;        // [IF_COUNT][n]
+    T* err_ring;       // [FW_END_ERR_WINDOW * 3][n]
+    double* metrics;   // [n][FW_NMETRIC] (written on done)
+    double* ep_ret;    // [n] episode return / length / term of the episode that ended at the last step
+    int32_t* ep_len;
+    int32_t* ep_term;
+    const double* noise;   // injected unit white noise [n][4][noise_len] or nullptr (Philox)
+    int noise_len;
+    int n;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// Philox4x32-10 counter-based RNG (Salmon et al. SC'11).  Stream layout (identical in oracle/fw_oracle.c):
+//   key = seed;  counter = (env_id lo32, episode lo32, purpose << 28 | env_id hi bits, block)
+enum { RNG_RESET = 0, RNG_NOISE = 1, RNG_RESAMPLE = 2, RNG_ACTION = 3 };
+
+__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += 0x9E3779B9u;
+        key.y += 0xBB67AE85u;
+    }
+    return ctr;
+}
+__device__ __forceinline__ uint4 rng_block(unsigned long long seed, long long env_id, unsigned long long episode,
+                                           uint32_t purpose, uint32_t block) {
+    uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    uint4 ctr = make_uint4((uint32_t)env_id, (uint32_t)episode,
+                           (purpose << 28) | ((uint32_t)((unsigned long long)env_id >> 32) & 0x0FFFFFFFu), block);
+    return philox4x32(ctr, key);
+}
+__device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {
+    return (double)((((unsigned long long)hi) << 21) ^ (((unsigned long long)lo) >> 11)) * (1.0 / 9007199254740992.0);
+}
+template <typename T>
+__device__ __forceinline__ T rng_uniform(unsigned long long seed, long long env_id, unsigned long long episode,
+                                         uint32_t purpose, int idx) {
+    uint4 r = rng_block(seed, env_id, episode, purpose, (uint32_t)(idx >> 1));
+    return (T)((idx & 1) ? u53(r.z, r.w) : u53(r.x, r.y));
+}
+// four unit normals for turbulence sample k (Box-Muller on 32-bit uniforms; evaluated in double in both precisions:
+// it is 4 transcendentals per env-step against ~200 in the integrator)
+__device__ __forceinline__ void rng_noise4(unsigned long long seed, long long env_id, unsigned long long episode,
+                                           uint32_t k, double out[4]) {
+    uint4 r = rng_block(seed, env_id, episode, RNG_NOISE, k);
+    uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        double u1 = ((double)w[2 * i] + 0.5) * (1.0 / 4294967296.0);
+        double u2 = ((double)w[2 * i + 1] + 0.5) * (1.0 / 4294967296.0);
+        double rad = ::sqrt(-2.0 * ::log(u1)), s, c;
+        ::sincos(6.283185307179586476925 * u2, &s, &c);
+        out[2 * i] = rad * c;
+        out[2 * i + 1] = rad * s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ T clip(T v, T lo, T hi) { return v < lo ? lo : (v > hi ? hi : v); }
+template <typename T> __device__ __forceinline__ T sgn(T v) { return (T)((v > (T)0) - (v < (T)0)); }
+
+// per-step dynamics context that is constant during one integration
+template <typename T> struct DynCtx {
+    T cmd[3];      // constrained commands of elevon_right, elevon_left, throttle
+    T wind[3];     // steady wind NED
+    T tl[3];       // linear turbulence sample (body frame)
+    T ta[3];       // angular turbulence sample
+};
+
+// _rot_b_v Euler branch (pyfly.py:1757-1777) applied to a vector
+template <typename T>
+__device__ __forceinline__ void rot_euler_apply(T phi, T th, T psi, const T v[3], T out[3]) {
+    T sph, cph, sth, cth, sps, cps;
+    M<T>::sincos(phi, &sph, &cph);
+    M<T>::sincos(th, &sth, &cth);
+    M<T>::sincos(psi, &sps, &cps);
+    out[0] = cth * cps * v[0] + cth * sps * v[1] + (-sth) * v[2];
+    out[1] = (sph * sth * cps - cph * sps) * v[0] + (sph * sth * sps + cph * cps) * v[1] + sph * cth * v[2];
+    out[2] = (cph * sth * cps + sph * sps) * v[0] + (cph * sth * sps - sph * cps) * v[1] + cph * cth * v[2];
+}
+
+// PyFly._dynamics with _forces inlined.  `first` = the t == 0 call of solve_ivp (no state write-back, pyfly.py:1461):
+// constraint checks are skipped and elevator/aileron come from `elev0/ail0` (they are 0 right after a reset because
+// disabled ControlVariables reset to 0, pyfly.py:359-363).  Returns 0 or a FwTermCode.
+template <typename T, bool TURB>
+__device__ __forceinline__ int rhs(const DCfg<T>& c, const DynCtx<T>& x, const T (&y)[FW_NY], bool first, T elev0,
+                                   T ail0, T (&dy)[FW_NY]) {
+    const T e0 = y[0], e1 = y[1], e2 = y[2], e3 = y[3];
+    const T P = y[4], Q = y[5], R = y[6];
+    const T u = y[10], v = y[11], w = y[12];
+    if (!first) {
+        // _set_states_from_ode_solution(save=False): ConstraintException on p, q, r (pyfly.py:1872-1874)
+        if (P < c.omega_con_min[0] || P > c.omega_con_max[0]) return FW_TERM_OMEGA_P;
+        if (Q < c.omega_con_min[1] || Q > c.omega_con_max[1]) return FW_TERM_OMEGA_Q;
+        if (R < c.omega_con_min[2] || R > c.omega_con_max[2]) return FW_TERM_OMEGA_R;
+    }
+    // Actuation.set_states: the RHS sees CLIPPED actuator values / rates (pyfly.py:471-492, 312-328)
+    const T er = clip(y[13], c.elevon_min, c.elevon_max), el = clip(y[14], c.elevon_min, c.elevon_max);
+    const T thr = clip(y[15], c.throttle_min, c.throttle_max);
+    const T erd = clip(y[16], -c.elevon_dot_max, c.elevon_dot_max), eld = clip(y[17], -c.elevon_dot_max, c.elevon_dot_max);
+    const T elevator = first ? elev0 : (er + el) / (T)2;
+    const T aileron = first ? ail0 : (-er + el) / (T)2;
+
+    T p = P, q = Q, r = R;
+    if (TURB) { p -= x.ta[0]; q -= x.ta[1]; r -= x.ta[2]; }
+    // _calculate_airspeed_factors with the quaternion rotation (un-normalised quaternion, pyfly.py:1464,1782-1800)
+    const T r00 = (T)-1 + (T)2 * (e0 * e0 + e1 * e1), r01 = (T)2 * (e1 * e2 + e3 * e0), r02 = (T)2 * (e1 * e3 - e2 * e0);
+    const T r10 = (T)2 * (e1 * e2 - e3 * e0), r11 = (T)-1 + (T)2 * (e0 * e0 + e2 * e2), r12 = (T)2 * (e2 * e3 + e1 * e0);
+    const T r20 = (T)2 * (e1 * e3 + e2 * e0), r21 = (T)2 * (e2 * e3 - e1 * e0), r22 = (T)-1 + (T)2 * (e0 * e0 + e3 * e3);
+    T a0 = u - (r00 * x.wind[0] + r01 * x.wind[1] + r02 * x.wind[2] + (TURB ? x.tl[0] : (T)0));
+    T a1 = v - (r10 * x.wind[0] + r11 * x.wind[1] + r12 * x.wind[2] + (TURB ? x.tl[1] : (T)0));
+    T a2 = w - (r20 * x.wind[0] + r21 * x.wind[1] + r22 * x.wind[2] + (TURB ? x.tl[2] : (T)0));
+    T Va = M<T>::sqrt(a0 * a0 + a1 * a1 + a2 * a2);
+    const T alpha = M<T>::atan2(a2, a0);
+    const T beta = M<T>::asin(a1 / Va);
+    if (c.va_con_max > (T)0 && Va > c.va_con_max) return FW_TERM_VA;
+    if (Va < c.va_value_min) Va = c.va_value_min;
+
+    const T pre = c.half_rho * (Va * Va) * c.S_wing;
+    const T fgx = c.mg * ((T)2 * (e1 * e3 - e2 * e0)), fgy = c.mg * ((T)2 * (e2 * e3 + e1 * e0));
+    const T fgz = c.mg * (e3 * e3 + e0 * e0 - e1 * e1 - e2 * e2);
+    const T CLlin = c.C_L_0 + c.C_L_alpha * alpha;
+    T sigma;
+    if (sizeof(T) == 8) {
+        const T ex1 = M<T>::exp(-c.M_ * (alpha - c.a_0)), ex2 = M<T>::exp(c.M_ * (alpha + c.a_0));
+        sigma = ((T)1 + ex1 + ex2) / (((T)1 + ex1) * ((T)1 + ex2));
+    } else {
+        // algebraically identical, overflow-safe in fp32: sigma = 1 - s(-M(a-a0)) s(M(a+a0)), s = logistic
+        const T g1 = M<T>::exp(c.M_ * (alpha - c.a_0)), g2 = M<T>::exp(-c.M_ * (alpha + c.a_0));
+        sigma = (T)1 - (T)1 / (((T)1 + g1) * ((T)1 + g2));
+    }
+    T sa, ca, sb, cb;
+    M<T>::sincos(alpha, &sa, &ca);
+    M<T>::sincos(beta, &sb, &cb);
+    const T sg = sgn(alpha);
+    const T inv2Va = (T)1 / ((T)2 * Va);
+    const T C_L = ((T)1 - sigma) * CLlin + sigma * ((T)2 * sg * (sa * sa) * ca);
+    const T lift = pre * (C_L + c.C_L_q * c.c * inv2Va * q + c.C_L_delta_e * elevator);
+    const T C_Da = c.C_D_p + ((T)1 - sigma) * (CLlin * CLlin) / c.pi_e_ar + sigma * ((T)2 * sg * (sa * sa * sa));
+    const T C_Db = c.C_D_beta1 * beta + c.C_D_beta2 * (beta * beta);
+    const T drag = pre * (C_Da + C_Db + c.C_D_q * c.c * inv2Va * q + c.C_D_delta_e * (elevator * elevator));
+    const T C_m = ((T)1 - sigma) * (c.C_m_0 + c.C_m_alpha * alpha) + sigma * (c.C_m_fp * sg * (sa * sa));
+    const T bq = c.b * inv2Va;
+    const T m_ = pre * c.c * (C_m + c.C_m_q * bq * q + c.C_m_delta_e * elevator);   // sic: b (pyfly.py:1579)
+    const T fy = pre * (c.C_Y_0 + c.C_Y_beta * beta + c.C_Y_p * bq * p + c.C_Y_r * bq * r + c.C_Y_delta_a * aileron);
+    const T l_ = pre * c.b * (c.C_l_0 + c.C_l_beta * beta + c.C_l_p * bq * p + c.C_l_r * bq * r + c.C_l_delta_a * aileron);
+    const T n_ = pre * c.b * (c.C_n_0 + c.C_n_beta * beta + c.C_n_p * bq * p + c.C_n_r * bq * r + c.C_n_delta_a * aileron);
+    // f_aero = R_euler(0, alpha, beta) . [-drag, fy, -lift]  (pyfly.py:1617-1620; phi = 0 -> sin 0, cos 1)
+    const T s0 = -drag, s1 = fy, s2 = -lift;
+    const T fax = ca * cb * s0 + ca * sb * s1 + (-sa) * s2;
+    const T fay = (-sb) * s0 + cb * s1;
+    const T faz = sa * cb * s0 + sa * sb * s1 + ca * s2;
+    const T Vd = Va + thr * (c.k_motor - Va);
+    const T fprop = c.prop_k * Vd * (Vd - Va);
+    const T kt = c.k_Omega * thr;
+    const T fx = fprop + fgx + fax, fyb = fgy + fay, fz = fgz + faz;
+    const T tx = l_ + (-c.k_T_P * (kt * kt)), ty = m_, tz = n_;
+
+    // _f_attitude_dot uses the STATE omega (not turbulence corrected) (pyfly.py:1466,1476)
+    dy[0] = (T)0.5 * (-P * e1 - Q * e2 - R * e3);
+    dy[1] = (T)0.5 * (P * e0 + R * e2 - Q * e3);
+    dy[2] = (T)0.5 * (Q * e0 - R * e1 + P * e3);
+    dy[3] = (T)0.5 * (R * e0 + Q * e1 - P * e2);
+    dy[4] = c.gam[1] * P * Q - c.gam[2] * Q * R + c.gam[3] * tx + c.gam[4] * tz;
+    dy[5] = c.gam[5] * P * R - c.gam[6] * (P * P - R * R) + ty / c.Jy;
+    dy[6] = c.gam[7] * P * Q - c.gam[1] * Q * R + c.gam[4] * tx + c.gam[8] * tz;
+    // _f_p_dot: R(q)^T-like matrix of pyfly.py:1718-1736
+    dy[7] = (e1 * e1 + e0 * e0 - e2 * e2 - e3 * e3) * u + (T)2 * (e1 * e2 - e3 * e0) * v + (T)2 * (e1 * e3 + e2 * e0) * w;
+    dy[8] = (T)2 * (e1 * e2 + e3 * e0) * u + (e2 * e2 + e0 * e0 - e1 * e1 - e3 * e3) * v + (T)2 * (e2 * e3 - e1 * e0) * w;
+    dy[9] = (T)2 * (e1 * e3 - e2 * e0) * u + (T)2 * (e2 * e3 + e1 * e0) * v + (e3 * e3 + e0 * e0 - e1 * e1 - e2 * e2) * w;
+    dy[10] = R * v - Q * w + fx / c.mass;
+    dy[11] = P * w - R * u + fyb / c.mass;
+    dy[12] = Q * u - P * v + fz / c.mass;
+    // Actuation.rhs (pyfly.py:519-543): elevons 2nd order on clipped value/rate, throttle 1st order
+    dy[13] = erd;
+    dy[14] = eld;
+    dy[15] = thr * (-c.inv_tau) + x.cmd[2] * c.inv_tau;
+    dy[16] = er * (-c.w0sq) + x.cmd[0] * c.w0sq + erd * (-c.two_zeta_w0);
+    dy[17] = el * (-c.w0sq) + x.cmd[1] * c.w0sq + eld * (-c.two_zeta_w0);
+    dy[18] = (T)0;
+    return 0;
+}
+
+// Dormand-Prince 5(4) tableau (scipy rk.py class RK45).  Row 6 of A is B (FSAL), so stage 6's input is y_new.
+__device__ __constant__ const double RK_A[7][6] = {
+    {0, 0, 0, 0, 0, 0},
+    {1.0 / 5, 0, 0, 0, 0, 0},
+    {3.0 / 40, 9.0 / 40, 0, 0, 0, 0},
+    {44.0 / 45, -56.0 / 15, 32.0 / 9, 0, 0, 0},
+    {19372.0 / 6561, -25360.0 / 2187, 64448.0 / 6561, -212.0 / 729, 0, 0},
+    {9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656, 0},
+    {35.0 / 384, 0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84}};
+__device__ __constant__ const double RK_E[7] = {-71.0 / 57600, 0, 71.0 / 16695, -71.0 / 1920, 17253.0 / 339200,
+                                                -22.0 / 525, 1.0 / 40};
+
+template <typename T> __device__ __forceinline__ T rms19(const T (&x)[FW_NY]) {
+    T s = 0;
+#pragma unroll
+    for (int i = 0; i < FW_NY; ++i) s += x[i] * x[i];
+    return M<T>::sqrt(s) / M<T>::sqrt((T)FW_NY);
+}
+
+// scipy.integrate.solve_ivp(fun, (0, dt), y0) with RK45 defaults (pyfly.py:1393-1395), one env per thread.
+// The 7 stage derivatives live in shared memory, K[(stage * 19 + comp) * NT + tid]: 8-byte lanes of a warp hit 32
+// consecutive banks-pairs (conflict free) and the register file keeps y, y_stage and the RHS temporaries.
+template <typename T, bool TURB, int NT>
+__device__ __forceinline__ int solve_rk45(const DCfg<T>& c, const DynCtx<T>& x, T (&y)[FW_NY], T elev0, T ail0,
+                                          T* __restrict__ K, int& nfev, int& natt) {
+#define KS(s, i) K[((s) * FW_NY + (i)) * NT]
+    const T rtol = c.rtol, atol = c.atol, t_bound = c.dt;
+    T ys[FW_NY], dyv[FW_NY];
+    int rc;
+    // RungeKutta.__init__: f = fun(t0, y0)  (t == 0: no write-back)
+    rc = rhs<T, TURB>(c, x, y, true, elev0, ail0, dyv);
+    nfev = 1;
+    natt = 0;
+    if (rc) return rc;
+#pragma unroll
+    for (int i = 0; i < FW_NY; ++i) KS(0, i) = dyv[i];
+    // select_initial_step (common.py:68-134)
+    T h_abs;
+    {
+        T sc[FW_NY], tmp[FW_NY];
+#pragma unroll
+        for (int i = 0; i < FW_NY; ++i) { sc[i] = atol + M<T>::fabs(y[i]) * rtol; tmp[i] = y[i] / sc[i]; }
+        const T d0 = rms19(tmp);
+#pragma unroll
+        for (int i = 0; i < FW_NY; ++i) tmp[i] = dyv[i] / sc[i];
+        const T d1 = rms19(tmp);
+        T h0 = (d0 < (T)1e-5 || d1 < (T)1e-5) ? (T)1e-6 : (T)0.01 * d0 / d1;
+        h0 = M<T>::fmin(h0, t_bound);
+#pragma unroll
+        for (int i = 0; i < FW_NY; ++i) ys[i] = y[i] + h0 * dyv[i];
+        T f1[FW_NY];
+        rc = rhs<T, TURB>(c, x, ys, false, elev0, ail0, f1);
+        nfev++;
+        if (rc) return rc;
+#pragma unroll
+        for (int i = 0; i < FW_NY; ++i) tmp[i] = (f1[i] - dyv[i]) / sc[i];
+        const T d2 = rms19(tmp) / h0;
+        T h1;
+        if (d1 <= (T)1e-15 && d2 <= (T)1e-15) h1 = M<T>::fmax((T)1e-6, h0 * (T)1e-3);
+        else h1 = M<T>::pow((T)0.01 / M<T>::fmax(d1, d2), (T)0.2);
+        h_abs = M<T>::fmin(M<T>::fmin((T)100 * h0, h1), t_bound);
+    }
+    T t = 0;
+    while (t < t_bound) {
+        // RungeKutta._step_impl (rk.py:111-173); min_step = 10 * ulp(t)
+        const T min_step = (T)10 * (sizeof(T) == 8 ? (T)(::nextafter((double)t, CUDART_INF) - (double)t)
+                                                   : (T)(::nextafterf((float)t, CUDART_INF_F) - (float)t));
+        if (h_abs < min_step) h_abs = min_step;
+        bool accepted = false, rejected = false;
+        T t_new = t;
+        while (!accepted) {
+            if (h_abs < min_step) return 0;   // TOO_SMALL_STEP: solve_ivp status -1, ignored by pyfly
+            T h = h_abs;
+            t_new = t + h;
+            if (t_new - t_bound > (T)0) t_new = t_bound;
+            h = t_new - t;
+            h_abs = M<T>::fabs(h);
+            natt++;
+            // rk_step (rk.py:14-73): stages 1..5, then stage 6 = f(y_new)
+#pragma unroll 1
+            for (int s = 1; s <= 6; ++s) {
+                T acc[FW_NY];
+#pragma unroll
+                for (int i = 0; i < FW_NY; ++i) acc[i] = 0;
+#pragma unroll 1
+                for (int j = 0; j < s; ++j) {
+                    const T a = (T)RK_A[s][j];
+#pragma unroll
+                    for (int i = 0; i < FW_NY; ++i) acc[i] += KS(j, i) * a;
+                }
+#pragma unroll
+                for (int i = 0; i < FW_NY; ++i) ys[i] = y[i] + acc[i] * h;
+                rc = rhs<T, TURB>(c, x, ys, false, elev0, ail0, dyv);
+                nfev++;
+                if (rc) return rc;
+#pragma unroll
+                for (int i = 0; i < FW_NY; ++i) KS(s, i) = dyv[i];
+            }
+            // ys == y_new, dyv == f_new; error estimate (rk.py:100-104,139-141)
+            T errsq = 0;
+#pragma unroll
+            for (int i = 0; i < FW_NY; ++i) {
+                T acc = 0;
+#pragma unroll
+                for (int j = 0; j < 7; ++j) acc += KS(j, i) * (T)RK_E[j];
+                const T scl = atol + M<T>::fmax(M<T>::fabs(y[i]), M<T>::fabs(ys[i])) * rtol;
+                const T ei = acc * h / scl;
+                errsq += ei * ei;
+            }
+            const T err = M<T>::sqrt(errsq) / M<T>::sqrt((T)FW_NY);
+            if (err < (T)1) {
+                T factor = (err == (T)0) ? (T)10 : M<T>::fmin((T)10, (T)0.9 * M<T>::pow(err, (T)-0.2));
+                if (rejected) factor = M<T>::fmin((T)1, factor);
+                h_abs *= factor;
+                accepted = true;
+            } else {
+                h_abs *= M<T>::fmax((T)0.2, (T)0.9 * M<T>::pow(err, (T)-0.2));
+                rejected = true;
+            }
+        }
+        t = t_new;
+#pragma unroll
+        for (int i = 0; i < FW_NY; ++i) { y[i] = ys[i]; KS(0, i) = dyv[i]; }   // FSAL
+    }
+    return 0;
+#undef KS
+}
+
+// classical RK4 x substeps, register resident (throughput mode; same RHS with its clip/constraint side effects)
+template <typename T, bool TURB>
+__device__ __forceinline__ int solve_rk4(const DCfg<T>& c, const DynCtx<T>& x, T (&y)[FW_NY], T elev0, T ail0,
+                                         int& nfev, int& natt) {
+    const int n = c.rk4_substeps > 0 ? c.rk4_substeps : 1;
+    const T h = c.dt / (T)n;
+    T k[FW_NY], acc[FW_NY], ys[FW_NY];
+    int rc;
+    nfev = 0;
+    natt = n;
+#pragma unroll 1
+    for (int s = 0; s < n; ++s) {
+        if ((rc = rhs<T, TURB>(c, x, y, s == 0, elev0, ail0, k))) return rc;
+#pragma unroll
+        for (int i = 0; i < FW_NY; ++i) { acc[i] = k[i]; ys[i] = y[i] + (T)0.5 * h * k[i]; }
+        if ((rc = rhs<T, TURB>(c, x, ys, false, elev0, ail0, k))) return rc;
+#pragma unroll
+        for (int i = 0; i < FW_NY; ++i) { acc[i] += (T)2 * k[i]; ys[i] = y[i] + (T)0.5 * h * k[i]; }
+        if ((rc = rhs<T, TURB>(c, x, ys, false, elev0, ail0, k))) return rc;
+#pragma unroll
+        for (int i = 0; i < FW_NY; ++i) { acc[i] += (T)2 * k[i]; ys[i] = y[i] + h * k[i]; }
+        if ((rc = rhs<T, TURB>(c, x, ys, false, elev0, ail0, k))) return rc;
+#pragma unroll
+        for (int i = 0; i < FW_NY; ++i) y[i] = y[i] + h / (T)6 * (acc[i] + k[i]);
+        nfev += 4;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// gym-level helpers
+
+template <typename T> __device__ __forceinline__ T py_mod(T a, T b) {
+    T m = M<T>::fmod(a, b);
+    if (m != (T)0 && ((m < (T)0) != (b < (T)0))) m += b;
+    return m;
+}
+// _get_error (fixed_wing.py:1318-1344); roll wraps (pyfly_config.json "wrap": true)
+template <typename T> __device__ __forceinline__ T err_roll(T target, T value) {
+    const T PI = (T)3.141592653589793238462643383279502884;
+    T dist = py_mod(value - target + PI, (T)2 * PI) - PI;
+    if (dist < -PI) dist += (T)2 * PI;
+    return dist;
+}
+
+// numpy pairwise-sum order for n <= 128 (see oracle np_sum_*): matters only for the float32 action path
+template <typename F> __device__ __forceinline__ F np_sum(const F* a, int n) {
+    if (n < 8) { F s = 0; for (int i = 0; i < n; ++i) s += a[i]; return s; }
+    F r[8];
+    for (int j = 0; j < 8; ++j) r[j] = a[j];
+    int i;
+    for (i = 8; i < n - (n % 8); i += 8) for (int j = 0; j < 8; ++j) r[j] += a[i + j];
+    F res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < n; ++i) res += a[i];
+    return res;
+}
+
+// register-resident view of one env during a step
+template <typename T> struct EnvRegs {
+    T y[FW_NY];
+    T roll, pitch, Va, alpha, beta;
+    T wind[3], tgt[3];
+    int steps, steps_tgt, sim_step;
+    unsigned long long episode;
+};
+
+// advance the six shaping filters by one sample and evaluate y = C x + D u  (lsim recurrence, dryden.py:22-39)
+template <typename T>
+__device__ __forceinline__ void turb_eval(const DCfg<T>& c, const T fx[12], const T fu[4], T tl[3], T ta[3]) {
+#pragma unroll
+    for (int f = 0; f < 6; ++f) {
+        const DFilter<T>& F = c.filt[f];
+        T yv = 0;
+        for (int a = 0; a < F.order; ++a) yv += fx[FX_OFF[f] + a] * F.C[a];
+        yv += fu[F.noise_row] * F.D;
+        if (f < 3) tl[f] = yv; else ta[f - 3] = yv;
+    }
+}
+template <typename T>
+__device__ __forceinline__ void turb_advance(const DCfg<T>& c, T fx[12], T fu[4], const T un[4]) {
+#pragma unroll
+    for (int f = 0; f < 6; ++f) {
+        const DFilter<T>& F = c.filt[f];
+        const int n = F.order, o = FX_OFF[f];
+        T xn[3];
+        for (int a = 0; a < n; ++a) {
+            T s = 0;
+            for (int b = 0; b < n; ++b) s += fx[o + b] * F.Ad[b * n + a];
+            xn[a] = s + fu[F.noise_row] * F.Bd0[a] + un[F.noise_row] * F.Bd1[a];
+        }
+        for (int a = 0; a < n; ++a) fx[o + a] = xn[a];
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) fu[r] = un[r];
+}
+
+// scaled noise sample k for env (injected buffer or Philox)
+template <typename T>
+__device__ __forceinline__ void noise_sample(const DCfg<T>& c, const Soa<T>& S, int env, unsigned long long episode,
+                                             int k, T un[4]) {
+    double z[4];
+    if (S.noise) {
+        const int kk = k < S.noise_len ? k : S.noise_len - 1;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) z[r] = S.noise[((size_t)env * 4 + r) * S.noise_len + kk];
+    } else {
+        rng_noise4(c.seed, c.env_id_offset + env, episode, (uint32_t)k, z);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) un[r] = (T)z[r] * c.turb_noise_scale;
+}
+
+// sample_target (fixed_wing.py:654-746), constant / compensate classes
+template <typename T>
+__device__ __forceinline__ void sample_target(const DCfg<T>& c, T roll, T pitch, T Va, const T u3[3], T tgt[3]) {
+    const T val[3] = {roll, pitch, Va};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        T low = c.tgt_low[k], high = c.tgt_high[k];
+        if (!M<T>::isnan(c.tgt_delta[k])) {
+            low = M<T>::fmax(low, val[k] - c.tgt_delta[k]);
+            high = M<T>::fmax(M<T>::fmin(high, val[k] + c.tgt_delta[k]), low);
+        }
+        tgt[k] = low + (high - low) * u3[k];
+    }
+}
+
+// observation (fixed_wing.py:1113-1262, default 14-vector)
+template <typename T>
+__device__ __forceinline__ void write_obs(const T o[FW_NOBS], int env, float* obs, double* obs64) {
+    if (obs) {
+#pragma unroll
+        for (int j = 0; j < FW_NOBS; ++j) obs[(size_t)env * FW_NOBS + j] = (float)o[j];
+    }
+    if (obs64) {
+#pragma unroll
+        for (int j = 0; j < FW_NOBS; ++j) obs64[(size_t)env * FW_NOBS + j] = (double)o[j];
+    }
+}
+
+// FixedWingAircraft.reset -> PyFly.reset for one env; writes the full SoA row and the reset observation.
+template <typename T>
+__device__ void reset_env(const DCfg<T>& c, const Soa<T>& S, int env, const double* state_in, const double* target_in,
+                          float* obs, double* obs64) {
+    const int n = S.n;
+    const unsigned long long episode = (unsigned long long)(uint32_t)S.i[IF_EPISODE * n + env] + 1ull;
+    const long long gid = c.env_id_offset + env;
+    T s12[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        const double inj = state_in ? state_in[(size_t)env * FW_NSTATE_INJECT + i] : CUDART_NAN;
+        s12[i] = ::isnan(inj) ? c.init_lo[i] + (c.init_hi[i] - c.init_lo[i]) * rng_uniform<T>(c.seed, gid, episode, RNG_RESET, i)
+                              : (T)inj;
+    }
+    T a6[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const double inj = state_in ? state_in[(size_t)env * FW_NSTATE_INJECT + 12 + i] : CUDART_NAN;
+        a6[i] = ::isnan(inj) ? (T)0 : (T)inj;
+    }
+    a6[0] = clip(a6[0], c.elevon_min, c.elevon_max);
+    a6[1] = clip(a6[1], c.elevon_min, c.elevon_max);
+    a6[2] = clip(a6[2], c.throttle_min, c.throttle_max);
+    a6[3] = clip(a6[3], -c.elevon_dot_max, c.elevon_dot_max);
+    a6[4] = clip(a6[4], -c.elevon_dot_max, c.elevon_dot_max);
+    T wind[3];
+    {
+        double w0 = state_in ? state_in[(size_t)env * FW_NSTATE_INJECT + 18] : CUDART_NAN;
+        double w1 = state_in ? state_in[(size_t)env * FW_NSTATE_INJECT + 19] : CUDART_NAN;
+        double w2 = state_in ? state_in[(size_t)env * FW_NSTATE_INJECT + 20] : CUDART_NAN;
+        if (!::isnan(w0) && !::isnan(w1) && !::isnan(w2)) { wind[0] = (T)w0; wind[1] = (T)w1; wind[2] = (T)w2; }
+        else {   // Wind.reset (pyfly.py:815-823)
+            const T mag = c.wind_mag_min + (c.wind_mag_max - c.wind_mag_min) * rng_uniform<T>(c.seed, gid, episode, RNG_RESET, 12);
+            const T w_n = -mag + (mag - -mag) * rng_uniform<T>(c.seed, gid, episode, RNG_RESET, 13);
+            const T w_e_max = M<T>::sqrt(mag * mag - w_n * w_n);
+            const T w_e = -w_e_max + (w_e_max - -w_e_max) * rng_uniform<T>(c.seed, gid, episode, RNG_RESET, 14);
+            wind[0] = w_n; wind[1] = w_e; wind[2] = M<T>::sqrt(mag * mag - w_n * w_n - w_e * w_e);
+        }
+    }
+    const T roll = s12[0], pitch = s12[1], yaw = s12[2];
+    // turbulence: x_0 = 0, u_0 = first noise sample; column 0 of the reference's tables is C.0 + D u_0
+    T fx[12], fu[4], tl[3] = {0, 0, 0}, ta[3] = {0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 12; ++i) fx[i] = 0;
+    if (c.turbulence) { noise_sample(c, S, env, episode, 0, fu); turb_eval(c, fx, fu, tl, ta); }
+    else { fu[0] = fu[1] = fu[2] = fu[3] = 0; }
+    // Va, alpha, beta from Euler + vel (pyfly.py:1297-1306)
+    T wb[3];
+    rot_euler_apply(roll, pitch, yaw, wind, wb);
+    const T a0 = s12[9] - (wb[0] + tl[0]), a1 = s12[10] - (wb[1] + tl[1]), a2 = s12[11] - (wb[2] + tl[2]);
+    T Va = M<T>::sqrt(a0 * a0 + a1 * a1 + a2 * a2);
+    const T alpha = M<T>::atan2(a2, a0), beta = M<T>::asin(a1 / Va);
+    if (Va < c.va_value_min) Va = c.va_value_min;
+    // AttitudeQuaternion._from_euler_angles (pyfly.py:714-737)
+    T sps, cps, sth, cth, sph, cph;
+    M<T>::sincos(yaw / (T)2, &sps, &cps);
+    M<T>::sincos(pitch / (T)2, &sth, &cth);
+    M<T>::sincos(roll / (T)2, &sph, &cph);
+    T y[FW_NY];
+    y[0] = cps * cth * cph + sps * sth * sph;
+    y[1] = cps * cth * sph - sps * sth * cph;
+    y[2] = cps * sth * cph + sps * cth * sph;
+    y[3] = sps * cth * cph - cps * sth * sph;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) y[4 + i] = s12[3 + i];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) y[13 + i] = a6[i];
+    // targets (fixed_wing.py:443-450)
+    T u3[3], tgt[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) u3[k] = rng_uniform<T>(c.seed, gid, episode, RNG_RESET, 15 + k);
+    sample_target(c, roll, pitch, Va, u3, tgt);
+    if (target_in) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const double tv = target_in[(size_t)env * 3 + k];
+            if (!::isnan(tv)) tgt[k] = (T)tv;
+        }
+    }
+    // ---- store ----
+    T* r = S.r + env;
+    int32_t* ii = S.i + env;
+#pragma unroll
+    for (int i = 0; i < FW_NY; ++i) r[(RF_Y + i) * n] = y[i];
+    r[RF_ROLL * n] = roll; r[RF_PITCH * n] = pitch; r[RF_VA * n] = Va; r[RF_ALPHA * n] = alpha; r[RF_BETA * n] = beta;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { r[(RF_WIND + k) * n] = wind[k]; r[(RF_TGT + k) * n] = tgt[k]; }
+#pragma unroll
+    for (int i = 0; i < 12; ++i) r[(RF_FX + i) * n] = fx[i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r[(RF_FU + i) * n] = fu[i];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) { r[(RF_ACT_RING + i) * n] = 0; r[(RF_CMD_RING + i) * n] = 0; }
+    r[RF_CV_SUM * n] = 0;
+    const T e[3] = {err_roll(tgt[0], roll), tgt[1] - pitch, tgt[2] - Va};
+    int gbits[4];
+    gbits[3] = 1;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        r[(RF_E0 + k) * n] = e[k]; r[(RF_ESUM + k) * n] = e[k]; r[(RF_EABS + k) * n] = M<T>::fabs(e[k]);
+        r[(RF_EMIN + k) * n] = e[k]; r[(RF_EMAX + k) * n] = e[k]; r[(RF_EPREV + k) * n] = M<T>::fabs(e[k]);
+        S.err_ring[(size_t)(0 * 3 + k) * n + env] = e[k];
+        gbits[k] = M<T>::fabs(e[k]) <= c.tgt_bound[k];
+        gbits[3] &= gbits[k];
+    }
+    r[RF_EP_RET * n] = 0;
+    ii[IF_STEPS * n] = 0; ii[IF_STEPS_TGT * n] = 0; ii[IF_EPISODE * n] = (int32_t)episode; ii[IF_SIM_STEP * n] = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        ii[(IF_GOAL_RING + 4 * k) * n] = gbits[k];
+        ii[(IF_GOAL_RING + 4 * k + 1) * n] = 0; ii[(IF_GOAL_RING + 4 * k + 2) * n] = 0; ii[(IF_GOAL_RING + 4 * k + 3) * n] = 0;
+        ii[(IF_GOAL_CNT + k) * n] = gbits[k];
+        ii[(IF_GOAL_TOTAL + k) * n] = gbits[k];
+        ii[(IF_SETTLE + k) * n] = (c.streak_req == 1 && (double)gbits[k] >= (double)c.streak_fraction) ? 0 : -1;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { ii[(IF_RISE_LO + k) * n] = -1; ii[(IF_RISE_HI + k) * n] = -1; }
+    ii[IF_NFEV * n] = 0; ii[IF_NATT * n] = 0; ii[IF_ACT_F32 * n] = 0;
+    // reset observation: action entries are the actuator values mapped backward (fixed_wing.py:1188-1196);
+    // elevator/aileron read 0 right after reset (disabled ControlVariable.reset, pyfly.py:359-363)
+    T o[FW_NOBS] = {roll, pitch, Va, y[4], y[5], y[6], tgt[0], tgt[1], tgt[2], alpha, beta, 0, 0, 0};
+    const T av[3] = {(T)0, (T)0, a6[2]};
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+        o[11 + j] = c.scale_actions ? (c.scale_high - c.scale_low) * (av[j] - c.act_lo[j]) / (c.act_hi[j] - c.act_lo[j]) + c.scale_low
+                                    : av[j];
+    write_obs(o, env, obs, obs64);
+}
+
+}  // namespace fw

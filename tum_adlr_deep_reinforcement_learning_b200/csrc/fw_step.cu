@@ -1,0 +1,769 @@
+// fw_step.cu — the fused env-step kernel, the reset kernel and the C ABI of libfwb200.so (see include/fwb200.h).
+//
+// One launch of step_kernel == one VecEnv.step over every env of the handle:
+//   action scaling -> command constraint -> integrator (scipy-RK45 replica or RK4xN) -> post-step commit
+//   (quaternion renormalisation, Euler angles, Va/alpha/beta, constraint checks) -> Dryden filter advance ->
+//   goal ring / streak test -> reward -> target law -> observation -> termination -> streamed episode metrics ->
+//   auto-reset (Philox).  Nothing leaves the SM between these stages.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "fw_device.cuh"
+
+namespace fw {
+
+struct StepIO {
+    const void* actions;   // [n,3] f32 or f64
+    int actions_f64;
+    float* obs;            // [n,14]
+    float* rew;            // [n]
+    uint8_t* done;         // [n]
+    float* term_obs;       // [n,14] nullable
+    double* obs64;         // nullable
+    double* rew64;         // nullable
+    int auto_reset;
+    int random_actions;    // 1: draw U(-1,1)^3 from Philox (fw_step_random)
+    unsigned long long action_seed;
+    unsigned long long action_step;
+};
+
+template <typename T>
+__device__ __noinline__ void reset_env_noinline(const DCfg<T>& c, const Soa<T>& S, int env, float* obs, double* obs64) {
+    reset_env<T>(c, S, env, nullptr, nullptr, obs, obs64);
+}
+
+template <typename T>
+__global__ void reset_kernel(const __grid_constant__ DCfg<T> c, const Soa<T> S, const uint8_t* mask,
+                             const double* state_in, const double* target_in, float* obs, double* obs64) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= S.n) return;
+    if (mask && !mask[env]) return;
+    reset_env<T>(c, S, env, state_in, target_in, obs, obs64);
+}
+
+// sum |diff| of one column over the trailing window, accumulated in float32 like
+// np.sum(np.abs(np.diff(...)), dtype=np.float32) (fixed_wing.py:1198-1228)
+template <typename T>
+__device__ __forceinline__ T delta_feature(const T cur, const T* ring /* [4][3] strided by 3 */, int col, int n_prev,
+                                           bool f32) {
+    // chronological order: oldest previous ... most recent previous, current
+    float s = 0.f;
+    T newer;
+#pragma unroll
+    for (int age = 4; age >= 1; --age) {
+        if (age <= n_prev) {
+            const T older = ring[(age - 1) * 3 + col];
+            newer = (age == 1) ? cur : ring[(age - 2) * 3 + col];
+            const float d = f32 ? fabsf((float)newer - (float)older) : (float)M<T>::fabs(newer - older);
+            s += d;
+        }
+    }
+    return (T)s;
+}
+
+template <typename T, int INTEG, bool TURB, int NT>
+__global__ void __launch_bounds__(NT) step_kernel(const __grid_constant__ DCfg<T> c, const Soa<T> S, const StepIO io) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int env = blockIdx.x * NT + threadIdx.x;
+    const int n = S.n;
+    if (env >= n) return;
+    T* r = S.r + env;
+    int32_t* ii = S.i + env;
+
+    // ---------------- load ----------------
+    T y[FW_NY];
+#pragma unroll
+    for (int i = 0; i < FW_NY; ++i) y[i] = r[(RF_Y + i) * n];
+    const T roll_prev = r[RF_ROLL * n], pitch_prev = r[RF_PITCH * n], Va_prev = r[RF_VA * n];
+    const T alpha_prev = r[RF_ALPHA * n], beta_prev = r[RF_BETA * n];
+    const T omega_prev[3] = {y[4], y[5], y[6]};
+    DynCtx<T> x;
+    T tgt[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { x.wind[k] = r[(RF_WIND + k) * n]; tgt[k] = r[(RF_TGT + k) * n]; }
+    int steps = ii[IF_STEPS * n], steps_tgt = ii[IF_STEPS_TGT * n], sim_step = ii[IF_SIM_STEP * n];
+    const unsigned long long episode = (unsigned long long)(uint32_t)ii[IF_EPISODE * n];
+    T fx[12], fu[4];
+    if (TURB) {
+#pragma unroll
+        for (int i = 0; i < 12; ++i) fx[i] = r[(RF_FX + i) * n];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) fu[i] = r[(RF_FU + i) * n];
+        turb_eval(c, fx, fu, x.tl, x.ta);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { x.tl[k] = 0; x.ta[k] = 0; }
+    }
+
+    // ---------------- action (fixed_wing.py:491-506) ----------------
+    T a_raw[3];
+    bool act_f32;
+    if (io.random_actions) {
+        const uint4 rr = rng_block(io.action_seed, c.env_id_offset + env, io.action_step >> 32, RNG_ACTION,
+                                   (uint32_t)io.action_step);
+        const uint32_t w[3] = {rr.x, rr.y, rr.z};
+#pragma unroll
+        for (int j = 0; j < 3; ++j) a_raw[j] = (T)(float)(((double)w[j] + 0.5) * (2.0 / 4294967296.0) - 1.0);
+        act_f32 = true;
+    } else if (io.actions_f64) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) a_raw[j] = (T)((const double*)io.actions)[(size_t)env * 3 + j];
+        act_f32 = false;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) a_raw[j] = (T)((const float*)io.actions)[(size_t)env * 3 + j];
+        act_f32 = true;
+    }
+    T a_cmd[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        if (c.scale_actions) {   // linear_action_scaling(clip(action)) (fixed_wing.py:497-504, 630-652)
+            const T cl = clip(a_raw[j], c.scale_low, c.scale_high);
+            const T num = act_f32 ? (T)((float)cl - (float)c.scale_low) : (cl - c.scale_low);
+            a_cmd[j] = (c.act_hi[j] - c.act_lo[j]) * num / (c.scale_high - c.scale_low) + c.act_lo[j];
+        } else {
+            a_cmd[j] = a_raw[j];
+        }
+    }
+    // Actuation.set_and_constrain_commands (pyfly.py:545-582)
+    x.cmd[0] = clip(-a_cmd[1] + a_cmd[0], c.elevon_min, c.elevon_max);
+    x.cmd[1] = clip(a_cmd[1] + a_cmd[0], c.elevon_min, c.elevon_max);
+    x.cmd[2] = clip(a_cmd[2], c.throttle_min, c.throttle_max);
+    T cmd_in[3];
+    cmd_in[0] = clip((x.cmd[0] + x.cmd[1]) / (T)2, c.act_lo[0], c.act_hi[0]);
+    cmd_in[1] = clip((-x.cmd[0] + x.cmd[1]) / (T)2, c.act_lo[1], c.act_hi[1]);
+    cmd_in[2] = x.cmd[2];
+
+    // ---------------- integrate (pyfly.py:1372-1396) ----------------
+    // elevator/aileron seen by the t == 0 RHS call: 0 right after a reset (disabled ControlVariable.reset)
+    T elev0 = 0, ail0 = 0;
+    if (steps > 0) {
+        const T er = clip(y[13], c.elevon_min, c.elevon_max), el = clip(y[14], c.elevon_min, c.elevon_max);
+        elev0 = (er + el) / (T)2;
+        ail0 = (-er + el) / (T)2;
+    }
+    int nfev = 0, natt = 0, fail;
+    if (INTEG == FW_INT_RK45_SCIPY) {
+        T* K = reinterpret_cast<T*>(smem_raw) + threadIdx.x;
+        fail = solve_rk45<T, TURB, NT>(c, x, y, elev0, ail0, K, nfev, natt);
+    } else {
+        fail = solve_rk4<T, TURB>(c, x, y, elev0, ail0, nfev, natt);
+    }
+
+    // ---------------- post-step commit (pyfly.py:1396-1406, 1852-1881) ----------------
+    T roll = roll_prev, pitch = pitch_prev, Va = Va_prev, alpha = alpha_prev, beta = beta_prev;
+    T om_obs[3] = {omega_prev[0], omega_prev[1], omega_prev[2]};   // .history[-1] view for a terminal observation
+    if (!fail) {
+        const T nrm = M<T>::sqrt(y[0] * y[0] + y[1] * y[1] + y[2] * y[2] + y[3] * y[3]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) y[i] = y[i] / nrm;
+        const T e0 = y[0], e1 = y[1], e2 = y[2], e3 = y[3];
+        roll = M<T>::atan2((T)2 * (e0 * e1 + e2 * e3), e0 * e0 + e3 * e3 - e1 * e1 - e2 * e2);
+        pitch = M<T>::asin((T)2 * (e0 * e2 - e1 * e3));
+        const T yaw = M<T>::atan2((T)2 * (e0 * e3 + e1 * e2), e0 * e0 + e1 * e1 - e2 * e2 - e3 * e3);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            if (!fail) {
+                if (y[4 + i] < c.omega_con_min[i] || y[4 + i] > c.omega_con_max[i]) fail = FW_TERM_OMEGA_P + i;
+                else om_obs[i] = y[4 + i];
+            }
+        }
+        if (!fail) {
+            y[13] = clip(y[13], c.elevon_min, c.elevon_max);
+            y[14] = clip(y[14], c.elevon_min, c.elevon_max);
+            y[15] = clip(y[15], c.throttle_min, c.throttle_max);
+            y[16] = clip(y[16], -c.elevon_dot_max, c.elevon_dot_max);
+            y[17] = clip(y[17], -c.elevon_dot_max, c.elevon_dot_max);
+            T wb[3];
+            rot_euler_apply(roll, pitch, yaw, x.wind, wb);
+            const T a0 = y[10] - (wb[0] + x.tl[0]), a1 = y[11] - (wb[1] + x.tl[1]), a2 = y[12] - (wb[2] + x.tl[2]);
+            T Van = M<T>::sqrt(a0 * a0 + a1 * a1 + a2 * a2);
+            const T al = M<T>::atan2(a2, a0), be = M<T>::asin(a1 / Van);
+            if (c.va_con_max > (T)0 && Van > c.va_con_max) fail = FW_TERM_VA;
+            else {
+                if (Van < c.va_value_min) Van = c.va_value_min;
+                Va = Van; alpha = al; beta = be;
+            }
+        }
+    }
+    sim_step += 1;
+
+    // ---------------- gym head (fixed_wing.py:512-628) ----------------
+    const int steps_before = steps;
+    steps += 1;
+    steps_tgt += 1;
+    bool done = false;
+    int term = FW_TERM_NONE;
+    if (c.steps_max > 0 && steps >= c.steps_max) { done = true; term = FW_TERM_STEPS; }
+
+    // action / command rings: previous entries (age 1 = most recent)
+    T aring[12], cring[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) aring[i] = r[(RF_ACT_RING + i) * n];
+    const bool need_cring = !c.scale_actions;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) cring[i] = (need_cring || i < 3) ? r[(RF_CMD_RING + i) * n] : (T)0;
+    T cv_sum = r[RF_CV_SUM * n];
+    if (steps_before >= 1) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) cv_sum += M<T>::fabs(cmd_in[j] - cring[j]);
+    }
+    const int n_prev = steps_before < 4 ? steps_before : 4;   // valid previous ring entries
+
+    T e_new[3] = {0, 0, 0};
+    T reward;
+    T obs_v[FW_NOBS];
+    int gbits[4] = {0, 0, 0, 0};
+    int gcnt[4], gtot[4], settle[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        gcnt[k] = ii[(IF_GOAL_CNT + k) * n]; gtot[k] = ii[(IF_GOAL_TOTAL + k) * n]; settle[k] = ii[(IF_SETTLE + k) * n];
+    }
+    if (!fail) {
+        // goal status with the CURRENT target (fixed_wing.py:536-560)
+        const T eg[3] = {err_roll(tgt[0], roll), tgt[1] - pitch, tgt[2] - Va};
+        bool resample = false;
+        if (c.streak_req > 0) {
+            gbits[3] = 1;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { gbits[k] = M<T>::fabs(eg[k]) <= c.tgt_bound[k]; gbits[3] &= gbits[k]; }
+            const int idx = steps;                 // index of this entry in history["goal"] (entry 0 = reset)
+            const int w = (idx & 127) >> 5, b = idx & 31;
+            const int idx_old = idx - c.streak_req;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                int32_t* ring = ii + (IF_GOAL_RING + 4 * k) * n;
+                if (idx_old >= 0) gcnt[k] -= (ring[((idx_old & 127) >> 5) * n] >> (idx_old & 31)) & 1;
+                uint32_t word = (uint32_t)ring[w * n];
+                word = (word & ~(1u << b)) | ((uint32_t)gbits[k] << b);
+                ring[w * n] = (int32_t)word;
+                gcnt[k] += gbits[k];
+                gtot[k] += gbits[k];
+                if (settle[k] < 0 && idx + 1 >= c.streak_req &&
+                    (double)gcnt[k] / (double)c.streak_req >= (double)c.streak_fraction) settle[k] = idx;
+            }
+            if (steps_tgt >= c.streak_req && (double)gcnt[3] / (double)c.streak_req >= (double)c.streak_fraction) {
+                if (c.on_success == FW_SUCCESS_DONE) { done = true; term = FW_TERM_SUCCESS; }
+                else if (c.on_success == FW_SUCCESS_NEW) resample = true;
+            }
+        }
+        // reward (fixed_wing.py:941-1111, default factor family)
+        T val = 0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            if (c.rew_err_scaling[k] > (T)0) val -= clip(M<T>::fabs(eg[k]) / c.rew_err_scaling[k], (T)0, c.rew_err_max[k]);
+        if (c.rew_delta_scaling > (T)0 && steps > 1) {
+            const int np_ = (c.rew_delta_window - 1) < n_prev ? (c.rew_delta_window - 1) : n_prev;
+            T dv;
+            if (act_f32) {
+                float d[12];
+                int m = 0;
+                for (int age = np_; age >= 1; --age)
+                    for (int j = 0; j < 3; ++j) {
+                        const T newer = (age == 1) ? a_raw[j] : aring[(age - 2) * 3 + j];
+                        d[m++] = fabsf((float)newer - (float)aring[(age - 1) * 3 + j]);
+                    }
+                const float s = np_sum<float>(d, m);
+                dv = (T)fminf(fmaxf(s / (float)c.rew_delta_scaling, 0.f), (float)c.rew_delta_max);
+            } else {
+                T d[12];
+                int m = 0;
+                for (int age = np_; age >= 1; --age)
+                    for (int j = 0; j < 3; ++j) {
+                        const T newer = (age == 1) ? a_raw[j] : aring[(age - 2) * 3 + j];
+                        d[m++] = M<T>::fabs(newer - aring[(age - 1) * 3 + j]);
+                    }
+                dv = clip(np_sum<T>(d, m) / c.rew_delta_scaling, (T)0, c.rew_delta_max);
+            }
+            val -= dv;
+        }
+        if (c.rew_bound_scaling > (T)0 && c.has_action_bounds) {
+            T hi = 0, lo = 0;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                if (a_raw[j] > c.action_bounds_max[j]) hi += M<T>::fabs(a_raw[j] - c.action_bounds_max[j]);
+                if (a_raw[j] < c.action_bounds_min[j]) lo += M<T>::fabs(a_raw[j] - c.action_bounds_min[j]);
+            }
+            val -= clip(M<T>::fabs(hi + lo) / c.rew_bound_scaling, (T)0, c.rew_bound_max);
+        }
+        reward = val;
+        // target resample / advance (fixed_wing.py:569-580, 1363-1471)
+        if (resample || (c.resample_every > 0 && steps_tgt >= c.resample_every)) {
+            T u3[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const uint4 rr = rng_block(c.seed, c.env_id_offset + env, episode, RNG_RESAMPLE, (uint32_t)(steps * 2 + (k >> 1)));
+                u3[k] = (T)((k & 1) ? u53(rr.z, rr.w) : u53(rr.x, rr.y));
+            }
+            sample_target(c, roll, pitch, Va, u3, tgt);
+            steps_tgt = 0;
+        }
+        if (c.tgt_class[2] == FW_TGT_COMPENSATE) {
+            const T pitch_tar = tgt[1], va_t = tgt[2];
+            const T D2R = (T)(3.141592653589793238462643383279502884 / 180.0);
+            if (pitch_tar <= (T)-2.5 * D2R) {
+                const T va_end = (T)28.434 - (T)40.0841 * pitch_tar;
+                T slope = 0;
+                if (va_t <= va_end) {
+                    const T s = (va_t < va_end * (T)0.95) ? (T)1 : (T)1 - va_t / (va_end * (T)1.5);
+                    slope = (T)7 * M<T>::fmax((T)0, s);
+                }
+                tgt[2] = va_t + (slope * (-tgt[1]) - (T)0.25) * c.dt;
+            } else if (pitch_tar >= (T)5 * D2R) {
+                const T va_end = (T)26.27 - (T)41.2529 * pitch_tar;
+                if (va_t > va_end) tgt[2] = (steps_tgt < 750) ? va_t + (va_end - va_t) * (T)1 / (T)150 : va_end;
+            }
+        }
+        {
+            const T PI = (T)3.141592653589793238462643383279502884;
+            if (M<T>::fabs(tgt[0]) > PI) tgt[0] = sgn(tgt[0]) * (py_mod(M<T>::fabs(tgt[0]), PI) - PI);
+        }
+        e_new[0] = err_roll(tgt[0], roll); e_new[1] = tgt[1] - pitch; e_new[2] = tgt[2] - Va;
+    } else {
+        done = true;
+        term = fail;
+        reward = c.step_fail_timesteps ? (T)(steps - c.steps_max) : c.step_fail_value;
+    }
+
+    // ---------------- observation (fixed_wing.py:1113-1262) ----------------
+    obs_v[0] = roll; obs_v[1] = pitch; obs_v[2] = Va;
+    obs_v[3] = om_obs[0]; obs_v[4] = om_obs[1]; obs_v[5] = om_obs[2];
+    obs_v[6] = tgt[0]; obs_v[7] = tgt[1]; obs_v[8] = tgt[2];
+    obs_v[9] = alpha; obs_v[10] = beta;
+    {
+        const int np_ = (c.obs_act_window - 1) < n_prev ? (c.obs_act_window - 1) : n_prev;
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            obs_v[11 + j] = c.scale_actions ? delta_feature<T>(a_raw[j], aring, j, np_, act_f32)
+                                            : delta_feature<T>(cmd_in[j], cring, j, np_, false);
+    }
+
+    // ---------------- streamed episode statistics (fixed_wing.py:1644-1736) ----------------
+    T esum[3], eabs[3], emin[3], emax[3], e0v[3];
+    int rise_lo[3], rise_hi[3];
+    const T ep_ret = r[RF_EP_RET * n] + reward;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        e0v[k] = r[(RF_E0 + k) * n]; esum[k] = r[(RF_ESUM + k) * n]; eabs[k] = r[(RF_EABS + k) * n];
+        emin[k] = r[(RF_EMIN + k) * n]; emax[k] = r[(RF_EMAX + k) * n];
+        rise_lo[k] = ii[(IF_RISE_LO + k) * n]; rise_hi[k] = ii[(IF_RISE_HI + k) * n];
+    }
+    int n_err = steps_before + 1;           // entries in history["error"] before this step
+    if (!fail) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const T ea = M<T>::fabs(e_new[k]), prev = r[(RF_EPREV + k) * n];
+            const T low_lim = M<T>::fabs(c.rise_low * e0v[k]), high_lim = M<T>::fabs(c.rise_high * e0v[k]);
+            if (rise_lo[k] < 0 && prev >= low_lim && ea < low_lim) rise_lo[k] = n_err - 1;
+            if (rise_hi[k] < 0 && prev >= high_lim && ea < high_lim) rise_hi[k] = n_err - 1;
+            esum[k] += e_new[k]; eabs[k] += ea;
+            emin[k] = M<T>::fmin(emin[k], e_new[k]); emax[k] = M<T>::fmax(emax[k], e_new[k]);
+            r[(RF_EPREV + k) * n] = ea;
+            S.err_ring[(size_t)((n_err % FW_END_ERR_WINDOW) * 3 + k) * n + env] = e_new[k];
+        }
+        n_err += 1;
+    }
+
+    if (done) {
+        double* m = S.metrics + (size_t)env * FW_NMETRIC;
+        const int off = steps - (n_err - 1);     // rise index offset: 0 normally, 1 after a failed step
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const T e0 = e0v[k];
+            m[FW_M_AVG_ERROR + k] = (M<T>::fabs(e0) >= (T)0.01) ? (double)M<T>::fabs((esum[k] / (T)n_err) / e0) : CUDART_NAN;
+            m[FW_M_TOTAL_ERROR + k] = (double)eabs[k];
+            const int cnt = n_err < FW_END_ERR_WINDOW ? n_err : FW_END_ERR_WINDOW;
+            T s50 = 0;
+            for (int q = 0; q < cnt; ++q) {
+                const int slot = (n_err - cnt + q) % FW_END_ERR_WINDOW;
+                s50 += (slot == ((n_err - 1) % FW_END_ERR_WINDOW) && !fail) ? e_new[k]
+                                                                             : S.err_ring[(size_t)(slot * 3 + k) * n + env];
+            }
+            m[FW_M_END_ERROR + k] = (double)M<T>::fabs(s50 / (T)cnt);
+            const double re = rise_lo[k] >= 0 ? (double)(rise_lo[k] + off) : CUDART_NAN;
+            const double rs = rise_hi[k] >= 0 ? (double)(rise_hi[k] + off) : CUDART_NAN;
+            m[FW_M_RISE_TIME + k] = re - rs;
+            const T opp = (e0 > (T)0) ? emin[k] : emax[k];
+            m[FW_M_OVERSHOOT + k] = (sgn(opp) == sgn(e0)) ? CUDART_NAN : (double)M<T>::fabs(opp / e0);
+        }
+        m[FW_M_CONTROL_VARIATION] = (double)cv_sum / (3.0 * (double)c.dt * (double)(steps - 1));
+        const int n_goal = fail ? steps : steps + 1;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            m[FW_M_SUCCESS + k] = settle[k] >= 0 ? 1.0 : 0.0;
+            m[FW_M_SETTLING_TIME + k] = settle[k] >= 0 ? (double)settle[k] : CUDART_NAN;
+            m[FW_M_SUCCESS_TIME_FRAC + k] = (double)gtot[k] / (double)n_goal;
+        }
+        S.ep_ret[env] = (double)ep_ret;
+        S.ep_len[env] = steps;
+    }
+    S.ep_term[env] = term;
+
+    // ---------------- outputs ----------------
+    if (io.rew) io.rew[env] = (float)reward;
+    if (io.rew64) io.rew64[env] = (double)reward;
+    if (io.done) io.done[env] = done ? 1 : 0;
+    ii[IF_NFEV * n] = nfev;
+    ii[IF_NATT * n] = natt;
+
+    if (done && io.auto_reset) {
+        if (io.term_obs) write_obs(obs_v, env, io.term_obs, (double*)nullptr);
+        reset_env_noinline<T>(c, S, env, io.obs, io.obs64);
+        // keep the diagnostics of the step that ended the episode
+        ii[IF_NFEV * n] = nfev;
+        ii[IF_NATT * n] = natt;
+        return;
+    }
+    write_obs(obs_v, env, io.obs, io.obs64);
+
+    // ---------------- store ----------------
+    if (TURB && !fail) {
+        T un[4];
+        noise_sample(c, S, env, episode, sim_step, un);
+        turb_advance(c, fx, fu, un);
+#pragma unroll
+        for (int i = 0; i < 12; ++i) r[(RF_FX + i) * n] = fx[i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) r[(RF_FU + i) * n] = fu[i];
+    }
+    if (!fail) {
+#pragma unroll
+        for (int i = 0; i < FW_NY; ++i) r[(RF_Y + i) * n] = y[i];
+        r[RF_ROLL * n] = roll; r[RF_PITCH * n] = pitch; r[RF_VA * n] = Va; r[RF_ALPHA * n] = alpha; r[RF_BETA * n] = beta;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        r[(RF_TGT + k) * n] = tgt[k];
+        r[(RF_ESUM + k) * n] = esum[k]; r[(RF_EABS + k) * n] = eabs[k];
+        r[(RF_EMIN + k) * n] = emin[k]; r[(RF_EMAX + k) * n] = emax[k];
+        ii[(IF_RISE_LO + k) * n] = rise_lo[k]; ii[(IF_RISE_HI + k) * n] = rise_hi[k];
+    }
+    // rings shift: age k -> age k+1, current -> age 1
+#pragma unroll
+    for (int i = 11; i >= 3; --i) r[(RF_ACT_RING + i) * n] = aring[i - 3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) r[(RF_ACT_RING + j) * n] = a_raw[j];
+    if (need_cring) {
+#pragma unroll
+        for (int i = 11; i >= 3; --i) r[(RF_CMD_RING + i) * n] = cring[i - 3];
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) r[(RF_CMD_RING + j) * n] = cmd_in[j];
+    r[RF_CV_SUM * n] = cv_sum;
+    r[RF_EP_RET * n] = ep_ret;
+    ii[IF_STEPS * n] = steps; ii[IF_STEPS_TGT * n] = steps_tgt; ii[IF_SIM_STEP * n] = sim_step;
+    ii[IF_ACT_F32 * n] = act_f32 ? 1 : 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        ii[(IF_GOAL_CNT + k) * n] = gcnt[k]; ii[(IF_GOAL_TOTAL + k) * n] = gtot[k]; ii[(IF_SETTLE + k) * n] = settle[k];
+    }
+}
+
+// gather / scatter between SoA fields and row-major [n, width] buffers
+template <typename T>
+__global__ void field_copy_kernel(const __grid_constant__ DCfg<T> c, Soa<T> S, int field, void* buf, int to_soa) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = S.n;
+    if (env >= n) return;
+    double* d = (double*)buf;
+    int32_t* di = (int32_t*)buf;
+    T* r = S.r + env;
+    int32_t* ii = S.i + env;
+    auto rw = [&](int rf, int width, int col0, int stride) {
+        for (int k = 0; k < width; ++k) {
+            if (to_soa) r[(rf + k) * n] = (T)d[(size_t)env * stride + col0 + k];
+            else d[(size_t)env * stride + col0 + k] = (double)r[(rf + k) * n];
+        }
+    };
+    switch (field) {
+        case FW_FIELD_Y: rw(RF_Y, FW_NY, 0, FW_NY); break;
+        case FW_FIELD_EULER:
+            // yaw is not stored (recomputed every step); report roll, pitch, NaN
+            rw(RF_ROLL, 2, 0, 3);
+            if (!to_soa) d[(size_t)env * 3 + 2] = CUDART_NAN;
+            break;
+        case FW_FIELD_VAB: rw(RF_VA, 3, 0, 3); break;
+        case FW_FIELD_WIND: rw(RF_WIND, 3, 0, 3); break;
+        case FW_FIELD_TARGET: rw(RF_TGT, 3, 0, 3); break;
+        case FW_FIELD_CMD: rw(RF_CMD_RING, 3, 0, 3); break;
+        case FW_FIELD_TURB:
+            if (!to_soa) {
+                T fx[12], fu[4], tl[3] = {0, 0, 0}, ta[3] = {0, 0, 0};
+                for (int i = 0; i < 12; ++i) fx[i] = r[(RF_FX + i) * n];
+                for (int i = 0; i < 4; ++i) fu[i] = r[(RF_FU + i) * n];
+                if (c.turbulence) turb_eval(c, fx, fu, tl, ta);
+                for (int i = 0; i < 3; ++i) { d[(size_t)env * 6 + i] = (double)tl[i]; d[(size_t)env * 6 + 3 + i] = (double)ta[i]; }
+            }
+            break;
+        case FW_FIELD_COUNTERS:
+            for (int k = 0; k < 4; ++k) {
+                const int f = (k == 0) ? IF_STEPS : (k == 1) ? IF_STEPS_TGT : (k == 2) ? IF_SIM_STEP : IF_EPISODE;
+                if (to_soa) ii[f * n] = di[(size_t)env * 4 + k];
+                else di[(size_t)env * 4 + k] = ii[f * n];
+            }
+            break;
+        case FW_FIELD_NFEV:
+            if (!to_soa) { di[(size_t)env * 2] = ii[IF_NFEV * n]; di[(size_t)env * 2 + 1] = ii[IF_NATT * n]; }
+            break;
+        default: break;
+    }
+}
+
+__global__ void episode_info_kernel(int n, const int32_t* term, const double* metrics, const double* ep_ret,
+                                    const int32_t* ep_len, int32_t* term_out, double* metrics_out, double* ret_out,
+                                    int32_t* len_out) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= n) return;
+    if (term_out) term_out[env] = term[env];
+    if (ret_out) ret_out[env] = ep_ret[env];
+    if (len_out) len_out[env] = ep_len[env];
+    if (metrics_out)
+        for (int k = 0; k < FW_NMETRIC; ++k) metrics_out[(size_t)env * FW_NMETRIC + k] = metrics[(size_t)env * FW_NMETRIC + k];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+static thread_local char g_err[512] = "";
+static void set_err(const char* what, cudaError_t e) { snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e)); }
+#define CK(call)                                   \
+    do {                                           \
+        cudaError_t e_ = (call);                   \
+        if (e_ != cudaSuccess) { set_err(#call, e_); return FW_ECUDA; } \
+    } while (0)
+
+template <typename T> static void convert_cfg(const FwConfig& f, DCfg<T>& d) {
+    memset(&d, 0, sizeof(d));
+    d.integrator = f.integrator; d.rk4_substeps = f.rk4_substeps; d.turbulence = f.turbulence;
+    d.steps_max = f.steps_max; d.scale_actions = f.scale_actions; d.has_action_bounds = f.has_action_bounds;
+    for (int k = 0; k < 3; ++k) d.tgt_class[k] = f.tgt_class[k];
+    d.on_success = f.on_success; d.streak_req = f.streak_req; d.resample_every = f.resample_every;
+    d.rew_delta_window = f.rew_delta_window; d.obs_act_window = f.obs_act_window;
+    d.step_fail_timesteps = f.step_fail_timesteps;
+    d.rtol = (T)f.rtol; d.atol = (T)f.atol;
+#define CP(x) d.x = (T)f.x
+    CP(mass); CP(Jy); CP(S_wing); CP(b); CP(c); CP(k_motor); CP(k_T_P); CP(k_Omega); CP(a_0);
+    d.M_ = (T)f.M;
+    d.ar = (T)(f.b * f.b / f.S_wing);
+    CP(C_L_0); CP(C_L_alpha); CP(C_L_q); CP(C_L_delta_e); CP(C_D_p); CP(C_D_q); CP(C_D_beta1); CP(C_D_beta2); CP(C_D_delta_e);
+    CP(C_m_0); CP(C_m_alpha); CP(C_m_q); CP(C_m_delta_e); CP(C_m_fp);
+    CP(C_Y_0); CP(C_Y_beta); CP(C_Y_p); CP(C_Y_r); CP(C_Y_delta_a); CP(C_Y_delta_r);
+    CP(C_l_0); CP(C_l_beta); CP(C_l_p); CP(C_l_r); CP(C_l_delta_a); CP(C_l_delta_r);
+    CP(C_n_0); CP(C_n_beta); CP(C_n_p); CP(C_n_r); CP(C_n_delta_a); CP(C_n_delta_r);
+    {   // gammas (pyfly.py:1099-1116), evaluated in double on the host
+        const double I00 = f.Jx, I11 = f.Jy, I22 = f.Jz, I02 = -f.Jxz;
+        double g[9];
+        g[0] = I00 * I22 - I02 * I02;
+        g[1] = (fabs(I02) * (I00 - I11 + I22)) / g[0];
+        g[2] = (I22 * (I22 - I11) + I02 * I02) / g[0];
+        g[3] = I22 / g[0];
+        g[4] = fabs(I02) / g[0];
+        g[5] = (I22 - I00) / I11;
+        g[6] = fabs(I02) / I11;
+        g[7] = ((I00 - I11) * I00 + I02 * I02) / g[0];
+        g[8] = I00 / g[0];
+        for (int k = 0; k < 9; ++k) d.gam[k] = (T)g[k];
+    }
+    d.half_rho = (T)(0.5 * f.rho);
+    d.mg = (T)(f.mass * f.g);
+    d.prop_k = (T)(0.5 * f.rho * f.S_prop * f.C_prop);
+    d.pi_e_ar = (T)(3.14159265358979323846 * f.e_oswald * (f.b * f.b / f.S_wing));
+    CP(dt); CP(elevon_min); CP(elevon_max); CP(elevon_dot_max); CP(throttle_min); CP(throttle_max);
+    d.w0sq = (T)(f.elevon_omega0 * f.elevon_omega0);
+    d.two_zeta_w0 = (T)(2 * f.elevon_zeta * f.elevon_omega0);
+    d.inv_tau = (T)(1 / f.throttle_tau);
+    for (int k = 0; k < 3; ++k) { CP(omega_con_min[k]); CP(omega_con_max[k]); }
+    CP(va_value_min); CP(va_con_max);
+    for (int k = 0; k < 12; ++k) { CP(init_lo[k]); CP(init_hi[k]); }
+    CP(wind_mag_min); CP(wind_mag_max); CP(turb_noise_scale);
+    for (int fi = 0; fi < 6; ++fi) {
+        d.filt[fi].order = f.filt[fi].order; d.filt[fi].noise_row = f.filt[fi].noise_row;
+        for (int k = 0; k < 9; ++k) d.filt[fi].Ad[k] = (T)f.filt[fi].Ad[k];
+        for (int k = 0; k < 3; ++k) { d.filt[fi].Bd0[k] = (T)f.filt[fi].Bd0[k]; d.filt[fi].Bd1[k] = (T)f.filt[fi].Bd1[k]; d.filt[fi].C[k] = (T)f.filt[fi].C[k]; }
+        d.filt[fi].D = (T)f.filt[fi].D;
+    }
+    CP(scale_low); CP(scale_high);
+    for (int k = 0; k < 3; ++k) {
+        CP(act_lo[k]); CP(act_hi[k]); CP(action_bounds_min[k]); CP(action_bounds_max[k]);
+        CP(tgt_low[k]); CP(tgt_high[k]); CP(tgt_delta[k]); CP(tgt_bound[k]); CP(rew_err_scaling[k]); CP(rew_err_max[k]);
+    }
+    CP(streak_fraction); CP(rew_delta_scaling); CP(rew_delta_max); CP(rew_bound_scaling); CP(rew_bound_max);
+    CP(step_fail_value); CP(rise_low); CP(rise_high);
+#undef CP
+    d.seed = f.seed;
+    d.env_id_offset = f.env_id_offset;
+}
+
+}  // namespace fw
+
+using namespace fw;
+
+struct FwHandle {
+    FwConfig cfg;
+    int n, device;
+    DCfg<double> c64;
+    DCfg<float> c32;
+    Soa<double> s64;
+    Soa<float> s32;
+    void* r_buf; int32_t* i_buf; void* err_ring;
+    double* metrics; double* ep_ret; int32_t* ep_len; int32_t* ep_term;
+    unsigned long long random_step;
+};
+
+static const int NT_RK45_F64 = 64;     // 7*19*64*8 = 68096 B of stage storage per block: 3 blocks / SM
+static const int NT_RK45_F32 = 128;    // 7*19*128*4 = 68096 B
+static const int NT_RK4 = 128;
+
+template <typename T, int INTEG, int NT>
+static int launch_step_t(FwHandle* h, const DCfg<T>& c, const Soa<T>& S, const StepIO& io, cudaStream_t st) {
+    const size_t smem = (INTEG == FW_INT_RK45_SCIPY) ? (size_t)7 * FW_NY * NT * sizeof(T) : 0;
+    const int grid = (h->n + NT - 1) / NT;
+    if (c.turbulence) {
+        auto k = step_kernel<T, INTEG, true, NT>;
+        static bool attr_set = false;
+        if (smem && !attr_set) { CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+        k<<<grid, NT, smem, st>>>(c, S, io);
+    } else {
+        auto k = step_kernel<T, INTEG, false, NT>;
+        static bool attr_set = false;
+        if (smem && !attr_set) { CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+        k<<<grid, NT, smem, st>>>(c, S, io);
+    }
+    CK(cudaGetLastError());
+    return FW_OK;
+}
+
+static int launch_step(FwHandle* h, const StepIO& io, cudaStream_t st) {
+    if (h->cfg.precision == FW_F64) {
+        if (h->cfg.integrator == FW_INT_RK45_SCIPY) return launch_step_t<double, FW_INT_RK45_SCIPY, NT_RK45_F64>(h, h->c64, h->s64, io, st);
+        return launch_step_t<double, FW_INT_RK4_FIXED, NT_RK4>(h, h->c64, h->s64, io, st);
+    }
+    if (h->cfg.integrator == FW_INT_RK45_SCIPY) return launch_step_t<float, FW_INT_RK45_SCIPY, NT_RK45_F32>(h, h->c32, h->s32, io, st);
+    return launch_step_t<float, FW_INT_RK4_FIXED, NT_RK4>(h, h->c32, h->s32, io, st);
+}
+
+extern "C" {
+
+const char* fw_last_error(void) { return g_err; }
+int fw_abi_version(void) { return FW_ABI_VERSION; }
+int fw_config_size(void) { return (int)sizeof(FwConfig); }
+
+int fw_create(const FwConfig* cfg, int32_t n_envs, int32_t device, FwHandle** out) {
+    if (!cfg || !out || n_envs <= 0) { snprintf(g_err, sizeof(g_err), "fw_create: bad arguments"); return FW_EINVAL; }
+    if (cfg->abi_version != FW_ABI_VERSION) { snprintf(g_err, sizeof(g_err), "fw_create: ABI version mismatch"); return FW_EINVAL; }
+    if (cfg->streak_req > 128 || cfg->rew_delta_window > 5 || cfg->obs_act_window > 5 || cfg->steps_max <= 0 ||
+        (cfg->precision != FW_F64 && cfg->precision != FW_F32) ||
+        (cfg->integrator != FW_INT_RK45_SCIPY && cfg->integrator != FW_INT_RK4_FIXED)) {
+        snprintf(g_err, sizeof(g_err), "fw_create: unsupported config value");
+        return FW_EINVAL;
+    }
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+        snprintf(g_err, sizeof(g_err), "fw_create: no CUDA device %d (there is no CPU fallback)", device);
+        return FW_ENODEVICE;
+    }
+    CK(cudaSetDevice(device));
+    FwHandle* h = new (std::nothrow) FwHandle();
+    if (!h) return FW_ENOMEM;
+    memset(h, 0, sizeof(*h));
+    h->cfg = *cfg; h->n = n_envs; h->device = device;
+    convert_cfg<double>(*cfg, h->c64);
+    convert_cfg<float>(*cfg, h->c32);
+    const size_t esz = cfg->precision == FW_F64 ? 8 : 4, n = (size_t)n_envs;
+    CK(cudaMalloc(&h->r_buf, esz * RF_COUNT * n));
+    CK(cudaMalloc((void**)&h->i_buf, sizeof(int32_t) * IF_COUNT * n));
+    CK(cudaMalloc(&h->err_ring, esz * FW_END_ERR_WINDOW * 3 * n));
+    CK(cudaMalloc((void**)&h->metrics, sizeof(double) * FW_NMETRIC * n));
+    CK(cudaMalloc((void**)&h->ep_ret, sizeof(double) * n));
+    CK(cudaMalloc((void**)&h->ep_len, sizeof(int32_t) * n));
+    CK(cudaMalloc((void**)&h->ep_term, sizeof(int32_t) * n));
+    CK(cudaMemset(h->r_buf, 0, esz * RF_COUNT * n));
+    CK(cudaMemset(h->i_buf, 0, sizeof(int32_t) * IF_COUNT * n));
+    CK(cudaMemset(h->err_ring, 0, esz * FW_END_ERR_WINDOW * 3 * n));
+    CK(cudaMemset(h->metrics, 0, sizeof(double) * FW_NMETRIC * n));
+    CK(cudaMemset(h->ep_ret, 0, sizeof(double) * n));
+    CK(cudaMemset(h->ep_len, 0, sizeof(int32_t) * n));
+    CK(cudaMemset(h->ep_term, 0, sizeof(int32_t) * n));
+    h->s64 = Soa<double>{(double*)h->r_buf, h->i_buf, (double*)h->err_ring, h->metrics, h->ep_ret, h->ep_len, h->ep_term, nullptr, 0, n_envs};
+    h->s32 = Soa<float>{(float*)h->r_buf, h->i_buf, (float*)h->err_ring, h->metrics, h->ep_ret, h->ep_len, h->ep_term, nullptr, 0, n_envs};
+    CK(cudaDeviceSynchronize());
+    *out = h;
+    return FW_OK;
+}
+
+int fw_destroy(FwHandle* h) {
+    if (!h) return FW_EINVAL;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    cudaFree(h->r_buf); cudaFree(h->i_buf); cudaFree(h->err_ring); cudaFree(h->metrics);
+    cudaFree(h->ep_ret); cudaFree(h->ep_len); cudaFree(h->ep_term);
+    delete h;
+    return FW_OK;
+}
+
+int fw_reset(FwHandle* h, const uint8_t* mask_dev, const double* state_dev, const double* target_dev,
+             const double* noise_dev, int32_t noise_len, float* obs_dev, double* obs64_dev, void* stream) {
+    if (!h) return FW_EINVAL;
+    if (noise_dev && noise_len <= 0) { snprintf(g_err, sizeof(g_err), "fw_reset: noise_len must be > 0"); return FW_EINVAL; }
+    cudaStream_t st = (cudaStream_t)stream;
+    h->s64.noise = noise_dev; h->s64.noise_len = noise_len;
+    h->s32.noise = noise_dev; h->s32.noise_len = noise_len;
+    const int bs = 128, grid = (h->n + bs - 1) / bs;
+    if (h->cfg.precision == FW_F64) reset_kernel<double><<<grid, bs, 0, st>>>(h->c64, h->s64, mask_dev, state_dev, target_dev, obs_dev, obs64_dev);
+    else reset_kernel<float><<<grid, bs, 0, st>>>(h->c32, h->s32, mask_dev, state_dev, target_dev, obs_dev, obs64_dev);
+    CK(cudaGetLastError());
+    return FW_OK;
+}
+
+int fw_step(FwHandle* h, const void* actions_dev, int32_t actions_f64, float* obs_dev, float* rew_dev,
+            uint8_t* done_dev, float* term_obs_dev, double* obs64_dev, double* rew64_dev, int32_t auto_reset,
+            void* stream) {
+    if (!h || !actions_dev) { snprintf(g_err, sizeof(g_err), "fw_step: null handle/actions"); return FW_EINVAL; }
+    StepIO io;
+    memset(&io, 0, sizeof(io));
+    io.actions = actions_dev; io.actions_f64 = actions_f64; io.obs = obs_dev; io.rew = rew_dev; io.done = done_dev;
+    io.term_obs = term_obs_dev; io.obs64 = obs64_dev; io.rew64 = rew64_dev; io.auto_reset = auto_reset;
+    return launch_step(h, io, (cudaStream_t)stream);
+}
+
+int fw_step_random(FwHandle* h, int32_t k_steps, uint64_t action_seed, float* obs_dev, float* rew_dev,
+                   uint8_t* done_dev, void* stream) {
+    if (!h || k_steps <= 0) return FW_EINVAL;
+    StepIO io;
+    memset(&io, 0, sizeof(io));
+    io.obs = obs_dev; io.rew = rew_dev; io.done = done_dev; io.auto_reset = 1; io.random_actions = 1;
+    io.action_seed = action_seed;
+    for (int k = 0; k < k_steps; ++k) {
+        io.action_step = h->random_step++;
+        int rc = launch_step(h, io, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    return FW_OK;
+}
+
+int fw_get_episode_info(FwHandle* h, int32_t* term_code_dev, double* metrics_dev, double* ep_return_dev,
+                        int32_t* ep_length_dev, void* stream) {
+    if (!h) return FW_EINVAL;
+    const int bs = 128, grid = (h->n + bs - 1) / bs;
+    episode_info_kernel<<<grid, bs, 0, (cudaStream_t)stream>>>(h->n, h->ep_term, h->metrics, h->ep_ret, h->ep_len,
+                                                              term_code_dev, metrics_dev, ep_return_dev, ep_length_dev);
+    CK(cudaGetLastError());
+    return FW_OK;
+}
+
+static int field_copy(FwHandle* h, int32_t field, void* buf, int to_soa, void* stream) {
+    if (!h || !buf || field < 0 || field >= FW_FIELD_COUNT) return FW_EINVAL;
+    const int bs = 128, grid = (h->n + bs - 1) / bs;
+    if (h->cfg.precision == FW_F64) field_copy_kernel<double><<<grid, bs, 0, (cudaStream_t)stream>>>(h->c64, h->s64, field, buf, to_soa);
+    else field_copy_kernel<float><<<grid, bs, 0, (cudaStream_t)stream>>>(h->c32, h->s32, field, buf, to_soa);
+    CK(cudaGetLastError());
+    return FW_OK;
+}
+int fw_get_field(FwHandle* h, int32_t field, void* out_dev, void* stream) { return field_copy(h, field, out_dev, 0, stream); }
+int fw_set_field(FwHandle* h, int32_t field, const void* in_dev, void* stream) {
+    if (field == FW_FIELD_NFEV || field == FW_FIELD_TURB) return FW_EINVAL;
+    return field_copy(h, field, (void*)in_dev, 1, stream);
+}
+
+}  // extern "C"
