@@ -1,0 +1,76 @@
+"""CPU-only checks of the boundary: the C-ABI library loads and exports every symbol include/fwb200.h declares,
+struct layouts agree between C and Python, the config builder reproduces the reference's derived numbers, and
+the product path refuses to run without a GPU (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from tum_adlr_deep_reinforcement_learning_b200 import _lib
+from tum_adlr_deep_reinforcement_learning_b200 import config as C
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "fwb200.h")).read()
+    declared = set(re.findall(r"^(?:int|const char\*)\s+(fw_\w+)\s*\(", hdr, flags=re.M))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    L = _lib.lib()
+    for sym in declared:
+        assert hasattr(L, sym), sym
+    assert L.fw_abi_version() == C.FW_ABI_VERSION
+
+
+def test_config_struct_layout_matches_both_libraries():
+    from oracle import fw_oracle as O
+    assert _lib.lib().fw_config_size() == ctypes.sizeof(C.FwConfig) == O.lib().fwo_config_size()
+
+
+def test_default_config_numbers():
+    c = C.build_config()
+    assert c.steps_max == 2000 and c.dt == 0.01 and c.turbulence == 1
+    # Actuation.finalize limits: elevator [-30, 35] deg, aileron +-32.5 deg, throttle [0, 1]
+    assert np.allclose([c.act_lo[0], c.act_hi[0]], np.radians([-30, 35]))
+    assert np.allclose([c.act_lo[1], c.act_hi[1]], np.radians([-32.5, 32.5]))
+    assert (c.act_lo[2], c.act_hi[2]) == (0.0, 1.0)
+    assert c.elevon_dot_max == 3.4907                       # not degree-converted
+    assert np.allclose(c.omega_con_max[0], np.radians(720)) and c.va_con_max == 70
+    assert np.allclose([c.init_lo[0], c.init_hi[0]], np.radians([-110, 110]))     # curriculum level 1
+    assert (c.init_lo[8], c.init_hi[8]) == (-20, -100)      # position_d: low > high on purpose (App. E-7)
+    assert c.tgt_class[2] == 1 and np.allclose(c.tgt_bound[0], np.radians(5)) and c.tgt_bound[2] == 2
+    assert c.streak_req == 100 and c.streak_fraction == 0.95 and c.on_success == 0
+    # Dryden with the reference's shifted constructor arguments: noise scale sqrt(pi / 2000), Ad underflows to 0
+    assert np.isclose(c.turb_noise_scale, np.sqrt(np.pi / 2000))
+    assert all(abs(c.filt[i].Ad[0]) < 1e-300 for i in range(6))
+    assert [c.filt[i].noise_row for i in range(6)] == [0, 1, 2, 3, 1, 2]
+    assert [c.filt[i].order for i in range(6)] == [1, 2, 2, 1, 3, 3]
+
+
+def test_overrides_follow_reference_semantics():
+    c = C.build_config(config_kw={"steps_max": 1500, "target": {"on_success": "done", "success_streak_fraction": 1,
+                                                                "states": {2: {"bound": 3}}},
+                                  "action": {"scale_space": False}},
+                       sim_config_kw={"turbulence": False})
+    assert c.steps_max == 1500 and c.on_success == 1 and c.streak_fraction == 1 and c.tgt_bound[2] == 3
+    assert c.scale_actions == 0 and c.turbulence == 0
+
+
+def test_unsupported_configs_fail_loudly():
+    with pytest.raises(NotImplementedError):
+        C.build_config(config_kw={"observation": {"length": 5}})
+    with pytest.raises(NotImplementedError):
+        C.build_config(config_kw={"reward": {"form": "potential"}})
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from tum_adlr_deep_reinforcement_learning_b200.batched import BatchedFixedWing
+    with pytest.raises(_lib.FwError):
+        BatchedFixedWing(4)
+    h = ctypes.c_void_p()
+    rc = _lib.lib().fw_create(ctypes.byref(C.build_config()), 4, 0, ctypes.byref(h))
+    assert rc == -2 and b"no CPU fallback" in _lib.lib().fw_last_error()

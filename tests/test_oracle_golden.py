@@ -1,0 +1,157 @@
+"""Pins the oracle (oracle/fw_oracle.c): the C restatement must reproduce
+  (1) fixtures recorded by running the unmodified reference (tests/golden/make_golden.py), and
+  (2) the reference's own golden PID evaluation (examples/evaluations/eval_res_PID_none.npy on
+      examples/test_sets/test_set_wind_none_step20-20-3.npy), stored in tests/golden/pid_none.npz.
+CPU only.  These are the tests that entitle the GPU parity tests to use the oracle as their checker."""
+import numpy as np
+import pytest
+
+from conftest import TRAJ_CASES, close_or_both_nan, golden_metric_rows, load_golden
+from oracle import fw_oracle as O
+from oracle import pid as P
+from tum_adlr_deep_reinforcement_learning_b200.config import build_config
+
+
+def _rel(a, b):
+    return np.abs(a - b) / np.maximum(1.0, np.abs(b))
+
+
+@pytest.mark.parametrize("name,cfg_kw,sim_kw,f32", TRAJ_CASES, ids=[c[0] for c in TRAJ_CASES])
+def test_oracle_reproduces_live_reference_trajectories(name, cfg_kw, sim_kw, f32):
+    g = load_golden(name)
+    cfg = build_config(config_kw=cfg_kw, sim_config_kw=sim_kw)
+    E = g["actions"].shape[0]
+    rows, eps = golden_metric_rows(g) if "m_success" in g.files else ([], [])
+    for ep in range(E):
+        env = O.OracleEnv(cfg)
+        noise = g["noise"][ep] if "noise" in g.files else None
+        obs = env.reset(g["init_state"][ep], g["init_target"][ep], noise)
+        assert np.abs(obs - g["obs0"][ep]).max() < 1e-12
+        s = env.get()
+        assert np.abs(s["y"] - g["y0"][ep]).max() < 1e-14
+        if noise is not None:
+            ref = np.concatenate([g["turb_lin"][ep], g["turb_ang"][ep]])
+            assert np.abs(env.turbulence() - ref).max() < 1e-15
+        for t in range(int(g["n_valid"][ep])):
+            obs, rew, done, term = env.step(g["actions"][ep, t], f32)
+            s = env.get()
+            assert done == bool(g["done"][ep, t]) and term == int(g["term"][ep, t]), (ep, t)
+            assert s["nfev"] == int(g["nfev"][ep, t]), (ep, t, "RK45 step-size decisions differ")
+            if term < 10:
+                assert _rel(s["y"], g["y"][ep, t]).max() < 1e-9, (ep, t)
+                assert _rel(s["vab"], g["vab"][ep, t]).max() < 1e-9
+            assert _rel(obs, g["obs"][ep, t]).max() < 1e-9, (ep, t)
+            assert abs(rew - g["reward"][ep, t]) < 1e-9 * max(1.0, abs(g["reward"][ep, t]))
+            assert _rel(s["target"], g["target"][ep, t]).max() < 1e-12
+            assert _rel(s["cmd"], g["cmd"][ep, t]).max() < 1e-12
+        if ep in eps:
+            m, ret, ln, term = env.metrics()
+            row = rows[eps.index(ep)]
+            assert close_or_both_nan(m, row, 1e-7, 1e-9).all(), (ep, m, row)
+            assert ln == int(g["n_valid"][ep])
+
+
+def test_dryden_matches_reference_for_all_intensities():
+    g = load_golden("dryden")
+    for L in (2000, 300):
+        for inten in ("light", "moderate", "severe"):
+            tag = "L%d_%s" % (L, inten)
+            cfg = build_config(config_kw={"steps_max": L},
+                               sim_config_kw={"turbulence": True, "turbulence_intensity": inten})
+            out = O.dryden(cfg, g[tag + "_noise"])
+            ref = np.concatenate([g[tag + "_lin"], g[tag + "_ang"]])
+            assert np.abs(out - ref).max() <= 1e-12 * np.abs(ref).max(), tag
+            assert np.all(out[:, 0] == 0)      # column 0 is exactly zero (x_0 = 0, D = 0)
+
+
+def test_gae_bit_exact():
+    g = load_golden("gae")
+    for tag in ("a", "b", "c"):
+        adv, ret = O.gae(g[tag + "_rew"], g[tag + "_val"], g[tag + "_done"], g[tag + "_last_val"],
+                         g[tag + "_last_done"])
+        assert np.array_equal(adv, g[tag + "_adv"]), tag
+        assert np.array_equal(ret, g[tag + "_ret"]), tag
+
+
+def test_philox_known_answers():
+    # Random123 kat_vectors: philox4x32-10
+    assert O.philox4x32([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert O.philox4x32([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert O.philox4x32([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def run_pid_scenarios(step_fn, reset_fn, g, idx):
+    """Replays the reference's PID evaluation (evaluate_controller.py:155-215) for the scenarios in idx, all in
+    lock step.  reset_fn(state21, target3) -> obs [n,14] f64; step_fn(actions [n,3] f64) -> obs, rew, done."""
+    n = len(idx)
+    pid = P.BatchPID(n)
+    state = P.scenario_state21(g["init_state"][idx])
+    tgt = g["init_target"][idx].copy()
+    obs = reset_fn(state, tgt)
+    pid.set_reference(tgt)
+    first = g["first_ref"][idx]
+    has_first = ~np.isnan(first[:, 0])
+    pid.ref[has_first] = first[has_first]           # stale reference of the harness for the first action
+    rewards = np.zeros((n, 1500))
+    length = np.zeros(n, dtype=np.int64)
+    alive = np.ones(n, bool)
+    for t in range(1500):
+        a = pid.get_action(obs[:, 0], obs[:, 1], obs[:, 2], obs[:, 3:6])
+        obs, rew, done = step_fn(a)
+        rewards[alive, t] = rew[alive]
+        newly = alive & done
+        length[newly] = t + 1
+        alive &= ~done
+        pid.set_reference(obs[:, 6:9])                # info["target"] == the target entries of the observation
+        if not alive.any():
+            break
+    return rewards, length
+
+
+def test_oracle_reproduces_reference_golden_pid_evaluation():
+    g = load_golden("pid_none")
+    idx = np.arange(100)
+    cfg = build_config(config_kw=P.PID_EVAL_CONFIG_KW, sim_config_kw=P.PID_EVAL_SIM_KW)
+    envs = [O.OracleEnv(cfg) for _ in idx]
+    fin = {}
+
+    def reset_fn(state, tgt):
+        return np.stack([e.reset(state[i], tgt[i]) for i, e in enumerate(envs)])
+
+    def step_fn(a):
+        out = []
+        for i, e in enumerate(envs):
+            if i in fin:
+                out.append(fin[i])
+                continue
+            o, r, d, term = e.step(a[i])
+            if d:
+                fin[i] = (o, r, True)
+            out.append((o, r, d))
+        return (np.stack([x[0] for x in out]), np.array([x[1] for x in out]), np.array([x[2] for x in out]))
+
+    rewards, length = run_pid_scenarios(step_fn, reset_fn, g, idx)
+    # (a) against our own run of the reference in this container: tight
+    assert np.array_equal(length, g["live_len"])
+    for s in idx:
+        n = length[s]
+        assert np.abs(rewards[s, :n] - g["live_rewards"][s, :n]).max() < 1e-8, s
+    # (b) against the reference's own golden file (produced under the pinned scipy 1.6 / numpy 1.19 stack):
+    # episode lengths exact, reward traces to 1e-5 (the live reference itself agrees to 8.5e-6).  The last six
+    # golden traces carry extra entries appended after the scenario ended (harness artefact): compare the prefix.
+    for s in idx:
+        n = length[s]
+        if s < 94:
+            assert n == g["gold_len"][s], s
+        assert np.abs(rewards[s, :n] - g["gold_rewards"][s, :n]).max() < 2e-5, s
+    # (c) integer metrics: the golden file lists them in completion order -> compare as multisets
+    m = np.stack([envs[i].metrics()[0] for i in idx])
+    for name, lo, keys in (("settling_time", 3, ("roll", "pitch", "Va", "all")), ("rise_time", 0, ("roll", "pitch", "Va")),
+                           ("success", 17, ("roll", "pitch", "Va", "all"))):
+        gk = [str(k) for k in g["gold_%s_keys" % name]]
+        cols = [lo + keys.index(k) for k in gk]
+        ours = np.sort(np.nan_to_num(m[:, cols], nan=-1), axis=0)
+        gold = np.sort(np.nan_to_num(g["gold_" + name], nan=-1), axis=0)
+        assert np.array_equal(ours, gold), name
+    assert np.abs(np.sort(m[:, 16]) - np.sort(g["gold_control_variation"][:, 0])).max() < 1e-4
