@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py — env-steps/sec of the batched fixed-wing env step (x8 UAV, Dryden turbulence) on N B200s.
+
+  python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torch.distributed.run, one rank per GPU)
+  python bench.py --impl reference ...                     (CPU arm: the oracle port on the box's host cores)
+
+Workload (BASELINE.json configs[2], "C3"): 65536 envs PER GPU (weak scaling; envs are independent, no collective
+on the step), default attitude task, light Dryden turbulence + steady wind U(-8, 8), actions U(-1,1)^3 that change
+every step, fp64 exact mode (bit-for-logic scipy-RK45 replica) — the parity-graded path.  One "step" = one
+VecEnv.step over every env of the rank = ONE launch of step_kernel.
+
+Timed region (`value`): K launches with the action batches already resident in HBM, one CUDA-event pair per
+launch on the launching stream, an L2 flush (256 MiB write) between launches outside the event pairs; barrier +
+synchronize on both sides; max over ranks.  `e2e`: the same K steps through FixedWingVecEnv.step(numpy actions)
+with the pinned H2D copy of the actions and the D2H copy of obs/reward/done inside the timed region.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "env-steps/sec (x8 UAV, Dryden turb)"
+UNIT = "env-steps/s"
+ENVS_PER_GPU = 65536
+# algorithmic work per env-step (DESIGN.md "Roofline"; SURVEY §8d hand counts)
+W_RHS, W_ATT, W_ENV = 520.0, 1400.0, 400.0           # flops per RHS evaluation / RK45 attempt / env head
+T_RHS, T_ATT, T_ENV = 9.0, 1.0, 6.0                  # transcendental calls (counted as 1 flop each as well)
+BYTES_PER_ENV_STEP_F64 = 90 * 8 * 2 + 43 * 4 * 2 + 3 * 8 + 12 + 56 + 4 + 1   # SoA state r+w, err ring slot, I/O
+
+
+def workload_config(n):
+    return {"workload": "C3: %d envs/GPU, default attitude task (fixed_wing_config.json), light Dryden turbulence + "
+                        "steady wind U(-8,8), fresh U(-1,1)^3 actions every step, auto-reset" % n,
+            "envs_per_gpu": n, "mode": "fp64 exact (scipy-RK45 replica, rtol 1e-3 atol 1e-6)",
+            "cache": "L2 flushed (256 MiB write) between timed launches; per-launch CUDA events",
+            "scaling_unit": "envs sharded by global env id, no data-path collective"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.lines, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+# ----------------------------------------------------------------------------------------------- CPU arms
+def cpu_port_rate(cfg, budget_s, threads):
+    """Oracle port (oracle/fw_oracle.c) on the host cores: `threads` python threads each drive a sub-batch through
+    ctypes (the GIL is released inside the C call).  Bounded sample; returns (env-steps/s, description)."""
+    from oracle import fw_oracle as O
+    per = 128
+    batches = [O.OracleBatch(cfg_with_offset(cfg, i * per), per) for i in range(threads)]
+    for b in batches:
+        b.reset()
+
+    def run(b, k, step0):
+        b.step_random(k, 1, step0)
+
+    def timed(k, step0):
+        ts = [threading.Thread(target=run, args=(b, k, step0)) for b in batches]
+        t0 = time.perf_counter()
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        return time.perf_counter() - t0
+
+    timed(2, 0)                                   # warm-up
+    dt = timed(5, 2)
+    k = max(5, min(2000, int(budget_s / max(dt / 5, 1e-6))))
+    dt = timed(k, 7)
+    rate = threads * per * k / dt
+    return rate, "%d threads x %d envs x %d steps of the C3 workload (%.1f s)" % (threads, per, k, dt)
+
+
+def cfg_with_offset(cfg, off):
+    import copy
+    c = copy.copy(cfg)
+    c.env_id_offset = cfg.env_id_offset + off
+    return c
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's CPU implementation of the path.  The reference is pure Python and cannot
+    travel to the GPU box (no /root/reference there), so this arm times the oracle port with every host thread."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from tum_adlr_deep_reinforcement_learning_b200.config import build_config
+    cfg = build_config(sim_config_kw={"turbulence": True}, seed=0)
+    threads = os.cpu_count() or 1
+    from oracle import fw_oracle as O
+    per = 128
+    batches = [O.OracleBatch(cfg_with_offset(cfg, i * per), per) for i in range(threads)]
+    for b in batches:
+        b.reset()
+
+    def one_step(step0):
+        ts = [threading.Thread(target=b.step_random, args=(1, 1, step0)) for b in batches]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+
+    for w in range(args.warmup):
+        one_step(w)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        one_step(args.warmup + k)
+    dt = time.perf_counter() - t0
+    n = threads * per
+    value = n * args.steps / dt
+    sample = "%d threads x %d envs, %d steps of the C3 workload per timed step" % (threads, per, 1)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(ENVS_PER_GPU),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                             "note": "C restatement of the pure-Python reference; the Python reference itself ran at "
+                                     "126 env-steps/s/core in the build container (BASELINE.md §2)"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
+    ap.add_argument("--cpu-budget-s", type=float, default=12.0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the fp32 / PPO side measurements")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from tum_adlr_deep_reinforcement_learning_b200 import batched as bt
+    from tum_adlr_deep_reinforcement_learning_b200.config import build_config
+    from tum_adlr_deep_reinforcement_learning_b200.vec_env import FixedWingVecEnv
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the env step has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    n, K, W = args.envs_per_gpu, args.steps, args.warmup
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def time_device_steps(env, pool, flush):
+        """K launches, per-launch events, L2 flush between; returns (total ms of the launches, nfev stats)."""
+        for w in range(W):
+            env.step(pool[w % len(pool)])
+        nf_sum = np.zeros(2)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        nf_acc = torch.zeros(2, dtype=torch.float64, device=dev)
+        barrier()
+        for k in range(K):
+            flush.add_(1.0)                      # 256 MiB read+write: evicts L2
+            ev[k][0].record()
+            env.step(pool[(W + k) % len(pool)])
+            ev[k][1].record()
+            nf_acc += env.get_field(bt.FIELD_NFEV).to(torch.float64).sum(0)   # outside the event pair
+        barrier()
+        ms = sum(a.elapsed_time(b) for a, b in ev)
+        nf_sum = (nf_acc / (n * K)).cpu().numpy()
+        return ms, nf_sum
+
+    # ---- main arm: fp64 exact mode ----
+    cfg = build_config(sim_config_kw={"turbulence": True}, precision="f64", integrator="rk45", seed=0,
+                       env_id_offset=rank * n)
+    env = bt.BatchedFixedWing(n, cfg=cfg, device=local)
+    env.reset()
+    g = torch.Generator(device=dev)
+    g.manual_seed(1000 + rank)
+    pool = [(torch.rand(n, 3, device=dev, generator=g) * 2 - 1).contiguous() for _ in range(16)]
+    flush = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device=dev)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms_total, nf = time_device_steps(env, pool, flush)
+    clocks = sampler.stop()
+    ms_total = max_over_ranks(ms_total)
+    ms_per_step = ms_total / K
+    value = world * n * K / (ms_total * 1e-3)
+
+    # ---- roofline of the dominant kernel (step_kernel<double, RK45, turbulence>) ----
+    peaks, peak_kind = measured_peaks()
+    fp64_peak = bt.measure_fma_peak(local, "f64")
+    fp32_peak = bt.measure_fma_peak(local, "f32")
+    flops_env_step = nf[0] * (W_RHS + T_RHS) + nf[1] * (W_ATT + T_ATT) + (W_ENV + T_ENV)
+    achieved_tf = flops_env_step * n / (ms_per_step * 1e-3) / 1e12
+    hbm_gbs = BYTES_PER_ENV_STEP_F64 * n / (ms_per_step * 1e-3) / 1e9
+    roofline = {"bound": "fp64", "kernel": "step_kernel<double, RK45_SCIPY, turbulence, 64>",
+                "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak,
+                "peak_source": "DFMA micro-benchmark fw_measure_fma_peak on this GPU, same process (MEASURED_PEAKS.json "
+                               "has no vector-pipe figure)",
+                "flops_per_env_step": flops_env_step, "mean_rhs_evals": float(nf[0]), "mean_rk_attempts": float(nf[1]),
+                "traffic": None,
+                "hbm": {"achieved": hbm_gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                        "frac": hbm_gbs / peaks.get("hbm_gbs"), "peak_source": peak_kind + " (MEASURED_PEAKS.json)",
+                        "bytes_per_env_step": BYTES_PER_ENV_STEP_F64},
+                "fp32_peak_tflops": fp32_peak}
+    env.close()
+    del env
+
+    # ---- e2e: VecEnv API, host numpy actions in, numpy obs/rew/done out ----
+    e2e = None
+    if not args.no_e2e:
+        venv = FixedWingVecEnv(n, sim_config_kw={"turbulence": True}, device=local, seed=0, env_id_offset=rank * n,
+                               precision="f64", integrator="rk45")
+        venv.reset()
+        rs = np.random.RandomState(rank)
+        host_pool = [rs.uniform(-1, 1, (n, 3)).astype(np.float32) for _ in range(8)]
+        for w in range(W):
+            venv.step(host_pool[w % 8])
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(K):
+            obs, rew, done, infos = venv.step(host_pool[(W + k) % 8])
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": world * n * K / dt, "unit": UNIT, "h2d_bytes_per_step": venv.h2d_bytes_per_step,
+               "d2h_bytes_per_step": venv.d2h_bytes_per_step, "ms_per_step": dt / K * 1e3,
+               "api": "FixedWingVecEnv.step(numpy float32 actions) -> numpy obs, rewards, dones, infos (lazy)"}
+        venv.close()
+        del venv
+
+    # ---- side measurements (not the headline): fp32 fixed-step mode ----
+    extra = {}
+    if not args.no_extra:
+        for tag, prec, integ in (("fp32_rk4x4", "f32", "rk4"), ("fp64_rk4x4", "f64", "rk4")):
+            c2 = build_config(sim_config_kw={"turbulence": True}, precision=prec, integrator=integ, rk4_substeps=4,
+                              seed=0, env_id_offset=rank * n)
+            e2 = bt.BatchedFixedWing(n, cfg=c2, device=local)
+            e2.reset()
+            ms2, _ = time_device_steps(e2, pool, flush)
+            ms2 = max_over_ranks(ms2)
+            extra[tag] = {"value": world * n * K / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2 / K,
+                          "note": "fixed-step mode, graded at its own tolerance (tests/test_gpu_modes.py), not the "
+                                  "parity path"}
+            e2.close()
+
+    # ---- CPU baseline (rank 0 only, N = 1 only) ----
+    cpu = None
+    if rank == 0 and world == 1:
+        threads = os.cpu_count() or 1
+        rate, sample = cpu_port_rate(cfg, args.cpu_budget_s, threads)
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": workload_config(n), "roofline": roofline,
+                "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": K, "clocks": clocks, "modes": extra}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,341 @@
+"""FixedWingVecEnv — the SB3 `VecEnv` contract over the batched CUDA simulator, and the single-env
+`FixedWingAircraft` gym-style API on top of a one-env batch.
+
+Drop-in boundary: what `collect_rollouts` / `evaluate_policy` / the reference scripts call on
+`VecNormalize(SubprocVecEnv([make_env]*N))`:
+  reset(), step_async(), step_wait(), step(), close(), seed(), get_attr(), set_attr(), env_method(), num_envs,
+  observation_space, action_space              (stable_baselines3/common/vec_env/base_vec_env.py:48-224)
+  auto-reset + info["terminal_observation"]    (subproc_vec_env.py:26-31, dummy_vec_env.py:46-50)
+  info["episode"] = {"r","l","t"}              (common/monitor.py:99-113)
+  info["target"], info["termination"], the 9 metric dicts on done   (fixed_wing.py:519-626)
+There are no worker processes and no per-env Python objects: one CUDA launch steps every env.  Host copies happen
+only at this numpy edge (pinned buffers); `step_tensor` skips them entirely.
+"""
+import time
+
+import numpy as np
+import torch
+
+from . import batched as bt
+from .config import (GOAL_STATES, METRIC_LAYOUT, TARGET_STATES, TERM_NAMES, build_config, observation_bounds)
+
+
+class Box:
+    """Minimal stand-in for gym.spaces.Box (gym is not a dependency of this package)."""
+
+    def __init__(self, low, high, dtype=np.float32):
+        self.low = np.asarray(low, dtype=dtype)
+        self.high = np.asarray(high, dtype=dtype)
+        self.shape = self.low.shape
+        self.dtype = np.dtype(dtype)
+
+    def sample(self):
+        lo = np.where(np.isfinite(self.low) & (np.abs(self.low) < 1e30), self.low, -1.0)
+        hi = np.where(np.isfinite(self.high) & (np.abs(self.high) < 1e30), self.high, 1.0)
+        return np.random.uniform(lo, hi).astype(self.dtype)
+
+    def contains(self, x):
+        x = np.asarray(x)
+        return x.shape == self.shape and bool(np.all(x >= self.low) and np.all(x <= self.high))
+
+    def __repr__(self):
+        return "Box(%s, %s)" % (self.shape, self.dtype)
+
+
+class _SimulatorView:
+    """What the scripts read through get_attr("simulator") (evaluate_controller.py:120): dt and state values."""
+
+    def __init__(self, venv, index):
+        self._venv, self._i = venv, index
+        self.dt = venv.cfg.dt
+
+    @property
+    def state(self):
+        return self._venv.state_dict(self._i)
+
+
+_EMPTY_INFO = {}
+
+
+class FixedWingVecEnv:
+    """n_envs reference-semantics fixed-wing envs on one GPU behind the VecEnv API.
+
+    info_mode: "compat" builds the reference's per-env info dict for every env every step (info["target"] always
+    present, fixed_wing.py:626); "lazy" (default) builds dicts only for envs that finished and hands out one shared
+    empty dict for the rest — at tens of thousands of envs the dict loop, not the simulator, bounds the step rate.
+    """
+
+    def __init__(self, num_envs, config_path=None, config_kw=None, sim_config_path=None, sim_config_kw=None,
+                 device=0, seed=0, env_id_offset=0, precision="f64", integrator="rk45", rk4_substeps=4,
+                 info_mode="lazy", copy_outputs=True):
+        self.cfg = build_config(env_cfg=config_path, sim_cfg=sim_config_path, config_kw=config_kw,
+                                sim_config_kw=sim_config_kw, precision=precision, integrator=integrator,
+                                rk4_substeps=rk4_substeps, seed=seed, env_id_offset=env_id_offset)
+        self._build_kw = dict(env_cfg=config_path, sim_cfg=sim_config_path, config_kw=config_kw,
+                              sim_config_kw=sim_config_kw, precision=precision, integrator=integrator,
+                              rk4_substeps=rk4_substeps, seed=seed, env_id_offset=env_id_offset)
+        self.num_envs = int(num_envs)
+        self.sim = bt.BatchedFixedWing(self.num_envs, cfg=self.cfg, device=device)
+        self.device = self.sim.device
+        lo, hi = observation_bounds(cfg=self.cfg)
+        self.observation_space = Box(lo, hi)
+        f32max = np.finfo(np.float32).max
+        self.action_space = Box(np.full(3, -f32max), np.full(3, f32max))
+        self.info_mode = info_mode
+        self.copy_outputs = copy_outputs
+        self.training = True
+        self.curriculum_level = 1.0
+        n = self.num_envs
+        self._act_pin = torch.zeros(n, 3, dtype=torch.float32).pin_memory()
+        self._act_dev = torch.zeros(n, 3, dtype=torch.float32, device=self.device)
+        self._obs_pin = torch.zeros(n, 14, dtype=torch.float32).pin_memory()
+        self._rew_pin = torch.zeros(n, dtype=torch.float32).pin_memory()
+        self._done_pin = torch.zeros(n, dtype=torch.uint8).pin_memory()
+        self._waiting = False
+        self._t_start = time.time()
+        self.h2d_bytes_per_step = self._act_pin.numel() * 4
+        self.d2h_bytes_per_step = self._obs_pin.numel() * 4 + self._rew_pin.numel() * 4 + self._done_pin.numel()
+
+    # ------------------------------------------------------------------ tensor fast path
+    def reset_tensor(self):
+        return self.sim.reset()
+
+    def step_tensor(self, actions):
+        """actions: [n,3] float32/float64 CUDA tensor.  Returns (obs, rew, done) CUDA tensors (views of buffers that
+        the next call overwrites).  Auto-resets like a VecEnv; terminal rows are in `self.sim.term_obs`."""
+        return self.sim.step(actions, auto_reset=True)
+
+    # ------------------------------------------------------------------ VecEnv API
+    def reset(self):
+        obs = self.sim.reset()
+        self._obs_pin.copy_(obs, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        out = self._obs_pin.numpy()
+        return out.copy() if self.copy_outputs else out
+
+    def step_async(self, actions):
+        if self._waiting:
+            raise RuntimeError("step_async called while a step is pending (subproc_vec_env.py:112 contract)")
+        a = np.asarray(actions)
+        assert a.shape == (self.num_envs, 3), a.shape
+        assert not np.any(np.isnan(a)), "NaN action (fixed_wing.py:494)"
+        self._act_pin.numpy()[...] = a            # casts to float32 like DummyVecEnv buffers / SB3 policies
+        self._act_dev.copy_(self._act_pin, non_blocking=True)
+        self.sim.step(self._act_dev, auto_reset=True)
+        self._obs_pin.copy_(self.sim.obs, non_blocking=True)
+        self._rew_pin.copy_(self.sim.rew, non_blocking=True)
+        self._done_pin.copy_(self.sim.done, non_blocking=True)
+        self._waiting = True
+
+    def step_wait(self):
+        if not self._waiting:
+            raise RuntimeError("step_wait without step_async")
+        torch.cuda.current_stream(self.device).synchronize()
+        self._waiting = False
+        obs, rew = self._obs_pin.numpy(), self._rew_pin.numpy()
+        done = self._done_pin.numpy().astype(bool)
+        infos = self._build_infos(done)
+        if self.copy_outputs:
+            obs, rew = obs.copy(), rew.copy()
+        return obs, rew, done, infos
+
+    def step(self, actions):
+        self.step_async(actions)
+        return self.step_wait()
+
+    def close(self):
+        self.sim.close()
+
+    def seed(self, seed=None):
+        """Env i is seeded seed + i (subproc_vec_env.py:120-123): here the Philox key is `seed` and the counter
+        carries the global env id, which gives every env its own stream.  Takes effect at the next reset."""
+        seed = 0 if seed is None else int(seed)
+        self._build_kw["seed"] = seed
+        self._rebuild()
+        return [seed + i for i in range(self.num_envs)]
+
+    def _rebuild(self):
+        self.cfg = build_config(**self._build_kw)
+        self.sim.close()
+        self.sim = bt.BatchedFixedWing(self.num_envs, cfg=self.cfg, device=self.device.index)
+
+    def _indices(self, indices):
+        if indices is None:
+            return list(range(self.num_envs))
+        if isinstance(indices, int):
+            return [indices]
+        return list(indices)
+
+    def get_attr(self, attr_name, indices=None):
+        idx = self._indices(indices)
+        if attr_name == "simulator":
+            return [_SimulatorView(self, i) for i in idx]
+        if attr_name == "cfg":
+            return [self.cfg for _ in idx]
+        if attr_name == "target":
+            t = self.sim.get_field(bt.FIELD_TARGET).cpu().numpy()
+            return [dict(zip(TARGET_STATES, map(float, t[i]))) for i in idx]
+        if attr_name == "steps_count":
+            c = self.sim.get_field(bt.FIELD_COUNTERS).cpu().numpy()
+            return [int(c[i, 0]) for i in idx]
+        return [getattr(self, attr_name) for _ in idx]
+
+    def set_attr(self, attr_name, value, indices=None):
+        if attr_name not in ("training", "info_mode", "copy_outputs"):
+            raise AttributeError("cannot set %r on the batched env" % attr_name)
+        setattr(self, attr_name, value)
+
+    def env_method(self, method_name, *args, indices=None, **kwargs):
+        idx = self._indices(indices)
+        if method_name == "reset":
+            return self._reset_indices(idx, *args, **kwargs)
+        if method_name == "set_curriculum_level":
+            return self._set_curriculum_level(*args, **kwargs)
+        if method_name == "seed":
+            return self.seed(*args, **kwargs)
+        raise NotImplementedError("env_method(%r)" % method_name)
+
+    def _set_curriculum_level(self, level):
+        """fixed_wing.py:334-412: rescales init / target ranges; applies to all envs from their next reset."""
+        assert 0 <= level <= 1
+        self.curriculum_level = float(level)
+        self._build_kw["curriculum_level"] = float(level)
+        self._rebuild()
+        return [None] * self.num_envs
+
+    def _reset_indices(self, idx, state=None, target=None, turbulence_noise=None):
+        """env_method("reset", indices=i, state={...}, target={...}) as used by evaluate_controller.py:174."""
+        n = self.num_envs
+        mask = np.zeros(n, np.uint8)
+        mask[idx] = 1
+        st = np.full((n, 21), np.nan)
+        tg = np.full((n, 3), np.nan)
+        if state is not None:
+            st[idx] = state_dict_to_row(state)
+        if target is not None:
+            tg[idx] = [target.get(k, np.nan) for k in TARGET_STATES]
+        noise = None
+        if turbulence_noise is not None:
+            noise = np.zeros((n, 4, turbulence_noise.shape[1]))
+            noise[idx] = turbulence_noise
+        if self.sim.obs64 is None:
+            self.sim.enable_f64_outputs()
+        self.sim.reset(mask=mask, state=st, target=tg, noise=noise)
+        obs = self.sim.obs64.cpu().numpy()
+        return [obs[i].copy() for i in idx]
+
+    # ------------------------------------------------------------------ info dicts
+    def state_dict(self, i):
+        y = self.sim.get_field(bt.FIELD_Y)[i].cpu().numpy()
+        e = self.sim.get_field(bt.FIELD_EULER)[i].cpu().numpy()
+        v = self.sim.get_field(bt.FIELD_VAB)[i].cpu().numpy()
+        names = ("omega_p", "omega_q", "omega_r", "position_n", "position_e", "position_d", "velocity_u",
+                 "velocity_v", "velocity_w", "elevon_right", "elevon_left", "throttle")
+        d = {k: float(y[4 + j]) for j, k in enumerate(names)}
+        d.update(roll=float(e[0]), pitch=float(e[1]), Va=float(v[0]), alpha=float(v[1]), beta=float(v[2]))
+        return d
+
+    def _build_infos(self, done):
+        n = self.num_envs
+        done_idx = np.flatnonzero(done)
+        if self.info_mode == "lazy" and done_idx.size == 0:
+            return [_EMPTY_INFO] * n
+        if self.info_mode == "compat":
+            tgt = self.sim.get_field(bt.FIELD_TARGET).cpu().numpy()
+            infos = [{"target": dict(zip(TARGET_STATES, map(float, tgt[i])))} for i in range(n)]
+        else:
+            infos = [_EMPTY_INFO] * n
+        if done_idx.size:
+            term, metrics, ret, length = (x.cpu().numpy() for x in self.sim.episode_info())
+            term_obs = self.sim.term_obs.cpu().numpy()
+            now = round(time.time() - self._t_start, 6)
+            for i in done_idx:
+                info = dict(infos[i])
+                info["termination"] = TERM_NAMES.get(int(term[i]), int(term[i]))
+                for name, off, keys in METRIC_LAYOUT:
+                    vals = metrics[i, off:off + len(keys)]
+                    if name == "success":
+                        info[name] = {k: bool(x) for k, x in zip(keys, vals)}
+                    else:
+                        info[name] = {k: float(x) for k, x in zip(keys, vals)}
+                info["terminal_observation"] = term_obs[i].copy()
+                info["episode"] = {"r": float(ret[i]), "l": int(length[i]), "t": now}
+                # fixed_wing.py:626 reports the finished episode's target; it sits in terminal_observation[6:9]
+                info.setdefault("target", dict(zip(TARGET_STATES, map(float, term_obs[i, 6:9]))))
+                infos[i] = info
+        return infos
+
+
+def state_dict_to_row(state):
+    """Reference-style state dict (pyfly.py:1262-1294 keys) -> FW_NSTATE_INJECT row; missing entries = NaN (sampled)."""
+    row = np.full(21, np.nan)
+    keys = ("roll", "pitch", "yaw", "omega_p", "omega_q", "omega_r", "position_n", "position_e", "position_d",
+            "velocity_u", "velocity_v", "velocity_w")
+    for j, k in enumerate(keys):
+        if k in state:
+            row[j] = float(state[k])
+    for j, k in enumerate(("elevon_right", "elevon_left", "throttle")):
+        if k in state:
+            v = state[k]
+            try:
+                row[12 + j], row[15 + j] = float(v[0]), float(v[1])
+            except (TypeError, IndexError):
+                row[12 + j], row[15 + j] = float(v), 0.0
+    if "wind" in state and not np.isscalar(state["wind"]):
+        row[18:21] = np.asarray(state["wind"], dtype=np.float64)
+    elif all(k in state for k in ("wind_n", "wind_e", "wind_d")):
+        row[18:21] = [float(state["wind_n"]), float(state["wind_e"]), float(state["wind_d"])]
+    return row
+
+
+class FixedWingAircraft:
+    """Single-env gym-style API of the reference env (fixed_wing.py:13-628) on a one-env batch: reset(state, target,
+    turbulence_noise) -> obs (float64 like the reference), step(action) -> (obs, reward, done, info),
+    seed, set_curriculum_level, target, observation_space / action_space."""
+
+    def __init__(self, config_path=None, sim_config_path=None, sim_parameter_path=None, config_kw=None,
+                 sim_config_kw=None, device=0, **kw):
+        self._v = FixedWingVecEnv(1, config_path=config_path, config_kw=config_kw, sim_config_path=sim_config_path,
+                                  sim_config_kw=sim_config_kw, device=device, info_mode="compat", **kw)
+        self._v.sim.enable_f64_outputs()
+        self.cfg = self._v.cfg
+        self.observation_space, self.action_space = self._v.observation_space, self._v.action_space
+        self.steps_max = self.cfg.steps_max
+        self.simulator = _SimulatorView(self._v, 0)
+
+    @property
+    def target(self):
+        return self._v.get_attr("target")[0]
+
+    @property
+    def steps_count(self):
+        return self._v.get_attr("steps_count")[0]
+
+    def seed(self, seed=None):
+        return self._v.seed(seed)[:1]
+
+    def set_curriculum_level(self, level):
+        self._v.env_method("set_curriculum_level", level)
+        self._v.sim.enable_f64_outputs()
+
+    def reset(self, state=None, target=None, **sim_reset_kw):
+        return self._v.env_method("reset", indices=[0], state=state, target=target,
+                                  turbulence_noise=sim_reset_kw.get("turbulence_noise"))[0]
+
+    def step(self, action):
+        a = np.asarray(action)
+        f64 = a.dtype != np.float32
+        t = torch.as_tensor(a.reshape(1, 3), dtype=torch.float64 if f64 else torch.float32).to(self._v.device)
+        self._v.sim.step(t.contiguous(), auto_reset=False)
+        obs = self._v.sim.obs64.cpu().numpy()[0].copy()
+        rew = float(self._v.sim.rew64.cpu().numpy()[0])
+        done = bool(self._v.sim.done.cpu().numpy()[0])
+        if done:
+            self._v.sim.term_obs.copy_(self._v.sim.obs)
+        info = self._v._build_infos(np.array([done]))[0]
+        info.pop("terminal_observation", None)
+        info.pop("episode", None)
+        return obs, rew, done, info
+
+    def close(self):
+        self._v.close()
