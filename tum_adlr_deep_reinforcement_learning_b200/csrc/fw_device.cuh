@@ -123,7 +123,6 @@ enum IField {
     IF_NFEV = 38, IF_NATT = 39, IF_TERM = 40, IF_EP_LEN = 41, IF_ACT_F32 = 42,
     IF_COUNT = 43
 };
-__device__ __constant__ const int FX_OFF[6] = {0, 1, 3, 5, 6, 9};   // orders 1 2 2 1 3 3
 
 template <typename T> struct Soa {
     T* r;              // [RF_COUNT][n]
@@ -191,6 +190,12 @@ __device__ __forceinline__ void rng_noise4(unsigned long long seed, long long en
 template <typename T> __device__ __forceinline__ T clip(T v, T lo, T hi) { return v < lo ? lo : (v > hi ? hi : v); }
 template <typename T> __device__ __forceinline__ T sgn(T v) { return (T)((v > (T)0) - (v < (T)0)); }
 
+// out-of-line math for code that runs once per step (post-step commit, reset): one shared copy each instead of an
+// inlined expansion per call site keeps the kernel's cold instruction footprint small
+template <typename T> __device__ __noinline__ T atan2_ni(T a, T b) { return M<T>::atan2(a, b); }
+template <typename T> __device__ __noinline__ T asin_ni(T a) { return M<T>::asin(a); }
+template <typename T> __device__ __noinline__ void sincos_ni(T a, T* sn, T* cs) { M<T>::sincos(a, sn, cs); }
+
 // per-step dynamics context that is constant during one integration
 template <typename T> struct DynCtx {
     T cmd[3];      // constrained commands of elevon_right, elevon_left, throttle
@@ -203,9 +208,9 @@ template <typename T> struct DynCtx {
 template <typename T>
 __device__ __forceinline__ void rot_euler_apply(T phi, T th, T psi, const T v[3], T out[3]) {
     T sph, cph, sth, cth, sps, cps;
-    M<T>::sincos(phi, &sph, &cph);
-    M<T>::sincos(th, &sth, &cth);
-    M<T>::sincos(psi, &sps, &cps);
+    sincos_ni<T>(phi, &sph, &cph);
+    sincos_ni<T>(th, &sth, &cth);
+    sincos_ni<T>(psi, &sps, &cps);
     out[0] = cth * cps * v[0] + cth * sps * v[1] + (-sth) * v[2];
     out[1] = (sph * sth * cps - cph * sps) * v[0] + (sph * sth * sps + cph * cps) * v[1] + sph * cth * v[2];
     out[2] = (cph * sth * cps + sph * sps) * v[0] + (cph * sth * sps - sph * cps) * v[1] + cph * cth * v[2];
@@ -313,161 +318,195 @@ __device__ __forceinline__ int rhs(const DCfg<T>& c, const DynCtx<T>& x, const T
     return 0;
 }
 
-// Dormand-Prince 5(4) tableau (scipy rk.py class RK45).  Row 6 of A is B (FSAL), so stage 6's input is y_new.
-__device__ __constant__ const double RK_A[7][6] = {
+// Dormand-Prince 5(4) tableau (scipy rk.py class RK45) as "evaluation rows": row r gives the coefficients of the
+// stage derivatives K[0..] that form the input of RHS evaluation r.
+//   row 0      : y                                  -> f0 = fun(t0, y0)          (RungeKutta.__init__)
+//   rows 1..5  : y + h * sum_j A[r][j] K[j]         -> K[r]                      (rk_step)
+//   row 6      : y + h * sum_j B[j] K[j] = y_new    -> f_new (row 6 of A is B: FSAL)
+//   row 7      : y + h0 * K[0]                      -> f1 of select_initial_step (common.py:121-123)
+__device__ __constant__ const double RK_ROW[8][6] = {
     {0, 0, 0, 0, 0, 0},
     {1.0 / 5, 0, 0, 0, 0, 0},
     {3.0 / 40, 9.0 / 40, 0, 0, 0, 0},
     {44.0 / 45, -56.0 / 15, 32.0 / 9, 0, 0, 0},
     {19372.0 / 6561, -25360.0 / 2187, 64448.0 / 6561, -212.0 / 729, 0, 0},
     {9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656, 0},
-    {35.0 / 384, 0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84}};
+    {35.0 / 384, 0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84},
+    {1.0, 0, 0, 0, 0, 0}};
+__device__ __constant__ const int RK_NTERM[8] = {0, 1, 2, 3, 4, 5, 6, 1};
 __device__ __constant__ const double RK_E[7] = {-71.0 / 57600, 0, 71.0 / 16695, -71.0 / 1920, 17253.0 / 339200,
                                                 -22.0 / 525, 1.0 / 40};
 
-template <typename T> __device__ __forceinline__ T rms19(const T (&x)[FW_NY]) {
-    T s = 0;
-#pragma unroll
-    for (int i = 0; i < FW_NY; ++i) s += x[i] * x[i];
-    return M<T>::sqrt(s) / M<T>::sqrt((T)FW_NY);
-}
+template <typename T> __device__ __noinline__ T pow_ni(T x, T y) { return M<T>::pow(x, y); }
+
+#define FW_NK 18   // stage-derivative components kept: d/dt of y[18] (throttle rate state) is identically 0
 
 // scipy.integrate.solve_ivp(fun, (0, dt), y0) with RK45 defaults (pyfly.py:1393-1395), one env per thread.
-// The 7 stage derivatives live in shared memory, K[(stage * 19 + comp) * NT + tid]: 8-byte lanes of a warp hit 32
-// consecutive banks-pairs (conflict free) and the register file keeps y, y_stage and the RHS temporaries.
+//
+// Written as ONE loop around ONE inlined RHS instance (a state machine over the evaluation rows above): the hot
+// loop is ~3.5k SASS instructions instead of three inlined RHS copies, which is what keeps it inside the
+// instruction cache.  All lanes of a warp walk rows 0, 7, then 1..6 repeatedly in lock step, so the only
+// divergence left is lanes that finish their [0, dt] interval in fewer attempts than their neighbours.
+// Stage derivatives K[0..5] live in shared memory, K[(row * 18 + comp) * NT + tid] (conflict-free 8-byte lanes);
+// f_new (row 6) never leaves registers: it is consumed by the error estimate and becomes K[0] on acceptance.
 template <typename T, bool TURB, int NT>
 __device__ __forceinline__ int solve_rk45(const DCfg<T>& c, const DynCtx<T>& x, T (&y)[FW_NY], T elev0, T ail0,
                                           T* __restrict__ K, int& nfev, int& natt) {
-#define KS(s, i) K[((s) * FW_NY + (i)) * NT]
+#define KS(s, i) K[((s) * FW_NK + (i)) * NT]
     const T rtol = c.rtol, atol = c.atol, t_bound = c.dt;
     T ys[FW_NY], dyv[FW_NY];
-    int rc;
-    // RungeKutta.__init__: f = fun(t0, y0)  (t == 0: no write-back)
-    rc = rhs<T, TURB>(c, x, y, true, elev0, ail0, dyv);
-    nfev = 1;
+    T t = 0, t_new = 0, h = 0, h_abs = 0, d1 = 0, min_step = 0;
+    bool rejected = false;
+    int row = 0, rc = 0;
+    nfev = 0;
     natt = 0;
-    if (rc) return rc;
+    while (true) {
+        // ---- input of this evaluation ----
+        {
+            T acc[FW_NK];
 #pragma unroll
-    for (int i = 0; i < FW_NY; ++i) KS(0, i) = dyv[i];
-    // select_initial_step (common.py:68-134)
-    T h_abs;
-    {
-        T sc[FW_NY], tmp[FW_NY];
-#pragma unroll
-        for (int i = 0; i < FW_NY; ++i) { sc[i] = atol + M<T>::fabs(y[i]) * rtol; tmp[i] = y[i] / sc[i]; }
-        const T d0 = rms19(tmp);
-#pragma unroll
-        for (int i = 0; i < FW_NY; ++i) tmp[i] = dyv[i] / sc[i];
-        const T d1 = rms19(tmp);
-        T h0 = (d0 < (T)1e-5 || d1 < (T)1e-5) ? (T)1e-6 : (T)0.01 * d0 / d1;
-        h0 = M<T>::fmin(h0, t_bound);
-#pragma unroll
-        for (int i = 0; i < FW_NY; ++i) ys[i] = y[i] + h0 * dyv[i];
-        T f1[FW_NY];
-        rc = rhs<T, TURB>(c, x, ys, false, elev0, ail0, f1);
-        nfev++;
-        if (rc) return rc;
-#pragma unroll
-        for (int i = 0; i < FW_NY; ++i) tmp[i] = (f1[i] - dyv[i]) / sc[i];
-        const T d2 = rms19(tmp) / h0;
-        T h1;
-        if (d1 <= (T)1e-15 && d2 <= (T)1e-15) h1 = M<T>::fmax((T)1e-6, h0 * (T)1e-3);
-        else h1 = M<T>::pow((T)0.01 / M<T>::fmax(d1, d2), (T)0.2);
-        h_abs = M<T>::fmin(M<T>::fmin((T)100 * h0, h1), t_bound);
-    }
-    T t = 0;
-    while (t < t_bound) {
-        // RungeKutta._step_impl (rk.py:111-173); min_step = 10 * ulp(t)
-        const T min_step = (T)10 * (sizeof(T) == 8 ? (T)(::nextafter((double)t, CUDART_INF) - (double)t)
-                                                   : (T)(::nextafterf((float)t, CUDART_INF_F) - (float)t));
-        if (h_abs < min_step) h_abs = min_step;
-        bool accepted = false, rejected = false;
-        T t_new = t;
-        while (!accepted) {
-            if (h_abs < min_step) return 0;   // TOO_SMALL_STEP: solve_ivp status -1, ignored by pyfly
-            T h = h_abs;
-            t_new = t + h;
-            if (t_new - t_bound > (T)0) t_new = t_bound;
-            h = t_new - t;
-            h_abs = M<T>::fabs(h);
-            natt++;
-            // rk_step (rk.py:14-73): stages 1..5, then stage 6 = f(y_new)
+            for (int i = 0; i < FW_NK; ++i) acc[i] = 0;
+            const int nterm = RK_NTERM[row];
 #pragma unroll 1
-            for (int s = 1; s <= 6; ++s) {
-                T acc[FW_NY];
+            for (int j = 0; j < nterm; ++j) {
+                const T a = (T)RK_ROW[row][j];
 #pragma unroll
-                for (int i = 0; i < FW_NY; ++i) acc[i] = 0;
-#pragma unroll 1
-                for (int j = 0; j < s; ++j) {
-                    const T a = (T)RK_A[s][j];
-#pragma unroll
-                    for (int i = 0; i < FW_NY; ++i) acc[i] += KS(j, i) * a;
-                }
-#pragma unroll
-                for (int i = 0; i < FW_NY; ++i) ys[i] = y[i] + acc[i] * h;
-                rc = rhs<T, TURB>(c, x, ys, false, elev0, ail0, dyv);
-                nfev++;
-                if (rc) return rc;
-#pragma unroll
-                for (int i = 0; i < FW_NY; ++i) KS(s, i) = dyv[i];
+                for (int i = 0; i < FW_NK; ++i) acc[i] += KS(j, i) * a;
             }
-            // ys == y_new, dyv == f_new; error estimate (rk.py:100-104,139-141)
-            T errsq = 0;
+#pragma unroll
+            for (int i = 0; i < FW_NK; ++i) ys[i] = (row == 0) ? y[i] : y[i] + acc[i] * h;
+            ys[18] = y[18];
+        }
+        rc = rhs<T, TURB>(c, x, ys, row == 0, elev0, ail0, dyv);
+        nfev++;
+        if (rc) break;
+        // ---- what the evaluation was for ----
+        if (row >= 1 && row <= 5) {
+#pragma unroll
+            for (int i = 0; i < FW_NK; ++i) KS(row, i) = dyv[i];
+            row++;
+            continue;
+        }
+        if (row == 0) {
+            // RungeKutta.__init__: f = fun(t0, y0); select_initial_step part 1 (common.py:68-123)
+            T s0 = 0, s1 = 0;
 #pragma unroll
             for (int i = 0; i < FW_NY; ++i) {
+                const T inv = (T)1 / (atol + M<T>::fabs(y[i]) * rtol);
+                const T a = y[i] * inv, b = dyv[i] * inv;
+                s0 += a * a;
+                s1 += b * b;
+            }
+#pragma unroll
+            for (int i = 0; i < FW_NK; ++i) KS(0, i) = dyv[i];
+            const T d0 = M<T>::sqrt(s0) / M<T>::sqrt((T)FW_NY);
+            d1 = M<T>::sqrt(s1) / M<T>::sqrt((T)FW_NY);
+            T h0 = (d0 < (T)1e-5 || d1 < (T)1e-5) ? (T)1e-6 : (T)0.01 * d0 / d1;
+            h = M<T>::fmin(h0, t_bound);       // h doubles as h0 for row 7
+            row = 7;
+            continue;
+        }
+        bool new_attempt = false;
+        if (row == 7) {
+            // select_initial_step part 2 (common.py:124-134), order = error_estimator_order = 4
+            T s2 = 0;
+#pragma unroll
+            for (int i = 0; i < FW_NK; ++i) {
+                const T inv = (T)1 / (atol + M<T>::fabs(y[i]) * rtol);
+                const T d = (dyv[i] - KS(0, i)) * inv;
+                s2 += d * d;
+            }
+            const T d2 = (M<T>::sqrt(s2) / M<T>::sqrt((T)FW_NY)) / h;
+            T h1;
+            if (d1 <= (T)1e-15 && d2 <= (T)1e-15) h1 = M<T>::fmax((T)1e-6, h * (T)1e-3);
+            else h1 = pow_ni<T>((T)0.01 / M<T>::fmax(d1, d2), (T)0.2);
+            h_abs = M<T>::fmin(M<T>::fmin((T)100 * h, h1), t_bound);
+            new_attempt = true;
+            t = 0;
+        } else {
+            // row 6: ys == y_new, dyv == f_new.  Error estimate and step-size control (rk.py:100-104, 139-166)
+            T errsq = 0;
+#pragma unroll
+            for (int i = 0; i < FW_NK; ++i) {
                 T acc = 0;
 #pragma unroll
-                for (int j = 0; j < 7; ++j) acc += KS(j, i) * (T)RK_E[j];
+                for (int j = 0; j < 6; ++j) acc += KS(j, i) * (T)RK_E[j];
+                acc += dyv[i] * (T)RK_E[6];
                 const T scl = atol + M<T>::fmax(M<T>::fabs(y[i]), M<T>::fabs(ys[i])) * rtol;
                 const T ei = acc * h / scl;
                 errsq += ei * ei;
             }
             const T err = M<T>::sqrt(errsq) / M<T>::sqrt((T)FW_NY);
+            // err == 0: pow(0, -0.2) = inf -> min(10, inf) = MAX_FACTOR, the same as scipy's special case
+            const T pf = (T)0.9 * pow_ni<T>(err, (T)-0.2);
             if (err < (T)1) {
-                T factor = (err == (T)0) ? (T)10 : M<T>::fmin((T)10, (T)0.9 * M<T>::pow(err, (T)-0.2));
+                T factor = (err == (T)0) ? (T)10 : M<T>::fmin((T)10, pf);
                 if (rejected) factor = M<T>::fmin((T)1, factor);
                 h_abs *= factor;
-                accepted = true;
+                t = t_new;
+#pragma unroll
+                for (int i = 0; i < FW_NK; ++i) { y[i] = ys[i]; KS(0, i) = dyv[i]; }   // FSAL
+                if (!(t < t_bound)) break;                   // solver.status == 'finished'
+                rejected = false;
+                new_attempt = true;
             } else {
-                h_abs *= M<T>::fmax((T)0.2, (T)0.9 * M<T>::pow(err, (T)-0.2));
+                h_abs *= M<T>::fmax((T)0.2, pf);
                 rejected = true;
             }
         }
-        t = t_new;
-#pragma unroll
-        for (int i = 0; i < FW_NY; ++i) { y[i] = ys[i]; KS(0, i) = dyv[i]; }   // FSAL
+        if (new_attempt) {
+            // top of RungeKutta._step_impl (rk.py:111-127): min_step = 10 * ulp(t)
+            min_step = (T)10 * (sizeof(T) == 8 ? (T)(::nextafter((double)t, CUDART_INF) - (double)t)
+                                               : (T)(::nextafterf((float)t, CUDART_INF_F) - (float)t));
+            if (h_abs < min_step) h_abs = min_step;
+        }
+        // top of the `while not step_accepted` loop (rk.py:129-141)
+        if (h_abs < min_step) break;        // TOO_SMALL_STEP: solve_ivp returns status -1, pyfly ignores it
+        t_new = t + h_abs;
+        if (t_new - t_bound > (T)0) t_new = t_bound;
+        h = t_new - t;
+        h_abs = M<T>::fabs(h);
+        natt++;
+        row = 1;
     }
-    return 0;
+    return rc;
 #undef KS
 }
 
-// classical RK4 x substeps, register resident (throughput mode; same RHS with its clip/constraint side effects)
+// classical RK4 x substeps, register resident (throughput mode; same RHS with its clip/constraint side effects),
+// also one loop around one RHS instance.
 template <typename T, bool TURB>
 __device__ __forceinline__ int solve_rk4(const DCfg<T>& c, const DynCtx<T>& x, T (&y)[FW_NY], T elev0, T ail0,
                                          int& nfev, int& natt) {
     const int n = c.rk4_substeps > 0 ? c.rk4_substeps : 1;
     const T h = c.dt / (T)n;
-    T k[FW_NY], acc[FW_NY], ys[FW_NY];
-    int rc;
+    T k[FW_NY], acc[FW_NK], ys[FW_NY];
+    int rc = 0;
     nfev = 0;
     natt = n;
+#pragma unroll
+    for (int i = 0; i < FW_NK; ++i) acc[i] = 0;
+#pragma unroll
+    for (int i = 0; i < FW_NY; ++i) k[i] = 0;
 #pragma unroll 1
-    for (int s = 0; s < n; ++s) {
-        if ((rc = rhs<T, TURB>(c, x, y, s == 0, elev0, ail0, k))) return rc;
+    for (int e = 0; e < 4 * n; ++e) {
+        const int st = e & 3;
+        const T cs = (st == 0) ? (T)0 : ((st == 3) ? h : (T)0.5 * h);
 #pragma unroll
-        for (int i = 0; i < FW_NY; ++i) { acc[i] = k[i]; ys[i] = y[i] + (T)0.5 * h * k[i]; }
-        if ((rc = rhs<T, TURB>(c, x, ys, false, elev0, ail0, k))) return rc;
+        for (int i = 0; i < FW_NK; ++i) ys[i] = y[i] + cs * k[i];
+        ys[18] = y[18];
+        rc = rhs<T, TURB>(c, x, ys, e == 0, elev0, ail0, k);
+        nfev++;
+        if (rc) break;
+        const T w = (st == 1 || st == 2) ? (T)2 : (T)1;
 #pragma unroll
-        for (int i = 0; i < FW_NY; ++i) { acc[i] += (T)2 * k[i]; ys[i] = y[i] + (T)0.5 * h * k[i]; }
-        if ((rc = rhs<T, TURB>(c, x, ys, false, elev0, ail0, k))) return rc;
+        for (int i = 0; i < FW_NK; ++i) acc[i] = (st == 0) ? k[i] : acc[i] + w * k[i];
+        if (st == 3) {
 #pragma unroll
-        for (int i = 0; i < FW_NY; ++i) { acc[i] += (T)2 * k[i]; ys[i] = y[i] + h * k[i]; }
-        if ((rc = rhs<T, TURB>(c, x, ys, false, elev0, ail0, k))) return rc;
-#pragma unroll
-        for (int i = 0; i < FW_NY; ++i) y[i] = y[i] + h / (T)6 * (acc[i] + k[i]);
-        nfev += 4;
+            for (int i = 0; i < FW_NK; ++i) y[i] = y[i] + h / (T)6 * acc[i];
+        }
     }
-    return 0;
+    return rc;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -478,11 +517,20 @@ template <typename T> __device__ __forceinline__ T py_mod(T a, T b) {
     if (m != (T)0 && ((m < (T)0) != (b < (T)0))) m += b;
     return m;
 }
-// _get_error (fixed_wing.py:1318-1344); roll wraps (pyfly_config.json "wrap": true)
+// _get_error (fixed_wing.py:1318-1344); roll wraps (pyfly_config.json "wrap": true):
+//   dist = (value - target + pi) % (2 pi) - pi.   Python's float % is fmod plus a sign fix-up; for |x| < 4 pi the exact
+// fmod is a single Sterbenz-exact subtraction, so the generic (large, loop-based) fmod is kept off the hot path.
+template <typename T> __device__ __noinline__ T py_mod_generic(T a, T b) { return py_mod(a, b); }
 template <typename T> __device__ __forceinline__ T err_roll(T target, T value) {
-    const T PI = (T)3.141592653589793238462643383279502884;
-    T dist = py_mod(value - target + PI, (T)2 * PI) - PI;
-    if (dist < -PI) dist += (T)2 * PI;
+    const T PI = (T)3.141592653589793238462643383279502884, TWO_PI = (T)2 * PI;
+    const T xx = value - target + PI;
+    T m;
+    if (xx >= (T)0 && xx < TWO_PI) m = xx;
+    else if (xx >= TWO_PI && xx < (T)2 * TWO_PI) m = xx - TWO_PI;      // exact (Sterbenz)
+    else if (xx < (T)0 && xx > -TWO_PI) m = xx + TWO_PI;              // fmod keeps x, python adds the divisor
+    else m = py_mod_generic<T>(xx, TWO_PI);
+    T dist = m - PI;
+    if (dist < -PI) dist += TWO_PI;
     return dist;
 }
 
@@ -507,32 +555,48 @@ template <typename T> struct EnvRegs {
     unsigned long long episode;
 };
 
-// advance the six shaping filters by one sample and evaluate y = C x + D u  (lsim recurrence, dryden.py:22-39)
-template <typename T>
-__device__ __forceinline__ void turb_eval(const DCfg<T>& c, const T fx[12], const T fu[4], T tl[3], T ta[3]) {
+// The six Dryden shaping filters have fixed orders (dryden.py:126-143): H_u 1, H_v 2, H_w 2, H_p 1, H_q 3, H_r 3,
+// so their states pack into fx[12] at offsets 0,1,3,5,6,9 and every loop below has a compile-time trip count.
+template <typename T, int ORD, int OFF>
+__device__ __forceinline__ T filt_out(const DFilter<T>& F, const T (&fx)[12], const T (&fu)[4]) {
+    T yv = 0;
 #pragma unroll
-    for (int f = 0; f < 6; ++f) {
-        const DFilter<T>& F = c.filt[f];
-        T yv = 0;
-        for (int a = 0; a < F.order; ++a) yv += fx[FX_OFF[f] + a] * F.C[a];
-        yv += fu[F.noise_row] * F.D;
-        if (f < 3) tl[f] = yv; else ta[f - 3] = yv;
-    }
+    for (int a = 0; a < ORD; ++a) yv += fx[OFF + a] * F.C[a];
+    return yv + fu[F.noise_row & 3] * F.D;
 }
-template <typename T>
-__device__ __forceinline__ void turb_advance(const DCfg<T>& c, T fx[12], T fu[4], const T un[4]) {
+template <typename T, int ORD, int OFF>
+__device__ __forceinline__ void filt_adv(const DFilter<T>& F, T (&fx)[12], const T (&fu)[4], const T (&un)[4]) {
+    T xn[ORD];
+    const T up = fu[F.noise_row & 3], uc = un[F.noise_row & 3];
 #pragma unroll
-    for (int f = 0; f < 6; ++f) {
-        const DFilter<T>& F = c.filt[f];
-        const int n = F.order, o = FX_OFF[f];
-        T xn[3];
-        for (int a = 0; a < n; ++a) {
-            T s = 0;
-            for (int b = 0; b < n; ++b) s += fx[o + b] * F.Ad[b * n + a];
-            xn[a] = s + fu[F.noise_row] * F.Bd0[a] + un[F.noise_row] * F.Bd1[a];
-        }
-        for (int a = 0; a < n; ++a) fx[o + a] = xn[a];
+    for (int a = 0; a < ORD; ++a) {
+        T sacc = 0;
+#pragma unroll
+        for (int b = 0; b < ORD; ++b) sacc += fx[OFF + b] * F.Ad[b * ORD + a];
+        xn[a] = sacc + up * F.Bd0[a] + uc * F.Bd1[a];
     }
+#pragma unroll
+    for (int a = 0; a < ORD; ++a) fx[OFF + a] = xn[a];
+}
+// y = C x + D u  (lsim output equation, dryden.py:22-39)
+template <typename T>
+__device__ __forceinline__ void turb_eval(const DCfg<T>& c, const T (&fx)[12], const T (&fu)[4], T (&tl)[3], T (&ta)[3]) {
+    tl[0] = filt_out<T, 1, 0>(c.filt[0], fx, fu);
+    tl[1] = filt_out<T, 2, 1>(c.filt[1], fx, fu);
+    tl[2] = filt_out<T, 2, 3>(c.filt[2], fx, fu);
+    ta[0] = filt_out<T, 1, 5>(c.filt[3], fx, fu);
+    ta[1] = filt_out<T, 3, 6>(c.filt[4], fx, fu);
+    ta[2] = filt_out<T, 3, 9>(c.filt[5], fx, fu);
+}
+// x_{k+1} = Ad x_k + Bd0 u_k + Bd1 u_{k+1}  (lsim recurrence, row-vector convention)
+template <typename T>
+__device__ __forceinline__ void turb_advance(const DCfg<T>& c, T (&fx)[12], T (&fu)[4], const T (&un)[4]) {
+    filt_adv<T, 1, 0>(c.filt[0], fx, fu, un);
+    filt_adv<T, 2, 1>(c.filt[1], fx, fu, un);
+    filt_adv<T, 2, 3>(c.filt[2], fx, fu, un);
+    filt_adv<T, 1, 5>(c.filt[3], fx, fu, un);
+    filt_adv<T, 3, 6>(c.filt[4], fx, fu, un);
+    filt_adv<T, 3, 9>(c.filt[5], fx, fu, un);
 #pragma unroll
     for (int r = 0; r < 4; ++r) fu[r] = un[r];
 }
@@ -540,7 +604,7 @@ __device__ __forceinline__ void turb_advance(const DCfg<T>& c, T fx[12], T fu[4]
 // scaled noise sample k for env (injected buffer or Philox)
 template <typename T>
 __device__ __forceinline__ void noise_sample(const DCfg<T>& c, const Soa<T>& S, int env, unsigned long long episode,
-                                             int k, T un[4]) {
+                                             int k, T (&un)[4]) {
     double z[4];
     if (S.noise) {
         const int kk = k < S.noise_len ? k : S.noise_len - 1;

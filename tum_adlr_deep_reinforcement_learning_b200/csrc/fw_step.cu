@@ -160,9 +160,9 @@ __global__ void __launch_bounds__(NT) step_kernel(const __grid_constant__ DCfg<T
 #pragma unroll
         for (int i = 0; i < 4; ++i) y[i] = y[i] / nrm;
         const T e0 = y[0], e1 = y[1], e2 = y[2], e3 = y[3];
-        roll = M<T>::atan2((T)2 * (e0 * e1 + e2 * e3), e0 * e0 + e3 * e3 - e1 * e1 - e2 * e2);
-        pitch = M<T>::asin((T)2 * (e0 * e2 - e1 * e3));
-        const T yaw = M<T>::atan2((T)2 * (e0 * e3 + e1 * e2), e0 * e0 + e1 * e1 - e2 * e2 - e3 * e3);
+        roll = atan2_ni<T>((T)2 * (e0 * e1 + e2 * e3), e0 * e0 + e3 * e3 - e1 * e1 - e2 * e2);
+        pitch = asin_ni<T>((T)2 * (e0 * e2 - e1 * e3));
+        const T yaw = atan2_ni<T>((T)2 * (e0 * e3 + e1 * e2), e0 * e0 + e1 * e1 - e2 * e2 - e3 * e3);
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             if (!fail) {
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(NT) step_kernel(const __grid_constant__ DCfg<T
             rot_euler_apply(roll, pitch, yaw, x.wind, wb);
             const T a0 = y[10] - (wb[0] + x.tl[0]), a1 = y[11] - (wb[1] + x.tl[1]), a2 = y[12] - (wb[2] + x.tl[2]);
             T Van = M<T>::sqrt(a0 * a0 + a1 * a1 + a2 * a2);
-            const T al = M<T>::atan2(a2, a0), be = M<T>::asin(a1 / Van);
+            const T al = atan2_ni<T>(a2, a0), be = asin_ni<T>(a1 / Van);
             if (c.va_con_max > (T)0 && Van > c.va_con_max) fail = FW_TERM_VA;
             else {
                 if (Van < c.va_value_min) Van = c.va_value_min;
@@ -611,13 +611,13 @@ struct FwHandle {
     unsigned long long random_step;
 };
 
-static const int NT_RK45_F64 = 64;     // 7*19*64*8 = 68096 B of stage storage per block: 3 blocks / SM
-static const int NT_RK45_F32 = 128;    // 7*19*128*4 = 68096 B
+static const int NT_RK45_F64 = 64;     // 6*18*64*8 = 55296 B of stage storage per block: 4 blocks (8 warps) / SM
+static const int NT_RK45_F32 = 128;    // 6*18*128*4 = 55296 B
 static const int NT_RK4 = 128;
 
 template <typename T, int INTEG, int NT>
 static int launch_step_t(FwHandle* h, const DCfg<T>& c, const Soa<T>& S, const StepIO& io, cudaStream_t st) {
-    const size_t smem = (INTEG == FW_INT_RK45_SCIPY) ? (size_t)7 * FW_NY * NT * sizeof(T) : 0;
+    const size_t smem = (INTEG == FW_INT_RK45_SCIPY) ? (size_t)6 * FW_NK * NT * sizeof(T) : 0;
     const int grid = (h->n + NT - 1) / NT;
     if (c.turbulence) {
         auto k = step_kernel<T, INTEG, true, NT>;
@@ -636,7 +636,12 @@ static int launch_step_t(FwHandle* h, const DCfg<T>& c, const Soa<T>& S, const S
 
 static int launch_step(FwHandle* h, const StepIO& io, cudaStream_t st) {
     if (h->cfg.precision == FW_F64) {
-        if (h->cfg.integrator == FW_INT_RK45_SCIPY) return launch_step_t<double, FW_INT_RK45_SCIPY, NT_RK45_F64>(h, h->c64, h->s64, io, st);
+        if (h->cfg.integrator == FW_INT_RK45_SCIPY) {
+            // block-size experiment hook (FW_NT=32|64), default 64
+            static const int nt = getenv("FW_NT") ? atoi(getenv("FW_NT")) : NT_RK45_F64;
+            if (nt == 32) return launch_step_t<double, FW_INT_RK45_SCIPY, 32>(h, h->c64, h->s64, io, st);
+            return launch_step_t<double, FW_INT_RK45_SCIPY, NT_RK45_F64>(h, h->c64, h->s64, io, st);
+        }
         return launch_step_t<double, FW_INT_RK4_FIXED, NT_RK4>(h, h->c64, h->s64, io, st);
     }
     if (h->cfg.integrator == FW_INT_RK45_SCIPY) return launch_step_t<float, FW_INT_RK45_SCIPY, NT_RK45_F32>(h, h->c32, h->s32, io, st);
