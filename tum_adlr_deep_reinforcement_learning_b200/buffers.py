@@ -1,0 +1,166 @@
+"""On-device rollout storage + GAE for PPO, and the running-moment normaliser of VecNormalize.
+
+Mirrors the reference's forked SB3:
+  RolloutBuffer.reset / add / compute_returns_and_advantage / get   (stable_baselines3/common/buffers.py:259-389)
+  RunningMeanStd.update (Chan parallel update)                       (common/running_mean_std.py:19-39)
+  VecNormalize.step_wait / normalize_obs / normalize_reward          (common/vec_env/vec_normalize.py:106-178)
+Everything is a CUDA tensor: time-major [T, N, ...] float32 arrays that never leave HBM; GAE runs in the
+hand-written fw_gae kernel (bit-exact with the reference's mixed f32/f64 arithmetic); minibatches are
+device-side gathers of a device-side permutation instead of host numpy slices + H2D copies.
+"""
+from collections import namedtuple
+
+import torch
+
+from . import batched as bt
+
+RolloutBufferSamples = namedtuple("RolloutBufferSamples", ["observations", "actions", "old_values", "old_log_prob",
+                                                           "advantages", "returns"])
+
+
+class RolloutBuffer:
+    def __init__(self, buffer_size, n_envs, obs_dim=14, action_dim=3, device="cuda", gae_lambda=0.95, gamma=0.99):
+        self.buffer_size, self.n_envs = int(buffer_size), int(n_envs)
+        self.obs_dim, self.action_dim = obs_dim, action_dim
+        self.device = torch.device(device)
+        self.gae_lambda, self.gamma = gae_lambda, gamma
+        T, N, d = self.buffer_size, self.n_envs, self.device
+        self.observations = torch.zeros(T, N, obs_dim, dtype=torch.float32, device=d)
+        self.actions = torch.zeros(T, N, action_dim, dtype=torch.float32, device=d)
+        self.rewards = torch.zeros(T, N, dtype=torch.float32, device=d)
+        self.dones = torch.zeros(T, N, dtype=torch.float32, device=d)
+        self.values = torch.zeros(T, N, dtype=torch.float32, device=d)
+        self.log_probs = torch.zeros(T, N, dtype=torch.float32, device=d)
+        self.advantages = torch.zeros(T, N, dtype=torch.float32, device=d)
+        self.returns = torch.zeros(T, N, dtype=torch.float32, device=d)
+        self.pos = 0
+        self.full = False
+
+    def reset(self):
+        self.pos = 0
+        self.full = False
+
+    def add(self, obs, action, reward, done, value, log_prob):
+        """`done` is the "episode ended before obs" flag of the PREVIOUS step, exactly like the reference stores
+        `self._last_dones` (on_policy_algorithm.py:178-180)."""
+        t = self.pos
+        self.observations[t].copy_(obs)
+        self.actions[t].copy_(action)
+        self.rewards[t].copy_(reward)
+        self.dones[t].copy_(done)
+        self.values[t].copy_(value.reshape(-1))
+        self.log_probs[t].copy_(log_prob.reshape(-1))
+        self.pos += 1
+        if self.pos == self.buffer_size:
+            self.full = True
+
+    def compute_returns_and_advantage(self, last_values, dones):
+        """GAE(lambda) without time-limit bootstrapping, as buffers.py:304-333.  `dones`: the done vector returned by
+        the final env.step (bool / uint8)."""
+        adv, ret = bt.gae(self.rewards, self.values, self.dones, last_values.reshape(-1).to(torch.float32),
+                          dones.reshape(-1).to(torch.uint8), self.gamma, self.gae_lambda)
+        self.advantages, self.returns = adv, ret
+
+    def flat(self, x):
+        """swap_and_flatten (buffers.py:51-64): [T, N, ...] -> [N*T, ...] in env-major order."""
+        shape = x.shape
+        return x.transpose(0, 1).reshape(shape[0] * shape[1], *shape[2:])
+
+    def get(self, batch_size=None, generator=None):
+        assert self.full, "rollout buffer is not full"
+        total = self.buffer_size * self.n_envs
+        perm = torch.randperm(total, device=self.device, generator=generator)
+        flat = [self.flat(x) for x in (self.observations, self.actions, self.values, self.log_probs, self.advantages,
+                                       self.returns)]
+        if batch_size is None:
+            batch_size = total
+        for start in range(0, total, batch_size):
+            idx = perm[start:start + batch_size]
+            yield RolloutBufferSamples(*(f.index_select(0, idx) for f in flat))
+
+
+class RunningMeanStd:
+    """running_mean_std.py:6-39 on the device, float64 statistics.  `sync(group)` all-reduces the moments so that every
+    data-parallel rank normalises identically."""
+
+    def __init__(self, shape=(), device="cuda", epsilon=1e-4):
+        self.mean = torch.zeros(shape, dtype=torch.float64, device=device)
+        self.var = torch.ones(shape, dtype=torch.float64, device=device)
+        self.count = torch.tensor(float(epsilon), dtype=torch.float64, device=device)
+
+    def update(self, x):
+        x = x.to(torch.float64)
+        self.update_from_moments(x.mean(dim=0), x.var(dim=0, unbiased=False), x.shape[0])
+
+    def update_from_moments(self, batch_mean, batch_var, batch_count):
+        delta = batch_mean - self.mean
+        tot = self.count + batch_count
+        new_mean = self.mean + delta * batch_count / tot
+        m_2 = self.var * self.count + batch_var * batch_count + delta.square() * self.count * batch_count / tot
+        self.mean, self.var, self.count = new_mean, m_2 / tot, tot
+
+    def sync(self, dist):
+        """Merge the per-rank moments with one all-reduce of (count, count*mean, count*(var + mean^2))."""
+        packed = torch.cat([self.count.reshape(1), (self.count * self.mean).reshape(-1),
+                            (self.count * (self.var + self.mean.square())).reshape(-1)])
+        dist.all_reduce(packed)
+        k = self.mean.numel()
+        cnt = packed[0]
+        mean = (packed[1:1 + k] / cnt).reshape(self.mean.shape)
+        ex2 = (packed[1 + k:] / cnt).reshape(self.mean.shape)
+        world = dist.get_world_size()
+        self.mean, self.var, self.count = mean, (ex2 - mean.square()).clamp_min(0), cnt / world
+
+
+class DeviceVecNormalize:
+    """VecNormalize (vec_normalize.py:13-243) over device tensors: running obs / return statistics, clipped
+    normalisation, `ret = ret * gamma + r`, `ret[done] = 0`."""
+
+    def __init__(self, n_envs, obs_dim=14, device="cuda", norm_obs=True, norm_reward=True, clip_obs=10.0,
+                 clip_reward=10.0, gamma=0.99, epsilon=1e-8, training=True):
+        self.obs_rms = RunningMeanStd((obs_dim,), device)
+        self.ret_rms = RunningMeanStd((), device)
+        self.ret = torch.zeros(n_envs, dtype=torch.float64, device=device)
+        self.norm_obs, self.norm_reward = norm_obs, norm_reward
+        self.clip_obs, self.clip_reward, self.gamma, self.epsilon = clip_obs, clip_reward, gamma, epsilon
+        self.training = training
+
+    def normalize_obs(self, obs):
+        if not self.norm_obs:
+            return obs
+        o = (obs.to(torch.float64) - self.obs_rms.mean) / torch.sqrt(self.obs_rms.var + self.epsilon)
+        return o.clamp(-self.clip_obs, self.clip_obs).to(torch.float32)
+
+    def normalize_reward(self, rew):
+        if not self.norm_reward:
+            return rew
+        r = rew.to(torch.float64) / torch.sqrt(self.ret_rms.var + self.epsilon)
+        return r.clamp(-self.clip_reward, self.clip_reward).to(torch.float32)
+
+    def reset(self, obs):
+        self.ret.zero_()
+        if self.training:
+            self.obs_rms.update(obs)
+        return self.normalize_obs(obs)
+
+    def step(self, obs, rew, done):
+        """vec_normalize.py:106-127 order: update return, update obs stats, normalise, zero finished returns."""
+        self.ret = self.ret * self.gamma + rew.to(torch.float64)
+        if self.training:
+            self.obs_rms.update(obs)
+            self.ret_rms.update(self.ret)
+        out = self.normalize_obs(obs), self.normalize_reward(rew)
+        self.ret = torch.where(done.bool(), torch.zeros_like(self.ret), self.ret)
+        return out
+
+    def sync(self, dist):
+        self.obs_rms.sync(dist)
+        self.ret_rms.sync(dist)
+
+    def state_dict(self):
+        return {"obs_mean": self.obs_rms.mean, "obs_var": self.obs_rms.var, "obs_count": self.obs_rms.count,
+                "ret_mean": self.ret_rms.mean, "ret_var": self.ret_rms.var, "ret_count": self.ret_rms.count}
+
+    def load_state_dict(self, sd):
+        self.obs_rms.mean, self.obs_rms.var, self.obs_rms.count = sd["obs_mean"], sd["obs_var"], sd["obs_count"]
+        self.ret_rms.mean, self.ret_rms.var, self.ret_rms.count = sd["ret_mean"], sd["ret_var"], sd["ret_count"]

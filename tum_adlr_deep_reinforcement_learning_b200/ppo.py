@@ -1,0 +1,215 @@
+"""PPO over the batched CUDA simulator: rollout collection, GAE and the clipped-surrogate update all stay in HBM.
+
+Re-hosts the reference's on-policy loop on device tensors:
+  OnPolicyAlgorithm.collect_rollouts / learn   (stable_baselines3/common/on_policy_algorithm.py:123-246)
+  PPO.train                                    (stable_baselines3/ppo/ppo.py:133-240; defaults :69-79)
+  ActorCriticPolicy, MlpPolicy                 (stable_baselines3/common/policies.py:331-637; net_arch pi/vf [64,64], tanh,
+                                               state-independent log_std initialised to 0)
+The policy MLP stays in PyTorch (north_star).  Data parallel: one process per GPU, envs sharded by global env id, no
+traffic on the env step; per optimiser step ONE all-reduce over the flattened gradient, per rollout one small
+all-reduce of the VecNormalize moments.  Advantage normalisation is per minibatch and rank-local as in ppo.py:170.
+"""
+import math
+import time
+
+import torch
+import torch.nn as nn
+
+from .buffers import DeviceVecNormalize, RolloutBuffer
+from .vec_env import FixedWingVecEnv
+
+
+class ActorCritic(nn.Module):
+    def __init__(self, obs_dim=14, action_dim=3, hidden=(64, 64), log_std_init=0.0):
+        super().__init__()
+
+        def mlp():
+            layers, d = [], obs_dim
+            for h in hidden:
+                layers += [nn.Linear(d, h), nn.Tanh()]
+                d = h
+            return nn.Sequential(*layers), d
+
+        self.pi, d_pi = mlp()
+        self.vf, d_vf = mlp()
+        self.action_net = nn.Linear(d_pi, action_dim)
+        self.value_net = nn.Linear(d_vf, 1)
+        self.log_std = nn.Parameter(torch.full((action_dim,), float(log_std_init)))
+        # SB3 orthogonal init: sqrt(2) for the extractors, 0.01 for the action head, 1 for the value head
+        for m in list(self.pi) + list(self.vf):
+            if isinstance(m, nn.Linear):
+                nn.init.orthogonal_(m.weight, gain=math.sqrt(2))
+                nn.init.zeros_(m.bias)
+        nn.init.orthogonal_(self.action_net.weight, gain=0.01)
+        nn.init.zeros_(self.action_net.bias)
+        nn.init.orthogonal_(self.value_net.weight, gain=1.0)
+        nn.init.zeros_(self.value_net.bias)
+
+    def _dist(self, obs):
+        mean = self.action_net(self.pi(obs))
+        return mean, self.log_std.expand_as(mean)
+
+    @staticmethod
+    def _log_prob(actions, mean, log_std):
+        var = torch.exp(2 * log_std)
+        return (-((actions - mean) ** 2) / (2 * var) - log_std - 0.5 * math.log(2 * math.pi)).sum(dim=1)
+
+    def forward(self, obs, deterministic=False):
+        mean, log_std = self._dist(obs)
+        actions = mean if deterministic else mean + torch.exp(log_std) * torch.randn_like(mean)
+        values = self.value_net(self.vf(obs)).squeeze(-1)
+        return actions, values, self._log_prob(actions, mean, log_std)
+
+    def evaluate_actions(self, obs, actions):
+        mean, log_std = self._dist(obs)
+        values = self.value_net(self.vf(obs)).squeeze(-1)
+        entropy = (0.5 + 0.5 * math.log(2 * math.pi) + log_std).sum(dim=1)
+        return values, self._log_prob(actions, mean, log_std), entropy
+
+    def predict_values(self, obs):
+        return self.value_net(self.vf(obs)).squeeze(-1)
+
+
+def allreduce_gradients(params, dist, world_size):
+    """One all-reduce(SUM) over the flattened gradient (~10.5k fp32 = 42 KB: latency bound), then the mean."""
+    grads = [p.grad for p in params if p.grad is not None]
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat)
+    flat /= world_size
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].view_as(g))
+        off += n
+    return flat
+
+
+class PPO:
+    """learning_rate 3e-4, n_epochs 10, gamma 0.99, gae_lambda 0.95, clip_range 0.2, ent_coef 0, vf_coef 0.5,
+    max_grad_norm 0.5 are the reference defaults (ppo.py:69-79).  n_steps / batch_size default to values that make
+    sense at thousands of envs per GPU (SB3's 2048 / 64 are sized for a handful of envs)."""
+
+    def __init__(self, env: FixedWingVecEnv, n_steps=32, batch_size=32768, n_epochs=10, learning_rate=3e-4, gamma=0.99,
+                 gae_lambda=0.95, clip_range=0.2, ent_coef=0.0, vf_coef=0.5, max_grad_norm=0.5, normalize=True,
+                 seed=0, dist=None):
+        self.env = env
+        self.device = env.device
+        self.n_envs = env.num_envs
+        self.n_steps, self.batch_size, self.n_epochs = n_steps, batch_size, n_epochs
+        self.gamma, self.gae_lambda, self.clip_range = gamma, gae_lambda, clip_range
+        self.ent_coef, self.vf_coef, self.max_grad_norm = ent_coef, vf_coef, max_grad_norm
+        self.dist = dist
+        self.world = dist.get_world_size() if dist is not None else 1
+        self.rank = dist.get_rank() if dist is not None else 0
+        torch.manual_seed(seed)                      # identical initial weights on every rank
+        self.policy = ActorCritic().to(self.device)
+        torch.manual_seed(seed + 1000 * (self.rank + 1))   # different action noise per rank
+        self.optimizer = torch.optim.Adam(self.policy.parameters(), lr=learning_rate, eps=1e-5)
+        self.buffer = RolloutBuffer(n_steps, self.n_envs, device=self.device, gae_lambda=gae_lambda, gamma=gamma)
+        self.norm = DeviceVecNormalize(self.n_envs, device=self.device, gamma=gamma, norm_obs=normalize,
+                                       norm_reward=normalize)
+        self.num_timesteps = 0
+        self._last_obs = None
+        self._last_dones = None
+        # on-device episode statistics (Monitor-equivalent, no per-env python objects)
+        self.ep_ret_sum = torch.zeros((), dtype=torch.float64, device=self.device)
+        self.ep_len_sum = torch.zeros((), dtype=torch.float64, device=self.device)
+        self.ep_count = torch.zeros((), dtype=torch.float64, device=self.device)
+        self._run_ret = torch.zeros(self.n_envs, dtype=torch.float64, device=self.device)
+        self._run_len = torch.zeros(self.n_envs, dtype=torch.float64, device=self.device)
+        self.logs = []
+
+    # ------------------------------------------------------------------ rollout
+    def _setup(self):
+        raw = self.env.reset_tensor()
+        self._last_obs = self.norm.reset(raw).clone()
+        self._last_dones = torch.zeros(self.n_envs, dtype=torch.float32, device=self.device)
+
+    def _rollout_step(self, t):
+        with torch.no_grad():
+            actions, values, log_probs = self.policy(self._last_obs)
+        obs_raw, rew_raw, done = self.env.step_tensor(actions.contiguous())
+        self._run_ret += rew_raw.to(torch.float64)
+        self._run_len += 1
+        d = done.bool()
+        self.ep_ret_sum += torch.where(d, self._run_ret, torch.zeros_like(self._run_ret)).sum()
+        self.ep_len_sum += torch.where(d, self._run_len, torch.zeros_like(self._run_len)).sum()
+        self.ep_count += d.sum()
+        self._run_ret = torch.where(d, torch.zeros_like(self._run_ret), self._run_ret)
+        self._run_len = torch.where(d, torch.zeros_like(self._run_len), self._run_len)
+        obs, rew = self.norm.step(obs_raw, rew_raw, done)
+        self.buffer.add(self._last_obs, actions, rew, self._last_dones, values, log_probs)
+        self._last_obs = obs
+        self._last_dones = done.to(torch.float32)
+
+    def collect_rollouts(self):
+        self.buffer.reset()
+        for t in range(self.n_steps):
+            self._rollout_step(t)
+        self.num_timesteps += self.n_steps * self.n_envs * self.world
+        with torch.no_grad():
+            last_values = self.policy.predict_values(self._last_obs)
+        self.buffer.compute_returns_and_advantage(last_values, self._last_dones)
+        if self.dist is not None:
+            self.norm.sync(self.dist)
+
+    # ------------------------------------------------------------------ update (ppo.py:133-240)
+    def train(self):
+        params = [p for p in self.policy.parameters()]
+        stats = {}
+        for epoch in range(self.n_epochs):
+            for batch in self.buffer.get(self.batch_size):
+                values, log_prob, entropy = self.policy.evaluate_actions(batch.observations, batch.actions)
+                adv = batch.advantages
+                adv = (adv - adv.mean()) / (adv.std() + 1e-8)
+                ratio = torch.exp(log_prob - batch.old_log_prob)
+                pl1 = adv * ratio
+                pl2 = adv * torch.clamp(ratio, 1 - self.clip_range, 1 + self.clip_range)
+                policy_loss = -torch.min(pl1, pl2).mean()
+                value_loss = torch.nn.functional.mse_loss(batch.returns, values)
+                entropy_loss = -entropy.mean()
+                loss = policy_loss + self.ent_coef * entropy_loss + self.vf_coef * value_loss
+                self.optimizer.zero_grad(set_to_none=False)
+                loss.backward()
+                if self.dist is not None and self.world > 1:
+                    allreduce_gradients(params, self.dist, self.world)
+                torch.nn.utils.clip_grad_norm_(params, self.max_grad_norm)
+                self.optimizer.step()
+        stats.update(policy_loss=policy_loss.detach(), value_loss=value_loss.detach(),
+                     std=torch.exp(self.policy.log_std).mean().detach())
+        return stats
+
+    def learn(self, total_timesteps, log_interval=1, callback=None):
+        if self._last_obs is None:
+            self._setup()
+        t0 = time.time()
+        it = 0
+        while self.num_timesteps < total_timesteps:
+            self.collect_rollouts()
+            stats = self.train()
+            it += 1
+            if it % log_interval == 0:
+                packed = torch.stack([self.ep_ret_sum, self.ep_len_sum, self.ep_count])
+                if self.dist is not None and self.world > 1:
+                    self.dist.all_reduce(packed)
+                r, l, c = packed.tolist()
+                self.ep_ret_sum.zero_(); self.ep_len_sum.zero_(); self.ep_count.zero_()
+                row = {"iteration": it, "timesteps": self.num_timesteps, "fps": self.num_timesteps / (time.time() - t0),
+                       "ep_rew_mean": r / c if c else float("nan"), "ep_len_mean": l / c if c else float("nan"),
+                       "episodes": int(c), **{k: float(v) for k, v in stats.items()}}
+                self.logs.append(row)
+                if callback is not None:
+                    callback(row)
+        return self
+
+    # ------------------------------------------------------------------ checkpoint (policy / optimiser / normaliser)
+    def save(self, path):
+        torch.save({"policy": self.policy.state_dict(), "optimizer": self.optimizer.state_dict(),
+                    "normalizer": self.norm.state_dict(), "num_timesteps": self.num_timesteps}, path)
+
+    def load(self, path):
+        sd = torch.load(path, map_location=self.device)
+        self.policy.load_state_dict(sd["policy"])
+        self.optimizer.load_state_dict(sd["optimizer"])
+        self.norm.load_state_dict(sd["normalizer"])
+        self.num_timesteps = sd["num_timesteps"]
