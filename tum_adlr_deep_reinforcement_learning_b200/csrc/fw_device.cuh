@@ -320,20 +320,16 @@ __device__ __forceinline__ int rhs(const DCfg<T>& c, const DynCtx<T>& x, const T
 
 // Dormand-Prince 5(4) tableau (scipy rk.py class RK45) as "evaluation rows": row r gives the coefficients of the
 // stage derivatives K[0..] that form the input of RHS evaluation r.
-//   row 0      : y                                  -> f0 = fun(t0, y0)          (RungeKutta.__init__)
-//   rows 1..5  : y + h * sum_j A[r][j] K[j]         -> K[r]                      (rk_step)
+//   rows 1..5  : y + h * sum_{j<r} A[r][j] K[j]     -> K[r]                      (rk_step)
 //   row 6      : y + h * sum_j B[j] K[j] = y_new    -> f_new (row 6 of A is B: FSAL)
-//   row 7      : y + h0 * K[0]                      -> f1 of select_initial_step (common.py:121-123)
-__device__ __constant__ const double RK_ROW[8][6] = {
+__device__ __constant__ const double RK_ROW[7][6] = {
     {0, 0, 0, 0, 0, 0},
     {1.0 / 5, 0, 0, 0, 0, 0},
     {3.0 / 40, 9.0 / 40, 0, 0, 0, 0},
     {44.0 / 45, -56.0 / 15, 32.0 / 9, 0, 0, 0},
     {19372.0 / 6561, -25360.0 / 2187, 64448.0 / 6561, -212.0 / 729, 0, 0},
     {9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656, 0},
-    {35.0 / 384, 0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84},
-    {1.0, 0, 0, 0, 0, 0}};
-__device__ __constant__ const int RK_NTERM[8] = {0, 1, 2, 3, 4, 5, 6, 1};
+    {35.0 / 384, 0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84}};
 __device__ __constant__ const double RK_E[7] = {-71.0 / 57600, 0, 71.0 / 16695, -71.0 / 1920, 17253.0 / 339200,
                                                 -22.0 / 525, 1.0 / 40};
 
@@ -341,54 +337,28 @@ template <typename T> __device__ __noinline__ T pow_ni(T x, T y) { return M<T>::
 
 #define FW_NK 18   // stage-derivative components kept: d/dt of y[18] (throttle rate state) is identically 0
 
-// scipy.integrate.solve_ivp(fun, (0, dt), y0) with RK45 defaults (pyfly.py:1393-1395), one env per thread.
+// scipy.integrate.solve_ivp(fun, (0, dt), y0) with RK45 defaults (pyfly.py:1393-1395) is split over two kernels:
 //
-// Written as ONE loop around ONE inlined RHS instance (a state machine over the evaluation rows above): the hot
-// loop is ~3.5k SASS instructions instead of three inlined RHS copies, which is what keeps it inside the
-// instruction cache.  All lanes of a warp walk rows 0, 7, then 1..6 repeatedly in lock step, so the only
-// divergence left is lanes that finish their [0, dt] interval in fewer attempts than their neighbours.
-// Stage derivatives K[0..5] live in shared memory, K[(row * 18 + comp) * NT + tid] (conflict-free 8-byte lanes);
-// f_new (row 6) never leaves registers: it is consumed by the error estimate and becomes K[0] on acceptance.
-template <typename T, bool TURB, int NT>
-__device__ __forceinline__ int solve_rk45(const DCfg<T>& c, const DynCtx<T>& x, T (&y)[FW_NY], T elev0, T ail0,
-                                          T* __restrict__ K, int& nfev, int& natt) {
-#define KS(s, i) K[((s) * FW_NK + (i)) * NT]
+//   rk45_init   rows 0 and 7 for every env in lock step (RungeKutta.__init__ + select_initial_step, common.py:68-134):
+//               f0 and the first step size go to a scratch SoA.
+//   the attempt loop (rk45_attempt_kernel in fw_step.cu): every lane always executes the same row 1..6 of an
+//               attempt, so ONE inlined RHS instance serves all lanes at full occupancy of the warp; a lane whose env
+//               finished its [0, dt] interval pulls the next env from a queue instead of idling (the number of
+//               attempts per env-step varies 2..7, which cost 32 % of the lanes when envs were pinned to threads).
+template <typename T, bool TURB>
+__device__ __forceinline__ int rk45_init(const DCfg<T>& c, const DynCtx<T>& x, const T (&y)[FW_NY], T elev0, T ail0,
+                                         T (&f0)[FW_NY], T& h_abs) {
     const T rtol = c.rtol, atol = c.atol, t_bound = c.dt;
     T ys[FW_NY], dyv[FW_NY];
-    T t = 0, t_new = 0, h = 0, h_abs = 0, d1 = 0, min_step = 0;
-    bool rejected = false;
-    int row = 0, rc = 0;
-    nfev = 0;
-    natt = 0;
-    while (true) {
-        // ---- input of this evaluation ----
-        {
-            T acc[FW_NK];
-#pragma unroll
-            for (int i = 0; i < FW_NK; ++i) acc[i] = 0;
-            const int nterm = RK_NTERM[row];
+    T d1 = 0, h0 = 0;
+    int rc = 0;
 #pragma unroll 1
-            for (int j = 0; j < nterm; ++j) {
-                const T a = (T)RK_ROW[row][j];
+    for (int pass = 0; pass < 2; ++pass) {
 #pragma unroll
-                for (int i = 0; i < FW_NK; ++i) acc[i] += KS(j, i) * a;
-            }
-#pragma unroll
-            for (int i = 0; i < FW_NK; ++i) ys[i] = (row == 0) ? y[i] : y[i] + acc[i] * h;
-            ys[18] = y[18];
-        }
-        rc = rhs<T, TURB>(c, x, ys, row == 0, elev0, ail0, dyv);
-        nfev++;
-        if (rc) break;
-        // ---- what the evaluation was for ----
-        if (row >= 1 && row <= 5) {
-#pragma unroll
-            for (int i = 0; i < FW_NK; ++i) KS(row, i) = dyv[i];
-            row++;
-            continue;
-        }
-        if (row == 0) {
-            // RungeKutta.__init__: f = fun(t0, y0); select_initial_step part 1 (common.py:68-123)
+        for (int i = 0; i < FW_NY; ++i) ys[i] = (pass == 0) ? y[i] : y[i] + h0 * f0[i];
+        rc = rhs<T, TURB>(c, x, ys, pass == 0, elev0, ail0, dyv);
+        if (rc) return rc;
+        if (pass == 0) {
             T s0 = 0, s1 = 0;
 #pragma unroll
             for (int i = 0; i < FW_NY; ++i) {
@@ -396,81 +366,33 @@ __device__ __forceinline__ int solve_rk45(const DCfg<T>& c, const DynCtx<T>& x, 
                 const T a = y[i] * inv, b = dyv[i] * inv;
                 s0 += a * a;
                 s1 += b * b;
+                f0[i] = dyv[i];
             }
-#pragma unroll
-            for (int i = 0; i < FW_NK; ++i) KS(0, i) = dyv[i];
             const T d0 = M<T>::sqrt(s0) / M<T>::sqrt((T)FW_NY);
             d1 = M<T>::sqrt(s1) / M<T>::sqrt((T)FW_NY);
-            T h0 = (d0 < (T)1e-5 || d1 < (T)1e-5) ? (T)1e-6 : (T)0.01 * d0 / d1;
-            h = M<T>::fmin(h0, t_bound);       // h doubles as h0 for row 7
-            row = 7;
-            continue;
-        }
-        bool new_attempt = false;
-        if (row == 7) {
-            // select_initial_step part 2 (common.py:124-134), order = error_estimator_order = 4
+            h0 = (d0 < (T)1e-5 || d1 < (T)1e-5) ? (T)1e-6 : (T)0.01 * d0 / d1;
+            h0 = M<T>::fmin(h0, t_bound);
+        } else {
             T s2 = 0;
 #pragma unroll
-            for (int i = 0; i < FW_NK; ++i) {
+            for (int i = 0; i < FW_NY; ++i) {
                 const T inv = (T)1 / (atol + M<T>::fabs(y[i]) * rtol);
-                const T d = (dyv[i] - KS(0, i)) * inv;
+                const T d = (dyv[i] - f0[i]) * inv;
                 s2 += d * d;
             }
-            const T d2 = (M<T>::sqrt(s2) / M<T>::sqrt((T)FW_NY)) / h;
+            const T d2 = (M<T>::sqrt(s2) / M<T>::sqrt((T)FW_NY)) / h0;
             T h1;
-            if (d1 <= (T)1e-15 && d2 <= (T)1e-15) h1 = M<T>::fmax((T)1e-6, h * (T)1e-3);
+            if (d1 <= (T)1e-15 && d2 <= (T)1e-15) h1 = M<T>::fmax((T)1e-6, h0 * (T)1e-3);
             else h1 = pow_ni<T>((T)0.01 / M<T>::fmax(d1, d2), (T)0.2);
-            h_abs = M<T>::fmin(M<T>::fmin((T)100 * h, h1), t_bound);
-            new_attempt = true;
-            t = 0;
-        } else {
-            // row 6: ys == y_new, dyv == f_new.  Error estimate and step-size control (rk.py:100-104, 139-166)
-            T errsq = 0;
-#pragma unroll
-            for (int i = 0; i < FW_NK; ++i) {
-                T acc = 0;
-#pragma unroll
-                for (int j = 0; j < 6; ++j) acc += KS(j, i) * (T)RK_E[j];
-                acc += dyv[i] * (T)RK_E[6];
-                const T scl = atol + M<T>::fmax(M<T>::fabs(y[i]), M<T>::fabs(ys[i])) * rtol;
-                const T ei = acc * h / scl;
-                errsq += ei * ei;
-            }
-            const T err = M<T>::sqrt(errsq) / M<T>::sqrt((T)FW_NY);
-            // err == 0: pow(0, -0.2) = inf -> min(10, inf) = MAX_FACTOR, the same as scipy's special case
-            const T pf = (T)0.9 * pow_ni<T>(err, (T)-0.2);
-            if (err < (T)1) {
-                T factor = (err == (T)0) ? (T)10 : M<T>::fmin((T)10, pf);
-                if (rejected) factor = M<T>::fmin((T)1, factor);
-                h_abs *= factor;
-                t = t_new;
-#pragma unroll
-                for (int i = 0; i < FW_NK; ++i) { y[i] = ys[i]; KS(0, i) = dyv[i]; }   // FSAL
-                if (!(t < t_bound)) break;                   // solver.status == 'finished'
-                rejected = false;
-                new_attempt = true;
-            } else {
-                h_abs *= M<T>::fmax((T)0.2, pf);
-                rejected = true;
-            }
+            h_abs = M<T>::fmin(M<T>::fmin((T)100 * h0, h1), t_bound);
         }
-        if (new_attempt) {
-            // top of RungeKutta._step_impl (rk.py:111-127): min_step = 10 * ulp(t)
-            min_step = (T)10 * (sizeof(T) == 8 ? (T)(::nextafter((double)t, CUDART_INF) - (double)t)
-                                               : (T)(::nextafterf((float)t, CUDART_INF_F) - (float)t));
-            if (h_abs < min_step) h_abs = min_step;
-        }
-        // top of the `while not step_accepted` loop (rk.py:129-141)
-        if (h_abs < min_step) break;        // TOO_SMALL_STEP: solve_ivp returns status -1, pyfly ignores it
-        t_new = t + h_abs;
-        if (t_new - t_bound > (T)0) t_new = t_bound;
-        h = t_new - t;
-        h_abs = M<T>::fabs(h);
-        natt++;
-        row = 1;
     }
-    return rc;
-#undef KS
+    return 0;
+}
+
+template <typename T> __device__ __forceinline__ T ulp10(T t) {   // min_step = 10 * |nextafter(t, inf) - t| (rk.py:118)
+    return (T)10 * (sizeof(T) == 8 ? (T)(::nextafter((double)t, CUDART_INF) - (double)t)
+                                   : (T)(::nextafterf((float)t, CUDART_INF_F) - (float)t));
 }
 
 // classical RK4 x substeps, register resident (throughput mode; same RHS with its clip/constraint side effects),

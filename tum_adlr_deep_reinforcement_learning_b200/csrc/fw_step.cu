@@ -1,10 +1,15 @@
-// fw_step.cu — the fused env-step kernel, the reset kernel and the C ABI of libfwb200.so (see include/fwb200.h).
+// fw_step.cu — the env-step kernels, the reset kernel and the C ABI of libfwb200.so (see include/fwb200.h).
 //
-// One launch of step_kernel == one VecEnv.step over every env of the handle:
-//   action scaling -> command constraint -> integrator (scipy-RK45 replica or RK4xN) -> post-step commit
-//   (quaternion renormalisation, Euler angles, Va/alpha/beta, constraint checks) -> Dryden filter advance ->
-//   goal ring / streak test -> reward -> target law -> observation -> termination -> streamed episode metrics ->
-//   auto-reset (Philox).  Nothing leaves the SM between these stages.
+// One VecEnv.step over every env of the handle = three launches on the caller's stream (exact mode):
+//   rk45_init_kernel     action scaling -> command constraint -> f0 = fun(t0, y0) and scipy's select_initial_step
+//   rk45_attempt_kernel  the RK45 attempt loop; persistent lanes pull envs from a queue, so every lane of every warp
+//                        executes the same RHS row all the time (8 warps/SM: 255 registers + 864 B of stage storage)
+//   head_kernel          post-step commit (quaternion renormalisation, Euler angles, Va/alpha/beta, constraint
+//                        checks) -> Dryden filter advance -> goal ring / streak test -> reward -> target law ->
+//                        observation -> termination -> streamed episode metrics -> auto-reset (Philox).
+// The once-per-step head code is large and cold; in its own kernel it runs at high occupancy instead of stalling
+// the register-heavy integrator warps on instruction fetch (profiles/r01_*.txt).  Fixed-step modes use
+// rk4_kernel -> head_kernel.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -63,43 +68,22 @@ __device__ __forceinline__ T delta_feature(const T cur, const T* ring /* [4][3] 
     return (T)s;
 }
 
-template <typename T, int INTEG, bool TURB, int NT>
-__global__ void __launch_bounds__(NT) step_kernel(const __grid_constant__ DCfg<T> c, const Soa<T> S, const StepIO io) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int env = blockIdx.x * NT + threadIdx.x;
-    const int n = S.n;
-    if (env >= n) return;
-    T* r = S.r + env;
-    int32_t* ii = S.i + env;
+// scratch SoA between the kernels of one step
+template <typename T> struct Scratch {
+    T* f0;        // [18][n]  fun(t0, y0)                           (init -> attempt)
+    T* hinit;     // [n]      first step size                        (init -> attempt)
+    T* cmd;       // [3][n]   constrained elevon_r / elevon_l / throttle commands
+    T* turb;      // [6][n]   turbulence sample of this step (lin3, ang3)
+    T* ytmp;      // [19][n]  sol.y[:, -1] before the commit          (attempt / rk4 -> head)
+    int32_t* fail;     // [n] FwTermCode raised inside the integrator (0 = none)
+    int32_t* counter;  // work-queue head of the attempt kernel
+};
 
-    // ---------------- load ----------------
-    T y[FW_NY];
-#pragma unroll
-    for (int i = 0; i < FW_NY; ++i) y[i] = r[(RF_Y + i) * n];
-    const T roll_prev = r[RF_ROLL * n], pitch_prev = r[RF_PITCH * n], Va_prev = r[RF_VA * n];
-    const T alpha_prev = r[RF_ALPHA * n], beta_prev = r[RF_BETA * n];
-    const T omega_prev[3] = {y[4], y[5], y[6]};
-    DynCtx<T> x;
-    T tgt[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { x.wind[k] = r[(RF_WIND + k) * n]; tgt[k] = r[(RF_TGT + k) * n]; }
-    int steps = ii[IF_STEPS * n], steps_tgt = ii[IF_STEPS_TGT * n], sim_step = ii[IF_SIM_STEP * n];
-    const unsigned long long episode = (unsigned long long)(uint32_t)ii[IF_EPISODE * n];
-    T fx[12], fu[4];
-    if (TURB) {
-#pragma unroll
-        for (int i = 0; i < 12; ++i) fx[i] = r[(RF_FX + i) * n];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) fu[i] = r[(RF_FU + i) * n];
-        turb_eval(c, fx, fu, x.tl, x.ta);
-    } else {
-#pragma unroll
-        for (int k = 0; k < 3; ++k) { x.tl[k] = 0; x.ta[k] = 0; }
-    }
-
-    // ---------------- action (fixed_wing.py:491-506) ----------------
-    T a_raw[3];
-    bool act_f32;
+// raw action -> (a_raw, act_f32, constrained dynamics commands, constrained input commands)
+// fixed_wing.py:491-506 + Actuation.set_and_constrain_commands pyfly.py:545-582
+template <typename T>
+__device__ __forceinline__ void prep_action(const DCfg<T>& c, const StepIO& io, int env, T (&a_raw)[3], bool& act_f32,
+                                            T (&cmd_dyn)[3], T (&cmd_in)[3]) {
     if (io.random_actions) {
         const uint4 rr = rng_block(io.action_seed, c.env_id_offset + env, io.action_step >> 32, RNG_ACTION,
                                    (uint32_t)io.action_step);
@@ -127,29 +111,275 @@ __global__ void __launch_bounds__(NT) step_kernel(const __grid_constant__ DCfg<T
             a_cmd[j] = a_raw[j];
         }
     }
-    // Actuation.set_and_constrain_commands (pyfly.py:545-582)
-    x.cmd[0] = clip(-a_cmd[1] + a_cmd[0], c.elevon_min, c.elevon_max);
-    x.cmd[1] = clip(a_cmd[1] + a_cmd[0], c.elevon_min, c.elevon_max);
-    x.cmd[2] = clip(a_cmd[2], c.throttle_min, c.throttle_max);
-    T cmd_in[3];
-    cmd_in[0] = clip((x.cmd[0] + x.cmd[1]) / (T)2, c.act_lo[0], c.act_hi[0]);
-    cmd_in[1] = clip((-x.cmd[0] + x.cmd[1]) / (T)2, c.act_lo[1], c.act_hi[1]);
-    cmd_in[2] = x.cmd[2];
+    cmd_dyn[0] = clip(-a_cmd[1] + a_cmd[0], c.elevon_min, c.elevon_max);
+    cmd_dyn[1] = clip(a_cmd[1] + a_cmd[0], c.elevon_min, c.elevon_max);
+    cmd_dyn[2] = clip(a_cmd[2], c.throttle_min, c.throttle_max);
+    cmd_in[0] = clip((cmd_dyn[0] + cmd_dyn[1]) / (T)2, c.act_lo[0], c.act_hi[0]);
+    cmd_in[1] = clip((-cmd_dyn[0] + cmd_dyn[1]) / (T)2, c.act_lo[1], c.act_hi[1]);
+    cmd_in[2] = cmd_dyn[2];
+}
 
-    // ---------------- integrate (pyfly.py:1372-1396) ----------------
+// loads what one integration needs: y, steady wind, this step's turbulence sample, commands
+template <typename T, bool TURB>
+__device__ __forceinline__ void load_dyn(const DCfg<T>& c, const Soa<T>& S, const StepIO& io, int env, T (&y)[FW_NY],
+                                         DynCtx<T>& x, T& elev0, T& ail0) {
+    const int n = S.n;
+    const T* r = S.r + env;
+#pragma unroll
+    for (int i = 0; i < FW_NY; ++i) y[i] = r[(RF_Y + i) * n];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) x.wind[k] = r[(RF_WIND + k) * n];
+    if (TURB) {
+        T fx[12], fu[4];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) fx[i] = r[(RF_FX + i) * n];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) fu[i] = r[(RF_FU + i) * n];
+        turb_eval(c, fx, fu, x.tl, x.ta);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { x.tl[k] = 0; x.ta[k] = 0; }
+    }
+    T a_raw[3], cmd_in[3];
+    bool act_f32;
+    prep_action(c, io, env, a_raw, act_f32, x.cmd, cmd_in);
     // elevator/aileron seen by the t == 0 RHS call: 0 right after a reset (disabled ControlVariable.reset)
-    T elev0 = 0, ail0 = 0;
-    if (steps > 0) {
+    elev0 = 0; ail0 = 0;
+    if (S.i[IF_STEPS * n + env] > 0) {
         const T er = clip(y[13], c.elevon_min, c.elevon_max), el = clip(y[14], c.elevon_min, c.elevon_max);
         elev0 = (er + el) / (T)2;
         ail0 = (-er + el) / (T)2;
     }
-    int nfev = 0, natt = 0, fail;
-    if (INTEG == FW_INT_RK45_SCIPY) {
-        T* K = reinterpret_cast<T*>(smem_raw) + threadIdx.x;
-        fail = solve_rk45<T, TURB, NT>(c, x, y, elev0, ail0, K, nfev, natt);
-    } else {
-        fail = solve_rk4<T, TURB>(c, x, y, elev0, ail0, nfev, natt);
+}
+
+// ---- kernel A0: RungeKutta.__init__ + select_initial_step for every env, lock step ----
+template <typename T, bool TURB>
+__global__ void __launch_bounds__(128) rk45_init_kernel(const __grid_constant__ DCfg<T> c, const Soa<T> S, const StepIO io,
+                                                        const Scratch<T> W, int attempt_threads) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = S.n;
+    if (env == 0) *W.counter = attempt_threads;      // queue head: the first attempt_threads envs are pre-assigned
+    if (env >= n) return;
+    T y[FW_NY], f0[FW_NY], h_abs = 0, elev0, ail0;
+    DynCtx<T> x;
+    load_dyn<T, TURB>(c, S, io, env, y, x, elev0, ail0);
+    const int rc = rk45_init<T, TURB>(c, x, y, elev0, ail0, f0, h_abs);
+#pragma unroll
+    for (int i = 0; i < FW_NK; ++i) W.f0[i * n + env] = f0[i];
+    W.hinit[env] = h_abs;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { W.cmd[k * n + env] = x.cmd[k]; W.turb[k * n + env] = x.tl[k]; W.turb[(3 + k) * n + env] = x.ta[k]; }
+    W.fail[env] = rc;
+    S.i[IF_NFEV * n + env] = 2;              // a raise can only come from the second evaluation (t > 0)
+    S.i[IF_NATT * n + env] = 0;
+}
+
+// ---- kernel A1: the attempt loop, persistent lanes pulling envs from a queue ----
+template <typename T, bool TURB, int NT>
+__global__ void __launch_bounds__(NT) rk45_attempt_kernel(const __grid_constant__ DCfg<T> c, const Soa<T> S,
+                                                          const Scratch<T> W) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* K = reinterpret_cast<T*>(smem_raw) + threadIdx.x;
+#define KS(s, i) K[((s) * FW_NK + (i)) * NT]
+    const int n = S.n;
+    const T rtol = c.rtol, atol = c.atol, t_bound = c.dt;
+    const unsigned lane = threadIdx.x & 31;
+    int env = blockIdx.x * NT + threadIdx.x;
+    bool need = true, exhausted = false, first_fetch = true;
+    T y[FW_NY], ys[FW_NY], dyv[FW_NY];
+    DynCtx<T> x;
+    T t = 0, t_new = 0, h = 0, h_abs = 0, min_step = 0;
+    bool rejected = false;
+    int nfev = 0, natt = 0;
+#pragma unroll
+    for (int i = 0; i < FW_NY; ++i) { y[i] = 0; ys[i] = 0; }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { x.cmd[k] = 0; x.wind[k] = 0; x.tl[k] = 0; x.ta[k] = 0; }
+    y[0] = 1; ys[0] = 1; ys[10] = 20; y[10] = 20;      // a benign state for lanes that never get an env
+
+    while (true) {
+        // ---------------- fetch: lanes without an env take the next one from the queue ----------------
+        while (true) {
+            const unsigned want = __ballot_sync(0xffffffffu, need && !exhausted);
+            if (want == 0) break;
+            if (need && !exhausted) {
+                if (!first_fetch) {
+                    int base = 0;
+                    const unsigned peers = __activemask();
+                    const int leader = __ffs(peers) - 1;
+                    if ((int)lane == leader) base = atomicAdd(W.counter, __popc(peers));
+                    base = __shfl_sync(peers, base, leader);
+                    env = base + __popc(peers & ((1u << lane) - 1u));
+                }
+                first_fetch = false;
+                if (env >= n) exhausted = true;
+                else if (W.fail[env] != 0) { /* raised during initialisation: nothing to integrate */ }
+                else {
+#pragma unroll
+                    for (int i = 0; i < FW_NY; ++i) y[i] = S.r[(RF_Y + i) * n + env];
+#pragma unroll
+                    for (int i = 0; i < FW_NK; ++i) KS(0, i) = W.f0[i * n + env];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        x.cmd[k] = W.cmd[k * n + env]; x.wind[k] = S.r[(RF_WIND + k) * n + env];
+                        x.tl[k] = W.turb[k * n + env]; x.ta[k] = W.turb[(3 + k) * n + env];
+                    }
+                    h_abs = W.hinit[env];
+                    t = 0; rejected = false; nfev = 2; natt = 0;
+                    // top of RungeKutta._step_impl (rk.py:111-127)
+                    min_step = ulp10<T>(t);
+                    if (h_abs < min_step) h_abs = min_step;
+                    need = false;
+                }
+            }
+        }
+        if (__all_sync(0xffffffffu, exhausted)) break;
+        const bool active = !exhausted && !need;
+        // ---------------- one attempt: top of the `while not step_accepted` loop (rk.py:129-141) ----------------
+        bool finished = false;
+        int rc = 0;
+        if (active) {
+            if (h_abs < min_step) finished = true;     // TOO_SMALL_STEP: solve_ivp status -1, ignored by pyfly
+            else {
+                t_new = t + h_abs;
+                if (t_new - t_bound > (T)0) t_new = t_bound;
+                h = t_new - t;
+                h_abs = M<T>::fabs(h);
+                natt++;
+            }
+        }
+        const bool run = active && !finished;
+#pragma unroll 1
+        for (int row = 1; row <= 6; ++row) {
+            {
+                T acc[FW_NK];
+#pragma unroll
+                for (int i = 0; i < FW_NK; ++i) acc[i] = 0;
+#pragma unroll 1
+                for (int j = 0; j < row; ++j) {
+                    const T a = (T)RK_ROW[row][j];
+#pragma unroll
+                    for (int i = 0; i < FW_NK; ++i) acc[i] += KS(j, i) * a;
+                }
+#pragma unroll
+                for (int i = 0; i < FW_NK; ++i) ys[i] = y[i] + acc[i] * h;
+                ys[18] = y[18];
+            }
+            const int r2 = rhs<T, TURB>(c, x, ys, false, (T)0, (T)0, dyv);
+            if (run && rc == 0) {
+                nfev++;
+                if (r2) rc = r2;
+                else if (row < 6) {
+#pragma unroll
+                    for (int i = 0; i < FW_NK; ++i) KS(row, i) = dyv[i];
+                }
+            }
+        }
+        if (run) {
+            if (rc) finished = true;
+            else {
+                // ys == y_new, dyv == f_new: error estimate and step-size control (rk.py:100-104, 139-166)
+                T errsq = 0;
+#pragma unroll
+                for (int i = 0; i < FW_NK; ++i) {
+                    T acc = 0;
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) acc += KS(j, i) * (T)RK_E[j];
+                    acc += dyv[i] * (T)RK_E[6];
+                    const T scl = atol + M<T>::fmax(M<T>::fabs(y[i]), M<T>::fabs(ys[i])) * rtol;
+                    const T ei = acc * h / scl;
+                    errsq += ei * ei;
+                }
+                const T err = M<T>::sqrt(errsq) / M<T>::sqrt((T)FW_NY);
+                // err == 0: pow(0, -0.2) = inf -> min(10, inf) = MAX_FACTOR, the same as scipy's special case
+                const T pf = (T)0.9 * pow_ni<T>(err, (T)-0.2);
+                if (err < (T)1) {
+                    T factor = (err == (T)0) ? (T)10 : M<T>::fmin((T)10, pf);
+                    if (rejected) factor = M<T>::fmin((T)1, factor);
+                    h_abs *= factor;
+                    t = t_new;
+#pragma unroll
+                    for (int i = 0; i < FW_NK; ++i) { y[i] = ys[i]; KS(0, i) = dyv[i]; }   // FSAL
+                    if (!(t < t_bound)) finished = true;            // solver.status == 'finished'
+                    else {
+                        rejected = false;
+                        min_step = ulp10<T>(t);
+                        if (h_abs < min_step) h_abs = min_step;
+                    }
+                } else {
+                    h_abs *= M<T>::fmax((T)0.2, pf);
+                    rejected = true;
+                }
+            }
+        }
+        if (active && finished) {
+#pragma unroll
+            for (int i = 0; i < FW_NY; ++i) W.ytmp[i * n + env] = y[i];
+            W.fail[env] = rc;
+            S.i[IF_NFEV * n + env] = nfev;
+            S.i[IF_NATT * n + env] = natt;
+            need = true;
+        }
+    }
+#undef KS
+}
+
+// ---- fixed-step modes: lock-step integrate kernel (no adaptivity, no divergence to rebalance) ----
+template <typename T, bool TURB>
+__global__ void __launch_bounds__(128) rk4_kernel(const __grid_constant__ DCfg<T> c, const Soa<T> S, const StepIO io,
+                                                  const Scratch<T> W) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = S.n;
+    if (env >= n) return;
+    T y[FW_NY], elev0, ail0;
+    DynCtx<T> x;
+    load_dyn<T, TURB>(c, S, io, env, y, x, elev0, ail0);
+    int nfev = 0, natt = 0;
+    const int rc = solve_rk4<T, TURB>(c, x, y, elev0, ail0, nfev, natt);
+#pragma unroll
+    for (int i = 0; i < FW_NY; ++i) W.ytmp[i * n + env] = y[i];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { W.turb[k * n + env] = x.tl[k]; W.turb[(3 + k) * n + env] = x.ta[k]; }
+    W.fail[env] = rc;
+    S.i[IF_NFEV * n + env] = nfev;
+    S.i[IF_NATT * n + env] = natt;
+}
+
+// ---- kernel B: everything after the integrator (once per step, high occupancy) ----
+template <typename T, bool TURB>
+__global__ void __launch_bounds__(128) head_kernel(const __grid_constant__ DCfg<T> c, const Soa<T> S, const StepIO io,
+                                                   const Scratch<T> W) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = S.n;
+    if (env >= n) return;
+    T* r = S.r + env;
+    int32_t* ii = S.i + env;
+    int fail = W.fail[env];
+    T y[FW_NY];
+#pragma unroll
+    for (int i = 0; i < FW_NY; ++i) y[i] = fail ? r[(RF_Y + i) * n] : W.ytmp[i * n + env];
+    const T roll_prev = r[RF_ROLL * n], pitch_prev = r[RF_PITCH * n], Va_prev = r[RF_VA * n];
+    const T alpha_prev = r[RF_ALPHA * n], beta_prev = r[RF_BETA * n];
+    const T omega_prev[3] = {r[(RF_Y + 4) * n], r[(RF_Y + 5) * n], r[(RF_Y + 6) * n]};
+    DynCtx<T> x;
+    T tgt[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        x.wind[k] = r[(RF_WIND + k) * n]; tgt[k] = r[(RF_TGT + k) * n];
+        x.tl[k] = TURB ? W.turb[k * n + env] : (T)0; x.ta[k] = TURB ? W.turb[(3 + k) * n + env] : (T)0;
+    }
+    int steps = ii[IF_STEPS * n], steps_tgt = ii[IF_STEPS_TGT * n], sim_step = ii[IF_SIM_STEP * n];
+    const unsigned long long episode = (unsigned long long)(uint32_t)ii[IF_EPISODE * n];
+    const int nfev = ii[IF_NFEV * n], natt = ii[IF_NATT * n];
+    T a_raw[3], cmd_in[3];
+    bool act_f32;
+    prep_action(c, io, env, a_raw, act_f32, x.cmd, cmd_in);
+    T fx[12], fu[4];
+    if (TURB) {
+#pragma unroll
+        for (int i = 0; i < 12; ++i) fx[i] = r[(RF_FX + i) * n];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) fu[i] = r[(RF_FU + i) * n];
     }
 
     // ---------------- post-step commit (pyfly.py:1396-1406, 1852-1881) ----------------
@@ -608,44 +838,72 @@ struct FwHandle {
     Soa<float> s32;
     void* r_buf; int32_t* i_buf; void* err_ring;
     double* metrics; double* ep_ret; int32_t* ep_len; int32_t* ep_term;
+    void* w_real; int32_t* w_int;          // scratch between the kernels of one step
+    Scratch<double> w64;
+    Scratch<float> w32;
+    int sm_count;
     unsigned long long random_step;
 };
 
 static const int NT_RK45_F64 = 64;     // 6*18*64*8 = 55296 B of stage storage per block: 4 blocks (8 warps) / SM
 static const int NT_RK45_F32 = 128;    // 6*18*128*4 = 55296 B
-static const int NT_RK4 = 128;
+static const int W_REAL_FIELDS = FW_NK + 1 + 3 + 6 + FW_NY;   // f0, hinit, cmd, turb, ytmp
 
-template <typename T, int INTEG, int NT>
-static int launch_step_t(FwHandle* h, const DCfg<T>& c, const Soa<T>& S, const StepIO& io, cudaStream_t st) {
-    const size_t smem = (INTEG == FW_INT_RK45_SCIPY) ? (size_t)6 * FW_NK * NT * sizeof(T) : 0;
-    const int grid = (h->n + NT - 1) / NT;
-    if (c.turbulence) {
-        auto k = step_kernel<T, INTEG, true, NT>;
-        static bool attr_set = false;
-        if (smem && !attr_set) { CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
-        k<<<grid, NT, smem, st>>>(c, S, io);
-    } else {
-        auto k = step_kernel<T, INTEG, false, NT>;
-        static bool attr_set = false;
-        if (smem && !attr_set) { CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
-        k<<<grid, NT, smem, st>>>(c, S, io);
+template <typename T> static Scratch<T> make_scratch(void* real, int32_t* ints, size_t n) {
+    T* p = (T*)real;
+    Scratch<T> w;
+    w.f0 = p; p += FW_NK * n;
+    w.hinit = p; p += n;
+    w.cmd = p; p += 3 * n;
+    w.turb = p; p += 6 * n;
+    w.ytmp = p;
+    w.fail = ints;
+    w.counter = ints + n;
+    return w;
+}
+
+// One env step = init kernel -> persistent attempt kernel -> head kernel (RK45), or rk4 kernel -> head kernel.
+template <typename T, bool TURB, int NT>
+static int launch_rk45(FwHandle* h, const DCfg<T>& c, const Soa<T>& S, const Scratch<T>& W, const StepIO& io, cudaStream_t st) {
+    const size_t smem = (size_t)6 * FW_NK * NT * sizeof(T);
+    auto k = rk45_attempt_kernel<T, TURB, NT>;
+    static int blocks_per_sm = 0;
+    if (!blocks_per_sm) {
+        CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k, NT, smem));
+        if (blocks_per_sm < 1) blocks_per_sm = 1;
     }
+    int grid = h->sm_count * blocks_per_sm;
+    const int need = (h->n + NT - 1) / NT;
+    if (grid > need) grid = need;
+    const int g0 = (h->n + 127) / 128;
+    rk45_init_kernel<T, TURB><<<g0, 128, 0, st>>>(c, S, io, W, grid * NT);
+    k<<<grid, NT, smem, st>>>(c, S, W);
+    head_kernel<T, TURB><<<g0, 128, 0, st>>>(c, S, io, W);
+    CK(cudaGetLastError());
+    return FW_OK;
+}
+template <typename T, bool TURB>
+static int launch_rk4(FwHandle* h, const DCfg<T>& c, const Soa<T>& S, const Scratch<T>& W, const StepIO& io, cudaStream_t st) {
+    const int g0 = (h->n + 127) / 128;
+    rk4_kernel<T, TURB><<<g0, 128, 0, st>>>(c, S, io, W);
+    head_kernel<T, TURB><<<g0, 128, 0, st>>>(c, S, io, W);
     CK(cudaGetLastError());
     return FW_OK;
 }
 
 static int launch_step(FwHandle* h, const StepIO& io, cudaStream_t st) {
+    const bool turb = h->cfg.turbulence != 0, rk45 = h->cfg.integrator == FW_INT_RK45_SCIPY;
     if (h->cfg.precision == FW_F64) {
-        if (h->cfg.integrator == FW_INT_RK45_SCIPY) {
-            // block-size experiment hook (FW_NT=32|64), default 64
-            static const int nt = getenv("FW_NT") ? atoi(getenv("FW_NT")) : NT_RK45_F64;
-            if (nt == 32) return launch_step_t<double, FW_INT_RK45_SCIPY, 32>(h, h->c64, h->s64, io, st);
-            return launch_step_t<double, FW_INT_RK45_SCIPY, NT_RK45_F64>(h, h->c64, h->s64, io, st);
-        }
-        return launch_step_t<double, FW_INT_RK4_FIXED, NT_RK4>(h, h->c64, h->s64, io, st);
+        if (rk45) return turb ? launch_rk45<double, true, NT_RK45_F64>(h, h->c64, h->s64, h->w64, io, st)
+                              : launch_rk45<double, false, NT_RK45_F64>(h, h->c64, h->s64, h->w64, io, st);
+        return turb ? launch_rk4<double, true>(h, h->c64, h->s64, h->w64, io, st)
+                    : launch_rk4<double, false>(h, h->c64, h->s64, h->w64, io, st);
     }
-    if (h->cfg.integrator == FW_INT_RK45_SCIPY) return launch_step_t<float, FW_INT_RK45_SCIPY, NT_RK45_F32>(h, h->c32, h->s32, io, st);
-    return launch_step_t<float, FW_INT_RK4_FIXED, NT_RK4>(h, h->c32, h->s32, io, st);
+    if (rk45) return turb ? launch_rk45<float, true, NT_RK45_F32>(h, h->c32, h->s32, h->w32, io, st)
+                          : launch_rk45<float, false, NT_RK45_F32>(h, h->c32, h->s32, h->w32, io, st);
+    return turb ? launch_rk4<float, true>(h, h->c32, h->s32, h->w32, io, st)
+                : launch_rk4<float, false>(h, h->c32, h->s32, h->w32, io, st);
 }
 
 extern "C" {
@@ -683,6 +941,13 @@ int fw_create(const FwConfig* cfg, int32_t n_envs, int32_t device, FwHandle** ou
     CK(cudaMalloc((void**)&h->ep_ret, sizeof(double) * n));
     CK(cudaMalloc((void**)&h->ep_len, sizeof(int32_t) * n));
     CK(cudaMalloc((void**)&h->ep_term, sizeof(int32_t) * n));
+    CK(cudaMalloc(&h->w_real, esz * W_REAL_FIELDS * n));
+    CK(cudaMalloc((void**)&h->w_int, sizeof(int32_t) * (n + 4)));
+    CK(cudaMemset(h->w_real, 0, esz * W_REAL_FIELDS * n));
+    CK(cudaMemset(h->w_int, 0, sizeof(int32_t) * (n + 4)));
+    h->w64 = make_scratch<double>(h->w_real, h->w_int, n);
+    h->w32 = make_scratch<float>(h->w_real, h->w_int, n);
+    CK(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));
     CK(cudaMemset(h->r_buf, 0, esz * RF_COUNT * n));
     CK(cudaMemset(h->i_buf, 0, sizeof(int32_t) * IF_COUNT * n));
     CK(cudaMemset(h->err_ring, 0, esz * FW_END_ERR_WINDOW * 3 * n));
@@ -702,7 +967,7 @@ int fw_destroy(FwHandle* h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     cudaFree(h->r_buf); cudaFree(h->i_buf); cudaFree(h->err_ring); cudaFree(h->metrics);
-    cudaFree(h->ep_ret); cudaFree(h->ep_len); cudaFree(h->ep_term);
+    cudaFree(h->ep_ret); cudaFree(h->ep_len); cudaFree(h->ep_term); cudaFree(h->w_real); cudaFree(h->w_int);
     delete h;
     return FW_OK;
 }
