@@ -82,7 +82,7 @@ template <typename T> struct DCfg {
     T C_l_0, C_l_beta, C_l_p, C_l_r, C_l_delta_a, C_l_delta_r;
     T C_n_0, C_n_beta, C_n_p, C_n_r, C_n_delta_a, C_n_delta_r;
     T gam[9];
-    T half_rho, mg, prop_k /* 0.5 rho S_prop C_prop */, pi_e_ar;
+    T half_rho, mg, prop_k /* 0.5 rho S_prop C_prop */, inv_pi_e_ar, inv_Jy, inv_mass;
     T dt, elevon_min, elevon_max, elevon_dot_max, w0sq, two_zeta_w0, inv_tau, throttle_min, throttle_max;
     T omega_con_min[3], omega_con_max[3], va_value_min, va_con_max;
     T init_lo[12], init_hi[12], wind_mag_min, wind_mag_max, turb_noise_scale;
@@ -249,8 +249,15 @@ __device__ __forceinline__ int rhs(const DCfg<T>& c, const DynCtx<T>& x, const T
     T a2 = w - (r20 * x.wind[0] + r21 * x.wind[1] + r22 * x.wind[2] + (TURB ? x.tl[2] : (T)0));
     T Va = M<T>::sqrt(a0 * a0 + a1 * a1 + a2 * a2);
     const T alpha = M<T>::atan2(a2, a0);
-    const T beta = M<T>::asin(a1 / Va);
+    const T sb = a1 / Va;                       // == sin(beta): beta = asin(a1 / Va) (pyfly.py:1848)
+    const T beta = M<T>::asin(sb);
     if (c.va_con_max > (T)0 && Va > c.va_con_max) return FW_TERM_VA;
+    // sin/cos of alpha = atan2(a2, a0) and cos of beta = asin(a1/Va) follow from the airspeed triangle without any
+    // trigonometric evaluation (identical up to rounding): sin a = a2/r, cos a = a0/r, cos b = r/Va, r = |(a0, a2)|
+    const T rxz = M<T>::sqrt(a0 * a0 + a2 * a2);
+    const T inv_rxz = (T)1 / rxz;
+    const T sa = (rxz > (T)0) ? a2 * inv_rxz : (T)0, ca = (rxz > (T)0) ? a0 * inv_rxz : (T)1;
+    const T cb = rxz / Va;
     if (Va < c.va_value_min) Va = c.va_value_min;
 
     const T pre = c.half_rho * (Va * Va) * c.S_wing;
@@ -266,14 +273,11 @@ __device__ __forceinline__ int rhs(const DCfg<T>& c, const DynCtx<T>& x, const T
         const T g1 = M<T>::exp(c.M_ * (alpha - c.a_0)), g2 = M<T>::exp(-c.M_ * (alpha + c.a_0));
         sigma = (T)1 - (T)1 / (((T)1 + g1) * ((T)1 + g2));
     }
-    T sa, ca, sb, cb;
-    M<T>::sincos(alpha, &sa, &ca);
-    M<T>::sincos(beta, &sb, &cb);
     const T sg = sgn(alpha);
     const T inv2Va = (T)1 / ((T)2 * Va);
     const T C_L = ((T)1 - sigma) * CLlin + sigma * ((T)2 * sg * (sa * sa) * ca);
     const T lift = pre * (C_L + c.C_L_q * c.c * inv2Va * q + c.C_L_delta_e * elevator);
-    const T C_Da = c.C_D_p + ((T)1 - sigma) * (CLlin * CLlin) / c.pi_e_ar + sigma * ((T)2 * sg * (sa * sa * sa));
+    const T C_Da = c.C_D_p + ((T)1 - sigma) * (CLlin * CLlin) * c.inv_pi_e_ar + sigma * ((T)2 * sg * (sa * sa * sa));
     const T C_Db = c.C_D_beta1 * beta + c.C_D_beta2 * (beta * beta);
     const T drag = pre * (C_Da + C_Db + c.C_D_q * c.c * inv2Va * q + c.C_D_delta_e * (elevator * elevator));
     const T C_m = ((T)1 - sigma) * (c.C_m_0 + c.C_m_alpha * alpha) + sigma * (c.C_m_fp * sg * (sa * sa));
@@ -299,15 +303,15 @@ __device__ __forceinline__ int rhs(const DCfg<T>& c, const DynCtx<T>& x, const T
     dy[2] = (T)0.5 * (Q * e0 - R * e1 + P * e3);
     dy[3] = (T)0.5 * (R * e0 + Q * e1 - P * e2);
     dy[4] = c.gam[1] * P * Q - c.gam[2] * Q * R + c.gam[3] * tx + c.gam[4] * tz;
-    dy[5] = c.gam[5] * P * R - c.gam[6] * (P * P - R * R) + ty / c.Jy;
+    dy[5] = c.gam[5] * P * R - c.gam[6] * (P * P - R * R) + ty * c.inv_Jy;
     dy[6] = c.gam[7] * P * Q - c.gam[1] * Q * R + c.gam[4] * tx + c.gam[8] * tz;
     // _f_p_dot: R(q)^T-like matrix of pyfly.py:1718-1736
     dy[7] = (e1 * e1 + e0 * e0 - e2 * e2 - e3 * e3) * u + (T)2 * (e1 * e2 - e3 * e0) * v + (T)2 * (e1 * e3 + e2 * e0) * w;
     dy[8] = (T)2 * (e1 * e2 + e3 * e0) * u + (e2 * e2 + e0 * e0 - e1 * e1 - e3 * e3) * v + (T)2 * (e2 * e3 - e1 * e0) * w;
     dy[9] = (T)2 * (e1 * e3 - e2 * e0) * u + (T)2 * (e2 * e3 + e1 * e0) * v + (e3 * e3 + e0 * e0 - e1 * e1 - e2 * e2) * w;
-    dy[10] = R * v - Q * w + fx / c.mass;
-    dy[11] = P * w - R * u + fyb / c.mass;
-    dy[12] = Q * u - P * v + fz / c.mass;
+    dy[10] = R * v - Q * w + fx * c.inv_mass;
+    dy[11] = P * w - R * u + fyb * c.inv_mass;
+    dy[12] = Q * u - P * v + fz * c.inv_mass;
     // Actuation.rhs (pyfly.py:519-543): elevons 2nd order on clipped value/rate, throttle 1st order
     dy[13] = erd;
     dy[14] = eld;

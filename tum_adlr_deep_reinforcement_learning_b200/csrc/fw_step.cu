@@ -154,7 +154,7 @@ __device__ __forceinline__ void load_dyn(const DCfg<T>& c, const Soa<T>& S, cons
 
 // ---- kernel A0: RungeKutta.__init__ + select_initial_step for every env, lock step ----
 template <typename T, bool TURB>
-__global__ void __launch_bounds__(128) rk45_init_kernel(const __grid_constant__ DCfg<T> c, const Soa<T> S, const StepIO io,
+__global__ void __launch_bounds__(128, 3) rk45_init_kernel(const __grid_constant__ DCfg<T> c, const Soa<T> S, const StepIO io,
                                                         const Scratch<T> W, int attempt_threads) {
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = S.n;
@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(128) rk4_kernel(const __grid_constant__ DCfg<T
 
 // ---- kernel B: everything after the integrator (once per step, high occupancy) ----
 template <typename T, bool TURB>
-__global__ void __launch_bounds__(128) head_kernel(const __grid_constant__ DCfg<T> c, const Soa<T> S, const StepIO io,
+__global__ void __launch_bounds__(128, 4) head_kernel(const __grid_constant__ DCfg<T> c, const Soa<T> S, const StepIO io,
                                                    const Scratch<T> W) {
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = S.n;
@@ -798,7 +798,9 @@ template <typename T> static void convert_cfg(const FwConfig& f, DCfg<T>& d) {
     d.half_rho = (T)(0.5 * f.rho);
     d.mg = (T)(f.mass * f.g);
     d.prop_k = (T)(0.5 * f.rho * f.S_prop * f.C_prop);
-    d.pi_e_ar = (T)(3.14159265358979323846 * f.e_oswald * (f.b * f.b / f.S_wing));
+    d.inv_pi_e_ar = (T)(1.0 / (3.14159265358979323846 * f.e_oswald * (f.b * f.b / f.S_wing)));
+    d.inv_Jy = (T)(1.0 / f.Jy);
+    d.inv_mass = (T)(1.0 / f.mass);
     CP(dt); CP(elevon_min); CP(elevon_max); CP(elevon_dot_max); CP(throttle_min); CP(throttle_max);
     d.w0sq = (T)(f.elevon_omega0 * f.elevon_omega0);
     d.two_zeta_w0 = (T)(2 * f.elevon_zeta * f.elevon_omega0);
