@@ -7,7 +7,7 @@
 Workload (BASELINE.json configs[2], "C3"): 65536 envs PER GPU (weak scaling; envs are independent, no collective
 on the step), default attitude task, light Dryden turbulence + steady wind U(-8, 8), actions U(-1,1)^3 that change
 every step, fp64 exact mode (bit-for-logic scipy-RK45 replica) — the parity-graded path.  One "step" = one
-VecEnv.step over every env of the rank = ONE launch of step_kernel.
+VecEnv.step over every env of the rank = three launches (rk45_init_kernel, rk45_attempt_kernel, head_kernel).
 
 Timed region (`value`): K launches with the action batches already resident in HBM, one CUDA-event pair per
 launch on the launching stream, an L2 flush (256 MiB write) between launches outside the event pairs; barrier +
@@ -126,7 +126,7 @@ def cpu_port_rate(cfg, budget_s, threads):
 
     timed(2, 0)                                   # warm-up
     dt = timed(5, 2)
-    k = max(5, min(2000, int(budget_s / max(dt / 5, 1e-6))))
+    k = max(5, min(20000, int(budget_s / max(dt / 5, 1e-6))))
     dt = timed(k, 7)
     rate = threads * per * k / dt
     return rate, "%d threads x %d envs x %d steps of the C3 workload (%.1f s)" % (threads, per, k, dt)
@@ -274,7 +274,7 @@ def main():
     flops_env_step = nf[0] * (W_RHS + T_RHS) + nf[1] * (W_ATT + T_ATT) + (W_ENV + T_ENV)
     achieved_tf = flops_env_step * n / (ms_per_step * 1e-3) / 1e12
     hbm_gbs = BYTES_PER_ENV_STEP_F64 * n / (ms_per_step * 1e-3) / 1e9
-    roofline = {"bound": "fp64", "kernel": "step_kernel<double, RK45_SCIPY, turbulence, 64>",
+    roofline = {"bound": "fp64", "kernel": "rk45_attempt_kernel<double, turbulence, 64> (+ rk45_init_kernel, head_kernel: the whole step is timed)",
                 "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak,
                 "peak_source": "DFMA micro-benchmark fw_measure_fma_peak on this GPU, same process (MEASURED_PEAKS.json "
                                "has no vector-pipe figure)",
@@ -324,6 +324,25 @@ def main():
                                   "parity path"}
             e2.close()
 
+    # ---- PPO train env-steps/s (BASELINE.json second metric, config C4: 8192 envs/GPU, updates included) ----
+    ppo = None
+    if not args.no_extra:
+        from tum_adlr_deep_reinforcement_learning_b200.ppo import PPO
+        n_ppo, n_steps, iters = 8192, 32, 3
+        venv = FixedWingVecEnv(n_ppo, sim_config_kw={"turbulence": True}, device=local, seed=0, env_id_offset=rank * n_ppo)
+        algo = PPO(venv, n_steps=n_steps, batch_size=n_ppo * n_steps // 8, n_epochs=10, dist=dist if world > 1 else None)
+        algo.learn(total_timesteps=world * n_ppo * n_steps)            # warm-up iteration
+        barrier()
+        t0 = time.perf_counter()
+        algo.learn(total_timesteps=algo.num_timesteps + iters * world * n_ppo * n_steps)
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        ppo = {"value": iters * world * n_ppo * n_steps / dt, "unit": "env-steps/s (rollout + GAE + 10-epoch update)",
+               "envs_per_gpu": n_ppo, "n_steps": n_steps, "minibatch": n_ppo * n_steps // 8, "n_epochs": 10,
+               "iterations_timed": iters, "ep_rew_mean": algo.logs[-1]["ep_rew_mean"],
+               "note": "policy 2x64 tanh MLP in PyTorch; one gradient all-reduce per optimiser step when n_gpus > 1"}
+        venv.close()
+
     # ---- CPU baseline (rank 0 only, N = 1 only) ----
     cpu = None
     if rank == 0 and world == 1:
@@ -335,7 +354,8 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": workload_config(n), "roofline": roofline,
-                "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": K, "clocks": clocks, "modes": extra}
+                "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 3 * K, "gpu_launches_note": "rk45_init_kernel + rk45_attempt_kernel + head_kernel per step",
+                "clocks": clocks, "modes": extra, "ppo": ppo}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

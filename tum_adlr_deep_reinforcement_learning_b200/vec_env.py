@@ -63,11 +63,13 @@ class FixedWingVecEnv:
     info_mode: "compat" builds the reference's per-env info dict for every env every step (info["target"] always
     present, fixed_wing.py:626); "lazy" (default) builds dicts only for envs that finished and hands out one shared
     empty dict for the rest — at tens of thousands of envs the dict loop, not the simulator, bounds the step rate.
+    copy_outputs: False (default) returns views of double-buffered pinned host arrays that stay valid until the
+    second-next step() (enough for SB3's collect_rollouts); True returns fresh copies every step.
     """
 
     def __init__(self, num_envs, config_path=None, config_kw=None, sim_config_path=None, sim_config_kw=None,
                  device=0, seed=0, env_id_offset=0, precision="f64", integrator="rk45", rk4_substeps=4,
-                 info_mode="lazy", copy_outputs=True):
+                 info_mode="lazy", copy_outputs=False):
         self.cfg = build_config(env_cfg=config_path, sim_cfg=sim_config_path, config_kw=config_kw,
                                 sim_config_kw=sim_config_kw, precision=precision, integrator=integrator,
                                 rk4_substeps=rk4_substeps, seed=seed, env_id_offset=env_id_offset)
@@ -87,14 +89,19 @@ class FixedWingVecEnv:
         self.curriculum_level = 1.0
         n = self.num_envs
         self._act_pin = torch.zeros(n, 3, dtype=torch.float32).pin_memory()
+        self._act_np = self._act_pin.numpy()
         self._act_dev = torch.zeros(n, 3, dtype=torch.float32, device=self.device)
-        self._obs_pin = torch.zeros(n, 14, dtype=torch.float32).pin_memory()
-        self._rew_pin = torch.zeros(n, dtype=torch.float32).pin_memory()
-        self._done_pin = torch.zeros(n, dtype=torch.uint8).pin_memory()
+        # double-buffered pinned outputs: with copy_outputs=False the arrays returned by step k stay valid until
+        # step k+2 (SB3's collect_rollouts reads obs_k after step k+1 returns, on_policy_algorithm.py:163-180)
+        self._out = [(torch.zeros(n, 14, dtype=torch.float32).pin_memory(), torch.zeros(n, dtype=torch.float32).pin_memory(),
+                      torch.zeros(n, dtype=torch.uint8).pin_memory()) for _ in range(2)]
+        self._out_np = [(o.numpy(), r.numpy(), d.numpy().view(np.bool_)) for o, r, d in self._out]
+        self._flip = 0
+        self._no_done_infos = [_EMPTY_INFO] * n
         self._waiting = False
         self._t_start = time.time()
         self.h2d_bytes_per_step = self._act_pin.numel() * 4
-        self.d2h_bytes_per_step = self._obs_pin.numel() * 4 + self._rew_pin.numel() * 4 + self._done_pin.numel()
+        self.d2h_bytes_per_step = n * 14 * 4 + n * 4 + n
 
     # ------------------------------------------------------------------ tensor fast path
     def reset_tensor(self):
@@ -108,9 +115,10 @@ class FixedWingVecEnv:
     # ------------------------------------------------------------------ VecEnv API
     def reset(self):
         obs = self.sim.reset()
-        self._obs_pin.copy_(obs, non_blocking=True)
+        self._flip ^= 1
+        self._out[self._flip][0].copy_(obs, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
-        out = self._obs_pin.numpy()
+        out = self._out_np[self._flip][0]
         return out.copy() if self.copy_outputs else out
 
     def step_async(self, actions):
@@ -118,13 +126,15 @@ class FixedWingVecEnv:
             raise RuntimeError("step_async called while a step is pending (subproc_vec_env.py:112 contract)")
         a = np.asarray(actions)
         assert a.shape == (self.num_envs, 3), a.shape
-        assert not np.any(np.isnan(a)), "NaN action (fixed_wing.py:494)"
-        self._act_pin.numpy()[...] = a            # casts to float32 like DummyVecEnv buffers / SB3 policies
+        self._act_np[...] = a                     # casts to float32 like DummyVecEnv buffers / SB3 policies
+        assert not np.isnan(self._act_np.sum()), "NaN action (fixed_wing.py:494)"
         self._act_dev.copy_(self._act_pin, non_blocking=True)
         self.sim.step(self._act_dev, auto_reset=True)
-        self._obs_pin.copy_(self.sim.obs, non_blocking=True)
-        self._rew_pin.copy_(self.sim.rew, non_blocking=True)
-        self._done_pin.copy_(self.sim.done, non_blocking=True)
+        self._flip ^= 1
+        o, r, d = self._out[self._flip]
+        o.copy_(self.sim.obs, non_blocking=True)
+        r.copy_(self.sim.rew, non_blocking=True)
+        d.copy_(self.sim.done, non_blocking=True)
         self._waiting = True
 
     def step_wait(self):
@@ -132,11 +142,10 @@ class FixedWingVecEnv:
             raise RuntimeError("step_wait without step_async")
         torch.cuda.current_stream(self.device).synchronize()
         self._waiting = False
-        obs, rew = self._obs_pin.numpy(), self._rew_pin.numpy()
-        done = self._done_pin.numpy().astype(bool)
+        obs, rew, done = self._out_np[self._flip]
         infos = self._build_infos(done)
         if self.copy_outputs:
-            obs, rew = obs.copy(), rew.copy()
+            obs, rew, done = obs.copy(), rew.copy(), done.copy()
         return obs, rew, done, infos
 
     def step(self, actions):
@@ -237,9 +246,9 @@ class FixedWingVecEnv:
 
     def _build_infos(self, done):
         n = self.num_envs
+        if self.info_mode == "lazy" and not done.any():
+            return self._no_done_infos            # one shared list of one shared empty dict: treat as read-only
         done_idx = np.flatnonzero(done)
-        if self.info_mode == "lazy" and done_idx.size == 0:
-            return [_EMPTY_INFO] * n
         if self.info_mode == "compat":
             tgt = self.sim.get_field(bt.FIELD_TARGET).cpu().numpy()
             infos = [{"target": dict(zip(TARGET_STATES, map(float, tgt[i])))} for i in range(n)]
