@@ -228,6 +228,10 @@ int fw_gae(const float* rew_dev, const float* val_dev, const float* done_dev, co
  * returns achieved TFLOP/s (2 flop per FMA) measured with CUDA events on `device`. */
 int fw_measure_fma_peak(int32_t device, int32_t precision, double* tflops_out);
 
+/* Diagnostic: evaluates the straight-line FP64 math of the RHS hot loop elementwise (op 0: exp(x), 1: asin(x),
+ * 2: atan2(y, x)); used by the tests to bound their error against the host libm. */
+int fw_debug_math(int32_t op, const double* x_dev, const double* y_dev, double* out_dev, int32_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

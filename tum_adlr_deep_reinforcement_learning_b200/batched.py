@@ -141,3 +141,13 @@ def measure_fma_peak(device=0, precision="f64"):
     _lib.check(_lib.lib().fw_measure_fma_peak(device, 0 if precision == "f64" else 1, ctypes.byref(out)),
                "fw_measure_fma_peak")
     return out.value
+
+
+def debug_math(op, x, y=None):
+    """Elementwise evaluation of the RHS hot-loop math (0 exp, 1 asin, 2 atan2(y, x)) on float64 CUDA tensors."""
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    st = ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+    _lib.check(_lib.lib().fw_debug_math(int(op), _ptr(x), _ptr(None if y is None else y.contiguous()), _ptr(out),
+                                        x.numel(), st), "fw_debug_math")
+    return out

@@ -20,6 +20,7 @@
 #include <stdint.h>
 
 #include "../../include/fwb200.h"
+#include "fw_math.cuh"
 
 namespace fw {
 
@@ -33,6 +34,11 @@ template <> struct M<double> {
     static __device__ __forceinline__ double exp(double x) { return ::exp(x); }
     static __device__ __forceinline__ double log(double x) { return ::log(x); }
     static __device__ __forceinline__ double sqrt(double x) { return ::sqrt(x); }
+    static __device__ __forceinline__ double rsqrt(double x) { return ::rsqrt(x); }
+    // straight-line versions for the RHS hot loop (fw_math.cuh)
+    static __device__ __forceinline__ double atan2_hot(double y, double x) { return atan2_bf(y, x); }
+    static __device__ __forceinline__ double asin_hot(double x) { return asin_bf(x); }
+    static __device__ __forceinline__ double exp_hot(double x) { return exp_bf(x); }
     static __device__ __forceinline__ double atan2(double y, double x) { return ::atan2(y, x); }
     static __device__ __forceinline__ double asin(double x) { return ::asin(x); }
     static __device__ __forceinline__ double pow(double x, double y) { return ::pow(x, y); }
@@ -51,6 +57,10 @@ template <> struct M<float> {
     static __device__ __forceinline__ float exp(float x) { return ::expf(x); }
     static __device__ __forceinline__ float log(float x) { return ::logf(x); }
     static __device__ __forceinline__ float sqrt(float x) { return ::sqrtf(x); }
+    static __device__ __forceinline__ float rsqrt(float x) { return ::rsqrtf(x); }
+    static __device__ __forceinline__ float atan2_hot(float y, float x) { return ::atan2f(y, x); }
+    static __device__ __forceinline__ float asin_hot(float x) { return ::asinf(x); }
+    static __device__ __forceinline__ float exp_hot(float x) { return ::expf(x); }
     static __device__ __forceinline__ float atan2(float y, float x) { return ::atan2f(y, x); }
     static __device__ __forceinline__ float asin(float x) { return ::asinf(x); }
     static __device__ __forceinline__ float pow(float x, float y) { return ::powf(x, y); }
@@ -82,7 +92,7 @@ template <typename T> struct DCfg {
     T C_l_0, C_l_beta, C_l_p, C_l_r, C_l_delta_a, C_l_delta_r;
     T C_n_0, C_n_beta, C_n_p, C_n_r, C_n_delta_a, C_n_delta_r;
     T gam[9];
-    T half_rho, mg, prop_k /* 0.5 rho S_prop C_prop */, inv_pi_e_ar, inv_Jy, inv_mass;
+    T half_rho, mg, prop_k /* 0.5 rho S_prop C_prop */, inv_pi_e_ar, inv_Jy, inv_mass, exp_M_a0;
     T dt, elevon_min, elevon_max, elevon_dot_max, w0sq, two_zeta_w0, inv_tau, throttle_min, throttle_max;
     T omega_con_min[3], omega_con_max[3], va_value_min, va_con_max;
     T init_lo[12], init_hi[12], wind_mag_min, wind_mag_max, turb_noise_scale;
@@ -247,18 +257,23 @@ __device__ __forceinline__ int rhs(const DCfg<T>& c, const DynCtx<T>& x, const T
     T a0 = u - (r00 * x.wind[0] + r01 * x.wind[1] + r02 * x.wind[2] + (TURB ? x.tl[0] : (T)0));
     T a1 = v - (r10 * x.wind[0] + r11 * x.wind[1] + r12 * x.wind[2] + (TURB ? x.tl[1] : (T)0));
     T a2 = w - (r20 * x.wind[0] + r21 * x.wind[1] + r22 * x.wind[2] + (TURB ? x.tl[2] : (T)0));
-    T Va = M<T>::sqrt(a0 * a0 + a1 * a1 + a2 * a2);
-    const T alpha = M<T>::atan2(a2, a0);
-    const T sb = a1 / Va;                       // == sin(beta): beta = asin(a1 / Va) (pyfly.py:1848)
-    const T beta = M<T>::asin(sb);
+    // airspeed triangle.  One reciprocal square root per length: Va = s * rsqrt(s) and 1/Va = rsqrt(s) are within
+    // 1-2 ulp of the reference's sqrt / divide, far inside the 1e-9 parity bar, and cost a third of sqrt + 3 divides.
+    const T s_xz = a0 * a0 + a2 * a2, s_all = a0 * a0 + a1 * a1 + a2 * a2;
+    const T inv_Va_raw = M<T>::rsqrt(s_all), inv_rxz = M<T>::rsqrt(s_xz);
+    T Va = s_all * inv_Va_raw;
+    const T rxz = s_xz * inv_rxz;
+    const T alpha = M<T>::atan2_hot(a2, a0);
+    const T sb = a1 * inv_Va_raw;               // == sin(beta): beta = asin(a1 / Va) (pyfly.py:1848)
+    const T beta = M<T>::asin_hot(sb);
     if (c.va_con_max > (T)0 && Va > c.va_con_max) return FW_TERM_VA;
-    // sin/cos of alpha = atan2(a2, a0) and cos of beta = asin(a1/Va) follow from the airspeed triangle without any
+    // sin/cos of alpha = atan2(a2, a0) and cos of beta = asin(a1/Va) follow from the triangle without any
     // trigonometric evaluation (identical up to rounding): sin a = a2/r, cos a = a0/r, cos b = r/Va, r = |(a0, a2)|
-    const T rxz = M<T>::sqrt(a0 * a0 + a2 * a2);
-    const T inv_rxz = (T)1 / rxz;
-    const T sa = (rxz > (T)0) ? a2 * inv_rxz : (T)0, ca = (rxz > (T)0) ? a0 * inv_rxz : (T)1;
-    const T cb = rxz / Va;
-    if (Va < c.va_value_min) Va = c.va_value_min;
+    const T sa = (s_xz > (T)0) ? a2 * inv_rxz : (T)0, ca = (s_xz > (T)0) ? a0 * inv_rxz : (T)1;
+    const T cb = (s_xz > (T)0) ? rxz * inv_Va_raw : (T)0;
+    T inv2Va = (T)0.5 * inv_Va_raw;
+    if (!(s_all > (T)0)) Va = (T)0;             // rsqrt(0) = inf: keep Va = 0 like sqrt(0)
+    if (Va < c.va_value_min) { Va = c.va_value_min; inv2Va = (T)1 / ((T)2 * Va); }
 
     const T pre = c.half_rho * (Va * Va) * c.S_wing;
     const T fgx = c.mg * ((T)2 * (e1 * e3 - e2 * e0)), fgy = c.mg * ((T)2 * (e2 * e3 + e1 * e0));
@@ -266,15 +281,17 @@ __device__ __forceinline__ int rhs(const DCfg<T>& c, const DynCtx<T>& x, const T
     const T CLlin = c.C_L_0 + c.C_L_alpha * alpha;
     T sigma;
     if (sizeof(T) == 8) {
-        const T ex1 = M<T>::exp(-c.M_ * (alpha - c.a_0)), ex2 = M<T>::exp(c.M_ * (alpha + c.a_0));
-        sigma = ((T)1 + ex1 + ex2) / (((T)1 + ex1) * ((T)1 + ex2));
+        // sigma = (1 + e1 + e2) / ((1 + e1)(1 + e2)), e1 = exp(-M(a - a0)), e2 = exp(M(a + a0))  (pyfly.py:1541-1543).
+        // With E = exp(M a), C = exp(M a0): e1 = C / E, e2 = C E, and multiplying through by E gives the same value
+        // from ONE exponential and ONE division, all terms positive (no cancellation): |a| <= pi keeps E^2 < 1e137.
+        const T E = M<T>::exp_hot(c.M_ * alpha);
+        sigma = (E + c.exp_M_a0 + c.exp_M_a0 * (E * E)) / ((E + c.exp_M_a0) * ((T)1 + c.exp_M_a0 * E));
     } else {
-        // algebraically identical, overflow-safe in fp32: sigma = 1 - s(-M(a-a0)) s(M(a+a0)), s = logistic
+        // overflow-safe in fp32: sigma = 1 - s(-M(a-a0)) s(M(a+a0)), s = logistic
         const T g1 = M<T>::exp(c.M_ * (alpha - c.a_0)), g2 = M<T>::exp(-c.M_ * (alpha + c.a_0));
         sigma = (T)1 - (T)1 / (((T)1 + g1) * ((T)1 + g2));
     }
     const T sg = sgn(alpha);
-    const T inv2Va = (T)1 / ((T)2 * Va);
     const T C_L = ((T)1 - sigma) * CLlin + sigma * ((T)2 * sg * (sa * sa) * ca);
     const T lift = pre * (C_L + c.C_L_q * c.c * inv2Va * q + c.C_L_delta_e * elevator);
     const T C_Da = c.C_D_p + ((T)1 - sigma) * (CLlin * CLlin) * c.inv_pi_e_ar + sigma * ((T)2 * sg * (sa * sa * sa));

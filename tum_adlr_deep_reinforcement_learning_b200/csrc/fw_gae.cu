@@ -11,6 +11,7 @@
 #include <stdio.h>
 
 #include "../../include/fwb200.h"
+#include "fw_math.cuh"
 
 namespace {
 
@@ -45,6 +46,15 @@ __global__ void gae_kernel(const float* __restrict__ rew, const float* __restric
         ret[o] = __fadd_rn(a, v);
         v_next = v;
     }
+}
+
+// diagnostic: evaluates the hot-loop math kernels of fw_math.cuh elementwise (tests/test_gpu_math.py)
+__global__ void debug_math_kernel(int op, const double* x, const double* y, double* out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (op == 0) out[i] = fw::exp_bf(x[i]);
+    else if (op == 1) out[i] = fw::asin_bf(x[i]);
+    else out[i] = fw::atan2_bf(y[i], x[i]);
 }
 
 template <typename T, int ILP>
@@ -106,6 +116,12 @@ int fw_gae(const float* rew_dev, const float* val_dev, const float* done_dev, co
     const int bs = 128, grid = (N + bs - 1) / bs;
     gae_kernel<<<grid, bs, 0, (cudaStream_t)stream>>>(rew_dev, val_dev, done_dev, last_val_dev, last_done_dev, adv_dev,
                                                      ret_dev, T, N, gamma, gl);
+    return cudaGetLastError() == cudaSuccess ? FW_OK : FW_ECUDA;
+}
+
+int fw_debug_math(int32_t op, const double* x_dev, const double* y_dev, double* out_dev, int32_t n, void* stream) {
+    if (!x_dev || !out_dev || n <= 0 || op < 0 || op > 2 || (op == 2 && !y_dev)) return FW_EINVAL;
+    debug_math_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(op, x_dev, y_dev, out_dev, n);
     return cudaGetLastError() == cudaSuccess ? FW_OK : FW_ECUDA;
 }
 

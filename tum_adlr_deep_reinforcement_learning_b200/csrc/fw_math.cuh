@@ -1,0 +1,104 @@
+// fw_math.cuh — branch-free FP64 exp / asin / atan2 for the RHS of the flight dynamics.
+//
+// Why: the attempt kernel is latency bound (one FP64 issue per ~6 cycles per warp, 2 warps per scheduler, profiles/
+// r01_v3): the CUDA math library's asin/atan2/exp are correct to <= 2 ulp but are built from short basic blocks
+// (special-case branches) around dependent Horner chains, which stops the compiler from interleaving them with each
+// other and with the independent kinematics of the same RHS.  The versions below are straight-line code (selects
+// instead of branches, even/odd split polynomials), accurate to ~1 ulp on the domain the dynamics can reach;
+// out-of-domain arguments fall back to the library.  Coefficients: tools/gen_math_coeffs.py (Chebyshev interpolation
+// in 60-digit arithmetic).  Accuracy is tested on the GPU against the host libm (tests/test_gpu_math.py).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace fw {
+
+// exp(x) for |x| <= 700: n = rint(x log2 e), r = x - n ln2 (two-term Cody-Waite), Taylor degree 13 on |r| <= 0.3466
+// (truncation 4e-18), scaled by 2^n through the exponent field.
+__device__ __forceinline__ double exp_bf(double x) {
+    const double t = x * 1.4426950408889634074;
+    const double n = (t + 6755399441055744.0) - 6755399441055744.0;       // rint via the 1.5 * 2^52 trick
+    double r = fma(-n, 6.93147180369123816490e-01, x);
+    r = fma(-n, 1.90821492927058770002e-10, r);
+    const double r2 = r * r;
+    // even / odd Horner halves of sum r^k / k!
+    double pe = 1.0 / 479001600.0;                 // 1/12!
+    pe = fma(pe, r2, 1.0 / 3628800.0);             // 1/10!
+    pe = fma(pe, r2, 1.0 / 40320.0);
+    pe = fma(pe, r2, 1.0 / 720.0);
+    pe = fma(pe, r2, 1.0 / 24.0);
+    pe = fma(pe, r2, 0.5);
+    pe = fma(pe, r2, 1.0);
+    double po = 1.0 / 6227020800.0;                // 1/13!
+    po = fma(po, r2, 1.0 / 39916800.0);            // 1/11!
+    po = fma(po, r2, 1.0 / 362880.0);
+    po = fma(po, r2, 1.0 / 5040.0);
+    po = fma(po, r2, 1.0 / 120.0);
+    po = fma(po, r2, 1.0 / 6.0);
+    po = fma(po, r2, 1.0);
+    const double p = fma(po, r, pe);
+    const int ni = (int)n;
+    return __hiloint2double(__double2hiint(p) + ni * 1048576, __double2loint(p));
+}
+
+static __device__ __noinline__ double asin_lib(double x) { return ::asin(x); }
+
+// asin(x): x + x z g(z), z = x^2, for |x| <= 1/2 (the sideslip of a flying aircraft); library call otherwise.
+__device__ __forceinline__ double asin_bf(double x) {
+    const double z = x * x;
+    const double z2 = z * z;
+    double pe, po;
+    pe = -0.01924167174674304;
+    pe = fma(pe, z2, 0.0030448799094556773);
+    pe = fma(pe, z2, 0.009621842970100282);
+    pe = fma(pe, z2, 0.01396378001220357);
+    pe = fma(pe, z2, 0.02237215744350722);
+    pe = fma(pe, z2, 0.044642857142551895);
+    pe = fma(pe, z2, 0.16666666666666666);
+    po = 0.02961201126495512;
+    po = fma(po, z2, 0.019554513336123378);
+    po = fma(po, z2, 0.009319560794767446);
+    po = fma(po, z2, 0.011566459612121669);
+    po = fma(po, z2, 0.017352816540325496);
+    po = fma(po, z2, 0.03038194447553234);
+    po = fma(po, z2, 0.07500000000000118);
+    const double g = fma(po, z, pe);
+    double res = fma(x * z, g, x);
+    if (fabs(x) > 0.5) res = asin_lib(x);
+    return res;
+}
+
+// atan2(y, x): one division.  m = min/max of |x|, |y|; if m > tan(pi/8) the argument is folded with
+// atan(m) = pi/4 + atan((m - 1)/(m + 1)) which is formed directly as (mn - mx)/(mn + mx); then |t| <= tan(pi/8) and
+// atan(t) = t + t w q(w), w = t^2.  Octant / quadrant fix-ups are selects with hi/lo split constants.
+__device__ __forceinline__ double atan2_bf(double y, double x) {
+    const double ax = fabs(x), ay = fabs(y);
+    const double mx = fmax(ax, ay), mn = fmin(ax, ay);
+    const bool big = mn > 0.41421356237309503 * mx;
+    const double num = big ? mn - mx : mn;
+    const double den = big ? mn + mx : mx;
+    double t = num / den;
+    if (!(mx > 0.0)) t = 0.0;                      // atan2(0, 0) = 0
+    const double z = t * t;
+    const double z2 = z * z;
+    double pe, po;
+    pe = -0.034570561981427744;
+    pe = fma(pe, z2, -0.05230454270650244);
+    pe = fma(pe, z2, -0.06666424885738255);
+    pe = fma(pe, z2, -0.09090908753500877);
+    pe = fma(pe, z2, -0.14285714285659828);
+    pe = fma(pe, z2, -0.3333333333333333);
+    po = 0.016285756855221028;
+    po = fma(po, z2, 0.04551593220626549);
+    po = fma(po, z2, 0.05878928997834775);
+    po = fma(po, z2, 0.07692296375032143);
+    po = fma(po, z2, 0.11111111105155447);
+    po = fma(po, z2, 0.19999999999999804);
+    const double q = fma(po, z, pe);
+    double a = fma(t * z, q, t);
+    if (big) a = 7.85398163397448278999e-01 + (a + 3.06161699786838301793e-17);        // + pi/4
+    if (ay > ax) a = 1.57079632679489655800e+00 - (a - 6.12323399573676603587e-17);    // pi/2 - a
+    if (x < 0.0) a = 3.14159265358979311600e+00 - (a - 1.22464679914735317723e-16);    // pi - a
+    return copysign(a, y);
+}
+
+}  // namespace fw

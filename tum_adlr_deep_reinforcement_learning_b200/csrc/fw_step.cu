@@ -12,6 +12,7 @@
 // rk4_kernel -> head_kernel.
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <new>
 
@@ -801,6 +802,7 @@ template <typename T> static void convert_cfg(const FwConfig& f, DCfg<T>& d) {
     d.inv_pi_e_ar = (T)(1.0 / (3.14159265358979323846 * f.e_oswald * (f.b * f.b / f.S_wing)));
     d.inv_Jy = (T)(1.0 / f.Jy);
     d.inv_mass = (T)(1.0 / f.mass);
+    d.exp_M_a0 = (T)exp(f.M * f.a_0);
     CP(dt); CP(elevon_min); CP(elevon_max); CP(elevon_dot_max); CP(throttle_min); CP(throttle_max);
     d.w0sq = (T)(f.elevon_omega0 * f.elevon_omega0);
     d.two_zeta_w0 = (T)(2 * f.elevon_zeta * f.elevon_omega0);
