@@ -39,6 +39,7 @@ template <> struct M<double> {
     static __device__ __forceinline__ double atan2_hot(double y, double x) { return atan2_bf(y, x); }
     static __device__ __forceinline__ double asin_hot(double x) { return asin_bf(x); }
     static __device__ __forceinline__ double exp_hot(double x) { return exp_bf(x); }
+    static __device__ __forceinline__ double rcp_hot(double x) { return rcp_fast(x); }
     static __device__ __forceinline__ double atan2(double y, double x) { return ::atan2(y, x); }
     static __device__ __forceinline__ double asin(double x) { return ::asin(x); }
     static __device__ __forceinline__ double pow(double x, double y) { return ::pow(x, y); }
@@ -61,6 +62,7 @@ template <> struct M<float> {
     static __device__ __forceinline__ float atan2_hot(float y, float x) { return ::atan2f(y, x); }
     static __device__ __forceinline__ float asin_hot(float x) { return ::asinf(x); }
     static __device__ __forceinline__ float exp_hot(float x) { return ::expf(x); }
+    static __device__ __forceinline__ float rcp_hot(float x) { return 1.0f / x; }
     static __device__ __forceinline__ float atan2(float y, float x) { return ::atan2f(y, x); }
     static __device__ __forceinline__ float asin(float x) { return ::asinf(x); }
     static __device__ __forceinline__ float pow(float x, float y) { return ::powf(x, y); }
@@ -285,7 +287,7 @@ __device__ __forceinline__ int rhs(const DCfg<T>& c, const DynCtx<T>& x, const T
         // With E = exp(M a), C = exp(M a0): e1 = C / E, e2 = C E, and multiplying through by E gives the same value
         // from ONE exponential and ONE division, all terms positive (no cancellation): |a| <= pi keeps E^2 < 1e137.
         const T E = M<T>::exp_hot(c.M_ * alpha);
-        sigma = (E + c.exp_M_a0 + c.exp_M_a0 * (E * E)) / ((E + c.exp_M_a0) * ((T)1 + c.exp_M_a0 * E));
+        sigma = (E + c.exp_M_a0 + c.exp_M_a0 * (E * E)) * M<T>::rcp_hot((E + c.exp_M_a0) * ((T)1 + c.exp_M_a0 * E));
     } else {
         // overflow-safe in fp32: sigma = 1 - s(-M(a-a0)) s(M(a+a0)), s = logistic
         const T g1 = M<T>::exp(c.M_ * (alpha - c.a_0)), g2 = M<T>::exp(-c.M_ * (alpha + c.a_0));

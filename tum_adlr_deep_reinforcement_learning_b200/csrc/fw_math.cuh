@@ -5,7 +5,7 @@
 // (special-case branches) around dependent Horner chains, which stops the compiler from interleaving them with each
 // other and with the independent kinematics of the same RHS.  The versions below are straight-line code (selects
 // instead of branches, even/odd split polynomials), accurate to ~1 ulp on the domain the dynamics can reach;
-// out-of-domain arguments fall back to the library.  Coefficients: tools/gen_math_coeffs.py (Chebyshev interpolation
+// the full domain of each function is covered without a library fallback.  Coefficients: tools/gen_math_coeffs.py (Chebyshev interpolation
 // in 60-digit arithmetic).  Accuracy is tested on the GPU against the host libm (tests/test_gpu_math.py).
 #pragma once
 #include <cuda_runtime.h>
@@ -40,11 +40,30 @@ __device__ __forceinline__ double exp_bf(double x) {
     return __hiloint2double(__double2hiint(p) + ni * 1048576, __double2loint(p));
 }
 
-static __device__ __noinline__ double asin_lib(double x) { return ::asin(x); }
+// 1/x for normal-range x: hardware seed (rcp.approx.ftz.f64, ~2^-23) + two Newton steps -> ~1 ulp, 6 instructions
+// instead of the ~35 of an IEEE-rounded division with its special-case fix-ups.
+__device__ __forceinline__ double rcp_fast(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
 
-// asin(x): x + x z g(z), z = x^2, for |x| <= 1/2 (the sideslip of a flying aircraft); library call otherwise.
+// asin(x), |x| <= 1, straight line.  |x| <= 1/2: x + x z g(z), z = x^2.  Otherwise asin = pi/2 - 2 asin(sqrt((1-|x|)/2))
+// with the same polynomial on z = (1-|x|)/2; the square root comes from rsqrt plus its exact residual (fma) so that the
+// doubled term keeps ~1 ulp.  Worst error 1.6 ulp (tools/gen_math_coeffs.py grid; tests/test_gpu_math.py).
 __device__ __forceinline__ double asin_bf(double x) {
-    const double z = x * x;
+    const double ax = fabs(x);
+    const bool big = ax > 0.5;
+    const double z = big ? (1.0 - ax) * 0.5 : x * x;
+    const double rs = ::rsqrt(z);
+    double sq = z * rs;                                   // ~sqrt(z)
+    double corr = fma(-sq, sq, z) * (0.5 * rs);           // sqrt(z) - sq to first order
+    if (!(z > 0.0)) { sq = 0.0; corr = 0.0; }
+    const double sv = big ? sq : ax;
+    const double cv = big ? corr : 0.0;
     const double z2 = z * z;
     double pe, po;
     pe = -0.01924167174674304;
@@ -62,12 +81,12 @@ __device__ __forceinline__ double asin_bf(double x) {
     po = fma(po, z2, 0.03038194447553234);
     po = fma(po, z2, 0.07500000000000118);
     const double g = fma(po, z, pe);
-    double res = fma(x * z, g, x);
-    if (fabs(x) > 0.5) res = asin_lib(x);
-    return res;
+    const double pp = sv + fma(sv * z, g, cv);
+    const double res = big ? 1.57079632679489655800e+00 - (2.0 * pp - 6.12323399573676603587e-17) : pp;
+    return copysign(res, x);
 }
 
-// atan2(y, x): one division.  m = min/max of |x|, |y|; if m > tan(pi/8) the argument is folded with
+// atan2(y, x): one reciprocal.  m = min/max of |x|, |y|; if m > tan(pi/8) the argument is folded with
 // atan(m) = pi/4 + atan((m - 1)/(m + 1)) which is formed directly as (mn - mx)/(mn + mx); then |t| <= tan(pi/8) and
 // atan(t) = t + t w q(w), w = t^2.  Octant / quadrant fix-ups are selects with hi/lo split constants.
 __device__ __forceinline__ double atan2_bf(double y, double x) {
@@ -76,8 +95,8 @@ __device__ __forceinline__ double atan2_bf(double y, double x) {
     const bool big = mn > 0.41421356237309503 * mx;
     const double num = big ? mn - mx : mn;
     const double den = big ? mn + mx : mx;
-    double t = num / den;
-    if (!(mx > 0.0)) t = 0.0;                      // atan2(0, 0) = 0
+    double t = num * rcp_fast(den);
+    if (!(mx > 1e-290)) t = 0.0;                   // atan2(0, 0) = 0 (and the flushed-denormal corner)
     const double z = t * t;
     const double z2 = z * z;
     double pe, po;

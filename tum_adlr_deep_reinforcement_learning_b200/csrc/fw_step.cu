@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(NT) rk45_attempt_kernel(const __grid_constant_
                     for (int j = 0; j < 6; ++j) acc += KS(j, i) * (T)RK_E[j];
                     acc += dyv[i] * (T)RK_E[6];
                     const T scl = atol + M<T>::fmax(M<T>::fabs(y[i]), M<T>::fabs(ys[i])) * rtol;
-                    const T ei = acc * h / scl;
+                    const T ei = acc * h * M<T>::rcp_hot(scl);      // scl >= atol: normal range
                     errsq += ei * ei;
                 }
                 const T err = M<T>::sqrt(errsq) / M<T>::sqrt((T)FW_NY);
