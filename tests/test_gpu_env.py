@@ -179,7 +179,11 @@ def test_ppo_plumbing_runs_and_improves_value_fit(cuda_device):
     venv = FixedWingVecEnv(1024, sim_config_kw={"turbulence": True}, seed=1)
     algo = PPO(venv, n_steps=16, batch_size=4096, n_epochs=2)
     algo.learn(total_timesteps=3 * 16 * 1024)
-    assert algo.num_timesteps == 3 * 16 * 1024 and len(algo.logs) == 3
+    rows = [r for r in algo.logs if "iteration" in r]
+    assert not [r for r in algo.logs if "iteration" not in r], algo.logs      # CUDA-graph capture must have worked
+    assert algo._rollout_graph is not None and algo._train_graph
+    assert algo.num_timesteps == 3 * 16 * 1024 and len(rows) == 3
+    algo.logs = rows
     assert all(np.isfinite(r["value_loss"]) and np.isfinite(r["policy_loss"]) for r in algo.logs)
     assert algo.buffer.advantages.shape == (16, 1024) and torch.isfinite(algo.buffer.advantages).all()
     venv.close()

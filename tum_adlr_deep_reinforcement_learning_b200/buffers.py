@@ -59,7 +59,8 @@ class RolloutBuffer:
         the final env.step (bool / uint8)."""
         adv, ret = bt.gae(self.rewards, self.values, self.dones, last_values.reshape(-1).to(torch.float32),
                           dones.reshape(-1).to(torch.uint8), self.gamma, self.gae_lambda)
-        self.advantages, self.returns = adv, ret
+        self.advantages.copy_(adv)
+        self.returns.copy_(ret)
 
     def flat(self, x):
         """swap_and_flatten (buffers.py:51-64): [T, N, ...] -> [N*T, ...] in env-major order."""
@@ -97,7 +98,10 @@ class RunningMeanStd:
         tot = self.count + batch_count
         new_mean = self.mean + delta * batch_count / tot
         m_2 = self.var * self.count + batch_var * batch_count + delta.square() * self.count * batch_count / tot
-        self.mean, self.var, self.count = new_mean, m_2 / tot, tot
+        # in place: the tensors keep their addresses, so the update can live inside a captured CUDA graph
+        self.mean.copy_(new_mean)
+        self.var.copy_(m_2 / tot)
+        self.count.copy_(tot)
 
     def sync(self, dist):
         """Merge the per-rank moments with one all-reduce of (count, count*mean, count*(var + mean^2))."""
@@ -109,7 +113,9 @@ class RunningMeanStd:
         mean = (packed[1:1 + k] / cnt).reshape(self.mean.shape)
         ex2 = (packed[1 + k:] / cnt).reshape(self.mean.shape)
         world = dist.get_world_size()
-        self.mean, self.var, self.count = mean, (ex2 - mean.square()).clamp_min(0), cnt / world
+        self.mean.copy_(mean)
+        self.var.copy_((ex2 - mean.square()).clamp_min(0))
+        self.count.copy_(cnt / world)
 
 
 class DeviceVecNormalize:
@@ -145,12 +151,12 @@ class DeviceVecNormalize:
 
     def step(self, obs, rew, done):
         """vec_normalize.py:106-127 order: update return, update obs stats, normalise, zero finished returns."""
-        self.ret = self.ret * self.gamma + rew.to(torch.float64)
+        self.ret.mul_(self.gamma).add_(rew.to(torch.float64))
         if self.training:
             self.obs_rms.update(obs)
             self.ret_rms.update(self.ret)
         out = self.normalize_obs(obs), self.normalize_reward(rew)
-        self.ret = torch.where(done.bool(), torch.zeros_like(self.ret), self.ret)
+        self.ret.masked_fill_(done.bool(), 0.0)
         return out
 
     def sync(self, dist):
@@ -162,5 +168,7 @@ class DeviceVecNormalize:
                 "ret_mean": self.ret_rms.mean, "ret_var": self.ret_rms.var, "ret_count": self.ret_rms.count}
 
     def load_state_dict(self, sd):
-        self.obs_rms.mean, self.obs_rms.var, self.obs_rms.count = sd["obs_mean"], sd["obs_var"], sd["obs_count"]
-        self.ret_rms.mean, self.ret_rms.var, self.ret_rms.count = sd["ret_mean"], sd["ret_var"], sd["ret_count"]
+        for rms, pre in ((self.obs_rms, "obs"), (self.ret_rms, "ret")):
+            rms.mean.copy_(sd[pre + "_mean"])
+            rms.var.copy_(sd[pre + "_var"])
+            rms.count.copy_(sd[pre + "_count"])
