@@ -254,12 +254,13 @@ class PPO:
     def learn(self, total_timesteps, log_interval=1, callback=None):
         if self._last_obs is None:
             self._setup()
-        t0 = time.time()
-        it = 0
+            self._t_start, self._iteration = time.time(), 0
+        t0 = self._t_start
         while self.num_timesteps < total_timesteps:
             self.collect_rollouts()
             stats = self.train()
-            it += 1
+            self._iteration += 1
+            it = self._iteration
             if it % log_interval == 0:
                 packed = torch.stack([self.ep_ret_sum, self.ep_len_sum, self.ep_count])
                 if self.dist is not None and self.world > 1:
