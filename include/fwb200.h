@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define FW_ABI_VERSION 1
+#define FW_ABI_VERSION 2
 
 #define FW_NY 19        /* ODE state: quat[4] omega[3] pos[3] vel[3] act_value[3] act_rate[3]  (pyfly.py:1372-1389) */
 #define FW_NOBS 14      /* default observation vector (fixed_wing_config.json "observation.states")               */
@@ -148,6 +148,9 @@ typedef struct FwConfig {
     int32_t _pad2;
     double step_fail_value;
     double rise_low, rise_high;           /* rise_time metric limits (0.1, 0.9) */
+    double obs_noise_mean, obs_noise_std; /* observation.noise {mean, var}: every entry += N(mean, var) where numpy's
+                                             `scale=var` makes "var" a standard deviation (fixed_wing.py:1246-1247);
+                                             std <= 0 and mean == 0 disables (the reference's default) */
 
     /* ---- counter-based RNG (Philox4x32-10) for auto-reset and turbulence noise ---- */
     uint64_t seed;

@@ -88,7 +88,7 @@ void fwo_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4
 
 /* Stream layout shared with the CUDA path (DESIGN.md "RNG"): counter = (env_id lo32, episode lo32, purpose|env hi,
  * block); two 53-bit uniforms per block. */
-enum { FWO_RNG_RESET = 0, FWO_RNG_NOISE = 1, FWO_RNG_RESAMPLE = 2, FWO_RNG_ACTION = 3 };
+enum { FWO_RNG_RESET = 0, FWO_RNG_NOISE = 1, FWO_RNG_RESAMPLE = 2, FWO_RNG_ACTION = 3, FWO_RNG_OBS = 4 };
 
 static void rng_block(uint64_t seed, int64_t env_id, uint64_t episode, uint32_t purpose, uint32_t block,
                       uint32_t out[4]) {
@@ -613,7 +613,27 @@ static double delta_feature_f32(const double* hist, int n, int col, int window, 
     return (double)s;
 }
 
-/* get_observation (fixed_wing.py:1113-1262) for observation.length == 1, no noise/normalisation */
+/* observation.noise (fixed_wing.py:1246-1247): every entry += N(mean, var).  MT19937 cannot be reproduced: the draws
+ * come from the Philox stream (purpose OBS, block = 4 * steps_count + b), 14 Box-Muller normals per observation. */
+static void add_obs_noise(const FwoEnv* e, double obs[FW_NOBS]) {
+    const FwConfig* c = &e->cfg;
+    if (!(c->obs_noise_std > 0) && c->obs_noise_mean == 0) return;
+    for (int b = 0; b < 4; ++b) {
+        uint32_t r[4];
+        rng_block(c->seed, e->env_id, e->episode, FWO_RNG_OBS, (uint32_t)(e->steps_count * 4 + b), r);
+        for (int i = 0; i < 2; ++i) {
+            double u1 = ((double)r[2 * i] + 0.5) * (1.0 / 4294967296.0);
+            double u2 = ((double)r[2 * i + 1] + 0.5) * (1.0 / 4294967296.0);
+            double rad = sqrt(-2.0 * log(u1));
+            double z0 = rad * cos(6.283185307179586476925 * u2), z1 = rad * sin(6.283185307179586476925 * u2);
+            int j = b * 4 + i * 2;
+            if (j < FW_NOBS) obs[j] += c->obs_noise_mean + c->obs_noise_std * z0;
+            if (j + 1 < FW_NOBS) obs[j + 1] += c->obs_noise_mean + c->obs_noise_std * z1;
+        }
+    }
+}
+
+/* get_observation (fixed_wing.py:1113-1262) for observation.length == 1, no normalisation */
 static void get_observation(const FwoEnv* e, double obs[FW_NOBS]) {
     const FwConfig* c = &e->cfg;
     obs[0] = e->h_roll; obs[1] = e->h_pitch; obs[2] = e->h_Va;
@@ -633,6 +653,7 @@ static void get_observation(const FwoEnv* e, double obs[FW_NOBS]) {
             obs[11 + j] = delta_feature_f32(e->cmd_hist, e->n_cmd, j, c->obs_act_window, 0);
         }
     }
+    add_obs_noise(e, obs);
 }
 
 /* get_reward (fixed_wing.py:941-1111) for the default factor family: three linear error factors, a linear

@@ -74,3 +74,28 @@ def test_no_cpu_fallback():
     h = ctypes.c_void_p()
     rc = _lib.lib().fw_create(ctypes.byref(C.build_config()), 4, 0, ctypes.byref(h))
     assert rc == -2 and b"no CPU fallback" in _lib.lib().fw_last_error()
+
+
+def test_reference_config_variants_build():
+    """The numeric variants of fixed_wing_config.json shipped with the reference (fixed_wing_config_dev.json,
+    examples/fixed_wing_config.json, examples/models/{mlp_controller,reproduceMLP,rep}) expressed as overrides."""
+    dev = C.build_config(config_kw={"action": {"scale_space": False}, "observation": {"noise": {"mean": 0, "var": 0.1}},
+                                    "target": {"states": {0: {"bound": 3}, 1: {"bound": 3}}}})
+    assert dev.scale_actions == 0 and dev.obs_noise_std == 0.1 and np.isclose(dev.tgt_bound[0], np.radians(3))
+    ex = C.build_config(config_kw={"reward": {"factors": {0: {"max": None}, 1: {"max": None}, 2: {"max": None},
+                                                          3: {"scaling": 45}}},
+                                   "simulator": {"states": {6: {"constraint_min": -360, "constraint_max": 360}}}})
+    assert np.isinf(ex.rew_err_max[0]) and ex.rew_delta_scaling == 45 and np.isclose(ex.omega_con_max[0], np.radians(360))
+    assert np.isclose(ex.omega_con_max[1], np.radians(720))
+
+
+def test_oracle_observation_noise_statistics():
+    from oracle import fw_oracle as O
+    cfg0 = C.build_config(sim_config_kw={"turbulence": False}, seed=3)
+    cfg1 = C.build_config(sim_config_kw={"turbulence": False}, seed=3,
+                          config_kw={"observation": {"noise": {"mean": 0.5, "var": 0.1}}})
+    clean = O.OracleBatch(cfg0, 4000).reset().copy()
+    noisy = O.OracleBatch(cfg1, 4000).reset().copy()
+    d = noisy - clean                       # same Philox reset stream -> identical states, only the noise differs
+    assert abs(d.mean() - 0.5) < 0.005 and abs(d.std() - 0.1) < 0.005
+    assert abs(np.corrcoef(d[:, 0], d[:, 1])[0, 1]) < 0.06

@@ -95,14 +95,20 @@ def test_reference_fixture_trajectories(name, cfg_kw, sim_kw, f32, cuda_device):
                 assert np.array_equal(np.nan_to_num(got[lo:hi], nan=-1), np.nan_to_num(row[lo:hi], nan=-1))
 
 
-def test_batch_against_oracle_random_policy(cuda_device):
-    """2048 envs x 40 steps, Philox resets, turbulence on, float32 actions: CUDA vs C oracle, state-for-state."""
+DEV_CONFIG_KW = {"action": {"scale_space": False}, "observation": {"noise": {"mean": 0, "var": 0.1}},
+                 "target": {"states": {0: {"bound": 3}, 1: {"bound": 3}}}}      # fixed_wing_config_dev.json
+
+
+@pytest.mark.parametrize("config_kw,amp", [(None, 1.5), (DEV_CONFIG_KW, 0.4)], ids=["default", "dev_config_obs_noise"])
+def test_batch_against_oracle_random_policy(config_kw, amp, cuda_device):
+    """2048 envs x 40 steps, Philox resets, turbulence on, float32 actions: CUDA vs C oracle, state-for-state.
+    The second case is the reference's fixed_wing_config_dev.json: unscaled actions, observation noise (Philox)."""
     import torch
     from oracle import fw_oracle as O
     from tum_adlr_deep_reinforcement_learning_b200 import batched as bt
     from tum_adlr_deep_reinforcement_learning_b200.config import build_config
     n, T = 2048, 40
-    cfg = build_config(sim_config_kw={"turbulence": True}, seed=1234)
+    cfg = build_config(config_kw=config_kw, sim_config_kw={"turbulence": True}, seed=1234)
     env = bt.BatchedFixedWing(n, cfg=cfg)
     env.enable_f64_outputs()
     env.reset()
@@ -111,7 +117,7 @@ def test_batch_against_oracle_random_policy(cuda_device):
     assert _rel(env.obs64.cpu().numpy(), obs_ref).max() < 1e-12
     rs = np.random.RandomState(0)
     for t in range(T):
-        a = rs.uniform(-1.5, 1.5, (n, 3)).astype(np.float32)
+        a = rs.uniform(-amp, amp, (n, 3)).astype(np.float32)
         env.step(torch.as_tensor(a).cuda(), auto_reset=True)
         o_ref, r_ref, d_ref = ob.step(a)
         assert np.array_equal(env.done.cpu().numpy(), d_ref)

@@ -20,7 +20,7 @@ import numpy as np
 
 _DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
 
-FW_ABI_VERSION = 1
+FW_ABI_VERSION = 2
 FW_NY, FW_NOBS, FW_NACT, FW_NSTATE_INJECT, FW_NMETRIC = 19, 14, 3, 21, 28
 FW_F64, FW_F32 = 0, 1
 FW_INT_RK45_SCIPY, FW_INT_RK4_FIXED = 0, 1
@@ -70,6 +70,7 @@ class FwConfig(ctypes.Structure):
            ("rew_err_scaling", _d * 3), ("rew_err_max", _d * 3), ("rew_delta_scaling", _d), ("rew_delta_max", _d),
            ("rew_bound_scaling", _d), ("rew_bound_max", _d), ("rew_delta_window", _i), ("obs_act_window", _i),
            ("step_fail_timesteps", _i), ("_pad2", _i), ("step_fail_value", _d), ("rise_low", _d), ("rise_high", _d),
+           ("obs_noise_mean", _d), ("obs_noise_std", _d),
            ("seed", ctypes.c_uint64), ("env_id_offset", ctypes.c_int64)])
 
 
@@ -425,8 +426,10 @@ def build_config(env_cfg=None, sim_cfg=None, config_kw=None, sim_config_kw=None,
     c.step_fail_timesteps = int(fail == "timesteps")
     c.step_fail_value = 0.0 if fail == "timesteps" else float(fail)
     obs = env["observation"]
-    if obs.get("length", 1) != 1 or obs.get("normalize", False) or (obs.get("noise") or {}).get("var", 0) != 0:
-        raise NotImplementedError("observation history / normalisation / noise (SURVEY §8f row 1)")
+    if obs.get("length", 1) != 1 or obs.get("normalize", False):
+        raise NotImplementedError("observation history / normalisation (SURVEY §8f row 1)")
+    noise = obs.get("noise") or {}
+    c.obs_noise_mean, c.obs_noise_std = float(noise.get("mean", 0) or 0), float(noise.get("var", 0) or 0)
     names = [(s["name"], s["type"]) for s in obs["states"]]
     expect = [("roll", "state"), ("pitch", "state"), ("Va", "state"), ("omega_p", "state"), ("omega_q", "state"),
               ("omega_r", "state"), ("roll", "target"), ("pitch", "target"), ("Va", "target"), ("alpha", "state"),

@@ -102,7 +102,7 @@ template <typename T> struct DCfg {
     T scale_low, scale_high, act_lo[3], act_hi[3], action_bounds_min[3], action_bounds_max[3];
     T tgt_low[3], tgt_high[3], tgt_delta[3], tgt_bound[3], streak_fraction;
     T rew_err_scaling[3], rew_err_max[3], rew_delta_scaling, rew_delta_max, rew_bound_scaling, rew_bound_max;
-    T step_fail_value, rise_low, rise_high;
+    T step_fail_value, rise_low, rise_high, obs_noise_mean, obs_noise_std;
     unsigned long long seed;
     long long env_id_offset;
 };
@@ -152,7 +152,7 @@ template <typename T> struct Soa {
 // ---------------------------------------------------------------------------------------------------------------
 // Philox4x32-10 counter-based RNG (Salmon et al. SC'11).  Stream layout (identical in oracle/fw_oracle.c):
 //   key = seed;  counter = (env_id lo32, episode lo32, purpose << 28 | env_id hi bits, block)
-enum { RNG_RESET = 0, RNG_NOISE = 1, RNG_RESAMPLE = 2, RNG_ACTION = 3 };
+enum { RNG_RESET = 0, RNG_NOISE = 1, RNG_RESAMPLE = 2, RNG_ACTION = 3, RNG_OBS = 4 };
 
 __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
 #pragma unroll
@@ -577,6 +577,29 @@ __device__ __forceinline__ void sample_target(const DCfg<T>& c, T roll, T pitch,
     }
 }
 
+// observation.noise (fixed_wing.py:1246-1247): every entry += N(mean, var); Philox purpose OBS, block = 4 * steps + b,
+// 14 Box-Muller normals per observation (same stream as oracle add_obs_noise).  Out of line: off by default.
+template <typename T>
+__device__ __noinline__ void add_obs_noise(const DCfg<T>& c, long long gid, unsigned long long episode, int steps,
+                                           T (&o)[FW_NOBS]) {
+#pragma unroll 1
+    for (int b = 0; b < 4; ++b) {
+        const uint4 r = rng_block(c.seed, gid, episode, RNG_OBS, (uint32_t)(steps * 4 + b));
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const double u1 = ((double)w[2 * i] + 0.5) * (1.0 / 4294967296.0);
+            const double u2 = ((double)w[2 * i + 1] + 0.5) * (1.0 / 4294967296.0);
+            const double rad = ::sqrt(-2.0 * ::log(u1));
+            double sn, cs;
+            ::sincos(6.283185307179586476925 * u2, &sn, &cs);
+            const int j = b * 4 + i * 2;
+            if (j < FW_NOBS) o[j] += c.obs_noise_mean + c.obs_noise_std * (T)(rad * cs);
+            if (j + 1 < FW_NOBS) o[j + 1] += c.obs_noise_mean + c.obs_noise_std * (T)(rad * sn);
+        }
+    }
+}
+
 // observation (fixed_wing.py:1113-1262, default 14-vector)
 template <typename T>
 __device__ __forceinline__ void write_obs(const T o[FW_NOBS], int env, float* obs, double* obs64) {
@@ -716,6 +739,7 @@ __device__ void reset_env(const DCfg<T>& c, const Soa<T>& S, int env, const doub
     for (int j = 0; j < 3; ++j)
         o[11 + j] = c.scale_actions ? (c.scale_high - c.scale_low) * (av[j] - c.act_lo[j]) / (c.act_hi[j] - c.act_lo[j]) + c.scale_low
                                     : av[j];
+    if (c.obs_noise_std > (T)0 || c.obs_noise_mean != (T)0) add_obs_noise<T>(c, gid, episode, 0, o);
     write_obs(o, env, obs, obs64);
 }
 

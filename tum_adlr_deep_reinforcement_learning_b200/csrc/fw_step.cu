@@ -571,6 +571,8 @@ __global__ void __launch_bounds__(128, 4) head_kernel(const __grid_constant__ DC
                                             : delta_feature<T>(cmd_in[j], cring, j, np_, false);
     }
 
+    if (c.obs_noise_std > (T)0 || c.obs_noise_mean != (T)0) add_obs_noise<T>(c, c.env_id_offset + env, episode, steps, obs_v);
+
     // ---------------- streamed episode statistics (fixed_wing.py:1644-1736) ----------------
     T esum[3], eabs[3], emin[3], emax[3], e0v[3];
     int rise_lo[3], rise_hi[3];
@@ -823,7 +825,7 @@ template <typename T> static void convert_cfg(const FwConfig& f, DCfg<T>& d) {
         CP(tgt_low[k]); CP(tgt_high[k]); CP(tgt_delta[k]); CP(tgt_bound[k]); CP(rew_err_scaling[k]); CP(rew_err_max[k]);
     }
     CP(streak_fraction); CP(rew_delta_scaling); CP(rew_delta_max); CP(rew_bound_scaling); CP(rew_bound_max);
-    CP(step_fail_value); CP(rise_low); CP(rise_high);
+    CP(step_fail_value); CP(rise_low); CP(rise_high); CP(obs_noise_mean); CP(obs_noise_std);
 #undef CP
     d.seed = f.seed;
     d.env_id_offset = f.env_id_offset;
