@@ -187,3 +187,19 @@ def test_ppo_plumbing_runs_and_improves_value_fit(cuda_device):
     assert all(np.isfinite(r["value_loss"]) and np.isfinite(r["policy_loss"]) for r in algo.logs)
     assert algo.buffer.advantages.shape == (16, 1024) and torch.isfinite(algo.buffer.advantages).all()
     venv.close()
+
+
+def test_sac_multi_env_gpu_replay_plumbing(cuda_device):
+    """Config C5 in miniature: 256 envs, turbulence on, replay ring on the GPU, a few hundred updates."""
+    import torch
+    from tum_adlr_deep_reinforcement_learning_b200.sac import SAC
+    from tum_adlr_deep_reinforcement_learning_b200.vec_env import FixedWingVecEnv
+    venv = FixedWingVecEnv(256, sim_config_kw={"turbulence": True}, seed=2)
+    algo = SAC(venv, buffer_size=20_000, batch_size=512, gradient_steps=2, learning_starts=2048)
+    algo.learn(total_timesteps=256 * 120, log_every=20)
+    assert algo.buffer.full and algo.buffer.size() == 20_000
+    assert algo.num_timesteps == 256 * 120 and len(algo.logs) == 6
+    last = algo.logs[-1]
+    assert all(np.isfinite(last[k]) for k in ("critic_loss", "actor_loss", "ent_coef")) and last["ent_coef"] > 0
+    assert torch.isfinite(algo.buffer.observations).all() and algo.buffer.dones.sum() >= 0
+    venv.close()

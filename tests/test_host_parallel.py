@@ -107,3 +107,26 @@ def test_env_sharding_is_independent_of_rank_count():
         parts.append(O.OracleBatch(c, 8).reset().copy())
     assert np.array_equal(whole, np.concatenate(parts))
     assert len({tuple(r) for r in whole}) == 16          # every env has its own stream
+
+
+def test_replay_buffer_ring_semantics():
+    """Multi-env ring insert (the widening of common/buffers.py:146-256 to N envs per step): wrap-around, size,
+    uniform sampling only from filled slots."""
+    from tum_adlr_deep_reinforcement_learning_b200.sac import ReplayBuffer
+    buf = ReplayBuffer(10, obs_dim=2, action_dim=1, device="cpu")
+    for k in range(4):                                   # 4 inserts of 3 transitions into capacity 10
+        base = 3 * k
+        obs = torch.arange(base, base + 3, dtype=torch.float32).reshape(3, 1).repeat(1, 2)
+        buf.add(obs, obs + 100, torch.zeros(3, 1), obs[:, 0], torch.tensor([0, 0, 1]))
+        assert buf.size() == min(10, base + 3)
+    assert buf.full and buf.pos == 2
+    # slots 0,1 were overwritten by transitions 10, 11; the rest still hold 2..9
+    assert buf.observations[:, 0].tolist() == [10, 11, 2, 3, 4, 5, 6, 7, 8, 9]
+    assert buf.next_observations[0, 0].item() == 110 and buf.dones[1].item() == 1.0
+    g = torch.Generator().manual_seed(0)
+    o, a, no, d, r = buf.sample(256, generator=g)
+    assert o.shape == (256, 2) and set(o[:, 0].tolist()) <= set(range(2, 12))
+    assert torch.equal(no, o + 100) and torch.equal(r, o[:, 0])
+    small = ReplayBuffer(100, obs_dim=2, action_dim=1, device="cpu")
+    small.add(torch.ones(3, 2), torch.ones(3, 2), torch.zeros(3, 1), torch.ones(3), torch.zeros(3))
+    assert small.size() == 3 and small.sample(64)[0].eq(1).all()
