@@ -358,7 +358,8 @@ __device__ __constant__ const double RK_E[7] = {-71.0 / 57600, 0, 71.0 / 16695, 
 
 template <typename T> __device__ __noinline__ T pow_ni(T x, T y) { return M<T>::pow(x, y); }
 
-#define FW_NK 18   // stage-derivative components kept: d/dt of y[18] (throttle rate state) is identically 0
+#define FW_NK 18   // ODE components that evolve: d/dt of y[18] (throttle rate state) is identically 0
+#define FW_NS 15   // of those, components whose stage derivatives are stored (all but position y[7..9])
 
 // scipy.integrate.solve_ivp(fun, (0, dt), y0) with RK45 defaults (pyfly.py:1393-1395) is split over two kernels:
 //

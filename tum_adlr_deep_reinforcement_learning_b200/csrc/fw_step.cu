@@ -177,17 +177,22 @@ __global__ void __launch_bounds__(128, 3) rk45_init_kernel(const __grid_constant
 
 // ---- kernel A1: the attempt loop, persistent lanes pulling envs from a queue ----
 template <typename T, bool TURB, int NT>
-__global__ void __launch_bounds__(NT) rk45_attempt_kernel(const __grid_constant__ DCfg<T> c, const Soa<T> S,
+__global__ void __maxnreg__(224) rk45_attempt_kernel(const __grid_constant__ DCfg<T> c, const Soa<T> S,
                                                           const Scratch<T> W) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* K = reinterpret_cast<T*>(smem_raw) + threadIdx.x;
-#define KS(s, i) K[((s) * FW_NK + (i)) * NT]
+    // Stage storage holds FW_NS = 15 components: position (y[7..9]) never feeds back into the RHS, so its stage
+    // inputs are never needed and its two quadratures (sum B_j K_j for y_new, sum E_j K_j for the error estimate) are
+    // carried in registers, accumulated in the same j order as the stored components.
+#define KS(s, cc) K[((s) * FW_NS + (cc)) * NT]
+#define KC(cc) ((cc) < 7 ? (cc) : (cc) + 3)       /* stored slot -> ODE component */
     const int n = S.n;
     const T rtol = c.rtol, atol = c.atol, t_bound = c.dt;
     const unsigned lane = threadIdx.x & 31;
     int env = blockIdx.x * NT + threadIdx.x;
     bool need = true, exhausted = false, first_fetch = true;
     T y[FW_NY], ys[FW_NY], dyv[FW_NY];
+    T kpos0[3] = {0, 0, 0}, posB[3] = {0, 0, 0}, posE[3] = {0, 0, 0};
     DynCtx<T> x;
     T t = 0, t_new = 0, h = 0, h_abs = 0, min_step = 0;
     bool rejected = false;
@@ -219,9 +224,10 @@ __global__ void __launch_bounds__(NT) rk45_attempt_kernel(const __grid_constant_
 #pragma unroll
                     for (int i = 0; i < FW_NY; ++i) y[i] = S.r[(RF_Y + i) * n + env];
 #pragma unroll
-                    for (int i = 0; i < FW_NK; ++i) KS(0, i) = W.f0[i * n + env];
+                    for (int cc = 0; cc < FW_NS; ++cc) KS(0, cc) = W.f0[KC(cc) * n + env];
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
+                        kpos0[k] = W.f0[(7 + k) * n + env];
                         x.cmd[k] = W.cmd[k * n + env]; x.wind[k] = S.r[(RF_WIND + k) * n + env];
                         x.tl[k] = W.turb[k * n + env]; x.ta[k] = W.turb[(3 + k) * n + env];
                     }
@@ -250,20 +256,24 @@ __global__ void __launch_bounds__(NT) rk45_attempt_kernel(const __grid_constant_
             }
         }
         const bool run = active && !finished;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { posB[k] = kpos0[k] * (T)RK_ROW[6][0]; posE[k] = kpos0[k] * (T)RK_E[0]; }
 #pragma unroll 1
         for (int row = 1; row <= 6; ++row) {
             {
-                T acc[FW_NK];
+                T acc[FW_NS];
 #pragma unroll
-                for (int i = 0; i < FW_NK; ++i) acc[i] = 0;
+                for (int cc = 0; cc < FW_NS; ++cc) acc[cc] = 0;
 #pragma unroll 1
                 for (int j = 0; j < row; ++j) {
                     const T a = (T)RK_ROW[row][j];
 #pragma unroll
-                    for (int i = 0; i < FW_NK; ++i) acc[i] += KS(j, i) * a;
+                    for (int cc = 0; cc < FW_NS; ++cc) acc[cc] += KS(j, cc) * a;
                 }
 #pragma unroll
-                for (int i = 0; i < FW_NK; ++i) ys[i] = y[i] + acc[i] * h;
+                for (int cc = 0; cc < FW_NS; ++cc) ys[KC(cc)] = y[KC(cc)] + acc[cc] * h;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) ys[7 + k] = y[7 + k] + posB[k] * h;     // == y_new at row 6; unused before
                 ys[18] = y[18];
             }
             const int r2 = rhs<T, TURB>(c, x, ys, false, (T)0, (T)0, dyv);
@@ -272,7 +282,10 @@ __global__ void __launch_bounds__(NT) rk45_attempt_kernel(const __grid_constant_
                 if (r2) rc = r2;
                 else if (row < 6) {
 #pragma unroll
-                    for (int i = 0; i < FW_NK; ++i) KS(row, i) = dyv[i];
+                    for (int cc = 0; cc < FW_NS; ++cc) KS(row, cc) = dyv[KC(cc)];
+                    const T bj = (T)RK_ROW[6][row], ej = (T)RK_E[row];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) { posB[k] += dyv[7 + k] * bj; posE[k] += dyv[7 + k] * ej; }
                 }
             }
         }
@@ -284,8 +297,12 @@ __global__ void __launch_bounds__(NT) rk45_attempt_kernel(const __grid_constant_
 #pragma unroll
                 for (int i = 0; i < FW_NK; ++i) {
                     T acc = 0;
+                    if (i >= 7 && i <= 9) acc = posE[i - 7];
+                    else {
+                        const int cc = i < 7 ? i : i - 3;
 #pragma unroll
-                    for (int j = 0; j < 6; ++j) acc += KS(j, i) * (T)RK_E[j];
+                        for (int j = 0; j < 6; ++j) acc += KS(j, cc) * (T)RK_E[j];
+                    }
                     acc += dyv[i] * (T)RK_E[6];
                     const T scl = atol + M<T>::fmax(M<T>::fabs(y[i]), M<T>::fabs(ys[i])) * rtol;
                     const T ei = acc * h * M<T>::rcp_hot(scl);      // scl >= atol: normal range
@@ -300,7 +317,11 @@ __global__ void __launch_bounds__(NT) rk45_attempt_kernel(const __grid_constant_
                     h_abs *= factor;
                     t = t_new;
 #pragma unroll
-                    for (int i = 0; i < FW_NK; ++i) { y[i] = ys[i]; KS(0, i) = dyv[i]; }   // FSAL
+                    for (int i = 0; i < FW_NK; ++i) y[i] = ys[i];
+#pragma unroll
+                    for (int cc = 0; cc < FW_NS; ++cc) KS(0, cc) = dyv[KC(cc)];              // FSAL
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) kpos0[k] = dyv[7 + k];
                     if (!(t < t_bound)) finished = true;            // solver.status == 'finished'
                     else {
                         rejected = false;
@@ -322,6 +343,7 @@ __global__ void __launch_bounds__(NT) rk45_attempt_kernel(const __grid_constant_
             need = true;
         }
     }
+#undef KC
 #undef KS
 }
 
@@ -851,8 +873,8 @@ struct FwHandle {
     unsigned long long random_step;
 };
 
-static const int NT_RK45_F64 = 64;     // 6*18*64*8 = 55296 B of stage storage per block: 4 blocks (8 warps) / SM
-static const int NT_RK45_F32 = 128;    // 6*18*128*4 = 55296 B
+static const int NT_RK45_F64 = 32;     // 6*15*32*8 = 23040 B of stage storage per one-warp block: 9 blocks / SM
+static const int NT_RK45_F32 = 64;     // 6*15*64*4 = 23040 B
 static const int W_REAL_FIELDS = FW_NK + 1 + 3 + 6 + FW_NY;   // f0, hinit, cmd, turb, ytmp
 
 template <typename T> static Scratch<T> make_scratch(void* real, int32_t* ints, size_t n) {
@@ -871,7 +893,7 @@ template <typename T> static Scratch<T> make_scratch(void* real, int32_t* ints, 
 // One env step = init kernel -> persistent attempt kernel -> head kernel (RK45), or rk4 kernel -> head kernel.
 template <typename T, bool TURB, int NT>
 static int launch_rk45(FwHandle* h, const DCfg<T>& c, const Soa<T>& S, const Scratch<T>& W, const StepIO& io, cudaStream_t st) {
-    const size_t smem = (size_t)6 * FW_NK * NT * sizeof(T);
+    const size_t smem = (size_t)6 * FW_NS * NT * sizeof(T);
     auto k = rk45_attempt_kernel<T, TURB, NT>;
     static int blocks_per_sm = 0;
     if (!blocks_per_sm) {
