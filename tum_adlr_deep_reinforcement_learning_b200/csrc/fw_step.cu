@@ -413,9 +413,9 @@ __global__ void __launch_bounds__(128, 4) head_kernel(const __grid_constant__ DC
 #pragma unroll
         for (int i = 0; i < 4; ++i) y[i] = y[i] / nrm;
         const T e0 = y[0], e1 = y[1], e2 = y[2], e3 = y[3];
-        roll = atan2_ni<T>((T)2 * (e0 * e1 + e2 * e3), e0 * e0 + e3 * e3 - e1 * e1 - e2 * e2);
-        pitch = asin_ni<T>((T)2 * (e0 * e2 - e1 * e3));
-        const T yaw = atan2_ni<T>((T)2 * (e0 * e3 + e1 * e2), e0 * e0 + e1 * e1 - e2 * e2 - e3 * e3);
+        roll = M<T>::atan2_hot((T)2 * (e0 * e1 + e2 * e3), e0 * e0 + e3 * e3 - e1 * e1 - e2 * e2);
+        pitch = M<T>::asin_hot((T)2 * (e0 * e2 - e1 * e3));
+        // yaw (pyfly.py:704-706) only feeds the Euler-angle rotation below and is not observed: it is not materialised
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             if (!fail) {
@@ -429,11 +429,16 @@ __global__ void __launch_bounds__(128, 4) head_kernel(const __grid_constant__ DC
             y[15] = clip(y[15], c.throttle_min, c.throttle_max);
             y[16] = clip(y[16], -c.elevon_dot_max, c.elevon_dot_max);
             y[17] = clip(y[17], -c.elevon_dot_max, c.elevon_dot_max);
+            // pyfly.py:1398-1406 rotates the steady wind with the matrix built from (roll, pitch, yaw); for the
+            // normalised quaternion those Euler angles came from, that matrix equals the quaternion form of
+            // _rot_b_v (pyfly.py:1782-1800) up to rounding, so no angle -> sin/cos round trip is needed.
             T wb[3];
-            rot_euler_apply(roll, pitch, yaw, x.wind, wb);
+            wb[0] = ((T)-1 + (T)2 * (e0 * e0 + e1 * e1)) * x.wind[0] + (T)2 * (e1 * e2 + e3 * e0) * x.wind[1] + (T)2 * (e1 * e3 - e2 * e0) * x.wind[2];
+            wb[1] = (T)2 * (e1 * e2 - e3 * e0) * x.wind[0] + ((T)-1 + (T)2 * (e0 * e0 + e2 * e2)) * x.wind[1] + (T)2 * (e2 * e3 + e1 * e0) * x.wind[2];
+            wb[2] = (T)2 * (e1 * e3 + e2 * e0) * x.wind[0] + (T)2 * (e2 * e3 - e1 * e0) * x.wind[1] + ((T)-1 + (T)2 * (e0 * e0 + e3 * e3)) * x.wind[2];
             const T a0 = y[10] - (wb[0] + x.tl[0]), a1 = y[11] - (wb[1] + x.tl[1]), a2 = y[12] - (wb[2] + x.tl[2]);
             T Van = M<T>::sqrt(a0 * a0 + a1 * a1 + a2 * a2);
-            const T al = atan2_ni<T>(a2, a0), be = asin_ni<T>(a1 / Van);
+            const T al = M<T>::atan2_hot(a2, a0), be = M<T>::asin_hot(a1 / Van);
             if (c.va_con_max > (T)0 && Van > c.va_con_max) fail = FW_TERM_VA;
             else {
                 if (Van < c.va_value_min) Van = c.va_value_min;
