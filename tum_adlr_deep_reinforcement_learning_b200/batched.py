@@ -99,14 +99,28 @@ class BatchedFixedWing:
         return self.obs, self.rew, self.done
 
     def episode_info(self):
-        dev = self.device
-        term = torch.zeros(self.n, dtype=torch.int32, device=dev)
-        metrics = torch.zeros(self.n, FW_NMETRIC, dtype=torch.float64, device=dev)
-        ret = torch.zeros(self.n, dtype=torch.float64, device=dev)
-        length = torch.zeros(self.n, dtype=torch.int32, device=dev)
+        """(term_code [n] i32, metrics [n,28] f64, episode return [n] f64, episode length [n] i32) device tensors,
+        valid for the envs whose done flag was set by the last step.  The tensors are reused by the next call."""
+        if getattr(self, "_ep_bufs", None) is None:
+            dev = self.device
+            self._ep_bufs = (torch.zeros(self.n, dtype=torch.int32, device=dev),
+                             torch.zeros(self.n, FW_NMETRIC, dtype=torch.float64, device=dev),
+                             torch.zeros(self.n, dtype=torch.float64, device=dev),
+                             torch.zeros(self.n, dtype=torch.int32, device=dev))
+        term, metrics, ret, length = self._ep_bufs
         _lib.check(_lib.lib().fw_get_episode_info(self._h, _ptr(term), _ptr(metrics), _ptr(ret), _ptr(length),
                                                   self._stream()), "fw_get_episode_info")
         return term, metrics, ret, length
+
+    def episode_info_rows(self, idx):
+        """Rows `idx` (LongTensor on the device) of (metrics | return | length | term_code | terminal observation) as
+        ONE packed host array [k, 28 + 3 + 14] — a single small D2H copy instead of four full-size ones."""
+        term, metrics, ret, length = self.episode_info()
+        packed = torch.cat([metrics.index_select(0, idx), ret.index_select(0, idx)[:, None],
+                            length.index_select(0, idx)[:, None].to(torch.float64),
+                            term.index_select(0, idx)[:, None].to(torch.float64),
+                            self.term_obs.index_select(0, idx).to(torch.float64)], dim=1)
+        return packed.cpu().numpy()
 
     def get_field(self, field):
         width, dtype = _FIELD_SHAPE[field]
