@@ -278,7 +278,12 @@ def main():
                 "peak_source": "DFMA micro-benchmark fw_measure_fma_peak on this GPU, same process (MEASURED_PEAKS.json "
                                "has no vector-pipe figure)",
                 "flops_per_env_step": flops_env_step, "mean_rhs_evals": float(nf[0]), "mean_rk_attempts": float(nf[1]),
-                "traffic": None,
+                "traffic": 2.365e8,
+                "traffic_note": "dram__bytes_read+write per step summed over the three kernels, ncu --set full capture "
+                                "profiles/r01_v5_kernels_raw_summary.txt (attempt kernel alone: 26.5 MB)",
+                "executed_fp64_flop_per_env_step_ncu": 24830,
+                "executed_note": "2*DFMA + DMUL + DADD thread instructions of the same capture / 65536 envs (n_rhs 24.05): "
+                                 "the instrumented count behind the hand-counted flops_per_env_step",
                 "hbm": {"achieved": hbm_gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                         "frac": hbm_gbs / peaks.get("hbm_gbs"), "peak_source": peak_kind + " (MEASURED_PEAKS.json)",
                         "bytes_per_env_step": BYTES_PER_ENV_STEP_F64},

@@ -203,3 +203,31 @@ def test_sac_multi_env_gpu_replay_plumbing(cuda_device):
     assert all(np.isfinite(last[k]) for k in ("critic_loss", "actor_loss", "ent_coef")) and last["ent_coef"] > 0
     assert torch.isfinite(algo.buffer.observations).all() and algo.buffer.dones.sum() >= 0
     venv.close()
+
+
+def test_single_env_gym_api_matches_oracle(cuda_device):
+    """FixedWingAircraft (gym API of fixed_wing.py:13-628 on a one-env batch): float64 observations, reset with
+    injected state / target, step -> (obs, reward, done, info) against the oracle."""
+    from oracle import fw_oracle as O
+    from tum_adlr_deep_reinforcement_learning_b200.config import build_config
+    from tum_adlr_deep_reinforcement_learning_b200.vec_env import FixedWingAircraft, state_dict_to_row
+    kw = dict(config_kw={"steps_max": 30}, sim_config_kw={"turbulence": False})
+    env = FixedWingAircraft(**kw)
+    state = {"roll": 0.2, "pitch": -0.05, "yaw": 0.1, "omega_p": 0.1, "omega_q": 0.0, "omega_r": -0.1,
+             "position_n": 0.0, "position_e": 0.0, "position_d": -50.0, "velocity_u": 19.0, "velocity_v": 0.5,
+             "velocity_w": 1.0, "wind": [1.0, -2.0, 0.5]}
+    target = {"roll": 0.0, "pitch": 0.05, "Va": 21.0}
+    obs = env.reset(state=state, target=target)
+    assert obs.dtype == np.float64 and obs.shape == (14,)
+    ref = O.OracleEnv(build_config(**kw))
+    obs_ref = ref.reset(state_dict_to_row(state), [target["roll"], target["pitch"], target["Va"]])
+    assert np.abs(obs - obs_ref).max() < 1e-12
+    rs = np.random.RandomState(0)
+    for t in range(30):
+        a = rs.uniform(-1, 1, 3)
+        obs, rew, done, info = env.step(a)
+        o2, r2, d2, term = ref.step(a)
+        assert np.abs(obs - o2).max() < 1e-9 and abs(rew - r2) < 1e-9 and done == d2
+        assert set(env.target) == {"roll", "pitch", "Va"}
+    assert done and info["termination"] == "steps" and "success" in info
+    env.close()
