@@ -1005,6 +1005,11 @@ void fwo_batch_step(FwoBatch* b, const float* actions, double* obs, double* rew,
     }
 }
 
+/* per-env RHS-evaluation / attempt counters of the last step, for step-size-decision parity statistics */
+void fwo_batch_counters(const FwoBatch* b, int32_t* nfev, int32_t* natt) {
+    for (int i = 0; i < b->n; ++i) { nfev[i] = b->envs[i]->last_nfev; natt[i] = b->envs[i]->last_natt; }
+}
+
 /* U(-1,1)^3 action for (env, global step) from the Philox action stream shared with fw_step_random */
 void fwo_random_action(uint64_t action_seed, int64_t env_id, uint64_t step, float a[3]) {
     uint32_t r[4];

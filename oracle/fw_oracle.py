@@ -59,6 +59,7 @@ def lib():
         L.fwo_batch_step.argtypes = [ctypes.c_void_p, _fp, _dp, _dp, _u8p]
         L.fwo_batch_step_random.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, _dp,
                                             _dp, _u8p]
+        L.fwo_batch_counters.argtypes = [ctypes.c_void_p, _i32p, _i32p]
         L.fwo_random_action.argtypes = [ctypes.c_uint64, ctypes.c_int64, ctypes.c_uint64, _fp]
         L.fwo_config_size.restype = ctypes.c_int
         _lib = L
@@ -189,6 +190,11 @@ class OracleBatch:
         a = np.ascontiguousarray(actions, dtype=np.float32)
         lib().fwo_batch_step(self._h, _p(a, _fp), _p(self.obs), _p(self.rew), _p(self.done, _u8p))
         return self.obs, self.rew, self.done
+
+    def counters(self):
+        nfev, natt = np.zeros(self.n, np.int32), np.zeros(self.n, np.int32)
+        lib().fwo_batch_counters(self._h, _p(nfev, _i32p), _p(natt, _i32p))
+        return nfev, natt
 
     def step_random(self, k, seed, step0):
         lib().fwo_batch_step_random(self._h, k, seed, step0, _p(self.obs), _p(self.rew), _p(self.done, _u8p))

@@ -101,13 +101,13 @@ DEV_CONFIG_KW = {"action": {"scale_space": False}, "observation": {"noise": {"me
 
 @pytest.mark.parametrize("config_kw,amp", [(None, 1.5), (DEV_CONFIG_KW, 0.4)], ids=["default", "dev_config_obs_noise"])
 def test_batch_against_oracle_random_policy(config_kw, amp, cuda_device):
-    """2048 envs x 40 steps, Philox resets, turbulence on, float32 actions: CUDA vs C oracle, state-for-state.
+    """4096 envs x 60 steps, Philox resets, turbulence on, float32 actions: CUDA vs C oracle, state-for-state.
     The second case is the reference's fixed_wing_config_dev.json: unscaled actions, observation noise (Philox)."""
     import torch
     from oracle import fw_oracle as O
     from tum_adlr_deep_reinforcement_learning_b200 import batched as bt
     from tum_adlr_deep_reinforcement_learning_b200.config import build_config
-    n, T = 2048, 40
+    n, T = 4096, 60
     cfg = build_config(config_kw=config_kw, sim_config_kw={"turbulence": True}, seed=1234)
     env = bt.BatchedFixedWing(n, cfg=cfg)
     env.enable_f64_outputs()
@@ -116,6 +116,7 @@ def test_batch_against_oracle_random_policy(config_kw, amp, cuda_device):
     obs_ref = ob.reset().copy()
     assert _rel(env.obs64.cpu().numpy(), obs_ref).max() < 1e-12
     rs = np.random.RandomState(0)
+    same = tot = 0
     for t in range(T):
         a = rs.uniform(-amp, amp, (n, 3)).astype(np.float32)
         env.step(torch.as_tensor(a).cuda(), auto_reset=True)
@@ -123,6 +124,14 @@ def test_batch_against_oracle_random_policy(config_kw, amp, cuda_device):
         assert np.array_equal(env.done.cpu().numpy(), d_ref)
         assert _rel(env.obs64.cpu().numpy(), o_ref).max() < RTOL_F64, t
         assert _rel(env.rew64.cpu().numpy(), r_ref).max() < RTOL_F64, t
+        # step-size decisions: RHS-evaluation counts of the step that just ran (envs that auto-reset keep the count of
+        # the step that ended the episode on both sides)
+        nf = env.get_field(bt.FIELD_NFEV).cpu().numpy()
+        nf_ref, na_ref = ob.counters()
+        same += int((nf[:, 0] == nf_ref).sum() + 0)
+        tot += n
+    print("\n[oracle batch] identical RHS-evaluation counts on %d/%d env-steps" % (same, tot))
+    assert same == tot
     env.close()
 
 
