@@ -324,7 +324,7 @@ def main():
             ms2, _ = time_device_steps(e2, pool, flush)
             ms2 = max_over_ranks(ms2)
             extra[tag] = {"value": world * n * K / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2 / K,
-                          "note": "fixed-step mode, graded at its own tolerance (tests/test_gpu_modes.py), not the "
+                          "note": "fixed-step mode, graded at its own tolerance (tests/test_gpu_env.py::test_fast_modes_at_their_stated_tolerance), not the "
                                   "parity path"}
             e2.close()
 

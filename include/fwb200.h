@@ -191,9 +191,10 @@ int fw_step(FwHandle* h, const void* actions_dev, int32_t actions_f64, float* ob
             uint8_t* done_dev, float* term_obs_dev, double* obs64_dev, double* rew64_dev, int32_t auto_reset,
             void* stream);
 
-/* K fused steps per launch with Philox U(-1,1)^3 actions generated in-kernel (random-action throughput workloads
- * C2/C3 of BASELINE.json; the policy-free analogue of collect_rollouts, on_policy_algorithm.py:123-191).
- * Accumulates per-env reward sums / done counts into the episode-statistics arrays. */
+/* k_steps env steps with Philox U(-1,1)^3 actions generated in-kernel (random-action throughput workloads C2/C3 of
+ * BASELINE.json; the policy-free analogue of collect_rollouts, on_policy_algorithm.py:123-191): no action buffer is
+ * read, the launches of consecutive steps are queued back to back on `stream`, auto-reset is on.  The outputs hold
+ * the result of the LAST step. */
 int fw_step_random(FwHandle* h, int32_t k_steps, uint64_t action_seed, float* obs_dev, float* rew_dev,
                    uint8_t* done_dev, void* stream);
 
@@ -206,7 +207,7 @@ int fw_get_episode_info(FwHandle* h, int32_t* term_code_dev, double* metrics_dev
  * field ids: see FwField. */
 enum FwField {
     FW_FIELD_Y = 0,          /* [n,19] f64 ODE state                                          */
-    FW_FIELD_EULER = 1,      /* [n,3]  roll pitch yaw (state .value)                          */
+    FW_FIELD_EULER = 1,      /* [n,3]  roll pitch (state .value); yaw is not materialised: NaN */
     FW_FIELD_VAB = 2,        /* [n,3]  Va alpha beta                                          */
     FW_FIELD_WIND = 3,       /* [n,3]  steady wind NED                                        */
     FW_FIELD_TARGET = 4,     /* [n,3]  roll pitch Va targets                                  */

@@ -76,8 +76,8 @@ class BatchedFixedWing:
             noise = torch.as_tensor(noise, dtype=torch.float64, device=dev).contiguous()
             assert noise.shape[:2] == (self.n, 4)
             nlen = noise.shape[2]
-        self._noise = noise
-        self._keep = (mask, state, target)
+        self._noise = noise                      # the kernels keep reading it until the next reset: keep it alive
+        self._reset_args = (mask, state, target)   # the reset kernel is asynchronous: keep its inputs alive too
         _lib.check(_lib.lib().fw_reset(self._h, _ptr(mask), _ptr(state), _ptr(target), _ptr(noise), nlen,
                                        _ptr(self.obs), _ptr(self.obs64), self._stream()), "fw_reset")
         return self.obs
