@@ -26,10 +26,13 @@
 extern "C" {
 #endif
 
-#define FW_ABI_VERSION 2
+#define FW_ABI_VERSION 3
 
 #define FW_NY 19        /* ODE state: quat[4] omega[3] pos[3] vel[3] act_value[3] act_rate[3]  (pyfly.py:1372-1389) */
 #define FW_NOBS 14      /* default observation vector (fixed_wing_config.json "observation.states")               */
+#define FW_OBS_ENTRIES_MAX 16  /* entries per observation row                                                     */
+#define FW_OBS_LEN_MAX 5       /* observation.length (rows of history)                                            */
+#define FW_NOBS_MAX (FW_OBS_ENTRIES_MAX * FW_OBS_LEN_MAX)
 #define FW_NACT 3       /* elevator, aileron, throttle (fixed_wing_config.json "action.states")                   */
 #define FW_NSTATE_INJECT 21 /* roll pitch yaw p q r pn pe pd u v w | er el thr | er_dot el_dot thr_dot | wind n e d */
 #define FW_NMETRIC 28   /* see FwMetricIndex                                                                      */
@@ -61,6 +64,10 @@ enum FwIntegrator {
 };
 
 enum FwPrecision { FW_F64 = 0, FW_F32 = 1 };
+
+/* observation entry kinds (fixed_wing.py:1149-1234) and the state indices an entry of kind STATE may name */
+enum FwObsKind { FW_OBS_STATE = 0, FW_OBS_TARGET_ABS = 1, FW_OBS_TARGET_REL = 2, FW_OBS_ACTION = 3 };
+enum FwObsState { FW_S_ROLL = 0, FW_S_PITCH, FW_S_VA, FW_S_OMEGA_P, FW_S_OMEGA_Q, FW_S_OMEGA_R, FW_S_ALPHA, FW_S_BETA };
 
 enum FwTargetClass { FW_TGT_CONSTANT = 0, FW_TGT_COMPENSATE = 1 };   /* fixed_wing.py:1375-1431 */
 enum FwOnSuccess { FW_SUCCESS_NONE = 0, FW_SUCCESS_DONE = 1, FW_SUCCESS_NEW = 2 }; /* fixed_wing.py:548-553 */
@@ -152,6 +159,15 @@ typedef struct FwConfig {
                                              `scale=var` makes "var" a standard deviation (fixed_wing.py:1246-1247);
                                              std <= 0 and mean == 0 disables (the reference's default) */
 
+    /* ---- general observation layout (fixed_wing.py:1113-1262): obs_len rows (history, newest first) of obs_n entries.
+     * obs_generic == 0 selects the default 14-vector fast path and ignores the arrays below. ---- */
+    int32_t obs_generic, obs_len, obs_n, obs_normalize;
+    int32_t obs_kind[FW_OBS_ENTRIES_MAX], obs_idx[FW_OBS_ENTRIES_MAX], obs_window[FW_OBS_ENTRIES_MAX];
+    int32_t obs_norm_flag[FW_OBS_ENTRIES_MAX];
+    double obs_mean[FW_OBS_ENTRIES_MAX], obs_var[FW_OBS_ENTRIES_MAX];
+    double obs_init_noise;                /* rows older than the episode get += U(-1,1)*dt (fixed_wing.py:1142-1145);
+                                             a finite value here replaces the Philox draw (parity tests) */
+
     /* ---- counter-based RNG (Philox4x32-10) for auto-reset and turbulence noise ---- */
     uint64_t seed;
     int64_t env_id_offset;                /* global id of env 0 of this handle (sharding: rank*n_envs) */
@@ -163,6 +179,7 @@ typedef struct FwHandle FwHandle;
  * `device` is the CUDA ordinal.  All envs start un-reset (call fw_reset with mask=NULL). */
 int fw_create(const FwConfig* cfg, int32_t n_envs, int32_t device, FwHandle** out);
 int fw_destroy(FwHandle* h);
+int fw_obs_dim(const FwHandle* h);   /* floats per observation row of this handle */
 const char* fw_last_error(void);
 int fw_abi_version(void);
 
@@ -172,8 +189,9 @@ int fw_abi_version(void);
  *  target_dev      [n, 3] f64, nullable: injected targets (roll, pitch, Va).
  *  noise_dev       [n, 4, noise_len] f64, nullable: injected unit white noise (pyfly.py:1294, dryden.py:184-188);
  *                  when NULL turbulence noise is generated from Philox. The buffer must stay alive while in use.
- *  obs_dev         [n, FW_NOBS] f32, nullable: reset observation for the masked envs (others untouched).
- *  obs64_dev       [n, FW_NOBS] f64, nullable.
+ *  obs_dev         [n, obs_dim] f32, nullable: reset observation for the masked envs (others untouched);
+ *                  obs_dim = FW_NOBS for the default layout, obs_len * obs_n for a general one (fw_obs_dim).
+ *  obs64_dev       [n, obs_dim] f64, nullable.
  */
 int fw_reset(FwHandle* h, const uint8_t* mask_dev, const double* state_dev, const double* target_dev,
              const double* noise_dev, int32_t noise_len, float* obs_dev, double* obs64_dev, void* stream);

@@ -64,6 +64,8 @@ typedef struct FwoEnv {
     double* cmd_hist;  int n_cmd;                    /* elevator/aileron/throttle .history["command"], [t][3] */
     double* err_hist;  int n_err;                    /* history["error"], [t][3] */
     uint8_t* goal_hist; int n_goal;                  /* history["goal"], [t][4] roll pitch Va all */
+    double* st_hist;   int n_st;                     /* state .history of roll pitch Va p q r alpha beta, [t][8] */
+    double* tgt_hist;  int n_tgt;                    /* history["target"], [t][3] */
     double ep_return;
     double metrics[FW_NMETRIC];
     int term_code;
@@ -88,7 +90,8 @@ void fwo_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4
 
 /* Stream layout shared with the CUDA path (DESIGN.md "RNG"): counter = (env_id lo32, episode lo32, purpose|env hi,
  * block); two 53-bit uniforms per block. */
-enum { FWO_RNG_RESET = 0, FWO_RNG_NOISE = 1, FWO_RNG_RESAMPLE = 2, FWO_RNG_ACTION = 3, FWO_RNG_OBS = 4 };
+enum { FWO_RNG_RESET = 0, FWO_RNG_NOISE = 1, FWO_RNG_RESAMPLE = 2, FWO_RNG_ACTION = 3, FWO_RNG_OBS = 4,
+       FWO_RNG_OBS_INIT = 5 };
 
 static void rng_block(uint64_t seed, int64_t env_id, uint64_t episode, uint32_t purpose, uint32_t block,
                       uint32_t out[4]) {
@@ -615,27 +618,107 @@ static double delta_feature_f32(const double* hist, int n, int col, int window, 
 
 /* observation.noise (fixed_wing.py:1246-1247): every entry += N(mean, var).  MT19937 cannot be reproduced: the draws
  * come from the Philox stream (purpose OBS, block = 4 * steps_count + b), 14 Box-Muller normals per observation. */
-static void add_obs_noise(const FwoEnv* e, double obs[FW_NOBS]) {
+static void add_obs_noise(const FwoEnv* e, double* obs, int dim) {
     const FwConfig* c = &e->cfg;
     if (!(c->obs_noise_std > 0) && c->obs_noise_mean == 0) return;
-    for (int b = 0; b < 4; ++b) {
+    for (int b = 0; b * 4 < dim; ++b) {
         uint32_t r[4];
-        rng_block(c->seed, e->env_id, e->episode, FWO_RNG_OBS, (uint32_t)(e->steps_count * 4 + b), r);
+        rng_block(c->seed, e->env_id, e->episode, FWO_RNG_OBS, (uint32_t)(e->steps_count * 32 + b), r);
         for (int i = 0; i < 2; ++i) {
             double u1 = ((double)r[2 * i] + 0.5) * (1.0 / 4294967296.0);
             double u2 = ((double)r[2 * i + 1] + 0.5) * (1.0 / 4294967296.0);
             double rad = sqrt(-2.0 * log(u1));
             double z0 = rad * cos(6.283185307179586476925 * u2), z1 = rad * sin(6.283185307179586476925 * u2);
             int j = b * 4 + i * 2;
-            if (j < FW_NOBS) obs[j] += c->obs_noise_mean + c->obs_noise_std * z0;
-            if (j + 1 < FW_NOBS) obs[j + 1] += c->obs_noise_mean + c->obs_noise_std * z1;
+            if (j < dim) obs[j] += c->obs_noise_mean + c->obs_noise_std * z0;
+            if (j + 1 < dim) obs[j + 1] += c->obs_noise_mean + c->obs_noise_std * z1;
         }
     }
 }
 
-/* get_observation (fixed_wing.py:1113-1262) for observation.length == 1, no normalisation */
-static void get_observation(const FwoEnv* e, double obs[FW_NOBS]) {
+static void push_state_history(FwoEnv* e) {
+    double* p = e->st_hist + (size_t)e->n_st * 8;
+    p[0] = e->roll; p[1] = e->pitch; p[2] = e->Va; p[3] = e->omega[0]; p[4] = e->omega[1]; p[5] = e->omega[2];
+    p[6] = e->alpha; p[7] = e->beta;
+    e->n_st++;
+}
+
+/* sum |diff| over hist[lo..hi) of one column, accumulated in float32 (np.sum(..., dtype=np.float32)) */
+static double window_feature_f32(const double* hist, int lo, int hi, int col, int is_f32) {
+    float s = 0;
+    for (int t = lo + 1; t < hi; ++t) {
+        float d;
+        if (is_f32) d = fabsf((float)hist[t * 3 + col] - (float)hist[(t - 1) * 3 + col]);
+        else d = (float)fabs(hist[t * 3 + col] - hist[(t - 1) * 3 + col]);
+        s += d;
+    }
+    return (double)s;
+}
+
+/* get_observation (fixed_wing.py:1113-1262), general layout: obs_len rows (newest first) of obs_n entries, entry kinds
+ * state / target absolute / target relative / action, history rows clamped to the episode start with the
+ * `init_noise` offset, optional (val - mean) / var normalisation. */
+static void get_observation_generic(const FwoEnv* e, double* obs) {
     const FwConfig* c = &e->cfg;
+    const int L = c->obs_len, n = c->obs_n;
+    const double cur_state[8] = {e->h_roll, e->h_pitch, e->h_Va, e->h_omega[0], e->h_omega[1], e->h_omega[2],
+                                 e->h_alpha, e->h_beta};
+    const double actval[3] = {e->elev, e->ail, e->act_val[2]};
+    for (int i = 1; i <= L; ++i) {
+        int ie = i;
+        double init_noise = 0;
+        if (i > e->steps_count) {
+            ie = e->steps_count + 1;
+            if (L > 1) {
+                double u;
+                if (!isnan(c->obs_init_noise)) u = c->obs_init_noise;
+                else {
+                    uint32_t r[4];
+                    rng_block(c->seed, e->env_id, e->episode, FWO_RNG_OBS_INIT, (uint32_t)(e->steps_count * 8 + (i - 1)), r);
+                    u = 2.0 * u53(r[0], r[1]) - 1.0;
+                }
+                init_noise = u * c->dt;
+            }
+        }
+        for (int k = 0; k < n; ++k) {
+            double val;
+            const int idx = c->obs_idx[k];
+            switch (c->obs_kind[k]) {
+                case FW_OBS_STATE:
+                    val = (ie == 1) ? cur_state[idx] : e->st_hist[(size_t)(e->n_st - ie) * 8 + idx];
+                    break;
+                case FW_OBS_TARGET_ABS:
+                    val = (ie == 1) ? e->target[idx] : e->tgt_hist[(size_t)(e->n_tgt - ie) * 3 + idx];
+                    break;
+                case FW_OBS_TARGET_REL:
+                    val = (ie == 1) ? get_error(e, idx) : e->err_hist[(size_t)(e->n_err - ie) * 3 + idx];
+                    break;
+                default: {
+                    if (e->steps_count - ie < 0) {
+                        val = actval[idx];
+                        if (c->scale_actions)
+                            val = (c->scale_high - c->scale_low) * (val - c->act_lo[idx]) / (c->act_hi[idx] - c->act_lo[idx]) + c->scale_low;
+                    } else {
+                        const double* hist = c->scale_actions ? e->act_hist : e->cmd_hist;
+                        const int N = c->scale_actions ? e->n_act : e->n_cmd;
+                        int hi = N - (ie - 1), lo = N - c->obs_window[k] - ie + 1;
+                        if (lo < 0) lo = 0;
+                        val = window_feature_f32(hist, lo, hi, idx, c->scale_actions ? e->act_is_f32 : 0);
+                    }
+                }
+            }
+            val += init_noise;
+            if (c->obs_normalize && c->obs_norm_flag[k]) { val -= c->obs_mean[k]; val /= c->obs_var[k]; }
+            obs[(i - 1) * n + k] = val;
+        }
+    }
+    add_obs_noise(e, obs, L * n);
+}
+
+/* get_observation (fixed_wing.py:1113-1262) for observation.length == 1, no normalisation */
+static void get_observation(const FwoEnv* e, double* obs) {
+    const FwConfig* c = &e->cfg;
+    if (c->obs_generic) { get_observation_generic(e, obs); return; }
     obs[0] = e->h_roll; obs[1] = e->h_pitch; obs[2] = e->h_Va;
     obs[3] = e->h_omega[0]; obs[4] = e->h_omega[1]; obs[5] = e->h_omega[2];
     obs[6] = e->target[0]; obs[7] = e->target[1]; obs[8] = e->target[2];
@@ -653,7 +736,7 @@ static void get_observation(const FwoEnv* e, double obs[FW_NOBS]) {
             obs[11 + j] = delta_feature_f32(e->cmd_hist, e->n_cmd, j, c->obs_act_window, 0);
         }
     }
-    add_obs_noise(e, obs);
+    add_obs_noise(e, obs, FW_NOBS);
 }
 
 /* get_reward (fixed_wing.py:941-1111) for the default factor family: three linear error factors, a linear
@@ -765,6 +848,8 @@ FwoEnv* fwo_create(const FwConfig* cfg, int64_t env_id) {
     e->cmd_hist = (double*)calloc((size_t)3 * L, sizeof(double));
     e->err_hist = (double*)calloc((size_t)3 * L, sizeof(double));
     e->goal_hist = (uint8_t*)calloc((size_t)4 * L, 1);
+    e->st_hist = (double*)calloc((size_t)8 * L, sizeof(double));
+    e->tgt_hist = (double*)calloc((size_t)3 * L, sizeof(double));
     e->env_id = env_id;
     e->episode = 0;
     return e;
@@ -772,7 +857,8 @@ FwoEnv* fwo_create(const FwConfig* cfg, int64_t env_id) {
 
 void fwo_destroy(FwoEnv* e) {
     if (!e) return;
-    free(e->turb); free(e->act_hist); free(e->cmd_hist); free(e->err_hist); free(e->goal_hist); free(e);
+    free(e->turb); free(e->act_hist); free(e->cmd_hist); free(e->err_hist); free(e->goal_hist);
+    free(e->st_hist); free(e->tgt_hist); free(e);
 }
 
 /* FixedWingAircraft.reset (fixed_wing.py:414-481) -> PyFly.reset (pyfly.py:1262-1311).
@@ -840,6 +926,8 @@ void fwo_reset(FwoEnv* e, const double* state, const double* target, const doubl
     e->h_roll = e->roll; e->h_pitch = e->pitch; e->h_Va = e->Va; e->h_alpha = e->alpha; e->h_beta = e->beta;
     for (int i = 0; i < 3; ++i) e->h_omega[i] = e->omega[i];
     e->n_act = 0; e->n_cmd = 0; e->n_err = 0; e->n_goal = 0; e->act_is_f32 = 0;
+    e->n_st = 0; e->n_tgt = 0;
+    push_state_history(e);          /* Variable.reset: history = [value] (pyfly.py:89-104) */
     e->ep_return = 0; e->term_code = 0;
     /* sample_target, then injected targets override (fixed_wing.py:443-450) */
     double u3[3];
@@ -847,8 +935,8 @@ void fwo_reset(FwoEnv* e, const double* state, const double* target, const doubl
     sample_target(e, u3);
     if (target) for (int k = 0; k < 3; ++k) if (!isnan(target[k])) e->target[k] = target[k];
     get_observation(e, obs);
-    for (int k = 0; k < 3; ++k) e->err_hist[k] = get_error(e, k);
-    e->n_err = 1;
+    for (int k = 0; k < 3; ++k) { e->err_hist[k] = get_error(e, k); e->tgt_hist[k] = e->target[k]; }
+    e->n_err = 1; e->n_tgt = 1;
     goal_status(e, e->goal_hist);
     e->n_goal = 1;
 }
@@ -869,6 +957,7 @@ void fwo_step(FwoEnv* e, const double action[3], int action_is_f32, double obs[F
         }
     }
     int fail = sim_step(e, a);
+    if (!fail) push_state_history(e);
     e->steps_count += 1;
     e->steps_for_target += 1;
     int d = 0, tc = FW_TERM_NONE;
@@ -899,8 +988,11 @@ void fwo_step(FwoEnv* e, const double action[3], int action_is_f32, double obs[F
             sample_target(e, u3);
         }
         next_target(e);
-        for (int k = 0; k < 3; ++k) e->err_hist[(size_t)e->n_err * 3 + k] = get_error(e, k);
-        e->n_err++;
+        for (int k = 0; k < 3; ++k) {
+            e->err_hist[(size_t)e->n_err * 3 + k] = get_error(e, k);
+            e->tgt_hist[(size_t)e->n_tgt * 3 + k] = e->target[k];
+        }
+        e->n_err++; e->n_tgt++;
         get_observation(e, obs);
     } else {
         d = 1;
@@ -975,11 +1067,13 @@ void fwo_gae(const float* rew, const float* val, const float* done, const float*
 
 /* ------------------------------------------------------------------------------------------------------------- */
 /* batch driver for the CPU baseline: n envs, auto-reset on done (VecEnv contract), OpenMP over envs */
-typedef struct FwoBatch { int n; FwoEnv** envs; } FwoBatch;
+int fwo_obs_dim(const FwConfig* c);
+typedef struct FwoBatch { int n; int od; FwoEnv** envs; } FwoBatch;
 
 FwoBatch* fwo_batch_create(const FwConfig* cfg, int n) {
     FwoBatch* b = (FwoBatch*)calloc(1, sizeof(FwoBatch));
     b->n = n;
+    b->od = fwo_obs_dim(cfg);
     b->envs = (FwoEnv**)calloc((size_t)n, sizeof(FwoEnv*));
     for (int i = 0; i < n; ++i) b->envs[i] = fwo_create(cfg, cfg->env_id_offset + i);
     return b;
@@ -991,7 +1085,7 @@ void fwo_batch_destroy(FwoBatch* b) {
 FwoEnv* fwo_batch_env(FwoBatch* b, int i) { return b->envs[i]; }
 
 void fwo_batch_reset(FwoBatch* b, double* obs) {
-    for (int i = 0; i < b->n; ++i) fwo_reset(b->envs[i], NULL, NULL, NULL, 0, obs + (size_t)i * FW_NOBS);
+    for (int i = 0; i < b->n; ++i) fwo_reset(b->envs[i], NULL, NULL, NULL, 0, obs + (size_t)i * b->od);
 }
 
 /* actions [n][3] f32 (SB3 policy dtype); k_steps > 1 repeats the same batch call with Philox actions */
@@ -999,9 +1093,9 @@ void fwo_batch_step(FwoBatch* b, const float* actions, double* obs, double* rew,
     for (int i = 0; i < b->n; ++i) {
         double a[3] = {actions[i * 3], actions[i * 3 + 1], actions[i * 3 + 2]};
         int d, tc;
-        fwo_step(b->envs[i], a, 1, obs + (size_t)i * FW_NOBS, rew + i, &d, &tc);
+        fwo_step(b->envs[i], a, 1, obs + (size_t)i * b->od, rew + i, &d, &tc);
         done[i] = (uint8_t)d;
-        if (d) fwo_reset(b->envs[i], NULL, NULL, NULL, 0, obs + (size_t)i * FW_NOBS);
+        if (d) fwo_reset(b->envs[i], NULL, NULL, NULL, 0, obs + (size_t)i * b->od);
     }
 }
 
@@ -1025,11 +1119,12 @@ void fwo_batch_step_random(FwoBatch* b, int k_steps, uint64_t action_seed, uint6
             fwo_random_action(action_seed, b->envs[i]->env_id, step0 + (uint64_t)k, af);
             double a[3] = {af[0], af[1], af[2]};
             int d, tc;
-            fwo_step(b->envs[i], a, 1, obs + (size_t)i * FW_NOBS, rew + i, &d, &tc);
+            fwo_step(b->envs[i], a, 1, obs + (size_t)i * b->od, rew + i, &d, &tc);
             done[i] = (uint8_t)d;
-            if (d) fwo_reset(b->envs[i], NULL, NULL, NULL, 0, obs + (size_t)i * FW_NOBS);
+            if (d) fwo_reset(b->envs[i], NULL, NULL, NULL, 0, obs + (size_t)i * b->od);
         }
     }
 }
 
 int fwo_config_size(void) { return (int)sizeof(FwConfig); }
+int fwo_obs_dim(const FwConfig* c) { return c->obs_generic ? c->obs_len * c->obs_n : FW_NOBS; }

@@ -62,6 +62,7 @@ def lib():
         L.fwo_batch_counters.argtypes = [ctypes.c_void_p, _i32p, _i32p]
         L.fwo_random_action.argtypes = [ctypes.c_uint64, ctypes.c_int64, ctypes.c_uint64, _fp]
         L.fwo_config_size.restype = ctypes.c_int
+        L.fwo_obs_dim.argtypes = [ctypes.POINTER(FwConfig)]
         _lib = L
     return _lib
 
@@ -75,6 +76,7 @@ class OracleEnv:
 
     def __init__(self, cfg, env_id=0):
         self.cfg = cfg
+        self.obs_dim = lib().fwo_obs_dim(ctypes.byref(cfg))
         self._h = lib().fwo_create(ctypes.byref(cfg), env_id)
 
     def __del__(self):
@@ -83,7 +85,7 @@ class OracleEnv:
             self._h = None
 
     def reset(self, state=None, target=None, noise=None):
-        obs = np.zeros(FW_NOBS)
+        obs = np.zeros(self.obs_dim)
         st = None if state is None else np.ascontiguousarray(state, dtype=np.float64)
         tg = None if target is None else np.ascontiguousarray(target, dtype=np.float64)
         nz = None if noise is None else np.ascontiguousarray(noise, dtype=np.float64)
@@ -92,7 +94,7 @@ class OracleEnv:
 
     def step(self, action, f32=False):
         a = np.ascontiguousarray(action, dtype=np.float64)
-        obs = np.zeros(FW_NOBS)
+        obs = np.zeros(self.obs_dim)
         rew = ctypes.c_double()
         done, term = ctypes.c_int(), ctypes.c_int()
         lib().fwo_step(self._h, _p(a), int(f32), _p(obs), ctypes.byref(rew), ctypes.byref(done), ctypes.byref(term))
@@ -173,7 +175,7 @@ class OracleBatch:
     def __init__(self, cfg, n):
         self.n = n
         self._h = lib().fwo_batch_create(ctypes.byref(cfg), n)
-        self.obs = np.zeros((n, FW_NOBS))
+        self.obs = np.zeros((n, lib().fwo_obs_dim(ctypes.byref(cfg))))
         self.rew = np.zeros(n)
         self.done = np.zeros(n, np.uint8)
 

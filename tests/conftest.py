@@ -51,3 +51,32 @@ def cuda_device():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     return 0
+
+
+def cnn_env_config():
+    """examples/models/cnn_controller/fixed_wing_config.json of the reference, as a delta on the default config:
+    observation length 5 / shape matrix, relative targets, no alpha/beta entries."""
+    from tum_adlr_deep_reinforcement_learning_b200.config import default_env_config
+    cfg = default_env_config()
+
+    def st(name, lo=None, hi=None, rad=False):
+        d = {"name": name, "type": "state"}
+        if lo is not None:
+            d["low"] = lo
+        if hi is not None:
+            d["high"] = hi
+        if rad:
+            d["convert_to_radians"] = True
+        return d
+
+    cfg["observation"] = {
+        "length": 5, "step": 1, "shape": "matrix",
+        "states": [st("roll", -180, 180, True), st("pitch", -85, 85, True), st("Va", None, 60),
+                   st("omega_p", -720, 720, True), st("omega_q", -720, 720, True), st("omega_r", -720, 720, True),
+                   {"name": "roll", "type": "target", "value": "relative"},
+                   {"name": "pitch", "type": "target", "value": "relative"},
+                   {"name": "Va", "type": "target", "value": "relative"},
+                   {"name": "elevator", "type": "action", "window_size": 5},
+                   {"name": "aileron", "type": "action", "window_size": 5},
+                   {"name": "throttle", "type": "action", "window_size": 5}]}
+    return cfg

@@ -31,8 +31,8 @@ STATE_KEYS = ["roll", "pitch", "yaw", "omega_p", "omega_q", "omega_r", "position
 TARGET_KEYS = ["roll", "pitch", "Va"]
 
 
-def make_env(turbulence, config_kw=None, intensity="light"):
-    env = FixedWingAircraft(refshim.GYM_CONFIG, config_kw=config_kw,
+def make_env(turbulence, config_kw=None, intensity="light", config_path=None):
+    env = FixedWingAircraft(config_path or refshim.GYM_CONFIG, config_kw=config_kw,
                             sim_config_kw={"turbulence": turbulence, "turbulence_intensity": intensity})
     env.seed(0)
     sim = env.simulator
@@ -230,6 +230,42 @@ def gen_full():
     np.savez_compressed(os.path.join(HERE, "traj_full300_turb.npz"), **out)
 
 
+class FixedDraws:
+    """Stand-in for the env-level RandomState: uniform(lo, hi) always returns lo + 0.625 (hi - lo) (i.e. 0.25 for the
+    U(-1, 1) draw behind `init_noise`, fixed_wing.py:1145), normal(loc, scale) returns loc."""
+
+    def uniform(self, low=0.0, high=1.0):
+        return low + 0.625 * (high - low)
+
+    def normal(self, loc=0.0, scale=1.0):
+        return loc
+
+
+def gen_cnn():
+    """The reference's CNN-controller config (examples/models/cnn_controller/fixed_wing_config.json): observation
+    length 5, shape matrix, relative targets, no alpha/beta — the general observation path."""
+    path = os.path.join(os.path.dirname(refshim.GYM_CONFIG), "examples", "models", "cnn_controller",
+                        "fixed_wing_config.json")
+    env = make_env(False, config_path=path)
+    env.np_random = FixedDraws()
+    rs = np.random.RandomState(77)
+    flat_env = env
+
+    class Flat:                      # run_episodes stores obs as arrays: flatten the [5, 12] matrix
+        def __getattr__(self, k):
+            return getattr(flat_env, k)
+
+        def reset(self, **kw):
+            return np.asarray(flat_env.reset(**kw)).ravel()
+
+        def step(self, a):
+            o, r, d, i = flat_env.step(a)
+            return np.asarray(o).ravel(), r, d, i
+
+    out = run_episodes(Flat(), 4, 60, rs, False, wind_mag=4.0, action_amp=1.3)
+    np.savez_compressed(os.path.join(HERE, "traj_cnn_obs.npz"), **out)
+
+
 def gen_pid(max_scen=100, num_envs=6):
     """Lock-step emulation of examples/evaluate_controller.py:57-232 (use_pid=True) with `num_envs` env slots.
 
@@ -375,7 +411,7 @@ def gen_dryden():
 
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
-    jobs = {"params": gen_params, "traj": gen_traj, "turb": gen_turb, "fail": gen_fail, "full": gen_full,
+    jobs = {"cnn": gen_cnn, "params": gen_params, "traj": gen_traj, "turb": gen_turb, "fail": gen_fail, "full": gen_full,
             "pid": gen_pid, "gae": gen_gae, "dryden": gen_dryden}
     for name, fn in jobs.items():
         if what in (name, "all"):

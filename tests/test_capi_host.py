@@ -59,7 +59,9 @@ def test_overrides_follow_reference_semantics():
 
 def test_unsupported_configs_fail_loudly():
     with pytest.raises(NotImplementedError):
-        C.build_config(config_kw={"observation": {"length": 5}})
+        C.build_config(config_kw={"observation": {"step": 2}})
+    with pytest.raises(NotImplementedError):
+        C.build_config(config_kw={"target": {"states": {0: {"class": "sinusoidal"}}}})
     with pytest.raises(NotImplementedError):
         C.build_config(config_kw={"reward": {"form": "potential"}})
 

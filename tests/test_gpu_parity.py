@@ -145,3 +145,46 @@ def test_gae_bit_exact_vs_reference_fixture(cuda_device):
                        dev(g[tag + "_last_done"].astype(np.uint8)))
         assert np.array_equal(adv.cpu().numpy(), g[tag + "_adv"]), tag
         assert np.array_equal(ret.cpu().numpy(), g[tag + "_ret"]), tag
+
+
+def test_general_observation_layout_cnn_config(cuda_device):
+    """The reference's CNN-controller config (5 x 12 observation matrix: history rows, relative targets, action
+    windows shifted in time) on the CUDA path against the live-reference fixture and, with Philox init_noise and
+    observation noise switched on, against the oracle."""
+    import torch
+    from conftest import cnn_env_config
+    from oracle import fw_oracle as O
+    from tum_adlr_deep_reinforcement_learning_b200 import batched as bt
+    from tum_adlr_deep_reinforcement_learning_b200.config import build_config
+    g = load_golden("traj_cnn_obs")
+    E, T = g["actions"].shape[:2]
+    cfg = build_config(env_cfg=cnn_env_config(), sim_config_kw={"turbulence": False}, obs_init_noise=0.25)
+    env = bt.BatchedFixedWing(E, cfg=cfg)
+    assert env.obs_dim == 60
+    env.enable_f64_outputs()
+    env.reset(state=g["init_state"], target=g["init_target"])
+    assert np.abs(env.obs64.cpu().numpy() - g["obs0"]).max() < 1e-12
+    for t in range(T):
+        env.step(torch.as_tensor(g["actions"][:, t]).cuda().contiguous(), auto_reset=False)
+        assert _rel(env.obs64.cpu().numpy(), g["obs"][:, t]).max() < RTOL_F64, t
+        assert _rel(env.rew64.cpu().numpy(), g["reward"][:, t]).max() < RTOL_F64
+    env.close()
+    # random resets / Philox init_noise / observation noise / auto-reset: CUDA vs oracle
+    ecfg = cnn_env_config()
+    ecfg["observation"]["noise"] = {"mean": 0.0, "var": 0.05}
+    ecfg["steps_max"] = 12
+    cfg = build_config(env_cfg=ecfg, sim_config_kw={"turbulence": True}, seed=9)
+    n = 512
+    env = bt.BatchedFixedWing(n, cfg=cfg)
+    env.enable_f64_outputs()
+    env.reset()
+    ob = O.OracleBatch(cfg, n)
+    assert _rel(env.obs64.cpu().numpy(), ob.reset()).max() < 1e-12
+    rs = np.random.RandomState(3)
+    for t in range(30):
+        a = rs.uniform(-1.2, 1.2, (n, 3)).astype(np.float32)
+        env.step(torch.as_tensor(a).cuda(), auto_reset=True)
+        o_ref, r_ref, d_ref = ob.step(a)
+        assert np.array_equal(env.done.cpu().numpy(), d_ref)
+        assert _rel(env.obs64.cpu().numpy(), o_ref).max() < RTOL_F64, t
+    env.close()

@@ -155,3 +155,20 @@ def test_oracle_reproduces_reference_golden_pid_evaluation():
         gold = np.sort(np.nan_to_num(g["gold_" + name], nan=-1), axis=0)
         assert np.array_equal(ours, gold), name
     assert np.abs(np.sort(m[:, 16]) - np.sort(g["gold_control_variation"][:, 0])).max() < 1e-4
+
+
+def test_oracle_general_observation_layout_cnn_config():
+    """examples/models/cnn_controller/fixed_wing_config.json: 5 x 12 observation matrix with history rows, relative
+    targets and the init_noise offset (pinned to u = 0.25 in the fixture run and here)."""
+    from conftest import cnn_env_config
+    g = load_golden("traj_cnn_obs")
+    cfg = build_config(env_cfg=cnn_env_config(), sim_config_kw={"turbulence": False}, obs_init_noise=0.25)
+    assert cfg.obs_generic == 1 and (cfg.obs_len, cfg.obs_n) == (5, 12)
+    for ep in range(g["actions"].shape[0]):
+        env = O.OracleEnv(cfg)
+        obs = env.reset(g["init_state"][ep], g["init_target"][ep])
+        assert obs.shape == (60,) and np.abs(obs - g["obs0"][ep]).max() < 1e-12
+        for t in range(int(g["n_valid"][ep])):
+            obs, rew, done, term = env.step(g["actions"][ep, t])
+            assert _rel(obs, g["obs"][ep, t]).max() < 1e-9, (ep, t)
+            assert abs(rew - g["reward"][ep, t]) < 1e-9 and done == bool(g["done"][ep, t])

@@ -31,10 +31,11 @@ class BatchedFixedWing:
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().fw_create(ctypes.byref(self.cfg), self.n, device, ctypes.byref(self._h)), "fw_create")
         n, dev = self.n, self.device
-        self.obs = torch.zeros(n, FW_NOBS, dtype=torch.float32, device=dev)
+        self.obs_dim = _lib.lib().fw_obs_dim(self._h)
+        self.obs = torch.zeros(n, self.obs_dim, dtype=torch.float32, device=dev)
         self.rew = torch.zeros(n, dtype=torch.float32, device=dev)
         self.done = torch.zeros(n, dtype=torch.uint8, device=dev)
-        self.term_obs = torch.zeros(n, FW_NOBS, dtype=torch.float32, device=dev)
+        self.term_obs = torch.zeros(n, self.obs_dim, dtype=torch.float32, device=dev)
         self.obs64 = None
         self.rew64 = None
         self._noise = None   # keeps an injected noise buffer alive
@@ -51,7 +52,7 @@ class BatchedFixedWing:
             pass
 
     def enable_f64_outputs(self):
-        self.obs64 = torch.zeros(self.n, FW_NOBS, dtype=torch.float64, device=self.device)
+        self.obs64 = torch.zeros(self.n, self.obs_dim, dtype=torch.float64, device=self.device)
         self.rew64 = torch.zeros(self.n, dtype=torch.float64, device=self.device)
 
     def _stream(self):
@@ -114,7 +115,7 @@ class BatchedFixedWing:
 
     def episode_info_rows(self, idx):
         """Rows `idx` (LongTensor on the device) of (metrics | return | length | term_code | terminal observation) as
-        ONE packed host array [k, 28 + 3 + 14] — a single small D2H copy instead of four full-size ones."""
+        ONE packed host array [k, 28 + 3 + obs_dim] — a single small D2H copy instead of four full-size ones."""
         term, metrics, ret, length = self.episode_info()
         packed = torch.cat([metrics.index_select(0, idx), ret.index_select(0, idx)[:, None],
                             length.index_select(0, idx)[:, None].to(torch.float64),

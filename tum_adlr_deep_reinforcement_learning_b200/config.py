@@ -20,7 +20,7 @@ import numpy as np
 
 _DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
 
-FW_ABI_VERSION = 2
+FW_ABI_VERSION = 3
 FW_NY, FW_NOBS, FW_NACT, FW_NSTATE_INJECT, FW_NMETRIC = 19, 14, 3, 21, 28
 FW_F64, FW_F32 = 0, 1
 FW_INT_RK45_SCIPY, FW_INT_RK4_FIXED = 0, 1
@@ -71,6 +71,9 @@ class FwConfig(ctypes.Structure):
            ("rew_bound_scaling", _d), ("rew_bound_max", _d), ("rew_delta_window", _i), ("obs_act_window", _i),
            ("step_fail_timesteps", _i), ("_pad2", _i), ("step_fail_value", _d), ("rise_low", _d), ("rise_high", _d),
            ("obs_noise_mean", _d), ("obs_noise_std", _d),
+           ("obs_generic", _i), ("obs_len", _i), ("obs_n", _i), ("obs_normalize", _i),
+           ("obs_kind", _i * 16), ("obs_idx", _i * 16), ("obs_window", _i * 16), ("obs_norm_flag", _i * 16),
+           ("obs_mean", _d * 16), ("obs_var", _d * 16), ("obs_init_noise", _d),
            ("seed", ctypes.c_uint64), ("env_id_offset", ctypes.c_int64)])
 
 
@@ -269,7 +272,7 @@ def dryden_filters(sim_length, sim_dt, wingspan, intensity="light", spec=False):
 
 def build_config(env_cfg=None, sim_cfg=None, config_kw=None, sim_config_kw=None, params=None,
                  curriculum_level=1.0, precision="f64", integrator="rk45", rk4_substeps=4, rtol=1e-3, atol=1e-6,
-                 seed=0, env_id_offset=0, dryden_spec=False):
+                 seed=0, env_id_offset=0, dryden_spec=False, obs_init_noise=None):
     """Flatten reference-format configs into an `FwConfig`.  `env_cfg` / `sim_cfg`: dict or JSON path (defaults above)."""
     def load(x, default):
         if x is None:
@@ -426,19 +429,65 @@ def build_config(env_cfg=None, sim_cfg=None, config_kw=None, sim_config_kw=None,
     c.step_fail_timesteps = int(fail == "timesteps")
     c.step_fail_value = 0.0 if fail == "timesteps" else float(fail)
     obs = env["observation"]
-    if obs.get("length", 1) != 1 or obs.get("normalize", False):
-        raise NotImplementedError("observation history / normalisation (SURVEY §8f row 1)")
     noise = obs.get("noise") or {}
     c.obs_noise_mean, c.obs_noise_std = float(noise.get("mean", 0) or 0), float(noise.get("var", 0) or 0)
-    names = [(s["name"], s["type"]) for s in obs["states"]]
-    expect = [("roll", "state"), ("pitch", "state"), ("Va", "state"), ("omega_p", "state"), ("omega_q", "state"),
-              ("omega_r", "state"), ("roll", "target"), ("pitch", "target"), ("Va", "target"), ("alpha", "state"),
-              ("beta", "state"), ("elevator", "action"), ("aileron", "action"), ("throttle", "action")]
-    if names != expect:
-        raise NotImplementedError("observation layout other than the default 14-vector")
-    c.obs_act_window = int([s for s in obs["states"] if s["type"] == "action"][0].get("window_size", 1))
-    if max(c.obs_act_window, c.rew_delta_window) > 8:
-        raise NotImplementedError("action windows > 8")
+    if obs.get("step", 1) != 1:
+        raise NotImplementedError("observation.step != 1")
+    L = int(obs.get("length", 1))
+    states = obs["states"]
+    if L > 5 or len(states) > 16:
+        raise NotImplementedError("observation.length > 5 or more than 16 entries per row")
+    names = [(s_["name"], s_["type"]) for s_ in states]
+    default_layout = [("roll", "state"), ("pitch", "state"), ("Va", "state"), ("omega_p", "state"),
+                      ("omega_q", "state"), ("omega_r", "state"), ("roll", "target"), ("pitch", "target"),
+                      ("Va", "target"), ("alpha", "state"), ("beta", "state"), ("elevator", "action"),
+                      ("aileron", "action"), ("throttle", "action")]
+    c.obs_normalize = int(bool(obs.get("normalize", False)))
+    c.obs_len, c.obs_n = L, len(states)
+    c.obs_generic = int(not (L == 1 and names == default_layout and not c.obs_normalize
+                             and all(s_.get("value", "absolute") == "absolute" for s_ in states if s_["type"] == "target")))
+    c.obs_init_noise = float("nan") if obs_init_noise is None else float(obs_init_noise)
+    state_idx = {"roll": 0, "pitch": 1, "Va": 2, "omega_p": 3, "omega_q": 4, "omega_r": 5, "alpha": 6, "beta": 7}
+    act_names = [a_["name"] for a_ in act["states"]]
+    f32max = float(np.finfo(np.float32).max)
+    windows = [1]
+    for e, s_ in enumerate(states):
+        kind = s_["type"]
+        if kind == "state":
+            if s_["name"] not in state_idx:
+                raise NotImplementedError("observation of state %r" % s_["name"])
+            c.obs_kind[e], c.obs_idx[e] = 0, state_idx[s_["name"]]
+        elif kind == "target":
+            value = s_.get("value", "absolute")
+            if value not in ("absolute", "relative"):
+                raise NotImplementedError("target observation value %r" % value)
+            c.obs_kind[e], c.obs_idx[e] = (1 if value == "absolute" else 2), TARGET_STATES.index(s_["name"])
+        elif kind == "action":
+            c.obs_kind[e], c.obs_idx[e] = 3, act_names.index(s_["name"])
+            c.obs_window[e] = int(s_.get("window_size", 1))
+            windows.append(c.obs_window[e])
+        else:
+            raise NotImplementedError("observation entry type %r" % kind)
+        # normalisation constants (fixed_wing.py:95-161); limits come from the entry or the pyfly variable
+        v = var.get(s_["name"], {})
+        hi, lo = s_.get("high"), s_.get("low")
+        if hi is None:
+            hi = v.get("value_max") if v.get("value_max") is not None else v.get("constraint_max")
+            hi = f32max if hi is None else hi
+        elif s_.get("convert_to_radians"):
+            hi = float(np.radians(hi))
+        if lo is None:
+            lo = v.get("value_min") if v.get("value_min") is not None else v.get("constraint_min")
+            lo = -f32max if lo is None else lo
+        elif s_.get("convert_to_radians"):
+            lo = float(np.radians(lo))
+        finite = hi != f32max and lo != -f32max
+        c.obs_mean[e] = s_["mean"] if s_.get("mean") is not None else ((hi - lo) if finite else 0.0)
+        c.obs_var[e] = s_["var"] if s_.get("var") is not None else ((hi - lo) / 16 if finite else 1.0)
+        c.obs_norm_flag[e] = int(bool(s_.get("norm", True)))
+    c.obs_act_window = max(windows)
+    if max(c.obs_act_window, c.rew_delta_window) + (L - 1) > 9:
+        raise NotImplementedError("action windows + observation length exceed the 8-deep action ring")
     c.rise_low, c.rise_high = 0.1, 0.9
     for m in env.get("metrics", []):
         if m["name"] == "rise_time":
@@ -448,8 +497,16 @@ def build_config(env_cfg=None, sim_cfg=None, config_kw=None, sim_config_kw=None,
     return c
 
 
+def obs_dim(cfg):
+    return cfg.obs_len * cfg.obs_n if cfg.obs_generic else FW_NOBS
+
+
 def observation_bounds(env_cfg=None, cfg=None):
-    """observation_space low/high (fixed_wing.py:92-140) for the default 14-vector."""
+    """observation_space low/high (fixed_wing.py:92-140) for the default 14-vector; a general layout reports
+    unbounded boxes of its own shape."""
+    if cfg is not None and cfg.obs_generic:
+        f32max = float(np.finfo(np.float32).max)
+        return (np.full(obs_dim(cfg), -f32max, np.float32), np.full(obs_dim(cfg), f32max, np.float32))
     f32max = float(np.finfo(np.float32).max)
     d = np.radians
     lo = [d(-180), d(-85), 0, d(-720), d(-720), d(-720)]

@@ -103,6 +103,9 @@ template <typename T> struct DCfg {
     T tgt_low[3], tgt_high[3], tgt_delta[3], tgt_bound[3], streak_fraction;
     T rew_err_scaling[3], rew_err_max[3], rew_delta_scaling, rew_delta_max, rew_bound_scaling, rew_bound_max;
     T step_fail_value, rise_low, rise_high, obs_noise_mean, obs_noise_std;
+    int obs_generic, obs_len, obs_n, obs_normalize;
+    int obs_kind[FW_OBS_ENTRIES_MAX], obs_idx[FW_OBS_ENTRIES_MAX], obs_window[FW_OBS_ENTRIES_MAX], obs_norm_flag[FW_OBS_ENTRIES_MAX];
+    T obs_mean[FW_OBS_ENTRIES_MAX], obs_var[FW_OBS_ENTRIES_MAX], obs_init_noise;
     unsigned long long seed;
     long long env_id_offset;
 };
@@ -122,7 +125,12 @@ enum RField {
     RF_E0 = 71,               // 3 initial errors
     RF_ESUM = 74, RF_EABS = 77, RF_EMIN = 80, RF_EMAX = 83, RF_EPREV = 86,   // 3 each
     RF_EP_RET = 89,
-    RF_COUNT = 90
+    // general observation layout only (obs_generic): 4 older rows of (8 states, 3 targets, 3 errors), and 8-deep rings
+    // of raw actions / constrained commands (slot (age-1)*3 + j)
+    RF_HIST = 90,             // 4 x 14
+    RF_GACT = 146,            // 8 x 3
+    RF_GCMD = 170,            // 8 x 3
+    RF_COUNT = 194
 };
 enum IField {
     IF_STEPS = 0, IF_STEPS_TGT, IF_EPISODE, IF_SIM_STEP,
@@ -152,7 +160,7 @@ template <typename T> struct Soa {
 // ---------------------------------------------------------------------------------------------------------------
 // Philox4x32-10 counter-based RNG (Salmon et al. SC'11).  Stream layout (identical in oracle/fw_oracle.c):
 //   key = seed;  counter = (env_id lo32, episode lo32, purpose << 28 | env_id hi bits, block)
-enum { RNG_RESET = 0, RNG_NOISE = 1, RNG_RESAMPLE = 2, RNG_ACTION = 3, RNG_OBS = 4 };
+enum { RNG_RESET = 0, RNG_NOISE = 1, RNG_RESAMPLE = 2, RNG_ACTION = 3, RNG_OBS = 4, RNG_OBS_INIT = 5 };
 
 __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
 #pragma unroll
@@ -578,14 +586,14 @@ __device__ __forceinline__ void sample_target(const DCfg<T>& c, T roll, T pitch,
     }
 }
 
-// observation.noise (fixed_wing.py:1246-1247): every entry += N(mean, var); Philox purpose OBS, block = 4 * steps + b,
-// 14 Box-Muller normals per observation (same stream as oracle add_obs_noise).  Out of line: off by default.
+// observation.noise (fixed_wing.py:1246-1247): every entry += N(mean, var); Philox purpose OBS, block = 32 * steps + b,
+// four Box-Muller normals per block (same stream as oracle add_obs_noise).  Out of line: off by default.
 template <typename T>
 __device__ __noinline__ void add_obs_noise(const DCfg<T>& c, long long gid, unsigned long long episode, int steps,
-                                           T (&o)[FW_NOBS]) {
+                                           T* o, int dim) {
 #pragma unroll 1
-    for (int b = 0; b < 4; ++b) {
-        const uint4 r = rng_block(c.seed, gid, episode, RNG_OBS, (uint32_t)(steps * 4 + b));
+    for (int b = 0; b * 4 < dim; ++b) {
+        const uint4 r = rng_block(c.seed, gid, episode, RNG_OBS, (uint32_t)(steps * 32 + b));
         const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
@@ -595,22 +603,99 @@ __device__ __noinline__ void add_obs_noise(const DCfg<T>& c, long long gid, unsi
             double sn, cs;
             ::sincos(6.283185307179586476925 * u2, &sn, &cs);
             const int j = b * 4 + i * 2;
-            if (j < FW_NOBS) o[j] += c.obs_noise_mean + c.obs_noise_std * (T)(rad * cs);
-            if (j + 1 < FW_NOBS) o[j + 1] += c.obs_noise_mean + c.obs_noise_std * (T)(rad * sn);
+            if (j < dim) o[j] += c.obs_noise_mean + c.obs_noise_std * (T)(rad * cs);
+            if (j + 1 < dim) o[j + 1] += c.obs_noise_mean + c.obs_noise_std * (T)(rad * sn);
         }
     }
 }
 
-// observation (fixed_wing.py:1113-1262, default 14-vector)
+template <typename T> __device__ __forceinline__ int obs_dim(const DCfg<T>& c) {
+    return c.obs_generic ? c.obs_len * c.obs_n : FW_NOBS;
+}
+
+// observation (fixed_wing.py:1113-1262): row-major [obs_len][obs_n] floats per env (the default layout is one row of 14)
 template <typename T>
-__device__ __forceinline__ void write_obs(const T o[FW_NOBS], int env, float* obs, double* obs64) {
-    if (obs) {
-#pragma unroll
-        for (int j = 0; j < FW_NOBS; ++j) obs[(size_t)env * FW_NOBS + j] = (float)o[j];
+__device__ __forceinline__ void write_obs(const T* o, int dim, int env, float* obs, double* obs64) {
+    if (obs) for (int j = 0; j < dim; ++j) obs[(size_t)env * dim + j] = (float)o[j];
+    if (obs64) for (int j = 0; j < dim; ++j) obs64[(size_t)env * dim + j] = (double)o[j];
+}
+
+// General observation layout (fixed_wing.py:1113-1262): obs_len rows, newest first; row i reads `.history[-i]` of the
+// states, targets and errors, clamped to the start of the episode (then the row gets the `init_noise` offset
+// U(-1,1) * dt, one draw per row, fixed_wing.py:1142-1145), action entries sum |diff| over a window of raw actions (or
+// constrained commands when actions are not scaled) that ends i-1 steps back, or the backward-scaled actuator value
+// while the episode is younger than the row.  `steps` = steps_count (0 at reset).  When `push` the rings are advanced
+// with this step's values afterwards.
+template <typename T>
+__device__ __noinline__ void generic_observation(const DCfg<T>& c, const Soa<T>& S, int env, int steps, bool push,
+                                                 const T (&cur)[14] /* 8 states, 3 targets, 3 errors */,
+                                                 const T (&a_raw)[3], bool act_f32, const T (&cmd_in)[3],
+                                                 const T (&actval)[3], unsigned long long episode, T* o) {
+    const int n = S.n, L = c.obs_len, ne = c.obs_n;
+    T* r = S.r + env;
+    T hist[4][14], gact[24], gcmd[24];
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k)
+        for (int q = 0; q < 14; ++q) hist[k][q] = r[(RF_HIST + k * 14 + q) * n];
+#pragma unroll 1
+    for (int k = 0; k < 24; ++k) { gact[k] = r[(RF_GACT + k) * n]; gcmd[k] = r[(RF_GCMD + k) * n]; }
+    const int N = steps;                                     // number of actions so far, the current one included
+#pragma unroll 1
+    for (int i = 1; i <= L; ++i) {
+        int ie = i;
+        T init_noise = 0;
+        if (i > steps) {
+            ie = steps + 1;
+            if (L > 1) {
+                T u;
+                if (!M<T>::isnan(c.obs_init_noise)) u = c.obs_init_noise;
+                else {
+                    const uint4 rr = rng_block(c.seed, c.env_id_offset + env, episode, RNG_OBS_INIT, (uint32_t)(steps * 8 + (i - 1)));
+                    u = (T)(2.0 * u53(rr.x, rr.y) - 1.0);
+                }
+                init_noise = u * c.dt;
+            }
+        }
+#pragma unroll 1
+        for (int k = 0; k < ne; ++k) {
+            const int idx = c.obs_idx[k], kind = c.obs_kind[k];
+            T val;
+            if (kind != FW_OBS_ACTION) {
+                const int q = (kind == FW_OBS_STATE) ? idx : (kind == FW_OBS_TARGET_ABS ? 8 + idx : 11 + idx);
+                val = (ie == 1) ? cur[q] : hist[ie - 2][q];
+            } else if (steps - ie < 0) {
+                val = actval[idx];
+                if (c.scale_actions)
+                    val = (c.scale_high - c.scale_low) * (val - c.act_lo[idx]) / (c.act_hi[idx] - c.act_lo[idx]) + c.scale_low;
+            } else {
+                const bool f32 = c.scale_actions ? act_f32 : false;
+                const T* ring = c.scale_actions ? gact : gcmd;
+                const T curv = c.scale_actions ? a_raw[idx] : cmd_in[idx];
+                const int hi = N - (ie - 1);
+                int lo = N - c.obs_window[k] - ie + 1;
+                if (lo < 0) lo = 0;
+                float sacc = 0.f;
+                for (int t = lo + 1; t < hi; ++t) {
+                    const T newer = (t == N - 1) ? curv : ring[(N - 2 - t) * 3 + idx];
+                    const T older = ring[(N - 2 - (t - 1)) * 3 + idx];
+                    sacc += f32 ? fabsf((float)newer - (float)older) : (float)M<T>::fabs(newer - older);
+                }
+                val = (T)sacc;
+            }
+            val += init_noise;
+            if (c.obs_normalize && c.obs_norm_flag[k]) { val -= c.obs_mean[k]; val /= c.obs_var[k]; }
+            o[(i - 1) * ne + k] = val;
+        }
     }
-    if (obs64) {
-#pragma unroll
-        for (int j = 0; j < FW_NOBS; ++j) obs64[(size_t)env * FW_NOBS + j] = (double)o[j];
+    if (c.obs_noise_std > (T)0 || c.obs_noise_mean != (T)0) add_obs_noise<T>(c, c.env_id_offset + env, episode, steps, o, L * ne);
+    if (push) {
+#pragma unroll 1
+        for (int k = 3; k >= 1; --k)
+            for (int q = 0; q < 14; ++q) r[(RF_HIST + k * 14 + q) * n] = hist[k - 1][q];
+        for (int q = 0; q < 14; ++q) r[(RF_HIST + q) * n] = cur[q];
+#pragma unroll 1
+        for (int k = 23; k >= 3; --k) { r[(RF_GACT + k) * n] = gact[k - 3]; r[(RF_GCMD + k) * n] = gcmd[k - 3]; }
+        for (int j = 0; j < 3; ++j) { r[(RF_GACT + j) * n] = a_raw[j]; r[(RF_GCMD + j) * n] = cmd_in[j]; }
     }
 }
 
@@ -740,8 +825,21 @@ __device__ void reset_env(const DCfg<T>& c, const Soa<T>& S, int env, const doub
     for (int j = 0; j < 3; ++j)
         o[11 + j] = c.scale_actions ? (c.scale_high - c.scale_low) * (av[j] - c.act_lo[j]) / (c.act_hi[j] - c.act_lo[j]) + c.scale_low
                                     : av[j];
-    if (c.obs_noise_std > (T)0 || c.obs_noise_mean != (T)0) add_obs_noise<T>(c, gid, episode, 0, o);
-    write_obs(o, env, obs, obs64);
+    if (c.obs_generic) {
+        // history rings start with the reset entry (Variable.reset: history = [value]); the reset observation has every
+        // row clamped to the current values
+        const T cur[14] = {roll, pitch, Va, y[4], y[5], y[6], alpha, beta, tgt[0], tgt[1], tgt[2], e[0], e[1], e[2]};
+        for (int q = 0; q < 14; ++q) r[(RF_HIST + q) * n] = cur[q];
+        for (int k = 14; k < 56; ++k) r[(RF_HIST + k) * n] = 0;
+        for (int k = 0; k < 24; ++k) { r[(RF_GACT + k) * n] = 0; r[(RF_GCMD + k) * n] = 0; }
+        T og[FW_NOBS_MAX];
+        const T zero3[3] = {0, 0, 0};
+        generic_observation<T>(c, S, env, 0, false, cur, zero3, false, zero3, av, episode, og);
+        write_obs(og, obs_dim(c), env, obs, obs64);
+        return;
+    }
+    if (c.obs_noise_std > (T)0 || c.obs_noise_mean != (T)0) add_obs_noise<T>(c, gid, episode, 0, o, FW_NOBS);
+    write_obs(o, FW_NOBS, env, obs, obs64);
 }
 
 }  // namespace fw

@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(128) rk4_kernel(const __grid_constant__ DCfg<T
 }
 
 // ---- kernel B: everything after the integrator (once per step, high occupancy) ----
-template <typename T, bool TURB>
+template <typename T, bool TURB, bool GENERIC>
 __global__ void __launch_bounds__(128, 4) head_kernel(const __grid_constant__ DCfg<T> c, const Soa<T> S, const StepIO io,
                                                    const Scratch<T> W) {
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
@@ -598,7 +598,20 @@ __global__ void __launch_bounds__(128, 4) head_kernel(const __grid_constant__ DC
                                             : delta_feature<T>(cmd_in[j], cring, j, np_, false);
     }
 
-    if (c.obs_noise_std > (T)0 || c.obs_noise_mean != (T)0) add_obs_noise<T>(c, c.env_id_offset + env, episode, steps, obs_v);
+    if (!GENERIC && (c.obs_noise_std > (T)0 || c.obs_noise_mean != (T)0))
+        add_obs_noise<T>(c, c.env_id_offset + env, episode, steps, obs_v, FW_NOBS);
+    T og[GENERIC ? FW_NOBS_MAX : 1];
+    const T* obs_out = obs_v;
+    int odim = FW_NOBS;
+    if constexpr (GENERIC) {
+        const T e_cur[3] = {fail ? err_roll(tgt[0], roll) : e_new[0], fail ? tgt[1] - pitch : e_new[1], fail ? tgt[2] - Va : e_new[2]};
+        const T cur[14] = {roll, pitch, Va, om_obs[0], om_obs[1], om_obs[2], alpha, beta, tgt[0], tgt[1], tgt[2],
+                           e_cur[0], e_cur[1], e_cur[2]};
+        const T actval[3] = {(y[13] + y[14]) / (T)2, (-y[13] + y[14]) / (T)2, y[15]};
+        generic_observation<T>(c, S, env, steps, !fail, cur, a_raw, act_f32, cmd_in, actval, episode, og);
+        obs_out = og;
+        odim = c.obs_len * c.obs_n;
+    }
 
     // ---------------- streamed episode statistics (fixed_wing.py:1644-1736) ----------------
     T esum[3], eabs[3], emin[3], emax[3], e0v[3];
@@ -669,14 +682,14 @@ __global__ void __launch_bounds__(128, 4) head_kernel(const __grid_constant__ DC
     ii[IF_NATT * n] = natt;
 
     if (done && io.auto_reset) {
-        if (io.term_obs) write_obs(obs_v, env, io.term_obs, (double*)nullptr);
+        if (io.term_obs) write_obs(obs_out, odim, env, io.term_obs, (double*)nullptr);
         reset_env_noinline<T>(c, S, env, io.obs, io.obs64);
         // keep the diagnostics of the step that ended the episode
         ii[IF_NFEV * n] = nfev;
         ii[IF_NATT * n] = natt;
         return;
     }
-    write_obs(obs_v, env, io.obs, io.obs64);
+    write_obs(obs_out, odim, env, io.obs, io.obs64);
 
     // ---------------- store ----------------
     if (TURB && !fail) {
@@ -852,7 +865,12 @@ template <typename T> static void convert_cfg(const FwConfig& f, DCfg<T>& d) {
         CP(tgt_low[k]); CP(tgt_high[k]); CP(tgt_delta[k]); CP(tgt_bound[k]); CP(rew_err_scaling[k]); CP(rew_err_max[k]);
     }
     CP(streak_fraction); CP(rew_delta_scaling); CP(rew_delta_max); CP(rew_bound_scaling); CP(rew_bound_max);
-    CP(step_fail_value); CP(rise_low); CP(rise_high); CP(obs_noise_mean); CP(obs_noise_std);
+    CP(step_fail_value); CP(rise_low); CP(rise_high); CP(obs_noise_mean); CP(obs_noise_std); CP(obs_init_noise);
+    d.obs_generic = f.obs_generic; d.obs_len = f.obs_len; d.obs_n = f.obs_n; d.obs_normalize = f.obs_normalize;
+    for (int k = 0; k < FW_OBS_ENTRIES_MAX; ++k) {
+        d.obs_kind[k] = f.obs_kind[k]; d.obs_idx[k] = f.obs_idx[k]; d.obs_window[k] = f.obs_window[k];
+        d.obs_norm_flag[k] = f.obs_norm_flag[k]; CP(obs_mean[k]); CP(obs_var[k]);
+    }
 #undef CP
     d.seed = f.seed;
     d.env_id_offset = f.env_id_offset;
@@ -912,7 +930,8 @@ static int launch_rk45(FwHandle* h, const DCfg<T>& c, const Soa<T>& S, const Scr
     const int g0 = (h->n + 127) / 128;
     rk45_init_kernel<T, TURB><<<g0, 128, 0, st>>>(c, S, io, W, grid * NT);
     k<<<grid, NT, smem, st>>>(c, S, W);
-    head_kernel<T, TURB><<<g0, 128, 0, st>>>(c, S, io, W);
+    if (h->cfg.obs_generic) head_kernel<T, TURB, true><<<g0, 128, 0, st>>>(c, S, io, W);
+    else head_kernel<T, TURB, false><<<g0, 128, 0, st>>>(c, S, io, W);
     CK(cudaGetLastError());
     return FW_OK;
 }
@@ -920,7 +939,8 @@ template <typename T, bool TURB>
 static int launch_rk4(FwHandle* h, const DCfg<T>& c, const Soa<T>& S, const Scratch<T>& W, const StepIO& io, cudaStream_t st) {
     const int g0 = (h->n + 127) / 128;
     rk4_kernel<T, TURB><<<g0, 128, 0, st>>>(c, S, io, W);
-    head_kernel<T, TURB><<<g0, 128, 0, st>>>(c, S, io, W);
+    if (h->cfg.obs_generic) head_kernel<T, TURB, true><<<g0, 128, 0, st>>>(c, S, io, W);
+    else head_kernel<T, TURB, false><<<g0, 128, 0, st>>>(c, S, io, W);
     CK(cudaGetLastError());
     return FW_OK;
 }
@@ -944,11 +964,15 @@ extern "C" {
 const char* fw_last_error(void) { return g_err; }
 int fw_abi_version(void) { return FW_ABI_VERSION; }
 int fw_config_size(void) { return (int)sizeof(FwConfig); }
+int fw_obs_dim(const FwHandle* h) { return h ? (h->cfg.obs_generic ? h->cfg.obs_len * h->cfg.obs_n : FW_NOBS) : FW_EINVAL; }
 
 int fw_create(const FwConfig* cfg, int32_t n_envs, int32_t device, FwHandle** out) {
     if (!cfg || !out || n_envs <= 0) { snprintf(g_err, sizeof(g_err), "fw_create: bad arguments"); return FW_EINVAL; }
     if (cfg->abi_version != FW_ABI_VERSION) { snprintf(g_err, sizeof(g_err), "fw_create: ABI version mismatch"); return FW_EINVAL; }
-    if (cfg->streak_req > 128 || cfg->rew_delta_window > 5 || cfg->obs_act_window > 5 || cfg->steps_max <= 0 ||
+    if (cfg->streak_req > 128 || cfg->rew_delta_window > 5 || cfg->steps_max <= 0 ||
+        (!cfg->obs_generic && cfg->obs_act_window > 5) ||
+        (cfg->obs_generic && (cfg->obs_len < 1 || cfg->obs_len > FW_OBS_LEN_MAX || cfg->obs_n < 1 || cfg->obs_n > FW_OBS_ENTRIES_MAX ||
+                              cfg->obs_act_window + cfg->obs_len - 1 > 9)) ||
         (cfg->precision != FW_F64 && cfg->precision != FW_F32) ||
         (cfg->integrator != FW_INT_RK45_SCIPY && cfg->integrator != FW_INT_RK4_FIXED)) {
         snprintf(g_err, sizeof(g_err), "fw_create: unsupported config value");

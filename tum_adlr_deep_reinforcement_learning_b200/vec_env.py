@@ -93,7 +93,8 @@ class FixedWingVecEnv:
         self._act_dev = torch.zeros(n, 3, dtype=torch.float32, device=self.device)
         # double-buffered pinned outputs: with copy_outputs=False the arrays returned by step k stay valid until
         # step k+2 (SB3's collect_rollouts reads obs_k after step k+1 returns, on_policy_algorithm.py:163-180)
-        self._out = [(torch.zeros(n, 14, dtype=torch.float32).pin_memory(), torch.zeros(n, dtype=torch.float32).pin_memory(),
+        self._out = [(torch.zeros(n, self.sim.obs_dim, dtype=torch.float32).pin_memory(),
+                      torch.zeros(n, dtype=torch.float32).pin_memory(),
                       torch.zeros(n, dtype=torch.uint8).pin_memory()) for _ in range(2)]
         self._out_np = [(o.numpy(), r.numpy(), d.numpy().view(np.bool_)) for o, r, d in self._out]
         self._flip = 0
@@ -103,7 +104,7 @@ class FixedWingVecEnv:
         self._waiting = False
         self._t_start = time.time()
         self.h2d_bytes_per_step = self._act_pin.numel() * 4
-        self.d2h_bytes_per_step = n * 14 * 4 + n * 4 + n
+        self.d2h_bytes_per_step = n * self.sim.obs_dim * 4 + n * 4 + n
 
     # ------------------------------------------------------------------ tensor fast path
     def reset_tensor(self):
@@ -261,7 +262,7 @@ class FixedWingVecEnv:
             now = round(time.time() - self._t_start, 6)
             for row, i in zip(rows, done_idx):
                 info = dict(infos[i])
-                metrics, ret, length, term, term_obs = row[:28], row[28], int(row[29]), int(row[30]), row[31:45]
+                metrics, ret, length, term, term_obs = row[:28], row[28], int(row[29]), int(row[30]), row[31:]
                 info["termination"] = TERM_NAMES.get(term, term)
                 for name, off, keys in METRIC_LAYOUT:
                     vals = metrics[off:off + len(keys)]
@@ -271,8 +272,9 @@ class FixedWingVecEnv:
                         info[name] = {k: float(x) for k, x in zip(keys, vals)}
                 info["terminal_observation"] = term_obs.astype(np.float32)
                 info["episode"] = {"r": float(ret), "l": length, "t": now}
-                # fixed_wing.py:626 reports the finished episode's target; it sits in terminal_observation[6:9]
-                info.setdefault("target", dict(zip(TARGET_STATES, map(float, term_obs[6:9]))))
+                if not self.cfg.obs_generic:
+                    # fixed_wing.py:626 reports the finished episode's target; it sits in terminal_observation[6:9]
+                    info.setdefault("target", dict(zip(TARGET_STATES, map(float, term_obs[6:9]))))
                 infos[i] = info
         return infos
 
