@@ -26,13 +26,14 @@
 extern "C" {
 #endif
 
-#define FW_ABI_VERSION 3
+#define FW_ABI_VERSION 4
 
 #define FW_NY 19        /* ODE state: quat[4] omega[3] pos[3] vel[3] act_value[3] act_rate[3]  (pyfly.py:1372-1389) */
 #define FW_NOBS 14      /* default observation vector (fixed_wing_config.json "observation.states")               */
 #define FW_OBS_ENTRIES_MAX 16  /* entries per observation row                                                     */
 #define FW_OBS_LEN_MAX 5       /* observation.length (rows of history)                                            */
 #define FW_NOBS_MAX (FW_OBS_ENTRIES_MAX * FW_OBS_LEN_MAX)
+#define FW_REW_FACTORS_MAX 12
 #define FW_NACT 3       /* elevator, aileron, throttle (fixed_wing_config.json "action.states")                   */
 #define FW_NSTATE_INJECT 21 /* roll pitch yaw p q r pn pe pd u v w | er el thr | er_dot el_dot thr_dot | wind n e d */
 #define FW_NMETRIC 28   /* see FwMetricIndex                                                                      */
@@ -66,6 +67,11 @@ enum FwIntegrator {
 enum FwPrecision { FW_F64 = 0, FW_F32 = 1 };
 
 /* observation entry kinds (fixed_wing.py:1149-1234) and the state indices an entry of kind STATE may name */
+/* general reward engine (fixed_wing.py:941-1111): factor classes/types and function classes */
+enum FwRewFactor { FW_RF_STATE_ERROR = 0, FW_RF_STATE_VALUE, FW_RF_ACTION_VALUE, FW_RF_ACTION_DELTA, FW_RF_ACTION_BOUND,
+                   FW_RF_SUCCESS, FW_RF_STEP, FW_RF_GOAL_PER_STATE, FW_RF_GOAL_ALL };
+enum FwRewFunction { FW_FN_LINEAR = 0, FW_FN_EXPONENTIAL = 1, FW_FN_QUADRATIC = 2 };
+
 enum FwObsKind { FW_OBS_STATE = 0, FW_OBS_TARGET_ABS = 1, FW_OBS_TARGET_REL = 2, FW_OBS_ACTION = 3 };
 enum FwObsState { FW_S_ROLL = 0, FW_S_PITCH, FW_S_VA, FW_S_OMEGA_P, FW_S_OMEGA_Q, FW_S_OMEGA_R, FW_S_ALPHA, FW_S_BETA };
 
@@ -158,6 +164,16 @@ typedef struct FwConfig {
     double obs_noise_mean, obs_noise_std; /* observation.noise {mean, var}: every entry += N(mean, var) where numpy's
                                              `scale=var` makes "var" a standard deviation (fixed_wing.py:1246-1247);
                                              std <= 0 and mean == 0 disables (the reference's default) */
+
+    /* ---- general reward engine; rew_generic == 0 selects the default factor family above ---- */
+    int32_t rew_generic, rew_n, rew_potential, rew_nterms;
+    int32_t rew_class[FW_REW_FACTORS_MAX];      /* FwRewFactor */
+    int32_t rew_idx[FW_REW_FACTORS_MAX];        /* target index (error) or FwObsState index (value) */
+    int32_t rew_fclass[FW_REW_FACTORS_MAX];     /* FwRewFunction */
+    int32_t rew_shaping[FW_REW_FACTORS_MAX], rew_window[FW_REW_FACTORS_MAX], rew_value_timesteps[FW_REW_FACTORS_MAX];
+    double rew_scaling[FW_REW_FACTORS_MAX], rew_maxv[FW_REW_FACTORS_MAX], rew_sign[FW_REW_FACTORS_MAX], rew_value[FW_REW_FACTORS_MAX];
+    int32_t term_fclass[4];                     /* terms in config order (3 used) */
+    double term_weight[4];
 
     /* ---- general observation layout (fixed_wing.py:1113-1262): obs_len rows (history, newest first) of obs_n entries.
      * obs_generic == 0 selects the default 14-vector fast path and ignores the arrays below. ---- */

@@ -66,6 +66,8 @@ typedef struct FwoEnv {
     uint8_t* goal_hist; int n_goal;                  /* history["goal"], [t][4] roll pitch Va all */
     double* st_hist;   int n_st;                     /* state .history of roll pitch Va p q r alpha beta, [t][8] */
     double* tgt_hist;  int n_tgt;                    /* history["target"], [t][3] */
+    double prev_shaping[3]; int has_prev_shaping[3];   /* self.prev_shaping per function class (None after reset) */
+    int goal_achieved;                                /* self.goal_achieved: set once, never cleared by reset */
     double ep_return;
     double metrics[FW_NMETRIC];
     int term_code;
@@ -783,6 +785,88 @@ static double get_reward(const FwoEnv* e, const double action[3]) {
     return 1.0 * (val_plain + val_shaping);
 }
 
+/* get_reward (fixed_wing.py:941-1111), the general engine: any list of factors (state error / value, action value /
+ * delta / bound, success, step, goal per_state / all) with linear / exponential / quadratic function classes, shaping
+ * and non-shaping parts per term, absolute or potential form. */
+static double get_reward_generic(FwoEnv* e, const double action[3], int success) {
+    const FwConfig* c = &e->cfg;
+    double val_t[3] = {0, 0, 0}, shp_t[3] = {0, 0, 0};
+    const double states[8] = {e->roll, e->pitch, e->Va, e->omega[0], e->omega[1], e->omega[2], e->alpha, e->beta};
+    uint8_t g[4];
+    goal_status(e, g);
+    for (int i = 0; i < c->rew_n; ++i) {
+        double val = 0;
+        switch (c->rew_class[i]) {
+            case FW_RF_STATE_ERROR: val = get_error(e, c->rew_idx[i]); break;
+            case FW_RF_STATE_VALUE: val = states[c->rew_idx[i]]; break;
+            case FW_RF_ACTION_VALUE:
+                if (e->act_is_f32) { float sacc = 0; for (int j = 0; j < 3; ++j) sacc += fabsf((float)action[j]); val = sacc; }
+                else for (int j = 0; j < 3; ++j) val += fabs(action[j]);
+                break;
+            case FW_RF_ACTION_DELTA:
+                if (e->steps_count > 1) {
+                    int w = c->rew_window[i], lo = e->n_act - w < 0 ? 0 : e->n_act - w, rows = e->n_act - lo - 1;
+                    if (e->act_is_f32) {
+                        float d[3 * FW_ACT_WINDOW_MAX];
+                        for (int t = 0; t < rows; ++t) for (int j = 0; j < 3; ++j)
+                            d[t * 3 + j] = fabsf((float)e->act_hist[(lo + t + 1) * 3 + j] - (float)e->act_hist[(lo + t) * 3 + j]);
+                        val = (double)np_sum_f32(d, rows * 3);
+                    } else {
+                        double d[3 * FW_ACT_WINDOW_MAX];
+                        for (int t = 0; t < rows; ++t) for (int j = 0; j < 3; ++j)
+                            d[t * 3 + j] = fabs(e->act_hist[(lo + t + 1) * 3 + j] - e->act_hist[(lo + t) * 3 + j]);
+                        val = np_sum_f64(d, rows * 3);
+                    }
+                }
+                break;
+            case FW_RF_ACTION_BOUND: {
+                double hi = 0, lo = 0;
+                for (int j = 0; j < 3; ++j) {
+                    if (action[j] > c->action_bounds_max[j]) hi += fabs(action[j] - c->action_bounds_max[j]);
+                    if (action[j] < c->action_bounds_min[j]) lo += fabs(action[j] - c->action_bounds_min[j]);
+                }
+                val = hi + lo;
+                break;
+            }
+            case FW_RF_SUCCESS:
+                val = success ? (c->rew_value_timesteps[i] ? (double)(c->steps_max - e->steps_count) : c->rew_value[i]) : 0;
+                break;
+            case FW_RF_STEP: val = c->rew_value[i]; break;
+            case FW_RF_GOAL_PER_STATE:
+                for (int k = 0; k < 3; ++k) val += g[k] ? c->rew_value[i] / 3 : 0;
+                break;
+            case FW_RF_GOAL_ALL: val += g[3] ? c->rew_value[i] : 0; break;
+        }
+        /* values derived from a float32 action array stay float32 through the function class (numpy keeps the array
+         * dtype against python scalars); everything else is float64 */
+        const int f32v = e->act_is_f32 && (c->rew_class[i] == FW_RF_ACTION_DELTA || c->rew_class[i] == FW_RF_ACTION_VALUE);
+        if (c->rew_fclass[i] == FW_FN_LINEAR) {
+            if (f32v) val = (double)fminf(fmaxf(fabsf((float)val) / (float)c->rew_scaling[i], 0.0f), (float)c->rew_maxv[i]);
+            else val = clipd(fabs(val) / c->rew_scaling[i], 0, c->rew_maxv[i]);
+        } else if (f32v) val = (double)(((float)val * (float)val) / (float)c->rew_scaling[i]);
+        else val = val * val / c->rew_scaling[i];
+        if (c->rew_shaping[i]) shp_t[c->rew_fclass[i]] += val * c->rew_sign[i];
+        else val_t[c->rew_fclass[i]] += val * c->rew_sign[i];
+    }
+    double reward = 0;
+    for (int t = 0; t < c->rew_nterms; ++t) {
+        const int fc = c->term_fclass[t];
+        double v;
+        if (fc == FW_FN_EXPONENTIAL) {
+            if (c->rew_potential) v = e->has_prev_shaping[fc] ? -1 + exp(val_t[fc] + (shp_t[fc] - e->prev_shaping[fc])) : -1 + exp(val_t[fc]);
+            else v = -1 + exp(val_t[fc] + shp_t[fc]);
+        } else {
+            v = val_t[fc];
+            if (c->rew_potential) { if (e->has_prev_shaping[fc]) v += shp_t[fc] - e->prev_shaping[fc]; }
+            else v += shp_t[fc];
+        }
+        e->prev_shaping[fc] = shp_t[fc];
+        e->has_prev_shaping[fc] = 1;
+        reward += c->term_weight[t] * v;
+    }
+    return reward;
+}
+
 /* get_metric x9 (fixed_wing.py:1644-1736) computed from the full histories exactly as the reference does */
 static void compute_metrics(FwoEnv* e) {
     const FwConfig* c = &e->cfg;
@@ -927,6 +1011,7 @@ void fwo_reset(FwoEnv* e, const double* state, const double* target, const doubl
     for (int i = 0; i < 3; ++i) e->h_omega[i] = e->omega[i];
     e->n_act = 0; e->n_cmd = 0; e->n_err = 0; e->n_goal = 0; e->act_is_f32 = 0;
     e->n_st = 0; e->n_tgt = 0;
+    for (int k = 0; k < 3; ++k) { e->prev_shaping[k] = 0; e->has_prev_shaping[k] = 0; }
     push_state_history(e);          /* Variable.reset: history = [value] (pyfly.py:89-104) */
     e->ep_return = 0; e->term_code = 0;
     /* sample_target, then injected targets override (fixed_wing.py:443-450) */
@@ -964,7 +1049,7 @@ void fwo_step(FwoEnv* e, const double action[3], int action_is_f32, double obs[F
     double rew;
     if (c->steps_max > 0 && e->steps_count >= c->steps_max) { d = 1; tc = FW_TERM_STEPS; }
     if (!fail) {
-        int resample = 0;
+        int resample = 0, success_on_step = 0;
         if (c->streak_req > 0) {
             goal_status(e, e->goal_hist + (size_t)e->n_goal * 4);
             e->n_goal++;
@@ -972,12 +1057,14 @@ void fwo_step(FwoEnv* e, const double action[3], int action_is_f32, double obs[F
                 int cnt = 0;
                 for (int t = e->n_goal - c->streak_req; t < e->n_goal; ++t) cnt += e->goal_hist[t * 4 + 3];
                 if ((double)cnt / c->streak_req >= c->streak_fraction) {
+                    success_on_step = !e->goal_achieved;     /* fixed_wing.py:546-547 */
+                    e->goal_achieved = 1;
                     if (c->on_success == FW_SUCCESS_DONE) { d = 1; tc = FW_TERM_SUCCESS; }
                     else if (c->on_success == FW_SUCCESS_NEW) resample = 1;
                 }
             }
         }
-        rew = get_reward(e, action);
+        rew = c->rew_generic ? get_reward_generic(e, action, success_on_step) : get_reward(e, action);
         if (resample || (c->resample_every > 0 && e->steps_for_target >= c->resample_every)) {
             double u3[3];
             for (int k = 0; k < 3; ++k) {

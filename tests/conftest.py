@@ -80,3 +80,46 @@ def cnn_env_config():
                    {"name": "aileron", "type": "action", "window_size": 5},
                    {"name": "throttle", "type": "action", "window_size": 5}]}
     return cfg
+
+
+def rich_reward_env_config():
+    """The config of tests/golden/make_golden.py:gen_reward: potential form, three terms, every factor class."""
+    import importlib.util
+    from tum_adlr_deep_reinforcement_learning_b200.config import default_env_config
+    cfg = default_env_config()
+    cfg["reward"] = RICH_REWARD
+    cfg["steps_max"] = 80
+    cfg["target"]["success_streak_req"] = 6
+    cfg["target"]["success_streak_fraction"] = 0.5
+    for s_, b in zip(cfg["target"]["states"], (60, 40, 12)):
+        s_["bound"] = b
+    return cfg
+
+
+RICH_REWARD = {
+    "form": "potential", "randomize_scaling": False, "step_fail": -50,
+    "terms": [{"function_class": "linear", "weight": 1.0}, {"function_class": "exponential", "weight": 0.5},
+              {"function_class": "quadratic", "weight": 0.1}],
+    "factors": [
+        {"name": "roll", "class": "state", "type": "error", "function_class": "linear", "scaling": 3.2,
+         "shaping": True, "max": 0.3, "sign": -1},
+        {"name": "pitch", "class": "state", "type": "error", "function_class": "exponential", "scaling": 2.0,
+         "shaping": True, "sign": -1},
+        {"name": "Va", "class": "state", "type": "error", "function_class": "quadratic", "scaling": 100,
+         "shaping": False, "sign": -1},
+        {"name": "omega_q", "class": "state", "type": "value", "function_class": "quadratic", "scaling": 50,
+         "shaping": True, "sign": -1},
+        {"name": "action", "class": "action", "type": "value", "function_class": "linear", "scaling": 30,
+         "shaping": False, "sign": -1},
+        {"name": "action", "class": "action", "type": "delta", "function_class": "linear", "window_size": 3,
+         "scaling": 60, "shaping": False, "sign": -1},
+        {"name": "action_bound", "class": "action", "type": "bound", "function_class": "linear", "scaling": 1,
+         "shaping": False, "sign": -1},
+        {"name": "success", "class": "success", "value": "timesteps", "function_class": "linear", "scaling": 100,
+         "shaping": False, "sign": 1},
+        {"name": "step", "class": "step", "value": 1, "function_class": "linear", "scaling": 10, "shaping": False,
+         "sign": -1},
+        {"name": "goal", "class": "goal", "type": "per_state", "value": 0.3, "function_class": "linear",
+         "scaling": 1, "shaping": False, "sign": 1},
+        {"name": "goal_all", "class": "goal", "type": "all", "value": 1.0, "function_class": "exponential",
+         "scaling": 4, "shaping": False, "sign": 1}]}

@@ -266,6 +266,57 @@ def gen_cnn():
     np.savez_compressed(os.path.join(HERE, "traj_cnn_obs.npz"), **out)
 
 
+RICH_REWARD = {
+    "form": "potential", "randomize_scaling": False, "step_fail": -50,
+    "terms": [{"function_class": "linear", "weight": 1.0}, {"function_class": "exponential", "weight": 0.5},
+              {"function_class": "quadratic", "weight": 0.1}],
+    "factors": [
+        {"name": "roll", "class": "state", "type": "error", "function_class": "linear", "scaling": 3.2,
+         "shaping": True, "max": 0.3, "sign": -1},
+        {"name": "pitch", "class": "state", "type": "error", "function_class": "exponential", "scaling": 2.0,
+         "shaping": True, "sign": -1},
+        {"name": "Va", "class": "state", "type": "error", "function_class": "quadratic", "scaling": 100,
+         "shaping": False, "sign": -1},
+        {"name": "omega_q", "class": "state", "type": "value", "function_class": "quadratic", "scaling": 50,
+         "shaping": True, "sign": -1},
+        {"name": "action", "class": "action", "type": "value", "function_class": "linear", "scaling": 30,
+         "shaping": False, "sign": -1},
+        {"name": "action", "class": "action", "type": "delta", "function_class": "linear", "window_size": 3,
+         "scaling": 60, "shaping": False, "sign": -1},
+        {"name": "action_bound", "class": "action", "type": "bound", "function_class": "linear", "scaling": 1,
+         "shaping": False, "sign": -1},
+        {"name": "success", "class": "success", "value": "timesteps", "function_class": "linear", "scaling": 100,
+         "shaping": False, "sign": 1},
+        {"name": "step", "class": "step", "value": 1, "function_class": "linear", "scaling": 10, "shaping": False,
+         "sign": -1},
+        {"name": "goal", "class": "goal", "type": "per_state", "value": 0.3, "function_class": "linear",
+         "scaling": 1, "shaping": False, "sign": 1},
+        {"name": "goal_all", "class": "goal", "type": "all", "value": 1.0, "function_class": "exponential",
+         "scaling": 4, "shaping": False, "sign": 1}]}
+
+
+def gen_reward():
+    """A config that exercises the whole reward engine (fixed_wing.py:941-1111): potential form, three terms, every
+    factor class; wide goal bounds and a short streak so that goals and the one-off success bonus fire."""
+    import tempfile
+    cfg = json.load(open(refshim.GYM_CONFIG))
+    cfg["reward"] = RICH_REWARD
+    cfg["steps_max"] = 80
+    cfg["target"]["success_streak_req"] = 6
+    cfg["target"]["success_streak_fraction"] = 0.5
+    for s_, b in zip(cfg["target"]["states"], (60, 40, 12)):
+        s_["bound"] = b
+    with tempfile.NamedTemporaryFile("w", suffix=".json", delete=False) as f:
+        json.dump(cfg, f)
+    env = make_env(False, config_path=f.name)
+    rs = np.random.RandomState(4242)
+    out = run_episodes(env, 5, 80, rs, False, wind_mag=3.0, action_amp=1.8)
+    np.savez_compressed(os.path.join(HERE, "traj_reward_rich.npz"), **out)
+    rs = np.random.RandomState(4243)
+    out = run_episodes(env, 3, 80, rs, False, wind_mag=3.0, action_amp=1.8, f32_actions=True)
+    np.savez_compressed(os.path.join(HERE, "traj_reward_rich_f32.npz"), **out)
+
+
 def gen_pid(max_scen=100, num_envs=6):
     """Lock-step emulation of examples/evaluate_controller.py:57-232 (use_pid=True) with `num_envs` env slots.
 
@@ -411,7 +462,7 @@ def gen_dryden():
 
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
-    jobs = {"cnn": gen_cnn, "params": gen_params, "traj": gen_traj, "turb": gen_turb, "fail": gen_fail, "full": gen_full,
+    jobs = {"reward": gen_reward, "cnn": gen_cnn, "params": gen_params, "traj": gen_traj, "turb": gen_turb, "fail": gen_fail, "full": gen_full,
             "pid": gen_pid, "gae": gen_gae, "dryden": gen_dryden}
     for name, fn in jobs.items():
         if what in (name, "all"):

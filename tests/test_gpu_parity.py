@@ -188,3 +188,41 @@ def test_general_observation_layout_cnn_config(cuda_device):
         assert np.array_equal(env.done.cpu().numpy(), d_ref)
         assert _rel(env.obs64.cpu().numpy(), o_ref).max() < RTOL_F64, t
     env.close()
+
+
+def test_general_reward_engine(cuda_device):
+    """The general reward engine on the CUDA path: (a) the live-reference fixture replayed on a ONE-env handle across
+    episodes (goal_achieved persists like in the reference), (b) 1024 envs with auto-reset against the oracle."""
+    import torch
+    from conftest import rich_reward_env_config
+    from oracle import fw_oracle as O
+    from tum_adlr_deep_reinforcement_learning_b200 import batched as bt
+    from tum_adlr_deep_reinforcement_learning_b200.config import build_config
+    cfg = build_config(env_cfg=rich_reward_env_config(), sim_config_kw={"turbulence": False})
+    env = bt.BatchedFixedWing(1, cfg=cfg)
+    env.enable_f64_outputs()
+    for name, f32 in (("traj_reward_rich", False), ("traj_reward_rich_f32", True)):
+        g = load_golden(name)
+        for ep in range(g["actions"].shape[0]):
+            env.reset(state=g["init_state"][ep:ep + 1], target=g["init_target"][ep:ep + 1])
+            for t in range(int(g["n_valid"][ep])):
+                a = torch.as_tensor(g["actions"][ep:ep + 1, t], dtype=torch.float32 if f32 else torch.float64).cuda()
+                env.step(a.contiguous(), auto_reset=False)
+                r = float(env.rew64.cpu().numpy()[0])
+                assert abs(r - g["reward"][ep, t]) < 1e-9 * max(1.0, abs(g["reward"][ep, t])), (name, ep, t)
+    env.close()
+    cfg = build_config(env_cfg=rich_reward_env_config(), sim_config_kw={"turbulence": True}, seed=21)
+    n = 1024
+    env = bt.BatchedFixedWing(n, cfg=cfg)
+    env.enable_f64_outputs()
+    env.reset()
+    ob = O.OracleBatch(cfg, n)
+    ob.reset()
+    rs = np.random.RandomState(8)
+    for t in range(170):                      # > 2 episodes of 80 steps: prev_shaping / goal_achieved across resets
+        a = rs.uniform(-1.6, 1.6, (n, 3)).astype(np.float32)
+        env.step(torch.as_tensor(a).cuda(), auto_reset=True)
+        o_ref, r_ref, d_ref = ob.step(a)
+        assert np.array_equal(env.done.cpu().numpy(), d_ref), t
+        assert _rel(env.rew64.cpu().numpy(), r_ref).max() < RTOL_F64, t
+    env.close()

@@ -172,3 +172,21 @@ def test_oracle_general_observation_layout_cnn_config():
             obs, rew, done, term = env.step(g["actions"][ep, t])
             assert _rel(obs, g["obs"][ep, t]).max() < 1e-9, (ep, t)
             assert abs(rew - g["reward"][ep, t]) < 1e-9 and done == bool(g["done"][ep, t])
+
+
+def test_oracle_general_reward_engine():
+    """Potential-form reward with three terms and every factor class (tests/golden/make_golden.py:gen_reward), f64 and
+    float32 actions.  ONE env object across all episodes, like the fixture run: `goal_achieved` is never cleared by
+    reset (fixed_wing.py:81), so the success bonus fires once in the env's lifetime."""
+    from conftest import rich_reward_env_config
+    cfg = build_config(env_cfg=rich_reward_env_config(), sim_config_kw={"turbulence": False})
+    assert cfg.rew_generic == 1 and cfg.rew_n == 11 and cfg.rew_potential == 1
+    env = O.OracleEnv(cfg)
+    for name, f32 in (("traj_reward_rich", False), ("traj_reward_rich_f32", True)):
+        g = load_golden(name)
+        for ep in range(g["actions"].shape[0]):
+            env.reset(g["init_state"][ep], g["init_target"][ep])
+            for t in range(int(g["n_valid"][ep])):
+                obs, rew, done, term = env.step(g["actions"][ep, t], f32)
+                assert abs(rew - g["reward"][ep, t]) < 1e-9 * max(1.0, abs(g["reward"][ep, t])), (name, ep, t)
+                assert done == bool(g["done"][ep, t])

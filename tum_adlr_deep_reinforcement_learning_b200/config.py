@@ -20,7 +20,7 @@ import numpy as np
 
 _DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
 
-FW_ABI_VERSION = 3
+FW_ABI_VERSION = 4
 FW_NY, FW_NOBS, FW_NACT, FW_NSTATE_INJECT, FW_NMETRIC = 19, 14, 3, 21, 28
 FW_F64, FW_F32 = 0, 1
 FW_INT_RK45_SCIPY, FW_INT_RK4_FIXED = 0, 1
@@ -71,6 +71,10 @@ class FwConfig(ctypes.Structure):
            ("rew_bound_scaling", _d), ("rew_bound_max", _d), ("rew_delta_window", _i), ("obs_act_window", _i),
            ("step_fail_timesteps", _i), ("_pad2", _i), ("step_fail_value", _d), ("rise_low", _d), ("rise_high", _d),
            ("obs_noise_mean", _d), ("obs_noise_std", _d),
+           ("rew_generic", _i), ("rew_n", _i), ("rew_potential", _i), ("rew_nterms", _i),
+           ("rew_class", _i * 12), ("rew_idx", _i * 12), ("rew_fclass", _i * 12), ("rew_shaping", _i * 12),
+           ("rew_window", _i * 12), ("rew_value_timesteps", _i * 12), ("rew_scaling", _d * 12), ("rew_maxv", _d * 12),
+           ("rew_sign", _d * 12), ("rew_value", _d * 12), ("term_fclass", _i * 4), ("term_weight", _d * 4),
            ("obs_generic", _i), ("obs_len", _i), ("obs_n", _i), ("obs_normalize", _i),
            ("obs_kind", _i * 16), ("obs_idx", _i * 16), ("obs_window", _i * 16), ("obs_norm_flag", _i * 16),
            ("obs_mean", _d * 16), ("obs_var", _d * 16), ("obs_init_noise", _d),
@@ -403,28 +407,84 @@ def build_config(env_cfg=None, sim_cfg=None, config_kw=None, sim_config_kw=None,
     c.streak_fraction = float(tgt["success_streak_fraction"])
     c.resample_every = int(tgt.get("resample_every", 0) or 0)
     rew = env["reward"]
-    if rew.get("form", "absolute") != "absolute" or len(rew["terms"]) != 1 or rew["terms"][0]["weight"] != 1 \
-            or rew["terms"][0]["function_class"] != "linear":
-        raise NotImplementedError("reward form/terms other than one absolute linear term (SURVEY §8f row 1)")
+    fn_id = {"linear": 0, "exponential": 1, "quadratic": 2}
+    state_names = {"roll": 0, "pitch": 1, "Va": 2, "omega_p": 3, "omega_q": 4, "omega_r": 5, "alpha": 6, "beta": 7}
     for k in range(3):
         c.rew_err_scaling[k], c.rew_err_max[k] = 0.0, np.inf
     c.rew_delta_scaling = c.rew_bound_scaling = 0.0
     c.rew_delta_max = c.rew_bound_max = np.inf
     c.rew_delta_window = 5
+    default_family = (rew.get("form", "absolute") == "absolute" and len(rew["terms"]) == 1
+                      and rew["terms"][0]["weight"] == 1 and rew["terms"][0]["function_class"] == "linear")
+    seen = set()
     for f in rew["factors"]:
-        if f["function_class"] != "linear" or f.get("sign", -1) >= 0:
-            raise NotImplementedError("reward factor %r" % (f,))
-        mx = f.get("max")
-        mx = np.inf if mx is None else float(mx)
-        if f["class"] == "state" and f["type"] == "error":
-            k = TARGET_STATES.index(f["name"])
-            c.rew_err_scaling[k], c.rew_err_max[k] = float(f["scaling"]), mx
-        elif f["class"] == "action" and f["type"] == "delta":
-            c.rew_delta_scaling, c.rew_delta_max, c.rew_delta_window = float(f["scaling"]), mx, int(f["window_size"])
-        elif f["class"] == "action" and f["type"] == "bound":
-            c.rew_bound_scaling, c.rew_bound_max = float(f["scaling"]), mx
-        else:
-            raise NotImplementedError("reward factor %r" % (f,))
+        key = (f["class"], f.get("type"), f.get("name"))
+        simple = f["function_class"] == "linear" and f.get("sign", -1) < 0 and key not in seen and (
+            (f["class"] == "state" and f.get("type") == "error" and f.get("name") in TARGET_STATES)
+            or (f["class"] == "action" and f.get("type") in ("delta", "bound")))
+        if f["class"] == "action":
+            key = (f["class"], f.get("type"), None)
+            simple = simple and key not in seen
+        seen.add(key)
+        default_family = default_family and simple
+    c.rew_generic = int(not default_family)
+    if default_family:
+        for f in rew["factors"]:
+            mx = f.get("max")
+            mx = np.inf if mx is None else float(mx)
+            if f["class"] == "state":
+                k = TARGET_STATES.index(f["name"])
+                c.rew_err_scaling[k], c.rew_err_max[k] = float(f["scaling"]), mx
+            elif f["type"] == "delta":
+                c.rew_delta_scaling, c.rew_delta_max, c.rew_delta_window = float(f["scaling"]), mx, int(f["window_size"])
+            else:
+                c.rew_bound_scaling, c.rew_bound_max = float(f["scaling"]), mx
+    else:
+        # the general engine of fixed_wing.py:941-1111
+        if len(rew["factors"]) > 12 or len(rew["terms"]) > 3:
+            raise NotImplementedError("more than 12 reward factors / 3 terms")
+        c.rew_potential = int(rew.get("form", "absolute") == "potential")
+        c.rew_nterms = len(rew["terms"])
+        term_classes = []
+        for t, term in enumerate(rew["terms"]):
+            c.term_fclass[t], c.term_weight[t] = fn_id[term["function_class"]], float(term["weight"])
+            term_classes.append(term["function_class"])
+        c.rew_n = len(rew["factors"])
+        for i, f in enumerate(rew["factors"]):
+            if f["function_class"] not in term_classes:
+                raise KeyError("reward factor %r uses function_class %r that has no term" % (f.get("name"), f["function_class"]))
+            cls, typ = f["class"], f.get("type")
+            c.rew_fclass[i] = fn_id[f["function_class"]]
+            c.rew_scaling[i] = float(f["scaling"])
+            c.rew_maxv[i] = np.inf if f.get("max") is None else float(f["max"])
+            c.rew_shaping[i] = int(bool(f.get("shaping", False)))
+            c.rew_sign[i] = float(np.sign(f.get("sign", -1)))
+            c.rew_window[i] = int(f.get("window_size", 0) or 0)
+            if cls == "state" and typ == "error":
+                c.rew_class[i], c.rew_idx[i] = 0, TARGET_STATES.index(f["name"])
+            elif cls == "state" and typ == "value":
+                if f["name"] not in state_names:
+                    raise NotImplementedError("reward on state %r" % f["name"])
+                c.rew_class[i], c.rew_idx[i] = 1, state_names[f["name"]]
+            elif cls == "action" and typ == "value":
+                c.rew_class[i] = 2
+            elif cls == "action" and typ == "delta":
+                c.rew_class[i] = 3
+                if c.rew_window[i] > 5:
+                    raise NotImplementedError("reward action-delta window > 5")
+                c.rew_delta_window = max(c.rew_delta_window, c.rew_window[i])
+            elif cls == "action" and typ == "bound":
+                c.rew_class[i] = 4
+            elif cls == "success":
+                c.rew_class[i] = 5
+                c.rew_value_timesteps[i] = int(f["value"] == "timesteps")
+                c.rew_value[i] = 0.0 if f["value"] == "timesteps" else float(f["value"])
+            elif cls == "step":
+                c.rew_class[i], c.rew_value[i] = 6, float(f["value"])
+            elif cls == "goal" and typ in ("per_state", "all"):
+                c.rew_class[i], c.rew_value[i] = (7 if typ == "per_state" else 8), float(f["value"])
+            else:
+                raise NotImplementedError("reward factor %r" % (f,))
     fail = rew.get("step_fail", 0)
     c.step_fail_timesteps = int(fail == "timesteps")
     c.step_fail_value = 0.0 if fail == "timesteps" else float(fail)

@@ -103,6 +103,12 @@ template <typename T> struct DCfg {
     T tgt_low[3], tgt_high[3], tgt_delta[3], tgt_bound[3], streak_fraction;
     T rew_err_scaling[3], rew_err_max[3], rew_delta_scaling, rew_delta_max, rew_bound_scaling, rew_bound_max;
     T step_fail_value, rise_low, rise_high, obs_noise_mean, obs_noise_std;
+    int rew_generic, rew_n, rew_potential, rew_nterms;
+    int rew_class[FW_REW_FACTORS_MAX], rew_idx[FW_REW_FACTORS_MAX], rew_fclass[FW_REW_FACTORS_MAX];
+    int rew_shaping[FW_REW_FACTORS_MAX], rew_window[FW_REW_FACTORS_MAX], rew_value_timesteps[FW_REW_FACTORS_MAX];
+    T rew_scaling[FW_REW_FACTORS_MAX], rew_maxv[FW_REW_FACTORS_MAX], rew_sign[FW_REW_FACTORS_MAX], rew_value[FW_REW_FACTORS_MAX];
+    int term_fclass[4];
+    T term_weight[4];
     int obs_generic, obs_len, obs_n, obs_normalize;
     int obs_kind[FW_OBS_ENTRIES_MAX], obs_idx[FW_OBS_ENTRIES_MAX], obs_window[FW_OBS_ENTRIES_MAX], obs_norm_flag[FW_OBS_ENTRIES_MAX];
     T obs_mean[FW_OBS_ENTRIES_MAX], obs_var[FW_OBS_ENTRIES_MAX], obs_init_noise;
@@ -130,7 +136,8 @@ enum RField {
     RF_HIST = 90,             // 4 x 14
     RF_GACT = 146,            // 8 x 3
     RF_GCMD = 170,            // 8 x 3
-    RF_COUNT = 194
+    RF_PREV_SHAPING = 194,    // 3: prev_shaping per function class of the general reward engine (NaN = None)
+    RF_COUNT = 197
 };
 enum IField {
     IF_STEPS = 0, IF_STEPS_TGT, IF_EPISODE, IF_SIM_STEP,
@@ -141,7 +148,8 @@ enum IField {
     IF_RISE_LO = 32,          // 3 first index t with |e_t| >= low_lim and |e_{t+1}| < low_lim (-1 = none)
     IF_RISE_HI = 35,          // 3
     IF_NFEV = 38, IF_NATT = 39, IF_TERM = 40, IF_EP_LEN = 41, IF_ACT_F32 = 42,
-    IF_COUNT = 43
+    IF_GOAL_ACHIEVED = 43,    // self.goal_achieved: set by the first success, never cleared (fixed_wing.py:81, 546-547)
+    IF_COUNT = 44
 };
 
 template <typename T> struct Soa {
@@ -620,6 +628,92 @@ __device__ __forceinline__ void write_obs(const T* o, int dim, int env, float* o
     if (obs64) for (int j = 0; j < dim; ++j) obs64[(size_t)env * dim + j] = (double)o[j];
 }
 
+// get_reward (fixed_wing.py:941-1111), the general engine: any list of factors with linear / exponential / quadratic
+// function classes, shaping and plain parts per term, absolute or potential form.  Out of line: the default factor
+// family has its own straight-line code in the head kernel.
+template <typename T>
+__device__ __noinline__ T generic_reward(const DCfg<T>& c, const Soa<T>& S, int env, const T (&eg)[3], const T (&st8)[8],
+                                         const T (&a_raw)[3], bool act_f32, const T* aring, int n_prev, int steps,
+                                         const int (&gbits)[4], bool success) {
+    const int n = S.n;
+    T val_t[3] = {0, 0, 0}, shp_t[3] = {0, 0, 0};
+#pragma unroll 1
+    for (int i = 0; i < c.rew_n; ++i) {
+        T val = 0;
+        const int cls = c.rew_class[i];
+        if (cls == FW_RF_STATE_ERROR) val = eg[c.rew_idx[i]];
+        else if (cls == FW_RF_STATE_VALUE) val = st8[c.rew_idx[i]];
+        else if (cls == FW_RF_ACTION_VALUE) {
+            if (act_f32) { float sa = 0.f; for (int j = 0; j < 3; ++j) sa += fabsf((float)a_raw[j]); val = (T)sa; }
+            else for (int j = 0; j < 3; ++j) val += M<T>::fabs(a_raw[j]);
+        } else if (cls == FW_RF_ACTION_DELTA) {
+            if (steps > 1) {
+                const int np_ = (c.rew_window[i] - 1) < n_prev ? (c.rew_window[i] - 1) : n_prev;
+                if (act_f32) {
+                    float d[12];
+                    int m = 0;
+                    for (int age = np_; age >= 1; --age)
+                        for (int j = 0; j < 3; ++j) {
+                            const T newer = (age == 1) ? a_raw[j] : aring[(age - 2) * 3 + j];
+                            d[m++] = fabsf((float)newer - (float)aring[(age - 1) * 3 + j]);
+                        }
+                    val = (T)np_sum<float>(d, m);
+                } else {
+                    T d[12];
+                    int m = 0;
+                    for (int age = np_; age >= 1; --age)
+                        for (int j = 0; j < 3; ++j) {
+                            const T newer = (age == 1) ? a_raw[j] : aring[(age - 2) * 3 + j];
+                            d[m++] = M<T>::fabs(newer - aring[(age - 1) * 3 + j]);
+                        }
+                    val = np_sum<T>(d, m);
+                }
+            }
+        } else if (cls == FW_RF_ACTION_BOUND) {
+            T hi = 0, lo = 0;
+            for (int j = 0; j < 3; ++j) {
+                if (a_raw[j] > c.action_bounds_max[j]) hi += M<T>::fabs(a_raw[j] - c.action_bounds_max[j]);
+                if (a_raw[j] < c.action_bounds_min[j]) lo += M<T>::fabs(a_raw[j] - c.action_bounds_min[j]);
+            }
+            val = hi + lo;
+        } else if (cls == FW_RF_SUCCESS) {
+            val = success ? (c.rew_value_timesteps[i] ? (T)(c.steps_max - steps) : c.rew_value[i]) : (T)0;
+        } else if (cls == FW_RF_STEP) val = c.rew_value[i];
+        else if (cls == FW_RF_GOAL_PER_STATE) {
+            for (int k = 0; k < 3; ++k) val += gbits[k] ? c.rew_value[i] / (T)3 : (T)0;
+        } else if (cls == FW_RF_GOAL_ALL) val = gbits[3] ? c.rew_value[i] : (T)0;
+        // values derived from a float32 action array stay float32 through the function class
+        const bool f32v = act_f32 && (cls == FW_RF_ACTION_DELTA || cls == FW_RF_ACTION_VALUE);
+        const int fc = c.rew_fclass[i];
+        if (fc == FW_FN_LINEAR) {
+            if (f32v) val = (T)fminf(fmaxf(fabsf((float)val) / (float)c.rew_scaling[i], 0.f), (float)c.rew_maxv[i]);
+            else val = clip(M<T>::fabs(val) / c.rew_scaling[i], (T)0, c.rew_maxv[i]);
+        } else if (f32v) val = (T)(((float)val * (float)val) / (float)c.rew_scaling[i]);
+        else val = val * val / c.rew_scaling[i];
+        if (c.rew_shaping[i]) shp_t[fc] += val * c.rew_sign[i];
+        else val_t[fc] += val * c.rew_sign[i];
+    }
+    T reward = 0;
+#pragma unroll 1
+    for (int t = 0; t < c.rew_nterms; ++t) {
+        const int fc = c.term_fclass[t];
+        const T prev = S.r[(RF_PREV_SHAPING + fc) * n + env];
+        const bool has_prev = !M<T>::isnan(prev);
+        T v;
+        if (fc == FW_FN_EXPONENTIAL) {
+            if (c.rew_potential) v = has_prev ? (T)-1 + M<T>::exp(val_t[fc] + (shp_t[fc] - prev)) : (T)-1 + M<T>::exp(val_t[fc]);
+            else v = (T)-1 + M<T>::exp(val_t[fc] + shp_t[fc]);
+        } else {
+            v = val_t[fc];
+            if (c.rew_potential) { if (has_prev) v += shp_t[fc] - prev; }
+            else v += shp_t[fc];
+        }
+        S.r[(RF_PREV_SHAPING + fc) * n + env] = shp_t[fc];
+        reward += c.term_weight[t] * v;
+    }
+    return reward;
+}
+
 // General observation layout (fixed_wing.py:1113-1262): obs_len rows, newest first; row i reads `.history[-i]` of the
 // states, targets and errors, clamped to the start of the episode (then the row gets the `init_noise` offset
 // U(-1,1) * dt, one draw per row, fixed_wing.py:1142-1145), action entries sum |diff| over a window of raw actions (or
@@ -805,6 +899,8 @@ __device__ void reset_env(const DCfg<T>& c, const Soa<T>& S, int env, const doub
         gbits[3] &= gbits[k];
     }
     r[RF_EP_RET * n] = 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) r[(RF_PREV_SHAPING + k) * n] = M<T>::nan();
     ii[IF_STEPS * n] = 0; ii[IF_STEPS_TGT * n] = 0; ii[IF_EPISODE * n] = (int32_t)episode; ii[IF_SIM_STEP * n] = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {

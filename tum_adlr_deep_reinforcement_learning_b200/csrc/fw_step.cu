@@ -482,7 +482,7 @@ __global__ void __launch_bounds__(128, 4) head_kernel(const __grid_constant__ DC
     if (!fail) {
         // goal status with the CURRENT target (fixed_wing.py:536-560)
         const T eg[3] = {err_roll(tgt[0], roll), tgt[1] - pitch, tgt[2] - Va};
-        bool resample = false;
+        bool resample = false, success_on_step = false;
         if (c.streak_req > 0) {
             gbits[3] = 1;
 #pragma unroll
@@ -503,12 +503,20 @@ __global__ void __launch_bounds__(128, 4) head_kernel(const __grid_constant__ DC
                     (double)gcnt[k] / (double)c.streak_req >= (double)c.streak_fraction) settle[k] = idx;
             }
             if (steps_tgt >= c.streak_req && (double)gcnt[3] / (double)c.streak_req >= (double)c.streak_fraction) {
+                if (c.rew_generic) {                       // goal_achieved_on_step (fixed_wing.py:546-547)
+                    success_on_step = ii[IF_GOAL_ACHIEVED * n] == 0;
+                    ii[IF_GOAL_ACHIEVED * n] = 1;
+                }
                 if (c.on_success == FW_SUCCESS_DONE) { done = true; term = FW_TERM_SUCCESS; }
                 else if (c.on_success == FW_SUCCESS_NEW) resample = true;
             }
         }
         // reward (fixed_wing.py:941-1111, default factor family)
         T val = 0;
+        if (c.rew_generic) {
+            const T st8[8] = {roll, pitch, Va, y[4], y[5], y[6], alpha, beta};
+            val = generic_reward<T>(c, S, env, eg, st8, a_raw, act_f32, aring, n_prev, steps, gbits, success_on_step);
+        } else {
 #pragma unroll
         for (int k = 0; k < 3; ++k)
             if (c.rew_err_scaling[k] > (T)0) val -= clip(M<T>::fabs(eg[k]) / c.rew_err_scaling[k], (T)0, c.rew_err_max[k]);
@@ -545,6 +553,7 @@ __global__ void __launch_bounds__(128, 4) head_kernel(const __grid_constant__ DC
                 if (a_raw[j] < c.action_bounds_min[j]) lo += M<T>::fabs(a_raw[j] - c.action_bounds_min[j]);
             }
             val -= clip(M<T>::fabs(hi + lo) / c.rew_bound_scaling, (T)0, c.rew_bound_max);
+        }
         }
         reward = val;
         // target resample / advance (fixed_wing.py:569-580, 1363-1471)
@@ -866,6 +875,13 @@ template <typename T> static void convert_cfg(const FwConfig& f, DCfg<T>& d) {
     }
     CP(streak_fraction); CP(rew_delta_scaling); CP(rew_delta_max); CP(rew_bound_scaling); CP(rew_bound_max);
     CP(step_fail_value); CP(rise_low); CP(rise_high); CP(obs_noise_mean); CP(obs_noise_std); CP(obs_init_noise);
+    d.rew_generic = f.rew_generic; d.rew_n = f.rew_n; d.rew_potential = f.rew_potential; d.rew_nterms = f.rew_nterms;
+    for (int k = 0; k < FW_REW_FACTORS_MAX; ++k) {
+        d.rew_class[k] = f.rew_class[k]; d.rew_idx[k] = f.rew_idx[k]; d.rew_fclass[k] = f.rew_fclass[k];
+        d.rew_shaping[k] = f.rew_shaping[k]; d.rew_window[k] = f.rew_window[k]; d.rew_value_timesteps[k] = f.rew_value_timesteps[k];
+        CP(rew_scaling[k]); CP(rew_maxv[k]); CP(rew_sign[k]); CP(rew_value[k]);
+    }
+    for (int k = 0; k < 4; ++k) { d.term_fclass[k] = f.term_fclass[k]; CP(term_weight[k]); }
     d.obs_generic = f.obs_generic; d.obs_len = f.obs_len; d.obs_n = f.obs_n; d.obs_normalize = f.obs_normalize;
     for (int k = 0; k < FW_OBS_ENTRIES_MAX; ++k) {
         d.obs_kind[k] = f.obs_kind[k]; d.obs_idx[k] = f.obs_idx[k]; d.obs_window[k] = f.obs_window[k];
