@@ -519,17 +519,19 @@ template <typename T> struct EnvRegs {
 
 // The six Dryden shaping filters have fixed orders (dryden.py:126-143): H_u 1, H_v 2, H_w 2, H_p 1, H_q 3, H_r 3,
 // so their states pack into fx[12] at offsets 0,1,3,5,6,9 and every loop below has a compile-time trip count.
-template <typename T, int ORD, int OFF>
+// The noise row of each filter is fixed too (dryden.py:238-252: u<-0, v<-1, w<-2, p<-3, q<-1, r<-2): a compile-time
+// index keeps fu / un in registers (a runtime index put them in local memory: 8 % of the head kernel's stall samples).
+template <typename T, int ORD, int OFF, int ROW>
 __device__ __forceinline__ T filt_out(const DFilter<T>& F, const T (&fx)[12], const T (&fu)[4]) {
     T yv = 0;
 #pragma unroll
     for (int a = 0; a < ORD; ++a) yv += fx[OFF + a] * F.C[a];
-    return yv + fu[F.noise_row & 3] * F.D;
+    return yv + fu[ROW] * F.D;
 }
-template <typename T, int ORD, int OFF>
+template <typename T, int ORD, int OFF, int ROW>
 __device__ __forceinline__ void filt_adv(const DFilter<T>& F, T (&fx)[12], const T (&fu)[4], const T (&un)[4]) {
     T xn[ORD];
-    const T up = fu[F.noise_row & 3], uc = un[F.noise_row & 3];
+    const T up = fu[ROW], uc = un[ROW];
 #pragma unroll
     for (int a = 0; a < ORD; ++a) {
         T sacc = 0;
@@ -543,22 +545,22 @@ __device__ __forceinline__ void filt_adv(const DFilter<T>& F, T (&fx)[12], const
 // y = C x + D u  (lsim output equation, dryden.py:22-39)
 template <typename T>
 __device__ __forceinline__ void turb_eval(const DCfg<T>& c, const T (&fx)[12], const T (&fu)[4], T (&tl)[3], T (&ta)[3]) {
-    tl[0] = filt_out<T, 1, 0>(c.filt[0], fx, fu);
-    tl[1] = filt_out<T, 2, 1>(c.filt[1], fx, fu);
-    tl[2] = filt_out<T, 2, 3>(c.filt[2], fx, fu);
-    ta[0] = filt_out<T, 1, 5>(c.filt[3], fx, fu);
-    ta[1] = filt_out<T, 3, 6>(c.filt[4], fx, fu);
-    ta[2] = filt_out<T, 3, 9>(c.filt[5], fx, fu);
+    tl[0] = filt_out<T, 1, 0, 0>(c.filt[0], fx, fu);
+    tl[1] = filt_out<T, 2, 1, 1>(c.filt[1], fx, fu);
+    tl[2] = filt_out<T, 2, 3, 2>(c.filt[2], fx, fu);
+    ta[0] = filt_out<T, 1, 5, 3>(c.filt[3], fx, fu);
+    ta[1] = filt_out<T, 3, 6, 1>(c.filt[4], fx, fu);
+    ta[2] = filt_out<T, 3, 9, 2>(c.filt[5], fx, fu);
 }
 // x_{k+1} = Ad x_k + Bd0 u_k + Bd1 u_{k+1}  (lsim recurrence, row-vector convention)
 template <typename T>
 __device__ __forceinline__ void turb_advance(const DCfg<T>& c, T (&fx)[12], T (&fu)[4], const T (&un)[4]) {
-    filt_adv<T, 1, 0>(c.filt[0], fx, fu, un);
-    filt_adv<T, 2, 1>(c.filt[1], fx, fu, un);
-    filt_adv<T, 2, 3>(c.filt[2], fx, fu, un);
-    filt_adv<T, 1, 5>(c.filt[3], fx, fu, un);
-    filt_adv<T, 3, 6>(c.filt[4], fx, fu, un);
-    filt_adv<T, 3, 9>(c.filt[5], fx, fu, un);
+    filt_adv<T, 1, 0, 0>(c.filt[0], fx, fu, un);
+    filt_adv<T, 2, 1, 1>(c.filt[1], fx, fu, un);
+    filt_adv<T, 2, 3, 2>(c.filt[2], fx, fu, un);
+    filt_adv<T, 1, 5, 3>(c.filt[3], fx, fu, un);
+    filt_adv<T, 3, 6, 1>(c.filt[4], fx, fu, un);
+    filt_adv<T, 3, 9, 2>(c.filt[5], fx, fu, un);
 #pragma unroll
     for (int r = 0; r < 4; ++r) fu[r] = un[r];
 }

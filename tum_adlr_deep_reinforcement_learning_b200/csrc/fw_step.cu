@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(128, 3) rk45_init_kernel(const __grid_constant
 
 // ---- kernel A1: the attempt loop, persistent lanes pulling envs from a queue ----
 template <typename T, bool TURB, int NT>
-__global__ void __maxnreg__(224) rk45_attempt_kernel(const __grid_constant__ DCfg<T> c, const Soa<T> S,
+__global__ void __maxnreg__(255) rk45_attempt_kernel(const __grid_constant__ DCfg<T> c, const Soa<T> S,
                                                           const Scratch<T> W) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* K = reinterpret_cast<T*>(smem_raw) + threadIdx.x;
@@ -985,6 +985,12 @@ int fw_obs_dim(const FwHandle* h) { return h ? (h->cfg.obs_generic ? h->cfg.obs_
 int fw_create(const FwConfig* cfg, int32_t n_envs, int32_t device, FwHandle** out) {
     if (!cfg || !out || n_envs <= 0) { snprintf(g_err, sizeof(g_err), "fw_create: bad arguments"); return FW_EINVAL; }
     if (cfg->abi_version != FW_ABI_VERSION) { snprintf(g_err, sizeof(g_err), "fw_create: ABI version mismatch"); return FW_EINVAL; }
+    static const int kNoiseRow[6] = {0, 1, 2, 3, 1, 2}, kOrder[6] = {1, 2, 2, 1, 3, 3};
+    for (int f = 0; f < 6; ++f)
+        if (cfg->turbulence && (cfg->filt[f].noise_row != kNoiseRow[f] || cfg->filt[f].order != kOrder[f])) {
+            snprintf(g_err, sizeof(g_err), "fw_create: Dryden filter %d must have order %d and noise row %d", f, kOrder[f], kNoiseRow[f]);
+            return FW_EINVAL;
+        }
     if (cfg->streak_req > 128 || cfg->rew_delta_window > 5 || cfg->steps_max <= 0 ||
         (!cfg->obs_generic && cfg->obs_act_window > 5) ||
         (cfg->obs_generic && (cfg->obs_len < 1 || cfg->obs_len > FW_OBS_LEN_MAX || cfg->obs_n < 1 || cfg->obs_n > FW_OBS_ENTRIES_MAX ||
