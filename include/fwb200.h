@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define FW_ABI_VERSION 4
+#define FW_ABI_VERSION 5
 
 #define FW_NY 19        /* ODE state: quat[4] omega[3] pos[3] vel[3] act_value[3] act_rate[3]  (pyfly.py:1372-1389) */
 #define FW_NOBS 14      /* default observation vector (fixed_wing_config.json "observation.states")               */
@@ -75,7 +75,7 @@ enum FwRewFunction { FW_FN_LINEAR = 0, FW_FN_EXPONENTIAL = 1, FW_FN_QUADRATIC = 
 enum FwObsKind { FW_OBS_STATE = 0, FW_OBS_TARGET_ABS = 1, FW_OBS_TARGET_REL = 2, FW_OBS_ACTION = 3 };
 enum FwObsState { FW_S_ROLL = 0, FW_S_PITCH, FW_S_VA, FW_S_OMEGA_P, FW_S_OMEGA_Q, FW_S_OMEGA_R, FW_S_ALPHA, FW_S_BETA };
 
-enum FwTargetClass { FW_TGT_CONSTANT = 0, FW_TGT_COMPENSATE = 1 };   /* fixed_wing.py:1375-1431 */
+enum FwTargetClass { FW_TGT_CONSTANT = 0, FW_TGT_COMPENSATE = 1, FW_TGT_LINEAR = 2, FW_TGT_SINUSOIDAL = 3 };   /* fixed_wing.py:1375-1452 */
 enum FwOnSuccess { FW_SUCCESS_NONE = 0, FW_SUCCESS_DONE = 1, FW_SUCCESS_NEW = 2 }; /* fixed_wing.py:548-553 */
 
 /* Layout of the per-env metric row written when an episode ends (fixed_wing.py:1644-1736). NaN = numpy nan. */
@@ -148,6 +148,12 @@ typedef struct FwConfig {
     double tgt_delta[3];                  /* NaN = no delta */
     double tgt_bound[3];                  /* goal bounds */
     int32_t tgt_class[3];                 /* FwTargetClass */
+    int32_t tgt_radians[3];               /* convert_to_radians of the target state (slope / amplitude are converted AFTER sampling) */
+    double tgt_slope_low[3], tgt_slope_high[3];          /* class linear (fixed_wing.py:699-707), per second */
+    double tgt_amp_low[3], tgt_amp_high[3];              /* class sinusoidal (fixed_wing.py:710-727) */
+    double tgt_period_low[3], tgt_period_high[3];        /* in steps (250, 500 by default) */
+    double rng_u_override;                /* finite: every uniform draw of target sampling returns this value instead
+                                             of the Philox stream (parity tests against a patched reference RNG) */
     int32_t on_success;                   /* FwOnSuccess */
     int32_t streak_req;                   /* target.success_streak_req (<=128) */
     int32_t resample_every;

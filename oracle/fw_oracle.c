@@ -60,6 +60,8 @@ typedef struct FwoEnv {
     /* ---- gym env ---- */
     int steps_count, steps_for_target;
     double target[3];
+    int tcls[3];                  /* _target_props[k]["class"] (an injected target forces constant, fixed_wing.py:446-450) */
+    double t_slope[3], t_amp[3], t_period[3], t_phase[3], t_bias[3];
     double* act_hist;  int n_act;  int act_is_f32;   /* history["action"], raw */
     double* cmd_hist;  int n_cmd;                    /* elevator/aileron/throttle .history["command"], [t][3] */
     double* err_hist;  int n_err;                    /* history["error"], [t][3] */
@@ -563,18 +565,46 @@ static void goal_status(const FwoEnv* e, uint8_t g[4]) {
     for (int k = 0; k < 3; ++k) { g[k] = fabs(get_error(e, k)) <= e->cfg.tgt_bound[k]; g[3] &= g[k]; }
 }
 
-/* sample_target (fixed_wing.py:654-746) for constant / compensate classes; u3 = three U[0,1) draws */
-static void sample_target(FwoEnv* e, const double u3[3]) {
+/* sample_target (fixed_wing.py:654-746).  u12: four U[0,1) draws per target state in the order the reference consumes
+ * them (initial value; slope, sign | amplitude, period, phase). */
+static void sample_target(FwoEnv* e, const double u12[12]) {
     const FwConfig* c = &e->cfg;
     double val[3] = {e->roll, e->pitch, e->Va};
     e->steps_for_target = 0;
     for (int k = 0; k < 3; ++k) {
+        const double* u = u12 + 4 * k;
         double low = c->tgt_low[k], high = c->tgt_high[k];
         if (!isnan(c->tgt_delta[k])) {
             low = fmax(low, val[k] - c->tgt_delta[k]);
             high = fmax(fmin(high, val[k] + c->tgt_delta[k]), low);
         }
-        e->target[k] = low + (high - low) * u3[k];   /* RandomState.uniform: low + (high-low)*random_sample() */
+        const double initial = low + (high - low) * u[0];   /* RandomState.uniform: low + (high-low)*random_sample() */
+        e->tcls[k] = c->tgt_class[k];
+        if (c->tgt_class[k] == FW_TGT_LINEAR) {
+            double slope = c->tgt_slope_low[k] + (c->tgt_slope_high[k] - c->tgt_slope_low[k]) * u[1];
+            if (u[2] < 0.5) slope *= -1;
+            if (c->tgt_radians[k]) slope = slope * (M_PI / 180.0);
+            e->t_slope[k] = slope;
+        } else if (c->tgt_class[k] == FW_TGT_SINUSOIDAL) {
+            double amp = c->tgt_amp_low[k] + (c->tgt_amp_high[k] - c->tgt_amp_low[k]) * u[1];
+            if (c->tgt_radians[k]) amp = amp * (M_PI / 180.0);
+            const double period = c->tgt_period_low[k] + (c->tgt_period_high[k] - c->tgt_period_low[k]) * u[2];
+            const double phase = (0 + (2 * M_PI - 0) * u[3]) / (2 * M_PI / period);
+            e->t_amp[k] = amp; e->t_period[k] = period; e->t_phase[k] = phase;
+            e->t_bias[k] = initial - amp * sin(2 * M_PI / period * (e->steps_count + phase));
+        }
+        e->target[k] = initial;
+    }
+}
+
+/* the twelve draws of one target sampling: Philox (purpose, block base) or the test override */
+static void target_draws(const FwoEnv* e, uint32_t purpose, uint32_t block0, double u12[12]) {
+    const FwConfig* c = &e->cfg;
+    for (int i = 0; i < 12; ++i) {
+        if (!isnan(c->rng_u_override)) { u12[i] = c->rng_u_override; continue; }
+        uint32_t r[4];
+        rng_block(c->seed, e->env_id, e->episode, purpose, block0 + (uint32_t)(i >> 1), r);
+        u12[i] = (i & 1) ? u53(r[2], r[3]) : u53(r[0], r[1]);
     }
 }
 
@@ -582,8 +612,14 @@ static void sample_target(FwoEnv* e, const double u3[3]) {
 static void next_target(FwoEnv* e) {
     const FwConfig* c = &e->cfg;
     double res[3] = {e->target[0], e->target[1], e->target[2]};
-    if (c->tgt_class[2] == FW_TGT_COMPENSATE) {
-        double pitch_tar = e->target[1], va_target = e->target[2];
+    for (int k = 0; k < 3; ++k) {
+        if (e->tcls[k] == FW_TGT_LINEAR) res[k] = e->target[k] + e->t_slope[k] * c->dt;
+        else if (e->tcls[k] == FW_TGT_SINUSOIDAL)
+            res[k] = e->t_amp[k] * sin(2 * M_PI / e->t_period[k] * (e->steps_count + e->t_phase[k])) + e->t_bias[k];
+    }
+    if (e->tcls[2] == FW_TGT_COMPENSATE) {
+        /* pitch target seen by the Va law: the target itself, or the bias of a sinusoidal one (:1381-1384) */
+        double pitch_tar = (e->tcls[1] == FW_TGT_SINUSOIDAL) ? e->t_bias[1] : e->target[1], va_target = e->target[2];
         if (pitch_tar <= -2.5 * (M_PI / 180.0)) {
             double va_end = 28.434 - 40.0841 * pitch_tar, slope;
             if (va_target <= va_end) {
@@ -1015,10 +1051,13 @@ void fwo_reset(FwoEnv* e, const double* state, const double* target, const doubl
     push_state_history(e);          /* Variable.reset: history = [value] (pyfly.py:89-104) */
     e->ep_return = 0; e->term_code = 0;
     /* sample_target, then injected targets override (fixed_wing.py:443-450) */
-    double u3[3];
-    for (int k = 0; k < 3; ++k) u3[k] = rng_uniform(e, FWO_RNG_RESET, 15 + k);
-    sample_target(e, u3);
-    if (target) for (int k = 0; k < 3; ++k) if (!isnan(target[k])) e->target[k] = target[k];
+    double u12[12];
+    target_draws(e, FWO_RNG_RESET, 8, u12);          /* blocks 8..13 of the reset stream (0..7: state and wind) */
+    sample_target(e, u12);
+    if (target) for (int k = 0; k < 3; ++k) if (!isnan(target[k])) {
+        if (e->tcls[k] != FW_TGT_CONSTANT && e->tcls[k] != FW_TGT_COMPENSATE) e->tcls[k] = FW_TGT_CONSTANT;
+        e->target[k] = target[k];
+    }
     get_observation(e, obs);
     for (int k = 0; k < 3; ++k) { e->err_hist[k] = get_error(e, k); e->tgt_hist[k] = e->target[k]; }
     e->n_err = 1; e->n_tgt = 1;
@@ -1066,13 +1105,9 @@ void fwo_step(FwoEnv* e, const double action[3], int action_is_f32, double obs[F
         }
         rew = c->rew_generic ? get_reward_generic(e, action, success_on_step) : get_reward(e, action);
         if (resample || (c->resample_every > 0 && e->steps_for_target >= c->resample_every)) {
-            double u3[3];
-            for (int k = 0; k < 3; ++k) {
-                uint32_t r[4];
-                rng_block(c->seed, e->env_id, e->episode, FWO_RNG_RESAMPLE, (uint32_t)(e->steps_count * 2 + (k >> 1)), r);
-                u3[k] = (k & 1) ? u53(r[2], r[3]) : u53(r[0], r[1]);
-            }
-            sample_target(e, u3);
+            double u12[12];
+            target_draws(e, FWO_RNG_RESAMPLE, (uint32_t)(e->steps_count * 8), u12);
+            sample_target(e, u12);
         }
         next_target(e);
         for (int k = 0; k < 3; ++k) {

@@ -123,3 +123,19 @@ RICH_REWARD = {
          "scaling": 1, "shaping": False, "sign": 1},
         {"name": "goal_all", "class": "goal", "type": "all", "value": 1.0, "function_class": "exponential",
          "scaling": 4, "shaping": False, "sign": 1}]}
+
+
+MOVING_TARGETS = [
+    {"name": "roll", "convert_to_radians": True, "low": -60, "high": 60, "delta": 180, "class": "linear",
+     "slope_low": 2, "slope_high": 8, "bound": 5},
+    {"name": "pitch", "convert_to_radians": True, "low": -25, "high": 25, "delta": 45, "class": "sinusoidal",
+     "amplitude_low": 3, "amplitude_high": 9, "period_low": 60, "period_high": 140, "bound": 5},
+    {"name": "Va", "low": 15, "high": 28, "delta": 6, "class": "compensate", "bound": 2}]
+
+
+def moving_targets_env_config():
+    from tum_adlr_deep_reinforcement_learning_b200.config import default_env_config
+    cfg = default_env_config()
+    cfg["target"]["states"] = MOVING_TARGETS
+    cfg["steps_max"] = 150
+    return cfg

@@ -295,6 +295,56 @@ RICH_REWARD = {
          "scaling": 4, "shaping": False, "sign": 1}]}
 
 
+class FixedDrawsU(FixedDraws):
+    def __init__(self, u):
+        self.u = u
+
+    def uniform(self, low=0.0, high=1.0):
+        return low + self.u * (high - low)
+
+
+MOVING_TARGETS = [
+    {"name": "roll", "convert_to_radians": True, "low": -60, "high": 60, "delta": 180, "class": "linear",
+     "slope_low": 2, "slope_high": 8, "bound": 5},
+    {"name": "pitch", "convert_to_radians": True, "low": -25, "high": 25, "delta": 45, "class": "sinusoidal",
+     "amplitude_low": 3, "amplitude_high": 9, "period_low": 60, "period_high": 140, "bound": 5},
+    {"name": "Va", "low": 15, "high": 28, "delta": 6, "class": "compensate", "bound": 2}]
+
+
+def gen_targets():
+    """Target classes linear / sinusoidal (+ Va compensate on a sinusoidal pitch target), fixed_wing.py:698-727,
+    1438-1452.  Targets are NOT injected (an injected target forces class constant, :446-450): the env-level RNG is
+    replaced by fixed draws u, and the same u is fed to our side through FwConfig.rng_u_override."""
+    import tempfile
+    cfg = json.load(open(refshim.GYM_CONFIG))
+    cfg["target"]["states"] = MOVING_TARGETS
+    cfg["steps_max"] = 150
+    with tempfile.NamedTemporaryFile("w", suffix=".json", delete=False) as f:
+        json.dump(cfg, f)
+    out = {}
+    for tag, u in (("a", 0.625), ("b", 0.3)):
+        env = make_env(False, config_path=f.name)
+        env.np_random = FixedDrawsU(u)
+        rs = np.random.RandomState(int(u * 1000))
+        rec = {k: [] for k in ("init_state", "actions", "target", "obs", "reward", "obs0", "target0")}
+        for ep in range(3):
+            st, _ = random_scenario(rs, 3.0)
+            obs0 = env.reset(state=dict(st))
+            rec["init_state"].append(scenario_arrays(st, {"roll": 0, "pitch": 0, "Va": 0})[0])
+            rec["obs0"].append(np.array(obs0))
+            rec["target0"].append([env.target[k] for k in TARGET_KEYS])
+            A, Tg, Ob, Rw = [], [], [], []
+            for t in range(150):
+                a = rs.uniform(-1.0, 1.0, 3)
+                obs, rew, done, info = env.step(a)
+                A.append(a), Tg.append([env.target[k] for k in TARGET_KEYS]), Ob.append(np.array(obs)), Rw.append(rew)
+            for k, v in (("actions", A), ("target", Tg), ("obs", Ob), ("reward", Rw)):
+                rec[k].append(np.array(v))
+        out.update({tag + "_" + k: np.array(v) for k, v in rec.items()})
+        out[tag + "_u"] = u
+    np.savez_compressed(os.path.join(HERE, "traj_moving_targets.npz"), **out)
+
+
 def gen_reward():
     """A config that exercises the whole reward engine (fixed_wing.py:941-1111): potential form, three terms, every
     factor class; wide goal bounds and a short streak so that goals and the one-off success bonus fire."""
@@ -462,7 +512,7 @@ def gen_dryden():
 
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
-    jobs = {"reward": gen_reward, "cnn": gen_cnn, "params": gen_params, "traj": gen_traj, "turb": gen_turb, "fail": gen_fail, "full": gen_full,
+    jobs = {"targets": gen_targets, "reward": gen_reward, "cnn": gen_cnn, "params": gen_params, "traj": gen_traj, "turb": gen_turb, "fail": gen_fail, "full": gen_full,
             "pid": gen_pid, "gae": gen_gae, "dryden": gen_dryden}
     for name, fn in jobs.items():
         if what in (name, "all"):

@@ -226,3 +226,49 @@ def test_general_reward_engine(cuda_device):
         assert np.array_equal(env.done.cpu().numpy(), d_ref), t
         assert _rel(env.rew64.cpu().numpy(), r_ref).max() < RTOL_F64, t
     env.close()
+
+
+def test_moving_target_classes(cuda_device):
+    """linear / sinusoidal targets on the CUDA path: the live-reference fixture (fixed draws), then Philox sampling with
+    on_success = "new" resampling against the oracle."""
+    import copy
+    import torch
+    from conftest import moving_targets_env_config
+    from oracle import fw_oracle as O
+    from tum_adlr_deep_reinforcement_learning_b200 import batched as bt
+    from tum_adlr_deep_reinforcement_learning_b200.config import build_config
+    g = load_golden("traj_moving_targets")
+    for tag in ("a", "b"):
+        cfg = build_config(env_cfg=moving_targets_env_config(), sim_config_kw={"turbulence": False},
+                           rng_u_override=float(g[tag + "_u"]))
+        env = bt.BatchedFixedWing(3, cfg=cfg)
+        env.enable_f64_outputs()
+        env.reset(state=g[tag + "_init_state"])
+        assert np.abs(env.get_field(bt.FIELD_TARGET).cpu().numpy() - g[tag + "_target0"]).max() < 1e-12
+        for t in range(150):
+            env.step(torch.as_tensor(g[tag + "_actions"][:, t]).cuda().contiguous(), auto_reset=False)
+            assert _rel(env.get_field(bt.FIELD_TARGET).cpu().numpy(), g[tag + "_target"][:, t]).max() < 1e-11, (tag, t)
+            assert _rel(env.obs64.cpu().numpy(), g[tag + "_obs"][:, t]).max() < RTOL_F64
+            assert _rel(env.rew64.cpu().numpy(), g[tag + "_reward"][:, t]).max() < RTOL_F64
+        env.close()
+    ecfg = copy.deepcopy(moving_targets_env_config())
+    ecfg["steps_max"] = 60
+    ecfg["target"].update(on_success="new", success_streak_req=5, success_streak_fraction=0.6)
+    for s_, b in zip(ecfg["target"]["states"], (80, 50, 15)):
+        s_["bound"] = b
+    cfg = build_config(env_cfg=ecfg, sim_config_kw={"turbulence": True}, seed=77)
+    n = 512
+    env = bt.BatchedFixedWing(n, cfg=cfg)
+    env.enable_f64_outputs()
+    env.reset()
+    ob = O.OracleBatch(cfg, n)
+    assert _rel(env.obs64.cpu().numpy(), ob.reset()).max() < 1e-12
+    rs = np.random.RandomState(5)
+    for t in range(130):
+        a = rs.uniform(-1.0, 1.0, (n, 3)).astype(np.float32)
+        env.step(torch.as_tensor(a).cuda(), auto_reset=True)
+        o_ref, r_ref, d_ref = ob.step(a)
+        assert np.array_equal(env.done.cpu().numpy(), d_ref), t
+        assert _rel(env.obs64.cpu().numpy(), o_ref).max() < RTOL_F64, t
+        assert _rel(env.rew64.cpu().numpy(), r_ref).max() < RTOL_F64, t
+    env.close()

@@ -190,3 +190,24 @@ def test_oracle_general_reward_engine():
                 obs, rew, done, term = env.step(g["actions"][ep, t], f32)
                 assert abs(rew - g["reward"][ep, t]) < 1e-9 * max(1.0, abs(g["reward"][ep, t])), (name, ep, t)
                 assert done == bool(g["done"][ep, t])
+
+
+def test_oracle_moving_target_classes():
+    """Target classes linear / sinusoidal with Va compensate on a sinusoidal pitch target, against a live-reference run
+    whose env-level RNG was replaced by fixed draws u (tests/golden/make_golden.py:gen_targets)."""
+    from conftest import moving_targets_env_config
+    g = load_golden("traj_moving_targets")
+    for tag in ("a", "b"):
+        cfg = build_config(env_cfg=moving_targets_env_config(), sim_config_kw={"turbulence": False},
+                           rng_u_override=float(g[tag + "_u"]))
+        assert list(cfg.tgt_class) == [2, 3, 1]
+        for ep in range(3):
+            env = O.OracleEnv(cfg)
+            obs = env.reset(g[tag + "_init_state"][ep])
+            assert np.abs(env.get()["target"] - g[tag + "_target0"][ep]).max() < 1e-12
+            assert np.abs(obs - g[tag + "_obs0"][ep]).max() < 1e-12
+            for t in range(150):
+                obs, rew, done, term = env.step(g[tag + "_actions"][ep, t])
+                assert _rel(env.get()["target"], g[tag + "_target"][ep, t]).max() < 1e-11, (tag, ep, t)
+                assert _rel(obs, g[tag + "_obs"][ep, t]).max() < 1e-9
+                assert abs(rew - g[tag + "_reward"][ep, t]) < 1e-9

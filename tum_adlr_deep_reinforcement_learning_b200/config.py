@@ -20,7 +20,7 @@ import numpy as np
 
 _DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
 
-FW_ABI_VERSION = 4
+FW_ABI_VERSION = 5
 FW_NY, FW_NOBS, FW_NACT, FW_NSTATE_INJECT, FW_NMETRIC = 19, 14, 3, 21, 28
 FW_F64, FW_F32 = 0, 1
 FW_INT_RK45_SCIPY, FW_INT_RK4_FIXED = 0, 1
@@ -65,7 +65,9 @@ class FwConfig(ctypes.Structure):
            ("act_lo", _d * 3), ("act_hi", _d * 3), ("has_action_bounds", _i), ("_pad1", _i),
            ("action_bounds_min", _d * 3), ("action_bounds_max", _d * 3),
            ("tgt_low", _d * 3), ("tgt_high", _d * 3), ("tgt_delta", _d * 3), ("tgt_bound", _d * 3),
-           ("tgt_class", _i * 3), ("on_success", _i), ("streak_req", _i), ("resample_every", _i),
+           ("tgt_class", _i * 3), ("tgt_radians", _i * 3), ("tgt_slope_low", _d * 3), ("tgt_slope_high", _d * 3),
+           ("tgt_amp_low", _d * 3), ("tgt_amp_high", _d * 3), ("tgt_period_low", _d * 3), ("tgt_period_high", _d * 3),
+           ("rng_u_override", _d), ("on_success", _i), ("streak_req", _i), ("resample_every", _i),
            ("streak_fraction", _d),
            ("rew_err_scaling", _d * 3), ("rew_err_max", _d * 3), ("rew_delta_scaling", _d), ("rew_delta_max", _d),
            ("rew_bound_scaling", _d), ("rew_bound_max", _d), ("rew_delta_window", _i), ("obs_act_window", _i),
@@ -276,7 +278,7 @@ def dryden_filters(sim_length, sim_dt, wingspan, intensity="light", spec=False):
 
 def build_config(env_cfg=None, sim_cfg=None, config_kw=None, sim_config_kw=None, params=None,
                  curriculum_level=1.0, precision="f64", integrator="rk45", rk4_substeps=4, rtol=1e-3, atol=1e-6,
-                 seed=0, env_id_offset=0, dryden_spec=False, obs_init_noise=None):
+                 seed=0, env_id_offset=0, dryden_spec=False, obs_init_noise=None, rng_u_override=None):
     """Flatten reference-format configs into an `FwConfig`.  `env_cfg` / `sim_cfg`: dict or JSON path (defaults above)."""
     def load(x, default):
         if x is None:
@@ -397,9 +399,22 @@ def build_config(env_cfg=None, sim_cfg=None, config_kw=None, sim_config_kw=None,
         c.tgt_delta[k] = np.nan if delta is None else delta
         c.tgt_bound[k] = np.inf if bound is None else bound
         cls = s.get("class", "constant")
-        if cls not in ("constant", "compensate"):
+        if cls not in ("constant", "compensate", "linear", "sinusoidal"):
             raise NotImplementedError("target class %r (SURVEY §8f 'next' row 1)" % cls)
-        c.tgt_class[k] = 1 if cls == "compensate" else 0
+        if cls == "compensate" and name != "Va":
+            raise NotImplementedError("target class compensate is only defined for Va (fixed_wing.py:1432-1435)")
+        c.tgt_class[k] = {"constant": 0, "compensate": 1, "linear": 2, "sinusoidal": 3}[cls]
+        c.tgt_radians[k] = int(bool(rad))
+        if cls == "linear":
+            c.tgt_slope_low[k], c.tgt_slope_high[k] = cur("slope_low", s["slope_low"]), cur("slope_high", s["slope_high"])
+        if cls == "sinusoidal":
+            c.tgt_amp_low[k] = cur("amplitude_low", s["amplitude_low"])
+            c.tgt_amp_high[k] = cur("amplitude_high", s["amplitude_high"])
+            c.tgt_period_low[k] = cur("period_low", s["period_low"]) if s.get("period_low") is not None else 250.0
+            c.tgt_period_high[k] = cur("period_high", s["period_high"]) if s.get("period_high") is not None else 500.0
+    if c.tgt_class[2] == 1 and c.tgt_class[1] not in (0, 2, 3):
+        raise NotImplementedError("Va compensate needs a constant / linear / sinusoidal pitch target")
+    c.rng_u_override = float("nan") if rng_u_override is None else float(rng_u_override)
     c.on_success = {"none": 0, "done": 1, "new": 2}[tgt.get("on_success", "none")]
     c.streak_req = int(tgt["success_streak_req"])
     if c.streak_req > 128:

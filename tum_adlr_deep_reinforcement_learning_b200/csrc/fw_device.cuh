@@ -101,6 +101,9 @@ template <typename T> struct DCfg {
     DFilter<T> filt[6];
     T scale_low, scale_high, act_lo[3], act_hi[3], action_bounds_min[3], action_bounds_max[3];
     T tgt_low[3], tgt_high[3], tgt_delta[3], tgt_bound[3], streak_fraction;
+    int tgt_radians[3], tgt_moving;     // tgt_moving: some target class is linear / sinusoidal
+    T tgt_slope_low[3], tgt_slope_high[3], tgt_amp_low[3], tgt_amp_high[3], tgt_period_low[3], tgt_period_high[3];
+    T rng_u_override;
     T rew_err_scaling[3], rew_err_max[3], rew_delta_scaling, rew_delta_max, rew_bound_scaling, rew_bound_max;
     T step_fail_value, rise_low, rise_high, obs_noise_mean, obs_noise_std;
     int rew_generic, rew_n, rew_potential, rew_nterms;
@@ -137,7 +140,8 @@ enum RField {
     RF_GACT = 146,            // 8 x 3
     RF_GCMD = 170,            // 8 x 3
     RF_PREV_SHAPING = 194,    // 3: prev_shaping per function class of the general reward engine (NaN = None)
-    RF_COUNT = 197
+    RF_TPROP = 197,           // 15: slope3 amplitude3 period3 phase3 bias3 of moving targets (tgt_moving only)
+    RF_COUNT = 212
 };
 enum IField {
     IF_STEPS = 0, IF_STEPS_TGT, IF_EPISODE, IF_SIM_STEP,
@@ -148,8 +152,9 @@ enum IField {
     IF_RISE_LO = 32,          // 3 first index t with |e_t| >= low_lim and |e_{t+1}| < low_lim (-1 = none)
     IF_RISE_HI = 35,          // 3
     IF_NFEV = 38, IF_NATT = 39, IF_TERM = 40, IF_EP_LEN = 41, IF_ACT_F32 = 42,
+    IF_TCLS = 44,             // 3: per-env target class (an injected target forces constant, fixed_wing.py:446-450)
     IF_GOAL_ACHIEVED = 43,    // self.goal_achieved: set by the first success, never cleared (fixed_wing.py:81, 546-547)
-    IF_COUNT = 44
+    IF_COUNT = 47
 };
 
 template <typename T> struct Soa {
@@ -581,10 +586,29 @@ __device__ __forceinline__ void noise_sample(const DCfg<T>& c, const Soa<T>& S, 
     for (int r = 0; r < 4; ++r) un[r] = (T)z[r] * c.turb_noise_scale;
 }
 
-// sample_target (fixed_wing.py:654-746), constant / compensate classes
+// the twelve uniform draws of one target sampling, four per target state in the order the reference consumes them
+// (initial value; slope, sign | amplitude, period, phase): Philox blocks block0 .. block0+5 of `purpose`, or the override
 template <typename T>
-__device__ __forceinline__ void sample_target(const DCfg<T>& c, T roll, T pitch, T Va, const T u3[3], T tgt[3]) {
+__device__ __forceinline__ void target_draws(const DCfg<T>& c, long long gid, unsigned long long episode, uint32_t purpose,
+                                             uint32_t block0, T (&u12)[12]) {
+#pragma unroll
+    for (int b = 0; b < 6; ++b) {
+        const uint4 rr = rng_block(c.seed, gid, episode, purpose, block0 + (uint32_t)b);
+        u12[2 * b] = (T)u53(rr.x, rr.y);
+        u12[2 * b + 1] = (T)u53(rr.z, rr.w);
+    }
+    if (!M<T>::isnan(c.rng_u_override)) {
+#pragma unroll
+        for (int i = 0; i < 12; ++i) u12[i] = c.rng_u_override;
+    }
+}
+
+// sample_target (fixed_wing.py:654-746): classes constant / compensate / linear / sinusoidal
+template <typename T>
+__device__ __forceinline__ void sample_target(const DCfg<T>& c, T roll, T pitch, T Va, int steps, const T (&u12)[12],
+                                              T (&tgt)[3], int (&tcls)[3], T (&tp)[15]) {
     const T val[3] = {roll, pitch, Va};
+    const T TWO_PI = (T)6.283185307179586476925286766559, D2R = (T)(3.141592653589793238462643383279502884 / 180.0);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         T low = c.tgt_low[k], high = c.tgt_high[k];
@@ -592,7 +616,22 @@ __device__ __forceinline__ void sample_target(const DCfg<T>& c, T roll, T pitch,
             low = M<T>::fmax(low, val[k] - c.tgt_delta[k]);
             high = M<T>::fmax(M<T>::fmin(high, val[k] + c.tgt_delta[k]), low);
         }
-        tgt[k] = low + (high - low) * u3[k];
+        const T initial = low + (high - low) * u12[4 * k];
+        tcls[k] = c.tgt_class[k];
+        if (c.tgt_class[k] == FW_TGT_LINEAR) {
+            T slope = c.tgt_slope_low[k] + (c.tgt_slope_high[k] - c.tgt_slope_low[k]) * u12[4 * k + 1];
+            if (u12[4 * k + 2] < (T)0.5) slope *= (T)-1;
+            if (c.tgt_radians[k]) slope = slope * D2R;
+            tp[k] = slope;
+        } else if (c.tgt_class[k] == FW_TGT_SINUSOIDAL) {
+            T amp = c.tgt_amp_low[k] + (c.tgt_amp_high[k] - c.tgt_amp_low[k]) * u12[4 * k + 1];
+            if (c.tgt_radians[k]) amp = amp * D2R;
+            const T period = c.tgt_period_low[k] + (c.tgt_period_high[k] - c.tgt_period_low[k]) * u12[4 * k + 2];
+            const T phase = ((T)0 + (TWO_PI - (T)0) * u12[4 * k + 3]) / (TWO_PI / period);
+            tp[3 + k] = amp; tp[6 + k] = period; tp[9 + k] = phase;
+            tp[12 + k] = initial - amp * M<T>::sin(TWO_PI / period * ((T)steps + phase));
+        }
+        tgt[k] = initial;
     }
 }
 
@@ -863,15 +902,20 @@ __device__ void reset_env(const DCfg<T>& c, const Soa<T>& S, int env, const doub
 #pragma unroll
     for (int i = 0; i < 6; ++i) y[13 + i] = a6[i];
     // targets (fixed_wing.py:443-450)
-    T u3[3], tgt[3];
+    T u12[12], tgt[3], tp[15];
+    int tcls[3];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) u3[k] = rng_uniform<T>(c.seed, gid, episode, RNG_RESET, 15 + k);
-    sample_target(c, roll, pitch, Va, u3, tgt);
+    for (int k = 0; k < 15; ++k) tp[k] = 0;
+    target_draws<T>(c, gid, episode, RNG_RESET, 8u, u12);       // blocks 8..13 of the reset stream (0..7: state, wind)
+    sample_target<T>(c, roll, pitch, Va, 0, u12, tgt, tcls, tp);
     if (target_in) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             const double tv = target_in[(size_t)env * 3 + k];
-            if (!::isnan(tv)) tgt[k] = (T)tv;
+            if (!::isnan(tv)) {
+                if (tcls[k] != FW_TGT_CONSTANT && tcls[k] != FW_TGT_COMPENSATE) tcls[k] = FW_TGT_CONSTANT;
+                tgt[k] = (T)tv;
+            }
         }
     }
     // ---- store ----
@@ -903,6 +947,12 @@ __device__ void reset_env(const DCfg<T>& c, const Soa<T>& S, int env, const doub
     r[RF_EP_RET * n] = 0;
 #pragma unroll
     for (int k = 0; k < 3; ++k) r[(RF_PREV_SHAPING + k) * n] = M<T>::nan();
+    if (c.tgt_moving) {
+#pragma unroll
+        for (int k = 0; k < 15; ++k) r[(RF_TPROP + k) * n] = tp[k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) ii[(IF_TCLS + k) * n] = tcls[k];
+    }
     ii[IF_STEPS * n] = 0; ii[IF_STEPS_TGT * n] = 0; ii[IF_EPISODE * n] = (int32_t)episode; ii[IF_SIM_STEP * n] = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {

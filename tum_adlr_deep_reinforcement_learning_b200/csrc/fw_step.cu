@@ -557,18 +557,43 @@ __global__ void __launch_bounds__(128, 4) head_kernel(const __grid_constant__ DC
         }
         reward = val;
         // target resample / advance (fixed_wing.py:569-580, 1363-1471)
-        if (resample || (c.resample_every > 0 && steps_tgt >= c.resample_every)) {
-            T u3[3];
+        int tcls[3] = {c.tgt_class[0], c.tgt_class[1], c.tgt_class[2]};
+        T tp[15];
+        if (c.tgt_moving) {
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const uint4 rr = rng_block(c.seed, c.env_id_offset + env, episode, RNG_RESAMPLE, (uint32_t)(steps * 2 + (k >> 1)));
-                u3[k] = (T)((k & 1) ? u53(rr.z, rr.w) : u53(rr.x, rr.y));
-            }
-            sample_target(c, roll, pitch, Va, u3, tgt);
-            steps_tgt = 0;
+            for (int k = 0; k < 15; ++k) tp[k] = r[(RF_TPROP + k) * n];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) tcls[k] = ii[(IF_TCLS + k) * n];
         }
-        if (c.tgt_class[2] == FW_TGT_COMPENSATE) {
-            const T pitch_tar = tgt[1], va_t = tgt[2];
+        if (resample || (c.resample_every > 0 && steps_tgt >= c.resample_every)) {
+            T u12[12];
+            target_draws<T>(c, c.env_id_offset + env, episode, RNG_RESAMPLE, (uint32_t)(steps * 8), u12);
+            sample_target<T>(c, roll, pitch, Va, steps, u12, tgt, tcls, tp);
+            steps_tgt = 0;
+            if (c.tgt_moving) {
+#pragma unroll
+                for (int k = 0; k < 15; ++k) r[(RF_TPROP + k) * n] = tp[k];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) ii[(IF_TCLS + k) * n] = tcls[k];
+            }
+        }
+        const T tgt_pitch_cur = tgt[1];
+        if (c.tgt_moving) {
+            const T TWO_PI = (T)6.283185307179586476925286766559;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {          // roll, pitch (Va is constant or compensate)
+                if (tcls[k] == FW_TGT_LINEAR) tgt[k] = tgt[k] + tp[k] * c.dt;
+                else if (tcls[k] == FW_TGT_SINUSOIDAL)
+                    tgt[k] = tp[3 + k] * M<T>::sin(TWO_PI / tp[6 + k] * ((T)steps + tp[9 + k])) + tp[12 + k];
+            }
+            if (tcls[2] == FW_TGT_LINEAR) tgt[2] = tgt[2] + tp[2] * c.dt;
+            else if (tcls[2] == FW_TGT_SINUSOIDAL)
+                tgt[2] = tp[5] * M<T>::sin(TWO_PI / tp[8] * ((T)steps + tp[11])) + tp[14];
+        }
+        if (tcls[2] == FW_TGT_COMPENSATE) {
+            // the Va law sees the pitch target itself, or the bias of a sinusoidal one (fixed_wing.py:1381-1384); every
+            // new value is computed from the targets BEFORE this step's advance
+            const T pitch_tar = (c.tgt_moving && tcls[1] == FW_TGT_SINUSOIDAL) ? tp[13] : tgt_pitch_cur, va_t = tgt[2];
             const T D2R = (T)(3.141592653589793238462643383279502884 / 180.0);
             if (pitch_tar <= (T)-2.5 * D2R) {
                 const T va_end = (T)28.434 - (T)40.0841 * pitch_tar;
@@ -577,7 +602,7 @@ __global__ void __launch_bounds__(128, 4) head_kernel(const __grid_constant__ DC
                     const T s = (va_t < va_end * (T)0.95) ? (T)1 : (T)1 - va_t / (va_end * (T)1.5);
                     slope = (T)7 * M<T>::fmax((T)0, s);
                 }
-                tgt[2] = va_t + (slope * (-tgt[1]) - (T)0.25) * c.dt;
+                tgt[2] = va_t + (slope * (-tgt_pitch_cur) - (T)0.25) * c.dt;
             } else if (pitch_tar >= (T)5 * D2R) {
                 const T va_end = (T)26.27 - (T)41.2529 * pitch_tar;
                 if (va_t > va_end) tgt[2] = (steps_tgt < 750) ? va_t + (va_end - va_t) * (T)1 / (T)150 : va_end;
@@ -872,7 +897,11 @@ template <typename T> static void convert_cfg(const FwConfig& f, DCfg<T>& d) {
     for (int k = 0; k < 3; ++k) {
         CP(act_lo[k]); CP(act_hi[k]); CP(action_bounds_min[k]); CP(action_bounds_max[k]);
         CP(tgt_low[k]); CP(tgt_high[k]); CP(tgt_delta[k]); CP(tgt_bound[k]); CP(rew_err_scaling[k]); CP(rew_err_max[k]);
+        d.tgt_radians[k] = f.tgt_radians[k];
+        CP(tgt_slope_low[k]); CP(tgt_slope_high[k]); CP(tgt_amp_low[k]); CP(tgt_amp_high[k]); CP(tgt_period_low[k]); CP(tgt_period_high[k]);
+        if (f.tgt_class[k] == FW_TGT_LINEAR || f.tgt_class[k] == FW_TGT_SINUSOIDAL) d.tgt_moving = 1;
     }
+    CP(rng_u_override);
     CP(streak_fraction); CP(rew_delta_scaling); CP(rew_delta_max); CP(rew_bound_scaling); CP(rew_bound_max);
     CP(step_fail_value); CP(rise_low); CP(rise_high); CP(obs_noise_mean); CP(obs_noise_std); CP(obs_init_noise);
     d.rew_generic = f.rew_generic; d.rew_n = f.rew_n; d.rew_potential = f.rew_potential; d.rew_nterms = f.rew_nterms;
