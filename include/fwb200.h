@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define FW_ABI_VERSION 5
+#define FW_ABI_VERSION 7
 
 #define FW_NY 19        /* ODE state: quat[4] omega[3] pos[3] vel[3] act_value[3] act_rate[3]  (pyfly.py:1372-1389) */
 #define FW_NOBS 14      /* default observation vector (fixed_wing_config.json "observation.states")               */
@@ -66,6 +66,14 @@ enum FwIntegrator {
 
 enum FwPrecision { FW_F64 = 0, FW_F32 = 1 };
 
+/* which env head runs on top of the simulator */
+enum FwEnvKind {
+    FW_ENV_ATTITUDE = 0,   /* FixedWingAircraft (fixed-wing-gym/gym_fixed_wing/fixed_wing.py) */
+    FW_ENV_WAYPOINT = 1    /* FixedWingAircraft_simple (magpie/magpy/simple_train.py:197-702): fly through a chain of waypoints */
+};
+#define FW_WP_ROW 15          /* waypoint row: position n e d | roll pitch yaw | velocity u v w | wind n e d | omega p q r (NaN = sample) */
+#define FW_NOBS_WAYPOINT 12   /* roll pitch Va p q r elevon_left elevon_right throttle position n e d (simple_train.py:248-261) */
+
 /* observation entry kinds (fixed_wing.py:1149-1234) and the state indices an entry of kind STATE may name */
 /* general reward engine (fixed_wing.py:941-1111): factor classes/types and function classes */
 enum FwRewFactor { FW_RF_STATE_ERROR = 0, FW_RF_STATE_VALUE, FW_RF_ACTION_VALUE, FW_RF_ACTION_DELTA, FW_RF_ACTION_BOUND,
@@ -102,6 +110,8 @@ typedef struct FwFilter {
     double Bd1[3];
     double C[3];
     double D;
+    double Ablk[9];       /* expm(A^T * turb_block_len * dt_dryden): lsim restarts every block from t = T[0] > 0 by
+                             propagating the carried state over [0, T[0]] with zero input (scipy lsim; dryden.py:30-36) */
 } FwFilter;
 
 typedef struct FwConfig {
@@ -190,6 +200,14 @@ typedef struct FwConfig {
     double obs_init_noise;                /* rows older than the episode get += U(-1,1)*dt (fixed_wing.py:1142-1145);
                                              a finite value here replaces the Philox draw (parity tests) */
 
+    /* ---- env head selection and the waypoint head's constants (simple_train.py:236-300) ---- */
+    int32_t env_kind;                     /* FwEnvKind */
+    int32_t turb_block_len;               /* turbulence_sim_length: pyfly re-simulates the filters in blocks of this many
+                                             samples; the state carried into block m is multiplied by Ablk^m (pyfly.py:870-871,
+                                             dryden.py:193-261) */
+    double wp_goal_bound[3];              /* goal box on position n e d (0.5 m) */
+    double wp_rew_range[3];               /* reward = exp(-sum |err_k| / range_k) (6 m) */
+
     /* ---- counter-based RNG (Philox4x32-10) for auto-reset and turbulence noise ---- */
     uint64_t seed;
     int64_t env_id_offset;                /* global id of env 0 of this handle (sharding: rank*n_envs) */
@@ -202,6 +220,12 @@ typedef struct FwHandle FwHandle;
 int fw_create(const FwConfig* cfg, int32_t n_envs, int32_t device, FwHandle** out);
 int fw_destroy(FwHandle* h);
 int fw_obs_dim(const FwHandle* h);   /* floats per observation row of this handle */
+
+/* Waypoint head only: the task table.  tasks_dev [n_tasks, wp_len, FW_WP_ROW] f64 (device, copied), task_of_env_dev [n]
+ * int32 (device, copied): the task every env flies.  Replaces FixedWingAircraft_simple.sample_tasks / reset_task
+ * (simple_train.py:330-375).  Must be called before the first fw_reset. */
+int fw_set_waypoint_tasks(FwHandle* h, const double* tasks_dev, int32_t n_tasks, int32_t wp_len,
+                          const int32_t* task_of_env_dev, void* stream);
 const char* fw_last_error(void);
 int fw_abi_version(void);
 

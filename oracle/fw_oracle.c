@@ -70,6 +70,9 @@ typedef struct FwoEnv {
     double* tgt_hist;  int n_tgt;                    /* history["target"], [t][3] */
     double prev_shaping[3]; int has_prev_shaping[3];   /* self.prev_shaping per function class (None after reset) */
     int goal_achieved;                                /* self.goal_achieved: set once, never cleared by reset */
+    /* ---- waypoint head (simple_train.py:197-702) ---- */
+    const double* wp_tasks; int wp_n_tasks, wp_len, wp_task, wp_pos;   /* [n_tasks][wp_len][FW_WP_ROW], not owned */
+    double wp_goal[3];
     double ep_return;
     double metrics[FW_NMETRIC];
     int term_code;
@@ -506,7 +509,21 @@ void fwo_dryden(const FwConfig* c, const double* noise, int L, double* out) {
         int n = F->order;
         for (int i = 0; i < L; ++i) {
             double ui = u[i] * c->turb_noise_scale;
-            if (i > 0) {
+            /* pyfly simulates blocks of turbulence_sim_length samples; every new block calls lsim with T[0] > 0, which
+             * first steps the carried state over [0, T[0]] with zero input: x <- x expm(A^T T[0]) = x Ablk^m
+             * (pyfly.py:870-871, dryden.py:30-36, scipy lsim) */
+            const int block_start = c->turb_block_len > 0 && (i % c->turb_block_len) == 0;
+            if (i > 0 && block_start) {
+                for (int m = 0; m < i / c->turb_block_len; ++m) {
+                    for (int a = 0; a < n; ++a) {
+                        double sacc = 0;
+                        for (int b = 0; b < n; ++b) sacc += x[b] * F->Ablk[b * n + a];
+                        xn[a] = sacc;
+                    }
+                    for (int a = 0; a < n; ++a) x[a] = xn[a];
+                }
+            }
+            if (i > 0 && !block_start) {
                 double up = u[i - 1] * c->turb_noise_scale;
                 /* xout[i] = xout[i-1] @ Ad + U[i-1] @ Bd0 + U[i] @ Bd1   (row-vector convention) */
                 for (int a = 0; a < n; ++a) {
@@ -981,12 +998,114 @@ void fwo_destroy(FwoEnv* e) {
     free(e->st_hist); free(e->tgt_hist); free(e);
 }
 
+/* turbulence for the whole episode (pyfly.py:870-871 -> dryden.simulate) */
+static void gen_turbulence(FwoEnv* e, const double* noise, int noise_len) {
+    const FwConfig* c = &e->cfg;
+    if (!c->turbulence) return;
+    int L = e->turb_len;
+    double* nz = (double*)malloc(sizeof(double) * 4 * L);
+    for (int k = 0; k < L; ++k) {
+        double n4[4];
+        if (noise) for (int r = 0; r < 4; ++r) n4[r] = noise[(size_t)r * noise_len + (k < noise_len ? k : noise_len - 1)];
+        else fwo_noise4(c->seed, e->env_id, e->episode, (uint32_t)k, n4);
+        for (int r = 0; r < 4; ++r) nz[(size_t)r * L + k] = n4[r];
+    }
+    fwo_dryden(c, nz, L, e->turb);
+    free(nz);
+}
+
+/* ---------------- waypoint head: FixedWingAircraft_simple (magpie/magpy/simple_train.py:197-702) ---------------- */
+
+/* simulator.reset(state=waypoint) (simple_train.py:357-363 -> pyfly.py:1262-1311): position, attitude, velocity and wind
+ * from the waypoint; omega from the waypoint row or, if NaN, uniform in the pyfly init range; actuators at their (0, 0)
+ * init range; turbulence restarted with a fresh noise stream. */
+static void wp_sim_reset(FwoEnv* e, const double* row) {
+    const FwConfig* c = &e->cfg;
+    e->episode += 1;                     /* a fresh Philox segment for omega and the turbulence noise */
+    e->cur_sim_step = 0;
+    for (int i = 0; i < 3; ++i) { e->pos[i] = row[i]; e->vel[i] = row[6 + i]; e->wind[i] = row[9 + i]; }
+    e->roll = row[3]; e->pitch = row[4]; e->yaw = row[5];
+    for (int i = 0; i < 3; ++i)
+        e->omega[i] = isnan(row[12 + i]) ? c->init_lo[3 + i] + (c->init_hi[3 + i] - c->init_lo[3 + i]) * rng_uniform(e, FWO_RNG_RESET, 3 + i)
+                                         : row[12 + i];
+    double a6[6] = {0, 0, 0, 0, 0, 0};
+    set_actuators(e, a6);
+    e->elev = 0; e->ail = 0;
+    gen_turbulence(e, NULL, 0);
+    double R[3][3];
+    rot_euler(e->roll, e->pitch, e->yaw, R);
+    airspeed(e, R, e->vel, &e->Va, &e->alpha, &e->beta);
+    if (e->Va < c->va_value_min) e->Va = c->va_value_min;
+    double phi = e->roll, theta = e->pitch, psi = e->yaw;
+    double cps = cos(psi / 2), sps = sin(psi / 2), cth = cos(theta / 2), sth = sin(theta / 2);
+    double cph = cos(phi / 2), sph = sin(phi / 2);
+    e->quat[0] = cps * cth * cph + sps * sth * sph;
+    e->quat[1] = cps * cth * sph - sps * sth * cph;
+    e->quat[2] = cps * sth * cph + sps * cth * sph;
+    e->quat[3] = sps * cth * cph - cps * sth * sph;
+    e->n_cmd = 0;
+}
+
+static void wp_set_leg(FwoEnv* e) {      /* sample_target(id, pos): start = tasks[id][pos], goal = tasks[id][pos+1] */
+    const double* start = e->wp_tasks + ((size_t)e->wp_task * e->wp_len + e->wp_pos) * FW_WP_ROW;
+    wp_sim_reset(e, start);
+    for (int k = 0; k < 3; ++k) e->wp_goal[k] = start[FW_WP_ROW + k];
+}
+
+static void wp_observation(const FwoEnv* e, double* obs) {   /* simple_train.py:692-702: the states' .value */
+    obs[0] = e->roll; obs[1] = e->pitch; obs[2] = e->Va;
+    obs[3] = e->omega[0]; obs[4] = e->omega[1]; obs[5] = e->omega[2];
+    obs[6] = e->act_val[1]; obs[7] = e->act_val[0]; obs[8] = e->act_val[2];      /* elevon_left, elevon_right, throttle */
+    obs[9] = e->pos[0]; obs[10] = e->pos[1]; obs[11] = e->pos[2];
+}
+
+void fwo_set_waypoint_tasks(FwoEnv* e, const double* tasks, int n_tasks, int wp_len, int task) {
+    e->wp_tasks = tasks; e->wp_n_tasks = n_tasks; e->wp_len = wp_len; e->wp_task = task; e->wp_pos = 0;
+}
+
+static void wp_reset(FwoEnv* e, double* obs) {               /* reset (simple_train.py:385-408): reset_task(idx) */
+    e->steps_count = 0;
+    e->wp_pos = 0;
+    e->ep_return = 0; e->term_code = 0;
+    wp_set_leg(e);
+    wp_observation(e, obs);
+}
+
+static void wp_step(FwoEnv* e, const double action[3], double* obs, double* reward, int* done, int* term) {
+    const FwConfig* c = &e->cfg;
+    int fail = sim_step(e, action);                          /* commands are passed straight through (:441-444) */
+    e->steps_count += 1;
+    int d = 0, tc = FW_TERM_NONE;
+    double rew;
+    if (c->steps_max > 0 && e->steps_count >= c->steps_max) { d = 1; tc = FW_TERM_STEPS; }
+    if (!fail) {
+        int all = 1;
+        for (int k = 0; k < 3; ++k) all &= fabs(e->wp_goal[k] - e->pos[k]) <= c->wp_goal_bound[k];
+        if (all) {                                           /* sample_task(idx) (simple_train.py:346-355, 487-491) */
+            if (e->wp_pos < e->wp_len - 2) e->wp_pos += 1; else e->wp_pos = 0;
+            wp_set_leg(e);
+        }
+        double s = 0;                                        /* get_reward (simple_train.py:673-690), after the teleport */
+        for (int k = 0; k < 3; ++k) s += 1.0 * (fabs(e->wp_goal[k] - e->pos[k]) / c->wp_rew_range[k]);
+        rew = 1 / exp(s);
+    } else {
+        d = 1;
+        rew = (double)(e->steps_count - c->steps_max);
+        tc = fail;
+    }
+    wp_observation(e, obs);
+    e->ep_return += rew;
+    if (d) { e->term_code = tc; for (int k = 0; k < FW_NMETRIC; ++k) e->metrics[k] = NAN; }
+    *reward = rew; *done = d; *term = tc;
+}
+
 /* FixedWingAircraft.reset (fixed_wing.py:414-481) -> PyFly.reset (pyfly.py:1262-1311).
  * state: FW_NSTATE_INJECT doubles or NULL, NaN entries are sampled; target: 3 doubles or NULL;
  * noise: [4][noise_len] unit normals or NULL (Philox). */
 void fwo_reset(FwoEnv* e, const double* state, const double* target, const double* noise, int noise_len,
                double obs[FW_NOBS]) {
     const FwConfig* c = &e->cfg;
+    if (c->env_kind == FW_ENV_WAYPOINT) { wp_reset(e, obs); return; }
     e->episode += 1;
     e->steps_count = 0;
     e->cur_sim_step = 0;
@@ -1015,19 +1134,7 @@ void fwo_reset(FwoEnv* e, const double* state, const double* target, const doubl
         double w_d = sqrt(mag * mag - w_n * w_n - w_e * w_e);
         e->wind[0] = w_n; e->wind[1] = w_e; e->wind[2] = w_d;
     }
-    /* turbulence for the whole episode (pyfly.py:870-871 -> dryden.simulate) */
-    if (c->turbulence) {
-        int L = e->turb_len;
-        double* nz = (double*)malloc(sizeof(double) * 4 * L);
-        for (int k = 0; k < L; ++k) {
-            double n4[4];
-            if (noise) for (int r = 0; r < 4; ++r) n4[r] = noise[(size_t)r * noise_len + (k < noise_len ? k : noise_len - 1)];
-            else fwo_noise4(c->seed, e->env_id, e->episode, (uint32_t)k, n4);
-            for (int r = 0; r < 4; ++r) nz[(size_t)r * L + k] = n4[r];
-        }
-        fwo_dryden(c, nz, L, e->turb);
-        free(nz);
-    }
+    gen_turbulence(e, noise, noise_len);
     /* Va, alpha, beta from Euler + vel (pyfly.py:1297-1306) */
     double R[3][3];
     rot_euler(e->roll, e->pitch, e->yaw, R);
@@ -1070,6 +1177,7 @@ void fwo_reset(FwoEnv* e, const double* state, const double* target, const doubl
 void fwo_step(FwoEnv* e, const double action[3], int action_is_f32, double obs[FW_NOBS], double* reward,
               int* done, int* term) {
     const FwConfig* c = &e->cfg;
+    if (c->env_kind == FW_ENV_WAYPOINT) { wp_step(e, action, obs, reward, done, term); return; }
     e->act_is_f32 = action_is_f32;
     if (e->n_act < c->steps_max + 1) { for (int j = 0; j < 3; ++j) e->act_hist[e->n_act * 3 + j] = action[j]; e->n_act++; }
     double a[3] = {action[0], action[1], action[2]};
@@ -1249,4 +1357,11 @@ void fwo_batch_step_random(FwoBatch* b, int k_steps, uint64_t action_seed, uint6
 }
 
 int fwo_config_size(void) { return (int)sizeof(FwConfig); }
-int fwo_obs_dim(const FwConfig* c) { return c->obs_generic ? c->obs_len * c->obs_n : FW_NOBS; }
+int fwo_obs_dim(const FwConfig* c) {
+    if (c->env_kind == FW_ENV_WAYPOINT) return FW_NOBS_WAYPOINT;
+    return c->obs_generic ? c->obs_len * c->obs_n : FW_NOBS;
+}
+
+void fwo_batch_set_waypoint_tasks(FwoBatch* b, const double* tasks, int n_tasks, int wp_len, const int32_t* task_of_env) {
+    for (int i = 0; i < b->n; ++i) fwo_set_waypoint_tasks(b->envs[i], tasks, n_tasks, wp_len, task_of_env[i]);
+}

@@ -59,6 +59,8 @@ def lib():
         L.fwo_batch_step.argtypes = [ctypes.c_void_p, _fp, _dp, _dp, _u8p]
         L.fwo_batch_step_random.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, _dp,
                                             _dp, _u8p]
+        L.fwo_set_waypoint_tasks.argtypes = [ctypes.c_void_p, _dp, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        L.fwo_batch_set_waypoint_tasks.argtypes = [ctypes.c_void_p, _dp, ctypes.c_int, ctypes.c_int, _i32p]
         L.fwo_batch_counters.argtypes = [ctypes.c_void_p, _i32p, _i32p]
         L.fwo_random_action.argtypes = [ctypes.c_uint64, ctypes.c_int64, ctypes.c_uint64, _fp]
         L.fwo_config_size.restype = ctypes.c_int
@@ -83,6 +85,11 @@ class OracleEnv:
         if getattr(self, "_h", None):
             lib().fwo_destroy(self._h)
             self._h = None
+
+    def set_waypoint_tasks(self, tasks, task=0):
+        """tasks: [n_tasks, wp_len, 15] float64 (FW_WP_ROW layout); the array is kept alive by this object."""
+        self._tasks = np.ascontiguousarray(tasks, dtype=np.float64)
+        lib().fwo_set_waypoint_tasks(self._h, _p(self._tasks), self._tasks.shape[0], self._tasks.shape[1], int(task))
 
     def reset(self, state=None, target=None, noise=None):
         obs = np.zeros(self.obs_dim)
@@ -183,6 +190,12 @@ class OracleBatch:
         if getattr(self, "_h", None):
             lib().fwo_batch_destroy(self._h)
             self._h = None
+
+    def set_waypoint_tasks(self, tasks, task_of_env):
+        self._tasks = np.ascontiguousarray(tasks, dtype=np.float64)
+        toe = np.ascontiguousarray(task_of_env, dtype=np.int32)
+        lib().fwo_batch_set_waypoint_tasks(self._h, _p(self._tasks), self._tasks.shape[0], self._tasks.shape[1],
+                                           _p(toe, _i32p))
 
     def reset(self):
         lib().fwo_batch_reset(self._h, _p(self.obs))

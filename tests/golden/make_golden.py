@@ -345,6 +345,71 @@ def gen_targets():
     np.savez_compressed(os.path.join(HERE, "traj_moving_targets.npz"), **out)
 
 
+def gen_waypoint():
+    """FixedWingAircraft_simple (magpie/magpy/simple_train.py:197-702), the waypoint env head.  The class is taken
+    from the reference file where it lies; PyFly is constructed with turbulence off and the waypoints carry explicit
+    omega so that nothing is drawn from an unseeded RandomState (the env re-creates its simulator on every reset)."""
+    import ast
+    import types
+    import gym
+    from pyfly import pyfly as pyfly_mod
+    src_path = os.path.join(refshim.REFERENCE_ROOT, "magpie", "magpy", "simple_train.py")
+    tree = ast.parse(open(src_path).read())
+    cls = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "FixedWingAircraft_simple"][0]
+    mod = types.ModuleType("simple_train_env")
+    cfgdir = os.path.dirname(refshim.X8_PARAMS) + "/"
+
+    def quiet_pyfly(config_path, parameter_path):
+        return pyfly_mod.PyFly(config_path, parameter_path, config_kw={"turbulence": False})
+
+    class NoRecorder:
+        def __init__(self, *a, **k):
+            pass
+
+        def savestate(self, *a, **k):
+            pass
+
+    mod.__dict__.update(gym=gym, np=np, os=os, random=__import__("random"), PyFly=quiet_pyfly, configDir=cfgdir,
+                        startingDir=os.path.dirname(src_path), simrecorder=NoRecorder, print=lambda *a, **k: None)
+    exec(compile(ast.Module(body=[cls], type_ignores=[]), src_path, "exec"), mod.__dict__)
+    rs = np.random.RandomState(31)
+    n_tasks, wp_len = 3, 5
+    keys = ["position_n", "position_e", "position_d", "roll", "pitch", "yaw", "velocity_u", "velocity_v", "velocity_w",
+            "wind_n", "wind_e", "wind_d", "omega_p", "omega_q", "omega_r"]
+    tasks = np.zeros((n_tasks, wp_len, 15))
+    for t in range(n_tasks):
+        p0 = np.array([rs.uniform(-20, 20), rs.uniform(-20, 20), rs.uniform(-90, -60)])
+        for w in range(wp_len):
+            tasks[t, w, :3] = p0 + w * np.array([1.6, 0.05 * (t - 1), -0.02 * t])    # ~1.6 m legs: reached within a few steps
+            tasks[t, w, 3:6] = [rs.uniform(-0.1, 0.1), rs.uniform(-0.05, 0.05), rs.uniform(-0.02, 0.02)]
+            tasks[t, w, 6:9] = [rs.uniform(16, 19), rs.uniform(-0.2, 0.2), rs.uniform(-0.2, 0.2)]
+            tasks[t, w, 9:12] = [rs.uniform(-1, 1), rs.uniform(-1, 1), rs.uniform(-0.3, 0.3)]
+            tasks[t, w, 12:15] = rs.uniform(-0.2, 0.2, 3)
+    task_dicts = [np.array([{k: float(v) for k, v in zip(keys, row)} for row in tasks[t]], dtype=object)
+                  for t in range(n_tasks)]
+
+    class Env(mod.FixedWingAircraft_simple):
+        def sample_tasks(self, num_tasks):
+            return task_dicts
+
+    out = {"tasks": tasks}
+    T = 120
+    for t in range(n_tasks):
+        env = Env(None, n_tasks=n_tasks)
+        env.set_skip(True)
+        env.idx = t
+        obs0 = env.reset()
+        A, Ob, Rw, Dn, Pos = [], [], [], [], []
+        for k in range(T):
+            a = np.array([rs.uniform(-0.1, 0.1), rs.uniform(-0.1, 0.1), rs.uniform(0.3, 0.9)])
+            obs, rew, done, info = env.step(a)
+            A.append(a), Ob.append(np.array(obs)), Rw.append(float(rew)), Dn.append(bool(done)), Pos.append(env.cur_pos)
+        out.update({"obs0_%d" % t: np.array(obs0), "actions_%d" % t: np.array(A), "obs_%d" % t: np.array(Ob),
+                    "reward_%d" % t: np.array(Rw), "done_%d" % t: np.array(Dn), "pos_%d" % t: np.array(Pos)})
+        print("task", t, "waypoint index over time:", sorted(set(Pos)), "final reward", Rw[-1])
+    np.savez_compressed(os.path.join(HERE, "traj_waypoint.npz"), **out)
+
+
 def gen_reward():
     """A config that exercises the whole reward engine (fixed_wing.py:941-1111): potential form, three terms, every
     factor class; wide goal bounds and a short streak so that goals and the one-off success bonus fire."""
@@ -507,12 +572,19 @@ def gen_dryden():
             out[tag + "_noise"] = noise
             out[tag + "_lin"] = np.array(w.dryden.vel_lin)
             out[tag + "_ang"] = np.array(w.dryden.vel_ang)
+    # two blocks of turbulence_sim_length = 300: the second simulate() call restarts lsim from the last state
+    w = Wind(turbulence=True, mag_min=-8, mag_max=8, b=2.1, turbulence_intensity="moderate", sim_length=300, dt=0.01)
+    noise = np.random.RandomState(600).standard_normal((4, 600))
+    w.reset([0.0, 0.0, 0.0], noise)
+    w.get_turbulence_linear(0)
+    w.get_turbulence_linear(300)
+    out["blocks_noise"], out["blocks_lin"], out["blocks_ang"] = noise, np.array(w.dryden.vel_lin), np.array(w.dryden.vel_ang)
     np.savez_compressed(os.path.join(HERE, "dryden.npz"), **out)
 
 
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
-    jobs = {"targets": gen_targets, "reward": gen_reward, "cnn": gen_cnn, "params": gen_params, "traj": gen_traj, "turb": gen_turb, "fail": gen_fail, "full": gen_full,
+    jobs = {"waypoint": gen_waypoint, "targets": gen_targets, "reward": gen_reward, "cnn": gen_cnn, "params": gen_params, "traj": gen_traj, "turb": gen_turb, "fail": gen_fail, "full": gen_full,
             "pid": gen_pid, "gae": gen_gae, "dryden": gen_dryden}
     for name, fn in jobs.items():
         if what in (name, "all"):

@@ -231,3 +231,63 @@ def test_single_env_gym_api_matches_oracle(cuda_device):
         assert set(env.target) == {"roll", "pitch", "Va"}
     assert done and info["termination"] == "steps" and "success" in info
     env.close()
+
+
+def test_waypoint_env_head(cuda_device):
+    """The waypoint env head on the CUDA path: (a) the live-reference fixture of FixedWingAircraft_simple, (b) 256 envs
+    with turbulence, sampled omega and 10 m legs for 340 steps (crosses the 300-sample turbulence block restart)
+    against the oracle, with auto-reset."""
+    import torch
+    from oracle import fw_oracle as O
+    from tum_adlr_deep_reinforcement_learning_b200 import batched as bt
+    from tum_adlr_deep_reinforcement_learning_b200.config import build_config
+    from tum_adlr_deep_reinforcement_learning_b200.vec_env import WaypointVecEnv
+    g = load_golden("traj_waypoint")
+    cfg = build_config(env_kind="waypoint", sim_config_kw={"turbulence": False})
+    env = bt.BatchedFixedWing(3, cfg=cfg)
+    assert env.obs_dim == 12
+    env.enable_f64_outputs()
+    env.set_waypoint_tasks(g["tasks"], [0, 1, 2])
+    env.reset()
+    ref0 = np.stack([g["obs0_%d" % t] for t in range(3)])
+    assert np.abs(env.obs64.cpu().numpy() - ref0).max() < 1e-12
+    for k in range(120):
+        a = np.stack([g["actions_%d" % t][k] for t in range(3)])
+        env.step(torch.as_tensor(a).cuda().contiguous(), auto_reset=False)
+        ref = np.stack([g["obs_%d" % t][k] for t in range(3)])
+        rr = np.array([g["reward_%d" % t][k] for t in range(3)])
+        assert (np.abs(env.obs64.cpu().numpy() - ref) / np.maximum(1, np.abs(ref))).max() < 1e-9, k
+        assert np.abs(env.rew64.cpu().numpy() - rr).max() < 1e-9
+    env.close()
+    rs = np.random.RandomState(2)
+    n_tasks, wp_len, n = 4, 6, 256
+    tasks = np.full((n_tasks, wp_len, 15), np.nan)
+    for t in range(n_tasks):
+        p0 = np.array([rs.uniform(-50, 50), rs.uniform(-50, 50), rs.uniform(-90, -60)])
+        for w in range(wp_len):
+            tasks[t, w, :3] = p0 + w * np.array([10.0, rs.uniform(-1, 1), rs.uniform(-0.5, 0.5)])
+            tasks[t, w, 3:6] = [0.0, 0.0, 0.0]
+            tasks[t, w, 6:9] = [17.5, 0.0, 0.0]
+            tasks[t, w, 9:12] = rs.uniform(-1.5, 1.5, 3)
+    toe = np.arange(n) % n_tasks
+    cfg = build_config(env_kind="waypoint", sim_config_kw={"turbulence": True}, seed=5)
+    env = bt.BatchedFixedWing(n, cfg=cfg)
+    env.enable_f64_outputs()
+    env.set_waypoint_tasks(tasks, toe)
+    env.reset()
+    ob = O.OracleBatch(cfg, n)
+    ob.set_waypoint_tasks(tasks, toe)
+    assert np.abs(env.obs64.cpu().numpy() - ob.reset()).max() < 1e-11
+    for k in range(340):
+        a = np.stack([rs.uniform(-0.05, 0.05, n), rs.uniform(-0.05, 0.05, n), rs.uniform(0.4, 0.7, n)], 1).astype(np.float32)
+        env.step(torch.as_tensor(a).cuda(), auto_reset=True)
+        o_ref, r_ref, d_ref = ob.step(a)
+        assert np.array_equal(env.done.cpu().numpy(), d_ref), k
+        assert (np.abs(env.obs64.cpu().numpy() - o_ref) / np.maximum(1, np.abs(o_ref))).max() < 1e-9, k
+        assert np.abs(env.rew64.cpu().numpy() - r_ref).max() < 1e-9, k
+    env.close()
+    venv = WaypointVecEnv(8, tasks, seed=1)
+    obs = venv.reset()
+    obs, rew, done, infos = venv.step(np.tile([0.0, 0.0, 0.5], (8, 1)))
+    assert obs.shape == (8, 12) and rew.shape == (8,) and (rew > 0).all() and not done.any() and len(infos) == 8
+    venv.close()

@@ -211,3 +211,32 @@ def test_oracle_moving_target_classes():
                 assert _rel(env.get()["target"], g[tag + "_target"][ep, t]).max() < 1e-11, (tag, ep, t)
                 assert _rel(obs, g[tag + "_obs"][ep, t]).max() < 1e-9
                 assert abs(rew - g[tag + "_reward"][ep, t]) < 1e-9
+
+
+def test_dryden_block_restart_matches_reference():
+    """pyfly re-simulates turbulence every turbulence_sim_length samples (300 for raw pyfly / the waypoint env); lsim then
+    restarts from T[0] > 0 and decays the carried state over [0, T[0]] first."""
+    g = load_golden("dryden")
+    cfg = build_config(env_kind="waypoint", sim_config_kw={"turbulence": True, "turbulence_intensity": "moderate"})
+    assert cfg.turb_block_len == 300
+    out = O.dryden(cfg, g["blocks_noise"])
+    ref = np.concatenate([g["blocks_lin"], g["blocks_ang"]])
+    assert np.abs(out - ref).max() <= 1e-12 * np.abs(ref).max()
+    assert np.all(out[:, 300] == 0) and np.abs(out[:, 301]).max() > 0
+
+
+def test_oracle_waypoint_env_head():
+    """FixedWingAircraft_simple (magpie/magpy/simple_train.py:197-702) run in place by make_golden.py:gen_waypoint:
+    observations, rewards and the teleports from leg to leg."""
+    g = load_golden("traj_waypoint")
+    cfg = build_config(env_kind="waypoint", sim_config_kw={"turbulence": False})
+    assert cfg.steps_max == 500 and cfg.scale_actions == 0 and cfg.va_con_max == 0
+    for t in range(3):
+        env = O.OracleEnv(cfg)
+        env.set_waypoint_tasks(g["tasks"], t)
+        obs = env.reset()
+        assert obs.shape == (12,) and np.abs(obs - g["obs0_%d" % t]).max() < 1e-12
+        for k in range(120):
+            obs, rew, done, term = env.step(g["actions_%d" % t][k])
+            assert _rel(obs, g["obs_%d" % t][k]).max() < 1e-9, (t, k)
+            assert abs(rew - g["reward_%d" % t][k]) < 1e-9 and done == bool(g["done_%d" % t][k])

@@ -51,6 +51,16 @@ class BatchedFixedWing:
         except Exception:
             pass
 
+    def set_waypoint_tasks(self, tasks, task_of_env):
+        """Waypoint head: tasks [n_tasks, wp_len, 15] float64 rows (position n e d, roll pitch yaw, velocity u v w, wind
+        n e d, omega p q r with NaN = sample), task_of_env [n] int.  The library keeps its own device copy."""
+        tasks = torch.as_tensor(tasks, dtype=torch.float64, device=self.device).contiguous()
+        toe = torch.as_tensor(task_of_env, dtype=torch.int32, device=self.device).contiguous()
+        assert tasks.dim() == 3 and tasks.shape[2] == 15 and toe.shape == (self.n,)
+        _lib.check(_lib.lib().fw_set_waypoint_tasks(self._h, _ptr(tasks), tasks.shape[0], tasks.shape[1], _ptr(toe),
+                                                    self._stream()), "fw_set_waypoint_tasks")
+        torch.cuda.current_stream(self.device).synchronize()
+
     def enable_f64_outputs(self):
         self.obs64 = torch.zeros(self.n, self.obs_dim, dtype=torch.float64, device=self.device)
         self.rew64 = torch.zeros(self.n, dtype=torch.float64, device=self.device)

@@ -20,7 +20,7 @@ import numpy as np
 
 _DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
 
-FW_ABI_VERSION = 5
+FW_ABI_VERSION = 7
 FW_NY, FW_NOBS, FW_NACT, FW_NSTATE_INJECT, FW_NMETRIC = 19, 14, 3, 21, 28
 FW_F64, FW_F32 = 0, 1
 FW_INT_RK45_SCIPY, FW_INT_RK4_FIXED = 0, 1
@@ -38,7 +38,7 @@ METRIC_LAYOUT = (("rise_time", 0, TARGET_STATES), ("settling_time", 3, GOAL_STAT
 class FwFilter(ctypes.Structure):
     _fields_ = [("order", ctypes.c_int32), ("noise_row", ctypes.c_int32), ("Ad", ctypes.c_double * 9),
                 ("Bd0", ctypes.c_double * 3), ("Bd1", ctypes.c_double * 3), ("C", ctypes.c_double * 3),
-                ("D", ctypes.c_double)]
+                ("D", ctypes.c_double), ("Ablk", ctypes.c_double * 9)]
 
 
 _AERO = ("mass Jx Jy Jz Jxz S_wing b c S_prop C_prop k_motor k_T_P k_Omega e_oswald M a_0 "
@@ -80,6 +80,7 @@ class FwConfig(ctypes.Structure):
            ("obs_generic", _i), ("obs_len", _i), ("obs_n", _i), ("obs_normalize", _i),
            ("obs_kind", _i * 16), ("obs_idx", _i * 16), ("obs_window", _i * 16), ("obs_norm_flag", _i * 16),
            ("obs_mean", _d * 16), ("obs_var", _d * 16), ("obs_init_noise", _d),
+           ("env_kind", _i), ("turb_block_len", _i), ("wp_goal_bound", _d * 3), ("wp_rew_range", _d * 3),
            ("seed", ctypes.c_uint64), ("env_id_offset", ctypes.c_int64)])
 
 
@@ -224,7 +225,7 @@ def dryden_filters(sim_length, sim_dt, wingspan, intensity="light", spec=False):
     (pyfly.py:781-783) against the signature (dt, b, h=100, V_a=25, intensity) (dryden.py:52), hence inside the
     model dt = sim_length, b = sim dt, h = wingspan.  `spec=True` gives the intended MIL-F-8785C parameters
     (dt = sim dt, b = wingspan, h = 100 m) — a labelled deviation from the reference, never used for parity.
-    Returns (filters [(order, noise_row, Ad, Bd0, Bd1, C, D)], noise_scale).
+    Returns (filters [(order, noise_row, Ad, Bd0, Bd1, C, D, Ablk)], noise_scale).
     """
     from scipy.linalg import expm
     if spec:
@@ -272,13 +273,16 @@ def dryden_filters(sim_length, sim_dt, wingspan, intensity="light", spec=False):
         Ad = eM[:n, :n]
         Bd1 = eM[n + 1:, :n]
         Bd0 = eM[n:n + 1, :n] - Bd1
-        out.append((n, row, Ad, Bd0.ravel(), Bd1.ravel(), C.ravel(), float(D)))
+        # second and later blocks: lsim is called with T[0] = block_start_time > 0 and first steps the carried state
+        # forward over [0, T[0]] with zero input, i.e. multiplies it by expm(A^T T[0]) (= Ablk^m for block m)
+        Ablk = expm(A.T * (sim_length * dt_d))
+        out.append((n, row, Ad, Bd0.ravel(), Bd1.ravel(), C.ravel(), float(D), Ablk))
     return out, math.sqrt(math.pi / dt_d)
 
 
 def build_config(env_cfg=None, sim_cfg=None, config_kw=None, sim_config_kw=None, params=None,
                  curriculum_level=1.0, precision="f64", integrator="rk45", rk4_substeps=4, rtol=1e-3, atol=1e-6,
-                 seed=0, env_id_offset=0, dryden_spec=False, obs_init_noise=None, rng_u_override=None):
+                 seed=0, env_id_offset=0, dryden_spec=False, obs_init_noise=None, rng_u_override=None, env_kind="attitude"):
     """Flatten reference-format configs into an `FwConfig`.  `env_cfg` / `sim_cfg`: dict or JSON path (defaults above)."""
     def load(x, default):
         if x is None:
@@ -290,10 +294,18 @@ def build_config(env_cfg=None, sim_cfg=None, config_kw=None, sim_config_kw=None,
 
     env = load(env_cfg, default_env_config)
     sim = load(sim_cfg, default_sim_config)
+    waypoint = env_kind == "waypoint"
+    if waypoint:
+        # FixedWingAircraft_simple builds PyFly from pyfly_config.json as is (simple_train.py:219-222): no gym overrides of
+        # the simulator, 500 steps, commands passed straight through, 12 raw states observed
+        env["steps_max"] = 500
+        env["action"]["scale_space"] = False
+        env["simulator"] = {"states": []}
     if config_kw:
         apply_overrides(env, copy.deepcopy(config_kw))
     sim_kw = copy.deepcopy(sim_config_kw) if sim_config_kw else {}
-    sim_kw["turbulence_sim_length"] = env["steps_max"]        # fixed_wing.py:62
+    if not waypoint:
+        sim_kw["turbulence_sim_length"] = env["steps_max"]    # fixed_wing.py:62
     apply_overrides(sim, sim_kw)
     P = load_aircraft_parameters() if params is None else dict(params)
 
@@ -346,16 +358,17 @@ def build_config(env_cfg=None, sim_cfg=None, config_kw=None, sim_config_kw=None,
     intensity = sim.get("turbulence_intensity")
     if intensity in ("None", "none"):
         intensity = None
-    L = int(sim["turbulence_sim_length"])
-    filters, scale = dryden_filters(L, c.dt, c.b, intensity, spec=dryden_spec)
+    L_turb = int(sim["turbulence_sim_length"])
+    filters, scale = dryden_filters(L_turb, c.dt, c.b, intensity, spec=dryden_spec)
     c.turb_noise_scale = scale
-    for fi, (n, row, Ad, Bd0, Bd1, C, D) in enumerate(filters):
+    for fi, (n, row, Ad, Bd0, Bd1, C, D, Ablk) in enumerate(filters):
         f = c.filt[fi]
         f.order, f.noise_row, f.D = n, row, D
         for a in range(n):
             f.Bd0[a], f.Bd1[a], f.C[a] = Bd0[a], Bd1[a], C[a]
             for b_ in range(n):
                 f.Ad[a * n + b_] = Ad[a, b_]
+                f.Ablk[a * n + b_] = Ablk[a, b_]
 
     # ---- gym env ----
     c.steps_max = int(env["steps_max"])
@@ -567,12 +580,18 @@ def build_config(env_cfg=None, sim_cfg=None, config_kw=None, sim_config_kw=None,
     for m in env.get("metrics", []):
         if m["name"] == "rise_time":
             c.rise_low, c.rise_high = m.get("low", 0.1), m.get("high", 0.9)
+    c.env_kind = 1 if waypoint else 0
+    c.turb_block_len = L_turb
+    for k in range(3):
+        c.wp_goal_bound[k], c.wp_rew_range[k] = 0.5, 6.0
     c.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
     c.env_id_offset = int(env_id_offset)
     return c
 
 
 def obs_dim(cfg):
+    if cfg.env_kind == 1:
+        return 12
     return cfg.obs_len * cfg.obs_n if cfg.obs_generic else FW_NOBS
 
 

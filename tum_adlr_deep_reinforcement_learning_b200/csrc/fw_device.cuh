@@ -80,7 +80,7 @@ template <> struct M<float> {
 // launch as a __grid_constant__ kernel parameter (constant bank, warp-uniform broadcast reads).
 template <typename T> struct DFilter {
     int order, noise_row;
-    T Ad[9], Bd0[3], Bd1[3], C[3], D;
+    T Ad[9], Bd0[3], Bd1[3], C[3], D, Ablk[9];
 };
 
 template <typename T> struct DCfg {
@@ -104,6 +104,8 @@ template <typename T> struct DCfg {
     int tgt_radians[3], tgt_moving;     // tgt_moving: some target class is linear / sinusoidal
     T tgt_slope_low[3], tgt_slope_high[3], tgt_amp_low[3], tgt_amp_high[3], tgt_period_low[3], tgt_period_high[3];
     T rng_u_override;
+    int env_kind, turb_block_len;
+    T wp_goal_bound[3], wp_rew_range[3];
     T rew_err_scaling[3], rew_err_max[3], rew_delta_scaling, rew_delta_max, rew_bound_scaling, rew_bound_max;
     T step_fail_value, rise_low, rise_high, obs_noise_mean, obs_noise_std;
     int rew_generic, rew_n, rew_potential, rew_nterms;
@@ -152,9 +154,10 @@ enum IField {
     IF_RISE_LO = 32,          // 3 first index t with |e_t| >= low_lim and |e_{t+1}| < low_lim (-1 = none)
     IF_RISE_HI = 35,          // 3
     IF_NFEV = 38, IF_NATT = 39, IF_TERM = 40, IF_EP_LEN = 41, IF_ACT_F32 = 42,
+    IF_WP_POS = 47,           // waypoint head: index of the current leg's start waypoint
     IF_TCLS = 44,             // 3: per-env target class (an injected target forces constant, fixed_wing.py:446-450)
     IF_GOAL_ACHIEVED = 43,    // self.goal_achieved: set by the first success, never cleared (fixed_wing.py:81, 546-547)
-    IF_COUNT = 47
+    IF_COUNT = 48
 };
 
 template <typename T> struct Soa {
@@ -168,6 +171,9 @@ template <typename T> struct Soa {
     const double* noise;   // injected unit white noise [n][4][noise_len] or nullptr (Philox)
     int noise_len;
     int n;
+    const double* wp_tasks;      // waypoint head: [n_tasks][wp_len][FW_WP_ROW]
+    const int32_t* wp_task_of_env;
+    int wp_n_tasks, wp_len;
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -570,6 +576,39 @@ __device__ __forceinline__ void turb_advance(const DCfg<T>& c, T (&fx)[12], T (&
     for (int r = 0; r < 4; ++r) fu[r] = un[r];
 }
 
+// x <- x Ablk (row-vector convention) for one filter
+template <typename T, int ORD, int OFF>
+__device__ __forceinline__ void filt_block(const DFilter<T>& F, T (&fx)[12]) {
+    T xn[ORD];
+#pragma unroll
+    for (int a = 0; a < ORD; ++a) {
+        T sacc = 0;
+#pragma unroll
+        for (int b = 0; b < ORD; ++b) sacc += fx[OFF + b] * F.Ablk[b * ORD + a];
+        xn[a] = sacc;
+    }
+#pragma unroll
+    for (int a = 0; a < ORD; ++a) fx[OFF + a] = xn[a];
+}
+
+// One step of the streamed turbulence: sample index `k_new` becomes current.  pyfly simulates blocks of
+// turbulence_sim_length samples; every new block calls lsim with T[0] > 0, which first steps the carried state over
+// [0, T[0]] with zero input: x <- x Ablk^m for block m, and the block's first output is C x + D u without a recurrence
+// step (pyfly.py:870-871, dryden.py:30-36, scipy lsim).  Inside a block it is the plain recurrence.
+template <typename T>
+__device__ __forceinline__ void turb_step(const DCfg<T>& c, T (&fx)[12], T (&fu)[4], const T (&un)[4], int k_new) {
+    if (c.turb_block_len > 0 && (k_new % c.turb_block_len) == 0) {
+        for (int m = 0; m < k_new / c.turb_block_len; ++m) {
+            filt_block<T, 1, 0>(c.filt[0], fx); filt_block<T, 2, 1>(c.filt[1], fx); filt_block<T, 2, 3>(c.filt[2], fx);
+            filt_block<T, 1, 5>(c.filt[3], fx); filt_block<T, 3, 6>(c.filt[4], fx); filt_block<T, 3, 9>(c.filt[5], fx);
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) fu[r] = un[r];
+    } else {
+        turb_advance(c, fx, fu, un);
+    }
+}
+
 // scaled noise sample k for env (injected buffer or Philox)
 template <typename T>
 __device__ __forceinline__ void noise_sample(const DCfg<T>& c, const Soa<T>& S, int env, unsigned long long episode,
@@ -659,6 +698,7 @@ __device__ __noinline__ void add_obs_noise(const DCfg<T>& c, long long gid, unsi
 }
 
 template <typename T> __device__ __forceinline__ int obs_dim(const DCfg<T>& c) {
+    if (c.env_kind == FW_ENV_WAYPOINT) return FW_NOBS_WAYPOINT;
     return c.obs_generic ? c.obs_len * c.obs_n : FW_NOBS;
 }
 
@@ -988,6 +1028,92 @@ __device__ void reset_env(const DCfg<T>& c, const Soa<T>& S, int env, const doub
     }
     if (c.obs_noise_std > (T)0 || c.obs_noise_mean != (T)0) add_obs_noise<T>(c, gid, episode, 0, o, FW_NOBS);
     write_obs(o, FW_NOBS, env, obs, obs64);
+}
+
+// ---------------- waypoint head: FixedWingAircraft_simple (magpie/magpy/simple_train.py:197-702) ----------------
+
+// simulator.reset(state=waypoint) + goal of the leg (simple_train.py:357-363 -> pyfly.py:1262-1311): position, attitude,
+// velocity and wind from the start waypoint; omega from the row or, if NaN, uniform in the pyfly init range; actuators at
+// their (0, 0) init range; turbulence restarted on a fresh noise segment.  Writes the SoA row of the simulator.
+template <typename T>
+__device__ __noinline__ void wp_start_leg(const DCfg<T>& c, const Soa<T>& S, int env, int wp_pos) {
+    const int n = S.n;
+    T* r = S.r + env;
+    int32_t* ii = S.i + env;
+    const double* row = S.wp_tasks + ((size_t)S.wp_task_of_env[env] * S.wp_len + wp_pos) * FW_WP_ROW;
+    const unsigned long long episode = (unsigned long long)(uint32_t)ii[IF_EPISODE * n] + 1ull;
+    const long long gid = c.env_id_offset + env;
+    const T roll = (T)row[3], pitch = (T)row[4], yaw = (T)row[5];
+    T om[3], wind[3], vel[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        om[i] = ::isnan(row[12 + i]) ? c.init_lo[3 + i] + (c.init_hi[3 + i] - c.init_lo[3 + i]) * rng_uniform<T>(c.seed, gid, episode, RNG_RESET, 3 + i)
+                                     : (T)row[12 + i];
+        wind[i] = (T)row[9 + i];
+        vel[i] = (T)row[6 + i];
+    }
+    T fx[12], fu[4], tl[3] = {0, 0, 0}, ta[3] = {0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 12; ++i) fx[i] = 0;
+    if (c.turbulence) { noise_sample(c, S, env, episode, 0, fu); turb_eval(c, fx, fu, tl, ta); }
+    else { fu[0] = fu[1] = fu[2] = fu[3] = 0; }
+    T wb[3];
+    rot_euler_apply(roll, pitch, yaw, wind, wb);
+    const T a0 = vel[0] - (wb[0] + tl[0]), a1 = vel[1] - (wb[1] + tl[1]), a2 = vel[2] - (wb[2] + tl[2]);
+    T Va = M<T>::sqrt(a0 * a0 + a1 * a1 + a2 * a2);
+    const T alpha = M<T>::atan2(a2, a0), beta = M<T>::asin(a1 / Va);
+    if (Va < c.va_value_min) Va = c.va_value_min;
+    T sps, cps, sth, cth, sph, cph;
+    M<T>::sincos(yaw / (T)2, &sps, &cps);
+    M<T>::sincos(pitch / (T)2, &sth, &cth);
+    M<T>::sincos(roll / (T)2, &sph, &cph);
+    r[(RF_Y + 0) * n] = cps * cth * cph + sps * sth * sph;
+    r[(RF_Y + 1) * n] = cps * cth * sph - sps * sth * cph;
+    r[(RF_Y + 2) * n] = cps * sth * cph + sps * cth * sph;
+    r[(RF_Y + 3) * n] = sps * cth * cph - cps * sth * sph;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        r[(RF_Y + 4 + i) * n] = om[i];
+        r[(RF_Y + 7 + i) * n] = (T)row[i];
+        r[(RF_Y + 10 + i) * n] = vel[i];
+        r[(RF_WIND + i) * n] = wind[i];
+        r[(RF_TGT + i) * n] = (T)row[FW_WP_ROW + i];         // goal = position of the next waypoint
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) r[(RF_Y + 13 + i) * n] = 0;
+    r[RF_ROLL * n] = roll; r[RF_PITCH * n] = pitch; r[RF_VA * n] = Va; r[RF_ALPHA * n] = alpha; r[RF_BETA * n] = beta;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) r[(RF_FX + i) * n] = fx[i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r[(RF_FU + i) * n] = fu[i];
+    ii[IF_EPISODE * n] = (int32_t)episode;
+    ii[IF_SIM_STEP * n] = 0;
+    ii[IF_WP_POS * n] = wp_pos;
+    // IF_STEPS of the simulator-level "fresh reset" quirk (elevator = aileron = 0 at the first RHS call) is tracked by
+    // IF_STEPS_TGT here: steps since the last simulator reset
+    ii[IF_STEPS_TGT * n] = 0;
+}
+
+template <typename T>
+__device__ __forceinline__ void wp_observation(const Soa<T>& S, int env, T (&o)[FW_NOBS_WAYPOINT]) {
+    const int n = S.n;
+    const T* r = S.r + env;
+    o[0] = r[RF_ROLL * n]; o[1] = r[RF_PITCH * n]; o[2] = r[RF_VA * n];
+    o[3] = r[(RF_Y + 4) * n]; o[4] = r[(RF_Y + 5) * n]; o[5] = r[(RF_Y + 6) * n];
+    o[6] = r[(RF_Y + 14) * n]; o[7] = r[(RF_Y + 13) * n]; o[8] = r[(RF_Y + 15) * n];    // elevon_left, elevon_right, throttle
+    o[9] = r[(RF_Y + 7) * n]; o[10] = r[(RF_Y + 8) * n]; o[11] = r[(RF_Y + 9) * n];
+}
+
+// reset (simple_train.py:385-408): steps 0, first leg of the env's task
+template <typename T>
+__device__ void wp_reset_env(const DCfg<T>& c, const Soa<T>& S, int env, float* obs, double* obs64) {
+    const int n = S.n;
+    S.i[IF_STEPS * n + env] = 0;
+    S.r[RF_EP_RET * n + env] = 0;
+    wp_start_leg<T>(c, S, env, 0);
+    T o[FW_NOBS_WAYPOINT];
+    wp_observation<T>(S, env, o);
+    write_obs(o, FW_NOBS_WAYPOINT, env, obs, obs64);
 }
 
 }  // namespace fw

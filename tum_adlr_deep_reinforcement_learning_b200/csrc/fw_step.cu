@@ -46,6 +46,7 @@ __global__ void reset_kernel(const __grid_constant__ DCfg<T> c, const Soa<T> S, 
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
     if (env >= S.n) return;
     if (mask && !mask[env]) return;
+    if (c.env_kind == FW_ENV_WAYPOINT) { wp_reset_env<T>(c, S, env, obs, obs64); return; }
     reset_env<T>(c, S, env, state_in, target_in, obs, obs64);
 }
 
@@ -146,7 +147,7 @@ __device__ __forceinline__ void load_dyn(const DCfg<T>& c, const Soa<T>& S, cons
     prep_action(c, io, env, a_raw, act_f32, x.cmd, cmd_in);
     // elevator/aileron seen by the t == 0 RHS call: 0 right after a reset (disabled ControlVariable.reset)
     elev0 = 0; ail0 = 0;
-    if (S.i[IF_STEPS * n + env] > 0) {
+    if (S.i[(c.env_kind == FW_ENV_WAYPOINT ? IF_STEPS_TGT : IF_STEPS) * n + env] > 0) {
         const T er = clip(y[13], c.elevon_min, c.elevon_max), el = clip(y[14], c.elevon_min, c.elevon_max);
         elev0 = (er + el) / (T)2;
         ail0 = (-er + el) / (T)2;
@@ -368,6 +369,53 @@ __global__ void __launch_bounds__(128) rk4_kernel(const __grid_constant__ DCfg<T
     S.i[IF_NATT * n + env] = natt;
 }
 
+// PyFly.step after solve_ivp (pyfly.py:1396-1406, 1852-1881): quaternion renormalisation, Euler angles, constraint checks
+// on p, q, r, actuator clips, Va / alpha / beta.  roll .. om_obs enter holding the previous committed values and leave
+// holding what each variable's `.history[-1]` is after a (possibly partial) commit.  Returns the FwTermCode.
+template <typename T>
+__device__ __forceinline__ int post_step_commit(const DCfg<T>& c, const DynCtx<T>& x, T (&y)[FW_NY], int fail, T& roll,
+                                                T& pitch, T& Va, T& alpha, T& beta, T (&om_obs)[3]) {
+    if (!fail) {
+        const T nrm = M<T>::sqrt(y[0] * y[0] + y[1] * y[1] + y[2] * y[2] + y[3] * y[3]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) y[i] = y[i] / nrm;
+        const T e0 = y[0], e1 = y[1], e2 = y[2], e3 = y[3];
+        roll = M<T>::atan2_hot((T)2 * (e0 * e1 + e2 * e3), e0 * e0 + e3 * e3 - e1 * e1 - e2 * e2);
+        pitch = M<T>::asin_hot((T)2 * (e0 * e2 - e1 * e3));
+        // yaw (pyfly.py:704-706) only feeds the Euler-angle rotation below and is not observed: it is not materialised
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            if (!fail) {
+                if (y[4 + i] < c.omega_con_min[i] || y[4 + i] > c.omega_con_max[i]) fail = FW_TERM_OMEGA_P + i;
+                else om_obs[i] = y[4 + i];
+            }
+        }
+        if (!fail) {
+            y[13] = clip(y[13], c.elevon_min, c.elevon_max);
+            y[14] = clip(y[14], c.elevon_min, c.elevon_max);
+            y[15] = clip(y[15], c.throttle_min, c.throttle_max);
+            y[16] = clip(y[16], -c.elevon_dot_max, c.elevon_dot_max);
+            y[17] = clip(y[17], -c.elevon_dot_max, c.elevon_dot_max);
+            // pyfly.py:1398-1406 rotates the steady wind with the matrix built from (roll, pitch, yaw); for the
+            // normalised quaternion those Euler angles came from, that matrix equals the quaternion form of
+            // _rot_b_v (pyfly.py:1782-1800) up to rounding, so no angle -> sin/cos round trip is needed.
+            T wb[3];
+            wb[0] = ((T)-1 + (T)2 * (e0 * e0 + e1 * e1)) * x.wind[0] + (T)2 * (e1 * e2 + e3 * e0) * x.wind[1] + (T)2 * (e1 * e3 - e2 * e0) * x.wind[2];
+            wb[1] = (T)2 * (e1 * e2 - e3 * e0) * x.wind[0] + ((T)-1 + (T)2 * (e0 * e0 + e2 * e2)) * x.wind[1] + (T)2 * (e2 * e3 + e1 * e0) * x.wind[2];
+            wb[2] = (T)2 * (e1 * e3 + e2 * e0) * x.wind[0] + (T)2 * (e2 * e3 - e1 * e0) * x.wind[1] + ((T)-1 + (T)2 * (e0 * e0 + e3 * e3)) * x.wind[2];
+            const T a0 = y[10] - (wb[0] + x.tl[0]), a1 = y[11] - (wb[1] + x.tl[1]), a2 = y[12] - (wb[2] + x.tl[2]);
+            T Van = M<T>::sqrt(a0 * a0 + a1 * a1 + a2 * a2);
+            const T al = M<T>::atan2_hot(a2, a0), be = M<T>::asin_hot(a1 / Van);
+            if (c.va_con_max > (T)0 && Van > c.va_con_max) fail = FW_TERM_VA;
+            else {
+                if (Van < c.va_value_min) Van = c.va_value_min;
+                Va = Van; alpha = al; beta = be;
+            }
+        }
+    }
+    return fail;
+}
+
 // ---- kernel B: everything after the integrator (once per step, high occupancy) ----
 template <typename T, bool TURB, bool GENERIC>
 __global__ void __launch_bounds__(128, 4) head_kernel(const __grid_constant__ DCfg<T> c, const Soa<T> S, const StepIO io,
@@ -408,44 +456,7 @@ __global__ void __launch_bounds__(128, 4) head_kernel(const __grid_constant__ DC
     // ---------------- post-step commit (pyfly.py:1396-1406, 1852-1881) ----------------
     T roll = roll_prev, pitch = pitch_prev, Va = Va_prev, alpha = alpha_prev, beta = beta_prev;
     T om_obs[3] = {omega_prev[0], omega_prev[1], omega_prev[2]};   // .history[-1] view for a terminal observation
-    if (!fail) {
-        const T nrm = M<T>::sqrt(y[0] * y[0] + y[1] * y[1] + y[2] * y[2] + y[3] * y[3]);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) y[i] = y[i] / nrm;
-        const T e0 = y[0], e1 = y[1], e2 = y[2], e3 = y[3];
-        roll = M<T>::atan2_hot((T)2 * (e0 * e1 + e2 * e3), e0 * e0 + e3 * e3 - e1 * e1 - e2 * e2);
-        pitch = M<T>::asin_hot((T)2 * (e0 * e2 - e1 * e3));
-        // yaw (pyfly.py:704-706) only feeds the Euler-angle rotation below and is not observed: it is not materialised
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            if (!fail) {
-                if (y[4 + i] < c.omega_con_min[i] || y[4 + i] > c.omega_con_max[i]) fail = FW_TERM_OMEGA_P + i;
-                else om_obs[i] = y[4 + i];
-            }
-        }
-        if (!fail) {
-            y[13] = clip(y[13], c.elevon_min, c.elevon_max);
-            y[14] = clip(y[14], c.elevon_min, c.elevon_max);
-            y[15] = clip(y[15], c.throttle_min, c.throttle_max);
-            y[16] = clip(y[16], -c.elevon_dot_max, c.elevon_dot_max);
-            y[17] = clip(y[17], -c.elevon_dot_max, c.elevon_dot_max);
-            // pyfly.py:1398-1406 rotates the steady wind with the matrix built from (roll, pitch, yaw); for the
-            // normalised quaternion those Euler angles came from, that matrix equals the quaternion form of
-            // _rot_b_v (pyfly.py:1782-1800) up to rounding, so no angle -> sin/cos round trip is needed.
-            T wb[3];
-            wb[0] = ((T)-1 + (T)2 * (e0 * e0 + e1 * e1)) * x.wind[0] + (T)2 * (e1 * e2 + e3 * e0) * x.wind[1] + (T)2 * (e1 * e3 - e2 * e0) * x.wind[2];
-            wb[1] = (T)2 * (e1 * e2 - e3 * e0) * x.wind[0] + ((T)-1 + (T)2 * (e0 * e0 + e2 * e2)) * x.wind[1] + (T)2 * (e2 * e3 + e1 * e0) * x.wind[2];
-            wb[2] = (T)2 * (e1 * e3 + e2 * e0) * x.wind[0] + (T)2 * (e2 * e3 - e1 * e0) * x.wind[1] + ((T)-1 + (T)2 * (e0 * e0 + e3 * e3)) * x.wind[2];
-            const T a0 = y[10] - (wb[0] + x.tl[0]), a1 = y[11] - (wb[1] + x.tl[1]), a2 = y[12] - (wb[2] + x.tl[2]);
-            T Van = M<T>::sqrt(a0 * a0 + a1 * a1 + a2 * a2);
-            const T al = M<T>::atan2_hot(a2, a0), be = M<T>::asin_hot(a1 / Van);
-            if (c.va_con_max > (T)0 && Van > c.va_con_max) fail = FW_TERM_VA;
-            else {
-                if (Van < c.va_value_min) Van = c.va_value_min;
-                Va = Van; alpha = al; beta = be;
-            }
-        }
-    }
+    fail = post_step_commit<T>(c, x, y, fail, roll, pitch, Va, alpha, beta, om_obs);
     sim_step += 1;
 
     // ---------------- gym head (fixed_wing.py:512-628) ----------------
@@ -729,7 +740,7 @@ __global__ void __launch_bounds__(128, 4) head_kernel(const __grid_constant__ DC
     if (TURB && !fail) {
         T un[4];
         noise_sample(c, S, env, episode, sim_step, un);
-        turb_advance(c, fx, fu, un);
+        turb_step(c, fx, fu, un, sim_step);
 #pragma unroll
         for (int i = 0; i < 12; ++i) r[(RF_FX + i) * n] = fx[i];
 #pragma unroll
@@ -766,6 +777,102 @@ __global__ void __launch_bounds__(128, 4) head_kernel(const __grid_constant__ DC
     for (int k = 0; k < 4; ++k) {
         ii[(IF_GOAL_CNT + k) * n] = gcnt[k]; ii[(IF_GOAL_TOTAL + k) * n] = gtot[k]; ii[(IF_SETTLE + k) * n] = settle[k];
     }
+}
+
+// ---- waypoint head (FixedWingAircraft_simple.step, simple_train.py:410-509) ----
+template <typename T, bool TURB>
+__global__ void __launch_bounds__(128, 4) waypoint_head_kernel(const __grid_constant__ DCfg<T> c, const Soa<T> S,
+                                                               const StepIO io, const Scratch<T> W) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = S.n;
+    if (env >= n) return;
+    T* r = S.r + env;
+    int32_t* ii = S.i + env;
+    int fail = W.fail[env];
+    T y[FW_NY];
+#pragma unroll
+    for (int i = 0; i < FW_NY; ++i) y[i] = fail ? r[(RF_Y + i) * n] : W.ytmp[i * n + env];
+    T roll = r[RF_ROLL * n], pitch = r[RF_PITCH * n], Va = r[RF_VA * n], alpha = r[RF_ALPHA * n], beta = r[RF_BETA * n];
+    T om_obs[3] = {r[(RF_Y + 4) * n], r[(RF_Y + 5) * n], r[(RF_Y + 6) * n]};
+    DynCtx<T> x;
+    T goal[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        x.wind[k] = r[(RF_WIND + k) * n]; goal[k] = r[(RF_TGT + k) * n];
+        x.tl[k] = TURB ? W.turb[k * n + env] : (T)0; x.ta[k] = TURB ? W.turb[(3 + k) * n + env] : (T)0;
+        x.cmd[k] = 0;
+    }
+    int steps = ii[IF_STEPS * n], sim_step = ii[IF_SIM_STEP * n];
+    const unsigned long long episode = (unsigned long long)(uint32_t)ii[IF_EPISODE * n];
+    fail = post_step_commit<T>(c, x, y, fail, roll, pitch, Va, alpha, beta, om_obs);
+    sim_step += 1;
+    steps += 1;
+    bool done = false;
+    int term = FW_TERM_NONE;
+    if (c.steps_max > 0 && steps >= c.steps_max) { done = true; term = FW_TERM_STEPS; }
+    T reward;
+    bool teleport = false;
+    if (!fail) {
+        // commit the simulator state
+#pragma unroll
+        for (int i = 0; i < FW_NY; ++i) r[(RF_Y + i) * n] = y[i];
+        r[RF_ROLL * n] = roll; r[RF_PITCH * n] = pitch; r[RF_VA * n] = Va; r[RF_ALPHA * n] = alpha; r[RF_BETA * n] = beta;
+        ii[IF_SIM_STEP * n] = sim_step;
+        ii[IF_STEPS_TGT * n] = ii[IF_STEPS_TGT * n] + 1;
+        bool all = true;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) all = all && (M<T>::fabs(goal[k] - y[7 + k]) <= c.wp_goal_bound[k]);
+        if (all) {                                   // sample_task(idx): next leg, wrapping (simple_train.py:346-355)
+            int pos = ii[IF_WP_POS * n];
+            pos = (pos < S.wp_len - 2) ? pos + 1 : 0;
+            wp_start_leg<T>(c, S, env, pos);
+            teleport = true;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { goal[k] = r[(RF_TGT + k) * n]; y[7 + k] = r[(RF_Y + 7 + k) * n]; }
+        }
+        T sacc = 0;                                  // get_reward (simple_train.py:673-690), after the teleport
+#pragma unroll
+        for (int k = 0; k < 3; ++k) sacc += (T)1 * (M<T>::fabs(goal[k] - y[7 + k]) / c.wp_rew_range[k]);
+        reward = (T)1 / M<T>::exp(sacc);
+        if (TURB && !teleport) {
+            T fx[12], fu[4], un[4];
+#pragma unroll
+            for (int i = 0; i < 12; ++i) fx[i] = r[(RF_FX + i) * n];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) fu[i] = r[(RF_FU + i) * n];
+            noise_sample(c, S, env, episode, sim_step, un);
+            turb_step(c, fx, fu, un, sim_step);
+#pragma unroll
+            for (int i = 0; i < 12; ++i) r[(RF_FX + i) * n] = fx[i];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) r[(RF_FU + i) * n] = fu[i];
+        }
+    } else {
+        done = true;
+        term = fail;
+        reward = (T)(steps - c.steps_max);
+    }
+    const T ep_ret = r[RF_EP_RET * n] + reward;
+    r[RF_EP_RET * n] = ep_ret;
+    ii[IF_STEPS * n] = steps;
+    T o[FW_NOBS_WAYPOINT];
+    wp_observation<T>(S, env, o);
+    if (done) {
+        double* m = S.metrics + (size_t)env * FW_NMETRIC;
+        for (int k = 0; k < FW_NMETRIC; ++k) m[k] = CUDART_NAN;     // this env computes no metrics (simple_train.py:501-503)
+        S.ep_ret[env] = (double)ep_ret;
+        S.ep_len[env] = steps;
+    }
+    S.ep_term[env] = term;
+    if (io.rew) io.rew[env] = (float)reward;
+    if (io.rew64) io.rew64[env] = (double)reward;
+    if (io.done) io.done[env] = done ? 1 : 0;
+    if (done && io.auto_reset) {
+        if (io.term_obs) write_obs(o, FW_NOBS_WAYPOINT, env, io.term_obs, (double*)nullptr);
+        wp_reset_env<T>(c, S, env, io.obs, io.obs64);
+        return;
+    }
+    write_obs(o, FW_NOBS_WAYPOINT, env, io.obs, io.obs64);
 }
 
 // gather / scatter between SoA fields and row-major [n, width] buffers
@@ -889,7 +996,7 @@ template <typename T> static void convert_cfg(const FwConfig& f, DCfg<T>& d) {
     CP(wind_mag_min); CP(wind_mag_max); CP(turb_noise_scale);
     for (int fi = 0; fi < 6; ++fi) {
         d.filt[fi].order = f.filt[fi].order; d.filt[fi].noise_row = f.filt[fi].noise_row;
-        for (int k = 0; k < 9; ++k) d.filt[fi].Ad[k] = (T)f.filt[fi].Ad[k];
+        for (int k = 0; k < 9; ++k) { d.filt[fi].Ad[k] = (T)f.filt[fi].Ad[k]; d.filt[fi].Ablk[k] = (T)f.filt[fi].Ablk[k]; }
         for (int k = 0; k < 3; ++k) { d.filt[fi].Bd0[k] = (T)f.filt[fi].Bd0[k]; d.filt[fi].Bd1[k] = (T)f.filt[fi].Bd1[k]; d.filt[fi].C[k] = (T)f.filt[fi].C[k]; }
         d.filt[fi].D = (T)f.filt[fi].D;
     }
@@ -902,6 +1009,8 @@ template <typename T> static void convert_cfg(const FwConfig& f, DCfg<T>& d) {
         if (f.tgt_class[k] == FW_TGT_LINEAR || f.tgt_class[k] == FW_TGT_SINUSOIDAL) d.tgt_moving = 1;
     }
     CP(rng_u_override);
+    d.env_kind = f.env_kind; d.turb_block_len = f.turb_block_len;
+    for (int k = 0; k < 3; ++k) { CP(wp_goal_bound[k]); CP(wp_rew_range[k]); }
     CP(streak_fraction); CP(rew_delta_scaling); CP(rew_delta_max); CP(rew_bound_scaling); CP(rew_bound_max);
     CP(step_fail_value); CP(rise_low); CP(rise_high); CP(obs_noise_mean); CP(obs_noise_std); CP(obs_init_noise);
     d.rew_generic = f.rew_generic; d.rew_n = f.rew_n; d.rew_potential = f.rew_potential; d.rew_nterms = f.rew_nterms;
@@ -935,6 +1044,7 @@ struct FwHandle {
     void* r_buf; int32_t* i_buf; void* err_ring;
     double* metrics; double* ep_ret; int32_t* ep_len; int32_t* ep_term;
     void* w_real; int32_t* w_int;          // scratch between the kernels of one step
+    double* wp_tasks; int32_t* wp_task_of_env;   // waypoint head: device copies of the task table
     Scratch<double> w64;
     Scratch<float> w32;
     int sm_count;
@@ -975,7 +1085,8 @@ static int launch_rk45(FwHandle* h, const DCfg<T>& c, const Soa<T>& S, const Scr
     const int g0 = (h->n + 127) / 128;
     rk45_init_kernel<T, TURB><<<g0, 128, 0, st>>>(c, S, io, W, grid * NT);
     k<<<grid, NT, smem, st>>>(c, S, W);
-    if (h->cfg.obs_generic) head_kernel<T, TURB, true><<<g0, 128, 0, st>>>(c, S, io, W);
+    if (h->cfg.env_kind == FW_ENV_WAYPOINT) waypoint_head_kernel<T, TURB><<<g0, 128, 0, st>>>(c, S, io, W);
+    else if (h->cfg.obs_generic) head_kernel<T, TURB, true><<<g0, 128, 0, st>>>(c, S, io, W);
     else head_kernel<T, TURB, false><<<g0, 128, 0, st>>>(c, S, io, W);
     CK(cudaGetLastError());
     return FW_OK;
@@ -984,7 +1095,8 @@ template <typename T, bool TURB>
 static int launch_rk4(FwHandle* h, const DCfg<T>& c, const Soa<T>& S, const Scratch<T>& W, const StepIO& io, cudaStream_t st) {
     const int g0 = (h->n + 127) / 128;
     rk4_kernel<T, TURB><<<g0, 128, 0, st>>>(c, S, io, W);
-    if (h->cfg.obs_generic) head_kernel<T, TURB, true><<<g0, 128, 0, st>>>(c, S, io, W);
+    if (h->cfg.env_kind == FW_ENV_WAYPOINT) waypoint_head_kernel<T, TURB><<<g0, 128, 0, st>>>(c, S, io, W);
+    else if (h->cfg.obs_generic) head_kernel<T, TURB, true><<<g0, 128, 0, st>>>(c, S, io, W);
     else head_kernel<T, TURB, false><<<g0, 128, 0, st>>>(c, S, io, W);
     CK(cudaGetLastError());
     return FW_OK;
@@ -1009,7 +1121,31 @@ extern "C" {
 const char* fw_last_error(void) { return g_err; }
 int fw_abi_version(void) { return FW_ABI_VERSION; }
 int fw_config_size(void) { return (int)sizeof(FwConfig); }
-int fw_obs_dim(const FwHandle* h) { return h ? (h->cfg.obs_generic ? h->cfg.obs_len * h->cfg.obs_n : FW_NOBS) : FW_EINVAL; }
+int fw_obs_dim(const FwHandle* h) {
+    if (!h) return FW_EINVAL;
+    if (h->cfg.env_kind == FW_ENV_WAYPOINT) return FW_NOBS_WAYPOINT;
+    return h->cfg.obs_generic ? h->cfg.obs_len * h->cfg.obs_n : FW_NOBS;
+}
+
+int fw_set_waypoint_tasks(FwHandle* h, const double* tasks_dev, int32_t n_tasks, int32_t wp_len,
+                          const int32_t* task_of_env_dev, void* stream) {
+    if (!h || !tasks_dev || !task_of_env_dev || n_tasks <= 0 || wp_len < 2 || h->cfg.env_kind != FW_ENV_WAYPOINT) {
+        snprintf(g_err, sizeof(g_err), "fw_set_waypoint_tasks: needs a waypoint handle, n_tasks > 0, wp_len >= 2");
+        return FW_EINVAL;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaFree(h->wp_tasks); cudaFree(h->wp_task_of_env);
+    const size_t bytes = sizeof(double) * (size_t)n_tasks * wp_len * FW_WP_ROW;
+    CK(cudaMalloc((void**)&h->wp_tasks, bytes));
+    CK(cudaMalloc((void**)&h->wp_task_of_env, sizeof(int32_t) * h->n));
+    CK(cudaMemcpyAsync(h->wp_tasks, tasks_dev, bytes, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(h->wp_task_of_env, task_of_env_dev, sizeof(int32_t) * h->n, cudaMemcpyDeviceToDevice, st));
+    h->s64.wp_tasks = h->s32.wp_tasks = h->wp_tasks;
+    h->s64.wp_task_of_env = h->s32.wp_task_of_env = h->wp_task_of_env;
+    h->s64.wp_n_tasks = h->s32.wp_n_tasks = n_tasks;
+    h->s64.wp_len = h->s32.wp_len = wp_len;
+    return FW_OK;
+}
 
 int fw_create(const FwConfig* cfg, int32_t n_envs, int32_t device, FwHandle** out) {
     if (!cfg || !out || n_envs <= 0) { snprintf(g_err, sizeof(g_err), "fw_create: bad arguments"); return FW_EINVAL; }
@@ -1063,8 +1199,8 @@ int fw_create(const FwConfig* cfg, int32_t n_envs, int32_t device, FwHandle** ou
     CK(cudaMemset(h->ep_ret, 0, sizeof(double) * n));
     CK(cudaMemset(h->ep_len, 0, sizeof(int32_t) * n));
     CK(cudaMemset(h->ep_term, 0, sizeof(int32_t) * n));
-    h->s64 = Soa<double>{(double*)h->r_buf, h->i_buf, (double*)h->err_ring, h->metrics, h->ep_ret, h->ep_len, h->ep_term, nullptr, 0, n_envs};
-    h->s32 = Soa<float>{(float*)h->r_buf, h->i_buf, (float*)h->err_ring, h->metrics, h->ep_ret, h->ep_len, h->ep_term, nullptr, 0, n_envs};
+    h->s64 = Soa<double>{(double*)h->r_buf, h->i_buf, (double*)h->err_ring, h->metrics, h->ep_ret, h->ep_len, h->ep_term, nullptr, 0, n_envs, nullptr, nullptr, 0, 0};
+    h->s32 = Soa<float>{(float*)h->r_buf, h->i_buf, (float*)h->err_ring, h->metrics, h->ep_ret, h->ep_len, h->ep_term, nullptr, 0, n_envs, nullptr, nullptr, 0, 0};
     CK(cudaDeviceSynchronize());
     *out = h;
     return FW_OK;
@@ -1076,6 +1212,7 @@ int fw_destroy(FwHandle* h) {
     cudaDeviceSynchronize();
     cudaFree(h->r_buf); cudaFree(h->i_buf); cudaFree(h->err_ring); cudaFree(h->metrics);
     cudaFree(h->ep_ret); cudaFree(h->ep_len); cudaFree(h->ep_term); cudaFree(h->w_real); cudaFree(h->w_int);
+    cudaFree(h->wp_tasks); cudaFree(h->wp_task_of_env);
     delete h;
     return FW_OK;
 }
@@ -1084,6 +1221,7 @@ int fw_reset(FwHandle* h, const uint8_t* mask_dev, const double* state_dev, cons
              const double* noise_dev, int32_t noise_len, float* obs_dev, double* obs64_dev, void* stream) {
     if (!h) return FW_EINVAL;
     if (noise_dev && noise_len <= 0) { snprintf(g_err, sizeof(g_err), "fw_reset: noise_len must be > 0"); return FW_EINVAL; }
+    if (h->cfg.env_kind == FW_ENV_WAYPOINT && !h->wp_tasks) { snprintf(g_err, sizeof(g_err), "fw_reset: call fw_set_waypoint_tasks first"); return FW_EINVAL; }
     cudaStream_t st = (cudaStream_t)stream;
     h->s64.noise = noise_dev; h->s64.noise_len = noise_len;
     h->s32.noise = noise_dev; h->s32.noise_len = noise_len;

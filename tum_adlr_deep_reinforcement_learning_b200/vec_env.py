@@ -352,3 +352,76 @@ class FixedWingAircraft:
 
     def close(self):
         self._v.close()
+
+
+WAYPOINT_KEYS = ("position_n", "position_e", "position_d", "roll", "pitch", "yaw", "velocity_u", "velocity_v",
+                 "velocity_w", "wind_n", "wind_e", "wind_d", "omega_p", "omega_q", "omega_r")
+
+
+def waypoint_tasks_to_array(tasks):
+    """List of tasks, each a sequence of waypoint dicts as in magpie/magpy/tasks/*/*.npy (keys position_*, roll, pitch,
+    yaw, velocity_*, wind_*; optional omega_*), -> [n_tasks, wp_len, 15] float64 with NaN for missing omega."""
+    wp_len = min(len(t) for t in tasks)
+    out = np.full((len(tasks), wp_len, 15), np.nan)
+    for i, task in enumerate(tasks):
+        for j in range(wp_len):
+            for k, key in enumerate(WAYPOINT_KEYS):
+                if key in task[j]:
+                    out[i, j, k] = float(task[j][key])
+    assert not np.isnan(out[:, :, :12]).any(), "waypoints need position, attitude, velocity and wind"
+    return out
+
+
+class WaypointVecEnv:
+    """`FixedWingAircraft_simple` (magpie/magpy/simple_train.py:197-702) behind the VecEnv step contract: every env flies
+    the waypoint chain of its task; reaching a waypoint (0.5 m box) teleports to the next leg's start, reward
+    exp(-sum |position error| / 6), 12 raw states observed, 500 steps per episode, commands passed straight through."""
+
+    def __init__(self, num_envs, tasks, task_of_env=None, device=0, seed=0, env_id_offset=0, sim_config_kw=None,
+                 config_kw=None, precision="f64", integrator="rk45", rk4_substeps=4):
+        self.cfg = build_config(env_kind="waypoint", config_kw=config_kw, sim_config_kw=sim_config_kw, seed=seed,
+                                env_id_offset=env_id_offset, precision=precision, integrator=integrator,
+                                rk4_substeps=rk4_substeps)
+        self.num_envs = int(num_envs)
+        self.sim = bt.BatchedFixedWing(self.num_envs, cfg=self.cfg, device=device)
+        self.device = self.sim.device
+        self.tasks = tasks if isinstance(tasks, np.ndarray) else waypoint_tasks_to_array(tasks)
+        if task_of_env is None:
+            task_of_env = np.arange(self.num_envs) % self.tasks.shape[0]
+        self.task_of_env = np.asarray(task_of_env, dtype=np.int32)
+        self.sim.set_waypoint_tasks(self.tasks, self.task_of_env)
+        f32max = np.finfo(np.float32).max
+        self.observation_space = Box(np.full(12, -f32max), np.full(12, f32max))
+        self.action_space = Box(np.array([-1, -1, 0]), np.array([1, 1, 1]))        # simple_train.py:275-279
+
+    def reset_task(self, task_of_env):
+        """reset_task(idx) for every env (simple_train.py:368-375): takes effect at the next reset."""
+        self.task_of_env = np.asarray(task_of_env, dtype=np.int32)
+        self.sim.set_waypoint_tasks(self.tasks, self.task_of_env)
+
+    def reset_tensor(self):
+        return self.sim.reset()
+
+    def step_tensor(self, actions):
+        return self.sim.step(actions, auto_reset=True)
+
+    def reset(self):
+        return self.sim.reset().cpu().numpy()
+
+    def step(self, actions):
+        a = torch.as_tensor(np.asarray(actions, dtype=np.float32), device=self.device).contiguous()
+        obs, rew, done = self.sim.step(a, auto_reset=True)
+        done_np = done.cpu().numpy().astype(bool)
+        infos = [_EMPTY_INFO] * self.num_envs
+        if done_np.any():
+            idx = np.flatnonzero(done_np)
+            rows = self.sim.episode_info_rows(torch.as_tensor(idx, device=self.device))
+            infos = list(infos)
+            for row, i in zip(rows, idx):
+                term = int(row[30])
+                infos[i] = {"termination": TERM_NAMES.get(term, term), "terminal_observation": row[31:].astype(np.float32),
+                            "episode": {"r": float(row[28]), "l": int(row[29])}}
+        return obs.cpu().numpy(), rew.cpu().numpy(), done_np, infos
+
+    def close(self):
+        self.sim.close()
