@@ -61,9 +61,20 @@ def test_unsupported_configs_fail_loudly():
     with pytest.raises(NotImplementedError):
         C.build_config(config_kw={"observation": {"step": 2}})
     with pytest.raises(NotImplementedError):
-        C.build_config(config_kw={"target": {"states": {0: {"class": "sinusoidal"}}}})
+        C.build_config(config_kw={"target": {"states": {0: {"class": "attitude_angular"}}}})
     with pytest.raises(NotImplementedError):
-        C.build_config(config_kw={"reward": {"form": "potential"}})
+        C.build_config(config_kw={"reward": {"factors": {0: {"type": "int_error"}}}})
+    with pytest.raises(NotImplementedError):
+        C.build_config(config_kw={"observation": {"states": {0: {"name": "position_n"}}}})
+
+
+def test_general_env_head_configs_build():
+    c = C.build_config(config_kw={"reward": {"form": "potential"}, "observation": {"length": 3, "normalize": True},
+                                  "target": {"states": {0: {"class": "linear", "slope_low": 1, "slope_high": 2}}}})
+    assert c.rew_generic == 1 and c.rew_potential == 1 and c.obs_generic == 1 and c.obs_len == 3 and c.obs_normalize == 1
+    assert list(c.tgt_class) == [2, 0, 1] and c.tgt_slope_high[0] == 2
+    w = C.build_config(env_kind="waypoint")
+    assert w.env_kind == 1 and C.obs_dim(w) == 12 and w.turb_block_len == 300 and w.steps_max == 500
 
 
 def test_no_cpu_fallback():
