@@ -221,6 +221,19 @@ int fw_create(const FwConfig* cfg, int32_t n_envs, int32_t device, FwHandle** ou
 int fw_destroy(FwHandle* h);
 int fw_obs_dim(const FwHandle* h);   /* floats per observation row of this handle */
 
+/* Measurement aid (no reference counterpart; bench.py's per-kernel roofline): with profiling on, every fw_step /
+ * fw_step_random step records CUDA events on the launch stream around each of its kernels and ends with an event
+ * synchronise; fw_get_profile returns the summed durations in ms of {init, integrate (RK45 attempt loop or RK4),
+ * head} and the number of steps they cover.  fw_set_profiling(h, 0 or 1) also clears the sums. */
+int fw_set_profiling(FwHandle* h, int32_t on);
+
+/* fw_step with auto_reset recomputes, on a side stream of the handle, the precomputed next-episode rows that the step
+ * consumed; the next fw_step / fw_reset waits for that work by itself.  fw_join makes `stream` wait for it explicitly:
+ * call it before ending a CUDA stream capture that contains fw_step calls (a capture must not end with unjoined work)
+ * or before handing the handle to another thread.  No reference counterpart. */
+int fw_join(FwHandle* h, void* stream);
+int fw_get_profile(const FwHandle* h, double* ms_sum3, int64_t* steps);
+
 /* Waypoint head only: the task table.  tasks_dev [n_tasks, wp_len, FW_WP_ROW] f64 (device, copied), task_of_env_dev [n]
  * int32 (device, copied): the task every env flies.  Replaces FixedWingAircraft_simple.sample_tasks / reset_task
  * (simple_train.py:330-375).  Must be called before the first fw_reset. */

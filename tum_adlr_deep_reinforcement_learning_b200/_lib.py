@@ -3,7 +3,7 @@ is missing or cannot be loaded: there is no CPU / PyTorch fallback for the env s
 import ctypes
 import os
 
-from .build import LIB_PATH
+from .build import LIB_PATH as _DEFAULT_LIB_PATH
 from .config import FwConfig
 
 _lib = None
@@ -18,6 +18,8 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
+    # FWB200_LIB: load another build of the same library (kernel A/B runs of tools/ab_bench.py)
+    LIB_PATH = os.environ.get("FWB200_LIB", _DEFAULT_LIB_PATH)
     if not os.path.exists(LIB_PATH):
         raise FwError("%s is missing — run `python -c 'import __graft_entry__ as g; g.build()'` "
                       "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
@@ -36,6 +38,9 @@ def lib():
     L.fw_measure_fma_peak.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(ctypes.c_double)]
     L.fw_debug_math.argtypes = [ctypes.c_int32, _vp, _vp, _vp, ctypes.c_int32, _vp]
     L.fw_obs_dim.argtypes = [_vp]
+    L.fw_join.argtypes = [_vp, _vp]
+    L.fw_set_profiling.argtypes = [_vp, ctypes.c_int32]
+    L.fw_get_profile.argtypes = [_vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]
     L.fw_set_waypoint_tasks.argtypes = [_vp, _vp, ctypes.c_int32, ctypes.c_int32, _vp, _vp]
     L.fw_config_size.restype = ctypes.c_int
     L.fw_abi_version.restype = ctypes.c_int
@@ -52,4 +57,4 @@ def check(rc, what):
 
 EXPORTS = ("fw_create", "fw_destroy", "fw_last_error", "fw_abi_version", "fw_reset", "fw_step", "fw_step_random",
            "fw_get_episode_info", "fw_get_field", "fw_set_field", "fw_gae", "fw_measure_fma_peak", "fw_debug_math",
-           "fw_obs_dim", "fw_set_waypoint_tasks")
+           "fw_obs_dim", "fw_set_waypoint_tasks", "fw_set_profiling", "fw_get_profile", "fw_join")

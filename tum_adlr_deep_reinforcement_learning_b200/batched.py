@@ -109,6 +109,24 @@ class BatchedFixedWing:
                                              _ptr(self.done), self._stream()), "fw_step_random")
         return self.obs, self.rew, self.done
 
+    def join(self):
+        """Make the current stream wait for the side-stream refill of precomputed reset rows (fw_join): needed before
+        a CUDA graph capture that contains step() calls ends."""
+        _lib.check(_lib.lib().fw_join(self._h, self._stream()), "fw_join")
+
+    def set_profiling(self, on=True):
+        """Per-kernel CUDA-event timing of every following step (fw_set_profiling); clears the sums."""
+        _lib.check(_lib.lib().fw_set_profiling(self._h, int(bool(on))), "fw_set_profiling")
+
+    def profile(self):
+        """{"init_ms", "integrate_ms", "head_ms"}: mean duration per step of each kernel since set_profiling."""
+        import ctypes
+        ms = (ctypes.c_double * 3)()
+        steps = ctypes.c_int64()
+        _lib.check(_lib.lib().fw_get_profile(self._h, ms, ctypes.byref(steps)), "fw_get_profile")
+        k = max(int(steps.value), 1)
+        return {"init_ms": ms[0] / k, "integrate_ms": ms[1] / k, "head_ms": ms[2] / k, "steps": int(steps.value)}
+
     def episode_info(self):
         """(term_code [n] i32, metrics [n,28] f64, episode return [n] f64, episode length [n] i32) device tensors,
         valid for the envs whose done flag was set by the last step.  The tensors are reused by the next call."""

@@ -396,39 +396,54 @@ template <typename T> __device__ __noinline__ T pow_ni(T x, T y) { return M<T>::
 //               attempt, so ONE inlined RHS instance serves all lanes at full occupancy of the warp; a lane whose env
 //               finished its [0, dt] interval pulls the next env from a queue instead of idling (the number of
 //               attempts per env-step varies 2..7, which cost 32 % of the lanes when envs were pinned to threads).
+// A load the compiler may not satisfy from a register copy: the init kernel re-reads y0 and f0 after the second RHS
+// evaluation instead of keeping 38 values live across it (which cost a fourth warp per scheduler, or spills).
+__device__ __forceinline__ double ld_again(const double* p) {
+    double v;
+    asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float ld_again(const float* p) {
+    float v;
+    asm volatile("ld.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// ys enters holding y0 (which is also at ysrc[i * n]); f0 is written to f0dst[i * n] (i < FW_NK).
 template <typename T, bool TURB>
-__device__ __forceinline__ int rk45_init(const DCfg<T>& c, const DynCtx<T>& x, const T (&y)[FW_NY], T elev0, T ail0,
-                                         T (&f0)[FW_NY], T& h_abs) {
+__device__ __forceinline__ int rk45_init(const DCfg<T>& c, const DynCtx<T>& x, T (&ys)[FW_NY], const T* ysrc, T* f0dst,
+                                         int n, T elev0, T ail0, T& h_abs) {
     const T rtol = c.rtol, atol = c.atol, t_bound = c.dt;
-    T ys[FW_NY], dyv[FW_NY];
+    T dyv[FW_NY];
     T d1 = 0, h0 = 0;
     int rc = 0;
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
-#pragma unroll
-        for (int i = 0; i < FW_NY; ++i) ys[i] = (pass == 0) ? y[i] : y[i] + h0 * f0[i];
         rc = rhs<T, TURB>(c, x, ys, pass == 0, elev0, ail0, dyv);
         if (rc) return rc;
         if (pass == 0) {
             T s0 = 0, s1 = 0;
 #pragma unroll
             for (int i = 0; i < FW_NY; ++i) {
-                const T inv = (T)1 / (atol + M<T>::fabs(y[i]) * rtol);
-                const T a = y[i] * inv, b = dyv[i] * inv;
+                const T inv = (T)1 / (atol + M<T>::fabs(ys[i]) * rtol);
+                const T a = ys[i] * inv, b = dyv[i] * inv;
                 s0 += a * a;
                 s1 += b * b;
-                f0[i] = dyv[i];
+                if (i < FW_NK) f0dst[i * n] = dyv[i];
             }
             const T d0 = M<T>::sqrt(s0) / M<T>::sqrt((T)FW_NY);
             d1 = M<T>::sqrt(s1) / M<T>::sqrt((T)FW_NY);
             h0 = (d0 < (T)1e-5 || d1 < (T)1e-5) ? (T)1e-6 : (T)0.01 * d0 / d1;
             h0 = M<T>::fmin(h0, t_bound);
+#pragma unroll
+            for (int i = 0; i < FW_NY; ++i) ys[i] = ys[i] + h0 * dyv[i];
         } else {
             T s2 = 0;
 #pragma unroll
             for (int i = 0; i < FW_NY; ++i) {
-                const T inv = (T)1 / (atol + M<T>::fabs(y[i]) * rtol);
-                const T d = (dyv[i] - f0[i]) * inv;
+                const T y0 = ld_again(ysrc + i * n), f0 = (i < FW_NK) ? ld_again(f0dst + i * n) : (T)0;
+                const T inv = (T)1 / (atol + M<T>::fabs(y0) * rtol);
+                const T d = (dyv[i] - f0) * inv;
                 s2 += d * d;
             }
             const T d2 = (M<T>::sqrt(s2) / M<T>::sqrt((T)FW_NY)) / h0;
@@ -517,6 +532,52 @@ template <typename F> __device__ __forceinline__ F np_sum(const F* a, int n) {
     F res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
     for (; i < n; ++i) res += a[i];
     return res;
+}
+
+// the same order with a compile-time length: everything stays in registers
+template <typename F, int N> __device__ __forceinline__ F np_sum_n(const F (&a)[N]) {
+    if (N < 8) {
+        F s = 0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) s += a[i];
+        return s;
+    }
+    F r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = a[j < N ? j : 0];
+#pragma unroll
+    for (int i = 8; i < N - (N % 8); i += 8)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] += a[i + j < N ? i + j : 0];
+    F res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+#pragma unroll
+    for (int i = (N < 8 ? 0 : N - (N % 8)); i < N; ++i) res += a[i];
+    return res;
+}
+
+// sum over the trailing NP action deltas |a_t - a_{t-1}|, 3 columns each, chronological order (oldest first), of the
+// action ring (age 1 = most recent previous action) plus the current action; F = float for float32 actions
+template <int NP, typename F, typename T>
+__device__ __forceinline__ F ring_delta_sum(const T (&cur)[3], const T (&ring)[12]) {
+    F d[NP * 3];
+#pragma unroll
+    for (int e = 0; e < NP * 3; ++e) {
+        const int age = NP - e / 3, j = e % 3;
+        const T newer = (age == 1) ? cur[j] : ring[(age >= 2 ? age - 2 : 0) * 3 + j];
+        const F x = (F)newer - (F)ring[(age - 1) * 3 + j];
+        d[e] = M<F>::fabs(x);
+    }
+    return np_sum_n<F, NP * 3>(d);
+}
+template <typename F, typename T>
+__device__ __forceinline__ F ring_delta_sum_np(int np_, const T (&cur)[3], const T (&ring)[12]) {
+    switch (np_) {
+        case 1: return ring_delta_sum<1, F, T>(cur, ring);
+        case 2: return ring_delta_sum<2, F, T>(cur, ring);
+        case 3: return ring_delta_sum<3, F, T>(cur, ring);
+        case 4: return ring_delta_sum<4, F, T>(cur, ring);
+        default: return (F)0;
+    }
 }
 
 // register-resident view of one env during a step

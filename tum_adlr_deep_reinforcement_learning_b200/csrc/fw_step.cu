@@ -40,14 +40,99 @@ __device__ __noinline__ void reset_env_noinline(const DCfg<T>& c, const Soa<T>& 
     reset_env<T>(c, S, env, nullptr, nullptr, obs, obs64);
 }
 
+// Precomputed next-episode rows.  FixedWingAircraft.reset depends only on (seed, env id, episode number) — never on the
+// trajectory that just ended — so the complete post-reset row of every env (state SoA row, first error-ring entry, reset
+// observation) is computed AHEAD of time into a second SoA.  When an episode ends, head_kernel copies that row into
+// place (a few hundred independent loads/stores) instead of running the ~5 k-instruction reset on one lane while the
+// 31 other lanes of the warp — and, because one wave of warps runs the kernel, the whole step — wait for it; the
+// consumed rows are recomputed by refill_kernel on a side stream while the next step integrates.
+template <typename T> struct Spare {
+    Soa<T> S2;        // r [RF_COUNT][n], i [IF_COUNT][n], err_ring [3][n] of the precomputed rows
+    float* obs;       // [n][obs_dim]
+    double* obs64;    // [n][obs_dim]
+    int32_t* list;    // [2][n] envs that consumed their row at a step (indexed by step parity)
+    int32_t* count;   // [2]
+    int on;           // 0: inline reset (waypoint env)
+};
+
+// Warp-cooperative: for every lane whose episode ended (`mine`), all converged lanes of the warp copy that env's
+// precomputed row, field f by lane f mod width, every lane's loads in flight at once — one DRAM round trip per
+// finished env instead of one per field.  IF_GOAL_ACHIEVED survives a reset (fixed_wing.py keeps goal_achieved across
+// episodes); IF_NFEV / IF_NATT keep the diagnostics of the step that ended the episode.
 template <typename T>
-__global__ void reset_kernel(const __grid_constant__ DCfg<T> c, const Soa<T> S, const uint8_t* mask,
+__device__ __forceinline__ void take_spare_warp(const Soa<T>& S, const Spare<T>& P, bool mine, int env, int odim,
+                                                float* obs, double* obs64) {
+    const unsigned act = __activemask();
+    unsigned dm = __ballot_sync(act, mine);
+    if (!dm) return;
+    __syncwarp(act);                       // the owners' earlier stores to their rows are ordered before the copies
+    const int lane = threadIdx.x & 31;
+    const int rank = __popc(act & ((1u << lane) - 1u)), width = __popc(act);
+    const int n = S.n;
+    while (dm) {
+        const int owner = __ffs(dm) - 1;
+        dm &= dm - 1;
+        const int e = __shfl_sync(act, env, owner);
+        {
+            const T* src = P.S2.r + e;
+            T* dst = S.r + e;
+#pragma unroll 1
+            for (int f0 = rank; f0 < RF_COUNT; f0 += 8 * width) {
+                T tmp[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) tmp[j] = (f0 + j * width < RF_COUNT) ? src[(size_t)(f0 + j * width) * n] : (T)0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) if (f0 + j * width < RF_COUNT) dst[(size_t)(f0 + j * width) * n] = tmp[j];
+            }
+        }
+        {
+            const int32_t* src = P.S2.i + e;
+            int32_t* dst = S.i + e;
+#pragma unroll 1
+            for (int f0 = rank; f0 < IF_COUNT; f0 += 2 * width) {
+                int32_t tmp[2];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) tmp[j] = (f0 + j * width < IF_COUNT) ? src[(size_t)(f0 + j * width) * n] : 0;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int f = f0 + j * width;
+                    if (f < IF_COUNT && f != IF_GOAL_ACHIEVED && f != IF_NFEV && f != IF_NATT) dst[(size_t)f * n] = tmp[j];
+                }
+            }
+        }
+        if (rank < 3) S.err_ring[(size_t)rank * n + e] = P.S2.err_ring[(size_t)rank * n + e];
+        for (int q = rank; q < odim; q += width) {
+            if (obs) obs[(size_t)e * odim + q] = P.obs[(size_t)e * odim + q];
+            if (obs64) obs64[(size_t)e * odim + q] = P.obs64[(size_t)e * odim + q];
+        }
+    }
+}
+
+// the row of the episode after the one env is in now (main S): spare.episode := main.episode, then reset the spare
+template <typename T>
+__device__ void make_spare(const DCfg<T>& c, const Soa<T>& S, const Spare<T>& P, int env) {
+    P.S2.i[IF_EPISODE * S.n + env] = S.i[IF_EPISODE * S.n + env];
+    reset_env<T>(c, P.S2, env, nullptr, nullptr, P.obs, P.obs64);
+}
+
+template <typename T>
+__global__ void reset_kernel(const __grid_constant__ DCfg<T> c, const Soa<T> S, const Spare<T> P, const uint8_t* mask,
                              const double* state_in, const double* target_in, float* obs, double* obs64) {
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
     if (env >= S.n) return;
     if (mask && !mask[env]) return;
     if (c.env_kind == FW_ENV_WAYPOINT) { wp_reset_env<T>(c, S, env, obs, obs64); return; }
     reset_env<T>(c, S, env, state_in, target_in, obs, obs64);
+    if (P.on) make_spare<T>(c, S, P, env);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(32) refill_kernel(const __grid_constant__ DCfg<T> c, const Spare<T> P, int parity) {
+    const int n = P.S2.n;
+    const int cnt = P.count[parity];
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < cnt; j += gridDim.x * blockDim.x)
+        // the consumed row carried episode e + 1, which is what the spare's own counter still says: this makes e + 2
+        reset_env<T>(c, P.S2, P.list[(size_t)parity * n + j], nullptr, nullptr, P.obs, P.obs64);
 }
 
 // sum |diff| of one column over the trailing window, accumulated in float32 like
@@ -156,18 +241,19 @@ __device__ __forceinline__ void load_dyn(const DCfg<T>& c, const Soa<T>& S, cons
 
 // ---- kernel A0: RungeKutta.__init__ + select_initial_step for every env, lock step ----
 template <typename T, bool TURB>
-__global__ void __launch_bounds__(128, 3) rk45_init_kernel(const __grid_constant__ DCfg<T> c, const Soa<T> S, const StepIO io,
-                                                        const Scratch<T> W, int attempt_threads) {
+__global__ void __launch_bounds__(128, 4) rk45_init_kernel(const __grid_constant__ DCfg<T> c, const Soa<T> S, const StepIO io,
+                                                        const Scratch<T> W, int attempt_threads, int32_t* done_count) {
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = S.n;
-    if (env == 0) *W.counter = attempt_threads;      // queue head: the first attempt_threads envs are pre-assigned
+    if (env == 0) {
+        *W.counter = attempt_threads;      // queue head: the first attempt_threads envs are pre-assigned
+        *done_count = 0;                   // this step's list of envs that take their precomputed reset row
+    }
     if (env >= n) return;
-    T y[FW_NY], f0[FW_NY], h_abs = 0, elev0, ail0;
+    T y[FW_NY], h_abs = 0, elev0, ail0;
     DynCtx<T> x;
     load_dyn<T, TURB>(c, S, io, env, y, x, elev0, ail0);
-    const int rc = rk45_init<T, TURB>(c, x, y, elev0, ail0, f0, h_abs);
-#pragma unroll
-    for (int i = 0; i < FW_NK; ++i) W.f0[i * n + env] = f0[i];
+    const int rc = rk45_init<T, TURB>(c, x, y, S.r + (size_t)RF_Y * n + env, W.f0 + env, n, elev0, ail0, h_abs);
     W.hinit[env] = h_abs;
 #pragma unroll
     for (int k = 0; k < 3; ++k) { W.cmd[k * n + env] = x.cmd[k]; W.turb[k * n + env] = x.tl[k]; W.turb[(3 + k) * n + env] = x.ta[k]; }
@@ -351,9 +437,10 @@ __global__ void __maxnreg__(255) rk45_attempt_kernel(const __grid_constant__ DCf
 // ---- fixed-step modes: lock-step integrate kernel (no adaptivity, no divergence to rebalance) ----
 template <typename T, bool TURB>
 __global__ void __launch_bounds__(128) rk4_kernel(const __grid_constant__ DCfg<T> c, const Soa<T> S, const StepIO io,
-                                                  const Scratch<T> W) {
+                                                  const Scratch<T> W, int32_t* done_count) {
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = S.n;
+    if (env == 0) *done_count = 0;
     if (env >= n) return;
     T y[FW_NY], elev0, ail0;
     DynCtx<T> x;
@@ -416,22 +503,107 @@ __device__ __forceinline__ int post_step_commit(const DCfg<T>& c, const DynCtx<T
     return fail;
 }
 
+// sum of the last `cnt` entries of history["error"] per target state (end_error, fixed_wing.py:1690-1700), added in
+// chronological order.  The ring rows are read ten entries x three states at a time: one load per addition was one
+// exposed DRAM round trip per addition, 150 in a row, and — one wave of warps running the kernel — stretched every
+// step in which any episode ended by 70 us.
+template <typename T>
+__device__ __noinline__ void end_error_sums(const Soa<T>& S, int env, int n_err, int cnt, bool have_new,
+                                            const T (&e_new)[3], T (&s50)[3]) {
+    const int n = S.n;
+    const int newest = (n_err - 1) % FW_END_ERR_WINDOW;
+    s50[0] = s50[1] = s50[2] = 0;
+#pragma unroll 1
+    for (int q0 = 0; q0 < cnt; q0 += 10) {
+        T v[3][10];
+#pragma unroll
+        for (int j = 0; j < 10; ++j) {
+            const int q = q0 + j;
+            const int slot = (n_err - cnt + (q < cnt ? q : 0)) % FW_END_ERR_WINDOW;
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                v[k][j] = (q >= cnt) ? (T)0 : (slot == newest && have_new) ? e_new[k]
+                                                                           : S.err_ring[(size_t)(slot * 3 + k) * n + env];
+        }
+#pragma unroll
+        for (int j = 0; j < 10; ++j)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) s50[k] += v[k][j];
+    }
+}
+
 // ---- kernel B: everything after the integrator (once per step, high occupancy) ----
+// One wave of warps runs this kernel, so its duration is the critical path of ONE warp: every exposed DRAM round trip
+// adds to it in full.  All loads are therefore issued up front (a load cannot be moved above a store that may alias
+// it, so no store happens before the last load; only the two goal-ring words per goal wait for `steps`), and all
+// stores sit at the end.  Splitting the kernel into load -> compute -> store phases per subsystem was measured at
+// 1.5x the duration (one round trip per phase).
+// The same sums with the whole warp fetching: every lane loads 5 of the (up to) 150 ring entries of a finished env —
+// one DRAM round trip instead of five — and the owner adds them up in chronological order through shuffles.  The
+// entry of the current step is already in the ring (the owner stored it; __syncwarp orders that store before the loads).
+template <typename T>
+__device__ __forceinline__ void end_error_sums_warp(const Soa<T>& S, bool mine, int env, int n_err, T (&s50)[3]) {
+    const unsigned act = __activemask();
+    s50[0] = s50[1] = s50[2] = 0;
+    if (act != 0xffffffffu) {              // ragged last block: every finished env sums for itself
+        if (mine) {
+            const T none[3] = {0, 0, 0};
+            end_error_sums<T>(S, env, n_err, n_err < FW_END_ERR_WINDOW ? n_err : FW_END_ERR_WINDOW, false, none, s50);
+        }
+        return;
+    }
+    unsigned dm = __ballot_sync(act, mine);
+    if (!dm) return;
+    __syncwarp(act);
+    const int lane = threadIdx.x & 31, n = S.n;
+    while (dm) {
+        const int owner = __ffs(dm) - 1;
+        dm &= dm - 1;
+        const int e = __shfl_sync(act, env, owner), ne = __shfl_sync(act, n_err, owner);
+        const int cnt = ne < FW_END_ERR_WINDOW ? ne : FW_END_ERR_WINDOW;
+        T v[5];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            const int t = j * 32 + lane, q = t / 3, k = t - 3 * q;          // entry q (chronological), state k
+            const int slot = (ne - cnt + (q < cnt ? q : 0)) % FW_END_ERR_WINDOW;
+            v[j] = (q < cnt) ? S.err_ring[(size_t)(slot * 3 + k) * n + e] : (T)0;
+        }
+        T a0 = 0, a1 = 0, a2 = 0;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+#pragma unroll 1
+            for (int l = 0; l < 32; l += 3) {                              // t = j * 32 + l; state k = t % 3 rotates
+                const int k0 = (j * 32 + l) % 3;
+                const T x0 = __shfl_sync(act, v[j], l), x1 = __shfl_sync(act, v[j], (l + 1) & 31),
+                        x2 = __shfl_sync(act, v[j], (l + 2) & 31);
+                const bool h1 = l + 1 < 32, h2 = l + 2 < 32;
+                // entries beyond 3 * cnt were loaded as 0; adding 0 leaves the sums as they are
+                if (k0 == 0) { a0 += x0; if (h1) a1 += x1; if (h2) a2 += x2; }
+                else if (k0 == 1) { a1 += x0; if (h1) a2 += x1; if (h2) a0 += x2; }
+                else { a2 += x0; if (h1) a0 += x1; if (h2) a1 += x2; }
+            }
+        }
+        if (lane == owner) { s50[0] = a0; s50[1] = a1; s50[2] = a2; }
+    }
+}
+
 template <typename T, bool TURB, bool GENERIC>
-__global__ void __launch_bounds__(128, 4) head_kernel(const __grid_constant__ DCfg<T> c, const Soa<T> S, const StepIO io,
-                                                   const Scratch<T> W) {
+__global__ void __launch_bounds__(64, 8) head_kernel(const __grid_constant__ DCfg<T> c, const Soa<T> S, const StepIO io,
+                                                  const Scratch<T> W, const Spare<T> P, int parity) {
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = S.n;
     if (env >= n) return;
     T* r = S.r + env;
     int32_t* ii = S.i + env;
+
+    // ======================= loads =======================
     int fail = W.fail[env];
     T y[FW_NY];
 #pragma unroll
-    for (int i = 0; i < FW_NY; ++i) y[i] = fail ? r[(RF_Y + i) * n] : W.ytmp[i * n + env];
-    const T roll_prev = r[RF_ROLL * n], pitch_prev = r[RF_PITCH * n], Va_prev = r[RF_VA * n];
-    const T alpha_prev = r[RF_ALPHA * n], beta_prev = r[RF_BETA * n];
-    const T omega_prev[3] = {r[(RF_Y + 4) * n], r[(RF_Y + 5) * n], r[(RF_Y + 6) * n]};
+    for (int i = 0; i < FW_NY; ++i) y[i] = W.ytmp[i * n + env];     // not waiting for `fail`: a raise is the rare case
+    T roll = r[RF_ROLL * n], pitch = r[RF_PITCH * n], Va = r[RF_VA * n], alpha = r[RF_ALPHA * n], beta = r[RF_BETA * n];
+    // .history[-1] view of omega for a terminal observation
+    T om_obs[3] = {r[(RF_Y + 4) * n], r[(RF_Y + 5) * n], r[(RF_Y + 6) * n]};
     DynCtx<T> x;
     T tgt[3];
 #pragma unroll
@@ -441,33 +613,10 @@ __global__ void __launch_bounds__(128, 4) head_kernel(const __grid_constant__ DC
     }
     int steps = ii[IF_STEPS * n], steps_tgt = ii[IF_STEPS_TGT * n], sim_step = ii[IF_SIM_STEP * n];
     const unsigned long long episode = (unsigned long long)(uint32_t)ii[IF_EPISODE * n];
-    const int nfev = ii[IF_NFEV * n], natt = ii[IF_NATT * n];
     T a_raw[3], cmd_in[3];
     bool act_f32;
     prep_action(c, io, env, a_raw, act_f32, x.cmd, cmd_in);
-    T fx[12], fu[4];
-    if (TURB) {
-#pragma unroll
-        for (int i = 0; i < 12; ++i) fx[i] = r[(RF_FX + i) * n];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) fu[i] = r[(RF_FU + i) * n];
-    }
-
-    // ---------------- post-step commit (pyfly.py:1396-1406, 1852-1881) ----------------
-    T roll = roll_prev, pitch = pitch_prev, Va = Va_prev, alpha = alpha_prev, beta = beta_prev;
-    T om_obs[3] = {omega_prev[0], omega_prev[1], omega_prev[2]};   // .history[-1] view for a terminal observation
-    fail = post_step_commit<T>(c, x, y, fail, roll, pitch, Va, alpha, beta, om_obs);
-    sim_step += 1;
-
-    // ---------------- gym head (fixed_wing.py:512-628) ----------------
-    const int steps_before = steps;
-    steps += 1;
-    steps_tgt += 1;
-    bool done = false;
-    int term = FW_TERM_NONE;
-    if (c.steps_max > 0 && steps >= c.steps_max) { done = true; term = FW_TERM_STEPS; }
-
-    // action / command rings: previous entries (age 1 = most recent)
+    // loads: action / command rings (age 1 = most recent), goal counters and the two ring words each goal needs
     T aring[12], cring[12];
 #pragma unroll
     for (int i = 0; i < 12; ++i) aring[i] = r[(RF_ACT_RING + i) * n];
@@ -475,48 +624,97 @@ __global__ void __launch_bounds__(128, 4) head_kernel(const __grid_constant__ DC
 #pragma unroll
     for (int i = 0; i < 12; ++i) cring[i] = (need_cring || i < 3) ? r[(RF_CMD_RING + i) * n] : (T)0;
     T cv_sum = r[RF_CV_SUM * n];
-    if (steps_before >= 1) {
-#pragma unroll
-        for (int j = 0; j < 3; ++j) cv_sum += M<T>::fabs(cmd_in[j] - cring[j]);
-    }
-    const int n_prev = steps_before < 4 ? steps_before : 4;   // valid previous ring entries
-
-    T e_new[3] = {0, 0, 0};
-    T reward;
-    T obs_v[FW_NOBS];
     int gbits[4] = {0, 0, 0, 0};
     int gcnt[4], gtot[4], settle[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         gcnt[k] = ii[(IF_GOAL_CNT + k) * n]; gtot[k] = ii[(IF_GOAL_TOTAL + k) * n]; settle[k] = ii[(IF_SETTLE + k) * n];
     }
+    const int gidx = steps + 1;                // index of this entry in history["goal"] (entry 0 = reset)
+    const int gw = (gidx & 127) >> 5, gb = gidx & 31;
+    const int gidx_old = gidx - c.streak_req;
+    uint32_t gword[4] = {0, 0, 0, 0}, gold[4] = {0, 0, 0, 0};
+    if (c.streak_req > 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int32_t* ring = ii + (IF_GOAL_RING + 4 * k) * n;
+            gword[k] = (uint32_t)ring[gw * n];
+            if (gidx_old >= 0) gold[k] = (uint32_t)ring[((gidx_old & 127) >> 5) * n];
+        }
+    }
+    int goal_achieved = 0;
+    if (c.rew_generic) goal_achieved = ii[IF_GOAL_ACHIEVED * n];
+    int tcls[3] = {c.tgt_class[0], c.tgt_class[1], c.tgt_class[2]};
+    T tp[15];
+    if (c.tgt_moving) {
+#pragma unroll
+        for (int k = 0; k < 15; ++k) tp[k] = r[(RF_TPROP + k) * n];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) tcls[k] = ii[(IF_TCLS + k) * n];
+    }
+
+    T esum[3], eabs[3], emin[3], emax[3], e0v[3], eprev[3];
+    int rise_lo[3], rise_hi[3];
+    T ep_ret = r[RF_EP_RET * n];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        e0v[k] = r[(RF_E0 + k) * n]; esum[k] = r[(RF_ESUM + k) * n]; eabs[k] = r[(RF_EABS + k) * n];
+        emin[k] = r[(RF_EMIN + k) * n]; emax[k] = r[(RF_EMAX + k) * n]; eprev[k] = r[(RF_EPREV + k) * n];
+        rise_lo[k] = ii[(IF_RISE_LO + k) * n]; rise_hi[k] = ii[(IF_RISE_HI + k) * n];
+    }
+    T fx[12], fu[4];
+    if (TURB) {
+#pragma unroll
+        for (int i = 0; i < 12; ++i) fx[i] = r[(RF_FX + i) * n];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) fu[i] = r[(RF_FU + i) * n];
+    }
+    if (fail) {
+#pragma unroll
+        for (int i = 0; i < FW_NY; ++i) y[i] = r[(RF_Y + i) * n];
+    }
+    // ======================= post-step commit (pyfly.py:1396-1406, 1852-1881) =======================
+    fail = post_step_commit<T>(c, x, y, fail, roll, pitch, Va, alpha, beta, om_obs);
+    sim_step += 1;
+
+    // ======================= gym head (fixed_wing.py:512-628) =======================
+    const int steps_before = steps;
+    steps += 1;
+    steps_tgt += 1;
+    bool done = false;
+    int term = FW_TERM_NONE;
+    if (c.steps_max > 0 && steps >= c.steps_max) { done = true; term = FW_TERM_STEPS; }
+    const int n_prev = steps_before < 4 ? steps_before : 4;   // valid previous ring entries
+    const bool streak = c.streak_req > 0 && !fail;
+
+    if (steps_before >= 1) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) cv_sum += M<T>::fabs(cmd_in[j] - cring[j]);
+    }
+    T e_new[3] = {0, 0, 0};
+    T reward;
+    bool tprop_dirty = false;
     if (!fail) {
         // goal status with the CURRENT target (fixed_wing.py:536-560)
         const T eg[3] = {err_roll(tgt[0], roll), tgt[1] - pitch, tgt[2] - Va};
         bool resample = false, success_on_step = false;
-        if (c.streak_req > 0) {
+        if (streak) {
             gbits[3] = 1;
 #pragma unroll
             for (int k = 0; k < 3; ++k) { gbits[k] = M<T>::fabs(eg[k]) <= c.tgt_bound[k]; gbits[3] &= gbits[k]; }
-            const int idx = steps;                 // index of this entry in history["goal"] (entry 0 = reset)
-            const int w = (idx & 127) >> 5, b = idx & 31;
-            const int idx_old = idx - c.streak_req;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                int32_t* ring = ii + (IF_GOAL_RING + 4 * k) * n;
-                if (idx_old >= 0) gcnt[k] -= (ring[((idx_old & 127) >> 5) * n] >> (idx_old & 31)) & 1;
-                uint32_t word = (uint32_t)ring[w * n];
-                word = (word & ~(1u << b)) | ((uint32_t)gbits[k] << b);
-                ring[w * n] = (int32_t)word;
+                if (gidx_old >= 0) gcnt[k] -= (gold[k] >> (gidx_old & 31)) & 1;
+                gword[k] = (gword[k] & ~(1u << gb)) | ((uint32_t)gbits[k] << gb);
                 gcnt[k] += gbits[k];
                 gtot[k] += gbits[k];
-                if (settle[k] < 0 && idx + 1 >= c.streak_req &&
-                    (double)gcnt[k] / (double)c.streak_req >= (double)c.streak_fraction) settle[k] = idx;
+                if (settle[k] < 0 && gidx + 1 >= c.streak_req &&
+                    (double)gcnt[k] / (double)c.streak_req >= (double)c.streak_fraction) settle[k] = gidx;
             }
             if (steps_tgt >= c.streak_req && (double)gcnt[3] / (double)c.streak_req >= (double)c.streak_fraction) {
                 if (c.rew_generic) {                       // goal_achieved_on_step (fixed_wing.py:546-547)
-                    success_on_step = ii[IF_GOAL_ACHIEVED * n] == 0;
-                    ii[IF_GOAL_ACHIEVED * n] = 1;
+                    success_on_step = goal_achieved == 0;
+                    goal_achieved = 1;
                 }
                 if (c.on_success == FW_SUCCESS_DONE) { done = true; term = FW_TERM_SUCCESS; }
                 else if (c.on_success == FW_SUCCESS_NEW) resample = true;
@@ -529,64 +727,37 @@ __global__ void __launch_bounds__(128, 4) head_kernel(const __grid_constant__ DC
             val = generic_reward<T>(c, S, env, eg, st8, a_raw, act_f32, aring, n_prev, steps, gbits, success_on_step);
         } else {
 #pragma unroll
-        for (int k = 0; k < 3; ++k)
-            if (c.rew_err_scaling[k] > (T)0) val -= clip(M<T>::fabs(eg[k]) / c.rew_err_scaling[k], (T)0, c.rew_err_max[k]);
-        if (c.rew_delta_scaling > (T)0 && steps > 1) {
-            const int np_ = (c.rew_delta_window - 1) < n_prev ? (c.rew_delta_window - 1) : n_prev;
-            T dv;
-            if (act_f32) {
-                float d[12];
-                int m = 0;
-                for (int age = np_; age >= 1; --age)
-                    for (int j = 0; j < 3; ++j) {
-                        const T newer = (age == 1) ? a_raw[j] : aring[(age - 2) * 3 + j];
-                        d[m++] = fabsf((float)newer - (float)aring[(age - 1) * 3 + j]);
-                    }
-                const float s = np_sum<float>(d, m);
-                dv = (T)fminf(fmaxf(s / (float)c.rew_delta_scaling, 0.f), (float)c.rew_delta_max);
-            } else {
-                T d[12];
-                int m = 0;
-                for (int age = np_; age >= 1; --age)
-                    for (int j = 0; j < 3; ++j) {
-                        const T newer = (age == 1) ? a_raw[j] : aring[(age - 2) * 3 + j];
-                        d[m++] = M<T>::fabs(newer - aring[(age - 1) * 3 + j]);
-                    }
-                dv = clip(np_sum<T>(d, m) / c.rew_delta_scaling, (T)0, c.rew_delta_max);
+            for (int k = 0; k < 3; ++k)
+                if (c.rew_err_scaling[k] > (T)0) val -= clip(M<T>::fabs(eg[k]) / c.rew_err_scaling[k], (T)0, c.rew_err_max[k]);
+            if (c.rew_delta_scaling > (T)0 && steps > 1) {
+                const int np_ = (c.rew_delta_window - 1) < n_prev ? (c.rew_delta_window - 1) : n_prev;
+                T dv;
+                if (act_f32) {
+                    const float s = ring_delta_sum_np<float, T>(np_, a_raw, aring);
+                    dv = (T)fminf(fmaxf(s / (float)c.rew_delta_scaling, 0.f), (float)c.rew_delta_max);
+                } else {
+                    dv = clip(ring_delta_sum_np<T, T>(np_, a_raw, aring) / c.rew_delta_scaling, (T)0, c.rew_delta_max);
+                }
+                val -= dv;
             }
-            val -= dv;
-        }
-        if (c.rew_bound_scaling > (T)0 && c.has_action_bounds) {
-            T hi = 0, lo = 0;
+            if (c.rew_bound_scaling > (T)0 && c.has_action_bounds) {
+                T hi = 0, lo = 0;
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                if (a_raw[j] > c.action_bounds_max[j]) hi += M<T>::fabs(a_raw[j] - c.action_bounds_max[j]);
-                if (a_raw[j] < c.action_bounds_min[j]) lo += M<T>::fabs(a_raw[j] - c.action_bounds_min[j]);
+                for (int j = 0; j < 3; ++j) {
+                    if (a_raw[j] > c.action_bounds_max[j]) hi += M<T>::fabs(a_raw[j] - c.action_bounds_max[j]);
+                    if (a_raw[j] < c.action_bounds_min[j]) lo += M<T>::fabs(a_raw[j] - c.action_bounds_min[j]);
+                }
+                val -= clip(M<T>::fabs(hi + lo) / c.rew_bound_scaling, (T)0, c.rew_bound_max);
             }
-            val -= clip(M<T>::fabs(hi + lo) / c.rew_bound_scaling, (T)0, c.rew_bound_max);
-        }
         }
         reward = val;
         // target resample / advance (fixed_wing.py:569-580, 1363-1471)
-        int tcls[3] = {c.tgt_class[0], c.tgt_class[1], c.tgt_class[2]};
-        T tp[15];
-        if (c.tgt_moving) {
-#pragma unroll
-            for (int k = 0; k < 15; ++k) tp[k] = r[(RF_TPROP + k) * n];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) tcls[k] = ii[(IF_TCLS + k) * n];
-        }
         if (resample || (c.resample_every > 0 && steps_tgt >= c.resample_every)) {
             T u12[12];
             target_draws<T>(c, c.env_id_offset + env, episode, RNG_RESAMPLE, (uint32_t)(steps * 8), u12);
             sample_target<T>(c, roll, pitch, Va, steps, u12, tgt, tcls, tp);
             steps_tgt = 0;
-            if (c.tgt_moving) {
-#pragma unroll
-                for (int k = 0; k < 15; ++k) r[(RF_TPROP + k) * n] = tp[k];
-#pragma unroll
-                for (int k = 0; k < 3; ++k) ii[(IF_TCLS + k) * n] = tcls[k];
-            }
+            tprop_dirty = c.tgt_moving;
         }
         const T tgt_pitch_cur = tgt[1];
         if (c.tgt_moving) {
@@ -630,7 +801,8 @@ __global__ void __launch_bounds__(128, 4) head_kernel(const __grid_constant__ DC
         reward = c.step_fail_timesteps ? (T)(steps - c.steps_max) : c.step_fail_value;
     }
 
-    // ---------------- observation (fixed_wing.py:1113-1262) ----------------
+    // observation (fixed_wing.py:1113-1262)
+    T obs_v[FW_NOBS];
     obs_v[0] = roll; obs_v[1] = pitch; obs_v[2] = Va;
     obs_v[3] = om_obs[0]; obs_v[4] = om_obs[1]; obs_v[5] = om_obs[2];
     obs_v[6] = tgt[0]; obs_v[7] = tgt[1]; obs_v[8] = tgt[2];
@@ -642,9 +814,9 @@ __global__ void __launch_bounds__(128, 4) head_kernel(const __grid_constant__ DC
             obs_v[11 + j] = c.scale_actions ? delta_feature<T>(a_raw[j], aring, j, np_, act_f32)
                                             : delta_feature<T>(cmd_in[j], cring, j, np_, false);
     }
-
     if (!GENERIC && (c.obs_noise_std > (T)0 || c.obs_noise_mean != (T)0))
         add_obs_noise<T>(c, c.env_id_offset + env, episode, steps, obs_v, FW_NOBS);
+
     T og[GENERIC ? FW_NOBS_MAX : 1];
     const T* obs_out = obs_v;
     int odim = FW_NOBS;
@@ -658,48 +830,40 @@ __global__ void __launch_bounds__(128, 4) head_kernel(const __grid_constant__ DC
         odim = c.obs_len * c.obs_n;
     }
 
-    // ---------------- streamed episode statistics (fixed_wing.py:1644-1736) ----------------
-    T esum[3], eabs[3], emin[3], emax[3], e0v[3];
-    int rise_lo[3], rise_hi[3];
-    const T ep_ret = r[RF_EP_RET * n] + reward;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        e0v[k] = r[(RF_E0 + k) * n]; esum[k] = r[(RF_ESUM + k) * n]; eabs[k] = r[(RF_EABS + k) * n];
-        emin[k] = r[(RF_EMIN + k) * n]; emax[k] = r[(RF_EMAX + k) * n];
-        rise_lo[k] = ii[(IF_RISE_LO + k) * n]; rise_hi[k] = ii[(IF_RISE_HI + k) * n];
-    }
+    // ======================= streamed episode statistics (fixed_wing.py:1644-1736) =======================
+    ep_ret += reward;
     int n_err = steps_before + 1;           // entries in history["error"] before this step
     if (!fail) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            const T ea = M<T>::fabs(e_new[k]), prev = r[(RF_EPREV + k) * n];
+            const T ea = M<T>::fabs(e_new[k]);
             const T low_lim = M<T>::fabs(c.rise_low * e0v[k]), high_lim = M<T>::fabs(c.rise_high * e0v[k]);
-            if (rise_lo[k] < 0 && prev >= low_lim && ea < low_lim) rise_lo[k] = n_err - 1;
-            if (rise_hi[k] < 0 && prev >= high_lim && ea < high_lim) rise_hi[k] = n_err - 1;
+            if (rise_lo[k] < 0 && eprev[k] >= low_lim && ea < low_lim) rise_lo[k] = n_err - 1;
+            if (rise_hi[k] < 0 && eprev[k] >= high_lim && ea < high_lim) rise_hi[k] = n_err - 1;
             esum[k] += e_new[k]; eabs[k] += ea;
             emin[k] = M<T>::fmin(emin[k], e_new[k]); emax[k] = M<T>::fmax(emax[k], e_new[k]);
-            r[(RF_EPREV + k) * n] = ea;
+            eprev[k] = ea;
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            r[(RF_EPREV + k) * n] = eprev[k];
             S.err_ring[(size_t)((n_err % FW_END_ERR_WINDOW) * 3 + k) * n + env] = e_new[k];
         }
         n_err += 1;
     }
 
+    T s50[3];
+    end_error_sums_warp<T>(S, done, env, n_err, s50);
     if (done) {
         double* m = S.metrics + (size_t)env * FW_NMETRIC;
         const int off = steps - (n_err - 1);     // rise index offset: 0 normally, 1 after a failed step
+        const int end_cnt = n_err < FW_END_ERR_WINDOW ? n_err : FW_END_ERR_WINDOW;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             const T e0 = e0v[k];
             m[FW_M_AVG_ERROR + k] = (M<T>::fabs(e0) >= (T)0.01) ? (double)M<T>::fabs((esum[k] / (T)n_err) / e0) : CUDART_NAN;
             m[FW_M_TOTAL_ERROR + k] = (double)eabs[k];
-            const int cnt = n_err < FW_END_ERR_WINDOW ? n_err : FW_END_ERR_WINDOW;
-            T s50 = 0;
-            for (int q = 0; q < cnt; ++q) {
-                const int slot = (n_err - cnt + q) % FW_END_ERR_WINDOW;
-                s50 += (slot == ((n_err - 1) % FW_END_ERR_WINDOW) && !fail) ? e_new[k]
-                                                                             : S.err_ring[(size_t)(slot * 3 + k) * n + env];
-            }
-            m[FW_M_END_ERROR + k] = (double)M<T>::fabs(s50 / (T)cnt);
+            m[FW_M_END_ERROR + k] = (double)M<T>::fabs(s50[k] / (T)end_cnt);
             const double re = rise_lo[k] >= 0 ? (double)(rise_lo[k] + off) : CUDART_NAN;
             const double rs = rise_hi[k] >= 0 ? (double)(rise_hi[k] + off) : CUDART_NAN;
             m[FW_M_RISE_TIME + k] = re - rs;
@@ -718,47 +882,48 @@ __global__ void __launch_bounds__(128, 4) head_kernel(const __grid_constant__ DC
         S.ep_len[env] = steps;
     }
     S.ep_term[env] = term;
-
-    // ---------------- outputs ----------------
     if (io.rew) io.rew[env] = (float)reward;
     if (io.rew64) io.rew64[env] = (double)reward;
     if (io.done) io.done[env] = done ? 1 : 0;
-    ii[IF_NFEV * n] = nfev;
-    ii[IF_NATT * n] = natt;
 
-    if (done && io.auto_reset) {
-        if (io.term_obs) write_obs(obs_out, odim, env, io.term_obs, (double*)nullptr);
-        reset_env_noinline<T>(c, S, env, io.obs, io.obs64);
-        // keep the diagnostics of the step that ended the episode
-        ii[IF_NFEV * n] = nfev;
-        ii[IF_NATT * n] = natt;
+    // the goal flag survives a reset (fixed_wing.py keeps goal_achieved across episodes)
+    if (streak && c.rew_generic) ii[IF_GOAL_ACHIEVED * n] = goal_achieved;
+    // an episode that ended takes the next episode's row, computed ahead of time (refill_kernel recomputes it on the
+    // side stream while the next step integrates)
+    const bool take = done && io.auto_reset;
+    if (take && io.term_obs) write_obs(obs_out, odim, env, io.term_obs, (double*)nullptr);
+    take_spare_warp<T>(S, P, take, env, odim, io.obs, io.obs64);
+    if (take) {
+        P.list[(size_t)parity * n + atomicAdd(P.count + parity, 1)] = env;
         return;
     }
     write_obs(obs_out, odim, env, io.obs, io.obs64);
-
-    // ---------------- store ----------------
-    if (TURB && !fail) {
-        T un[4];
-        noise_sample(c, S, env, episode, sim_step, un);
-        turb_step(c, fx, fu, un, sim_step);
 #pragma unroll
-        for (int i = 0; i < 12; ++i) r[(RF_FX + i) * n] = fx[i];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) r[(RF_FU + i) * n] = fu[i];
+    for (int k = 0; k < 3; ++k) {
+        r[(RF_ESUM + k) * n] = esum[k]; r[(RF_EABS + k) * n] = eabs[k];
+        r[(RF_EMIN + k) * n] = emin[k]; r[(RF_EMAX + k) * n] = emax[k];
+        ii[(IF_RISE_LO + k) * n] = rise_lo[k]; ii[(IF_RISE_HI + k) * n] = rise_hi[k];
     }
+    r[RF_EP_RET * n] = ep_ret;
+
     if (!fail) {
 #pragma unroll
         for (int i = 0; i < FW_NY; ++i) r[(RF_Y + i) * n] = y[i];
         r[RF_ROLL * n] = roll; r[RF_PITCH * n] = pitch; r[RF_VA * n] = Va; r[RF_ALPHA * n] = alpha; r[RF_BETA * n] = beta;
     }
+    // stores of phase 1: goal ring and counters, target, rings (age k -> age k+1, current -> age 1), step counters
+    if (streak) {
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        r[(RF_TGT + k) * n] = tgt[k];
-        r[(RF_ESUM + k) * n] = esum[k]; r[(RF_EABS + k) * n] = eabs[k];
-        r[(RF_EMIN + k) * n] = emin[k]; r[(RF_EMAX + k) * n] = emax[k];
-        ii[(IF_RISE_LO + k) * n] = rise_lo[k]; ii[(IF_RISE_HI + k) * n] = rise_hi[k];
+        for (int k = 0; k < 4; ++k) ii[((IF_GOAL_RING + 4 * k) + gw) * n] = (int32_t)gword[k];
     }
-    // rings shift: age k -> age k+1, current -> age 1
+    if (tprop_dirty) {
+#pragma unroll
+        for (int k = 0; k < 15; ++k) r[(RF_TPROP + k) * n] = tp[k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) ii[(IF_TCLS + k) * n] = tcls[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) r[(RF_TGT + k) * n] = tgt[k];
 #pragma unroll
     for (int i = 11; i >= 3; --i) r[(RF_ACT_RING + i) * n] = aring[i - 3];
 #pragma unroll
@@ -770,12 +935,22 @@ __global__ void __launch_bounds__(128, 4) head_kernel(const __grid_constant__ DC
 #pragma unroll
     for (int j = 0; j < 3; ++j) r[(RF_CMD_RING + j) * n] = cmd_in[j];
     r[RF_CV_SUM * n] = cv_sum;
-    r[RF_EP_RET * n] = ep_ret;
     ii[IF_STEPS * n] = steps; ii[IF_STEPS_TGT * n] = steps_tgt; ii[IF_SIM_STEP * n] = sim_step;
     ii[IF_ACT_F32 * n] = act_f32 ? 1 : 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         ii[(IF_GOAL_CNT + k) * n] = gcnt[k]; ii[(IF_GOAL_TOTAL + k) * n] = gtot[k]; ii[(IF_SETTLE + k) * n] = settle[k];
+    }
+
+    // ======================= Dryden filter advance =======================
+    if (TURB && !fail) {
+        T un[4];
+        noise_sample(c, S, env, episode, sim_step, un);
+        turb_step(c, fx, fu, un, sim_step);
+#pragma unroll
+        for (int i = 0; i < 12; ++i) r[(RF_FX + i) * n] = fx[i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) r[(RF_FU + i) * n] = fu[i];
     }
 }
 
@@ -1049,7 +1224,34 @@ struct FwHandle {
     Scratch<float> w32;
     int sm_count;
     unsigned long long random_step;
+    // precomputed next-episode rows (Spare) and the side stream that refills them
+    void* r2_buf; int32_t* i2_buf; void* err2; float* spare_obs; double* spare_obs64; int32_t* done_list;
+    Spare<double> p64;
+    Spare<float> p32;
+    cudaStream_t side;
+    cudaEvent_t ev_head, ev_refill;
+    int refill_pending, step_parity;
+    // fw_set_profiling: CUDA events around each kernel of a step (the step then ends with an event synchronise)
+    int prof_on;
+    cudaEvent_t prof_ev[4];
+    double prof_ms[3];
+    long long prof_steps;
 };
+
+// event i is recorded BEFORE kernel i of the step (and event 3 after the last one)
+static inline void prof_mark(FwHandle* h, int i, cudaStream_t st) {
+    if (h->prof_on) cudaEventRecord(h->prof_ev[i], st);
+}
+static void prof_collect(FwHandle* h, bool has_init) {
+    if (!h->prof_on) return;
+    cudaEventSynchronize(h->prof_ev[3]);
+    float ms = 0;
+    for (int i = has_init ? 0 : 1; i < 3; ++i) {
+        cudaEventElapsedTime(&ms, h->prof_ev[i], h->prof_ev[i + 1]);
+        h->prof_ms[i] += ms;
+    }
+    h->prof_steps += 1;
+}
 
 static const int NT_RK45_F64 = 32;     // 6*15*32*8 = 23040 B of stage storage per one-warp block: 9 blocks / SM
 static const int NT_RK45_F32 = 64;     // 6*15*64*4 = 23040 B
@@ -1068,9 +1270,27 @@ template <typename T> static Scratch<T> make_scratch(void* real, int32_t* ints, 
     return w;
 }
 
+// head_kernel of this step reads the spare rows: the refill of the previous step's consumers must have finished
+static inline void spare_join(FwHandle* h, cudaStream_t st) {
+    if (h->refill_pending) { cudaStreamWaitEvent(st, h->ev_refill, 0); h->refill_pending = 0; }
+}
+// after head_kernel: recompute, on the side stream, the rows this step consumed (it overlaps the next step)
+template <typename T>
+static void spare_refill(FwHandle* h, const DCfg<T>& c, const Spare<T>& P, cudaStream_t st) {
+    if (!P.on) return;
+    cudaEventRecord(h->ev_head, st);
+    cudaStreamWaitEvent(h->side, h->ev_head, 0);
+    int grid = (h->n + 31) / 32;
+    if (grid > 4 * h->sm_count) grid = 4 * h->sm_count;
+    refill_kernel<T><<<grid, 32, 0, h->side>>>(c, P, h->step_parity);
+    cudaEventRecord(h->ev_refill, h->side);
+    h->refill_pending = 1;
+    h->step_parity ^= 1;
+}
+
 // One env step = init kernel -> persistent attempt kernel -> head kernel (RK45), or rk4 kernel -> head kernel.
 template <typename T, bool TURB, int NT>
-static int launch_rk45(FwHandle* h, const DCfg<T>& c, const Soa<T>& S, const Scratch<T>& W, const StepIO& io, cudaStream_t st) {
+static int launch_rk45(FwHandle* h, const DCfg<T>& c, const Soa<T>& S, const Scratch<T>& W, const Spare<T>& P, const StepIO& io, cudaStream_t st) {
     const size_t smem = (size_t)6 * FW_NS * NT * sizeof(T);
     auto k = rk45_attempt_kernel<T, TURB, NT>;
     static int blocks_per_sm = 0;
@@ -1082,38 +1302,55 @@ static int launch_rk45(FwHandle* h, const DCfg<T>& c, const Soa<T>& S, const Scr
     int grid = h->sm_count * blocks_per_sm;
     const int need = (h->n + NT - 1) / NT;
     if (grid > need) grid = need;
-    const int g0 = (h->n + 127) / 128;
-    rk45_init_kernel<T, TURB><<<g0, 128, 0, st>>>(c, S, io, W, grid * NT);
+    const int g0 = (h->n + 127) / 128, g0h = (h->n + 63) / 64;
+    prof_mark(h, 0, st);
+    const int par = h->step_parity;
+    rk45_init_kernel<T, TURB><<<g0, 128, 0, st>>>(c, S, io, W, grid * NT, P.count + par);
+    prof_mark(h, 1, st);
     k<<<grid, NT, smem, st>>>(c, S, W);
+    prof_mark(h, 2, st);
+    spare_join(h, st);
     if (h->cfg.env_kind == FW_ENV_WAYPOINT) waypoint_head_kernel<T, TURB><<<g0, 128, 0, st>>>(c, S, io, W);
-    else if (h->cfg.obs_generic) head_kernel<T, TURB, true><<<g0, 128, 0, st>>>(c, S, io, W);
-    else head_kernel<T, TURB, false><<<g0, 128, 0, st>>>(c, S, io, W);
+    else if (h->cfg.obs_generic) head_kernel<T, TURB, true><<<g0h, 64, 0, st>>>(c, S, io, W, P, par);
+    else head_kernel<T, TURB, false><<<g0h, 64, 0, st>>>(c, S, io, W, P, par);
     CK(cudaGetLastError());
+    prof_mark(h, 3, st);
+    if (io.auto_reset) spare_refill<T>(h, c, P, st);
+    CK(cudaGetLastError());
+    prof_collect(h, true);
     return FW_OK;
 }
 template <typename T, bool TURB>
-static int launch_rk4(FwHandle* h, const DCfg<T>& c, const Soa<T>& S, const Scratch<T>& W, const StepIO& io, cudaStream_t st) {
-    const int g0 = (h->n + 127) / 128;
-    rk4_kernel<T, TURB><<<g0, 128, 0, st>>>(c, S, io, W);
+static int launch_rk4(FwHandle* h, const DCfg<T>& c, const Soa<T>& S, const Scratch<T>& W, const Spare<T>& P, const StepIO& io, cudaStream_t st) {
+    const int g0 = (h->n + 127) / 128, g0h = (h->n + 63) / 64;
+    prof_mark(h, 1, st);
+    const int par = h->step_parity;
+    rk4_kernel<T, TURB><<<g0, 128, 0, st>>>(c, S, io, W, P.count + par);
+    prof_mark(h, 2, st);
+    spare_join(h, st);
     if (h->cfg.env_kind == FW_ENV_WAYPOINT) waypoint_head_kernel<T, TURB><<<g0, 128, 0, st>>>(c, S, io, W);
-    else if (h->cfg.obs_generic) head_kernel<T, TURB, true><<<g0, 128, 0, st>>>(c, S, io, W);
-    else head_kernel<T, TURB, false><<<g0, 128, 0, st>>>(c, S, io, W);
+    else if (h->cfg.obs_generic) head_kernel<T, TURB, true><<<g0h, 64, 0, st>>>(c, S, io, W, P, par);
+    else head_kernel<T, TURB, false><<<g0h, 64, 0, st>>>(c, S, io, W, P, par);
     CK(cudaGetLastError());
+    prof_mark(h, 3, st);
+    if (io.auto_reset) spare_refill<T>(h, c, P, st);
+    CK(cudaGetLastError());
+    prof_collect(h, false);
     return FW_OK;
 }
 
 static int launch_step(FwHandle* h, const StepIO& io, cudaStream_t st) {
     const bool turb = h->cfg.turbulence != 0, rk45 = h->cfg.integrator == FW_INT_RK45_SCIPY;
     if (h->cfg.precision == FW_F64) {
-        if (rk45) return turb ? launch_rk45<double, true, NT_RK45_F64>(h, h->c64, h->s64, h->w64, io, st)
-                              : launch_rk45<double, false, NT_RK45_F64>(h, h->c64, h->s64, h->w64, io, st);
-        return turb ? launch_rk4<double, true>(h, h->c64, h->s64, h->w64, io, st)
-                    : launch_rk4<double, false>(h, h->c64, h->s64, h->w64, io, st);
+        if (rk45) return turb ? launch_rk45<double, true, NT_RK45_F64>(h, h->c64, h->s64, h->w64, h->p64, io, st)
+                              : launch_rk45<double, false, NT_RK45_F64>(h, h->c64, h->s64, h->w64, h->p64, io, st);
+        return turb ? launch_rk4<double, true>(h, h->c64, h->s64, h->w64, h->p64, io, st)
+                    : launch_rk4<double, false>(h, h->c64, h->s64, h->w64, h->p64, io, st);
     }
-    if (rk45) return turb ? launch_rk45<float, true, NT_RK45_F32>(h, h->c32, h->s32, h->w32, io, st)
-                          : launch_rk45<float, false, NT_RK45_F32>(h, h->c32, h->s32, h->w32, io, st);
-    return turb ? launch_rk4<float, true>(h, h->c32, h->s32, h->w32, io, st)
-                : launch_rk4<float, false>(h, h->c32, h->s32, h->w32, io, st);
+    if (rk45) return turb ? launch_rk45<float, true, NT_RK45_F32>(h, h->c32, h->s32, h->w32, h->p32, io, st)
+                          : launch_rk45<float, false, NT_RK45_F32>(h, h->c32, h->s32, h->w32, h->p32, io, st);
+    return turb ? launch_rk4<float, true>(h, h->c32, h->s32, h->w32, h->p32, io, st)
+                : launch_rk4<float, false>(h, h->c32, h->s32, h->w32, h->p32, io, st);
 }
 
 extern "C" {
@@ -1125,6 +1362,29 @@ int fw_obs_dim(const FwHandle* h) {
     if (!h) return FW_EINVAL;
     if (h->cfg.env_kind == FW_ENV_WAYPOINT) return FW_NOBS_WAYPOINT;
     return h->cfg.obs_generic ? h->cfg.obs_len * h->cfg.obs_n : FW_NOBS;
+}
+
+int fw_join(FwHandle* h, void* stream) {
+    if (!h) return FW_EINVAL;
+    spare_join(h, (cudaStream_t)stream);
+    return FW_OK;
+}
+
+int fw_set_profiling(FwHandle* h, int32_t on) {
+    if (!h) return FW_EINVAL;
+    if (on && !h->prof_ev[0])
+        for (int i = 0; i < 4; ++i) CK(cudaEventCreate(&h->prof_ev[i]));
+    h->prof_on = on ? 1 : 0;
+    h->prof_steps = 0;
+    h->prof_ms[0] = h->prof_ms[1] = h->prof_ms[2] = 0;
+    return FW_OK;
+}
+
+int fw_get_profile(const FwHandle* h, double* ms_sum3, int64_t* steps) {
+    if (!h || !ms_sum3 || !steps) return FW_EINVAL;
+    for (int i = 0; i < 3; ++i) ms_sum3[i] = h->prof_ms[i];
+    *steps = h->prof_steps;
+    return FW_OK;
 }
 
 int fw_set_waypoint_tasks(FwHandle* h, const double* tasks_dev, int32_t n_tasks, int32_t wp_len,
@@ -1201,6 +1461,35 @@ int fw_create(const FwConfig* cfg, int32_t n_envs, int32_t device, FwHandle** ou
     CK(cudaMemset(h->ep_term, 0, sizeof(int32_t) * n));
     h->s64 = Soa<double>{(double*)h->r_buf, h->i_buf, (double*)h->err_ring, h->metrics, h->ep_ret, h->ep_len, h->ep_term, nullptr, 0, n_envs, nullptr, nullptr, 0, 0};
     h->s32 = Soa<float>{(float*)h->r_buf, h->i_buf, (float*)h->err_ring, h->metrics, h->ep_ret, h->ep_len, h->ep_term, nullptr, 0, n_envs, nullptr, nullptr, 0, 0};
+    {
+        const int odim = fw_obs_dim(h);
+        CK(cudaMalloc(&h->r2_buf, esz * RF_COUNT * n));
+        CK(cudaMalloc((void**)&h->i2_buf, sizeof(int32_t) * IF_COUNT * n));
+        CK(cudaMalloc(&h->err2, esz * 3 * n));
+        CK(cudaMalloc((void**)&h->spare_obs, sizeof(float) * odim * n));
+        CK(cudaMalloc((void**)&h->spare_obs64, sizeof(double) * odim * n));
+        CK(cudaMalloc((void**)&h->done_list, sizeof(int32_t) * (2 * n + 2)));
+        CK(cudaMemset(h->r2_buf, 0, esz * RF_COUNT * n));
+        CK(cudaMemset(h->i2_buf, 0, sizeof(int32_t) * IF_COUNT * n));
+        CK(cudaMemset(h->err2, 0, esz * 3 * n));
+        CK(cudaMemset(h->spare_obs, 0, sizeof(float) * odim * n));
+        CK(cudaMemset(h->spare_obs64, 0, sizeof(double) * odim * n));
+        CK(cudaMemset(h->done_list, 0, sizeof(int32_t) * (2 * n + 2)));
+        h->p64.S2 = h->s64; h->p64.S2.r = (double*)h->r2_buf; h->p64.S2.i = h->i2_buf; h->p64.S2.err_ring = (double*)h->err2;
+        h->p32.S2 = h->s32; h->p32.S2.r = (float*)h->r2_buf; h->p32.S2.i = h->i2_buf; h->p32.S2.err_ring = (float*)h->err2;
+        h->p64.obs = h->p32.obs = h->spare_obs;
+        h->p64.obs64 = h->p32.obs64 = h->spare_obs64;
+        h->p64.list = h->p32.list = h->done_list;
+        h->p64.count = h->p32.count = h->done_list + 2 * n;
+        h->p64.on = h->p32.on = cfg->env_kind == FW_ENV_WAYPOINT ? 0 : 1;
+        // highest priority: the few refill blocks must get an SM slot BEFORE the persistent integrator blocks of the
+        // next step fill every register file, or they would only run in that kernel's tail and delay its head kernel
+        int prio_least = 0, prio_greatest = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+        CK(cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, prio_greatest));
+        CK(cudaEventCreateWithFlags(&h->ev_head, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_refill, cudaEventDisableTiming));
+    }
     CK(cudaDeviceSynchronize());
     *out = h;
     return FW_OK;
@@ -1213,6 +1502,12 @@ int fw_destroy(FwHandle* h) {
     cudaFree(h->r_buf); cudaFree(h->i_buf); cudaFree(h->err_ring); cudaFree(h->metrics);
     cudaFree(h->ep_ret); cudaFree(h->ep_len); cudaFree(h->ep_term); cudaFree(h->w_real); cudaFree(h->w_int);
     cudaFree(h->wp_tasks); cudaFree(h->wp_task_of_env);
+    cudaFree(h->r2_buf); cudaFree(h->i2_buf); cudaFree(h->err2); cudaFree(h->spare_obs); cudaFree(h->spare_obs64);
+    cudaFree(h->done_list);
+    if (h->side) cudaStreamDestroy(h->side);
+    if (h->ev_head) cudaEventDestroy(h->ev_head);
+    if (h->ev_refill) cudaEventDestroy(h->ev_refill);
+    for (int i = 0; i < 4; ++i) if (h->prof_ev[i]) cudaEventDestroy(h->prof_ev[i]);
     delete h;
     return FW_OK;
 }
@@ -1225,9 +1520,12 @@ int fw_reset(FwHandle* h, const uint8_t* mask_dev, const double* state_dev, cons
     cudaStream_t st = (cudaStream_t)stream;
     h->s64.noise = noise_dev; h->s64.noise_len = noise_len;
     h->s32.noise = noise_dev; h->s32.noise_len = noise_len;
+    h->p64.S2.noise = noise_dev; h->p64.S2.noise_len = noise_len;
+    h->p32.S2.noise = noise_dev; h->p32.S2.noise_len = noise_len;
+    spare_join(h, st);        // the reset rewrites the precomputed rows of the envs it touches
     const int bs = 128, grid = (h->n + bs - 1) / bs;
-    if (h->cfg.precision == FW_F64) reset_kernel<double><<<grid, bs, 0, st>>>(h->c64, h->s64, mask_dev, state_dev, target_dev, obs_dev, obs64_dev);
-    else reset_kernel<float><<<grid, bs, 0, st>>>(h->c32, h->s32, mask_dev, state_dev, target_dev, obs_dev, obs64_dev);
+    if (h->cfg.precision == FW_F64) reset_kernel<double><<<grid, bs, 0, st>>>(h->c64, h->s64, h->p64, mask_dev, state_dev, target_dev, obs_dev, obs64_dev);
+    else reset_kernel<float><<<grid, bs, 0, st>>>(h->c32, h->s32, h->p32, mask_dev, state_dev, target_dev, obs_dev, obs64_dev);
     CK(cudaGetLastError());
     return FW_OK;
 }

@@ -155,6 +155,7 @@ class PPO:
         with torch.no_grad():
             last_values = self.policy.predict_values(self._last_obs)
         self.buffer.compute_returns_and_advantage(last_values, self._last_dones)
+        self.env.sim.join()       # the simulator's side-stream work joins this stream (a graph capture must end joined)
 
     def collect_rollouts(self):
         """One rollout of n_steps over all envs + GAE.  With use_cuda_graph the ~40 small launches per step (policy
@@ -162,6 +163,7 @@ class PPO:
         bound otherwise (0.9 ms/step eager vs 0.1 ms of simulator work at 8192 envs)."""
         if self.use_cuda_graph and self._rollout_graph is None and self._eager_rollouts >= 1:
             # the first rollout ran eagerly (lazy initialisation, allocator warm-up); capture the second one
+            self.env.sim.join()
             torch.cuda.synchronize(self.device)
             try:
                 g = torch.cuda.CUDAGraph()
