@@ -266,24 +266,48 @@ def main():
     ms_per_step = ms_total / K
     value = world * n * K / (ms_total * 1e-3)
 
-    # ---- roofline of the dominant kernel (step_kernel<double, RK45, turbulence>) ----
+    # ---- roofline of the dominant kernel: rk45_attempt_kernel, timed by itself ----
+    # fw_set_profiling records CUDA events on the launch stream around each kernel of a step; the pass below repeats
+    # the timed loop's conditions (fresh actions, L2 flush before every step) for up to 50 more steps.
+    env.set_profiling(True)
+    nf_prof = torch.zeros(2, dtype=torch.float64, device=dev)
+    KP = max(1, min(K, 50))
+    for k in range(KP):
+        flush.add_(1.0)
+        env.step(pool[k % len(pool)])
+        nf_prof += env.get_field(bt.FIELD_NFEV).to(torch.float64).sum(0)
+    prof = env.profile()
+    env.set_profiling(False)
+    nf_prof = (nf_prof / (n * KP)).cpu().numpy()
     peaks, peak_kind = measured_peaks()
     fp64_peak = bt.measure_fma_peak(local, "f64")
     fp32_peak = bt.measure_fma_peak(local, "f32")
+    # algorithmic flops of one attempt-kernel launch: every RHS evaluation after the two of the init kernel, plus the
+    # stage combinations / error norm of every attempt
+    flops_attempt_env = (nf_prof[0] - 2.0) * (W_RHS + T_RHS) + nf_prof[1] * (W_ATT + T_ATT)
+    achieved_tf = flops_attempt_env * n / (prof["integrate_ms"] * 1e-3) / 1e12
     flops_env_step = nf[0] * (W_RHS + T_RHS) + nf[1] * (W_ATT + T_ATT) + (W_ENV + T_ENV)
-    achieved_tf = flops_env_step * n / (ms_per_step * 1e-3) / 1e12
+    step_tf = flops_env_step * n / (ms_per_step * 1e-3) / 1e12
     hbm_gbs = BYTES_PER_ENV_STEP_F64 * n / (ms_per_step * 1e-3) / 1e9
-    roofline = {"bound": "fp64", "kernel": "rk45_attempt_kernel<double, turbulence, 64> (+ rk45_init_kernel, head_kernel: the whole step is timed)",
+    ksum = prof["init_ms"] + prof["integrate_ms"] + prof["head_ms"]
+    roofline = {"bound": "fp64", "kernel": "rk45_attempt_kernel<double, turbulence, 32>",
                 "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak,
+                "kernel_ms": prof["integrate_ms"], "kernel_timing": "CUDA events around the kernel on its launch "
+                "stream (fw_set_profiling), mean of %d launches, L2 flushed before each step" % KP,
                 "peak_source": "DFMA micro-benchmark fw_measure_fma_peak on this GPU, same process (MEASURED_PEAKS.json "
                                "has no vector-pipe figure)",
-                "flops_per_env_step": flops_env_step, "mean_rhs_evals": float(nf[0]), "mean_rk_attempts": float(nf[1]),
-                "traffic": 2.365e8,
-                "traffic_note": "dram__bytes_read+write per step summed over the three kernels, ncu --set full capture "
-                                "profiles/r01_v5_kernels_raw_summary.txt (attempt kernel alone: 26.5 MB)",
+                "flops_per_launch": flops_attempt_env * n, "flops_per_env_attempt_kernel": flops_attempt_env,
+                "mean_rhs_evals": float(nf_prof[0]), "mean_rk_attempts": float(nf_prof[1]),
+                "kernel_shares": {"rk45_init_kernel": prof["init_ms"] / ksum, "rk45_attempt_kernel": prof["integrate_ms"] / ksum,
+                                  "head_kernel": prof["head_ms"] / ksum,
+                                  "ms": [prof["init_ms"], prof["integrate_ms"], prof["head_ms"]]},
+                "traffic": 2.65e7,
+                "traffic_note": "dram__bytes_read+write of one rk45_attempt_kernel launch, ncu --set full capture "
+                                "(profiles/): the kernel is compute/latency bound, DRAM at ~2 % of peak",
                 "executed_fp64_flop_per_env_step_ncu": 24830,
-                "executed_note": "2*DFMA + DMUL + DADD thread instructions of the same capture / 65536 envs (n_rhs 24.05): "
-                                 "the instrumented count behind the hand-counted flops_per_env_step",
+                "executed_note": "2*DFMA + DMUL + DADD thread instructions of the three kernels / 65536 envs (n_rhs 24.05)",
+                "whole_step": {"achieved": step_tf, "frac": step_tf / fp64_peak, "flops_per_env_step": flops_env_step,
+                               "ms": ms_per_step},
                 "hbm": {"achieved": hbm_gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                         "frac": hbm_gbs / peaks.get("hbm_gbs"), "peak_source": peak_kind + " (MEASURED_PEAKS.json)",
                         "bytes_per_env_step": BYTES_PER_ENV_STEP_F64},
@@ -361,7 +385,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": workload_config(n), "roofline": roofline,
-                "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 3 * K, "gpu_launches_note": "rk45_init_kernel + rk45_attempt_kernel + head_kernel per step",
+                "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 4 * K, "gpu_launches_note": "rk45_init_kernel + rk45_attempt_kernel + head_kernel per step on the launch stream, refill_kernel on the side stream",
                 "clocks": clocks, "modes": extra, "ppo": ppo}
         print(json.dumps(line), flush=True)
     if world > 1:

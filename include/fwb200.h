@@ -232,6 +232,16 @@ int fw_set_profiling(FwHandle* h, int32_t on);
  * call it before ending a CUDA stream capture that contains fw_step calls (a capture must not end with unjoined work)
  * or before handing the handle to another thread.  No reference counterpart. */
 int fw_join(FwHandle* h, void* stream);
+
+/* Episode-end rows for a host-facing caller (VecEnv infos: Monitor's {"episode": {r, l}}, the gym env's metrics and
+ * terminal_observation, fixed_wing.py:589-628 / vec_env auto-reset).  After every auto-reset fw_step the buffer holds
+ *   int32 count at byte 0 (number of episodes that ended at the step; may exceed cap),
+ *   then, from byte 8, min(count, cap) rows of FW_INFO_HEAD + obs_dim doubles:
+ *   env index, FwTermCode, episode length, episode return, FW_NMETRIC metrics, terminal observation (float32 values)
+ * in no particular order.  Placed behind the step outputs in one allocation it reaches the host in the same copy.
+ * rows_dev = NULL switches it off.  The buffer must hold 8 + cap * (FW_INFO_HEAD + obs_dim) * 8 bytes. */
+#define FW_INFO_HEAD (4 + FW_NMETRIC)
+int fw_set_info_rows(FwHandle* h, double* rows_dev, int32_t cap);
 int fw_get_profile(const FwHandle* h, double* ms_sum3, int64_t* steps);
 
 /* Waypoint head only: the task table.  tasks_dev [n_tasks, wp_len, FW_WP_ROW] f64 (device, copied), task_of_env_dev [n]

@@ -6,7 +6,8 @@ v = FixedWingVecEnv(n, sim_config_kw={"turbulence": True}, seed=0)
 v.reset()
 a = np.random.uniform(-1, 1, (n, 3)).astype(np.float32)
 nd = []
-for _ in range(10): v.step(a)
+import sys
+for _ in range(int(sys.argv[1]) if len(sys.argv) > 1 else 10): v.step(a)
 pr = cProfile.Profile(); pr.enable()
 t0 = time.perf_counter()
 for _ in range(50):
@@ -14,4 +15,4 @@ for _ in range(50):
 dt = (time.perf_counter() - t0) / 50
 pr.disable()
 print("step %.0f us, dones per step: %s" % (dt * 1e6, nd[:20]))
-pstats.Stats(pr).sort_stats("cumulative").print_stats(14)
+pstats.Stats(pr).sort_stats("cumulative").print_stats(22)

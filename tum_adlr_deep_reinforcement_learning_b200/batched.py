@@ -20,6 +20,17 @@ def _ptr(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
+INFO_CAP = 64          # episode-end rows that travel with the step outputs; more than that in one step -> second fetch
+FW_INFO_HEAD = 4 + FW_NMETRIC
+
+
+def unpack_outputs(buf, n, obs_dim):
+    """Views (obs [n, obs_dim] f32, rew [n] f32, done [n] u8) of a packed output buffer (torch uint8 tensor)."""
+    o = n * obs_dim * 4
+    return (buf[:o].view(torch.float32).view(n, obs_dim), buf[o:o + n * 4].view(torch.float32),
+            buf[o + n * 4:o + n * 5])
+
+
 class BatchedFixedWing:
     def __init__(self, n_envs, cfg=None, device=0, **cfg_kw):
         if not torch.cuda.is_available():
@@ -32,9 +43,19 @@ class BatchedFixedWing:
             _lib.check(_lib.lib().fw_create(ctypes.byref(self.cfg), self.n, device, ctypes.byref(self._h)), "fw_create")
         n, dev = self.n, self.device
         self.obs_dim = _lib.lib().fw_obs_dim(self._h)
-        self.obs = torch.zeros(n, self.obs_dim, dtype=torch.float32, device=dev)
-        self.rew = torch.zeros(n, dtype=torch.float32, device=dev)
-        self.done = torch.zeros(n, dtype=torch.uint8, device=dev)
+        # obs | rew | done are views of ONE byte buffer, so that a host-facing caller fetches a step's outputs with a
+        # single device-to-host copy (vec_env.FixedWingVecEnv)
+        # ... followed (8-byte aligned) by the episode-end rows of fw_set_info_rows: count + INFO_CAP rows
+        self.info_width = FW_INFO_HEAD + self.obs_dim
+        self.info_offset = -(-(n * self.obs_dim * 4 + n * 4 + n) // 8) * 8
+        waypoint = self.cfg.env_kind != 0
+        self.info_cap = 0 if waypoint else INFO_CAP
+        self.out_nbytes = self.info_offset + (8 + self.info_cap * self.info_width * 8 if self.info_cap else 0)
+        self.out_packed = torch.zeros(self.out_nbytes, dtype=torch.uint8, device=dev)
+        self.obs, self.rew, self.done = unpack_outputs(self.out_packed, n, self.obs_dim)
+        if self.info_cap:
+            self.info_rows = self.out_packed[self.info_offset:].view(torch.float64)
+            _lib.check(_lib.lib().fw_set_info_rows(self._h, _ptr(self.info_rows), self.info_cap), "fw_set_info_rows")
         self.term_obs = torch.zeros(n, self.obs_dim, dtype=torch.float32, device=dev)
         self.obs64 = None
         self.rew64 = None

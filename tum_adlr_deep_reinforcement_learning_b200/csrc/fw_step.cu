@@ -33,6 +33,8 @@ struct StepIO {
     int random_actions;    // 1: draw U(-1,1)^3 from Philox (fw_step_random)
     unsigned long long action_seed;
     unsigned long long action_step;
+    double* info;          // fw_set_info_rows: [0] = int32 count of this step, then cap rows of FW_INFO_HEAD + obs_dim
+    int info_cap;
 };
 
 template <typename T>
@@ -248,6 +250,7 @@ __global__ void __launch_bounds__(128, 4) rk45_init_kernel(const __grid_constant
     if (env == 0) {
         *W.counter = attempt_threads;      // queue head: the first attempt_threads envs are pre-assigned
         *done_count = 0;                   // this step's list of envs that take their precomputed reset row
+        if (io.info) *reinterpret_cast<int32_t*>(io.info) = 0;
     }
     if (env >= n) return;
     T y[FW_NY], h_abs = 0, elev0, ail0;
@@ -440,7 +443,10 @@ __global__ void __launch_bounds__(128) rk4_kernel(const __grid_constant__ DCfg<T
                                                   const Scratch<T> W, int32_t* done_count) {
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = S.n;
-    if (env == 0) *done_count = 0;
+    if (env == 0) {
+        *done_count = 0;
+        if (io.info) *reinterpret_cast<int32_t*>(io.info) = 0;
+    }
     if (env >= n) return;
     T y[FW_NY], elev0, ail0;
     DynCtx<T> x;
@@ -895,6 +901,18 @@ __global__ void __launch_bounds__(64, 8) head_kernel(const __grid_constant__ DCf
     take_spare_warp<T>(S, P, take, env, odim, io.obs, io.obs64);
     if (take) {
         P.list[(size_t)parity * n + atomicAdd(P.count + parity, 1)] = env;
+        if (io.info) {
+            // packed episode-end row for the host (fw_set_info_rows): env, termination, length, return, 28 metrics,
+            // terminal observation — what VecEnv infos need, fetched together with the step outputs
+            const int slot = atomicAdd(reinterpret_cast<int32_t*>(io.info), 1);
+            if (slot < io.info_cap) {
+                double* row = io.info + 1 + (size_t)slot * (FW_INFO_HEAD + odim);
+                const double* m = S.metrics + (size_t)env * FW_NMETRIC;
+                row[0] = (double)env; row[1] = (double)term; row[2] = (double)steps; row[3] = (double)ep_ret;
+                for (int k = 0; k < FW_NMETRIC; ++k) row[4 + k] = m[k];
+                for (int q = 0; q < odim; ++q) row[FW_INFO_HEAD + q] = (double)(float)obs_out[q];
+            }
+        }
         return;
     }
     write_obs(obs_out, odim, env, io.obs, io.obs64);
@@ -1231,6 +1249,7 @@ struct FwHandle {
     cudaStream_t side;
     cudaEvent_t ev_head, ev_refill;
     int refill_pending, step_parity;
+    double* info_rows; int info_cap;       // fw_set_info_rows
     // fw_set_profiling: CUDA events around each kernel of a step (the step then ends with an event synchronise)
     int prof_on;
     cudaEvent_t prof_ev[4];
@@ -1339,7 +1358,10 @@ static int launch_rk4(FwHandle* h, const DCfg<T>& c, const Soa<T>& S, const Scra
     return FW_OK;
 }
 
-static int launch_step(FwHandle* h, const StepIO& io, cudaStream_t st) {
+static int launch_step(FwHandle* h, const StepIO& io_in, cudaStream_t st) {
+    StepIO io = io_in;
+    io.info = io.auto_reset ? h->info_rows : nullptr;
+    io.info_cap = h->info_cap;
     const bool turb = h->cfg.turbulence != 0, rk45 = h->cfg.integrator == FW_INT_RK45_SCIPY;
     if (h->cfg.precision == FW_F64) {
         if (rk45) return turb ? launch_rk45<double, true, NT_RK45_F64>(h, h->c64, h->s64, h->w64, h->p64, io, st)
@@ -1362,6 +1384,17 @@ int fw_obs_dim(const FwHandle* h) {
     if (!h) return FW_EINVAL;
     if (h->cfg.env_kind == FW_ENV_WAYPOINT) return FW_NOBS_WAYPOINT;
     return h->cfg.obs_generic ? h->cfg.obs_len * h->cfg.obs_n : FW_NOBS;
+}
+
+int fw_set_info_rows(FwHandle* h, double* rows_dev, int32_t cap) {
+    if (!h || (rows_dev && cap <= 0)) return FW_EINVAL;
+    if (h->cfg.env_kind == FW_ENV_WAYPOINT && rows_dev) {
+        snprintf(g_err, sizeof(g_err), "fw_set_info_rows: not available for the waypoint env");
+        return FW_EINVAL;
+    }
+    h->info_rows = rows_dev;
+    h->info_cap = rows_dev ? cap : 0;
+    return FW_OK;
 }
 
 int fw_join(FwHandle* h, void* stream) {

@@ -62,7 +62,8 @@ class FixedWingVecEnv:
 
     info_mode: "compat" builds the reference's per-env info dict for every env every step (info["target"] always
     present, fixed_wing.py:626); "lazy" (default) builds dicts only for envs that finished and hands out one shared
-    empty dict for the rest — at tens of thousands of envs the dict loop, not the simulator, bounds the step rate.
+    empty dict for the rest, in one persistent list that is valid until the next step — at tens of thousands of envs
+    the dict loop (or even copying the list), not the simulator, bounds the step rate.
     copy_outputs: False (default) returns views of double-buffered pinned host arrays that stay valid until the
     second-next step() (enough for SB3's collect_rollouts); True returns fresh copies every step.
     """
@@ -92,15 +93,18 @@ class FixedWingVecEnv:
         self._act_np = self._act_pin.numpy()
         self._act_dev = torch.zeros(n, 3, dtype=torch.float32, device=self.device)
         # double-buffered pinned outputs: with copy_outputs=False the arrays returned by step k stay valid until
-        # step k+2 (SB3's collect_rollouts reads obs_k after step k+1 returns, on_policy_algorithm.py:163-180)
-        self._out = [(torch.zeros(n, self.sim.obs_dim, dtype=torch.float32).pin_memory(),
-                      torch.zeros(n, dtype=torch.float32).pin_memory(),
-                      torch.zeros(n, dtype=torch.uint8).pin_memory()) for _ in range(2)]
+        # step k+2 (SB3's collect_rollouts reads obs_k after step k+1 returns, on_policy_algorithm.py:163-180).
+        # Each buffer mirrors the simulator's packed obs | rew | done layout: ONE device-to-host copy per step.
+        self._out_pin = [torch.zeros(self.sim.out_nbytes, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        self._out = [bt.unpack_outputs(b, n, self.sim.obs_dim) for b in self._out_pin]
+        self._info_np = ([b[self.sim.info_offset:].view(torch.float64).numpy() for b in self._out_pin]
+                         if self.sim.info_cap else None)
         self._out_np = [(o.numpy(), r.numpy(), d.numpy().view(np.bool_)) for o, r, d in self._out]
         self._flip = 0
         # touch the done-path once so that CUDA's lazy module loading does not land on the first finished episode
         self.sim.episode_info_rows(torch.zeros(1, dtype=torch.long, device=self.device))
-        self._no_done_infos = [_EMPTY_INFO] * n
+        self._lazy_infos = [_EMPTY_INFO] * n
+        self._lazy_dirty = []
         self._waiting = False
         self._t_start = time.time()
         self.h2d_bytes_per_step = self._act_pin.numel() * 4
@@ -130,14 +134,13 @@ class FixedWingVecEnv:
         a = np.asarray(actions)
         assert a.shape == (self.num_envs, 3), a.shape
         self._act_np[...] = a                     # casts to float32 like DummyVecEnv buffers / SB3 policies
-        assert not np.isnan(self._act_np.sum()), "NaN action (fixed_wing.py:494)"
         self._act_dev.copy_(self._act_pin, non_blocking=True)
         self.sim.step(self._act_dev, auto_reset=True)
         self._flip ^= 1
-        o, r, d = self._out[self._flip]
-        o.copy_(self.sim.obs, non_blocking=True)
-        r.copy_(self.sim.rew, non_blocking=True)
-        d.copy_(self.sim.done, non_blocking=True)
+        self._out_pin[self._flip].copy_(self.sim.out_packed, non_blocking=True)
+        # fixed_wing.py:494 asserts on NaN actions before stepping; here the check runs while the GPU works (max
+        # propagates NaN) — the step it rejects has been launched, but the assertion is fatal either way
+        assert not np.isnan(self._act_np.max()), "NaN action (fixed_wing.py:494)"
         self._waiting = True
 
     def step_wait(self):
@@ -247,35 +250,60 @@ class FixedWingVecEnv:
         d.update(roll=float(e[0]), pitch=float(e[1]), Va=float(v[0]), alpha=float(v[1]), beta=float(v[2]))
         return d
 
-    def _build_infos(self, done):
+    def _build_infos(self, done, packed_rows=True):
+        """packed_rows: the step was an auto-reset step whose outputs (and episode-end rows) are in the pinned buffer."""
         n = self.num_envs
-        if self.info_mode == "lazy" and not done.any():
-            return self._no_done_infos            # one shared list of one shared empty dict: treat as read-only
-        done_idx = np.flatnonzero(done)
-        if self.info_mode == "compat":
+        compat = self.info_mode == "compat"
+        # lazy mode hands out ONE persistent list whose entries are a shared empty dict except for the envs that
+        # finished at this step (treat as read-only; valid until the next step): copying a 65 536-entry list per step
+        # costs more than the simulator
+        if not compat:
+            infos = self._lazy_infos
+            for i in self._lazy_dirty:
+                infos[i] = _EMPTY_INFO
+            self._lazy_dirty = []
+        # the episode-end rows came with the step outputs (fw_set_info_rows); only a step in which more than INFO_CAP
+        # episodes end needs a second fetch
+        rows = done_idx = None
+        if packed_rows and self._info_np is not None:
+            head = self._info_np[self._flip]
+            cnt = int(head[:1].view(np.int32)[0])
+            if cnt == 0 and not compat:
+                return infos
+            if cnt <= self.sim.info_cap:
+                packed = head[1:1 + cnt * self.sim.info_width].reshape(cnt, self.sim.info_width)
+                done_idx = packed[:, 0].astype(np.int64)
+                # -> the layout of episode_info_rows: metrics | return | length | term code | terminal observation
+                rows = np.concatenate([packed[:, 4:32], packed[:, 3:4], packed[:, 2:3], packed[:, 1:2], packed[:, 32:]],
+                                      axis=1)
+        if rows is None:
+            done_idx = np.flatnonzero(done)
+            if done_idx.size == 0 and not compat:
+                return infos
+            rows = (self.sim.episode_info_rows(torch.as_tensor(done_idx, device=self.device)) if done_idx.size
+                    else np.zeros((0, 31 + self.sim.obs_dim)))
+        if compat:
             tgt = self.sim.get_field(bt.FIELD_TARGET).cpu().numpy()
             infos = [{"target": dict(zip(TARGET_STATES, map(float, tgt[i])))} for i in range(n)]
-        else:
-            infos = list(self._no_done_infos)
-        if done_idx.size:
-            rows = self.sim.episode_info_rows(torch.as_tensor(done_idx, device=self.device))
-            now = round(time.time() - self._t_start, 6)
-            for row, i in zip(rows, done_idx):
-                info = dict(infos[i])
-                metrics, ret, length, term, term_obs = row[:28], row[28], int(row[29]), int(row[30]), row[31:]
-                info["termination"] = TERM_NAMES.get(term, term)
-                for name, off, keys in METRIC_LAYOUT:
-                    vals = metrics[off:off + len(keys)]
-                    if name == "success":
-                        info[name] = {k: bool(x) for k, x in zip(keys, vals)}
-                    else:
-                        info[name] = {k: float(x) for k, x in zip(keys, vals)}
-                info["terminal_observation"] = term_obs.astype(np.float32)
-                info["episode"] = {"r": float(ret), "l": length, "t": now}
-                if not self.cfg.obs_generic:
-                    # fixed_wing.py:626 reports the finished episode's target; it sits in terminal_observation[6:9]
-                    info.setdefault("target", dict(zip(TARGET_STATES, map(float, term_obs[6:9]))))
-                infos[i] = info
+        now = round(time.time() - self._t_start, 6)
+        term_obs_all = rows[:, 31:].astype(np.float32)
+        generic = bool(self.cfg.obs_generic)
+        for j, (row, i) in enumerate(zip(rows[:, :31].tolist(), done_idx.tolist())):
+            info = dict(infos[i])
+            term = int(row[30])
+            info["termination"] = TERM_NAMES.get(term, term)
+            for name, off, keys in METRIC_LAYOUT:
+                vals = row[off:off + len(keys)]
+                info[name] = dict(zip(keys, map(bool, vals))) if name == "success" else dict(zip(keys, vals))
+            term_obs = term_obs_all[j]
+            info["terminal_observation"] = term_obs
+            info["episode"] = {"r": row[28], "l": int(row[29]), "t": now}
+            if not generic and "target" not in info:
+                # fixed_wing.py:626 reports the finished episode's target; it sits in terminal_observation[6:9]
+                info["target"] = dict(zip(TARGET_STATES, term_obs[6:9].tolist()))
+            infos[i] = info
+        if not compat:
+            self._lazy_dirty = done_idx.tolist()
         return infos
 
 
@@ -345,7 +373,7 @@ class FixedWingAircraft:
         done = bool(self._v.sim.done.cpu().numpy()[0])
         if done:
             self._v.sim.term_obs.copy_(self._v.sim.obs)
-        info = self._v._build_infos(np.array([done]))[0]
+        info = self._v._build_infos(np.array([done]), packed_rows=False)[0]
         info.pop("terminal_observation", None)
         info.pop("episode", None)
         return obs, rew, done, info
