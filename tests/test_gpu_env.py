@@ -291,3 +291,108 @@ def test_waypoint_env_head(cuda_device):
     obs, rew, done, infos = venv.step(np.tile([0.0, 0.0, 0.5], (8, 1)))
     assert obs.shape == (8, 12) and rew.shape == (8,) and (rew > 0).all() and not done.any() and len(infos) == 8
     venv.close()
+
+
+def test_precomputed_reset_rows_equal_an_inline_reset(cuda_device):
+    """Auto-reset copies a row that refill_kernel computed one or more steps earlier on the side stream.  It must be
+    the row a reset of that env into that episode produces: run A with auto-reset over several episode ends and replay every episode start in run B by an explicit masked reset
+    (reset_kernel: inline reset_env) — states, targets, filter states and observations must agree bit for bit."""
+    import torch
+    from tum_adlr_deep_reinforcement_learning_b200 import batched as bt
+    from tum_adlr_deep_reinforcement_learning_b200.config import build_config
+    n = 96
+    kw = dict(config_kw={"steps_max": 5}, sim_config_kw={"turbulence": True}, seed=11)
+    A = bt.BatchedFixedWing(n, cfg=build_config(**kw))
+    B = bt.BatchedFixedWing(n, cfg=build_config(**kw))
+    A.reset(); B.reset()
+    g = torch.Generator(device="cuda"); g.manual_seed(5)
+    fields = (bt.FIELD_Y, bt.FIELD_TARGET, bt.FIELD_EULER, bt.FIELD_VAB, bt.FIELD_COUNTERS)
+    ends = 0
+    for t in range(23):
+        a = (torch.rand(n, 3, device="cuda", generator=g) * 2 - 1).contiguous()
+        if t % 7 == 3:
+            a[::5] = 50.0          # saturated commands: some envs fail early, off the steps_max beat
+        oa, ra, da = A.step(a, auto_reset=True)
+        ob, rb, db = B.step(a, auto_reset=False)
+        assert torch.equal(da, db) and torch.equal(ra, rb)
+        if bool(db.any()):
+            ends += int(db.sum())
+            B.reset(mask=db)
+            ob = B.obs
+        assert torch.equal(oa, ob), "step %d" % t
+        for f in fields:
+            fa, fb = A.get_field(f), B.get_field(f)        # yaw is not materialised (NaN column of FIELD_EULER)
+            assert torch.equal(torch.nan_to_num(fa.double(), nan=-7.0), torch.nan_to_num(fb.double(), nan=-7.0)), (t, f)
+    assert ends >= 4 * n
+    A.close(); B.close()
+
+
+def test_episode_end_rows_travel_with_the_outputs(cuda_device):
+    """fw_set_info_rows: the packed rows of a step equal fw_get_episode_info + term_obs for exactly the done envs; a
+    step with more ends than INFO_CAP reports the true count and the VecEnv falls back to the second fetch."""
+    import torch
+    from tum_adlr_deep_reinforcement_learning_b200 import batched as bt
+    from tum_adlr_deep_reinforcement_learning_b200.config import build_config
+    from tum_adlr_deep_reinforcement_learning_b200.vec_env import FixedWingVecEnv
+    n = 48
+    env = bt.BatchedFixedWing(n, cfg=build_config(config_kw={"steps_max": 9}, sim_config_kw={"turbulence": False}, seed=2))
+    env.reset()
+    g = torch.Generator(device="cuda"); g.manual_seed(0)
+    seen = 0
+    for t in range(20):
+        a = (torch.rand(n, 3, device="cuda", generator=g) * 2 - 1).contiguous()
+        if t == 4:
+            a[:7] = 80.0
+        env.step(a)
+        head = env.info_rows.cpu().numpy()
+        cnt = int(head[:1].view(np.int32)[0])
+        done = env.done.cpu().numpy().astype(bool)
+        assert cnt == done.sum()
+        if cnt:
+            rows = head[1:1 + cnt * env.info_width].reshape(cnt, env.info_width)
+            term, metrics, ret, length = (x.cpu().numpy() for x in env.episode_info())
+            tobs = env.term_obs.cpu().numpy()
+            assert sorted(rows[:, 0].astype(int)) == list(np.flatnonzero(done))
+            for row in rows:
+                i = int(row[0])
+                assert row[1] == term[i] and row[2] == length[i] and row[3] == ret[i]
+                np.testing.assert_array_equal(row[4:32], metrics[i])
+                np.testing.assert_array_equal(row[32:], tobs[i].astype(np.float64))
+            seen += cnt
+    assert seen >= 2 * n
+    env.close()
+    # more ends than INFO_CAP in one step (all envs hit steps_max together): infos still complete
+    venv = FixedWingVecEnv(bt.INFO_CAP + 40, config_kw={"steps_max": 3}, sim_config_kw={"turbulence": False})
+    venv.reset()
+    for t in range(3):
+        obs, rew, done, infos = venv.step(np.zeros((venv.num_envs, 3), np.float32))
+    assert done.all() and all(info["episode"]["l"] == 3 and info["termination"] == "steps" for info in infos)
+    obs, rew, done, infos = venv.step(np.zeros((venv.num_envs, 3), np.float32))
+    assert not done.any() and all(info == {} for info in infos)
+    venv.close()
+
+
+def test_profiling_api_and_pinned_actions(cuda_device):
+    import torch
+    from tum_adlr_deep_reinforcement_learning_b200.vec_env import FixedWingVecEnv
+    outs = []
+    for pinned in (False, True):
+        venv = FixedWingVecEnv(256, sim_config_kw={"turbulence": True}, seed=4)
+        venv.reset()
+        rs = np.random.RandomState(1)
+        bufs = venv.pinned_actions(2) if pinned else [np.zeros((256, 3), np.float32) for _ in range(2)]
+        venv.sim.set_profiling(True)
+        for t in range(6):
+            bufs[t % 2][...] = rs.uniform(-1, 1, (256, 3))
+            obs, rew, done, infos = venv.step(bufs[t % 2])
+        p = venv.sim.profile()
+        assert p["steps"] == 6 and p["init_ms"] > 0 and p["integrate_ms"] > p["init_ms"] and p["head_ms"] > 0
+        venv.sim.set_profiling(False)
+        assert venv.sim.profile()["steps"] == 0
+        outs.append((obs.copy(), rew.copy()))
+        with pytest.raises(AssertionError):
+            bad = bufs[0]; bad[3, 1] = np.nan
+            venv.step(bad)
+        venv.close()
+    np.testing.assert_array_equal(outs[0][0], outs[1][0])
+    np.testing.assert_array_equal(outs[0][1], outs[1][1])

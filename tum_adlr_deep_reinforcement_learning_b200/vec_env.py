@@ -110,6 +110,13 @@ class FixedWingVecEnv:
         self.h2d_bytes_per_step = self._act_pin.numel() * 4
         self.d2h_bytes_per_step = n * self.sim.obs_dim * 4 + n * 4 + n
 
+    def pinned_actions(self, count=1):
+        """`count` float32 [num_envs, 3] arrays in page-locked host memory.  step() copies an array of this kind to the
+        device directly; any other array is first staged through an internal pinned buffer (one extra host copy)."""
+        bufs = [torch.zeros(self.num_envs, 3, dtype=torch.float32).pin_memory() for _ in range(count)]
+        self._user_pins = getattr(self, "_user_pins", []) + bufs        # keep the allocations alive
+        return [b.numpy() for b in bufs]
+
     # ------------------------------------------------------------------ tensor fast path
     def reset_tensor(self):
         return self.sim.reset()
@@ -133,14 +140,21 @@ class FixedWingVecEnv:
             raise RuntimeError("step_async called while a step is pending (subproc_vec_env.py:112 contract)")
         a = np.asarray(actions)
         assert a.shape == (self.num_envs, 3), a.shape
-        self._act_np[...] = a                     # casts to float32 like DummyVecEnv buffers / SB3 policies
-        self._act_dev.copy_(self._act_pin, non_blocking=True)
+        src = None
+        if a.dtype == np.float32 and a.flags.c_contiguous:
+            t = torch.from_numpy(a)
+            if t.is_pinned():                     # e.g. an array from pinned_actions(): DMA straight from it
+                src = t
+        if src is None:
+            self._act_np[...] = a                 # casts to float32 like DummyVecEnv buffers / SB3 policies
+            src, a = self._act_pin, self._act_np
+        self._act_dev.copy_(src, non_blocking=True)
         self.sim.step(self._act_dev, auto_reset=True)
         self._flip ^= 1
         self._out_pin[self._flip].copy_(self.sim.out_packed, non_blocking=True)
         # fixed_wing.py:494 asserts on NaN actions before stepping; here the check runs while the GPU works (max
         # propagates NaN) — the step it rejects has been launched, but the assertion is fatal either way
-        assert not np.isnan(self._act_np.max()), "NaN action (fixed_wing.py:494)"
+        assert not np.isnan(a.max()), "NaN action (fixed_wing.py:494)"
         self._waiting = True
 
     def step_wait(self):
