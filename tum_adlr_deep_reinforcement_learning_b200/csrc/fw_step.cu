@@ -49,13 +49,26 @@ __device__ __noinline__ void reset_env_noinline(const DCfg<T>& c, const Soa<T>& 
 // 31 other lanes of the warp — and, because one wave of warps runs the kernel, the whole step — wait for it; the
 // consumed rows are recomputed by refill_kernel on a side stream while the next step integrates.
 template <typename T> struct Spare {
-    Soa<T> S2;        // r [RF_COUNT][n], i [IF_COUNT][n], err_ring [3][n] of the precomputed rows
+    Soa<T> S2;        // r [n][RF_COUNT], i [n][IF_COUNT], err_ring [n][3] of the precomputed rows: env-major, so that
+                      // the copy of one env's row reads contiguous memory (one page, full sectors)
     float* obs;       // [n][obs_dim]
     double* obs64;    // [n][obs_dim]
     int32_t* list;    // [2][n] envs that consumed their row at a step (indexed by step parity)
     int32_t* count;   // [2]
     int on;           // 0: inline reset (waypoint env)
 };
+
+// reset_env addresses field f of env e as base[f * S.n + e]; with n = 1 and the base moved by e * (fields - 1) that is
+// base[e * fields + f], the env-major spare layout
+template <typename T>
+__device__ __forceinline__ Soa<T> spare_view(const Spare<T>& P, int env) {
+    Soa<T> L = P.S2;
+    L.r += (size_t)env * (RF_COUNT - 1);
+    L.i += (size_t)env * (IF_COUNT - 1);
+    L.err_ring += (size_t)env * 2;
+    L.n = 1;
+    return L;
+}
 
 // Warp-cooperative: for every lane whose episode ended (`mine`), all converged lanes of the warp copy that env's
 // precomputed row, field f by lane f mod width, every lane's loads in flight at once — one DRAM round trip per
@@ -76,25 +89,25 @@ __device__ __forceinline__ void take_spare_warp(const Soa<T>& S, const Spare<T>&
         dm &= dm - 1;
         const int e = __shfl_sync(act, env, owner);
         {
-            const T* src = P.S2.r + e;
+            const T* src = P.S2.r + (size_t)e * RF_COUNT;
             T* dst = S.r + e;
 #pragma unroll 1
             for (int f0 = rank; f0 < RF_COUNT; f0 += 8 * width) {
                 T tmp[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) tmp[j] = (f0 + j * width < RF_COUNT) ? src[(size_t)(f0 + j * width) * n] : (T)0;
+                for (int j = 0; j < 8; ++j) tmp[j] = (f0 + j * width < RF_COUNT) ? src[f0 + j * width] : (T)0;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) if (f0 + j * width < RF_COUNT) dst[(size_t)(f0 + j * width) * n] = tmp[j];
             }
         }
         {
-            const int32_t* src = P.S2.i + e;
+            const int32_t* src = P.S2.i + (size_t)e * IF_COUNT;
             int32_t* dst = S.i + e;
 #pragma unroll 1
             for (int f0 = rank; f0 < IF_COUNT; f0 += 2 * width) {
                 int32_t tmp[2];
 #pragma unroll
-                for (int j = 0; j < 2; ++j) tmp[j] = (f0 + j * width < IF_COUNT) ? src[(size_t)(f0 + j * width) * n] : 0;
+                for (int j = 0; j < 2; ++j) tmp[j] = (f0 + j * width < IF_COUNT) ? src[f0 + j * width] : 0;
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
                     const int f = f0 + j * width;
@@ -102,7 +115,7 @@ __device__ __forceinline__ void take_spare_warp(const Soa<T>& S, const Spare<T>&
                 }
             }
         }
-        if (rank < 3) S.err_ring[(size_t)rank * n + e] = P.S2.err_ring[(size_t)rank * n + e];
+        if (rank < 3) S.err_ring[(size_t)rank * n + e] = P.S2.err_ring[(size_t)e * 3 + rank];
         for (int q = rank; q < odim; q += width) {
             if (obs) obs[(size_t)e * odim + q] = P.obs[(size_t)e * odim + q];
             if (obs64) obs64[(size_t)e * odim + q] = P.obs64[(size_t)e * odim + q];
@@ -113,8 +126,9 @@ __device__ __forceinline__ void take_spare_warp(const Soa<T>& S, const Spare<T>&
 // the row of the episode after the one env is in now (main S): spare.episode := main.episode, then reset the spare
 template <typename T>
 __device__ void make_spare(const DCfg<T>& c, const Soa<T>& S, const Spare<T>& P, int env) {
-    P.S2.i[IF_EPISODE * S.n + env] = S.i[IF_EPISODE * S.n + env];
-    reset_env<T>(c, P.S2, env, nullptr, nullptr, P.obs, P.obs64);
+    const Soa<T> L = spare_view(P, env);
+    L.i[IF_EPISODE + env] = S.i[IF_EPISODE * S.n + env];
+    reset_env<T>(c, L, env, nullptr, nullptr, P.obs, P.obs64);
 }
 
 template <typename T>
@@ -132,9 +146,11 @@ template <typename T>
 __global__ void __launch_bounds__(32) refill_kernel(const __grid_constant__ DCfg<T> c, const Spare<T> P, int parity) {
     const int n = P.S2.n;
     const int cnt = P.count[parity];
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < cnt; j += gridDim.x * blockDim.x)
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < cnt; j += gridDim.x * blockDim.x) {
         // the consumed row carried episode e + 1, which is what the spare's own counter still says: this makes e + 2
-        reset_env<T>(c, P.S2, P.list[(size_t)parity * n + j], nullptr, nullptr, P.obs, P.obs64);
+        const int env = P.list[(size_t)parity * n + j];
+        reset_env<T>(c, spare_view(P, env), env, nullptr, nullptr, P.obs, P.obs64);
+    }
 }
 
 // sum |diff| of one column over the trailing window, accumulated in float32 like
