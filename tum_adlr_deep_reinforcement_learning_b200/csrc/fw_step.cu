@@ -37,11 +37,6 @@ struct StepIO {
     int info_cap;
 };
 
-template <typename T>
-__device__ __noinline__ void reset_env_noinline(const DCfg<T>& c, const Soa<T>& S, int env, float* obs, double* obs64) {
-    reset_env<T>(c, S, env, nullptr, nullptr, obs, obs64);
-}
-
 // Precomputed next-episode rows.  FixedWingAircraft.reset depends only on (seed, env id, episode number) — never on the
 // trajectory that just ended — so the complete post-reset row of every env (state SoA row, first error-ring entry, reset
 // observation) is computed AHEAD of time into a second SoA.  When an episode ends, head_kernel copies that row into
@@ -555,11 +550,15 @@ __device__ __noinline__ void end_error_sums(const Soa<T>& S, int env, int n_err,
 }
 
 // ---- kernel B: everything after the integrator (once per step, high occupancy) ----
-// One wave of warps runs this kernel, so its duration is the critical path of ONE warp: every exposed DRAM round trip
-// adds to it in full.  All loads are therefore issued up front (a load cannot be moved above a store that may alias
-// it, so no store happens before the last load; only the two goal-ring words per goal wait for `steps`), and all
-// stores sit at the end.  Splitting the kernel into load -> compute -> store phases per subsystem was measured at
-// 1.5x the duration (one round trip per phase).
+// One wave of warps runs this kernel (1024 blocks of 64 threads, 8 per SM), so its duration is the critical path of ONE
+// warp: every exposed DRAM round trip and every long dependent chain adds to it in full.  Hence: the integrator
+// output is loaded without waiting for the `fail` flag; the rare episode-end work is warp-cooperative (end-error ring
+// sums, the copy of the precomputed next-episode row) instead of one lane walking hundreds of dependent loads while the
+// whole grid waits (that was +70 us on every step in which any episode ended); the episode-end rows for the host are
+// written here so that they travel with the step outputs.  Two restructurings were measured and dropped: strict
+// load -> compute -> store phases per subsystem (one round trip per phase: 1.5x slower) and hoisting every load to the
+// top (1.5 KB of spills, 10 % slower).
+
 // The same sums with the whole warp fetching: every lane loads 5 of the (up to) 150 ring entries of a finished env —
 // one DRAM round trip instead of five — and the owner adds them up in chronological order through shuffles.  The
 // entry of the current step is already in the ring (the owner stored it; __syncwarp orders that store before the loads).
@@ -617,15 +616,17 @@ __global__ void __launch_bounds__(64, 8) head_kernel(const __grid_constant__ DCf
     if (env >= n) return;
     T* r = S.r + env;
     int32_t* ii = S.i + env;
-
-    // ======================= loads =======================
     int fail = W.fail[env];
     T y[FW_NY];
 #pragma unroll
     for (int i = 0; i < FW_NY; ++i) y[i] = W.ytmp[i * n + env];     // not waiting for `fail`: a raise is the rare case
-    T roll = r[RF_ROLL * n], pitch = r[RF_PITCH * n], Va = r[RF_VA * n], alpha = r[RF_ALPHA * n], beta = r[RF_BETA * n];
-    // .history[-1] view of omega for a terminal observation
-    T om_obs[3] = {r[(RF_Y + 4) * n], r[(RF_Y + 5) * n], r[(RF_Y + 6) * n]};
+    if (fail) {
+#pragma unroll
+        for (int i = 0; i < FW_NY; ++i) y[i] = r[(RF_Y + i) * n];
+    }
+    const T roll_prev = r[RF_ROLL * n], pitch_prev = r[RF_PITCH * n], Va_prev = r[RF_VA * n];
+    const T alpha_prev = r[RF_ALPHA * n], beta_prev = r[RF_BETA * n];
+    const T omega_prev[3] = {r[(RF_Y + 4) * n], r[(RF_Y + 5) * n], r[(RF_Y + 6) * n]};
     DynCtx<T> x;
     T tgt[3];
 #pragma unroll
@@ -635,55 +636,10 @@ __global__ void __launch_bounds__(64, 8) head_kernel(const __grid_constant__ DCf
     }
     int steps = ii[IF_STEPS * n], steps_tgt = ii[IF_STEPS_TGT * n], sim_step = ii[IF_SIM_STEP * n];
     const unsigned long long episode = (unsigned long long)(uint32_t)ii[IF_EPISODE * n];
+    const int nfev = ii[IF_NFEV * n], natt = ii[IF_NATT * n];
     T a_raw[3], cmd_in[3];
     bool act_f32;
     prep_action(c, io, env, a_raw, act_f32, x.cmd, cmd_in);
-    // loads: action / command rings (age 1 = most recent), goal counters and the two ring words each goal needs
-    T aring[12], cring[12];
-#pragma unroll
-    for (int i = 0; i < 12; ++i) aring[i] = r[(RF_ACT_RING + i) * n];
-    const bool need_cring = !c.scale_actions;
-#pragma unroll
-    for (int i = 0; i < 12; ++i) cring[i] = (need_cring || i < 3) ? r[(RF_CMD_RING + i) * n] : (T)0;
-    T cv_sum = r[RF_CV_SUM * n];
-    int gbits[4] = {0, 0, 0, 0};
-    int gcnt[4], gtot[4], settle[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        gcnt[k] = ii[(IF_GOAL_CNT + k) * n]; gtot[k] = ii[(IF_GOAL_TOTAL + k) * n]; settle[k] = ii[(IF_SETTLE + k) * n];
-    }
-    const int gidx = steps + 1;                // index of this entry in history["goal"] (entry 0 = reset)
-    const int gw = (gidx & 127) >> 5, gb = gidx & 31;
-    const int gidx_old = gidx - c.streak_req;
-    uint32_t gword[4] = {0, 0, 0, 0}, gold[4] = {0, 0, 0, 0};
-    if (c.streak_req > 0) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int32_t* ring = ii + (IF_GOAL_RING + 4 * k) * n;
-            gword[k] = (uint32_t)ring[gw * n];
-            if (gidx_old >= 0) gold[k] = (uint32_t)ring[((gidx_old & 127) >> 5) * n];
-        }
-    }
-    int goal_achieved = 0;
-    if (c.rew_generic) goal_achieved = ii[IF_GOAL_ACHIEVED * n];
-    int tcls[3] = {c.tgt_class[0], c.tgt_class[1], c.tgt_class[2]};
-    T tp[15];
-    if (c.tgt_moving) {
-#pragma unroll
-        for (int k = 0; k < 15; ++k) tp[k] = r[(RF_TPROP + k) * n];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) tcls[k] = ii[(IF_TCLS + k) * n];
-    }
-
-    T esum[3], eabs[3], emin[3], emax[3], e0v[3], eprev[3];
-    int rise_lo[3], rise_hi[3];
-    T ep_ret = r[RF_EP_RET * n];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        e0v[k] = r[(RF_E0 + k) * n]; esum[k] = r[(RF_ESUM + k) * n]; eabs[k] = r[(RF_EABS + k) * n];
-        emin[k] = r[(RF_EMIN + k) * n]; emax[k] = r[(RF_EMAX + k) * n]; eprev[k] = r[(RF_EPREV + k) * n];
-        rise_lo[k] = ii[(IF_RISE_LO + k) * n]; rise_hi[k] = ii[(IF_RISE_HI + k) * n];
-    }
     T fx[12], fu[4];
     if (TURB) {
 #pragma unroll
@@ -691,52 +647,71 @@ __global__ void __launch_bounds__(64, 8) head_kernel(const __grid_constant__ DCf
 #pragma unroll
         for (int i = 0; i < 4; ++i) fu[i] = r[(RF_FU + i) * n];
     }
-    if (fail) {
-#pragma unroll
-        for (int i = 0; i < FW_NY; ++i) y[i] = r[(RF_Y + i) * n];
-    }
-    // ======================= post-step commit (pyfly.py:1396-1406, 1852-1881) =======================
+
+    // ---------------- post-step commit (pyfly.py:1396-1406, 1852-1881) ----------------
+    T roll = roll_prev, pitch = pitch_prev, Va = Va_prev, alpha = alpha_prev, beta = beta_prev;
+    T om_obs[3] = {omega_prev[0], omega_prev[1], omega_prev[2]};   // .history[-1] view for a terminal observation
     fail = post_step_commit<T>(c, x, y, fail, roll, pitch, Va, alpha, beta, om_obs);
     sim_step += 1;
 
-    // ======================= gym head (fixed_wing.py:512-628) =======================
+    // ---------------- gym head (fixed_wing.py:512-628) ----------------
     const int steps_before = steps;
     steps += 1;
     steps_tgt += 1;
     bool done = false;
     int term = FW_TERM_NONE;
     if (c.steps_max > 0 && steps >= c.steps_max) { done = true; term = FW_TERM_STEPS; }
-    const int n_prev = steps_before < 4 ? steps_before : 4;   // valid previous ring entries
-    const bool streak = c.streak_req > 0 && !fail;
 
+    // action / command rings: previous entries (age 1 = most recent)
+    T aring[12], cring[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) aring[i] = r[(RF_ACT_RING + i) * n];
+    const bool need_cring = !c.scale_actions;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) cring[i] = (need_cring || i < 3) ? r[(RF_CMD_RING + i) * n] : (T)0;
+    T cv_sum = r[RF_CV_SUM * n];
     if (steps_before >= 1) {
 #pragma unroll
         for (int j = 0; j < 3; ++j) cv_sum += M<T>::fabs(cmd_in[j] - cring[j]);
     }
+    const int n_prev = steps_before < 4 ? steps_before : 4;   // valid previous ring entries
+
     T e_new[3] = {0, 0, 0};
     T reward;
-    bool tprop_dirty = false;
+    T obs_v[FW_NOBS];
+    int gbits[4] = {0, 0, 0, 0};
+    int gcnt[4], gtot[4], settle[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        gcnt[k] = ii[(IF_GOAL_CNT + k) * n]; gtot[k] = ii[(IF_GOAL_TOTAL + k) * n]; settle[k] = ii[(IF_SETTLE + k) * n];
+    }
     if (!fail) {
         // goal status with the CURRENT target (fixed_wing.py:536-560)
         const T eg[3] = {err_roll(tgt[0], roll), tgt[1] - pitch, tgt[2] - Va};
         bool resample = false, success_on_step = false;
-        if (streak) {
+        if (c.streak_req > 0) {
             gbits[3] = 1;
 #pragma unroll
             for (int k = 0; k < 3; ++k) { gbits[k] = M<T>::fabs(eg[k]) <= c.tgt_bound[k]; gbits[3] &= gbits[k]; }
+            const int idx = steps;                 // index of this entry in history["goal"] (entry 0 = reset)
+            const int w = (idx & 127) >> 5, b = idx & 31;
+            const int idx_old = idx - c.streak_req;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                if (gidx_old >= 0) gcnt[k] -= (gold[k] >> (gidx_old & 31)) & 1;
-                gword[k] = (gword[k] & ~(1u << gb)) | ((uint32_t)gbits[k] << gb);
+                int32_t* ring = ii + (IF_GOAL_RING + 4 * k) * n;
+                if (idx_old >= 0) gcnt[k] -= (ring[((idx_old & 127) >> 5) * n] >> (idx_old & 31)) & 1;
+                uint32_t word = (uint32_t)ring[w * n];
+                word = (word & ~(1u << b)) | ((uint32_t)gbits[k] << b);
+                ring[w * n] = (int32_t)word;
                 gcnt[k] += gbits[k];
                 gtot[k] += gbits[k];
-                if (settle[k] < 0 && gidx + 1 >= c.streak_req &&
-                    (double)gcnt[k] / (double)c.streak_req >= (double)c.streak_fraction) settle[k] = gidx;
+                if (settle[k] < 0 && idx + 1 >= c.streak_req &&
+                    (double)gcnt[k] / (double)c.streak_req >= (double)c.streak_fraction) settle[k] = idx;
             }
             if (steps_tgt >= c.streak_req && (double)gcnt[3] / (double)c.streak_req >= (double)c.streak_fraction) {
                 if (c.rew_generic) {                       // goal_achieved_on_step (fixed_wing.py:546-547)
-                    success_on_step = goal_achieved == 0;
-                    goal_achieved = 1;
+                    success_on_step = ii[IF_GOAL_ACHIEVED * n] == 0;
+                    ii[IF_GOAL_ACHIEVED * n] = 1;
                 }
                 if (c.on_success == FW_SUCCESS_DONE) { done = true; term = FW_TERM_SUCCESS; }
                 else if (c.on_success == FW_SUCCESS_NEW) resample = true;
@@ -749,37 +724,50 @@ __global__ void __launch_bounds__(64, 8) head_kernel(const __grid_constant__ DCf
             val = generic_reward<T>(c, S, env, eg, st8, a_raw, act_f32, aring, n_prev, steps, gbits, success_on_step);
         } else {
 #pragma unroll
-            for (int k = 0; k < 3; ++k)
-                if (c.rew_err_scaling[k] > (T)0) val -= clip(M<T>::fabs(eg[k]) / c.rew_err_scaling[k], (T)0, c.rew_err_max[k]);
-            if (c.rew_delta_scaling > (T)0 && steps > 1) {
-                const int np_ = (c.rew_delta_window - 1) < n_prev ? (c.rew_delta_window - 1) : n_prev;
-                T dv;
-                if (act_f32) {
-                    const float s = ring_delta_sum_np<float, T>(np_, a_raw, aring);
-                    dv = (T)fminf(fmaxf(s / (float)c.rew_delta_scaling, 0.f), (float)c.rew_delta_max);
-                } else {
-                    dv = clip(ring_delta_sum_np<T, T>(np_, a_raw, aring) / c.rew_delta_scaling, (T)0, c.rew_delta_max);
-                }
-                val -= dv;
+        for (int k = 0; k < 3; ++k)
+            if (c.rew_err_scaling[k] > (T)0) val -= clip(M<T>::fabs(eg[k]) / c.rew_err_scaling[k], (T)0, c.rew_err_max[k]);
+        if (c.rew_delta_scaling > (T)0 && steps > 1) {
+            const int np_ = (c.rew_delta_window - 1) < n_prev ? (c.rew_delta_window - 1) : n_prev;
+            T dv;
+            if (act_f32) {
+                const float sd = ring_delta_sum_np<float, T>(np_, a_raw, aring);
+                dv = (T)fminf(fmaxf(sd / (float)c.rew_delta_scaling, 0.f), (float)c.rew_delta_max);
+            } else {
+                dv = clip(ring_delta_sum_np<T, T>(np_, a_raw, aring) / c.rew_delta_scaling, (T)0, c.rew_delta_max);
             }
-            if (c.rew_bound_scaling > (T)0 && c.has_action_bounds) {
-                T hi = 0, lo = 0;
+            val -= dv;
+        }
+        if (c.rew_bound_scaling > (T)0 && c.has_action_bounds) {
+            T hi = 0, lo = 0;
 #pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    if (a_raw[j] > c.action_bounds_max[j]) hi += M<T>::fabs(a_raw[j] - c.action_bounds_max[j]);
-                    if (a_raw[j] < c.action_bounds_min[j]) lo += M<T>::fabs(a_raw[j] - c.action_bounds_min[j]);
-                }
-                val -= clip(M<T>::fabs(hi + lo) / c.rew_bound_scaling, (T)0, c.rew_bound_max);
+            for (int j = 0; j < 3; ++j) {
+                if (a_raw[j] > c.action_bounds_max[j]) hi += M<T>::fabs(a_raw[j] - c.action_bounds_max[j]);
+                if (a_raw[j] < c.action_bounds_min[j]) lo += M<T>::fabs(a_raw[j] - c.action_bounds_min[j]);
             }
+            val -= clip(M<T>::fabs(hi + lo) / c.rew_bound_scaling, (T)0, c.rew_bound_max);
+        }
         }
         reward = val;
         // target resample / advance (fixed_wing.py:569-580, 1363-1471)
+        int tcls[3] = {c.tgt_class[0], c.tgt_class[1], c.tgt_class[2]};
+        T tp[15];
+        if (c.tgt_moving) {
+#pragma unroll
+            for (int k = 0; k < 15; ++k) tp[k] = r[(RF_TPROP + k) * n];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) tcls[k] = ii[(IF_TCLS + k) * n];
+        }
         if (resample || (c.resample_every > 0 && steps_tgt >= c.resample_every)) {
             T u12[12];
             target_draws<T>(c, c.env_id_offset + env, episode, RNG_RESAMPLE, (uint32_t)(steps * 8), u12);
             sample_target<T>(c, roll, pitch, Va, steps, u12, tgt, tcls, tp);
             steps_tgt = 0;
-            tprop_dirty = c.tgt_moving;
+            if (c.tgt_moving) {
+#pragma unroll
+                for (int k = 0; k < 15; ++k) r[(RF_TPROP + k) * n] = tp[k];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) ii[(IF_TCLS + k) * n] = tcls[k];
+            }
         }
         const T tgt_pitch_cur = tgt[1];
         if (c.tgt_moving) {
@@ -823,8 +811,7 @@ __global__ void __launch_bounds__(64, 8) head_kernel(const __grid_constant__ DCf
         reward = c.step_fail_timesteps ? (T)(steps - c.steps_max) : c.step_fail_value;
     }
 
-    // observation (fixed_wing.py:1113-1262)
-    T obs_v[FW_NOBS];
+    // ---------------- observation (fixed_wing.py:1113-1262) ----------------
     obs_v[0] = roll; obs_v[1] = pitch; obs_v[2] = Va;
     obs_v[3] = om_obs[0]; obs_v[4] = om_obs[1]; obs_v[5] = om_obs[2];
     obs_v[6] = tgt[0]; obs_v[7] = tgt[1]; obs_v[8] = tgt[2];
@@ -836,9 +823,9 @@ __global__ void __launch_bounds__(64, 8) head_kernel(const __grid_constant__ DCf
             obs_v[11 + j] = c.scale_actions ? delta_feature<T>(a_raw[j], aring, j, np_, act_f32)
                                             : delta_feature<T>(cmd_in[j], cring, j, np_, false);
     }
+
     if (!GENERIC && (c.obs_noise_std > (T)0 || c.obs_noise_mean != (T)0))
         add_obs_noise<T>(c, c.env_id_offset + env, episode, steps, obs_v, FW_NOBS);
-
     T og[GENERIC ? FW_NOBS_MAX : 1];
     const T* obs_out = obs_v;
     int odim = FW_NOBS;
@@ -852,23 +839,27 @@ __global__ void __launch_bounds__(64, 8) head_kernel(const __grid_constant__ DCf
         odim = c.obs_len * c.obs_n;
     }
 
-    // ======================= streamed episode statistics (fixed_wing.py:1644-1736) =======================
-    ep_ret += reward;
+    // ---------------- streamed episode statistics (fixed_wing.py:1644-1736) ----------------
+    T esum[3], eabs[3], emin[3], emax[3], e0v[3];
+    int rise_lo[3], rise_hi[3];
+    const T ep_ret = r[RF_EP_RET * n] + reward;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        e0v[k] = r[(RF_E0 + k) * n]; esum[k] = r[(RF_ESUM + k) * n]; eabs[k] = r[(RF_EABS + k) * n];
+        emin[k] = r[(RF_EMIN + k) * n]; emax[k] = r[(RF_EMAX + k) * n];
+        rise_lo[k] = ii[(IF_RISE_LO + k) * n]; rise_hi[k] = ii[(IF_RISE_HI + k) * n];
+    }
     int n_err = steps_before + 1;           // entries in history["error"] before this step
     if (!fail) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            const T ea = M<T>::fabs(e_new[k]);
+            const T ea = M<T>::fabs(e_new[k]), prev = r[(RF_EPREV + k) * n];
             const T low_lim = M<T>::fabs(c.rise_low * e0v[k]), high_lim = M<T>::fabs(c.rise_high * e0v[k]);
-            if (rise_lo[k] < 0 && eprev[k] >= low_lim && ea < low_lim) rise_lo[k] = n_err - 1;
-            if (rise_hi[k] < 0 && eprev[k] >= high_lim && ea < high_lim) rise_hi[k] = n_err - 1;
+            if (rise_lo[k] < 0 && prev >= low_lim && ea < low_lim) rise_lo[k] = n_err - 1;
+            if (rise_hi[k] < 0 && prev >= high_lim && ea < high_lim) rise_hi[k] = n_err - 1;
             esum[k] += e_new[k]; eabs[k] += ea;
             emin[k] = M<T>::fmin(emin[k], e_new[k]); emax[k] = M<T>::fmax(emax[k], e_new[k]);
-            eprev[k] = ea;
-        }
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            r[(RF_EPREV + k) * n] = eprev[k];
+            r[(RF_EPREV + k) * n] = ea;
             S.err_ring[(size_t)((n_err % FW_END_ERR_WINDOW) * 3 + k) * n + env] = e_new[k];
         }
         n_err += 1;
@@ -908,8 +899,6 @@ __global__ void __launch_bounds__(64, 8) head_kernel(const __grid_constant__ DCf
     if (io.rew64) io.rew64[env] = (double)reward;
     if (io.done) io.done[env] = done ? 1 : 0;
 
-    // the goal flag survives a reset (fixed_wing.py keeps goal_achieved across episodes)
-    if (streak && c.rew_generic) ii[IF_GOAL_ACHIEVED * n] = goal_achieved;
     // an episode that ended takes the next episode's row, computed ahead of time (refill_kernel recomputes it on the
     // side stream while the next step integrates)
     const bool take = done && io.auto_reset;
@@ -932,32 +921,30 @@ __global__ void __launch_bounds__(64, 8) head_kernel(const __grid_constant__ DCf
         return;
     }
     write_obs(obs_out, odim, env, io.obs, io.obs64);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        r[(RF_ESUM + k) * n] = esum[k]; r[(RF_EABS + k) * n] = eabs[k];
-        r[(RF_EMIN + k) * n] = emin[k]; r[(RF_EMAX + k) * n] = emax[k];
-        ii[(IF_RISE_LO + k) * n] = rise_lo[k]; ii[(IF_RISE_HI + k) * n] = rise_hi[k];
-    }
-    r[RF_EP_RET * n] = ep_ret;
 
+    // ---------------- store ----------------
+    if (TURB && !fail) {
+        T un[4];
+        noise_sample(c, S, env, episode, sim_step, un);
+        turb_step(c, fx, fu, un, sim_step);
+#pragma unroll
+        for (int i = 0; i < 12; ++i) r[(RF_FX + i) * n] = fx[i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) r[(RF_FU + i) * n] = fu[i];
+    }
     if (!fail) {
 #pragma unroll
         for (int i = 0; i < FW_NY; ++i) r[(RF_Y + i) * n] = y[i];
         r[RF_ROLL * n] = roll; r[RF_PITCH * n] = pitch; r[RF_VA * n] = Va; r[RF_ALPHA * n] = alpha; r[RF_BETA * n] = beta;
     }
-    // stores of phase 1: goal ring and counters, target, rings (age k -> age k+1, current -> age 1), step counters
-    if (streak) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) ii[((IF_GOAL_RING + 4 * k) + gw) * n] = (int32_t)gword[k];
+    for (int k = 0; k < 3; ++k) {
+        r[(RF_TGT + k) * n] = tgt[k];
+        r[(RF_ESUM + k) * n] = esum[k]; r[(RF_EABS + k) * n] = eabs[k];
+        r[(RF_EMIN + k) * n] = emin[k]; r[(RF_EMAX + k) * n] = emax[k];
+        ii[(IF_RISE_LO + k) * n] = rise_lo[k]; ii[(IF_RISE_HI + k) * n] = rise_hi[k];
     }
-    if (tprop_dirty) {
-#pragma unroll
-        for (int k = 0; k < 15; ++k) r[(RF_TPROP + k) * n] = tp[k];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) ii[(IF_TCLS + k) * n] = tcls[k];
-    }
-#pragma unroll
-    for (int k = 0; k < 3; ++k) r[(RF_TGT + k) * n] = tgt[k];
+    // rings shift: age k -> age k+1, current -> age 1
 #pragma unroll
     for (int i = 11; i >= 3; --i) r[(RF_ACT_RING + i) * n] = aring[i - 3];
 #pragma unroll
@@ -969,22 +956,12 @@ __global__ void __launch_bounds__(64, 8) head_kernel(const __grid_constant__ DCf
 #pragma unroll
     for (int j = 0; j < 3; ++j) r[(RF_CMD_RING + j) * n] = cmd_in[j];
     r[RF_CV_SUM * n] = cv_sum;
+    r[RF_EP_RET * n] = ep_ret;
     ii[IF_STEPS * n] = steps; ii[IF_STEPS_TGT * n] = steps_tgt; ii[IF_SIM_STEP * n] = sim_step;
     ii[IF_ACT_F32 * n] = act_f32 ? 1 : 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         ii[(IF_GOAL_CNT + k) * n] = gcnt[k]; ii[(IF_GOAL_TOTAL + k) * n] = gtot[k]; ii[(IF_SETTLE + k) * n] = settle[k];
-    }
-
-    // ======================= Dryden filter advance =======================
-    if (TURB && !fail) {
-        T un[4];
-        noise_sample(c, S, env, episode, sim_step, un);
-        turb_step(c, fx, fu, un, sim_step);
-#pragma unroll
-        for (int i = 0; i < 12; ++i) r[(RF_FX + i) * n] = fx[i];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) r[(RF_FU + i) * n] = fu[i];
     }
 }
 
