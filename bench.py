@@ -182,6 +182,10 @@ def run_reference_arm(args):
 
 # ----------------------------------------------------------------------------------------------- GPU arm
 def main():
+    # NCCL prints its version banner (and any NCCL_DEBUG output) to stdout: keep stdout to the one JSON line
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -373,7 +377,7 @@ def main():
                "envs_per_gpu": n_ppo, "n_steps": n_steps, "minibatch": n_ppo * n_steps // 8, "n_epochs": 10,
                "iterations_timed": iters, "ep_rew_mean": algo.logs[-1]["ep_rew_mean"],
                "note": "policy 2x64 tanh MLP in PyTorch, rollout and minibatch update replayed as CUDA graphs; one "
-                       "gradient all-reduce per optimiser step when n_gpus > 1 (eager update then); learning curve of a "
+                       "gradient all-reduce per optimiser step when n_gpus > 1 (NCCL, captured in the update graph); learning curve of a "
                        "240 s run in results/r01_ppo_curve_240s.json"}
         venv.close()
 
@@ -392,7 +396,13 @@ def main():
                 "clocks": clocks, "modes": extra, "ppo": ppo}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # CUDA graphs that contain NCCL kernels (the PPO update) are alive until interpreter shutdown, and
+        # destroy_process_group was seen to wait forever behind them: everything is flushed and synchronised, so leave
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

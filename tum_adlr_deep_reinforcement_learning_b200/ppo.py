@@ -10,6 +10,7 @@ traffic on the env step; per optimiser step ONE all-reduce over the flattened gr
 all-reduce of the VecNormalize moments.  Advantage normalisation is per minibatch and rank-local as in ppo.py:170.
 """
 import math
+import os
 import time
 
 import torch
@@ -105,6 +106,8 @@ class PPO:
         self.policy = ActorCritic().to(self.device)
         torch.manual_seed(seed + 1000 * (self.rank + 1))   # different action noise per rank
         self.use_cuda_graph = bool(use_cuda_graph)
+        # capture the NCCL gradient all-reduce inside the minibatch-update graph (data-parallel runs)
+        self.graph_allreduce = os.environ.get("FWB200_PPO_GRAPH_ALLREDUCE", "1") != "0"
         self.optimizer = torch.optim.Adam(self.policy.parameters(), lr=learning_rate, eps=1e-5,
                                           capturable=self.use_cuda_graph)
         self._rollout_graph = None
@@ -211,7 +214,7 @@ class PPO:
         bs = min(self.batch_size, total)
         flat = [self.buffer.flat(x) for x in (self.buffer.observations, self.buffer.actions, self.buffer.values,
                                               self.buffer.log_probs, self.buffer.advantages, self.buffer.returns)]
-        graph_ok = self.use_cuda_graph and self.world == 1 and total % bs == 0
+        graph_ok = self.use_cuda_graph and (self.world == 1 or self.graph_allreduce) and total % bs == 0
         if graph_ok and self._train_graph is None:
             from .buffers import RolloutBufferSamples
             self._mb = RolloutBufferSamples(*(torch.empty(bs, *f.shape[1:], dtype=f.dtype, device=self.device) for f in flat))
