@@ -272,3 +272,52 @@ def test_moving_target_classes(cuda_device):
         assert _rel(env.obs64.cpu().numpy(), o_ref).max() < RTOL_F64, t
         assert _rel(env.rew64.cpu().numpy(), r_ref).max() < RTOL_F64, t
     env.close()
+
+
+def test_full_size_batch_properties(cuda_device):
+    """BASELINE.json's C3 size (65 536 envs on one GPU, turbulence, auto-reset), checked through properties that do not
+    depend on the size: (1) every env's trajectory is independent of the batch it runs in — a 192-env slice of the big
+    batch equals, bit for bit, a 192-env handle with the same global env ids, which in turn matches the C oracle;
+    (2) the persistent-lane work queue hands envs to lanes in a run-dependent order, yet two runs agree bit for bit;
+    (3) RHS evaluations = 2 + 6 x attempts for every env-step."""
+    import torch
+    from oracle import fw_oracle as O
+    from tum_adlr_deep_reinforcement_learning_b200 import batched as bt
+    from tum_adlr_deep_reinforcement_learning_b200.config import build_config
+    n, T, k0, m = 65536, 45, 40000, 192
+    kw = dict(config_kw={"steps_max": 17}, sim_config_kw={"turbulence": True}, seed=77)
+    g = torch.Generator(device="cuda"); g.manual_seed(3)
+    acts = [(torch.rand(n, 3, device="cuda", generator=g) * 3 - 1.5).contiguous() for _ in range(T)]
+    sums = []
+    for run in range(2):
+        big = bt.BatchedFixedWing(n, cfg=build_config(**kw))
+        big.reset()
+        small = ob = None
+        if run == 0:
+            cfg_s = build_config(env_id_offset=k0, **kw)
+            small = bt.BatchedFixedWing(m, cfg=cfg_s)
+            small.enable_f64_outputs()
+            small.reset()
+            ob = O.OracleBatch(cfg_s, m)
+            ob.reset()
+            assert torch.equal(big.obs[k0:k0 + m], small.obs)
+        acc = torch.zeros((), dtype=torch.float64, device="cuda")
+        ends = 0
+        for t in range(T):
+            big.step(acts[t])
+            acc += big.obs.double().sum() + big.rew.double().sum() * 3.0 + big.done.double().sum() * 7.0
+            nf = big.get_field(bt.FIELD_NFEV)
+            assert bool((nf[:, 0] == 2 + 6 * nf[:, 1]).all())
+            ends += int(big.done.sum())
+            if small is not None:
+                a = acts[t][k0:k0 + m].contiguous()
+                small.step(a)
+                assert torch.equal(big.obs[k0:k0 + m], small.obs) and torch.equal(big.rew[k0:k0 + m], small.rew)
+                assert torch.equal(big.done[k0:k0 + m], small.done), t
+                o_ref, r_ref, d_ref = ob.step(a.cpu().numpy())
+                assert np.array_equal(small.done.cpu().numpy(), d_ref)
+                assert _rel(small.obs64.cpu().numpy(), o_ref).max() < RTOL_F64, t
+        assert ends >= 2 * n                       # every env went through at least two auto-resets
+        sums.append(float(acc))
+        big.close()
+    assert sums[0] == sums[1]
