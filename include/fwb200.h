@@ -11,7 +11,10 @@
  *  - Every `*_dev` pointer is a DEVICE pointer owned by the caller (e.g. a torch CUDA tensor's data_ptr()).
  *    Env state (structure-of-arrays in HBM) is owned by the handle.
  *  - All compute entry points are asynchronous on the `stream` argument (a cudaStream_t passed as void*;
- *    NULL = legacy default stream).  Nothing here synchronises except fw_create / fw_destroy / the host getters.
+ *    NULL = legacy default stream).  Nothing here synchronises except fw_create / fw_destroy / the host getters
+ *    (and a step while fw_set_profiling is on).  The handle owns one more, non-blocking stream on which it
+ *    recomputes precomputed reset rows after an auto-reset step; the next fw_step / fw_reset orders itself
+ *    behind that work through events (fw_join does so explicitly).
  *  - Return value: 0 on success, negative FW_E* on USAGE errors only.  Simulation failures (constraint violations,
  *    pyfly's ConstraintException pyfly.py:11-16) are DATA: they set done=1 and term_code, never an error.
  *  - One handle per GPU; a handle is not thread-safe.  There is no CPU fallback: without a CUDA device

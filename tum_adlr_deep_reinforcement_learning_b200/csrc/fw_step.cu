@@ -1,12 +1,15 @@
-// fw_step.cu — the env-step kernels, the reset kernel and the C ABI of libfwb200.so (see include/fwb200.h).
+// fw_step.cu — the env-step kernels, the reset kernels and the C ABI of libfwb200.so (see include/fwb200.h).
 //
 // One VecEnv.step over every env of the handle = three launches on the caller's stream (exact mode):
 //   rk45_init_kernel     action scaling -> command constraint -> f0 = fun(t0, y0) and scipy's select_initial_step
 //   rk45_attempt_kernel  the RK45 attempt loop; persistent lanes pull envs from a queue, so every lane of every warp
-//                        executes the same RHS row all the time (8 warps/SM: 255 registers + 864 B of stage storage)
+//                        executes the same RHS row all the time (8 warps/SM: 240 registers + 720 B of stage storage)
 //   head_kernel          post-step commit (quaternion renormalisation, Euler angles, Va/alpha/beta, constraint
 //                        checks) -> Dryden filter advance -> goal ring / streak test -> reward -> target law ->
-//                        observation -> termination -> streamed episode metrics -> auto-reset (Philox).
+//                        observation -> termination -> streamed episode metrics -> episode-end rows for the host ->
+//                        auto-reset = warp-cooperative copy of the env's precomputed next-episode row
+// plus one on the handle's high-priority side stream:
+//   refill_kernel        FixedWingAircraft.reset (Philox) for the rows consumed at this step; overlaps the next step
 // The once-per-step head code is large and cold; in its own kernel it runs at high occupancy instead of stalling
 // the register-heavy integrator warps on instruction fetch (profiles/r01_*.txt).  Fixed-step modes use
 // rk4_kernel -> head_kernel.
