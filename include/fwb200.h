@@ -231,9 +231,11 @@ int fw_obs_dim(const FwHandle* h);   /* floats per observation row of this handl
 int fw_set_profiling(FwHandle* h, int32_t on);
 
 /* fw_step with auto_reset recomputes, on a side stream of the handle, the precomputed next-episode rows that the step
- * consumed; the next fw_step / fw_reset waits for that work by itself.  fw_join makes `stream` wait for it explicitly:
- * call it before ending a CUDA stream capture that contains fw_step calls (a capture must not end with unjoined work)
- * or before handing the handle to another thread.  No reference counterpart. */
+ * consumed; the next fw_step / fw_reset waits for that work by itself.  fw_join makes `stream` wait for it explicitly,
+ * e.g. before handing the handle to another thread.  CUDA stream capture: steps launched on a capturing stream join
+ * their side-stream work themselves, so a capture may end after any step; a capture must BEGIN after the work issued
+ * before it has completed (torch.cuda.graph() synchronises the device) or after fw_join + a stream synchronise.
+ * No reference counterpart. */
 int fw_join(FwHandle* h, void* stream);
 
 /* Episode-end rows for a host-facing caller (VecEnv infos: Monitor's {"episode": {r, l}}, the gym env's metrics and

@@ -396,3 +396,54 @@ def test_profiling_api_and_pinned_actions(cuda_device):
         venv.close()
     np.testing.assert_array_equal(outs[0][0], outs[1][0])
     np.testing.assert_array_equal(outs[0][1], outs[1][1])
+
+
+def test_env_steps_inside_a_cuda_graph(cuda_device):
+    """A caller may capture step_tensor calls into a CUDA graph (ppo.PPO does) without knowing about the library's
+    side stream: the capture ends joined, and replays reproduce the eager trajectory bit for bit, auto-resets
+    (precomputed rows consumed and refilled inside the graph) included."""
+    import torch
+    from tum_adlr_deep_reinforcement_learning_b200.vec_env import FixedWingVecEnv
+    n, per_graph, replays = 512, 4, 6
+    kw = dict(config_kw={"steps_max": 5}, sim_config_kw={"turbulence": True}, seed=9)
+    g = torch.Generator(device="cuda"); g.manual_seed(2)
+    acts = [(torch.rand(n, 3, device="cuda", generator=g) * 2 - 1).contiguous() for _ in range(per_graph * (replays + 1))]
+    eager = FixedWingVecEnv(n, **kw)
+    eager.reset_tensor()
+    ref = []
+    for a in acts:
+        o, r, d = eager.step_tensor(a)
+        ref.append((o.clone(), r.clone(), d.clone()))
+    eager.close()
+    env = FixedWingVecEnv(n, **kw)
+    env.reset_tensor()
+    a_static = [torch.zeros(n, 3, device="cuda") for _ in range(per_graph)]
+    outs = [[torch.zeros(n, 14, device="cuda"), torch.zeros(n, device="cuda"), torch.zeros(n, dtype=torch.uint8, device="cuda")]
+            for _ in range(per_graph)]
+
+    def body():
+        for j in range(per_graph):
+            o, r, d = env.step_tensor(a_static[j])
+            outs[j][0].copy_(o); outs[j][1].copy_(r); outs[j][2].copy_(d)
+
+    for j in range(per_graph):
+        a_static[j].copy_(acts[j])
+    body()                                           # eager warm-up: steps 0..3
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    for j in range(per_graph):
+        a_static[j].copy_(acts[per_graph + j])
+    with torch.cuda.graph(graph):                    # capture runs nothing: the env state stays after step 3
+        body()
+    ends = 0
+    for k in range(1, replays + 1):
+        for j in range(per_graph):
+            a_static[j].copy_(acts[k * per_graph + j])
+        graph.replay()
+        torch.cuda.synchronize()
+        for j in range(per_graph):
+            o, r, d = ref[k * per_graph + j]
+            assert torch.equal(outs[j][0], o) and torch.equal(outs[j][1], r) and torch.equal(outs[j][2], d), (k, j)
+            ends += int(d.sum())
+    assert ends >= 4 * n
+    env.close()

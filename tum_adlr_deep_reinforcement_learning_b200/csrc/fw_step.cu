@@ -1244,7 +1244,7 @@ struct FwHandle {
     Spare<float> p32;
     cudaStream_t side;
     cudaEvent_t ev_head, ev_refill;
-    int refill_pending, step_parity;
+    int refill_pending, refill_captured, step_parity;
     double* info_rows; int info_cap;       // fw_set_info_rows
     // fw_set_profiling: CUDA events around each kernel of a step (the step then ends with an event synchronise)
     int prof_on;
@@ -1286,8 +1286,19 @@ template <typename T> static Scratch<T> make_scratch(void* real, int32_t* ints, 
 }
 
 // head_kernel of this step reads the spare rows: the refill of the previous step's consumers must have finished
+static inline bool stream_is_capturing(cudaStream_t st) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    return cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusActive;
+}
 static inline void spare_join(FwHandle* h, cudaStream_t st) {
-    if (h->refill_pending) { cudaStreamWaitEvent(st, h->ev_refill, 0); h->refill_pending = 0; }
+    if (!h->refill_pending) return;
+    h->refill_pending = 0;
+    // A capturing stream cannot wait for an event recorded before the capture began (and a captured event means
+    // nothing outside its graph).  Whoever begins a capture has synchronised with the work before it —
+    // torch.cuda.graph() synchronises the device — or has called fw_join; inside a capture every step joins its own
+    // refill (spare_refill), so nothing captured is ever pending when the capture ends.
+    if (stream_is_capturing(st) != (h->refill_captured != 0)) return;
+    cudaStreamWaitEvent(st, h->ev_refill, 0);
 }
 // after head_kernel: recompute, on the side stream, the rows this step consumed (it overlaps the next step)
 template <typename T>
@@ -1301,6 +1312,10 @@ static void spare_refill(FwHandle* h, const DCfg<T>& c, const Spare<T>& P, cudaS
     cudaEventRecord(h->ev_refill, h->side);
     h->refill_pending = 1;
     h->step_parity ^= 1;
+    // inside a stream capture the side-stream work is joined right away: a capture must not end with unjoined work,
+    // and the caller may end it after any step (the refill then sits between this step and the next in the graph)
+    h->refill_captured = stream_is_capturing(st) ? 1 : 0;
+    if (h->refill_captured) spare_join(h, st);
 }
 
 // One env step = init kernel -> persistent attempt kernel -> head kernel (RK45), or rk4 kernel -> head kernel.
