@@ -320,6 +320,17 @@ int fw_gae(const float* rew_dev, const float* val_dev, const float* done_dev, co
            const uint8_t* last_done_dev, float* adv_dev, float* ret_dev, int32_t T, int32_t N, float gamma,
            float gae_lambda, void* stream);
 
+/* PPO minibatch loss and its gradient with respect to the network outputs, fused (stable_baselines3/ppo/ppo.py:163-218:
+ * advantage normalisation, ratio, clipped surrogate, value MSE, Gaussian entropy; diagonal Gaussian with a
+ * state-independent log_std, common/distributions.py:130-175).  Inputs are the policy mean [B,3], the value head
+ * output [B], log_std [3] and the rollout-buffer minibatch (actions [B,3], old_log_prob, advantages, returns [B]).
+ * Outputs: losses_dev[3] = {loss, policy_loss, value_loss}; grad_mean_dev [B,3], grad_values_dev [B], grad_log_std_dev
+ * [3] = d loss / d input (what autograd would hand to the networks' backward).  scratch_dev: 8 doubles. */
+int fw_ppo_loss(const float* mean_dev, const float* values_dev, const float* log_std_dev, const float* actions_dev,
+                const float* old_log_prob_dev, const float* adv_dev, const float* returns_dev, int32_t batch,
+                float clip_range, float ent_coef, float vf_coef, double* scratch_dev, float* grad_mean_dev,
+                float* grad_values_dev, float* grad_log_std_dev, float* losses_dev, void* stream);
+
 /* Vector-pipe peak micro-benchmarks (dependent-chain-free FMA loops) used as roofline denominators by bench.py:
  * returns achieved TFLOP/s (2 flop per FMA) measured with CUDA events on `device`. */
 int fw_measure_fma_peak(int32_t device, int32_t precision, double* tflops_out);

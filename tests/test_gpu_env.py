@@ -447,3 +447,57 @@ def test_env_steps_inside_a_cuda_graph(cuda_device):
             ends += int(d.sum())
     assert ends >= 4 * n
     env.close()
+
+
+@pytest.mark.parametrize("batch", [1000, 32768])
+def test_fused_ppo_loss_matches_autograd(batch, cuda_device):
+    """fw_ppo_loss against the PyTorch formulation of ppo.py:163-207 (float32, tolerance 2e-5 relative on the loss,
+    1e-5 of the largest entry on every gradient that reaches the parameters), including ratios outside the clip
+    range on both sides and zero advantages."""
+    import torch
+    from tum_adlr_deep_reinforcement_learning_b200.buffers import RolloutBufferSamples
+    from tum_adlr_deep_reinforcement_learning_b200.ppo import ActorCritic, FusedPPOLoss
+    torch.manual_seed(0)
+    dev = "cuda"
+    pol = ActorCritic().to(dev)
+    with torch.no_grad():
+        pol.log_std.copy_(torch.tensor([-0.3, 0.1, -1.2]))
+        pol.action_net.weight.mul_(30.0)              # spread the ratios well outside [0.8, 1.2]
+    obs = torch.randn(batch, 14, device=dev)
+    act = torch.randn(batch, 3, device=dev)
+    old_lp = torch.randn(batch, device=dev) * 0.3 - 3.0
+    adv = torch.randn(batch, device=dev) * 2.0 + 0.5
+    k7 = (batch - 1) // 7
+    adv[0:7 * k7:7] = adv[1:7 * k7:7]                 # ties / repeated values
+    ret = torch.randn(batch, device=dev)
+    clip, ent, vf = 0.2, 0.01, 0.5
+
+    def reference():
+        values, log_prob, entropy = pol.evaluate_actions(obs, act)
+        a = (adv - adv.mean()) / (adv.std() + 1e-8)
+        ratio = torch.exp(log_prob - old_lp)
+        policy_loss = -torch.min(a * ratio, a * torch.clamp(ratio, 1 - clip, 1 + clip)).mean()
+        value_loss = torch.nn.functional.mse_loss(ret, values)
+        return policy_loss + ent * (-entropy.mean()) + vf * value_loss, policy_loss, value_loss, ratio
+
+    def fused():
+        mean = pol.action_net(pol.pi(obs))
+        values = pol.value_net(pol.vf(obs)).squeeze(-1)
+        loss, parts = FusedPPOLoss.apply(mean, values, pol.log_std, act, old_lp, adv, ret, clip, ent, vf)
+        return loss, parts[1], parts[2]
+
+    pol.zero_grad()
+    l_ref, pl_ref, vl_ref, ratio = reference()
+    l_ref.backward()
+    g_ref = [p.grad.clone() for p in pol.parameters()]
+    frac_clipped = float(((ratio < 0.8) | (ratio > 1.2)).float().mean())
+    assert 0.2 < frac_clipped < 0.98
+    pol.zero_grad()
+    l_f, pl_f, vl_f = fused()
+    l_f.backward()
+    g_f = [p.grad.clone() for p in pol.parameters()]
+    for a, b in ((l_f, l_ref), (pl_f, pl_ref), (vl_f, vl_ref)):
+        assert abs(float(a) - float(b)) <= 2e-5 * max(1.0, abs(float(b))), (float(a), float(b))
+    for (name, _), a, b in zip(pol.named_parameters(), g_f, g_ref):
+        scale = float(b.abs().max()) + 1e-12
+        assert float((a - b).abs().max()) <= 1e-5 * scale + 1e-9, (name, float((a - b).abs().max()), scale)

@@ -38,6 +38,7 @@ def lib():
     L.fw_measure_fma_peak.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(ctypes.c_double)]
     L.fw_debug_math.argtypes = [ctypes.c_int32, _vp, _vp, _vp, ctypes.c_int32, _vp]
     L.fw_obs_dim.argtypes = [_vp]
+    L.fw_ppo_loss.argtypes = [_vp] * 7 + [ctypes.c_int32, ctypes.c_float, ctypes.c_float, ctypes.c_float] + [_vp] * 6
     L.fw_join.argtypes = [_vp, _vp]
     L.fw_set_info_rows.argtypes = [_vp, _vp, ctypes.c_int32]
     L.fw_set_profiling.argtypes = [_vp, ctypes.c_int32]
@@ -58,4 +59,4 @@ def check(rc, what):
 
 EXPORTS = ("fw_create", "fw_destroy", "fw_last_error", "fw_abi_version", "fw_reset", "fw_step", "fw_step_random",
            "fw_get_episode_info", "fw_get_field", "fw_set_field", "fw_gae", "fw_measure_fma_peak", "fw_debug_math",
-           "fw_obs_dim", "fw_set_waypoint_tasks", "fw_set_profiling", "fw_get_profile", "fw_join", "fw_set_info_rows")
+           "fw_obs_dim", "fw_set_waypoint_tasks", "fw_set_profiling", "fw_get_profile", "fw_join", "fw_set_info_rows", "fw_ppo_loss")

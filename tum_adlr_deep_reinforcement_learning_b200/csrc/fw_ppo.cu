@@ -1,0 +1,156 @@
+// fw_ppo.cu — the PPO minibatch loss and its gradient with respect to the policy/value network OUTPUTS, fused.
+//
+// The forked SB3 PPO (stable_baselines3/ppo/ppo.py:163-218) builds the clipped surrogate loss out of ~25 elementwise /
+// reduction ops on [B] and [B, 3] tensors, and autograd adds twice as many for the backward pass: at B = 32 768 every
+// one of them is a launch that moves 128-400 KB, i.e. pure launch latency (the update was 88 % of a PPO iteration).
+// Here the whole block between "network outputs" and "gradients of the network outputs" is three small launches:
+//   ppo_adv_stats_kernel   sum and sum of squares of the minibatch advantages (f64 accumulators)
+//   ppo_loss_kernel        per row: Gaussian log-prob, ratio, clipped surrogate, value error; writes dLoss/dmean [B,3]
+//                          and dLoss/dvalue [B]; block-reduces the loss terms and dLoss/dlog_std
+//   ppo_finish_kernel      means, entropy term, the three reported scalars
+// The MLPs themselves (and their backward) stay in PyTorch, as the north star asks; ppo.FusedPPOLoss hands the
+// gradients written here to autograd.  Reference formulas, with ppo.py line numbers:
+//   advantages = (adv - mean) / (std + 1e-8)                      :170   (torch.std: unbiased)
+//   ratio = exp(log_prob - old_log_prob)                          :173
+//   policy_loss = -mean(min(adv * ratio, adv * clamp(ratio, 1 - c, 1 + c)))   :176-178
+//   value_loss = mse(returns, values)                             :196
+//   entropy_loss = -mean(entropy)                                 :203
+//   loss = policy_loss + ent_coef * entropy_loss + vf_coef * value_loss       :207
+// with log_prob / entropy of the diagonal Gaussian (common/distributions.py:130-175, state-independent log_std).
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/fwb200.h"
+
+namespace {
+
+constexpr int ACT = 3;
+constexpr int TPB = 256;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// block sum of K doubles per thread -> atomicAdd into out[0..K)
+template <int K>
+__device__ __forceinline__ void block_accumulate(const double (&v)[K], double* out) {
+    __shared__ double sh[K][TPB / 32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const double s = warp_sum(v[k]);
+        if (lane == 0) sh[k][w] = s;
+    }
+    __syncthreads();
+    if (w == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            double s = lane < TPB / 32 ? sh[k][lane] : 0.0;
+            s = warp_sum(s);
+            if (lane == 0) atomicAdd(out + k, s);
+        }
+    }
+}
+
+// acc[0] = sum adv, acc[1] = sum adv^2
+__global__ void __launch_bounds__(TPB) ppo_adv_stats_kernel(const float* __restrict__ adv, int B, double* acc) {
+    double v[2] = {0.0, 0.0};
+    for (int i = blockIdx.x * TPB + threadIdx.x; i < B; i += gridDim.x * TPB) {
+        const double a = (double)adv[i];
+        v[0] += a;
+        v[1] += a * a;
+    }
+    block_accumulate<2>(v, acc);
+}
+
+// acc[2] = sum min(pl1, pl2), acc[3] = sum (ret - v)^2, acc[4..6] = sum_i g_i * ((a - m)^2 / var - 1) per action dim
+__global__ void __launch_bounds__(TPB) ppo_loss_kernel(const float* __restrict__ mean, const float* __restrict__ values,
+                                                       const float* __restrict__ log_std, const float* __restrict__ actions,
+                                                       const float* __restrict__ old_log_prob, const float* __restrict__ adv,
+                                                       const float* __restrict__ returns, int B, float clip_range,
+                                                       float vf_coef, double* acc, float* __restrict__ grad_mean,
+                                                       float* __restrict__ grad_values) {
+    const double n = (double)B;
+    const double mu = acc[0] / n;
+    // unbiased variance like torch.std(); a one-row batch gives NaN there as well
+    const double var_a = (acc[1] - n * mu * mu) / (n - 1.0);
+    const float a_mean = (float)mu, a_den = (float)sqrt(var_a > 0.0 ? var_a : 0.0) + 1e-8f;
+    float ls[ACT], inv_var[ACT];
+#pragma unroll
+    for (int j = 0; j < ACT; ++j) { ls[j] = log_std[j]; inv_var[j] = expf(-2.f * ls[j]); }
+    const float inv_b = 1.f / (float)B;
+    double v[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int i = blockIdx.x * TPB + threadIdx.x; i < B; i += gridDim.x * TPB) {
+        float d[ACT], lp = 0.f;
+#pragma unroll
+        for (int j = 0; j < ACT; ++j) {
+            d[j] = actions[(size_t)i * ACT + j] - mean[(size_t)i * ACT + j];
+            lp += -(d[j] * d[j]) * (0.5f * inv_var[j]) - ls[j] - 0.91893853320467274178f;      // 0.5 log(2 pi)
+        }
+        const float an = (adv[i] - a_mean) / a_den;
+        const float ratio = expf(lp - old_log_prob[i]);
+        const float lo = 1.f - clip_range, hi = 1.f + clip_range;
+        const float rc = fminf(fmaxf(ratio, lo), hi);
+        const float pl1 = an * ratio, pl2 = an * rc;
+        v[0] += (double)fminf(pl1, pl2);
+        // d min(pl1, pl2) / d ratio as autograd has it: inside the clip range both branches carry the gradient (a tie,
+        // split in halves, both lead to `an`); outside only the unclipped branch has one, and only where it is the min
+        const bool inside = ratio >= lo && ratio <= hi;
+        float g_ratio = 0.f;
+        if (inside) g_ratio = an;
+        else if (pl1 < pl2) g_ratio = an;
+        else if (pl1 == pl2) g_ratio = 0.5f * an;
+        const float g_lp = -inv_b * g_ratio * ratio;              // d policy_loss / d log_prob_i
+#pragma unroll
+        for (int j = 0; j < ACT; ++j) {
+            grad_mean[(size_t)i * ACT + j] = g_lp * d[j] * inv_var[j];
+            v[2 + j] += (double)(g_lp * (d[j] * d[j] * inv_var[j] - 1.f));
+        }
+        const float ve = values[i] - returns[i];
+        v[1] += (double)(ve * ve);
+        grad_values[i] = vf_coef * 2.f * inv_b * ve;
+    }
+    block_accumulate<5>(v, acc + 2);
+}
+
+// out[0] = loss, out[1] = policy_loss, out[2] = value_loss; grad_log_std[j]
+__global__ void ppo_finish_kernel(const double* acc, const float* log_std, int B, float ent_coef, float vf_coef,
+                                  float* out, float* grad_log_std) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const double n = (double)B;
+    const double policy_loss = -acc[2] / n, value_loss = acc[3] / n;
+    double entropy = 0.0;
+    for (int j = 0; j < ACT; ++j) {
+        entropy += 0.5 + 0.91893853320467274178 + (double)log_std[j];
+        grad_log_std[j] = (float)(acc[4 + j] - (double)ent_coef);   // entropy_loss = -entropy: d/d log_std_j = -1
+    }
+    out[0] = (float)(policy_loss - (double)ent_coef * entropy + (double)vf_coef * value_loss);
+    out[1] = (float)policy_loss;
+    out[2] = (float)value_loss;
+}
+
+}  // namespace
+
+extern "C" int fw_ppo_loss(const float* mean_dev, const float* values_dev, const float* log_std_dev,
+                           const float* actions_dev, const float* old_log_prob_dev, const float* adv_dev,
+                           const float* returns_dev, int32_t batch, float clip_range, float ent_coef, float vf_coef,
+                           double* scratch_dev, float* grad_mean_dev, float* grad_values_dev, float* grad_log_std_dev,
+                           float* losses_dev, void* stream) {
+    if (!mean_dev || !values_dev || !log_std_dev || !actions_dev || !old_log_prob_dev || !adv_dev || !returns_dev ||
+        !scratch_dev || !grad_mean_dev || !grad_values_dev || !grad_log_std_dev || !losses_dev || batch <= 0)
+        return FW_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (cudaMemsetAsync(scratch_dev, 0, sizeof(double) * 8, st) != cudaSuccess) return FW_ECUDA;
+    int grid = (batch + TPB - 1) / TPB;
+    if (grid > 592) grid = 592;
+    ppo_adv_stats_kernel<<<grid, TPB, 0, st>>>(adv_dev, batch, scratch_dev);
+    ppo_loss_kernel<<<grid, TPB, 0, st>>>(mean_dev, values_dev, log_std_dev, actions_dev, old_log_prob_dev, adv_dev,
+                                          returns_dev, batch, clip_range, vf_coef, scratch_dev, grad_mean_dev,
+                                          grad_values_dev);
+    ppo_finish_kernel<<<1, 32, 0, st>>>(scratch_dev, log_std_dev, batch, ent_coef, vf_coef, losses_dev, grad_log_std_dev);
+    return cudaGetLastError() == cudaSuccess ? FW_OK : FW_ECUDA;
+}

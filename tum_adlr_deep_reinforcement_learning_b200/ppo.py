@@ -20,6 +20,41 @@ from .buffers import DeviceVecNormalize, RolloutBuffer
 from .vec_env import FixedWingVecEnv
 
 
+class _LinearSplitK(torch.autograd.Function):
+    """y = x W^T + b whose weight gradient is a split-K batched GEMM.  For a [B, 64] activation with B = 32 768 the
+    weight gradient g^T x has a 64 x 64 (or smaller) output and K = B: cuBLAS runs it in ONE thread block (95 us per
+    layer, 60 % of the whole PPO minibatch update, tools/ppo_update_prof.py); cut into S row chunks it is one bmm launch
+    over S blocks plus a tiny sum."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        return torch.addmm(bias, x, weight.t())
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight = ctx.saved_tensors
+        g = g.contiguous()
+        B = x.shape[0]
+        S = 128
+        while S > 1 and B % S:
+            S //= 2
+        gi = g @ weight if ctx.needs_input_grad[0] else None
+        gs = g.view(S, B // S, g.shape[1])
+        gw = torch.bmm(gs.transpose(1, 2), x.view(S, B // S, x.shape[1])).sum(0)
+        gb = gs.sum(1).sum(0)
+        return gi, gw, gb
+
+
+class SplitKLinear(nn.Linear):
+    """nn.Linear (same parameters, same state_dict) with the split-K weight gradient for large training batches."""
+
+    def forward(self, x):
+        if x.is_cuda and x.dim() == 2 and x.shape[0] >= 4096 and torch.is_grad_enabled() and x.is_contiguous():
+            return _LinearSplitK.apply(x, self.weight, self.bias)
+        return nn.functional.linear(x, self.weight, self.bias)
+
+
 class ActorCritic(nn.Module):
     def __init__(self, obs_dim=14, action_dim=3, hidden=(64, 64), log_std_init=0.0):
         super().__init__()
@@ -27,14 +62,14 @@ class ActorCritic(nn.Module):
         def mlp():
             layers, d = [], obs_dim
             for h in hidden:
-                layers += [nn.Linear(d, h), nn.Tanh()]
+                layers += [SplitKLinear(d, h), nn.Tanh()]
                 d = h
             return nn.Sequential(*layers), d
 
         self.pi, d_pi = mlp()
         self.vf, d_vf = mlp()
-        self.action_net = nn.Linear(d_pi, action_dim)
-        self.value_net = nn.Linear(d_vf, 1)
+        self.action_net = SplitKLinear(d_pi, action_dim)
+        self.value_net = SplitKLinear(d_vf, 1)
         self.log_std = nn.Parameter(torch.full((action_dim,), float(log_std_init)))
         # SB3 orthogonal init: sqrt(2) for the extractors, 0.01 for the action head, 1 for the value head
         for m in list(self.pi) + list(self.vf):
@@ -71,6 +106,38 @@ class ActorCritic(nn.Module):
         return self.value_net(self.vf(obs)).squeeze(-1)
 
 
+class FusedPPOLoss(torch.autograd.Function):
+    """loss, policy_loss, value_loss = FusedPPOLoss.apply(mean, values, log_std, actions, old_log_prob, advantages,
+    returns, clip_range, ent_coef, vf_coef): the block of ppo.py:163-207 between the network outputs and the scalar
+    loss, forward and backward, in three launches of fw_ppo_loss (csrc/fw_ppo.cu) instead of ~75 elementwise kernels.
+    The networks stay in PyTorch: autograd receives d loss / d mean, d values, d log_std from the kernel."""
+
+    @staticmethod
+    def forward(ctx, mean, values, log_std, actions, old_log_prob, advantages, returns, clip_range, ent_coef, vf_coef):
+        import ctypes
+        from . import _lib
+        args = [t.detach().contiguous() for t in (mean, values, log_std, actions, old_log_prob, advantages, returns)]
+        assert all(t.is_cuda and t.dtype == torch.float32 for t in args)
+        B = args[0].shape[0]
+        assert args[0].shape == (B, 3) and args[3].shape == (B, 3) and all(t.shape == (B,) for t in (args[1], args[4], args[5], args[6]))
+        dev = args[0].device
+        g_mean, g_val, g_ls = torch.empty_like(args[0]), torch.empty_like(args[1]), torch.empty_like(args[2])
+        losses = torch.empty(3, dtype=torch.float32, device=dev)
+        scratch = torch.empty(8, dtype=torch.float64, device=dev)
+        ptr = lambda t: ctypes.c_void_p(t.data_ptr())
+        _lib.check(_lib.lib().fw_ppo_loss(*[ptr(t) for t in args], B, float(clip_range), float(ent_coef), float(vf_coef),
+                                          ptr(scratch), ptr(g_mean), ptr(g_val), ptr(g_ls), ptr(losses),
+                                          ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "fw_ppo_loss")
+        ctx.save_for_backward(g_mean, g_val, g_ls)
+        ctx.mark_non_differentiable(losses)
+        return losses[0].clone(), losses
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_losses):
+        g_mean, g_val, g_ls = ctx.saved_tensors
+        return g_loss * g_mean, g_loss * g_val, g_loss * g_ls, None, None, None, None, None, None, None
+
+
 def allreduce_gradients(params, dist, world_size):
     """One all-reduce(SUM) over the flattened gradient (~10.5k fp32 = 42 KB: latency bound), then the mean."""
     grads = [p.grad for p in params if p.grad is not None]
@@ -92,7 +159,7 @@ class PPO:
 
     def __init__(self, env: FixedWingVecEnv, n_steps=32, batch_size=32768, n_epochs=10, learning_rate=3e-4, gamma=0.99,
                  gae_lambda=0.95, clip_range=0.2, ent_coef=0.0, vf_coef=0.5, max_grad_norm=0.5, normalize=True,
-                 seed=0, dist=None, use_cuda_graph=True):
+                 seed=0, dist=None, use_cuda_graph=True, fused_loss=True):
         self.env = env
         self.device = env.device
         self.n_envs = env.num_envs
@@ -108,6 +175,7 @@ class PPO:
         self.use_cuda_graph = bool(use_cuda_graph)
         # capture the NCCL gradient all-reduce inside the minibatch-update graph (data-parallel runs)
         self.graph_allreduce = os.environ.get("FWB200_PPO_GRAPH_ALLREDUCE", "1") != "0"
+        self.fused_loss = bool(fused_loss)
         self.optimizer = torch.optim.Adam(self.policy.parameters(), lr=learning_rate, eps=1e-5,
                                           capturable=self.use_cuda_graph)
         self._rollout_graph = None
@@ -189,7 +257,14 @@ class PPO:
             self.norm.sync(self.dist)
 
     # ------------------------------------------------------------------ update (ppo.py:133-240)
-    def _minibatch_update(self, batch):
+    def _loss(self, batch):
+        """ppo.py:163-207.  On the GPU the part after the networks is the fused fw_ppo_loss kernel."""
+        if self.fused_loss and batch.observations.is_cuda:
+            mean = self.policy.action_net(self.policy.pi(batch.observations))
+            values = self.policy.value_net(self.policy.vf(batch.observations)).squeeze(-1)
+            loss, parts = FusedPPOLoss.apply(mean, values, self.policy.log_std, batch.actions, batch.old_log_prob,
+                                             batch.advantages, batch.returns, self.clip_range, self.ent_coef, self.vf_coef)
+            return loss, parts[1], parts[2]
         values, log_prob, entropy = self.policy.evaluate_actions(batch.observations, batch.actions)
         adv = batch.advantages
         adv = (adv - adv.mean()) / (adv.std() + 1e-8)
@@ -200,6 +275,10 @@ class PPO:
         value_loss = torch.nn.functional.mse_loss(batch.returns, values)
         entropy_loss = -entropy.mean()
         loss = policy_loss + self.ent_coef * entropy_loss + self.vf_coef * value_loss
+        return loss, policy_loss, value_loss
+
+    def _minibatch_update(self, batch):
+        loss, policy_loss, value_loss = self._loss(batch)
         self.optimizer.zero_grad(set_to_none=False)
         loss.backward()
         if self.dist is not None and self.world > 1:
