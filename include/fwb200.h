@@ -320,6 +320,35 @@ int fw_gae(const float* rew_dev, const float* val_dev, const float* done_dev, co
            const uint8_t* last_done_dev, float* adv_dev, float* ret_dev, int32_t T, int32_t N, float gamma,
            float gae_lambda, void* stream);
 
+/* One env step of rollout glue on the device: VecNormalize.step_wait + RunningMeanStd.update
+ * (common/vec_env/vec_normalize.py:106-127, common/running_mean_std.py:19-39), RolloutBuffer.add
+ * (common/buffers.py:292-302; the row stores the PREVIOUS observation / done flags, on_policy_algorithm.py:178-180) and
+ * Monitor-style episode totals (common/monitor.py:99-113).  All pointers are device pointers; statistics are float64. */
+typedef struct FwRolloutPost {
+    /* this step */
+    const float* obs_raw;      /* [n, obs_dim] raw observation returned by fw_step                                   */
+    const float* rew_raw;      /* [n]                                                                                */
+    const uint8_t* done;       /* [n]                                                                                */
+    const float* actions;      /* [n, act_dim] the actions that were stepped                                         */
+    const float* values;       /* [n]  value head output for last_obs                                                */
+    const float* log_probs;    /* [n]                                                                                */
+    /* persistent state */
+    float* last_obs;           /* [n, obs_dim] normalised observation the policy saw; replaced by the new one        */
+    float* last_dones;         /* [n] float 0/1; replaced by `done`                                                  */
+    double* ret;               /* [n] discounted return accumulators (VecNormalize.ret)                              */
+    double* obs_mean; double* obs_var; double* obs_count;      /* [obs_dim], [obs_dim], [1]                           */
+    double* ret_mean; double* ret_var; double* ret_count;      /* [1] each                                           */
+    double* run_ret; double* run_len;                          /* [n] running episode return / length                */
+    double* ep_stats;          /* [3] += sum of finished returns, sum of finished lengths, number of finished         */
+    /* rollout buffer row t */
+    float* buf_obs; float* buf_actions; float* buf_rewards; float* buf_dones; float* buf_values; float* buf_log_probs;
+    double* scratch;           /* [2 * obs_dim + 2]                                                                   */
+    int32_t n, obs_dim, act_dim;
+    float gamma, clip_obs, clip_reward, epsilon;
+    int32_t norm_obs, norm_reward, training;
+} FwRolloutPost;
+int fw_rollout_post_step(const FwRolloutPost* p, void* stream);
+
 /* PPO minibatch loss and its gradient with respect to the network outputs, fused (stable_baselines3/ppo/ppo.py:163-218:
  * advantage normalisation, ratio, clipped surrogate, value MSE, Gaussian entropy; diagonal Gaussian with a
  * state-independent log_std, common/distributions.py:130-175).  Inputs are the policy mean [B,3], the value head

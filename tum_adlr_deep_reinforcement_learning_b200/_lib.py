@@ -10,6 +10,17 @@ _lib = None
 _vp = ctypes.c_void_p
 
 
+class FwRolloutPost(ctypes.Structure):
+    """Mirror of FwRolloutPost in include/fwb200.h (field order and types must match)."""
+    _fields_ = ([(k, ctypes.c_void_p) for k in (
+        "obs_raw", "rew_raw", "done", "actions", "values", "log_probs", "last_obs", "last_dones", "ret", "obs_mean",
+        "obs_var", "obs_count", "ret_mean", "ret_var", "ret_count", "run_ret", "run_len", "ep_stats", "buf_obs",
+        "buf_actions", "buf_rewards", "buf_dones", "buf_values", "buf_log_probs", "scratch")] +
+        [("n", ctypes.c_int32), ("obs_dim", ctypes.c_int32), ("act_dim", ctypes.c_int32), ("gamma", ctypes.c_float),
+         ("clip_obs", ctypes.c_float), ("clip_reward", ctypes.c_float), ("epsilon", ctypes.c_float),
+         ("norm_obs", ctypes.c_int32), ("norm_reward", ctypes.c_int32), ("training", ctypes.c_int32)])
+
+
 class FwError(RuntimeError):
     pass
 
@@ -39,6 +50,7 @@ def lib():
     L.fw_debug_math.argtypes = [ctypes.c_int32, _vp, _vp, _vp, ctypes.c_int32, _vp]
     L.fw_obs_dim.argtypes = [_vp]
     L.fw_ppo_loss.argtypes = [_vp] * 7 + [ctypes.c_int32, ctypes.c_float, ctypes.c_float, ctypes.c_float] + [_vp] * 6
+    L.fw_rollout_post_step.argtypes = [ctypes.POINTER(FwRolloutPost), _vp]
     L.fw_join.argtypes = [_vp, _vp]
     L.fw_set_info_rows.argtypes = [_vp, _vp, ctypes.c_int32]
     L.fw_set_profiling.argtypes = [_vp, ctypes.c_int32]
@@ -59,4 +71,4 @@ def check(rc, what):
 
 EXPORTS = ("fw_create", "fw_destroy", "fw_last_error", "fw_abi_version", "fw_reset", "fw_step", "fw_step_random",
            "fw_get_episode_info", "fw_get_field", "fw_set_field", "fw_gae", "fw_measure_fma_peak", "fw_debug_math",
-           "fw_obs_dim", "fw_set_waypoint_tasks", "fw_set_profiling", "fw_get_profile", "fw_join", "fw_set_info_rows", "fw_ppo_loss")
+           "fw_obs_dim", "fw_set_waypoint_tasks", "fw_set_profiling", "fw_get_profile", "fw_join", "fw_set_info_rows", "fw_ppo_loss", "fw_rollout_post_step")

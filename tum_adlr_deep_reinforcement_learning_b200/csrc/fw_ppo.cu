@@ -154,3 +154,136 @@ extern "C" int fw_ppo_loss(const float* mean_dev, const float* values_dev, const
     ppo_finish_kernel<<<1, 32, 0, st>>>(scratch_dev, log_std_dev, batch, ent_coef, vf_coef, losses_dev, grad_log_std_dev);
     return cudaGetLastError() == cudaSuccess ? FW_OK : FW_ECUDA;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Rollout glue of one env step: VecNormalize.step_wait + RunningMeanStd.update (vec_normalize.py:106-127,
+// running_mean_std.py:19-39), RolloutBuffer.add (buffers.py:292-302) and the Monitor-style episode bookkeeping
+// (monitor.py:99-113), which as device-tensor ops were ~70 launches per step (launch latency: 3x the simulator's
+// own time at 8192 envs).  Three launches:
+//   rollout_stats_kernel    ret = ret * gamma + r; batch sums of obs, obs^2, ret, ret^2; episode trackers
+//   rollout_moments_kernel  Chan's parallel update of the running mean / var / count (one block)
+//   rollout_apply_kernel    normalise obs and reward with the UPDATED moments, write rollout-buffer row t
+//                           (previous obs / dones, this step's action, value, log-prob, reward), roll last_obs /
+//                           last_dones forward, zero the finished envs' return accumulators
+// All statistics are float64 like the reference; the batch variance is E[x^2] - mean^2 from f64 sums.
+namespace {
+
+// scratch layout: [0, D) sum obs_j, [D, 2D) sum obs_j^2, 2D sum ret, 2D+1 sum ret^2
+__global__ void __launch_bounds__(TPB) rollout_stats_kernel(const FwRolloutPost p) {
+    extern __shared__ double sh[];                       // 2 D + 5 partial sums of the block
+    const int D = p.obs_dim, NS = 2 * D + 5;
+    for (int k = threadIdx.x; k < NS; k += TPB) sh[k] = 0.0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    // every warp walks whole groups of 32 envs so that the shuffles below are full-warp
+    for (int base = (blockIdx.x * TPB + threadIdx.x - lane); base < p.n; base += gridDim.x * TPB) {
+        const int i = base + lane;
+        const bool on = i < p.n;
+        double r_new = 0.0, e_ret = 0.0, e_len = 0.0, e_cnt = 0.0;
+        if (on) {
+            const double rw = (double)p.rew_raw[i];
+            r_new = p.ret[i] * (double)p.gamma + rw;
+            p.ret[i] = r_new;
+            const double rr = p.run_ret[i] + rw, rl = p.run_len[i] + 1.0;
+            const bool d = p.done[i] != 0;
+            if (d) { e_ret = rr; e_len = rl; e_cnt = 1.0; }
+            p.run_ret[i] = d ? 0.0 : rr;
+            p.run_len[i] = d ? 0.0 : rl;
+        }
+        double s;
+        s = warp_sum(r_new); if (lane == 0) atomicAdd(sh + 2 * D, s);
+        s = warp_sum(r_new * r_new); if (lane == 0) atomicAdd(sh + 2 * D + 1, s);
+        s = warp_sum(e_ret); if (lane == 0 && s != 0.0) atomicAdd(sh + 2 * D + 2, s);
+        s = warp_sum(e_len); if (lane == 0 && s != 0.0) atomicAdd(sh + 2 * D + 3, s);
+        s = warp_sum(e_cnt); if (lane == 0 && s != 0.0) atomicAdd(sh + 2 * D + 4, s);
+        if (p.training) {
+            for (int j = 0; j < D; ++j) {
+                const double x = on ? (double)p.obs_raw[(size_t)i * D + j] : 0.0;
+                s = warp_sum(x); if (lane == 0) atomicAdd(sh + j, s);
+                s = warp_sum(x * x); if (lane == 0) atomicAdd(sh + D + j, s);
+            }
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < NS; k += TPB) {
+        if (k < 2 * D + 2) atomicAdd(p.scratch + k, sh[k]);
+        else if (sh[k] != 0.0) atomicAdd(p.ep_stats + (k - 2 * D - 2), sh[k]);
+    }
+}
+
+__device__ __forceinline__ void chan_update(double* mean, double* var, double count, double bsum, double bsumsq, double nb) {
+    const double bm = bsum / nb;
+    double bv = bsumsq / nb - bm * bm;
+    if (bv < 0.0) bv = 0.0;
+    const double delta = bm - *mean, tot = count + nb;
+    const double m2 = *var * count + bv * nb + delta * delta * count * nb / tot;
+    *mean = *mean + delta * nb / tot;
+    *var = m2 / tot;
+}
+
+__global__ void rollout_moments_kernel(const FwRolloutPost p) {
+    const int D = p.obs_dim;
+    const double nb = (double)p.n;
+    if (!p.training) return;
+    const int j = threadIdx.x;
+    const double oc = *p.obs_count, rc = *p.ret_count;
+    if (j < D) chan_update(p.obs_mean + j, p.obs_var + j, oc, p.scratch[j], p.scratch[D + j], nb);
+    if (j == 0) chan_update(p.ret_mean, p.ret_var, rc, p.scratch[2 * D], p.scratch[2 * D + 1], nb);
+    __syncthreads();
+    if (j == 0) {
+        *p.obs_count = oc + nb;
+        *p.ret_count = rc + nb;
+    }
+}
+
+__global__ void __launch_bounds__(TPB) rollout_apply_kernel(const FwRolloutPost p) {
+    const int i = blockIdx.x * TPB + threadIdx.x;
+    if (i >= p.n) return;
+    const int D = p.obs_dim, A = p.act_dim;
+    for (int j = 0; j < D; ++j) {
+        const size_t o = (size_t)i * D + j;
+        p.buf_obs[o] = p.last_obs[o];
+        const float raw = p.obs_raw[o];
+        float v = raw;
+        if (p.norm_obs) {
+            double x = ((double)raw - p.obs_mean[j]) / sqrt(p.obs_var[j] + (double)p.epsilon);
+            x = fmin(fmax(x, -(double)p.clip_obs), (double)p.clip_obs);
+            v = (float)x;
+        }
+        p.last_obs[o] = v;
+    }
+    for (int j = 0; j < A; ++j) p.buf_actions[(size_t)i * A + j] = p.actions[(size_t)i * A + j];
+    float rw = p.rew_raw[i];
+    if (p.norm_reward) {
+        double x = (double)rw / sqrt(*p.ret_var + (double)p.epsilon);
+        x = fmin(fmax(x, -(double)p.clip_reward), (double)p.clip_reward);
+        rw = (float)x;
+    }
+    p.buf_rewards[i] = rw;
+    p.buf_dones[i] = p.last_dones[i];
+    p.buf_values[i] = p.values[i];
+    p.buf_log_probs[i] = p.log_probs[i];
+    const bool d = p.done[i] != 0;
+    p.last_dones[i] = d ? 1.f : 0.f;
+    if (d) p.ret[i] = 0.0;
+}
+
+}  // namespace
+
+extern "C" int fw_rollout_post_step(const FwRolloutPost* p, void* stream) {
+    if (!p || p->n <= 0 || p->obs_dim <= 0 || p->obs_dim > 256 || p->act_dim <= 0 || !p->obs_raw || !p->rew_raw ||
+        !p->done || !p->actions || !p->values || !p->log_probs || !p->last_obs || !p->last_dones || !p->ret ||
+        !p->obs_mean || !p->obs_var || !p->obs_count || !p->ret_mean || !p->ret_var || !p->ret_count || !p->run_ret ||
+        !p->run_len || !p->ep_stats || !p->buf_obs || !p->buf_actions || !p->buf_rewards || !p->buf_dones ||
+        !p->buf_values || !p->buf_log_probs || !p->scratch)
+        return FW_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int D = p->obs_dim;
+    if (cudaMemsetAsync(p->scratch, 0, sizeof(double) * (2 * D + 2), st) != cudaSuccess) return FW_ECUDA;
+    int grid = (p->n + TPB - 1) / TPB;
+    if (grid > 296) grid = 296;
+    rollout_stats_kernel<<<grid, TPB, sizeof(double) * (2 * D + 5), st>>>(*p);
+    rollout_moments_kernel<<<1, 256, 0, st>>>(*p);
+    rollout_apply_kernel<<<(p->n + TPB - 1) / TPB, TPB, 0, st>>>(*p);
+    return cudaGetLastError() == cudaSuccess ? FW_OK : FW_ECUDA;
+}

@@ -159,7 +159,7 @@ class PPO:
 
     def __init__(self, env: FixedWingVecEnv, n_steps=32, batch_size=32768, n_epochs=10, learning_rate=3e-4, gamma=0.99,
                  gae_lambda=0.95, clip_range=0.2, ent_coef=0.0, vf_coef=0.5, max_grad_norm=0.5, normalize=True,
-                 seed=0, dist=None, use_cuda_graph=True, fused_loss=True):
+                 seed=0, dist=None, use_cuda_graph=True, fused_loss=True, fused_rollout=True):
         self.env = env
         self.device = env.device
         self.n_envs = env.num_envs
@@ -176,6 +176,7 @@ class PPO:
         # capture the NCCL gradient all-reduce inside the minibatch-update graph (data-parallel runs)
         self.graph_allreduce = os.environ.get("FWB200_PPO_GRAPH_ALLREDUCE", "1") != "0"
         self.fused_loss = bool(fused_loss)
+        self.fused_rollout = bool(fused_rollout)
         self.optimizer = torch.optim.Adam(self.policy.parameters(), lr=learning_rate, eps=1e-5,
                                           capturable=self.use_cuda_graph)
         self._rollout_graph = None
@@ -188,9 +189,9 @@ class PPO:
         self._last_obs = None
         self._last_dones = None
         # on-device episode statistics (Monitor-equivalent, no per-env python objects)
-        self.ep_ret_sum = torch.zeros((), dtype=torch.float64, device=self.device)
-        self.ep_len_sum = torch.zeros((), dtype=torch.float64, device=self.device)
-        self.ep_count = torch.zeros((), dtype=torch.float64, device=self.device)
+        self._ep_stats = torch.zeros(3, dtype=torch.float64, device=self.device)     # one buffer: fw_rollout_post_step
+        self.ep_ret_sum, self.ep_len_sum, self.ep_count = self._ep_stats[0], self._ep_stats[1], self._ep_stats[2]
+        self._post_scratch = torch.zeros(2 * 256 + 2, dtype=torch.float64, device=self.device)
         self._run_ret = torch.zeros(self.n_envs, dtype=torch.float64, device=self.device)
         self._run_len = torch.zeros(self.n_envs, dtype=torch.float64, device=self.device)
         self.logs = []
@@ -205,6 +206,8 @@ class PPO:
         with torch.no_grad():
             actions, values, log_probs = self.policy(self._last_obs)
         obs_raw, rew_raw, done = self.env.step_tensor(actions.contiguous())
+        if self.fused_rollout and obs_raw.is_cuda:
+            return self._fused_post_step(t, obs_raw, rew_raw, done, actions, values, log_probs)
         d = done.bool()
         self._run_ret.add_(rew_raw.to(torch.float64))
         self._run_len.add_(1.0)
@@ -218,6 +221,33 @@ class PPO:
         # static buffers (in-place) so that the whole rollout can be replayed as one CUDA graph
         self._last_obs.copy_(obs)
         self._last_dones.copy_(done)
+
+    def _fused_post_step(self, t, obs_raw, rew_raw, done, actions, values, log_probs):
+        """VecNormalize.step + RolloutBuffer.add + episode bookkeeping of one step in three launches
+        (fw_rollout_post_step, csrc/fw_ppo.cu) instead of ~70 tensor ops; same arithmetic (float64 statistics)."""
+        import ctypes
+        from . import _lib
+        nm, buf = self.norm, self.buffer
+        assert buf.pos == t
+        tens = dict(obs_raw=obs_raw, rew_raw=rew_raw, done=done, actions=actions.contiguous(),
+                    values=values.reshape(-1).contiguous(), log_probs=log_probs.reshape(-1).contiguous(),
+                    last_obs=self._last_obs, last_dones=self._last_dones, ret=nm.ret, obs_mean=nm.obs_rms.mean,
+                    obs_var=nm.obs_rms.var, obs_count=nm.obs_rms.count, ret_mean=nm.ret_rms.mean, ret_var=nm.ret_rms.var,
+                    ret_count=nm.ret_rms.count, run_ret=self._run_ret, run_len=self._run_len, ep_stats=self._ep_stats,
+                    buf_obs=buf.observations[t], buf_actions=buf.actions[t], buf_rewards=buf.rewards[t],
+                    buf_dones=buf.dones[t], buf_values=buf.values[t], buf_log_probs=buf.log_probs[t],
+                    scratch=self._post_scratch)
+        assert all(v.is_contiguous() for v in tens.values())
+        self._post_keep = tens                     # the launches are asynchronous: keep the temporaries alive
+        p = _lib.FwRolloutPost(**{k: v.data_ptr() for k, v in tens.items()}, n=self.n_envs, obs_dim=obs_raw.shape[1],
+                               act_dim=actions.shape[1], gamma=nm.gamma, clip_obs=nm.clip_obs, clip_reward=nm.clip_reward,
+                               epsilon=nm.epsilon, norm_obs=int(nm.norm_obs), norm_reward=int(nm.norm_reward),
+                               training=int(nm.training))
+        _lib.check(_lib.lib().fw_rollout_post_step(ctypes.byref(p), ctypes.c_void_p(
+            torch.cuda.current_stream(self.device).cuda_stream)), "fw_rollout_post_step")
+        buf.pos += 1
+        if buf.pos == buf.buffer_size:
+            buf.full = True
 
     def _rollout_body(self):
         self.buffer.reset()
