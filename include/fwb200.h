@@ -320,6 +320,13 @@ int fw_gae(const float* rew_dev, const float* val_dev, const float* done_dev, co
            const uint8_t* last_done_dev, float* adv_dev, float* ret_dev, int32_t T, int32_t N, float gamma,
            float gae_lambda, void* stream);
 
+/* clip_grad_norm_(max_norm, L2) followed by one Adam step (torch.optim.Adam: no weight decay, no amsgrad) over a flat
+ * float32 parameter vector and its flat gradient (stable_baselines3/ppo/ppo.py:212-214).  step_dev: device float,
+ * incremented by the call.  max_norm <= 0 disables clipping.  One launch, one block: meant for small policies. */
+int fw_adam_clip_step(float* param_dev, const float* grad_dev, float* exp_avg_dev, float* exp_avg_sq_dev,
+                      float* step_dev, int32_t n, float lr, float beta1, float beta2, float eps, float max_norm,
+                      void* stream);
+
 /* One env step of rollout glue on the device: VecNormalize.step_wait + RunningMeanStd.update
  * (common/vec_env/vec_normalize.py:106-127, common/running_mean_std.py:19-39), RolloutBuffer.add
  * (common/buffers.py:292-302; the row stores the PREVIOUS observation / done flags, on_policy_algorithm.py:178-180) and

@@ -532,3 +532,36 @@ def test_fused_rollout_glue_matches_tensor_ops(cuda_device):
     for name, a, b in zip(names, *res):
         scale = float(a.abs().max()) + 1e-12
         assert float((a - b).abs().max()) <= 2e-6 * scale + 1e-7, (name, float((a - b).abs().max()), scale)
+
+
+def test_flat_adam_matches_torch_adam_with_clipping(cuda_device):
+    """fw_adam_clip_step against clip_grad_norm_ + torch.optim.Adam(eps=1e-5) on the PPO policy: 6 optimiser steps
+    with gradients on both sides of the clipping threshold; parameters agree to float32 rounding."""
+    import copy
+    import torch
+    from tum_adlr_deep_reinforcement_learning_b200.ppo import ActorCritic, FlatAdam
+    torch.manual_seed(1)
+    ref = ActorCritic().cuda()
+    mine = copy.deepcopy(ref)
+    opt_ref = torch.optim.Adam(ref.parameters(), lr=3e-4, eps=1e-5)
+    opt = FlatAdam(mine, lr=3e-4, eps=1e-5, max_grad_norm=0.5)
+    obs = torch.randn(4096, 14, device="cuda")
+    act = torch.randn(4096, 3, device="cuda")
+    for it in range(6):
+        scale = 100.0 if it % 2 == 0 else 1e-3            # clipped / not clipped
+        for model, o in ((ref, opt_ref), (mine, opt)):
+            o.zero_grad(set_to_none=False)
+            values, log_prob, entropy = model.evaluate_actions(obs, act)
+            loss = scale * (log_prob.mean() + (values ** 2).mean())
+            loss.backward()
+            if o is opt_ref:
+                norm = torch.nn.utils.clip_grad_norm_(list(ref.parameters()), 0.5)
+                assert (float(norm) > 0.5) == (it % 2 == 0)
+            o.step()
+        for (name, a), b in zip(ref.named_parameters(), mine.parameters()):
+            a, b = a.detach(), b.detach()
+            assert float((a - b).abs().max()) <= 2e-6 * (float(a.abs().max()) + 1e-3), (it, name)
+    sd = opt.state_dict()
+    opt2 = FlatAdam(copy.deepcopy(mine), lr=1.0)
+    opt2.load_state_dict(sd)
+    assert float(opt2.step_count) == 6.0 and opt2.lr == 3e-4 and torch.equal(opt2.exp_avg, opt.exp_avg)

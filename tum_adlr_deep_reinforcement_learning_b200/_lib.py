@@ -51,6 +51,7 @@ def lib():
     L.fw_obs_dim.argtypes = [_vp]
     L.fw_ppo_loss.argtypes = [_vp] * 7 + [ctypes.c_int32, ctypes.c_float, ctypes.c_float, ctypes.c_float] + [_vp] * 6
     L.fw_rollout_post_step.argtypes = [ctypes.POINTER(FwRolloutPost), _vp]
+    L.fw_adam_clip_step.argtypes = [_vp] * 5 + [ctypes.c_int32] + [ctypes.c_float] * 5 + [_vp]
     L.fw_join.argtypes = [_vp, _vp]
     L.fw_set_info_rows.argtypes = [_vp, _vp, ctypes.c_int32]
     L.fw_set_profiling.argtypes = [_vp, ctypes.c_int32]
@@ -71,4 +72,4 @@ def check(rc, what):
 
 EXPORTS = ("fw_create", "fw_destroy", "fw_last_error", "fw_abi_version", "fw_reset", "fw_step", "fw_step_random",
            "fw_get_episode_info", "fw_get_field", "fw_set_field", "fw_gae", "fw_measure_fma_peak", "fw_debug_math",
-           "fw_obs_dim", "fw_set_waypoint_tasks", "fw_set_profiling", "fw_get_profile", "fw_join", "fw_set_info_rows", "fw_ppo_loss", "fw_rollout_post_step")
+           "fw_obs_dim", "fw_set_waypoint_tasks", "fw_set_profiling", "fw_get_profile", "fw_join", "fw_set_info_rows", "fw_ppo_loss", "fw_rollout_post_step", "fw_adam_clip_step")

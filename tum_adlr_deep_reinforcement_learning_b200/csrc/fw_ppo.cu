@@ -287,3 +287,59 @@ extern "C" int fw_rollout_post_step(const FwRolloutPost* p, void* stream) {
     rollout_apply_kernel<<<(p->n + TPB - 1) / TPB, TPB, 0, st>>>(*p);
     return cudaGetLastError() == cudaSuccess ? FW_OK : FW_ECUDA;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// clip_grad_norm_(max_norm) + Adam.step() over ONE flat parameter vector (ppo.py:212-214; torch.optim.Adam defaults
+// as SB3 sets them: betas (0.9, 0.999), eps 1e-5, no weight decay).  The policy has ~10.5 k parameters in 13 tensors:
+// as foreach ops that was ~25 launches per optimiser step; here one block does both (norm in f64, update in f32).
+// `step_dev` is the device-resident step counter (capturable in a CUDA graph).
+namespace {
+
+__global__ void __launch_bounds__(1024) adam_clip_kernel(float* __restrict__ param, const float* __restrict__ grad,
+                                                         float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq,
+                                                         float* step_dev, int n, float lr, float beta1, float beta2,
+                                                         float eps, float max_norm) {
+    __shared__ double sh[32];
+    __shared__ float s_coef, s_bc1, s_bc2;
+    double ss = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { const double g = (double)grad[i]; ss += g * g; }
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double v = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) {
+            // clip_grad_norm_: coef = max_norm / (total_norm + 1e-6), clamped to 1
+            const float total = (float)sqrt(v);
+            float coef = max_norm > 0.f ? max_norm / (total + 1e-6f) : 1.f;
+            s_coef = coef < 1.f ? coef : 1.f;
+            const float step = *step_dev + 1.f;
+            *step_dev = step;
+            s_bc1 = 1.f - powf(beta1, step);
+            s_bc2 = 1.f - powf(beta2, step);
+        }
+    }
+    __syncthreads();
+    const float coef = s_coef, step_size = lr / s_bc1, inv_sqrt_bc2 = rsqrtf(s_bc2);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float g = grad[i] * coef;
+        const float m = beta1 * exp_avg[i] + (1.f - beta1) * g;
+        const float v = beta2 * exp_avg_sq[i] + (1.f - beta2) * g * g;
+        exp_avg[i] = m;
+        exp_avg_sq[i] = v;
+        const float denom = sqrtf(v) * inv_sqrt_bc2 + eps;
+        param[i] -= step_size * (m / denom);
+    }
+}
+
+}  // namespace
+
+extern "C" int fw_adam_clip_step(float* param_dev, const float* grad_dev, float* exp_avg_dev, float* exp_avg_sq_dev,
+                                 float* step_dev, int32_t n, float lr, float beta1, float beta2, float eps,
+                                 float max_norm, void* stream) {
+    if (!param_dev || !grad_dev || !exp_avg_dev || !exp_avg_sq_dev || !step_dev || n <= 0) return FW_EINVAL;
+    adam_clip_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(param_dev, grad_dev, exp_avg_dev, exp_avg_sq_dev, step_dev, n,
+                                                           lr, beta1, beta2, eps, max_norm);
+    return cudaGetLastError() == cudaSuccess ? FW_OK : FW_ECUDA;
+}

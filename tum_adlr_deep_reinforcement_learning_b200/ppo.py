@@ -138,6 +138,51 @@ class FusedPPOLoss(torch.autograd.Function):
         return g_loss * g_mean, g_loss * g_val, g_loss * g_ls, None, None, None, None, None, None, None
 
 
+class FlatAdam:
+    """Adam + gradient-norm clipping over ONE flat buffer (fw_adam_clip_step, csrc/fw_ppo.cu).  The module's parameters
+    and their .grad become views of `flat` / `grad`, so zero_grad is one memset, the data-parallel all-reduce needs no
+    gather/scatter, and clip + step is one launch instead of ~25 foreach kernels.  Same update rule as
+    torch.optim.Adam(lr, betas=(0.9, 0.999), eps, weight_decay=0) after clip_grad_norm_(max_grad_norm)."""
+
+    def __init__(self, module, lr, eps=1e-5, betas=(0.9, 0.999), max_grad_norm=0.5):
+        self.params = [p for p in module.parameters()]
+        dev = self.params[0].device
+        assert dev.type == "cuda" and all(p.dtype == torch.float32 for p in self.params)
+        self.flat = torch.cat([p.data.reshape(-1) for p in self.params]).contiguous()
+        self.grad = torch.zeros_like(self.flat)
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            p.data = self.flat[off:off + n].view_as(p)
+            p.grad = self.grad[off:off + n].view_as(p)
+            off += n
+        self.exp_avg = torch.zeros_like(self.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat)
+        self.step_count = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.lr, self.eps, self.betas, self.max_grad_norm = float(lr), float(eps), betas, float(max_grad_norm)
+
+    def zero_grad(self, set_to_none=False):
+        self.grad.zero_()
+
+    def step(self):
+        import ctypes
+        from . import _lib
+        ptr = lambda t: ctypes.c_void_p(t.data_ptr())
+        _lib.check(_lib.lib().fw_adam_clip_step(ptr(self.flat), ptr(self.grad), ptr(self.exp_avg), ptr(self.exp_avg_sq),
+                                                ptr(self.step_count), self.flat.numel(), self.lr, self.betas[0],
+                                                self.betas[1], self.eps, self.max_grad_norm, ctypes.c_void_p(
+                                                    torch.cuda.current_stream(self.flat.device).cuda_stream)),
+                   "fw_adam_clip_step")
+
+    def state_dict(self):
+        return {"flat_adam": True, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq, "step": self.step_count,
+                "lr": self.lr, "eps": self.eps, "betas": self.betas, "max_grad_norm": self.max_grad_norm}
+
+    def load_state_dict(self, sd):
+        self.exp_avg.copy_(sd["exp_avg"]); self.exp_avg_sq.copy_(sd["exp_avg_sq"]); self.step_count.copy_(sd["step"])
+        self.lr, self.eps, self.betas = float(sd["lr"]), float(sd["eps"]), tuple(sd["betas"])
+
+
 def allreduce_gradients(params, dist, world_size):
     """One all-reduce(SUM) over the flattened gradient (~10.5k fp32 = 42 KB: latency bound), then the mean."""
     grads = [p.grad for p in params if p.grad is not None]
@@ -159,7 +204,8 @@ class PPO:
 
     def __init__(self, env: FixedWingVecEnv, n_steps=32, batch_size=32768, n_epochs=10, learning_rate=3e-4, gamma=0.99,
                  gae_lambda=0.95, clip_range=0.2, ent_coef=0.0, vf_coef=0.5, max_grad_norm=0.5, normalize=True,
-                 seed=0, dist=None, use_cuda_graph=True, fused_loss=True, fused_rollout=True):
+                 seed=0, dist=None, use_cuda_graph=True, fused_loss=True, fused_rollout=True,
+                 flat_optimizer=True):
         self.env = env
         self.device = env.device
         self.n_envs = env.num_envs
@@ -177,8 +223,12 @@ class PPO:
         self.graph_allreduce = os.environ.get("FWB200_PPO_GRAPH_ALLREDUCE", "1") != "0"
         self.fused_loss = bool(fused_loss)
         self.fused_rollout = bool(fused_rollout)
-        self.optimizer = torch.optim.Adam(self.policy.parameters(), lr=learning_rate, eps=1e-5,
-                                          capturable=self.use_cuda_graph)
+        self.flat_optimizer = bool(flat_optimizer) and self.device.type == "cuda"
+        if self.flat_optimizer:
+            self.optimizer = FlatAdam(self.policy, lr=learning_rate, eps=1e-5, max_grad_norm=max_grad_norm)
+        else:
+            self.optimizer = torch.optim.Adam(self.policy.parameters(), lr=learning_rate, eps=1e-5,
+                                              capturable=self.use_cuda_graph)
         self._rollout_graph = None
         self._train_graph = None
         self._eager_rollouts = 0
@@ -311,6 +361,12 @@ class PPO:
         loss, policy_loss, value_loss = self._loss(batch)
         self.optimizer.zero_grad(set_to_none=False)
         loss.backward()
+        if self.flat_optimizer:
+            if self.dist is not None and self.world > 1:       # the gradient already is one flat buffer
+                self.dist.all_reduce(self.optimizer.grad)
+                self.optimizer.grad.div_(self.world)
+            self.optimizer.step()                              # clip_grad_norm_ + Adam in one launch
+            return policy_loss.detach(), value_loss.detach()
         if self.dist is not None and self.world > 1:
             allreduce_gradients(self._params, self.dist, self.world)
         torch.nn.utils.clip_grad_norm_(self._params, self.max_grad_norm)
