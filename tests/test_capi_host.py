@@ -28,6 +28,11 @@ def test_config_struct_layout_matches_both_libraries():
     assert _lib.lib().fw_config_size() == ctypes.sizeof(C.FwConfig) == O.lib().fwo_config_size()
 
 
+def test_rollout_post_struct_layout():
+    """ctypes mirror of FwRolloutPost (25 device pointers, 3 ints, 4 floats, 3 ints) against the compiled struct."""
+    assert _lib.lib().fw_rollout_post_size() == ctypes.sizeof(_lib.FwRolloutPost) == 25 * 8 + 10 * 4
+
+
 def test_default_config_numbers():
     c = C.build_config()
     assert c.steps_max == 2000 and c.dt == 0.01 and c.turbulence == 1

@@ -61,6 +61,9 @@ def lib():
     L.fw_abi_version.restype = ctypes.c_int
     if L.fw_config_size() != ctypes.sizeof(FwConfig):
         raise FwError("FwConfig layout mismatch between config.py and include/fwb200.h")
+    L.fw_rollout_post_size.restype = ctypes.c_int
+    if L.fw_rollout_post_size() != ctypes.sizeof(FwRolloutPost):
+        raise FwError("FwRolloutPost layout mismatch between _lib.py and include/fwb200.h")
     _lib = L
     return L
 

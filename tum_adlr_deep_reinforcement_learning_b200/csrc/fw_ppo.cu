@@ -270,6 +270,8 @@ __global__ void __launch_bounds__(TPB) rollout_apply_kernel(const FwRolloutPost 
 
 }  // namespace
 
+extern "C" int fw_rollout_post_size(void) { return (int)sizeof(FwRolloutPost); }
+
 extern "C" int fw_rollout_post_step(const FwRolloutPost* p, void* stream) {
     if (!p || p->n <= 0 || p->obs_dim <= 0 || p->obs_dim > 256 || p->act_dim <= 0 || !p->obs_raw || !p->rew_raw ||
         !p->done || !p->actions || !p->values || !p->log_probs || !p->last_obs || !p->last_dones || !p->ret ||
