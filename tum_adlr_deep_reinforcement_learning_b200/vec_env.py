@@ -57,6 +57,25 @@ class _SimulatorView:
 _EMPTY_INFO = {}
 
 
+def _make_done_info():
+    """Compiles the episode-end info builder from METRIC_LAYOUT as ONE dict display (several times faster than a loop
+    of dict(zip(...)) — at ten finished episodes per step the loop cost more than a kernel).  row: 28 metrics |
+    return | length | termination code, as python floats."""
+    parts = ['"termination": TERM_NAMES.get(int(row[30]), int(row[30]))']
+    for name, off, keys in METRIC_LAYOUT:
+        conv = "bool(row[%d])" if name == "success" else "row[%d]"
+        parts.append('"%s": {%s}' % (name, ", ".join('"%s": %s' % (k, conv % (off + q)) for q, k in enumerate(keys))))
+    parts.append('"terminal_observation": term_obs')
+    parts.append('"episode": {"r": row[28], "l": int(row[29]), "t": now}')
+    src = "def _done_info(row, term_obs, now):\n    return {%s}\n" % ", ".join(parts)
+    ns = {"TERM_NAMES": TERM_NAMES}
+    exec(src, ns)
+    return ns["_done_info"]
+
+
+_done_info = _make_done_info()
+
+
 class FixedWingVecEnv:
     """n_envs reference-semantics fixed-wing envs on one GPU behind the VecEnv API.
 
@@ -303,16 +322,11 @@ class FixedWingVecEnv:
         term_obs_all = rows[:, 31:].astype(np.float32)
         generic = bool(self.cfg.obs_generic)
         for j, (row, i) in enumerate(zip(rows[:, :31].tolist(), done_idx.tolist())):
-            info = dict(infos[i])
-            term = int(row[30])
-            info["termination"] = TERM_NAMES.get(term, term)
-            for name, off, keys in METRIC_LAYOUT:
-                vals = row[off:off + len(keys)]
-                info[name] = dict(zip(keys, map(bool, vals))) if name == "success" else dict(zip(keys, vals))
             term_obs = term_obs_all[j]
-            info["terminal_observation"] = term_obs
-            info["episode"] = {"r": row[28], "l": int(row[29]), "t": now}
-            if not generic and "target" not in info:
+            info = _done_info(row, term_obs, now)
+            if compat:
+                info.update(infos[i])                 # keeps the per-step "target" entry of compat mode
+            elif not generic:
                 # fixed_wing.py:626 reports the finished episode's target; it sits in terminal_observation[6:9]
                 info["target"] = dict(zip(TARGET_STATES, term_obs[6:9].tolist()))
             infos[i] = info
