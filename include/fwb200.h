@@ -349,7 +349,7 @@ typedef struct FwRolloutPost {
     double* ep_stats;          /* [3] += sum of finished returns, sum of finished lengths, number of finished         */
     /* rollout buffer row t */
     float* buf_obs; float* buf_actions; float* buf_rewards; float* buf_dones; float* buf_values; float* buf_log_probs;
-    double* scratch;           /* [2 * obs_dim + 2]                                                                   */
+    double* scratch;           /* [3 * obs_dim + 3]                                                                   */
     int32_t n, obs_dim, act_dim;
     float gamma, clip_obs, clip_reward, epsilon;
     int32_t norm_obs, norm_reward, training;

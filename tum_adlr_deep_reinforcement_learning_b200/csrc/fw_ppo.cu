@@ -236,26 +236,34 @@ __global__ void rollout_moments_kernel(const FwRolloutPost p) {
     }
 }
 
+// scratch[2 D + 2 + j] = 1 / sqrt(obs_var_j + eps), scratch[3 D + 2] = 1 / sqrt(ret_var + eps): one square root per
+// statistic instead of one per element (runs after the moments update, also when training is off)
+__global__ void rollout_scales_kernel(const FwRolloutPost p) {
+    const int D = p.obs_dim, j = threadIdx.x;
+    if (j < D) p.scratch[2 * D + 2 + j] = 1.0 / sqrt(p.obs_var[j] + (double)p.epsilon);
+    if (j == 0) p.scratch[3 * D + 2] = 1.0 / sqrt(*p.ret_var + (double)p.epsilon);
+}
+
+// one thread per observation element (coalesced); the threads of column 0 also move the per-env scalars
 __global__ void __launch_bounds__(TPB) rollout_apply_kernel(const FwRolloutPost p) {
-    const int i = blockIdx.x * TPB + threadIdx.x;
-    if (i >= p.n) return;
     const int D = p.obs_dim, A = p.act_dim;
-    for (int j = 0; j < D; ++j) {
-        const size_t o = (size_t)i * D + j;
-        p.buf_obs[o] = p.last_obs[o];
-        const float raw = p.obs_raw[o];
-        float v = raw;
-        if (p.norm_obs) {
-            double x = ((double)raw - p.obs_mean[j]) / sqrt(p.obs_var[j] + (double)p.epsilon);
-            x = fmin(fmax(x, -(double)p.clip_obs), (double)p.clip_obs);
-            v = (float)x;
-        }
-        p.last_obs[o] = v;
+    const size_t o = (size_t)blockIdx.x * TPB + threadIdx.x;
+    if (o >= (size_t)p.n * D) return;
+    const int i = (int)(o / D), j = (int)(o - (size_t)i * D);
+    p.buf_obs[o] = p.last_obs[o];
+    const float raw = p.obs_raw[o];
+    float v = raw;
+    if (p.norm_obs) {
+        double x = ((double)raw - p.obs_mean[j]) * p.scratch[2 * D + 2 + j];
+        x = fmin(fmax(x, -(double)p.clip_obs), (double)p.clip_obs);
+        v = (float)x;
     }
-    for (int j = 0; j < A; ++j) p.buf_actions[(size_t)i * A + j] = p.actions[(size_t)i * A + j];
+    p.last_obs[o] = v;
+    if (j != 0) return;
+    for (int k = 0; k < A; ++k) p.buf_actions[(size_t)i * A + k] = p.actions[(size_t)i * A + k];
     float rw = p.rew_raw[i];
     if (p.norm_reward) {
-        double x = (double)rw / sqrt(*p.ret_var + (double)p.epsilon);
+        double x = (double)rw * p.scratch[3 * D + 2];
         x = fmin(fmax(x, -(double)p.clip_reward), (double)p.clip_reward);
         rw = (float)x;
     }
@@ -286,7 +294,8 @@ extern "C" int fw_rollout_post_step(const FwRolloutPost* p, void* stream) {
     if (grid > 296) grid = 296;
     rollout_stats_kernel<<<grid, TPB, sizeof(double) * (2 * D + 5), st>>>(*p);
     rollout_moments_kernel<<<1, 256, 0, st>>>(*p);
-    rollout_apply_kernel<<<(p->n + TPB - 1) / TPB, TPB, 0, st>>>(*p);
+    rollout_scales_kernel<<<1, 256, 0, st>>>(*p);
+    rollout_apply_kernel<<<(unsigned)(((size_t)p->n * D + TPB - 1) / TPB), TPB, 0, st>>>(*p);
     return cudaGetLastError() == cudaSuccess ? FW_OK : FW_ECUDA;
 }
 

@@ -241,7 +241,7 @@ class PPO:
         # on-device episode statistics (Monitor-equivalent, no per-env python objects)
         self._ep_stats = torch.zeros(3, dtype=torch.float64, device=self.device)     # one buffer: fw_rollout_post_step
         self.ep_ret_sum, self.ep_len_sum, self.ep_count = self._ep_stats[0], self._ep_stats[1], self._ep_stats[2]
-        self._post_scratch = torch.zeros(2 * 256 + 2, dtype=torch.float64, device=self.device)
+        self._post_scratch = torch.zeros(3 * 256 + 3, dtype=torch.float64, device=self.device)
         self._run_ret = torch.zeros(self.n_envs, dtype=torch.float64, device=self.device)
         self._run_len = torch.zeros(self.n_envs, dtype=torch.float64, device=self.device)
         self.logs = []
