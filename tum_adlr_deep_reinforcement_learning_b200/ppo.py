@@ -223,6 +223,8 @@ class PPO:
         self.graph_allreduce = os.environ.get("FWB200_PPO_GRAPH_ALLREDUCE", "1") != "0"
         self.fused_loss = bool(fused_loss)
         self.fused_rollout = bool(fused_rollout)
+        self.two_stream_nets = os.environ.get("FWB200_PPO_TWO_STREAMS", "1") != "0"
+        self._vf_stream = None
         self.flat_optimizer = bool(flat_optimizer) and self.device.type == "cuda"
         if self.flat_optimizer:
             self.optimizer = FlatAdam(self.policy, lr=learning_rate, eps=1e-5, max_grad_norm=max_grad_norm)
@@ -254,7 +256,21 @@ class PPO:
 
     def _rollout_step(self, t):
         with torch.no_grad():
-            actions, values, log_probs = self.policy(self._last_obs)
+            if self.two_stream_nets and self._last_obs.is_cuda:
+                # value head on the second stream, policy head + sampling on this one (see _loss)
+                cur = torch.cuda.current_stream(self.device)
+                if self._vf_stream is None:
+                    self._vf_stream = torch.cuda.Stream(self.device)
+                self._vf_stream.wait_stream(cur)
+                with torch.cuda.stream(self._vf_stream):
+                    values = self.policy.predict_values(self._last_obs)
+                mean, log_std = self.policy._dist(self._last_obs)
+                actions = mean + torch.exp(log_std) * torch.randn_like(mean)
+                log_probs = self.policy._log_prob(actions, mean, log_std)
+                cur.wait_stream(self._vf_stream)
+                values.record_stream(cur)
+            else:
+                actions, values, log_probs = self.policy(self._last_obs)
         obs_raw, rew_raw, done = self.env.step_tensor(actions.contiguous())
         if self.fused_rollout and obs_raw.is_cuda:
             return self._fused_post_step(t, obs_raw, rew_raw, done, actions, values, log_probs)
@@ -340,8 +356,22 @@ class PPO:
     def _loss(self, batch):
         """ppo.py:163-207.  On the GPU the part after the networks is the fused fw_ppo_loss kernel."""
         if self.fused_loss and batch.observations.is_cuda:
-            mean = self.policy.action_net(self.policy.pi(batch.observations))
-            values = self.policy.value_net(self.policy.vf(batch.observations)).squeeze(-1)
+            # the policy and the value network are independent until the loss: the value branch runs on a second
+            # stream (autograd replays its backward there as well), so that inside the captured update graph the two
+            # chains of small, latency-bound kernels overlap
+            cur = torch.cuda.current_stream(self.device)
+            if self.two_stream_nets:
+                if self._vf_stream is None:
+                    self._vf_stream = torch.cuda.Stream(self.device)
+                self._vf_stream.wait_stream(cur)
+                with torch.cuda.stream(self._vf_stream):
+                    values = self.policy.value_net(self.policy.vf(batch.observations)).squeeze(-1)
+                mean = self.policy.action_net(self.policy.pi(batch.observations))
+                cur.wait_stream(self._vf_stream)
+                values.record_stream(cur)
+            else:
+                mean = self.policy.action_net(self.policy.pi(batch.observations))
+                values = self.policy.value_net(self.policy.vf(batch.observations)).squeeze(-1)
             loss, parts = FusedPPOLoss.apply(mean, values, self.policy.log_std, batch.actions, batch.old_log_prob,
                                              batch.advantages, batch.returns, self.clip_range, self.ent_coef, self.vf_coef)
             return loss, parts[1], parts[2]
