@@ -377,7 +377,7 @@ def main():
                "envs_per_gpu": n_ppo, "n_steps": n_steps, "minibatch": n_ppo * n_steps // 8, "n_epochs": 10,
                "iterations_timed": iters, "ep_rew_mean": algo.logs[-1]["ep_rew_mean"],
                "note": "policy 2x64 tanh MLP in PyTorch (split-K weight gradients), loss block fused in fw_ppo_loss, rollout "
-                       "and minibatch update replayed as CUDA graphs; one gradient all-reduce per optimiser step when "
+                       "and minibatch update replayed as CUDA graphs (value branch on a second stream); one gradient all-reduce per optimiser step when "
                        "n_gpus > 1 (NCCL, captured in the update graph); learning curves in results/"}
         venv.close()
 
