@@ -565,3 +565,29 @@ def test_flat_adam_matches_torch_adam_with_clipping(cuda_device):
     opt2 = FlatAdam(copy.deepcopy(mine), lr=1.0)
     opt2.load_state_dict(sd)
     assert float(opt2.step_count) == 6.0 and opt2.lr == 3e-4 and torch.equal(opt2.exp_avg, opt.exp_avg)
+
+
+def test_ppo_on_other_observation_layouts(cuda_device):
+    """PPO takes the observation width from the env: the waypoint env head (12 raw states) and the reference's
+    CNN-controller layout (5 x 12 matrix flattened) both run rollouts + updates through the fused paths and graphs."""
+    import torch
+    from conftest import cnn_env_config
+    from tum_adlr_deep_reinforcement_learning_b200.ppo import PPO
+    from tum_adlr_deep_reinforcement_learning_b200.vec_env import FixedWingVecEnv, WaypointVecEnv
+    tasks = np.full((2, 4, 15), np.nan)
+    for t in range(2):
+        for w in range(4):
+            tasks[t, w, :3] = [10.0 * w, 2.0 * t, -80.0]
+            tasks[t, w, 3:6] = 0.0
+            tasks[t, w, 6:9] = [18.0, 0.0, 0.0]
+            tasks[t, w, 9:12] = 0.0
+    envs = [WaypointVecEnv(512, tasks, sim_config_kw={"turbulence": False}),
+            FixedWingVecEnv(512, config_path=cnn_env_config(), sim_config_kw={"turbulence": False})]
+    for env, dim in zip(envs, (12, 60)):
+        assert env.sim.obs_dim == dim
+        algo = PPO(env, n_steps=8, batch_size=2048, n_epochs=2)
+        algo.learn(total_timesteps=4 * 8 * 512)              # eager rollout, then captured graphs
+        assert algo.buffer.observations.shape == (8, 512, dim)
+        assert all(bool(torch.isfinite(p).all()) for p in algo.policy.parameters())
+        assert algo._rollout_graph is not None and algo._train_graph
+        env.close()

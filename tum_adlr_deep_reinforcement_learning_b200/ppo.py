@@ -216,7 +216,8 @@ class PPO:
         self.world = dist.get_world_size() if dist is not None else 1
         self.rank = dist.get_rank() if dist is not None else 0
         torch.manual_seed(seed)                      # identical initial weights on every rank
-        self.policy = ActorCritic().to(self.device)
+        self.obs_dim = int(getattr(getattr(env, "sim", None), "obs_dim", 14))    # 14 by default; general layouts, waypoint env
+        self.policy = ActorCritic(obs_dim=self.obs_dim).to(self.device)
         torch.manual_seed(seed + 1000 * (self.rank + 1))   # different action noise per rank
         self.use_cuda_graph = bool(use_cuda_graph)
         # capture the NCCL gradient all-reduce inside the minibatch-update graph (data-parallel runs)
@@ -234,8 +235,9 @@ class PPO:
         self._rollout_graph = None
         self._train_graph = None
         self._eager_rollouts = 0
-        self.buffer = RolloutBuffer(n_steps, self.n_envs, device=self.device, gae_lambda=gae_lambda, gamma=gamma)
-        self.norm = DeviceVecNormalize(self.n_envs, device=self.device, gamma=gamma, norm_obs=normalize,
+        self.buffer = RolloutBuffer(n_steps, self.n_envs, obs_dim=self.obs_dim, device=self.device,
+                                    gae_lambda=gae_lambda, gamma=gamma)
+        self.norm = DeviceVecNormalize(self.n_envs, obs_dim=self.obs_dim, device=self.device, gamma=gamma, norm_obs=normalize,
                                        norm_reward=normalize)
         self.num_timesteps = 0
         self._last_obs = None

@@ -103,17 +103,18 @@ class SAC:
         self.batch_size, self.gradient_steps, self.learning_starts = batch_size, gradient_steps, learning_starts
         self.gamma, self.tau = gamma, tau
         torch.manual_seed(seed)
-        self.actor = Actor().to(self.device)
-        self.critic = Critic().to(self.device)
-        self.critic_target = Critic().to(self.device)
+        od = int(getattr(getattr(env, "sim", None), "obs_dim", 14))
+        self.actor = Actor(obs_dim=od).to(self.device)
+        self.critic = Critic(obs_dim=od).to(self.device)
+        self.critic_target = Critic(obs_dim=od).to(self.device)
         self.critic_target.load_state_dict(self.critic.state_dict())
         self.log_ent_coef = torch.zeros(1, device=self.device, requires_grad=True)     # ent_coef "auto", init 1.0
         self.target_entropy = -3.0 if target_entropy == "auto" else float(target_entropy)
         self.actor_opt = torch.optim.Adam(self.actor.parameters(), lr=learning_rate)
         self.critic_opt = torch.optim.Adam(self.critic.parameters(), lr=learning_rate)
         self.ent_opt = torch.optim.Adam([self.log_ent_coef], lr=learning_rate)
-        self.buffer = ReplayBuffer(buffer_size, device=self.device)
-        self.norm = DeviceVecNormalize(self.n_envs, device=self.device, gamma=gamma, norm_obs=normalize,
+        self.buffer = ReplayBuffer(buffer_size, obs_dim=od, device=self.device)
+        self.norm = DeviceVecNormalize(self.n_envs, obs_dim=od, device=self.device, gamma=gamma, norm_obs=normalize,
                                        norm_reward=normalize)
         self.num_timesteps = 0
         self._last_obs = None
