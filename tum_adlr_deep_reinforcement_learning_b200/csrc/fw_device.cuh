@@ -425,7 +425,7 @@ __device__ __forceinline__ int rk45_init(const DCfg<T>& c, const DynCtx<T>& x, T
             T s0 = 0, s1 = 0;
 #pragma unroll
             for (int i = 0; i < FW_NY; ++i) {
-                const T inv = (T)1 / (atol + M<T>::fabs(ys[i]) * rtol);
+                const T inv = M<T>::rcp_hot(atol + M<T>::fabs(ys[i]) * rtol);      // >= atol: normal range
                 const T a = ys[i] * inv, b = dyv[i] * inv;
                 s0 += a * a;
                 s1 += b * b;
@@ -442,7 +442,7 @@ __device__ __forceinline__ int rk45_init(const DCfg<T>& c, const DynCtx<T>& x, T
 #pragma unroll
             for (int i = 0; i < FW_NY; ++i) {
                 const T y0 = ld_again(ysrc + i * n), f0 = (i < FW_NK) ? ld_again(f0dst + i * n) : (T)0;
-                const T inv = (T)1 / (atol + M<T>::fabs(y0) * rtol);
+                const T inv = M<T>::rcp_hot(atol + M<T>::fabs(y0) * rtol);
                 const T d = (dyv[i] - f0) * inv;
                 s2 += d * d;
             }
