@@ -34,6 +34,9 @@ class ReplayBuffer:
         self.dones = torch.zeros(self.capacity, dtype=torch.float32, device=d)
         self.pos = 0
         self.full = False
+        self.size_dev = torch.zeros((), dtype=torch.float32, device=d)
+        self.pos_dev = torch.zeros((), dtype=torch.long, device=d)
+        self._arange = None
 
     def size(self):
         return self.capacity if self.full else self.pos
@@ -52,9 +55,37 @@ class ReplayBuffer:
         if self.pos >= self.capacity:
             self.full = True
             self.pos -= self.capacity
+        self.size_dev.fill_(float(self.size()))
+        self.pos_dev.fill_(self.pos)
+
+    def add_capturable(self, obs, next_obs, action, reward, done):
+        """add() with the ring head read from / advanced on the device (`pos_dev`), as one scatter per array: usable
+        inside a captured CUDA graph.  The caller mirrors the advance on the host with advance_host(n)."""
+        n = obs.shape[0]
+        if self._arange is None or self._arange.numel() != n:
+            self._arange = torch.arange(n, device=self.device)
+        idx = (self.pos_dev + self._arange) % self.capacity
+        for dst, src in ((self.observations, obs), (self.next_observations, next_obs), (self.actions, action),
+                         (self.rewards, reward), (self.dones, done.to(torch.float32))):
+            dst.index_copy_(0, idx, src)
+        self.pos_dev.add_(n).remainder_(self.capacity)
+        self.size_dev.add_(float(n)).clamp_(max=float(self.capacity))
+
+    def advance_host(self, n):
+        self.pos += n
+        if self.pos >= self.capacity:
+            self.full = True
+            self.pos -= self.capacity
 
     def sample(self, batch_size, generator=None):
         idx = torch.randint(0, self.size(), (batch_size,), device=self.device, generator=generator)
+        return (self.observations[idx], self.actions[idx], self.next_observations[idx], self.dones[idx],
+                self.rewards[idx])
+
+    def sample_capturable(self, batch_size):
+        """Uniform sample whose range is read from a device scalar (`size_dev`, kept current by add()): usable inside a
+        captured CUDA graph, where a python-side size would be frozen at capture time."""
+        idx = (torch.rand(batch_size, device=self.device) * self.size_dev).long().clamp_(max=self.capacity - 1)
         return (self.observations[idx], self.actions[idx], self.next_observations[idx], self.dones[idx],
                 self.rewards[idx])
 
@@ -98,7 +129,8 @@ class Critic(nn.Module):
 
 class SAC:
     def __init__(self, env, buffer_size=1_000_000, batch_size=4096, gradient_steps=2, learning_starts=10_000,
-                 learning_rate=3e-4, gamma=0.99, tau=0.005, target_entropy="auto", normalize=True, seed=0):
+                 learning_rate=3e-4, gamma=0.99, tau=0.005, target_entropy="auto", normalize=True, seed=0,
+                 use_cuda_graph=True):
         self.env, self.device, self.n_envs = env, env.device, env.num_envs
         self.batch_size, self.gradient_steps, self.learning_starts = batch_size, gradient_steps, learning_starts
         self.gamma, self.tau = gamma, tau
@@ -110,9 +142,15 @@ class SAC:
         self.critic_target.load_state_dict(self.critic.state_dict())
         self.log_ent_coef = torch.zeros(1, device=self.device, requires_grad=True)     # ent_coef "auto", init 1.0
         self.target_entropy = -3.0 if target_entropy == "auto" else float(target_entropy)
-        self.actor_opt = torch.optim.Adam(self.actor.parameters(), lr=learning_rate)
-        self.critic_opt = torch.optim.Adam(self.critic.parameters(), lr=learning_rate)
-        self.ent_opt = torch.optim.Adam([self.log_ent_coef], lr=learning_rate)
+        self.use_cuda_graph = bool(use_cuda_graph) and self.device.type == "cuda"
+        cap = self.use_cuda_graph
+        self.actor_opt = torch.optim.Adam(self.actor.parameters(), lr=learning_rate, capturable=cap)
+        self.critic_opt = torch.optim.Adam(self.critic.parameters(), lr=learning_rate, capturable=cap)
+        self.ent_opt = torch.optim.Adam([self.log_ent_coef], lr=learning_rate, capturable=cap)
+        self._train_graph = None
+        self._graph_stats = None
+        self._env_graph = None
+        self._env_warm = 0
         self.buffer = ReplayBuffer(buffer_size, obs_dim=od, device=self.device)
         self.norm = DeviceVecNormalize(self.n_envs, obs_dim=od, device=self.device, gamma=gamma, norm_obs=normalize,
                                        norm_reward=normalize)
@@ -123,12 +161,12 @@ class SAC:
         self.ep_count = torch.zeros((), dtype=torch.float64, device=self.device)
         self._run_ret = torch.zeros(self.n_envs, dtype=torch.float64, device=self.device)
 
-    def _env_step(self):
+    def _env_step_body(self, use_actor, capturable=False):
         with torch.no_grad():
-            if self.num_timesteps < self.learning_starts:
-                actions = torch.rand(self.n_envs, 3, device=self.device) * 2 - 1      # uniform warm-up (sac.py learning_starts)
-            else:
+            if use_actor:
                 actions, _ = self.actor(self._last_obs)
+            else:
+                actions = torch.rand(self.n_envs, 3, device=self.device) * 2 - 1      # uniform warm-up (sac.py learning_starts)
         obs_raw, rew_raw, done = self.env.step_tensor(actions.contiguous())
         d = done.bool()
         self._run_ret.add_(rew_raw.to(torch.float64))
@@ -136,17 +174,78 @@ class SAC:
         self.ep_count.add_(d.sum())
         self._run_ret.masked_fill_(d, 0.0)
         obs, rew = self.norm.step(obs_raw, rew_raw, done)
-        self.buffer.add(self._last_obs, obs, actions, rew, done)
-        self._last_obs = obs.clone()
+        if capturable:
+            self.buffer.add_capturable(self._last_obs, obs, actions, rew, done)
+        else:
+            self.buffer.add(self._last_obs, obs, actions, rew, done)
+        self._last_obs.copy_(obs)
+
+    def _env_step(self):
+        """One env step of all envs + replay insert.  Once the actor drives the envs the step (actor forward, the
+        simulator kernels, normaliser, ring insert: ~100 launches) is replayed as one CUDA graph."""
+        use_actor = self.num_timesteps >= self.learning_starts
+        if use_actor and self.use_cuda_graph and self._env_graph is not False:
+            if self._env_graph is None:
+                if self._env_warm < 2:                              # two eager steps first (allocator, lazy init)
+                    self._env_warm += 1
+                    self._env_step_body(True, capturable=True)
+                    self.buffer.advance_host(self.n_envs)
+                    self.num_timesteps += self.n_envs
+                    return
+                self.env.sim.join()
+                torch.cuda.synchronize(self.device)
+                try:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self._env_step_body(True, capturable=True)
+                    self._env_graph = g
+                except Exception as e:
+                    self.logs.append({"env_cuda_graph_disabled": repr(e)})
+                    self._env_graph = False
+                    torch.cuda.synchronize(self.device)
+            if self._env_graph:
+                self._env_graph.replay()
+                self.buffer.advance_host(self.n_envs)
+                self.num_timesteps += self.n_envs
+                return
+        self._env_step_body(use_actor)
         self.num_timesteps += self.n_envs
 
-    def train_step(self):
+    def train_step_graphed(self):
+        """train_step replayed as one CUDA graph: the eager step is ~150 small launches driven from python (4.5 ms);
+        captured it is bound by the kernels themselves.  The first calls run eagerly (optimizer state, allocator)."""
+        if not self.use_cuda_graph:
+            return self.train_step()
+        if self._train_graph is None:
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    self.train_step(capturable=True)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    stats = self.train_step(capturable=True)
+                    self._graph_stats = tuple(x.clone() for x in stats)
+                self._train_graph = g
+            except Exception as e:                     # capture is an optimisation, never a requirement
+                self.logs.append({"cuda_graph_disabled": repr(e)})
+                self.use_cuda_graph = False
+                torch.cuda.synchronize(self.device)
+                return self.train_step()
+        self._train_graph.replay()
+        return self._graph_stats
+
+    def train_step(self, capturable=False):
         """One gradient step of sac.py:196-256 on a device-sampled batch."""
-        obs, act, next_obs, done, rew = self.buffer.sample(self.batch_size)
+        obs, act, next_obs, done, rew = (self.buffer.sample_capturable(self.batch_size) if capturable
+                                         else self.buffer.sample(self.batch_size))
         a_pi, logp = self.actor(obs)
         ent_coef = self.log_ent_coef.exp().detach()
         ent_loss = -(self.log_ent_coef * (logp + self.target_entropy).detach()).mean()
-        self.ent_opt.zero_grad(set_to_none=True)
+        self.ent_opt.zero_grad(set_to_none=not capturable)
         ent_loss.backward()
         self.ent_opt.step()
         with torch.no_grad():
@@ -155,18 +254,18 @@ class SAC:
             target = rew + (1 - done) * self.gamma * q_next
         q1, q2 = self.critic(obs, act)
         critic_loss = 0.5 * (F.mse_loss(q1, target) + F.mse_loss(q2, target))
-        self.critic_opt.zero_grad(set_to_none=True)
+        self.critic_opt.zero_grad(set_to_none=not capturable)
         critic_loss.backward()
         self.critic_opt.step()
         q_pi = torch.min(*self.critic(obs, a_pi))
         actor_loss = (ent_coef * logp - q_pi).mean()
-        self.actor_opt.zero_grad(set_to_none=True)
+        self.actor_opt.zero_grad(set_to_none=not capturable)
         actor_loss.backward()
         self.actor_opt.step()
         with torch.no_grad():
             for p, pt in zip(self.critic.parameters(), self.critic_target.parameters()):
                 pt.mul_(1 - self.tau).add_(p, alpha=self.tau)
-        return critic_loss.detach(), actor_loss.detach(), ent_coef
+        return critic_loss.detach(), actor_loss.detach(), ent_coef.reshape(())
 
     def learn(self, total_timesteps, log_every=50, callback=None):
         if self._last_obs is None:
@@ -177,7 +276,7 @@ class SAC:
             stats = None
             if self.num_timesteps >= self.learning_starts and self.buffer.size() >= self.batch_size:
                 for _ in range(self.gradient_steps):
-                    stats = self.train_step()
+                    stats = self.train_step_graphed()
             self._it += 1
             if self._it % log_every == 0:
                 r, c = self.ep_ret_sum.item(), self.ep_count.item()
