@@ -130,3 +130,39 @@ def test_replay_buffer_ring_semantics():
     small = ReplayBuffer(100, obs_dim=2, action_dim=1, device="cpu")
     small.add(torch.ones(3, 2), torch.ones(3, 2), torch.zeros(3, 1), torch.ones(3), torch.zeros(3))
     assert small.size() == 3 and small.sample(64)[0].eq(1).all()
+
+
+def test_split_k_linear_gradients_match_nn_linear():
+    """ppo._LinearSplitK (weight gradient as a chunked bmm + sum, bias gradient in two stages) against
+    torch.nn.functional.linear on CPU tensors, for batch sizes with and without a power-of-two chunking."""
+    import torch
+    from tum_adlr_deep_reinforcement_learning_b200.ppo import _LinearSplitK
+    torch.manual_seed(0)
+    for B, din, dout in ((8192, 14, 64), (4096, 64, 3), (1000, 64, 1)):
+        x = torch.randn(B, din, dtype=torch.float64, requires_grad=True)
+        w = torch.randn(dout, din, dtype=torch.float64, requires_grad=True)
+        b = torch.randn(dout, dtype=torch.float64, requires_grad=True)
+        up = torch.randn(B, dout, dtype=torch.float64)
+        (_LinearSplitK.apply(x, w, b) * up).sum().backward()
+        got = [t.grad.clone() for t in (x, w, b)]
+        for t in (x, w, b):
+            t.grad = None
+        (torch.nn.functional.linear(x, w, b) * up).sum().backward()
+        for g, t in zip(got, (x, w, b)):
+            assert torch.allclose(g, t.grad, rtol=1e-12, atol=1e-10)
+
+
+def test_episode_end_info_builder_layout():
+    """vec_env._done_info: the compiled dict display carries every reference key with the METRIC_LAYOUT offsets."""
+    import numpy as np
+    from tum_adlr_deep_reinforcement_learning_b200 import vec_env as V
+    from tum_adlr_deep_reinforcement_learning_b200.config import METRIC_LAYOUT
+    row = [float(i) for i in range(28)] + [-12.5, 77.0, 11.0]            # metrics | return | length | term code
+    tob = np.arange(14, dtype=np.float32)
+    info = V._done_info(row, tob, 3.25)
+    assert info["termination"] == "omega_q" or isinstance(info["termination"], (str, int))
+    assert info["episode"] == {"r": -12.5, "l": 77, "t": 3.25} and info["terminal_observation"] is tob
+    for name, off, keys in METRIC_LAYOUT:
+        assert list(info[name]) == list(keys)
+        for q, k in enumerate(keys):
+            assert info[name][k] == (bool(row[off + q]) if name == "success" else row[off + q])
