@@ -1,7 +1,7 @@
 """Generate the golden fixtures in this directory by running the UNMODIFIED reference where it lies.
 
 TEST INFRASTRUCTURE — run here (the build container, where /root/reference is mounted), never on the
-GPU box.  Usage:  python tests/golden/make_golden.py [params|traj|turb|fail|full|pid|gae|dryden|all]
+GPU box.  Usage:  python tests/golden/make_golden.py [params|traj|turb|fail|full|pid|gae|vecnorm|dryden|all]
 
 Everything is recorded through the reference's public surface:
   FixedWingAircraft.reset(state=, target=, turbulence_noise=) / .step(action)
@@ -556,6 +556,71 @@ def gen_gae():
     np.savez_compressed(os.path.join(HERE, "gae.npz"), **out)
 
 
+def gen_vecnorm():
+    """Reference VecNormalize (+ RunningMeanStd) and RolloutBuffer.add / swap_and_flatten driven by a scripted VecEnv
+    (vec_normalize.py:106-219, running_mean_std.py:19-39, buffers.py:51-64, 292-302): raw observations / rewards /
+    dones in, normalised observations / rewards, running moments and buffer contents out."""
+    import torch
+    from stable_baselines3.common.buffers import RolloutBuffer
+    from stable_baselines3.common.vec_env.base_vec_env import VecEnv
+    from stable_baselines3.common.vec_env.vec_normalize import VecNormalize
+    T, N, D = 24, 6, 14
+    rs = np.random.RandomState(2024)
+    obs_seq = (rs.standard_normal((T + 1, N, D)) * rs.uniform(0.1, 30, D) + rs.uniform(-5, 5, D)).astype(np.float32)
+    rew_seq = (rs.standard_normal((T, N)) * 3 - 1).astype(np.float32)
+    done_seq = rs.uniform(size=(T, N)) < 0.15
+    obs_space = refshim.Box(-np.inf * np.ones(D), np.inf * np.ones(D), dtype=np.float32)
+    act_space = refshim.Box(-np.ones(3), np.ones(3), dtype=np.float32)
+
+    class Scripted(VecEnv):
+        def __init__(self):
+            VecEnv.__init__(self, N, obs_space, act_space)
+            self.t = 0
+
+        def reset(self):
+            self.t = 0
+            return obs_seq[0].copy()
+
+        def step_async(self, actions):
+            pass
+
+        def step_wait(self):
+            t = self.t
+            self.t += 1
+            return obs_seq[t + 1].copy(), rew_seq[t].copy(), done_seq[t].copy(), [{} for _ in range(N)]
+
+        def close(self): pass
+        def get_attr(self, *a, **k): return [None] * N
+        def set_attr(self, *a, **k): pass
+        def env_method(self, *a, **k): return [None] * N
+        def seed(self, seed=None): return [None] * N
+
+    venv = VecNormalize(Scripted(), training=True, norm_obs=True, norm_reward=True, clip_obs=10.0, clip_reward=10.0,
+                        gamma=0.99, epsilon=1e-8)
+    buf = RolloutBuffer(T, obs_space, act_space, device="cpu", gae_lambda=0.95, gamma=0.99, n_envs=N)
+    acts = rs.uniform(-1, 1, (T, N, 3)).astype(np.float32)
+    vals = rs.standard_normal((T, N)).astype(np.float32)
+    logp = rs.standard_normal((T, N)).astype(np.float32)
+    last_obs = venv.reset()
+    last_dones = np.zeros(N, dtype=bool)
+    nobs, nrew = [last_obs.copy()], []
+    for t in range(T):
+        venv.step_async(acts[t])
+        o, r, d, _ = venv.step_wait()
+        buf.add(last_obs, acts[t], r, last_dones, torch.as_tensor(vals[t]), torch.as_tensor(logp[t]))   # on_policy_algorithm.py:178
+        last_obs, last_dones = o, d
+        nobs.append(o.copy()); nrew.append(np.asarray(r, dtype=np.float64).copy())
+    out = dict(obs_seq=obs_seq, rew_seq=rew_seq, done_seq=done_seq, acts=acts, vals=vals, logp=logp,
+               norm_obs=np.stack(nobs), norm_rew=np.stack(nrew),
+               obs_mean=venv.obs_rms.mean, obs_var=venv.obs_rms.var, obs_count=np.float64(venv.obs_rms.count),
+               ret_mean=np.float64(venv.ret_rms.mean), ret_var=np.float64(venv.ret_rms.var),
+               ret_count=np.float64(venv.ret_rms.count), ret=venv.ret.copy(),
+               buf_obs=buf.observations.copy(), buf_act=buf.actions.copy(), buf_rew=buf.rewards.copy(),
+               buf_done=buf.dones.copy(), buf_val=buf.values.copy(), buf_logp=buf.log_probs.copy(),
+               flat_obs=RolloutBuffer.swap_and_flatten(buf.observations.copy()))
+    np.savez_compressed(os.path.join(HERE, "vecnorm.npz"), **out)
+
+
 def gen_dryden():
     """Reference Dryden output for injected noise, for the gym parameterisation (dt<-2000, b<-0.01, h<-2.1;
     pyfly.py:781-783 vs dryden.py:52) and for raw pyfly (sim_length 300), all three intensities."""
@@ -585,7 +650,7 @@ def gen_dryden():
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     jobs = {"waypoint": gen_waypoint, "targets": gen_targets, "reward": gen_reward, "cnn": gen_cnn, "params": gen_params, "traj": gen_traj, "turb": gen_turb, "fail": gen_fail, "full": gen_full,
-            "pid": gen_pid, "gae": gen_gae, "dryden": gen_dryden}
+            "pid": gen_pid, "gae": gen_gae, "vecnorm": gen_vecnorm, "dryden": gen_dryden}
     for name, fn in jobs.items():
         if what in (name, "all"):
             t0 = time.time()

@@ -591,3 +591,40 @@ def test_ppo_on_other_observation_layouts(cuda_device):
         assert all(bool(torch.isfinite(p).all()) for p in algo.policy.parameters())
         assert algo._rollout_graph is not None and algo._train_graph
         env.close()
+
+
+def test_fused_rollout_glue_matches_the_reference_fixture(cuda_device):
+    """fw_rollout_post_step against the live reference's VecNormalize + RolloutBuffer on a scripted env
+    (tests/golden/vecnorm.npz, generated by tests/golden/make_golden.py vecnorm)."""
+    import torch
+    from tum_adlr_deep_reinforcement_learning_b200.buffers import DeviceVecNormalize, RolloutBuffer, fused_post_step
+    g = load_golden("vecnorm")
+    T, N, D = g["rew_seq"].shape[0], g["rew_seq"].shape[1], g["obs_seq"].shape[2]
+    dev = "cuda"
+    nm = DeviceVecNormalize(N, obs_dim=D, device=dev, gamma=0.99)
+    buf = RolloutBuffer(T, N, obs_dim=D, device=dev)
+    last_obs = nm.reset(torch.as_tensor(g["obs_seq"][0], device=dev)).clone()
+    last_dones = torch.zeros(N, device=dev)
+    run_ret = torch.zeros(N, dtype=torch.float64, device=dev)
+    run_len = torch.zeros(N, dtype=torch.float64, device=dev)
+    ep = torch.zeros(3, dtype=torch.float64, device=dev)
+    scratch = torch.zeros(3 * D + 3, dtype=torch.float64, device=dev)
+    for t in range(T):
+        fused_post_step(nm, buf, torch.as_tensor(g["obs_seq"][t + 1], device=dev), torch.as_tensor(g["rew_seq"][t], device=dev),
+                        torch.as_tensor(g["done_seq"][t].astype(np.uint8), device=dev), torch.as_tensor(g["acts"][t], device=dev),
+                        torch.as_tensor(g["vals"][t], device=dev), torch.as_tensor(g["logp"][t], device=dev),
+                        last_obs, last_dones, run_ret, run_len, ep, scratch)
+        assert np.allclose(last_obs.cpu().numpy(), g["norm_obs"][t + 1], rtol=2e-5, atol=2e-5), t
+        assert np.array_equal(last_dones.cpu().numpy(), g["done_seq"][t].astype(np.float32))
+    assert buf.full
+    assert np.allclose(nm.obs_rms.mean.cpu().numpy(), g["obs_mean"], rtol=1e-5, atol=1e-5)
+    assert np.allclose(nm.obs_rms.var.cpu().numpy(), g["obs_var"], rtol=1e-5)
+    assert np.isclose(float(nm.obs_rms.count), float(g["obs_count"])) and np.isclose(float(nm.ret_rms.count), float(g["ret_count"]))
+    assert np.isclose(float(nm.ret_rms.mean), float(g["ret_mean"]), rtol=1e-6) and np.isclose(float(nm.ret_rms.var), float(g["ret_var"]), rtol=1e-6)
+    assert np.allclose(nm.ret.cpu().numpy(), g["ret"], rtol=1e-6, atol=1e-6)
+    for mine, ref in ((buf.observations, "buf_obs"), (buf.actions, "buf_act"), (buf.rewards, "buf_rew"),
+                      (buf.dones, "buf_done"), (buf.values, "buf_val"), (buf.log_probs, "buf_logp")):
+        assert np.allclose(mine.cpu().numpy(), g[ref], rtol=2e-5, atol=2e-5), ref
+    # episode totals of the raw rewards (Monitor): finished episodes only
+    ends = g["done_seq"].sum()
+    assert float(ep[2]) == float(ends)

@@ -166,3 +166,42 @@ def test_episode_end_info_builder_layout():
         assert list(info[name]) == list(keys)
         for q, k in enumerate(keys):
             assert info[name][k] == (bool(row[off + q]) if name == "success" else row[off + q])
+
+
+def _vecnorm_fixture():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vecnorm.npz"))
+
+
+def test_vecnormalize_and_rollout_buffer_match_the_reference():
+    """buffers.DeviceVecNormalize / RunningMeanStd / RolloutBuffer (CPU tensors) against the live reference's
+    VecNormalize + RolloutBuffer on a scripted env (tests/golden/vecnorm.npz): reset semantics (the reset feeds zeros
+    to ret_rms and leaves obs_rms alone), normalised observations / rewards, running moments, buffer rows (previous
+    observation and done flags are stored), swap_and_flatten order.  The reference takes the batch moments of float32
+    observations in float32, hence the 1e-5 tolerances."""
+    import torch
+    from tum_adlr_deep_reinforcement_learning_b200.buffers import DeviceVecNormalize
+    g = _vecnorm_fixture()
+    T, N, D = g["rew_seq"].shape[0], g["rew_seq"].shape[1], g["obs_seq"].shape[2]
+    nm = DeviceVecNormalize(N, obs_dim=D, device="cpu", gamma=0.99)
+    buf = RolloutBuffer(T, N, obs_dim=D, device="cpu")
+    last_obs = nm.reset(torch.as_tensor(g["obs_seq"][0]))
+    assert np.allclose(last_obs.numpy(), g["norm_obs"][0], rtol=1e-6, atol=1e-6)
+    last_dones = torch.zeros(N)
+    for t in range(T):
+        o, r = nm.step(torch.as_tensor(g["obs_seq"][t + 1]), torch.as_tensor(g["rew_seq"][t]),
+                       torch.as_tensor(g["done_seq"][t]))
+        buf.add(last_obs, torch.as_tensor(g["acts"][t]), r, last_dones, torch.as_tensor(g["vals"][t]),
+                torch.as_tensor(g["logp"][t]))
+        last_obs, last_dones = o, torch.as_tensor(g["done_seq"][t]).float()
+        assert np.allclose(o.numpy(), g["norm_obs"][t + 1], rtol=2e-5, atol=2e-5), t
+        assert np.allclose(r.numpy(), g["norm_rew"][t], rtol=2e-5, atol=1e-6), t
+    assert np.allclose(nm.obs_rms.mean.numpy(), g["obs_mean"], rtol=1e-5, atol=1e-5)
+    assert np.allclose(nm.obs_rms.var.numpy(), g["obs_var"], rtol=1e-5)
+    assert np.isclose(float(nm.obs_rms.count), float(g["obs_count"])) and np.isclose(float(nm.ret_rms.count), float(g["ret_count"]))
+    assert np.isclose(float(nm.ret_rms.mean), float(g["ret_mean"]), rtol=1e-6) and np.isclose(float(nm.ret_rms.var), float(g["ret_var"]), rtol=1e-6)
+    assert np.allclose(nm.ret.numpy(), g["ret"], rtol=1e-6, atol=1e-6)
+    for mine, ref in ((buf.observations, "buf_obs"), (buf.actions, "buf_act"), (buf.rewards, "buf_rew"),
+                      (buf.dones, "buf_done"), (buf.values, "buf_val"), (buf.log_probs, "buf_logp")):
+        assert np.allclose(mine.numpy(), g[ref], rtol=2e-5, atol=2e-5), ref
+    assert np.allclose(buf.flat(buf.observations).numpy(), g["flat_obs"], rtol=2e-5, atol=2e-5)

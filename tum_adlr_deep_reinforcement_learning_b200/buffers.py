@@ -144,9 +144,11 @@ class DeviceVecNormalize:
         return r.clamp(-self.clip_reward, self.clip_reward).to(torch.float32)
 
     def reset(self, obs):
+        """vec_normalize.py:209-219: the return accumulators restart and, in training, the (all-zero) returns are fed
+        to ret_rms once; the observation statistics are NOT updated by a reset."""
         self.ret.zero_()
         if self.training:
-            self.obs_rms.update(obs)
+            self.ret_rms.update(self.ret)
         return self.normalize_obs(obs)
 
     def step(self, obs, rew, done):
@@ -172,3 +174,34 @@ class DeviceVecNormalize:
             rms.mean.copy_(sd[pre + "_mean"])
             rms.var.copy_(sd[pre + "_var"])
             rms.count.copy_(sd[pre + "_count"])
+
+
+def fused_post_step(norm, buf, obs_raw, rew_raw, done, actions, values, log_probs, last_obs, last_dones, run_ret,
+                    run_len, ep_stats, scratch):
+    """One step of rollout glue through fw_rollout_post_step (csrc/fw_ppo.cu): `norm` (DeviceVecNormalize) statistics
+    and return accumulators are updated, row `buf.pos` of `buf` (RolloutBuffer) receives the PREVIOUS observation /
+    done flags with this step's action, value, log-prob and normalised reward, `last_obs` / `last_dones` roll forward,
+    `run_ret` / `run_len` / `ep_stats` carry the Monitor-style episode totals.  All CUDA tensors; returns the tensors
+    that must stay alive until the launches have run."""
+    import ctypes
+    from . import _lib
+    t = buf.pos
+    tens = dict(obs_raw=obs_raw, rew_raw=rew_raw, done=done, actions=actions.contiguous(),
+                values=values.reshape(-1).contiguous(), log_probs=log_probs.reshape(-1).contiguous(),
+                last_obs=last_obs, last_dones=last_dones, ret=norm.ret, obs_mean=norm.obs_rms.mean,
+                obs_var=norm.obs_rms.var, obs_count=norm.obs_rms.count, ret_mean=norm.ret_rms.mean,
+                ret_var=norm.ret_rms.var, ret_count=norm.ret_rms.count, run_ret=run_ret, run_len=run_len,
+                ep_stats=ep_stats, buf_obs=buf.observations[t], buf_actions=buf.actions[t], buf_rewards=buf.rewards[t],
+                buf_dones=buf.dones[t], buf_values=buf.values[t], buf_log_probs=buf.log_probs[t], scratch=scratch)
+    assert all(v.is_cuda and v.is_contiguous() for v in tens.values())
+    assert scratch.numel() >= 3 * obs_raw.shape[1] + 3
+    p = _lib.FwRolloutPost(**{k: v.data_ptr() for k, v in tens.items()}, n=obs_raw.shape[0], obs_dim=obs_raw.shape[1],
+                           act_dim=actions.shape[1], gamma=norm.gamma, clip_obs=norm.clip_obs,
+                           clip_reward=norm.clip_reward, epsilon=norm.epsilon, norm_obs=int(norm.norm_obs),
+                           norm_reward=int(norm.norm_reward), training=int(norm.training))
+    _lib.check(_lib.lib().fw_rollout_post_step(ctypes.byref(p), ctypes.c_void_p(
+        torch.cuda.current_stream(obs_raw.device).cuda_stream)), "fw_rollout_post_step")
+    buf.pos += 1
+    if buf.pos == buf.buffer_size:
+        buf.full = True
+    return tens

@@ -291,31 +291,12 @@ class PPO:
         self._last_dones.copy_(done)
 
     def _fused_post_step(self, t, obs_raw, rew_raw, done, actions, values, log_probs):
-        """VecNormalize.step + RolloutBuffer.add + episode bookkeeping of one step in three launches
-        (fw_rollout_post_step, csrc/fw_ppo.cu) instead of ~70 tensor ops; same arithmetic (float64 statistics)."""
-        import ctypes
-        from . import _lib
-        nm, buf = self.norm, self.buffer
-        assert buf.pos == t
-        tens = dict(obs_raw=obs_raw, rew_raw=rew_raw, done=done, actions=actions.contiguous(),
-                    values=values.reshape(-1).contiguous(), log_probs=log_probs.reshape(-1).contiguous(),
-                    last_obs=self._last_obs, last_dones=self._last_dones, ret=nm.ret, obs_mean=nm.obs_rms.mean,
-                    obs_var=nm.obs_rms.var, obs_count=nm.obs_rms.count, ret_mean=nm.ret_rms.mean, ret_var=nm.ret_rms.var,
-                    ret_count=nm.ret_rms.count, run_ret=self._run_ret, run_len=self._run_len, ep_stats=self._ep_stats,
-                    buf_obs=buf.observations[t], buf_actions=buf.actions[t], buf_rewards=buf.rewards[t],
-                    buf_dones=buf.dones[t], buf_values=buf.values[t], buf_log_probs=buf.log_probs[t],
-                    scratch=self._post_scratch)
-        assert all(v.is_contiguous() for v in tens.values())
-        self._post_keep = tens                     # the launches are asynchronous: keep the temporaries alive
-        p = _lib.FwRolloutPost(**{k: v.data_ptr() for k, v in tens.items()}, n=self.n_envs, obs_dim=obs_raw.shape[1],
-                               act_dim=actions.shape[1], gamma=nm.gamma, clip_obs=nm.clip_obs, clip_reward=nm.clip_reward,
-                               epsilon=nm.epsilon, norm_obs=int(nm.norm_obs), norm_reward=int(nm.norm_reward),
-                               training=int(nm.training))
-        _lib.check(_lib.lib().fw_rollout_post_step(ctypes.byref(p), ctypes.c_void_p(
-            torch.cuda.current_stream(self.device).cuda_stream)), "fw_rollout_post_step")
-        buf.pos += 1
-        if buf.pos == buf.buffer_size:
-            buf.full = True
+        """VecNormalize.step + RolloutBuffer.add + episode bookkeeping of one step in a few launches
+        (buffers.fused_post_step -> fw_rollout_post_step) instead of ~70 tensor ops; float64 statistics."""
+        from .buffers import fused_post_step
+        self._post_keep = fused_post_step(self.norm, self.buffer, obs_raw, rew_raw, done, actions, values, log_probs,
+                                          self._last_obs, self._last_dones, self._run_ret, self._run_len,
+                                          self._ep_stats, self._post_scratch)
 
     def _rollout_body(self):
         self.buffer.reset()
