@@ -89,6 +89,8 @@ class _StubFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
             mod.Env, mod.GoalEnv, mod.Wrapper = Env, GoalEnv, Wrapper
         elif mod.__name__ == "gym.spaces":
             mod.Space, mod.Box = Space, Box
+        elif mod.__name__ == "gym.spaces.utils":
+            mod.flatdim = lambda space: int(np.prod(space.shape))
         elif mod.__name__ == "gym.utils.seeding":
             mod.np_random = lambda seed=None: (np.random.RandomState(seed), seed)
 
@@ -104,6 +106,7 @@ def install():
             sys.path.insert(0, os.path.join(_LIBS, sub))
         import gym  # noqa: F401
         import gym.spaces  # noqa: F401
+        import gym.spaces.utils  # noqa: F401
         import gym.utils.seeding  # noqa: F401
 
 

@@ -1,7 +1,7 @@
 """Generate the golden fixtures in this directory by running the UNMODIFIED reference where it lies.
 
 TEST INFRASTRUCTURE — run here (the build container, where /root/reference is mounted), never on the
-GPU box.  Usage:  python tests/golden/make_golden.py [params|traj|turb|fail|full|pid|gae|vecnorm|dryden|all]
+GPU box.  Usage:  python tests/golden/make_golden.py [params|traj|turb|fail|full|pid|gae|vecnorm|ppo_update|dryden|all]
 
 Everything is recorded through the reference's public surface:
   FixedWingAircraft.reset(state=, target=, turbulence_noise=) / .step(action)
@@ -621,6 +621,71 @@ def gen_vecnorm():
     np.savez_compressed(os.path.join(HERE, "vecnorm.npz"), **out)
 
 
+def gen_ppo_update():
+    """Three optimiser steps of the reference PPO.train() (ppo/ppo.py:133-240: evaluate_actions, advantage
+    normalisation, clipped surrogate, value MSE, entropy bonus, clip_grad_norm_ 0.5, Adam lr 3e-4 eps 1e-5) on a
+    hand-filled rollout buffer, one full-batch minibatch per call: weights before and after every step."""
+    import torch
+    from stable_baselines3 import PPO
+    from stable_baselines3.common.vec_env.base_vec_env import VecEnv
+    T, N, D = 32, 16, 14
+    obs_space = refshim.Box(-np.inf * np.ones(D), np.inf * np.ones(D), dtype=np.float32)
+    act_space = refshim.Box(-np.ones(3), np.ones(3), dtype=np.float32)
+
+    class Scripted(VecEnv):
+        def __init__(self):
+            VecEnv.__init__(self, N, obs_space, act_space)
+
+        def reset(self): return np.zeros((N, D), np.float32)
+        def step_async(self, actions): pass
+        def step_wait(self): return np.zeros((N, D), np.float32), np.zeros(N, np.float32), np.zeros(N, bool), [{} for _ in range(N)]
+        def close(self): pass
+        def get_attr(self, *a, **k): return [None] * N
+        def set_attr(self, *a, **k): pass
+        def env_method(self, *a, **k): return [None] * N
+        def seed(self, seed=None): return [None] * N
+
+    torch.manual_seed(0)
+    m = PPO("MlpPolicy", Scripted(), n_steps=T, batch_size=T * N, n_epochs=1, ent_coef=0.01, vf_coef=0.5,
+            max_grad_norm=0.5, learning_rate=3e-4, clip_range=0.2, device="cpu", verbose=0)
+    with torch.no_grad():                                  # spread the ratios on both sides of the clip range
+        m.policy.action_net.weight.mul_(40.0)
+        m.policy.log_std.copy_(torch.tensor([-0.3, 0.1, -0.8]))
+    rb = m.rollout_buffer
+    rs = np.random.RandomState(7)
+    rb.observations[:] = rs.standard_normal(rb.observations.shape)
+    rb.actions[:] = rs.uniform(-1, 1, rb.actions.shape)
+    rb.values[:] = rs.standard_normal(rb.values.shape)
+    rb.log_probs[:] = rs.standard_normal(rb.log_probs.shape) * 0.3 - 3.0
+    rb.advantages[:] = rs.standard_normal(rb.advantages.shape) * 2 + 0.5
+    rb.returns[:] = rs.standard_normal(rb.returns.shape)
+    rb.full, rb.pos = True, T
+    m._current_progress_remaining = 1.0
+    names = {"log_std": "log_std", "mlp_extractor.policy_net.0": "pi.0", "mlp_extractor.policy_net.2": "pi.2",
+             "mlp_extractor.value_net.0": "vf.0", "mlp_extractor.value_net.2": "vf.2", "action_net": "action_net",
+             "value_net": "value_net"}
+
+    def weights(tag):
+        o = {}
+        for k, v in m.policy.state_dict().items():
+            base, _, leaf = k.rpartition(".")
+            mine = names[k] if k in names else names[base] + "." + leaf
+            o["%s/%s" % (tag, mine)] = v.detach().numpy().copy()
+        return o
+
+    out = dict(obs=rb.observations.reshape(T * N, D).copy(), act=rb.actions.reshape(T * N, 3).copy(),
+               old_values=rb.values.reshape(-1).copy(), old_log_prob=rb.log_probs.reshape(-1).copy(),
+               adv=rb.advantages.reshape(-1).copy(), ret=rb.returns.reshape(-1).copy())
+    out.update(weights("w0"))
+    with torch.no_grad():
+        v, lp, ent = m.policy.evaluate_actions(torch.as_tensor(out["obs"]), torch.as_tensor(out["act"]))
+    out.update(eval_values=v.numpy().reshape(-1), eval_log_prob=lp.numpy(), eval_entropy=ent.numpy())
+    for k in (1, 2, 3):
+        m.train()
+        out.update(weights("w%d" % k))
+    np.savez_compressed(os.path.join(HERE, "ppo_update.npz"), **out)
+
+
 def gen_dryden():
     """Reference Dryden output for injected noise, for the gym parameterisation (dt<-2000, b<-0.01, h<-2.1;
     pyfly.py:781-783 vs dryden.py:52) and for raw pyfly (sim_length 300), all three intensities."""
@@ -650,7 +715,7 @@ def gen_dryden():
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     jobs = {"waypoint": gen_waypoint, "targets": gen_targets, "reward": gen_reward, "cnn": gen_cnn, "params": gen_params, "traj": gen_traj, "turb": gen_turb, "fail": gen_fail, "full": gen_full,
-            "pid": gen_pid, "gae": gen_gae, "vecnorm": gen_vecnorm, "dryden": gen_dryden}
+            "pid": gen_pid, "gae": gen_gae, "vecnorm": gen_vecnorm, "ppo_update": gen_ppo_update, "dryden": gen_dryden}
     for name, fn in jobs.items():
         if what in (name, "all"):
             t0 = time.time()

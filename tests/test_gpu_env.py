@@ -628,3 +628,29 @@ def test_fused_rollout_glue_matches_the_reference_fixture(cuda_device):
     # episode totals of the raw rewards (Monitor): finished episodes only
     ends = g["done_seq"].sum()
     assert float(ep[2]) == float(ends)
+
+
+def test_fused_ppo_update_matches_the_reference_fixture(cuda_device):
+    """Three optimiser steps through the fused path (fw_ppo_loss -> autograd through the PyTorch MLPs ->
+    fw_adam_clip_step on the flat parameter buffer) against the live reference's PPO.train()
+    (tests/golden/ppo_update.npz: weights after every step)."""
+    import torch
+    from test_host_parallel import _load_ppo_fixture_into, _ppo_fixture_batch
+    from tum_adlr_deep_reinforcement_learning_b200.ppo import ActorCritic, FlatAdam, FusedPPOLoss
+    g = load_golden("ppo_update")
+    pol = ActorCritic().cuda()
+    _load_ppo_fixture_into(pol, g, "w0")
+    opt = FlatAdam(pol, lr=3e-4, eps=1e-5, max_grad_norm=0.5)
+    b = _ppo_fixture_batch(g, "cuda")
+    for k in (1, 2, 3):
+        mean = pol.action_net(pol.pi(b.observations))
+        values = pol.value_net(pol.vf(b.observations)).squeeze(-1)
+        loss, parts = FusedPPOLoss.apply(mean, values, pol.log_std, b.actions, b.old_log_prob, b.advantages, b.returns,
+                                         0.2, 0.01, 0.5)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        for name, p in pol.named_parameters():
+            ref = g["w%d/%s" % (k, name)]
+            err = np.abs(p.detach().cpu().numpy() - ref).max()
+            assert err <= 2e-6 + 1e-5 * np.abs(ref - g["w0/" + name]).max(), (k, name, err)

@@ -205,3 +205,47 @@ def test_vecnormalize_and_rollout_buffer_match_the_reference():
                       (buf.dones, "buf_done"), (buf.values, "buf_val"), (buf.log_probs, "buf_logp")):
         assert np.allclose(mine.numpy(), g[ref], rtol=2e-5, atol=2e-5), ref
     assert np.allclose(buf.flat(buf.observations).numpy(), g["flat_obs"], rtol=2e-5, atol=2e-5)
+
+
+def _load_ppo_fixture_into(policy, g, tag):
+    import torch
+    with torch.no_grad():
+        for name, p in policy.named_parameters():
+            p.copy_(torch.as_tensor(g["%s/%s" % (tag, name)]).to(p.device))
+
+
+def _ppo_fixture_batch(g, device):
+    import torch
+    from tum_adlr_deep_reinforcement_learning_b200.buffers import RolloutBufferSamples
+    t = lambda k: torch.as_tensor(g[k]).to(device)
+    return RolloutBufferSamples(t("obs"), t("act"), t("old_values"), t("old_log_prob"), t("adv"), t("ret"))
+
+
+def test_ppo_policy_and_update_match_the_reference_on_cpu():
+    """ppo.ActorCritic.evaluate_actions and three PPO minibatch updates (tensor-op loss, clip_grad_norm_, torch Adam)
+    against the live reference's ActorCriticPolicy / PPO.train() (tests/golden/ppo_update.npz)."""
+    import torch
+    from tum_adlr_deep_reinforcement_learning_b200.ppo import ActorCritic
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ppo_update.npz"))
+    pol = ActorCritic()
+    _load_ppo_fixture_into(pol, g, "w0")
+    batch = _ppo_fixture_batch(g, "cpu")
+    with torch.no_grad():
+        v, lp, ent = pol.evaluate_actions(batch.observations, batch.actions)
+    assert np.allclose(v.numpy(), g["eval_values"], rtol=1e-5, atol=1e-5)
+    assert np.allclose(lp.numpy(), g["eval_log_prob"], rtol=1e-5, atol=1e-4)
+    assert np.allclose(ent.numpy(), g["eval_entropy"], rtol=1e-6)
+    opt = torch.optim.Adam(pol.parameters(), lr=3e-4, eps=1e-5)
+    for k in (1, 2, 3):
+        values, log_prob, entropy = pol.evaluate_actions(batch.observations, batch.actions)
+        adv = (batch.advantages - batch.advantages.mean()) / (batch.advantages.std() + 1e-8)
+        ratio = torch.exp(log_prob - batch.old_log_prob)
+        policy_loss = -torch.min(adv * ratio, adv * torch.clamp(ratio, 0.8, 1.2)).mean()
+        loss = policy_loss + 0.01 * (-entropy.mean()) + 0.5 * torch.nn.functional.mse_loss(batch.returns, values)
+        opt.zero_grad()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(pol.parameters(), 0.5)
+        opt.step()
+        for name, p in pol.named_parameters():
+            ref = g["w%d/%s" % (k, name)]
+            assert np.abs(p.detach().numpy() - ref).max() <= 2e-6 + 1e-5 * np.abs(ref - g["w0/" + name]).max(), (k, name)
