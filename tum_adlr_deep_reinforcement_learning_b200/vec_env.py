@@ -127,7 +127,7 @@ class FixedWingVecEnv:
         self._waiting = False
         self._t_start = time.time()
         self.h2d_bytes_per_step = self._act_pin.numel() * 4
-        self.d2h_bytes_per_step = n * self.sim.obs_dim * 4 + n * 4 + n
+        self.d2h_bytes_per_step = self.sim.out_nbytes        # obs | rew | done | episode-end rows, one copy
 
     def pinned_actions(self, count=1):
         """`count` float32 [num_envs, 3] arrays in page-locked host memory.  step() copies an array of this kind to the
