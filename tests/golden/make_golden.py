@@ -1,7 +1,7 @@
 """Generate the golden fixtures in this directory by running the UNMODIFIED reference where it lies.
 
 TEST INFRASTRUCTURE — run here (the build container, where /root/reference is mounted), never on the
-GPU box.  Usage:  python tests/golden/make_golden.py [params|traj|turb|fail|full|pid|gae|vecnorm|ppo_update|dryden|all]
+GPU box.  Usage:  python tests/golden/make_golden.py [params|traj|turb|fail|full|pid|gae|vecnorm|ppo_update|curriculum|dryden|all]
 
 Everything is recorded through the reference's public surface:
   FixedWingAircraft.reset(state=, target=, turbulence_noise=) / .step(action)
@@ -686,6 +686,27 @@ def gen_ppo_update():
     np.savez_compressed(os.path.join(HERE, "ppo_update.npz"), **out)
 
 
+def gen_curriculum():
+    """set_curriculum_level (fixed_wing.py:334-412) on the default config and on the dev config: initial-state
+    ranges of the simulator and target ranges, for several levels."""
+    out = {}
+    dev = os.path.join(os.path.dirname(refshim.GYM_CONFIG), "fixed_wing_config_dev.json")
+    for tag, path in (("default", refshim.GYM_CONFIG), ("dev", dev)):
+        env = FixedWingAircraft(path, config_kw={}, sim_config_kw={"turbulence": False})
+        for level in (0.0, 0.25, 0.6, 1.0):
+            env.set_curriculum_level(level)
+            s = env.simulator.state
+            lo = [float(s[k].init_min) if s[k].init_min is not None else np.nan for k in STATE_KEYS]
+            hi = [float(s[k].init_max) if s[k].init_max is not None else np.nan for k in STATE_KEYS]
+            tp = env._target_props_init["states"]
+            conv = lambda st, v: np.radians(v) if tp[st].get("convert_to_radians", False) else v
+            key = "%s_%g" % (tag, level)
+            out[key + "_init_lo"], out[key + "_init_hi"] = np.array(lo), np.array(hi)
+            for f in ("low", "high", "delta"):
+                out[key + "_tgt_" + f] = np.array([conv(st, tp[st][f]) for st in TARGET_KEYS], dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, "curriculum.npz"), **out)
+
+
 def gen_dryden():
     """Reference Dryden output for injected noise, for the gym parameterisation (dt<-2000, b<-0.01, h<-2.1;
     pyfly.py:781-783 vs dryden.py:52) and for raw pyfly (sim_length 300), all three intensities."""
@@ -715,7 +736,7 @@ def gen_dryden():
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     jobs = {"waypoint": gen_waypoint, "targets": gen_targets, "reward": gen_reward, "cnn": gen_cnn, "params": gen_params, "traj": gen_traj, "turb": gen_turb, "fail": gen_fail, "full": gen_full,
-            "pid": gen_pid, "gae": gen_gae, "vecnorm": gen_vecnorm, "ppo_update": gen_ppo_update, "dryden": gen_dryden}
+            "pid": gen_pid, "gae": gen_gae, "vecnorm": gen_vecnorm, "ppo_update": gen_ppo_update, "curriculum": gen_curriculum, "dryden": gen_dryden}
     for name, fn in jobs.items():
         if what in (name, "all"):
             t0 = time.time()

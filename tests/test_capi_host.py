@@ -117,3 +117,16 @@ def test_oracle_observation_noise_statistics():
     d = noisy - clean                       # same Philox reset stream -> identical states, only the noise differs
     assert abs(d.mean() - 0.5) < 0.005 and abs(d.std() - 0.1) < 0.005
     assert abs(np.corrcoef(d[:, 0], d[:, 1])[0, 1]) < 0.06
+
+
+def test_curriculum_scaling_matches_the_reference():
+    """build_config(curriculum_level=L) against the live reference's set_curriculum_level (tests/golden/curriculum.npz,
+    make_golden.py curriculum): initial-state ranges and target low / high / delta of the default config at four
+    levels (position_d keeps its reversed -20 .. -100 range, yaw its constraint-free +-30 deg)."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "curriculum.npz"))
+    for level in (0.0, 0.25, 0.6, 1.0):
+        key = "default_%g" % level
+        c = C.build_config(curriculum_level=level)
+        for mine, ref in ((c.init_lo, "_init_lo"), (c.init_hi, "_init_hi"), (c.tgt_low, "_tgt_low"),
+                          (c.tgt_high, "_tgt_high"), (c.tgt_delta, "_tgt_delta")):
+            assert np.allclose(list(mine), g[key + ref], rtol=1e-12, atol=1e-12), (key, ref, list(mine), g[key + ref])
