@@ -704,6 +704,8 @@ def gen_curriculum():
             out[key + "_init_lo"], out[key + "_init_hi"] = np.array(lo), np.array(hi)
             for f in ("low", "high", "delta"):
                 out[key + "_tgt_" + f] = np.array([conv(st, tp[st][f]) for st in TARGET_KEYS], dtype=np.float64)
+        out[tag + "_obs_low"], out[tag + "_obs_high"] = env.observation_space.low, env.observation_space.high
+        out[tag + "_act_low"], out[tag + "_act_high"] = env.action_space.low, env.action_space.high
     np.savez_compressed(os.path.join(HERE, "curriculum.npz"), **out)
 
 

@@ -130,3 +130,15 @@ def test_curriculum_scaling_matches_the_reference():
         for mine, ref in ((c.init_lo, "_init_lo"), (c.init_hi, "_init_hi"), (c.tgt_low, "_tgt_low"),
                           (c.tgt_high, "_tgt_high"), (c.tgt_delta, "_tgt_delta")):
             assert np.allclose(list(mine), g[key + ref], rtol=1e-12, atol=1e-12), (key, ref, list(mine), g[key + ref])
+
+
+def test_spaces_match_the_reference():
+    """observation_space / action_space bounds of the default env (fixed_wing.py:92-140, 245-258)."""
+    from tum_adlr_deep_reinforcement_learning_b200.config import observation_bounds
+    g = np.load(os.path.join(ROOT, "tests", "golden", "curriculum.npz"))
+    lo, hi = observation_bounds(cfg=C.build_config())
+    assert np.array_equal(np.asarray(lo, np.float32), g["default_obs_low"])
+    assert np.array_equal(np.asarray(hi, np.float32), g["default_obs_high"])
+    f32max = np.finfo(np.float32).max
+    assert np.array_equal(g["default_act_low"], np.full(3, -f32max, np.float32))
+    assert np.array_equal(g["default_act_high"], np.full(3, f32max, np.float32))
