@@ -133,6 +133,19 @@ MOVING_TARGETS = [
     {"name": "Va", "low": 15, "high": 28, "delta": 6, "class": "compensate", "bound": 2}]
 
 
+def resample_env_config():
+    """Default target classes with periodic and on-success resampling (fixed_wing.py:536-580): wide goal bounds so
+    that the 5-step success streak is reached."""
+    import copy
+    from tum_adlr_deep_reinforcement_learning_b200.config import default_env_config
+    cfg = copy.deepcopy(default_env_config())
+    cfg["steps_max"] = 150
+    cfg["target"].update(resample_every=37, on_success="new", success_streak_req=5, success_streak_fraction=0.6)
+    for st, b in zip(cfg["target"]["states"], (80, 50, 15)):
+        st["bound"] = b
+    return cfg
+
+
 def moving_targets_env_config():
     from tum_adlr_deep_reinforcement_learning_b200.config import default_env_config
     cfg = default_env_config()

@@ -345,6 +345,42 @@ def gen_targets():
     np.savez_compressed(os.path.join(HERE, "traj_moving_targets.npz"), **out)
 
 
+def gen_resample():
+    """resample_every and on_success = "new" (fixed_wing.py:536-580, 654-746) with the default target classes: the
+    env-level RNG is replaced by fixed draws u (as in gen_targets), targets are sampled, not injected."""
+    import tempfile
+    from conftest import resample_env_config
+    with tempfile.NamedTemporaryFile("w", suffix=".json", delete=False) as f:
+        json.dump(resample_env_config(), f)
+    out = {}
+    for tag, u in (("a", 0.41), ("b", 0.83)):
+        env = make_env(False, config_path=f.name)
+        env.np_random = FixedDrawsU(u)
+        rs = np.random.RandomState(int(u * 1000))
+        rec = {k: [] for k in ("init_state", "actions", "target", "obs", "reward", "obs0", "target0", "done")}
+        for ep in range(3):
+            st, _ = random_scenario(rs, 3.0)
+            obs0 = env.reset(state=dict(st))
+            rec["init_state"].append(scenario_arrays(st, {"roll": 0, "pitch": 0, "Va": 0})[0])
+            rec["obs0"].append(np.array(obs0))
+            rec["target0"].append([env.target[k] for k in TARGET_KEYS])
+            A, Tg, Ob, Rw, Dn = [], [], [], [], []
+            for t in range(150):
+                a = rs.uniform(-0.6, 0.6, 3)
+                obs, rew, done, info = env.step(a)
+                A.append(a), Tg.append([env.target[k] for k in TARGET_KEYS]), Ob.append(np.array(obs)), Rw.append(rew)
+                Dn.append(done)
+                if done:
+                    break
+            n = len(A)
+            pad = lambda v, w: np.concatenate([np.array(v, dtype=np.float64).reshape(n, -1), np.full((150 - n, w), np.nan)])
+            rec["actions"].append(pad(A, 3)); rec["target"].append(pad(Tg, 3)); rec["obs"].append(pad(Ob, 14))
+            rec["reward"].append(pad(Rw, 1)[:, 0]); rec["done"].append(np.array(Dn + [False] * (150 - n)))
+        out.update({tag + "_" + k: np.array(v) for k, v in rec.items()})
+        out[tag + "_u"] = u
+    np.savez_compressed(os.path.join(HERE, "traj_resample.npz"), **out)
+
+
 def gen_waypoint():
     """FixedWingAircraft_simple (magpie/magpy/simple_train.py:197-702), the waypoint env head.  The class is taken
     from the reference file where it lies; PyFly is constructed with turbulence off and the waypoints carry explicit
@@ -737,7 +773,7 @@ def gen_dryden():
 
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
-    jobs = {"waypoint": gen_waypoint, "targets": gen_targets, "reward": gen_reward, "cnn": gen_cnn, "params": gen_params, "traj": gen_traj, "turb": gen_turb, "fail": gen_fail, "full": gen_full,
+    jobs = {"waypoint": gen_waypoint, "targets": gen_targets, "resample": gen_resample, "reward": gen_reward, "cnn": gen_cnn, "params": gen_params, "traj": gen_traj, "turb": gen_turb, "fail": gen_fail, "full": gen_full,
             "pid": gen_pid, "gae": gen_gae, "vecnorm": gen_vecnorm, "ppo_update": gen_ppo_update, "curriculum": gen_curriculum, "dryden": gen_dryden}
     for name, fn in jobs.items():
         if what in (name, "all"):

@@ -274,6 +274,29 @@ def test_moving_target_classes(cuda_device):
     env.close()
 
 
+def test_target_resampling_against_reference(cuda_device):
+    """resample_every / on_success = "new" on the CUDA path against the live-reference fixture (fixed draws u)."""
+    import torch
+    from conftest import resample_env_config
+    from tum_adlr_deep_reinforcement_learning_b200 import batched as bt
+    from tum_adlr_deep_reinforcement_learning_b200.config import build_config
+    g = load_golden("traj_resample")
+    for tag in ("a", "b"):
+        cfg = build_config(env_cfg=resample_env_config(), sim_config_kw={"turbulence": False},
+                           rng_u_override=float(g[tag + "_u"]))
+        env = bt.BatchedFixedWing(3, cfg=cfg)
+        env.enable_f64_outputs()
+        env.reset(state=g[tag + "_init_state"])
+        assert np.abs(env.get_field(bt.FIELD_TARGET).cpu().numpy() - g[tag + "_target0"]).max() < 1e-12
+        assert np.isfinite(g[tag + "_reward"]).all()       # no episode of the fixture ends early
+        for t in range(150):
+            env.step(torch.as_tensor(g[tag + "_actions"][:, t]).cuda().contiguous(), auto_reset=False)
+            assert _rel(env.get_field(bt.FIELD_TARGET).cpu().numpy(), g[tag + "_target"][:, t]).max() < 1e-11, (tag, t)
+            assert _rel(env.obs64.cpu().numpy(), g[tag + "_obs"][:, t]).max() < RTOL_F64
+            assert _rel(env.rew64.cpu().numpy(), g[tag + "_reward"][:, t]).max() < RTOL_F64
+        env.close()
+
+
 def test_full_size_batch_properties(cuda_device):
     """BASELINE.json's C3 size (65 536 envs on one GPU, turbulence, auto-reset), checked through properties that do not
     depend on the size: (1) every env's trajectory is independent of the batch it runs in — a 192-env slice of the big

@@ -213,6 +213,35 @@ def test_oracle_moving_target_classes():
                 assert abs(rew - g[tag + "_reward"][ep, t]) < 1e-9
 
 
+def test_oracle_target_resampling_against_reference():
+    """resample_every = 37 and on_success = "new" (5-step streak) with the default target classes, against a
+    live-reference run whose env-level RNG was replaced by fixed draws u (make_golden.py:gen_resample): target
+    trajectories incl. the Va-compensate law restarting after every resample, observations, rewards."""
+    from conftest import resample_env_config
+    g = load_golden("traj_resample")
+    for tag in ("a", "b"):
+        cfg = build_config(env_cfg=resample_env_config(), sim_config_kw={"turbulence": False},
+                           rng_u_override=float(g[tag + "_u"]))
+        assert cfg.resample_every == 37 and cfg.on_success == 2 and cfg.streak_req == 5
+        jumps = 0
+        for ep in range(3):
+            env = O.OracleEnv(cfg)
+            obs = env.reset(g[tag + "_init_state"][ep])
+            assert np.abs(env.get()["target"] - g[tag + "_target0"][ep]).max() < 1e-12
+            assert np.abs(obs - g[tag + "_obs0"][ep]).max() < 1e-12
+            prev = g[tag + "_target0"][ep]
+            for t in range(150):
+                if not np.isfinite(g[tag + "_reward"][ep, t]):
+                    break
+                obs, rew, done, term = env.step(g[tag + "_actions"][ep, t])
+                assert _rel(env.get()["target"], g[tag + "_target"][ep, t]).max() < 1e-11, (tag, ep, t)
+                assert _rel(obs, g[tag + "_obs"][ep, t]).max() < 1e-9
+                assert abs(rew - g[tag + "_reward"][ep, t]) < 1e-9
+                jumps += int(abs(g[tag + "_target"][ep, t, 2] - prev[2]) > 0.05)
+                prev = g[tag + "_target"][ep, t]
+        assert jumps >= 6                                  # the fixture does exercise resampling
+
+
 def test_dryden_block_restart_matches_reference():
     """pyfly re-simulates turbulence every turbulence_sim_length samples (300 for raw pyfly / the waypoint env); lsim then
     restarts from T[0] > 0 and decays the carried state over [0, T[0]] first."""
