@@ -381,6 +381,24 @@ def main():
                        "n_gpus > 1 (NCCL, captured in the update graph); learning curves in results/"}
         venv.close()
 
+    # ---- SAC (BASELINE.json config C5: 1024 envs, replay ring in HBM, turbulence on), N = 1 only ----
+    sac = None
+    if not args.no_extra and world == 1:
+        from tum_adlr_deep_reinforcement_learning_b200.sac import SAC
+        venv = FixedWingVecEnv(1024, sim_config_kw={"turbulence": True}, device=local, seed=0)
+        salgo = SAC(venv, buffer_size=1_000_000, batch_size=4096, gradient_steps=2, learning_starts=10_000)
+        salgo.learn(total_timesteps=40 * 1024)                          # warm-up: random phase, graph captures
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n0 = salgo.num_timesteps
+        salgo.learn(total_timesteps=n0 + 1500 * 1024, log_every=10 ** 9)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        sac = {"value": (salgo.num_timesteps - n0) / dt, "unit": "env-steps/s (1 env step of 1024 envs + 2 gradient steps of batch 4096)",
+               "gradient_steps_per_s": 2 * (salgo.num_timesteps - n0) / 1024 / dt, "envs": 1024, "replay_capacity": 1_000_000,
+               "note": "env step and gradient step replayed as CUDA graphs; networks 2x256 ReLU in PyTorch"}
+        venv.close()
+
     # ---- CPU baseline (rank 0 only, N = 1 only) ----
     cpu = None
     if rank == 0 and world == 1:
@@ -393,7 +411,7 @@ def main():
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": workload_config(n), "roofline": roofline,
                 "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 4 * K, "gpu_launches_note": "rk45_init_kernel + rk45_attempt_kernel + head_kernel per step on the launch stream, refill_kernel on the side stream",
-                "clocks": clocks, "modes": extra, "ppo": ppo}
+                "clocks": clocks, "modes": extra, "ppo": ppo, "sac": sac}
         print(json.dumps(line), flush=True)
     if world > 1:
         # CUDA graphs that contain NCCL kernels (the PPO update) are alive until interpreter shutdown, and
