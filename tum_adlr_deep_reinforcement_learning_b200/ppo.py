@@ -36,8 +36,9 @@ class _LinearSplitK(torch.autograd.Function):
         x, weight = ctx.saved_tensors
         g = g.contiguous()
         B = x.shape[0]
+        # row chunks: as many as keep the partial sums [S, out, in] small (2 M elements) and divide the batch
         S = 128
-        while S > 1 and B % S:
+        while S > 1 and (B % S or S * weight.numel() > (1 << 21)):
             S //= 2
         gi = g @ weight if ctx.needs_input_grad[0] else None
         gs = g.view(S, B // S, g.shape[1])

@@ -91,11 +91,12 @@ class ReplayBuffer:
 
 
 def _mlp(inp, out, hidden=(256, 256)):
+    from .ppo import SplitKLinear          # nn.Linear whose weight gradient is a split-K bmm for large batches
     layers, d = [], inp
     for h in hidden:
-        layers += [nn.Linear(d, h), nn.ReLU()]
+        layers += [SplitKLinear(d, h), nn.ReLU()]
         d = h
-    layers.append(nn.Linear(d, out))
+    layers.append(SplitKLinear(d, out))
     return nn.Sequential(*layers)
 
 
@@ -262,9 +263,10 @@ class SAC:
         self.actor_opt.zero_grad(set_to_none=not capturable)
         actor_loss.backward()
         self.actor_opt.step()
-        with torch.no_grad():
-            for p, pt in zip(self.critic.parameters(), self.critic_target.parameters()):
-                pt.mul_(1 - self.tau).add_(p, alpha=self.tau)
+        with torch.no_grad():                                   # polyak update, two launches for all tensors
+            src, dst = list(self.critic.parameters()), list(self.critic_target.parameters())
+            torch._foreach_mul_(dst, 1 - self.tau)
+            torch._foreach_add_(dst, src, alpha=self.tau)
         return critic_loss.detach(), actor_loss.detach(), ent_coef.reshape(())
 
     def learn(self, total_timesteps, log_every=50, callback=None):
