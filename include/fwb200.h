@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define FW_ABI_VERSION 7
+#define FW_ABI_VERSION 8
 
 #define FW_NY 19        /* ODE state: quat[4] omega[3] pos[3] vel[3] act_value[3] act_rate[3]  (pyfly.py:1372-1389) */
 #define FW_NOBS 14      /* default observation vector (fixed_wing_config.json "observation.states")               */
@@ -223,6 +223,17 @@ typedef struct FwHandle FwHandle;
 int fw_create(const FwConfig* cfg, int32_t n_envs, int32_t device, FwHandle** out);
 int fw_destroy(FwHandle* h);
 int fw_obs_dim(const FwHandle* h);   /* floats per observation row of this handle */
+
+/* Replaces: FixedWingAircraft.set_curriculum_level (fixed_wing.py:334-412) and FixedWingAircraft.seed (:324-332) on a
+ * LIVE handle, as the reference's training scripts call them in the middle of a run
+ * (examples/train_rl_controller.py:137, env_method("set_curriculum_level", ...)).  `cfg` must equal the handle's
+ * configuration except for the reset-time fields: init_lo / init_hi, wind_mag_min / wind_mag_max, tgt_low / tgt_high /
+ * tgt_delta, the tgt_slope / tgt_amp / tgt_period ranges and seed (anything else: FW_EINVAL).  The new values apply to
+ * every reset and target resampling from now on; episodes that are running keep their state, their turbulence stream
+ * and their Philox key (an episode is keyed by the seed in force when it was reset).  Device pointers of the handle
+ * do not change, so CUDA graphs captured over fw_step stay valid.  Asynchronous on `stream` (not during capture):
+ * the precomputed next-episode rows are recomputed there. */
+int fw_set_config(FwHandle* h, const FwConfig* cfg, void* stream);
 
 /* Measurement aid (no reference counterpart; bench.py's per-kernel roofline): with profiling on, every fw_step /
  * fw_step_random step records CUDA events on the launch stream around each of its kernels and ends with an event

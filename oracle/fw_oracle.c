@@ -78,6 +78,7 @@ typedef struct FwoEnv {
     int term_code;
     int last_nfev, last_natt;
     uint64_t episode;
+    uint64_t ep_seed;      /* Philox key of the running episode: cfg.seed when it was reset (fwo_set_config) */
     int64_t env_id;
 } FwoEnv;
 
@@ -114,7 +115,7 @@ static double u53(uint32_t hi, uint32_t lo) {
 
 static double rng_uniform(const FwoEnv* e, uint32_t purpose, int idx) {
     uint32_t r[4];
-    rng_block(e->cfg.seed, e->env_id, e->episode, purpose, (uint32_t)(idx >> 1), r);
+    rng_block(e->ep_seed, e->env_id, e->episode, purpose, (uint32_t)(idx >> 1), r);
     return (idx & 1) ? u53(r[2], r[3]) : u53(r[0], r[1]);
 }
 
@@ -620,7 +621,7 @@ static void target_draws(const FwoEnv* e, uint32_t purpose, uint32_t block0, dou
     for (int i = 0; i < 12; ++i) {
         if (!isnan(c->rng_u_override)) { u12[i] = c->rng_u_override; continue; }
         uint32_t r[4];
-        rng_block(c->seed, e->env_id, e->episode, purpose, block0 + (uint32_t)(i >> 1), r);
+        rng_block(e->ep_seed, e->env_id, e->episode, purpose, block0 + (uint32_t)(i >> 1), r);
         u12[i] = (i & 1) ? u53(r[2], r[3]) : u53(r[0], r[1]);
     }
 }
@@ -678,7 +679,7 @@ static void add_obs_noise(const FwoEnv* e, double* obs, int dim) {
     if (!(c->obs_noise_std > 0) && c->obs_noise_mean == 0) return;
     for (int b = 0; b * 4 < dim; ++b) {
         uint32_t r[4];
-        rng_block(c->seed, e->env_id, e->episode, FWO_RNG_OBS, (uint32_t)(e->steps_count * 32 + b), r);
+        rng_block(e->ep_seed, e->env_id, e->episode, FWO_RNG_OBS, (uint32_t)(e->steps_count * 32 + b), r);
         for (int i = 0; i < 2; ++i) {
             double u1 = ((double)r[2 * i] + 0.5) * (1.0 / 4294967296.0);
             double u2 = ((double)r[2 * i + 1] + 0.5) * (1.0 / 4294967296.0);
@@ -729,7 +730,7 @@ static void get_observation_generic(const FwoEnv* e, double* obs) {
                 if (!isnan(c->obs_init_noise)) u = c->obs_init_noise;
                 else {
                     uint32_t r[4];
-                    rng_block(c->seed, e->env_id, e->episode, FWO_RNG_OBS_INIT, (uint32_t)(e->steps_count * 8 + (i - 1)), r);
+                    rng_block(e->ep_seed, e->env_id, e->episode, FWO_RNG_OBS_INIT, (uint32_t)(e->steps_count * 8 + (i - 1)), r);
                     u = 2.0 * u53(r[0], r[1]) - 1.0;
                 }
                 init_noise = u * c->dt;
@@ -1007,7 +1008,7 @@ static void gen_turbulence(FwoEnv* e, const double* noise, int noise_len) {
     for (int k = 0; k < L; ++k) {
         double n4[4];
         if (noise) for (int r = 0; r < 4; ++r) n4[r] = noise[(size_t)r * noise_len + (k < noise_len ? k : noise_len - 1)];
-        else fwo_noise4(c->seed, e->env_id, e->episode, (uint32_t)k, n4);
+        else fwo_noise4(e->ep_seed, e->env_id, e->episode, (uint32_t)k, n4);
         for (int r = 0; r < 4; ++r) nz[(size_t)r * L + k] = n4[r];
     }
     fwo_dryden(c, nz, L, e->turb);
@@ -1022,6 +1023,7 @@ static void gen_turbulence(FwoEnv* e, const double* noise, int noise_len) {
 static void wp_sim_reset(FwoEnv* e, const double* row) {
     const FwConfig* c = &e->cfg;
     e->episode += 1;                     /* a fresh Philox segment for omega and the turbulence noise */
+    e->ep_seed = e->cfg.seed;
     e->cur_sim_step = 0;
     for (int i = 0; i < 3; ++i) { e->pos[i] = row[i]; e->vel[i] = row[6 + i]; e->wind[i] = row[9 + i]; }
     e->roll = row[3]; e->pitch = row[4]; e->yaw = row[5];
@@ -1107,6 +1109,7 @@ void fwo_reset(FwoEnv* e, const double* state, const double* target, const doubl
     const FwConfig* c = &e->cfg;
     if (c->env_kind == FW_ENV_WAYPOINT) { wp_reset(e, obs); return; }
     e->episode += 1;
+    e->ep_seed = c->seed;
     e->steps_count = 0;
     e->cur_sim_step = 0;
     double s12[12];
@@ -1313,6 +1316,13 @@ void fwo_batch_destroy(FwoBatch* b) {
     free(b->envs); free(b);
 }
 FwoEnv* fwo_batch_env(FwoBatch* b, int i) { return b->envs[i]; }
+
+/* set_curriculum_level / seed on a live env (fixed_wing.py:324-412): the new ranges and seed serve every later reset
+ * and target resampling; the running episode keeps its state, turbulence table and Philox key (ep_seed). */
+void fwo_set_config(FwoEnv* e, const FwConfig* cfg) { e->cfg = *cfg; }
+void fwo_batch_set_config(FwoBatch* b, const FwConfig* cfg) {
+    for (int i = 0; i < b->n; ++i) fwo_set_config(b->envs[i], cfg);
+}
 
 void fwo_batch_reset(FwoBatch* b, double* obs) {
     for (int i = 0; i < b->n; ++i) fwo_reset(b->envs[i], NULL, NULL, NULL, 0, obs + (size_t)i * b->od);

@@ -53,6 +53,8 @@ def lib():
         L.fwo_batch_create.restype = ctypes.c_void_p
         L.fwo_batch_create.argtypes = [ctypes.POINTER(FwConfig), ctypes.c_int]
         L.fwo_batch_destroy.argtypes = [ctypes.c_void_p]
+        L.fwo_batch_set_config.argtypes = [ctypes.c_void_p, ctypes.POINTER(FwConfig)]
+        L.fwo_set_config.argtypes = [ctypes.c_void_p, ctypes.POINTER(FwConfig)]
         L.fwo_batch_env.restype = ctypes.c_void_p
         L.fwo_batch_env.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.fwo_batch_reset.argtypes = [ctypes.c_void_p, _dp]
@@ -196,6 +198,10 @@ class OracleBatch:
         toe = np.ascontiguousarray(task_of_env, dtype=np.int32)
         lib().fwo_batch_set_waypoint_tasks(self._h, _p(self._tasks), self._tasks.shape[0], self._tasks.shape[1],
                                            _p(toe, _i32p))
+
+    def set_config(self, cfg):
+        """Live change of the reset-time configuration (the oracle's fw_set_config)."""
+        lib().fwo_batch_set_config(self._h, ctypes.byref(cfg))
 
     def reset(self):
         lib().fwo_batch_reset(self._h, _p(self.obs))

@@ -5,8 +5,10 @@ neither of which is installed in this image.  This module fabricates just enough
 `pyfly`, `gym_fixed_wing` and the stable-baselines3 fork to import and run unmodified from where they
 lie, so that `tests/golden/make_golden.py` can record golden input/output vectors.
 
-`/root/reference` does not exist on the GPU box: nothing under `tests/ -m gpu`, `bench.py` or
-`__graft_entry__.smoke()` imports this file.
+`/root/reference` does not exist on the GPU box.  There the same unmodified libraries are found in the mirror
+`baseline/_ref/` (git-ignored; written by `baseline/install_ref.py`, travels with the gpurun snapshot), which lets
+`bench.py`'s reference legs time the Python reference on the box's host cores and the drop-in tests run the fork's own
+PPO on `FixedWingVecEnv`.  The product package never imports this file.
 """
 import importlib.abc
 import importlib.machinery
@@ -16,8 +18,16 @@ import types
 
 import numpy as np
 
+_MIRROR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
 REFERENCE_ROOT = os.environ.get("FW_REFERENCE_ROOT", "/root/reference")
+if not os.path.isdir(os.path.join(REFERENCE_ROOT, "magpie", "libs")) and os.path.isdir(os.path.join(_MIRROR, "magpie", "libs")):
+    REFERENCE_ROOT = _MIRROR
 _LIBS = os.path.join(REFERENCE_ROOT, "magpie", "libs")
+
+
+def available():
+    """True when the reference libraries can be imported (mounted tree or the baseline/_ref mirror)."""
+    return os.path.isdir(_LIBS)
 
 
 class Space:

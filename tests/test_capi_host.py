@@ -142,3 +142,69 @@ def test_spaces_match_the_reference():
     f32max = np.finfo(np.float32).max
     assert np.array_equal(g["default_act_low"], np.full(3, -f32max, np.float32))
     assert np.array_equal(g["default_act_high"], np.full(3, f32max, np.float32))
+
+
+def test_simulator_randomisation_blocks_are_refused():
+    """sample_simulator_parameters (fixed_wing.py:748-813): a `simulator.model` block (aircraft-parameter
+    randomisation) or any simulator key other than `states` must raise, not be dropped silently."""
+    env = C.default_env_config()
+    env["simulator"]["model"] = {"var_type": "relative", "var": 0.1, "parameters": [{"name": "C_L_alpha"}]}
+    with pytest.raises(NotImplementedError):
+        C.build_config(env_cfg=env)
+    env = C.default_env_config()
+    env["simulator"]["turbulence_intensity"] = {"values": ["light", "severe"]}
+    with pytest.raises(NotImplementedError):
+        C.build_config(env_cfg=env)
+
+
+def test_oracle_live_config_change_keeps_running_episodes():
+    """fw_set_config semantics, stated on the oracle: after set_curriculum_level / seed in the middle of a run
+    (train_rl_controller.py:137) episodes in flight continue exactly as in an untouched twin, and every reset from then
+    on draws from the new ranges / the new Philox key."""
+    from oracle import fw_oracle as O
+    kw = dict(sim_config_kw={"turbulence": True}, config_kw={"steps_max": 25}, seed=11)
+    cfg = C.build_config(**kw)
+    a, b = O.OracleBatch(cfg, 24), O.OracleBatch(cfg, 24)
+    a.reset(); b.reset()
+    rs = np.random.RandomState(0)
+    fresh = np.ones(24, bool)                     # envs of `b` still in the episode that was running at the change
+    new_cfg = C.build_config(curriculum_level=0.2, **dict(kw, seed=12))
+    seen_new = 0
+    for t in range(60):
+        act = rs.uniform(-1, 1, (24, 3)).astype(np.float32)
+        if t == 10:
+            b.set_config(new_cfg)
+        oa, ra, da = (x.copy() for x in a.step(act))
+        ob, rb, db = (x.copy() for x in b.step(act))
+        if t < 10:
+            assert np.array_equal(oa, ob)
+            continue
+        # reward / done of the running episode are unaffected even at the step that ends it
+        assert np.array_equal(ra[fresh], rb[fresh]) and np.array_equal(da[fresh], db[fresh])
+        ended = fresh & (db != 0)
+        fresh &= ~(db != 0)
+        assert np.array_equal(oa[fresh], ob[fresh])
+        # reset observations after the change: roll within the scaled init range (+-110 deg * 0.2), and not the twin's
+        for i in np.flatnonzero(ended):
+            assert abs(ob[i, 0]) <= np.radians(110) * 0.2 + 1e-12
+            assert not np.array_equal(oa[i], ob[i])
+            seen_new += 1
+    assert seen_new == 24
+
+
+def test_vecenv_classes_are_sb3_vecenvs():
+    """With stable_baselines3 importable the adapters are (virtual or real) subclasses of its VecEnv ABC, which is what
+    BaseAlgorithm._wrap_env tests (common/base_class.py:173-177); instances need a GPU (tests/test_gpu_dropin.py)."""
+    from oracle import refshim
+    if not refshim.available():
+        pytest.skip("reference libraries neither mounted nor mirrored under baseline/_ref")
+    refshim.install()
+    from stable_baselines3.common.vec_env.base_vec_env import VecEnv
+    from tum_adlr_deep_reinforcement_learning_b200 import vec_env as V
+    V.register_with_sb3()
+    assert issubclass(V.FixedWingVecEnv, VecEnv) and issubclass(V.WaypointVecEnv, VecEnv)
+    for name in ("reset", "step_async", "step_wait", "close", "get_attr", "set_attr", "env_method", "seed", "step",
+                 "env_is_wrapped", "getattr_depth_check", "_get_indices", "unwrapped", "render"):
+        assert hasattr(V.FixedWingVecEnv, name), name
+    import gym.spaces
+    assert isinstance(V.make_box([0.0], [1.0]), gym.spaces.Box)

@@ -48,8 +48,7 @@ class BatchedFixedWing:
         # ... followed (8-byte aligned) by the episode-end rows of fw_set_info_rows: count + INFO_CAP rows
         self.info_width = FW_INFO_HEAD + self.obs_dim
         self.info_offset = -(-(n * self.obs_dim * 4 + n * 4 + n) // 8) * 8
-        waypoint = self.cfg.env_kind != 0
-        self.info_cap = 0 if waypoint else INFO_CAP
+        self.info_cap = INFO_CAP
         self.out_nbytes = self.info_offset + (8 + self.info_cap * self.info_width * 8 if self.info_cap else 0)
         self.out_packed = torch.zeros(self.out_nbytes, dtype=torch.uint8, device=dev)
         self.obs, self.rew, self.done = unpack_outputs(self.out_packed, n, self.obs_dim)
@@ -71,6 +70,12 @@ class BatchedFixedWing:
             self.close()
         except Exception:
             pass
+
+    def set_config(self, cfg):
+        """Live update of the reset-time configuration (fw_set_config): init / target ranges and the seed.  Running
+        episodes, device pointers and captured CUDA graphs stay as they are; resets from now on use the new values."""
+        _lib.check(_lib.lib().fw_set_config(self._h, ctypes.byref(cfg), self._stream()), "fw_set_config")
+        self.cfg = cfg
 
     def set_waypoint_tasks(self, tasks, task_of_env):
         """Waypoint head: tasks [n_tasks, wp_len, 15] float64 rows (position n e d, roll pitch yaw, velocity u v w, wind

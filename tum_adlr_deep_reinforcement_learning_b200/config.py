@@ -20,7 +20,7 @@ import numpy as np
 
 _DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
 
-FW_ABI_VERSION = 7
+FW_ABI_VERSION = 8
 FW_NY, FW_NOBS, FW_NACT, FW_NSTATE_INJECT, FW_NMETRIC = 19, 14, 3, 21, 28
 FW_F64, FW_F32 = 0, 1
 FW_INT_RK45_SCIPY, FW_INT_RK4_FIXED = 0, 1
@@ -280,10 +280,10 @@ def dryden_filters(sim_length, sim_dt, wingspan, intensity="light", spec=False):
     return out, math.sqrt(math.pi / dt_d)
 
 
-def build_config(env_cfg=None, sim_cfg=None, config_kw=None, sim_config_kw=None, params=None,
-                 curriculum_level=1.0, precision="f64", integrator="rk45", rk4_substeps=4, rtol=1e-3, atol=1e-6,
-                 seed=0, env_id_offset=0, dryden_spec=False, obs_init_noise=None, rng_u_override=None, env_kind="attitude"):
-    """Flatten reference-format configs into an `FwConfig`.  `env_cfg` / `sim_cfg`: dict or JSON path (defaults above)."""
+def resolve_configs(env_cfg=None, sim_cfg=None, config_kw=None, sim_config_kw=None, env_kind="attitude"):
+    """The reference-format (env, sim) config dicts after the constructor overrides — what `FixedWingAircraft.cfg` and
+    `PyFly.cfg` hold in the reference (fixed_wing.py:34-62, pyfly.py:1067-1073).  `env_cfg` / `sim_cfg`: dict or JSON
+    path (defaults above)."""
     def load(x, default):
         if x is None:
             return default()
@@ -307,6 +307,22 @@ def build_config(env_cfg=None, sim_cfg=None, config_kw=None, sim_config_kw=None,
     if not waypoint:
         sim_kw["turbulence_sim_length"] = env["steps_max"]    # fixed_wing.py:62
     apply_overrides(sim, sim_kw)
+    return env, sim
+
+
+def build_config(env_cfg=None, sim_cfg=None, config_kw=None, sim_config_kw=None, params=None,
+                 curriculum_level=1.0, precision="f64", integrator="rk45", rk4_substeps=4, rtol=1e-3, atol=1e-6,
+                 seed=0, env_id_offset=0, dryden_spec=False, obs_init_noise=None, rng_u_override=None, env_kind="attitude"):
+    """Flatten reference-format configs into an `FwConfig`.  `env_cfg` / `sim_cfg`: dict or JSON path (defaults above)."""
+    env, sim = resolve_configs(env_cfg, sim_cfg, config_kw, sim_config_kw, env_kind)
+    waypoint = env_kind == "waypoint"
+    for key in env.get("simulator", {}):
+        # sample_simulator_parameters (fixed_wing.py:748-813) re-draws aircraft parameters ("model") or simulator
+        # attributes (any other key) at every reset; that is not implemented: refuse it instead of silently flying the
+        # nominal airframe
+        if key != "states":
+            raise NotImplementedError("simulator.%s: per-episode simulator / aircraft-parameter randomisation "
+                                      "(fixed_wing.py:748-813)" % key)
     P = load_aircraft_parameters() if params is None else dict(params)
 
     c = FwConfig()

@@ -121,6 +121,17 @@ template <typename T> struct DCfg {
     long long env_id_offset;
 };
 
+// Reset-time configuration: the ranges FixedWingAircraft.reset / sample_target draw from and the Philox key.  Unlike
+// DCfg (a kernel parameter, frozen into every captured CUDA graph) it lives in DEVICE memory behind a stable pointer,
+// so fw_set_config can change it on a live handle — set_curriculum_level (fixed_wing.py:334-412) and seed (:324-332)
+// touch exactly these values and apply to FUTURE resets only; running episodes continue untouched.
+template <typename T> struct ResetCfg {
+    T init_lo[12], init_hi[12], wind_mag_min, wind_mag_max;
+    T tgt_low[3], tgt_high[3], tgt_delta[3];
+    T tgt_slope_low[3], tgt_slope_high[3], tgt_amp_low[3], tgt_amp_high[3], tgt_period_low[3], tgt_period_high[3];
+    unsigned long long seed;
+};
+
 // ---------------------------------------------------------------------------------------------------------------
 // SoA field ids
 enum RField {
@@ -157,7 +168,8 @@ enum IField {
     IF_WP_POS = 47,           // waypoint head: index of the current leg's start waypoint
     IF_TCLS = 44,             // 3: per-env target class (an injected target forces constant, fixed_wing.py:446-450)
     IF_GOAL_ACHIEVED = 43,    // self.goal_achieved: set by the first success, never cleared (fixed_wing.py:81, 546-547)
-    IF_COUNT = 48
+    IF_SEED_LO = 48, IF_SEED_HI = 49,   // Philox key of the running episode = ResetCfg.seed when the episode was reset
+    IF_COUNT = 50
 };
 
 template <typename T> struct Soa {
@@ -174,7 +186,14 @@ template <typename T> struct Soa {
     const double* wp_tasks;      // waypoint head: [n_tasks][wp_len][FW_WP_ROW]
     const int32_t* wp_task_of_env;
     int wp_n_tasks, wp_len;
+    const ResetCfg<T>* rc;       // device memory (fw_set_config)
 };
+
+// the Philox key of env's running episode
+template <typename T> __device__ __forceinline__ unsigned long long env_seed(const Soa<T>& S, int env) {
+    return (unsigned long long)(uint32_t)S.i[IF_SEED_LO * S.n + env] |
+           ((unsigned long long)(uint32_t)S.i[IF_SEED_HI * S.n + env] << 32);
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // Philox4x32-10 counter-based RNG (Salmon et al. SC'11).  Stream layout (identical in oracle/fw_oracle.c):
@@ -680,7 +699,7 @@ __device__ __forceinline__ void noise_sample(const DCfg<T>& c, const Soa<T>& S, 
 #pragma unroll
         for (int r = 0; r < 4; ++r) z[r] = S.noise[((size_t)env * 4 + r) * S.noise_len + kk];
     } else {
-        rng_noise4(c.seed, c.env_id_offset + env, episode, (uint32_t)k, z);
+        rng_noise4(env_seed(S, env), c.env_id_offset + env, episode, (uint32_t)k, z);
     }
 #pragma unroll
     for (int r = 0; r < 4; ++r) un[r] = (T)z[r] * c.turb_noise_scale;
@@ -689,11 +708,11 @@ __device__ __forceinline__ void noise_sample(const DCfg<T>& c, const Soa<T>& S, 
 // the twelve uniform draws of one target sampling, four per target state in the order the reference consumes them
 // (initial value; slope, sign | amplitude, period, phase): Philox blocks block0 .. block0+5 of `purpose`, or the override
 template <typename T>
-__device__ __forceinline__ void target_draws(const DCfg<T>& c, long long gid, unsigned long long episode, uint32_t purpose,
-                                             uint32_t block0, T (&u12)[12]) {
+__device__ __forceinline__ void target_draws(const DCfg<T>& c, unsigned long long seed, long long gid,
+                                             unsigned long long episode, uint32_t purpose, uint32_t block0, T (&u12)[12]) {
 #pragma unroll
     for (int b = 0; b < 6; ++b) {
-        const uint4 rr = rng_block(c.seed, gid, episode, purpose, block0 + (uint32_t)b);
+        const uint4 rr = rng_block(seed, gid, episode, purpose, block0 + (uint32_t)b);
         u12[2 * b] = (T)u53(rr.x, rr.y);
         u12[2 * b + 1] = (T)u53(rr.z, rr.w);
     }
@@ -705,28 +724,28 @@ __device__ __forceinline__ void target_draws(const DCfg<T>& c, long long gid, un
 
 // sample_target (fixed_wing.py:654-746): classes constant / compensate / linear / sinusoidal
 template <typename T>
-__device__ __forceinline__ void sample_target(const DCfg<T>& c, T roll, T pitch, T Va, int steps, const T (&u12)[12],
-                                              T (&tgt)[3], int (&tcls)[3], T (&tp)[15]) {
+__device__ __forceinline__ void sample_target(const DCfg<T>& c, const ResetCfg<T>& rc, T roll, T pitch, T Va, int steps,
+                                              const T (&u12)[12], T (&tgt)[3], int (&tcls)[3], T (&tp)[15]) {
     const T val[3] = {roll, pitch, Va};
     const T TWO_PI = (T)6.283185307179586476925286766559, D2R = (T)(3.141592653589793238462643383279502884 / 180.0);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        T low = c.tgt_low[k], high = c.tgt_high[k];
-        if (!M<T>::isnan(c.tgt_delta[k])) {
-            low = M<T>::fmax(low, val[k] - c.tgt_delta[k]);
-            high = M<T>::fmax(M<T>::fmin(high, val[k] + c.tgt_delta[k]), low);
+        T low = rc.tgt_low[k], high = rc.tgt_high[k];
+        if (!M<T>::isnan(rc.tgt_delta[k])) {
+            low = M<T>::fmax(low, val[k] - rc.tgt_delta[k]);
+            high = M<T>::fmax(M<T>::fmin(high, val[k] + rc.tgt_delta[k]), low);
         }
         const T initial = low + (high - low) * u12[4 * k];
         tcls[k] = c.tgt_class[k];
         if (c.tgt_class[k] == FW_TGT_LINEAR) {
-            T slope = c.tgt_slope_low[k] + (c.tgt_slope_high[k] - c.tgt_slope_low[k]) * u12[4 * k + 1];
+            T slope = rc.tgt_slope_low[k] + (rc.tgt_slope_high[k] - rc.tgt_slope_low[k]) * u12[4 * k + 1];
             if (u12[4 * k + 2] < (T)0.5) slope *= (T)-1;
             if (c.tgt_radians[k]) slope = slope * D2R;
             tp[k] = slope;
         } else if (c.tgt_class[k] == FW_TGT_SINUSOIDAL) {
-            T amp = c.tgt_amp_low[k] + (c.tgt_amp_high[k] - c.tgt_amp_low[k]) * u12[4 * k + 1];
+            T amp = rc.tgt_amp_low[k] + (rc.tgt_amp_high[k] - rc.tgt_amp_low[k]) * u12[4 * k + 1];
             if (c.tgt_radians[k]) amp = amp * D2R;
-            const T period = c.tgt_period_low[k] + (c.tgt_period_high[k] - c.tgt_period_low[k]) * u12[4 * k + 2];
+            const T period = rc.tgt_period_low[k] + (rc.tgt_period_high[k] - rc.tgt_period_low[k]) * u12[4 * k + 2];
             const T phase = ((T)0 + (TWO_PI - (T)0) * u12[4 * k + 3]) / (TWO_PI / period);
             tp[3 + k] = amp; tp[6 + k] = period; tp[9 + k] = phase;
             tp[12 + k] = initial - amp * M<T>::sin(TWO_PI / period * ((T)steps + phase));
@@ -738,11 +757,11 @@ __device__ __forceinline__ void sample_target(const DCfg<T>& c, T roll, T pitch,
 // observation.noise (fixed_wing.py:1246-1247): every entry += N(mean, var); Philox purpose OBS, block = 32 * steps + b,
 // four Box-Muller normals per block (same stream as oracle add_obs_noise).  Out of line: off by default.
 template <typename T>
-__device__ __noinline__ void add_obs_noise(const DCfg<T>& c, long long gid, unsigned long long episode, int steps,
-                                           T* o, int dim) {
+__device__ __noinline__ void add_obs_noise(const DCfg<T>& c, unsigned long long seed, long long gid,
+                                           unsigned long long episode, int steps, T* o, int dim) {
 #pragma unroll 1
     for (int b = 0; b * 4 < dim; ++b) {
-        const uint4 r = rng_block(c.seed, gid, episode, RNG_OBS, (uint32_t)(steps * 32 + b));
+        const uint4 r = rng_block(seed, gid, episode, RNG_OBS, (uint32_t)(steps * 32 + b));
         const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
@@ -886,7 +905,7 @@ __device__ __noinline__ void generic_observation(const DCfg<T>& c, const Soa<T>&
                 T u;
                 if (!M<T>::isnan(c.obs_init_noise)) u = c.obs_init_noise;
                 else {
-                    const uint4 rr = rng_block(c.seed, c.env_id_offset + env, episode, RNG_OBS_INIT, (uint32_t)(steps * 8 + (i - 1)));
+                    const uint4 rr = rng_block(env_seed(S, env), c.env_id_offset + env, episode, RNG_OBS_INIT, (uint32_t)(steps * 8 + (i - 1)));
                     u = (T)(2.0 * u53(rr.x, rr.y) - 1.0);
                 }
                 init_noise = u * c.dt;
@@ -923,7 +942,7 @@ __device__ __noinline__ void generic_observation(const DCfg<T>& c, const Soa<T>&
             o[(i - 1) * ne + k] = val;
         }
     }
-    if (c.obs_noise_std > (T)0 || c.obs_noise_mean != (T)0) add_obs_noise<T>(c, c.env_id_offset + env, episode, steps, o, L * ne);
+    if (c.obs_noise_std > (T)0 || c.obs_noise_mean != (T)0) add_obs_noise<T>(c, env_seed(S, env), c.env_id_offset + env, episode, steps, o, L * ne);
     if (push) {
 #pragma unroll 1
         for (int k = 3; k >= 1; --k)
@@ -942,11 +961,16 @@ __device__ void reset_env(const DCfg<T>& c, const Soa<T>& S, int env, const doub
     const int n = S.n;
     const unsigned long long episode = (unsigned long long)(uint32_t)S.i[IF_EPISODE * n + env] + 1ull;
     const long long gid = c.env_id_offset + env;
+    const ResetCfg<T>& rc = *S.rc;
+    const unsigned long long seed = rc.seed;
+    // the episode keeps this key until its next reset (noise_sample / add_obs_noise / resampling read it back)
+    S.i[IF_SEED_LO * n + env] = (int32_t)(uint32_t)seed;
+    S.i[IF_SEED_HI * n + env] = (int32_t)(uint32_t)(seed >> 32);
     T s12[12];
 #pragma unroll
     for (int i = 0; i < 12; ++i) {
         const double inj = state_in ? state_in[(size_t)env * FW_NSTATE_INJECT + i] : CUDART_NAN;
-        s12[i] = ::isnan(inj) ? c.init_lo[i] + (c.init_hi[i] - c.init_lo[i]) * rng_uniform<T>(c.seed, gid, episode, RNG_RESET, i)
+        s12[i] = ::isnan(inj) ? rc.init_lo[i] + (rc.init_hi[i] - rc.init_lo[i]) * rng_uniform<T>(seed, gid, episode, RNG_RESET, i)
                               : (T)inj;
     }
     T a6[6];
@@ -967,10 +991,10 @@ __device__ void reset_env(const DCfg<T>& c, const Soa<T>& S, int env, const doub
         double w2 = state_in ? state_in[(size_t)env * FW_NSTATE_INJECT + 20] : CUDART_NAN;
         if (!::isnan(w0) && !::isnan(w1) && !::isnan(w2)) { wind[0] = (T)w0; wind[1] = (T)w1; wind[2] = (T)w2; }
         else {   // Wind.reset (pyfly.py:815-823)
-            const T mag = c.wind_mag_min + (c.wind_mag_max - c.wind_mag_min) * rng_uniform<T>(c.seed, gid, episode, RNG_RESET, 12);
-            const T w_n = -mag + (mag - -mag) * rng_uniform<T>(c.seed, gid, episode, RNG_RESET, 13);
+            const T mag = rc.wind_mag_min + (rc.wind_mag_max - rc.wind_mag_min) * rng_uniform<T>(seed, gid, episode, RNG_RESET, 12);
+            const T w_n = -mag + (mag - -mag) * rng_uniform<T>(seed, gid, episode, RNG_RESET, 13);
             const T w_e_max = M<T>::sqrt(mag * mag - w_n * w_n);
-            const T w_e = -w_e_max + (w_e_max - -w_e_max) * rng_uniform<T>(c.seed, gid, episode, RNG_RESET, 14);
+            const T w_e = -w_e_max + (w_e_max - -w_e_max) * rng_uniform<T>(seed, gid, episode, RNG_RESET, 14);
             wind[0] = w_n; wind[1] = w_e; wind[2] = M<T>::sqrt(mag * mag - w_n * w_n - w_e * w_e);
         }
     }
@@ -1007,8 +1031,8 @@ __device__ void reset_env(const DCfg<T>& c, const Soa<T>& S, int env, const doub
     int tcls[3];
 #pragma unroll
     for (int k = 0; k < 15; ++k) tp[k] = 0;
-    target_draws<T>(c, gid, episode, RNG_RESET, 8u, u12);       // blocks 8..13 of the reset stream (0..7: state, wind)
-    sample_target<T>(c, roll, pitch, Va, 0, u12, tgt, tcls, tp);
+    target_draws<T>(c, seed, gid, episode, RNG_RESET, 8u, u12);       // blocks 8..13 of the reset stream (0..7: state, wind)
+    sample_target<T>(c, rc, roll, pitch, Va, 0, u12, tgt, tcls, tp);
     if (target_in) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -1087,7 +1111,7 @@ __device__ void reset_env(const DCfg<T>& c, const Soa<T>& S, int env, const doub
         write_obs(og, obs_dim(c), env, obs, obs64);
         return;
     }
-    if (c.obs_noise_std > (T)0 || c.obs_noise_mean != (T)0) add_obs_noise<T>(c, gid, episode, 0, o, FW_NOBS);
+    if (c.obs_noise_std > (T)0 || c.obs_noise_mean != (T)0) add_obs_noise<T>(c, seed, gid, episode, 0, o, FW_NOBS);
     write_obs(o, FW_NOBS, env, obs, obs64);
 }
 
@@ -1104,11 +1128,15 @@ __device__ __noinline__ void wp_start_leg(const DCfg<T>& c, const Soa<T>& S, int
     const double* row = S.wp_tasks + ((size_t)S.wp_task_of_env[env] * S.wp_len + wp_pos) * FW_WP_ROW;
     const unsigned long long episode = (unsigned long long)(uint32_t)ii[IF_EPISODE * n] + 1ull;
     const long long gid = c.env_id_offset + env;
+    const ResetCfg<T>& rc = *S.rc;
+    const unsigned long long seed = rc.seed;
+    ii[IF_SEED_LO * n] = (int32_t)(uint32_t)seed;
+    ii[IF_SEED_HI * n] = (int32_t)(uint32_t)(seed >> 32);
     const T roll = (T)row[3], pitch = (T)row[4], yaw = (T)row[5];
     T om[3], wind[3], vel[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-        om[i] = ::isnan(row[12 + i]) ? c.init_lo[3 + i] + (c.init_hi[3 + i] - c.init_lo[3 + i]) * rng_uniform<T>(c.seed, gid, episode, RNG_RESET, 3 + i)
+        om[i] = ::isnan(row[12 + i]) ? rc.init_lo[3 + i] + (rc.init_hi[3 + i] - rc.init_lo[3 + i]) * rng_uniform<T>(seed, gid, episode, RNG_RESET, 3 + i)
                                      : (T)row[12 + i];
         wind[i] = (T)row[9 + i];
         vel[i] = (T)row[6 + i];

@@ -151,6 +151,14 @@ __global__ void __launch_bounds__(32) refill_kernel(const __grid_constant__ DCfg
     }
 }
 
+// fw_set_config: every env's precomputed next-episode row is recomputed from the new reset-time configuration
+template <typename T>
+__global__ void __launch_bounds__(128) respare_kernel(const __grid_constant__ DCfg<T> c, const Soa<T> S, const Spare<T> P) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= S.n) return;
+    make_spare<T>(c, S, P, env);
+}
+
 // sum |diff| of one column over the trailing window, accumulated in float32 like
 // np.sum(np.abs(np.diff(...)), dtype=np.float32) (fixed_wing.py:1198-1228)
 template <typename T>
@@ -762,8 +770,8 @@ __global__ void __launch_bounds__(64, 8) head_kernel(const __grid_constant__ DCf
         }
         if (resample || (c.resample_every > 0 && steps_tgt >= c.resample_every)) {
             T u12[12];
-            target_draws<T>(c, c.env_id_offset + env, episode, RNG_RESAMPLE, (uint32_t)(steps * 8), u12);
-            sample_target<T>(c, roll, pitch, Va, steps, u12, tgt, tcls, tp);
+            target_draws<T>(c, env_seed(S, env), c.env_id_offset + env, episode, RNG_RESAMPLE, (uint32_t)(steps * 8), u12);
+            sample_target<T>(c, *S.rc, roll, pitch, Va, steps, u12, tgt, tcls, tp);
             steps_tgt = 0;
             if (c.tgt_moving) {
 #pragma unroll
@@ -828,7 +836,7 @@ __global__ void __launch_bounds__(64, 8) head_kernel(const __grid_constant__ DCf
     }
 
     if (!GENERIC && (c.obs_noise_std > (T)0 || c.obs_noise_mean != (T)0))
-        add_obs_noise<T>(c, c.env_id_offset + env, episode, steps, obs_v, FW_NOBS);
+        add_obs_noise<T>(c, env_seed(S, env), c.env_id_offset + env, episode, steps, obs_v, FW_NOBS);
     T og[GENERIC ? FW_NOBS_MAX : 1];
     const T* obs_out = obs_v;
     int odim = FW_NOBS;
@@ -1058,6 +1066,15 @@ __global__ void __launch_bounds__(128, 4) waypoint_head_kernel(const __grid_cons
     if (io.done) io.done[env] = done ? 1 : 0;
     if (done && io.auto_reset) {
         if (io.term_obs) write_obs(o, FW_NOBS_WAYPOINT, env, io.term_obs, (double*)nullptr);
+        if (io.info) {      // packed episode-end row for the host (fw_set_info_rows), same layout as head_kernel's
+            const int slot = atomicAdd(reinterpret_cast<int32_t*>(io.info), 1);
+            if (slot < io.info_cap) {
+                double* row = io.info + 1 + (size_t)slot * (FW_INFO_HEAD + FW_NOBS_WAYPOINT);
+                row[0] = (double)env; row[1] = (double)term; row[2] = (double)steps; row[3] = (double)ep_ret;
+                for (int k = 0; k < FW_NMETRIC; ++k) row[4 + k] = CUDART_NAN;
+                for (int q = 0; q < FW_NOBS_WAYPOINT; ++q) row[FW_INFO_HEAD + q] = (double)(float)o[q];
+            }
+        }
         wp_reset_env<T>(c, S, env, io.obs, io.obs64);
         return;
     }
@@ -1219,6 +1236,31 @@ template <typename T> static void convert_cfg(const FwConfig& f, DCfg<T>& d) {
     d.env_id_offset = f.env_id_offset;
 }
 
+template <typename T> static void convert_reset_cfg(const FwConfig& f, ResetCfg<T>& d) {
+    memset(&d, 0, sizeof(d));
+#define CP(x) d.x = (T)f.x
+    for (int k = 0; k < 12; ++k) { CP(init_lo[k]); CP(init_hi[k]); }
+    CP(wind_mag_min); CP(wind_mag_max);
+    for (int k = 0; k < 3; ++k) {
+        CP(tgt_low[k]); CP(tgt_high[k]); CP(tgt_delta[k]);
+        CP(tgt_slope_low[k]); CP(tgt_slope_high[k]); CP(tgt_amp_low[k]); CP(tgt_amp_high[k]); CP(tgt_period_low[k]); CP(tgt_period_high[k]);
+    }
+#undef CP
+    d.seed = f.seed;
+}
+
+// the FwConfig fields fw_set_config may change on a live handle (everything ResetCfg carries); used to check that
+// nothing else differs
+static void blank_reset_fields(FwConfig& f) {
+    memset(f.init_lo, 0, sizeof(f.init_lo)); memset(f.init_hi, 0, sizeof(f.init_hi));
+    f.wind_mag_min = f.wind_mag_max = 0;
+    memset(f.tgt_low, 0, sizeof(f.tgt_low)); memset(f.tgt_high, 0, sizeof(f.tgt_high)); memset(f.tgt_delta, 0, sizeof(f.tgt_delta));
+    memset(f.tgt_slope_low, 0, sizeof(f.tgt_slope_low)); memset(f.tgt_slope_high, 0, sizeof(f.tgt_slope_high));
+    memset(f.tgt_amp_low, 0, sizeof(f.tgt_amp_low)); memset(f.tgt_amp_high, 0, sizeof(f.tgt_amp_high));
+    memset(f.tgt_period_low, 0, sizeof(f.tgt_period_low)); memset(f.tgt_period_high, 0, sizeof(f.tgt_period_high));
+    f.seed = 0;
+}
+
 }  // namespace fw
 
 using namespace fw;
@@ -1234,6 +1276,7 @@ struct FwHandle {
     double* metrics; double* ep_ret; int32_t* ep_len; int32_t* ep_term;
     void* w_real; int32_t* w_int;          // scratch between the kernels of one step
     double* wp_tasks; int32_t* wp_task_of_env;   // waypoint head: device copies of the task table
+    void* rc_dev;                          // ResetCfg<T> in device memory (fw_set_config rewrites it)
     Scratch<double> w64;
     Scratch<float> w32;
     int sm_count;
@@ -1399,10 +1442,6 @@ int fw_obs_dim(const FwHandle* h) {
 
 int fw_set_info_rows(FwHandle* h, double* rows_dev, int32_t cap) {
     if (!h || (rows_dev && cap <= 0)) return FW_EINVAL;
-    if (h->cfg.env_kind == FW_ENV_WAYPOINT && rows_dev) {
-        snprintf(g_err, sizeof(g_err), "fw_set_info_rows: not available for the waypoint env");
-        return FW_EINVAL;
-    }
     h->info_rows = rows_dev;
     h->info_cap = rows_dev ? cap : 0;
     return FW_OK;
@@ -1503,8 +1542,20 @@ int fw_create(const FwConfig* cfg, int32_t n_envs, int32_t device, FwHandle** ou
     CK(cudaMemset(h->ep_ret, 0, sizeof(double) * n));
     CK(cudaMemset(h->ep_len, 0, sizeof(int32_t) * n));
     CK(cudaMemset(h->ep_term, 0, sizeof(int32_t) * n));
-    h->s64 = Soa<double>{(double*)h->r_buf, h->i_buf, (double*)h->err_ring, h->metrics, h->ep_ret, h->ep_len, h->ep_term, nullptr, 0, n_envs, nullptr, nullptr, 0, 0};
-    h->s32 = Soa<float>{(float*)h->r_buf, h->i_buf, (float*)h->err_ring, h->metrics, h->ep_ret, h->ep_len, h->ep_term, nullptr, 0, n_envs, nullptr, nullptr, 0, 0};
+    h->s64 = Soa<double>{(double*)h->r_buf, h->i_buf, (double*)h->err_ring, h->metrics, h->ep_ret, h->ep_len, h->ep_term, nullptr, 0, n_envs, nullptr, nullptr, 0, 0, nullptr};
+    h->s32 = Soa<float>{(float*)h->r_buf, h->i_buf, (float*)h->err_ring, h->metrics, h->ep_ret, h->ep_len, h->ep_term, nullptr, 0, n_envs, nullptr, nullptr, 0, 0, nullptr};
+    {
+        CK(cudaMalloc(&h->rc_dev, sizeof(ResetCfg<double>)));
+        if (cfg->precision == FW_F64) {
+            ResetCfg<double> rc; convert_reset_cfg<double>(*cfg, rc);
+            CK(cudaMemcpy(h->rc_dev, &rc, sizeof(rc), cudaMemcpyHostToDevice));
+        } else {
+            ResetCfg<float> rc; convert_reset_cfg<float>(*cfg, rc);
+            CK(cudaMemcpy(h->rc_dev, &rc, sizeof(rc), cudaMemcpyHostToDevice));
+        }
+        h->s64.rc = (const ResetCfg<double>*)h->rc_dev;
+        h->s32.rc = (const ResetCfg<float>*)h->rc_dev;
+    }
     {
         const int odim = fw_obs_dim(h);
         CK(cudaMalloc(&h->r2_buf, esz * RF_COUNT * n));
@@ -1545,7 +1596,7 @@ int fw_destroy(FwHandle* h) {
     cudaDeviceSynchronize();
     cudaFree(h->r_buf); cudaFree(h->i_buf); cudaFree(h->err_ring); cudaFree(h->metrics);
     cudaFree(h->ep_ret); cudaFree(h->ep_len); cudaFree(h->ep_term); cudaFree(h->w_real); cudaFree(h->w_int);
-    cudaFree(h->wp_tasks); cudaFree(h->wp_task_of_env);
+    cudaFree(h->wp_tasks); cudaFree(h->wp_task_of_env); cudaFree(h->rc_dev);
     cudaFree(h->r2_buf); cudaFree(h->i2_buf); cudaFree(h->err2); cudaFree(h->spare_obs); cudaFree(h->spare_obs64);
     cudaFree(h->done_list);
     if (h->side) cudaStreamDestroy(h->side);
@@ -1553,6 +1604,40 @@ int fw_destroy(FwHandle* h) {
     if (h->ev_refill) cudaEventDestroy(h->ev_refill);
     for (int i = 0; i < 4; ++i) if (h->prof_ev[i]) cudaEventDestroy(h->prof_ev[i]);
     delete h;
+    return FW_OK;
+}
+
+int fw_set_config(FwHandle* h, const FwConfig* cfg, void* stream) {
+    if (!h || !cfg) { snprintf(g_err, sizeof(g_err), "fw_set_config: null handle/config"); return FW_EINVAL; }
+    {
+        FwConfig a = h->cfg, b = *cfg;
+        blank_reset_fields(a); blank_reset_fields(b);
+        if (memcmp(&a, &b, sizeof(FwConfig)) != 0) {
+            snprintf(g_err, sizeof(g_err), "fw_set_config: only the reset-time fields (init_lo/hi, wind_mag_min/max, tgt_low/high/delta, "
+                                           "tgt_slope/amp/period ranges, seed) may differ from the handle's configuration");
+            return FW_EINVAL;
+        }
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (stream_is_capturing(st)) { snprintf(g_err, sizeof(g_err), "fw_set_config: not allowed during stream capture"); return FW_EINVAL; }
+    spare_join(h, st);       // a refill in flight still reads the old values
+    // pageable source: cudaMemcpyAsync stages it before returning, so the stack copy may go out of scope
+    if (h->cfg.precision == FW_F64) {
+        ResetCfg<double> rc; convert_reset_cfg<double>(*cfg, rc);
+        CK(cudaMemcpyAsync(h->rc_dev, &rc, sizeof(rc), cudaMemcpyHostToDevice, st));
+    } else {
+        ResetCfg<float> rc; convert_reset_cfg<float>(*cfg, rc);
+        CK(cudaMemcpyAsync(h->rc_dev, &rc, sizeof(rc), cudaMemcpyHostToDevice, st));
+    }
+    h->cfg = *cfg;
+    convert_cfg<double>(*cfg, h->c64);
+    convert_cfg<float>(*cfg, h->c32);
+    if (h->p64.on) {
+        const int bs = 128, grid = (h->n + bs - 1) / bs;
+        if (h->cfg.precision == FW_F64) respare_kernel<double><<<grid, bs, 0, st>>>(h->c64, h->s64, h->p64);
+        else respare_kernel<float><<<grid, bs, 0, st>>>(h->c32, h->s32, h->p32);
+        CK(cudaGetLastError());
+    }
     return FW_OK;
 }
 

@@ -8,20 +8,26 @@ Drop-in boundary: what `collect_rollouts` / `evaluate_policy` / th
   auto-reset + info["terminal_observation"]    (subproc_vec_env.py:26-31, dummy_vec_env.py:46-50)
   info["episode"] = {"r","l","t"}              (common/monitor.py:99-113)
   info["target"], info["termination"], the 9 metric dicts on done   (fixed_wing.py:519-626)
+When stable_baselines3 is importable the classes here ARE `stable_baselines3.common.vec_env.VecEnv`s (derived, or
+registered with the ABC if stable_baselines3 was imported after this module) with `gym.spaces.Box` spaces, so the fork's
+`BaseAlgorithm._wrap_env` (common/base_class.py:173-177) and `VecNormalize` (vec_env/vec_normalize.py:28-39) take them
+as they are — tests/test_gpu_dropin.py runs the fork's own `PPO.learn` on them.
 There are no worker processes and no per-env Python objects: one CUDA launch steps every env.  Host copies happen
 only at this numpy edge (pinned buffers); `step_tensor` skips them entirely.
 """
+import sys
 import time
 
 import numpy as np
 import torch
 
 from . import batched as bt
-from .config import (GOAL_STATES, METRIC_LAYOUT, TARGET_STATES, TERM_NAMES, build_config, observation_bounds)
+from .config import (GOAL_STATES, METRIC_LAYOUT, TARGET_STATES, TERM_NAMES, build_config, observation_bounds,
+                     resolve_configs)
 
 
 class Box:
-    """Minimal stand-in for gym.spaces.Box (gym is not a dependency of this package)."""
+    """Minimal stand-in for gym.spaces.Box, used only when `gym` cannot be imported (it is not a dependency)."""
 
     def __init__(self, low, high, dtype=np.float32):
         self.low = np.asarray(low, dtype=dtype)
@@ -40,6 +46,71 @@ class Box:
 
     def __repr__(self):
         return "Box(%s, %s)" % (self.shape, self.dtype)
+
+
+def make_box(low, high):
+    """gym.spaces.Box (fixed_wing.py:245-258) when gym is importable — SB3 dispatches on isinstance(space, gym.spaces.Box)
+    (common/preprocessing.py, on_policy_algorithm.py:158) — else the stand-in above."""
+    low, high = np.asarray(low, dtype=np.float32), np.asarray(high, dtype=np.float32)
+    try:
+        import gym.spaces
+        return gym.spaces.Box(low=low, high=high, dtype=np.float32)
+    except Exception:
+        return Box(low, high)
+
+
+def _sb3_vecenv():
+    try:
+        from stable_baselines3.common.vec_env.base_vec_env import VecEnv
+        return VecEnv
+    except Exception:
+        return None
+
+
+_SB3VecEnv = _sb3_vecenv()
+
+
+class _VecEnvSurface(_SB3VecEnv if _SB3VecEnv is not None else object):
+    """The non-abstract part of stable_baselines3's VecEnv (base_vec_env.py:141-224), spelled out so that it is there
+    whether the class derives from VecEnv (stable_baselines3 importable when this module is loaded) or is registered
+    with the ABC afterwards."""
+
+    metadata = {"render.modes": []}
+
+    def _init_vecenv(self, num_envs, observation_space, action_space):
+        self.num_envs = int(num_envs)
+        self.observation_space = observation_space
+        self.action_space = action_space
+        register_with_sb3()                          # in case stable_baselines3 was imported after this module
+
+    def step(self, actions):
+        self.step_async(actions)
+        return self.step_wait()
+
+    def get_images(self):
+        raise NotImplementedError("rendering is out of scope (SURVEY §2 rows 15-16)")
+
+    def render(self, mode="human"):
+        return None
+
+    def env_is_wrapped(self, wrapper_class, indices=None):
+        return [False for _ in self._get_indices(indices)]
+
+    @property
+    def unwrapped(self):
+        return self
+
+    def getattr_depth_check(self, name, already_found):
+        if hasattr(self, name) and already_found:
+            return "%s.%s" % (type(self).__module__, type(self).__name__)
+        return None
+
+    def _get_indices(self, indices):
+        if indices is None:
+            return range(self.num_envs)
+        if isinstance(indices, (int, np.integer)):
+            return [int(indices)]
+        return indices
 
 
 class _SimulatorView:
@@ -76,7 +147,19 @@ def _make_done_info():
 _done_info = _make_done_info()
 
 
-class FixedWingVecEnv:
+def register_with_sb3():
+    """Registers the adapters with stable_baselines3's VecEnv ABC when that package was imported AFTER this module (when
+    it was importable at load time they derive from it).  Returns True if they are VecEnvs now."""
+    mod = sys.modules.get("stable_baselines3.common.vec_env.base_vec_env")
+    if mod is None:
+        return False
+    for cls in (FixedWingVecEnv, WaypointVecEnv):
+        if not issubclass(cls, mod.VecEnv):
+            mod.VecEnv.register(cls)
+    return True
+
+
+class FixedWingVecEnv(_VecEnvSurface):
     """n_envs reference-semantics fixed-wing envs on one GPU behind the VecEnv API.
 
     info_mode: "compat" builds the reference's per-env info dict for every env every step (info["target"] always
@@ -90,27 +173,29 @@ class FixedWingVecEnv:
     def __init__(self, num_envs, config_path=None, config_kw=None, sim_config_path=None, sim_config_kw=None,
                  device=0, seed=0, env_id_offset=0, precision="f64", integrator="rk45", rk4_substeps=4,
                  info_mode="lazy", copy_outputs=False):
-        self.cfg = build_config(env_cfg=config_path, sim_cfg=sim_config_path, config_kw=config_kw,
-                                sim_config_kw=sim_config_kw, precision=precision, integrator=integrator,
-                                rk4_substeps=rk4_substeps, seed=seed, env_id_offset=env_id_offset)
         self._build_kw = dict(env_cfg=config_path, sim_cfg=sim_config_path, config_kw=config_kw,
                               sim_config_kw=sim_config_kw, precision=precision, integrator=integrator,
                               rk4_substeps=rk4_substeps, seed=seed, env_id_offset=env_id_offset)
-        self.num_envs = int(num_envs)
-        self.sim = bt.BatchedFixedWing(self.num_envs, cfg=self.cfg, device=device)
+        self.cfg = build_config(**self._build_kw)                       # the flattened POD (include/fwb200.h FwConfig)
+        # the reference-format dicts `env.cfg` / `env.simulator.cfg` (what get_attr("cfg") hands to the scripts)
+        self.env_config, self.sim_config = resolve_configs(config_path, sim_config_path, config_kw, sim_config_kw)
+        self.sim = bt.BatchedFixedWing(int(num_envs), cfg=self.cfg, device=device)
         self.device = self.sim.device
         lo, hi = observation_bounds(cfg=self.cfg)
-        self.observation_space = Box(lo, hi)
         f32max = np.finfo(np.float32).max
-        self.action_space = Box(np.full(3, -f32max), np.full(3, f32max))
+        self._init_vecenv(num_envs, make_box(lo, hi), make_box(np.full(3, -f32max), np.full(3, f32max)))
+        self.curriculum_level = 1.0
+        self._init_host_edge(info_mode, copy_outputs)
+
+    def _init_host_edge(self, info_mode, copy_outputs):
+        """Pinned staging buffers of the numpy edge (shared by the attitude and the waypoint env)."""
         self.info_mode = info_mode
         self.copy_outputs = copy_outputs
         self.training = True
-        self.curriculum_level = 1.0
-        n = self.num_envs
-        self._act_pin = torch.zeros(n, 3, dtype=torch.float32).pin_memory()
+        n, adim = self.num_envs, self.action_space.shape[0]
+        self._act_pin = torch.zeros(n, adim, dtype=torch.float32).pin_memory()
         self._act_np = self._act_pin.numpy()
-        self._act_dev = torch.zeros(n, 3, dtype=torch.float32, device=self.device)
+        self._act_dev = torch.zeros(n, adim, dtype=torch.float32, device=self.device)
         # double-buffered pinned outputs: with copy_outputs=False the arrays returned by step k stay valid until
         # step k+2 (SB3's collect_rollouts reads obs_k after step k+1 returns, on_policy_algorithm.py:163-180).
         # Each buffer mirrors the simulator's packed obs | rew | done layout: ONE device-to-host copy per step.
@@ -196,29 +281,29 @@ class FixedWingVecEnv:
 
     def seed(self, seed=None):
         """Env i is seeded seed + i (subproc_vec_env.py:120-123): here the Philox key is `seed` and the counter
-        carries the global env id, which gives every env its own stream.  Takes effect at the next reset."""
+        carries the global env id, which gives every env its own stream.  Like the reference's env.seed
+        (fixed_wing.py:324-332) it re-keys the random draws of every reset from now on; running episodes continue."""
         seed = 0 if seed is None else int(seed)
         self._build_kw["seed"] = seed
-        self._rebuild()
+        self._apply_config()
         return [seed + i for i in range(self.num_envs)]
 
-    def _rebuild(self):
+    def _apply_config(self):
+        """Push the reset-time part of the configuration (curriculum-scaled init / target ranges, seed) to the live
+        handle (fw_set_config): env state, device pointers and any CUDA graph captured over the step stay valid."""
         self.cfg = build_config(**self._build_kw)
-        self.sim.close()
-        self.sim = bt.BatchedFixedWing(self.num_envs, cfg=self.cfg, device=self.device.index)
+        self.sim.set_config(self.cfg)
 
     def _indices(self, indices):
-        if indices is None:
-            return list(range(self.num_envs))
-        if isinstance(indices, int):
-            return [indices]
-        return list(indices)
+        return list(self._get_indices(indices))
 
     def get_attr(self, attr_name, indices=None):
         idx = self._indices(indices)
         if attr_name == "simulator":
             return [_SimulatorView(self, i) for i in idx]
-        if attr_name == "cfg":
+        if attr_name == "cfg":                       # the env's config dict (evaluate_controller.py:123)
+            return [self.env_config for _ in idx]
+        if attr_name == "fw_config":
             return [self.cfg for _ in idx]
         if attr_name == "target":
             t = self.sim.get_field(bt.FIELD_TARGET).cpu().numpy()
@@ -241,6 +326,8 @@ class FixedWingVecEnv:
             return self._set_curriculum_level(*args, **kwargs)
         if method_name == "seed":
             return self.seed(*args, **kwargs)
+        if method_name == "render":                 # plots are out of scope: accepted, no-op
+            return [None for _ in idx]
         raise NotImplementedError("env_method(%r)" % method_name)
 
     def _set_curriculum_level(self, level):
@@ -248,7 +335,7 @@ class FixedWingVecEnv:
         assert 0 <= level <= 1
         self.curriculum_level = float(level)
         self._build_kw["curriculum_level"] = float(level)
-        self._rebuild()
+        self._apply_config()
         return [None] * self.num_envs
 
     def _reset_indices(self, idx, state=None, target=None, turbulence_noise=None):
@@ -273,6 +360,8 @@ class FixedWingVecEnv:
         return [obs[i].copy() for i in idx]
 
     # ------------------------------------------------------------------ info dicts
+    _done_info = staticmethod(_done_info)
+
     def state_dict(self, i):
         y = self.sim.get_field(bt.FIELD_Y)[i].cpu().numpy()
         e = self.sim.get_field(bt.FIELD_EULER)[i].cpu().numpy()
@@ -315,18 +404,20 @@ class FixedWingVecEnv:
                 return infos
             rows = (self.sim.episode_info_rows(torch.as_tensor(done_idx, device=self.device)) if done_idx.size
                     else np.zeros((0, 31 + self.sim.obs_dim)))
+        waypoint = self.cfg.env_kind != 0
         if compat:
             tgt = self.sim.get_field(bt.FIELD_TARGET).cpu().numpy()
-            infos = [{"target": dict(zip(TARGET_STATES, map(float, tgt[i])))} for i in range(n)]
+            names = ("position_n", "position_e", "position_d") if waypoint else TARGET_STATES
+            infos = [{"target": dict(zip(names, map(float, tgt[i])))} for i in range(n)]
         now = round(time.time() - self._t_start, 6)
         term_obs_all = rows[:, 31:].astype(np.float32)
         generic = bool(self.cfg.obs_generic)
         for j, (row, i) in enumerate(zip(rows[:, :31].tolist(), done_idx.tolist())):
             term_obs = term_obs_all[j]
-            info = _done_info(row, term_obs, now)
+            info = self._done_info(row, term_obs, now)
             if compat:
                 info.update(infos[i])                 # keeps the per-step "target" entry of compat mode
-            elif not generic:
+            elif not generic and not waypoint:
                 # fixed_wing.py:626 reports the finished episode's target; it sits in terminal_observation[6:9]
                 info["target"] = dict(zip(TARGET_STATES, term_obs[6:9].tolist()))
             infos[i] = info
@@ -385,7 +476,6 @@ class FixedWingAircraft:
 
     def set_curriculum_level(self, level):
         self._v.env_method("set_curriculum_level", level)
-        self._v.sim.enable_f64_outputs()
 
     def reset(self, state=None, target=None, **sim_reset_kw):
         return self._v.env_method("reset", indices=[0], state=state, target=target,
@@ -428,56 +518,60 @@ def waypoint_tasks_to_array(tasks):
     return out
 
 
-class WaypointVecEnv:
-    """`FixedWingAircraft_simple` (magpie/magpy/simple_train.py:197-702) behind the VecEnv step contract: every env flies
-    the waypoint chain of its task; reaching a waypoint (0.5 m box) teleports to the next leg's start, reward
-    exp(-sum |position error| / 6), 12 raw states observed, 500 steps per episode, commands passed straight through."""
+class WaypointVecEnv(FixedWingVecEnv):
+    """`FixedWingAircraft_simple` (magpie/magpy/simple_train.py:197-702) behind the same VecEnv surface as
+    FixedWingVecEnv: every env flies the waypoint chain of its task; reaching a waypoint (0.5 m box) teleports to the next
+    leg's start, reward exp(-sum |position error| / 6), 12 raw states observed, 500 steps per episode, commands passed
+    straight through.  Episode-end infos carry termination / terminal_observation / episode (this env computes no
+    metrics, simple_train.py:501-503)."""
 
     def __init__(self, num_envs, tasks, task_of_env=None, device=0, seed=0, env_id_offset=0, sim_config_kw=None,
-                 config_kw=None, precision="f64", integrator="rk45", rk4_substeps=4):
-        self.cfg = build_config(env_kind="waypoint", config_kw=config_kw, sim_config_kw=sim_config_kw, seed=seed,
-                                env_id_offset=env_id_offset, precision=precision, integrator=integrator,
-                                rk4_substeps=rk4_substeps)
-        self.num_envs = int(num_envs)
-        self.sim = bt.BatchedFixedWing(self.num_envs, cfg=self.cfg, device=device)
+                 config_kw=None, precision="f64", integrator="rk45", rk4_substeps=4, info_mode="lazy",
+                 copy_outputs=False):
+        self._build_kw = dict(env_kind="waypoint", config_kw=config_kw, sim_config_kw=sim_config_kw, seed=seed,
+                              env_id_offset=env_id_offset, precision=precision, integrator=integrator,
+                              rk4_substeps=rk4_substeps)
+        self.cfg = build_config(**self._build_kw)
+        self.env_config, self.sim_config = resolve_configs(None, None, config_kw, sim_config_kw, env_kind="waypoint")
+        self.sim = bt.BatchedFixedWing(int(num_envs), cfg=self.cfg, device=device)
         self.device = self.sim.device
         self.tasks = tasks if isinstance(tasks, np.ndarray) else waypoint_tasks_to_array(tasks)
         if task_of_env is None:
-            task_of_env = np.arange(self.num_envs) % self.tasks.shape[0]
+            task_of_env = np.arange(int(num_envs)) % self.tasks.shape[0]
         self.task_of_env = np.asarray(task_of_env, dtype=np.int32)
         self.sim.set_waypoint_tasks(self.tasks, self.task_of_env)
         f32max = np.finfo(np.float32).max
-        self.observation_space = Box(np.full(12, -f32max), np.full(12, f32max))
-        self.action_space = Box(np.array([-1, -1, 0]), np.array([1, 1, 1]))        # simple_train.py:275-279
+        self._init_vecenv(num_envs, make_box(np.full(12, -f32max), np.full(12, f32max)),
+                          make_box(np.array([-1, -1, 0]), np.array([1, 1, 1])))          # simple_train.py:275-279
+        self.curriculum_level = 1.0
+        self._init_host_edge(info_mode, copy_outputs)
 
     def reset_task(self, task_of_env):
         """reset_task(idx) for every env (simple_train.py:368-375): takes effect at the next reset."""
         self.task_of_env = np.asarray(task_of_env, dtype=np.int32)
         self.sim.set_waypoint_tasks(self.tasks, self.task_of_env)
 
-    def reset_tensor(self):
-        return self.sim.reset()
+    def env_method(self, method_name, *args, indices=None, **kwargs):
+        if method_name == "reset_task":
+            idx = self._indices(indices)
+            toe = self.task_of_env.copy()
+            toe[idx] = args[0] if args else kwargs["idx"]
+            self.reset_task(toe)
+            return [None for _ in idx]
+        if method_name in ("set_curriculum_level", "reset"):
+            raise NotImplementedError("env_method(%r) on the waypoint env (simple_train.py has no such hook)" % method_name)
+        return super().env_method(method_name, *args, indices=indices, **kwargs)
 
-    def step_tensor(self, actions):
-        return self.sim.step(actions, auto_reset=True)
+    def get_attr(self, attr_name, indices=None):
+        if attr_name == "target":
+            g = self.sim.get_field(bt.FIELD_TARGET).cpu().numpy()
+            return [dict(zip(("position_n", "position_e", "position_d"), map(float, g[i]))) for i in self._indices(indices)]
+        return super().get_attr(attr_name, indices)
 
-    def reset(self):
-        return self.sim.reset().cpu().numpy()
-
-    def step(self, actions):
-        a = torch.as_tensor(np.asarray(actions, dtype=np.float32), device=self.device).contiguous()
-        obs, rew, done = self.sim.step(a, auto_reset=True)
-        done_np = done.cpu().numpy().astype(bool)
-        infos = [_EMPTY_INFO] * self.num_envs
-        if done_np.any():
-            idx = np.flatnonzero(done_np)
-            rows = self.sim.episode_info_rows(torch.as_tensor(idx, device=self.device))
-            infos = list(infos)
-            for row, i in zip(rows, idx):
-                term = int(row[30])
-                infos[i] = {"termination": TERM_NAMES.get(term, term), "terminal_observation": row[31:].astype(np.float32),
-                            "episode": {"r": float(row[28]), "l": int(row[29])}}
-        return obs.cpu().numpy(), rew.cpu().numpy(), done_np, infos
+    def _done_info(self, row, term_obs, now):
+        term = int(row[30])
+        return {"termination": TERM_NAMES.get(term, term), "terminal_observation": term_obs,
+                "episode": {"r": row[28], "l": int(row[29]), "t": now}}
 
     def close(self):
         self.sim.close()
