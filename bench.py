@@ -2,7 +2,9 @@
 """bench.py — env-steps/sec of the batched fixed-wing env step (x8 UAV, Dryden turbulence) on N B200s.
 
   python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torch.distributed.run, one rank per GPU)
-  python bench.py --impl reference ...                     (CPU arm: the oracle port on the box's host cores)
+  python bench.py --impl reference ...                     (CPU arm: the C port of the reference on every host thread;
+                                                            the line also carries the UNMODIFIED Python reference stepped in
+                                                            a SubprocVecEnv on the same cores, from baseline/_ref)
 
 Workload (BASELINE.json configs[2], "C3"): 65536 envs PER GPU (weak scaling; envs are independent, no collective
 on the step), default attitude task, light Dryden turbulence + steady wind U(-8, 8), actions U(-1,1)^3 that change
@@ -139,9 +141,79 @@ def cfg_with_offset(cfg, off):
     return c
 
 
+def python_reference_worker(budget_s):
+    """Runs in a fresh CPU-only process (fork-safe: no CUDA context): the unmodified reference — pyfly + fixed-wing-gym
+    under the stable-baselines3 fork's SubprocVecEnv, one worker per host core (BASELINE.md §3 recipe) — imported
+    from /root/reference or its mirror baseline/_ref (oracle/refshim.py fabricates the absent gym / matplotlib)."""
+    from oracle import refshim
+    if not refshim.available():
+        print(json.dumps({"unavailable": "reference libraries neither mounted nor mirrored under baseline/_ref"}))
+        return
+    import warnings
+    warnings.filterwarnings("ignore")
+    refshim.install()
+    from gym_fixed_wing.fixed_wing import FixedWingAircraft
+    from stable_baselines3.common.vec_env import SubprocVecEnv
+    C = os.cpu_count() or 1
+
+    def make_env(i):
+        def f():
+            env = FixedWingAircraft(refshim.GYM_CONFIG)
+            env.seed(i)
+            return env
+        return f
+
+    # C1: one env, random actions, reset on done (bounded sample of the 1000-step workload)
+    env = make_env(0)()
+    env.reset()
+    rs = np.random.RandomState(1)
+    n1 = 0
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < 0.15 * budget_s:
+        _, _, done, _ = env.step(rs.uniform(-1, 1, 3))
+        n1 += 1
+        if done:
+            env.reset()
+    single = n1 / (time.perf_counter() - t0)
+    # SubprocVecEnv over every core
+    venv = SubprocVecEnv([make_env(i) for i in range(C)], start_method="fork")
+    venv.reset()
+    rs = np.random.RandomState(0)
+    for _ in range(5):
+        venv.step(rs.uniform(-1, 1, (C, 3)))
+    k = 0
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < 0.6 * budget_s or k < 20:
+        venv.step(rs.uniform(-1, 1, (C, 3)))
+        k += 1
+    dt = time.perf_counter() - t0
+    venv.close()
+    print(json.dumps({"value": C * k / dt, "unit": UNIT, "cores": C, "workers": C, "kind": "reference",
+                      "single_env_value": single,
+                      "sample": "SubprocVecEnv(start_method=fork) of %d x FixedWingAircraft(fixed_wing_config.json), turbulence "
+                                "light, U(-1,1)^3 actions, %d timed vec steps (%.1f s); single env: %d steps" % (C, k, dt, n1)}))
+
+
+def python_reference_rate(budget_s):
+    """The Python reference on the box's host cores, measured in a subprocess; {"unavailable": ...} if it cannot run."""
+    try:
+        env = dict(os.environ, CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="1", MKL_NUM_THREADS="1")
+        res = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "python-reference", "--cpu-budget-s",
+                              str(budget_s)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env,
+                             timeout=60 + 4 * budget_s)
+        lines = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
+        if res.returncode != 0 or not lines:
+            return {"unavailable": "python reference run failed: " + (res.stderr.strip().splitlines() or ["?"])[-1][:200]}
+        return json.loads(lines[-1])
+    except Exception as e:                                   # a baseline that cannot be had is reported, not fatal
+        return {"unavailable": repr(e)[:200]}
+
+
 def run_reference_arm(args):
-    """--impl reference: the reference's CPU implementation of the path.  The reference is pure Python and cannot
-    travel to the GPU box (no /root/reference there), so this arm times the oracle port with every host thread."""
+    """--impl reference: the reference's CPU implementation of the path on the box's host cores.  `value` is the C port
+    of the reference (oracle/fw_oracle.c) on every host thread — the FASTEST CPU figure we can produce, so the driver's
+    ratio is conservative; one timed "step" = every thread advances its 128 envs by 16 env-steps in one C call.  The
+    unmodified Python reference (SubprocVecEnv over the same cores) is timed once and reported beside it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -149,7 +221,7 @@ def run_reference_arm(args):
     cfg = build_config(sim_config_kw={"turbulence": True}, seed=0)
     threads = os.cpu_count() or 1
     from oracle import fw_oracle as O
-    per = 512
+    per, inner = 128, 16
     batches = [O.OracleBatch(cfg_with_offset(cfg, i * per), per) for i in range(threads)]
     for b in batches:
         b.reset()
@@ -158,7 +230,7 @@ def run_reference_arm(args):
     pool = ThreadPoolExecutor(max_workers=threads)
 
     def one_step(step0):
-        list(pool.map(lambda b: b.step_random(1, 1, step0), batches))
+        list(pool.map(lambda b: b.step_random(inner, 1, step0 * inner), batches))
 
     for w in range(args.warmup):
         one_step(w)
@@ -166,16 +238,18 @@ def run_reference_arm(args):
     for k in range(args.steps):
         one_step(args.warmup + k)
     dt = time.perf_counter() - t0
-    n = threads * per
+    n = threads * per * inner
     value = n * args.steps / dt
-    sample = "%d threads x %d envs, %d steps of the C3 workload per timed step" % (threads, per, 1)
+    sample = "%d threads x %d envs x %d env-steps of the C3 workload per timed step" % (threads, per, inner)
+    pyref = python_reference_rate(args.cpu_budget_s)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(ENVS_PER_GPU),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
-                             "note": "C restatement of the pure-Python reference; the Python reference itself ran at "
-                                     "126 env-steps/s/core in the build container (BASELINE.md §2)"},
+                             "note": "C restatement of the pure-Python reference (the fastest CPU arm available); the "
+                                     "reference itself is in python_reference",
+                             "python_reference": pyref},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -190,15 +264,19 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "python-reference"])
     ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
     ap.add_argument("--cpu-budget-s", type=float, default=12.0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the fp32 / PPO side measurements")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference" and args.steps * 0.12 > 240:      # keep the reference arm within a few minutes
+        args.steps = 2000
     if args.impl == "reference":
         return run_reference_arm(args)
+    if args.impl == "python-reference":
+        return python_reference_worker(args.cpu_budget_s)
 
     import torch
     import torch.distributed as dist
@@ -234,8 +312,9 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    def time_device_steps(env, pool, flush):
+    def time_device_steps(env, pool, flush, n_envs=None):
         """K launches, per-launch events, L2 flush between; returns (total ms of the launches, nfev stats)."""
+        n_envs = n if n_envs is None else n_envs
         for w in range(W):
             env.step(pool[w % len(pool)])
         nf_sum = np.zeros(2)
@@ -250,7 +329,7 @@ def main():
             nf_acc += env.get_field(bt.FIELD_NFEV).to(torch.float64).sum(0)   # outside the event pair
         barrier()
         ms = sum(a.elapsed_time(b) for a, b in ev)
-        nf_sum = (nf_acc / (n * K)).cpu().numpy()
+        nf_sum = (nf_acc / (n_envs * K)).cpu().numpy()
         return ms, nf_sum
 
     # ---- main arm: fp64 exact mode ----
@@ -284,6 +363,12 @@ def main():
     env.set_profiling(False)
     nf_prof = (nf_prof / (n * KP)).cpu().numpy()
     peaks, peak_kind = measured_peaks()
+    # numbers that only a profiler can give are READ from the committed capture summary, never typed in here
+    ncu = {}
+    ncu_path = os.path.join(ROOT, "profiles", "ncu_attempt_kernel.json")
+    if os.path.exists(ncu_path):
+        with open(ncu_path) as f:
+            ncu = json.load(f)
     fp64_peak = bt.measure_fma_peak(local, "f64")
     fp32_peak = bt.measure_fma_peak(local, "f32")
     # algorithmic flops of one attempt-kernel launch: every RHS evaluation after the two of the init kernel, plus the
@@ -305,11 +390,9 @@ def main():
                 "kernel_shares": {"rk45_init_kernel": prof["init_ms"] / ksum, "rk45_attempt_kernel": prof["integrate_ms"] / ksum,
                                   "head_kernel": prof["head_ms"] / ksum,
                                   "ms": [prof["init_ms"], prof["integrate_ms"], prof["head_ms"]]},
-                "traffic": 2.65e7,
-                "traffic_note": "dram__bytes_read+write of one rk45_attempt_kernel launch, ncu --set full capture "
-                                "(profiles/): the kernel is compute/latency bound, DRAM at ~2 % of peak",
-                "executed_fp64_flop_per_env_step_ncu": 24830,
-                "executed_note": "2*DFMA + DMUL + DADD thread instructions of the three kernels / 65536 envs (n_rhs 24.05)",
+                "traffic": ncu.get("attempt_kernel_dram_bytes_per_launch"),
+                "traffic_note": ncu.get("note", "no ncu capture committed (profiles/ncu_attempt_kernel.json absent)"),
+                "executed_fp64_flop_per_env_step_ncu": ncu.get("executed_fp64_flop_per_env_step"),
                 "whole_step": {"achieved": step_tf, "frac": step_tf / fp64_peak, "flops_per_env_step": flops_env_step,
                                "ms": ms_per_step},
                 "hbm": {"achieved": hbm_gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
@@ -359,6 +442,91 @@ def main():
                                   "parity path"}
             e2.close()
 
+    # ---- BASELINE.json configs[1] ("C2"): 4096 envs, no turbulence, random actions — the pure dynamics step ----
+    configs = {}
+    if not args.no_extra:
+        c2 = build_config(sim_config_kw={"turbulence": False}, precision="f64", integrator="rk45", seed=0,
+                          env_id_offset=rank * 4096)
+        e2 = bt.BatchedFixedWing(4096, cfg=c2, device=local)
+        e2.reset()
+        pool2 = [p_[:4096].contiguous() for p_ in pool]
+        ms2, nf2 = time_device_steps(e2, pool2, flush, n_envs=4096)
+        ms2 = max_over_ranks(ms2)
+        configs["C2"] = {"workload": "4096 envs/GPU, turbulence off, U(-1,1)^3 actions, fp64 exact", "value": world * 4096 * K / (ms2 * 1e-3),
+                         "unit": UNIT, "ms_per_step": ms2 / K, "mean_rhs_evals": float(nf2[0]), "mean_rk_attempts": float(nf2[1]),
+                         "note": "4096 envs are 11 % of one wave of the persistent attempt kernel (37 888 lanes): the step "
+                                 "lasts as long as its slowest env (max attempts x per-attempt latency), not as long as its work"}
+        e2.close()
+        # ---- C3 as written ("65536 envs ... sharded across 1/2/4/8"): STRONG scaling, 65536 / N envs per GPU ----
+        if world > 1:
+            ns = ENVS_PER_GPU // world
+            c3s = build_config(sim_config_kw={"turbulence": True}, precision="f64", integrator="rk45", seed=0,
+                               env_id_offset=rank * ns)
+            e3 = bt.BatchedFixedWing(ns, cfg=c3s, device=local)
+            e3.reset()
+            pool3 = [p_[:ns].contiguous() for p_ in pool]
+            ms3, _ = time_device_steps(e3, pool3, flush, n_envs=ns)
+            ms3 = max_over_ranks(ms3)
+            configs["C3_strong"] = {"workload": "65536 envs in total, %d per GPU" % ns, "value": world * ns * K / (ms3 * 1e-3),
+                                    "unit": UNIT, "ms_per_step": ms3 / K, "scaling": "strong"}
+            e3.close()
+        else:
+            configs["C3_strong"] = {"workload": "65536 envs in total = the headline line at n_gpus 1", "value": value,
+                                    "unit": UNIT, "ms_per_step": ms_per_step, "scaling": "strong"}
+
+    # ---- the HBM-bound kernels of the PPO path at C4 sizes: GAE and the per-step rollout glue ----
+    hbm_kernels = {}
+    if not args.no_extra:
+        hbm_peak = peaks.get("hbm_gbs")
+        Tg, Ng = 2048, 8192                                   # SB3's default n_steps at 8192 envs/GPU: 335 MB per pass
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(7)
+        rew_g, val_g = (torch.randn(Tg, Ng, device=dev, generator=gen) for _ in range(2))
+        done_g = (torch.rand(Tg, Ng, device=dev, generator=gen) < 0.0005).float()
+        lv_g, ld_g = torch.randn(Ng, device=dev, generator=gen), torch.zeros(Ng, dtype=torch.uint8, device=dev)
+        for _ in range(3):
+            bt.gae(rew_g, val_g, done_g, lv_g, ld_g)
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
+        for a_, b_ in evs:                                    # 335 MB of inputs + outputs per pass: larger than L2
+            a_.record(); bt.gae(rew_g, val_g, done_g, lv_g, ld_g); b_.record()
+        torch.cuda.synchronize()
+        ms_g = float(np.median([a_.elapsed_time(b_) for a_, b_ in evs]))
+        gbs = 20.0 * Tg * Ng / (ms_g * 1e-3) / 1e9
+        hbm_kernels["gae"] = {"kernel": "gae_stream_kernel (fw_gae)", "T": Tg, "N": Ng, "bytes_per_transition": 20,
+                              "ms": ms_g, "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                              "timing": "median of 10 launches, CUDA events; working set 335 MB > L2"}
+        del rew_g, val_g, done_g
+        # fw_rollout_post_step: VecNormalize + RunningMeanStd + RolloutBuffer.add for one step of 8192 envs
+        from tum_adlr_deep_reinforcement_learning_b200.buffers import DeviceVecNormalize, RolloutBuffer, fused_post_step
+        nb, od = 8192, 14
+        norm_b = DeviceVecNormalize(nb, obs_dim=od, device=dev)
+        buf_b = RolloutBuffer(64, nb, obs_dim=od, device=dev)
+        ob_b, rw_b = torch.randn(nb, od, device=dev), torch.randn(nb, device=dev)
+        dn_b = torch.zeros(nb, dtype=torch.uint8, device=dev)
+        ac_b, vl_b, lp_b = torch.randn(nb, 3, device=dev), torch.randn(nb, device=dev), torch.randn(nb, device=dev)
+        lo_b, ld_b = torch.zeros(nb, od, device=dev), torch.zeros(nb, device=dev)
+        rr_b, rl_b = torch.zeros(nb, dtype=torch.float64, device=dev), torch.zeros(nb, dtype=torch.float64, device=dev)
+        es_b, sc_b = torch.zeros(3, dtype=torch.float64, device=dev), torch.zeros(3 * 256 + 3, dtype=torch.float64, device=dev)
+        times = []
+        for it in range(40):
+            buf_b.pos = it % 64
+            flush.add_(1.0)
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record()
+            fused_post_step(norm_b, buf_b, ob_b, rw_b, dn_b, ac_b, vl_b, lp_b, lo_b, ld_b, rr_b, rl_b, es_b, sc_b)
+            b_.record()
+            torch.cuda.synchronize()
+            if it >= 8:
+                times.append(a_.elapsed_time(b_))
+        ms_b = float(np.median(times))
+        bytes_env = 4 * (od + 1 + 3 + 1 + 1) + 1 + 2 * 4 * od + 2 * 4 + 2 * 8 * 3 + 4 * (od + 3 + 4)   # in, state r+w, row out
+        gbs = bytes_env * nb / (ms_b * 1e-3) / 1e9
+        hbm_kernels["rollout_post_step"] = {"kernel": "rollout_stats/moments/apply kernels (fw_rollout_post_step)", "N": nb,
+                                            "bytes_per_env": bytes_env, "ms": ms_b, "achieved": gbs, "peak": hbm_peak,
+                                            "unit": "GB/s", "frac": gbs / hbm_peak,
+                                            "note": "2.7 MB per call = 0.4 us at the HBM peak: three dependent launches, bound by "
+                                                    "launch latency, not bandwidth; inside ppo.PPO they are replayed from a CUDA graph"}
+
     # ---- PPO train env-steps/s (BASELINE.json second metric, config C4: 8192 envs/GPU, updates included) ----
     ppo = None
     if not args.no_extra:
@@ -368,6 +536,7 @@ def main():
         algo = PPO(venv, n_steps=n_steps, batch_size=n_ppo * n_steps // 8, n_epochs=10, ent_coef=0.01,
                    dist=dist if world > 1 else None)
         algo.learn(total_timesteps=3 * world * n_ppo * n_steps)        # warm-up: eager pass, CUDA-graph captures
+        assert algo._rollout_graph is not None and algo._train_graph, "PPO must run from captured CUDA graphs in the bench"
         barrier()
         t0 = time.perf_counter()
         algo.learn(total_timesteps=algo.num_timesteps + iters * world * n_ppo * n_steps)
@@ -375,7 +544,7 @@ def main():
         dt = max_over_ranks(time.perf_counter() - t0)
         ppo = {"value": iters * world * n_ppo * n_steps / dt, "unit": "env-steps/s (rollout + GAE + 10-epoch update)",
                "envs_per_gpu": n_ppo, "n_steps": n_steps, "minibatch": n_ppo * n_steps // 8, "n_epochs": 10,
-               "iterations_timed": iters, "ep_rew_mean": algo.logs[-1]["ep_rew_mean"],
+               "iterations_timed": iters, "ep_rew_mean": algo.logs[-1]["ep_rew_mean"], "cuda_graphs": True,
                "note": "policy 2x64 tanh MLP in PyTorch (split-K weight gradients), loss block fused in fw_ppo_loss, rollout "
                        "and minibatch update replayed as CUDA graphs (value branch on a second stream); one gradient all-reduce per optimiser step when "
                        "n_gpus > 1 (NCCL, captured in the update graph); learning curves in results/"}
@@ -394,8 +563,10 @@ def main():
         salgo.learn(total_timesteps=n0 + 1500 * 1024, log_every=10 ** 9)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        assert salgo._env_graph and salgo._train_graph, "SAC must run from captured CUDA graphs in the bench"
         sac = {"value": (salgo.num_timesteps - n0) / dt, "unit": "env-steps/s (1 env step of 1024 envs + 2 gradient steps of batch 4096)",
                "gradient_steps_per_s": 2 * (salgo.num_timesteps - n0) / 1024 / dt, "envs": 1024, "replay_capacity": 1_000_000,
+               "cuda_graphs": True,
                "note": "env step and gradient step replayed as CUDA graphs; networks 2x256 ReLU in PyTorch"}
         venv.close()
 
@@ -404,14 +575,15 @@ def main():
     if rank == 0 and world == 1:
         threads = os.cpu_count() or 1
         rate, sample = cpu_port_rate(cfg, args.cpu_budget_s, threads)
-        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+               "python_reference": python_reference_rate(args.cpu_budget_s)}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": workload_config(n), "roofline": roofline,
                 "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 4 * K, "gpu_launches_note": "rk45_init_kernel + rk45_attempt_kernel + head_kernel per step on the launch stream, refill_kernel on the side stream",
-                "clocks": clocks, "modes": extra, "ppo": ppo, "sac": sac}
+                "clocks": clocks, "modes": extra, "configs": configs, "hbm_kernels": hbm_kernels, "ppo": ppo, "sac": sac}
         print(json.dumps(line), flush=True)
     if world > 1:
         # CUDA graphs that contain NCCL kernels (the PPO update) are alive until interpreter shutdown, and

@@ -35,6 +35,10 @@ class Space:
         self.shape = None if shape is None else tuple(shape)
         self.dtype = None if dtype is None else np.dtype(dtype)
 
+    def seed(self, seed=None):                      # gym.Space.seed (BaseAlgorithm.set_random_seed calls it)
+        self._rng = np.random.RandomState(seed)
+        return [seed]
+
 
 class Box(Space):
     def __init__(self, low, high, shape=None, dtype=np.float32):

@@ -147,6 +147,23 @@ def test_gae_bit_exact_vs_reference_fixture(cuda_device):
         assert np.array_equal(ret.cpu().numpy(), g[tag + "_ret"]), tag
 
 
+def test_gae_streaming_kernel_bit_exact_vs_oracle(cuda_device):
+    """The cp.async streaming GAE kernel (strips of 32 / 16 / 8 env columns, tiles of 32 / 64 rows, ragged last tile) and
+    the plain fallback, against the oracle's restatement of buffers.py:304-333 — every bit of advantages and returns."""
+    import torch
+    from oracle import fw_oracle as O
+    from tum_adlr_deep_reinforcement_learning_b200.batched import gae
+    rs = np.random.RandomState(5)
+    for T, N in ((300, 1000), (131, 9472), (70, 20480), (2, 64), (1, 64), (65, 1001), (2048, 512)):
+        rew, val = rs.standard_normal((T, N)).astype(np.float32), rs.standard_normal((T, N)).astype(np.float32)
+        done = (rs.uniform(size=(T, N)) < 0.02).astype(np.float32)
+        lv, ld = rs.standard_normal(N).astype(np.float32), (rs.uniform(size=N) < 0.3).astype(np.uint8)
+        adv, ret = gae(*(torch.as_tensor(x).cuda() for x in (rew, val, done, lv, ld)))
+        adv_ref, ret_ref = O.gae(rew, val, done, lv, ld)
+        assert np.array_equal(adv.cpu().numpy(), adv_ref), (T, N)
+        assert np.array_equal(ret.cpu().numpy(), ret_ref), (T, N)
+
+
 def test_general_observation_layout_cnn_config(cuda_device):
     """The reference's CNN-controller config (5 x 12 observation matrix: history rows, relative targets, action
     windows shifted in time) on the CUDA path against the live-reference fixture and, with Philox init_noise and

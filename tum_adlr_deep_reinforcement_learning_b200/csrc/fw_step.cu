@@ -1279,7 +1279,7 @@ struct FwHandle {
     void* rc_dev;                          // ResetCfg<T> in device memory (fw_set_config rewrites it)
     Scratch<double> w64;
     Scratch<float> w32;
-    int sm_count;
+    int sm_count, att_blocks_per_sm;
     unsigned long long random_step;
     // precomputed next-episode rows (Spare) and the side stream that refills them
     void* r2_buf; int32_t* i2_buf; void* err2; float* spare_obs; double* spare_obs64; int32_t* done_list;
@@ -1366,13 +1366,13 @@ template <typename T, bool TURB, int NT>
 static int launch_rk45(FwHandle* h, const DCfg<T>& c, const Soa<T>& S, const Scratch<T>& W, const Spare<T>& P, const StepIO& io, cudaStream_t st) {
     const size_t smem = (size_t)6 * FW_NS * NT * sizeof(T);
     auto k = rk45_attempt_kernel<T, TURB, NT>;
-    static int blocks_per_sm = 0;
-    if (!blocks_per_sm) {
+    // per handle: function attributes and occupancy belong to the handle's device (one handle runs one instantiation)
+    if (!h->att_blocks_per_sm) {
         CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k, NT, smem));
-        if (blocks_per_sm < 1) blocks_per_sm = 1;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->att_blocks_per_sm, k, NT, smem));
+        if (h->att_blocks_per_sm < 1) h->att_blocks_per_sm = 1;
     }
-    int grid = h->sm_count * blocks_per_sm;
+    int grid = h->sm_count * h->att_blocks_per_sm;
     const int need = (h->n + NT - 1) / NT;
     if (grid > need) grid = need;
     const int g0 = (h->n + 127) / 128, g0h = (h->n + 63) / 64;

@@ -206,8 +206,11 @@ class PPO:
     def __init__(self, env: FixedWingVecEnv, n_steps=32, batch_size=32768, n_epochs=10, learning_rate=3e-4, gamma=0.99,
                  gae_lambda=0.95, clip_range=0.2, ent_coef=0.0, vf_coef=0.5, max_grad_norm=0.5, normalize=True,
                  seed=0, dist=None, use_cuda_graph=True, fused_loss=True, fused_rollout=True,
-                 flat_optimizer=True):
+                 flat_optimizer=True, allow_eager_fallback=False):
         self.env = env
+        # a failed CUDA-graph capture raises unless this is set: a silently eager run is ~10x slower and would make
+        # every throughput figure taken from it meaningless
+        self.allow_eager_fallback = bool(allow_eager_fallback)
         self.device = env.device
         self.n_envs = env.num_envs
         self.n_steps, self.batch_size, self.n_epochs = n_steps, batch_size, n_epochs
@@ -321,7 +324,10 @@ class PPO:
                 with torch.cuda.graph(g):
                     self._rollout_body()
                 self._rollout_graph = g
-            except Exception as e:                        # capture is an optimisation, never a requirement
+            except Exception as e:
+                if not self.allow_eager_fallback:
+                    raise RuntimeError("PPO: CUDA-graph capture of the rollout failed (pass allow_eager_fallback=True "
+                                       "or use_cuda_graph=False to run eagerly)") from e
                 self.use_cuda_graph = False
                 self._rollout_graph = None
                 self.logs.append({"cuda_graph_disabled": repr(e)})
@@ -401,6 +407,10 @@ class PPO:
                 dst.copy_(f[:bs])
             self._pl = torch.zeros((), device=self.device)
             self._vl = torch.zeros((), device=self.device)
+            # The warm-up below runs real optimiser steps on the first (unshuffled) rows, which the reference's
+            # PPO.train never performs: snapshot weights and optimiser state and put them back afterwards, so that the
+            # graphed and the eager path produce the same sequence of updates from the first iteration on.
+            snap = self._snapshot_optimizer()
             side = torch.cuda.Stream(self.device)
             side.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(side):                 # warm-up on a side stream as torch.cuda.graph requires
@@ -416,9 +426,13 @@ class PPO:
                     self._vl.copy_(vl)
                 self._train_graph = g
             except Exception as e:
+                if not self.allow_eager_fallback:
+                    raise RuntimeError("PPO: CUDA-graph capture of the minibatch update failed (pass "
+                                       "allow_eager_fallback=True or use_cuda_graph=False to run eagerly)") from e
                 self.logs.append({"train_cuda_graph_disabled": repr(e)})
                 self._train_graph = False
                 torch.cuda.synchronize(self.device)
+            self._restore_optimizer(snap)
         policy_loss = value_loss = None
         for epoch in range(self.n_epochs):
             perm = torch.randperm(total, device=self.device)
@@ -434,6 +448,33 @@ class PPO:
                     batch = RolloutBufferSamples(*(f.index_select(0, idx) for f in flat))
                     policy_loss, value_loss = self._minibatch_update(batch)
         return dict(policy_loss=policy_loss, value_loss=value_loss, std=torch.exp(self.policy.log_std).mean().detach())
+
+    def _snapshot_optimizer(self):
+        if self.flat_optimizer:
+            o = self.optimizer
+            return [t.clone() for t in (o.flat, o.exp_avg, o.exp_avg_sq, o.step_count)]
+        import copy
+        return (copy.deepcopy(self.policy.state_dict()), copy.deepcopy(self.optimizer.state_dict()))
+
+    def _restore_optimizer(self, snap):
+        if self.flat_optimizer:
+            o = self.optimizer
+            for dst, src in zip((o.flat, o.exp_avg, o.exp_avg_sq, o.step_count), snap):
+                dst.copy_(src)                       # in place: the captured graph holds these addresses
+            return
+        # torch.optim.Adam(capturable=True): state tensors are updated in place by the graph — restore in place too
+        cur_p, cur_o = self.policy.state_dict(), self.optimizer.state_dict()
+        for k, v in snap[0].items():
+            cur_p[k].copy_(v)
+        for pid, st in snap[1]["state"].items():
+            for k, v in st.items():
+                if torch.is_tensor(v):
+                    cur_o["state"][pid][k].copy_(v)
+        for pid in list(cur_o["state"].keys()):
+            if pid not in snap[1]["state"]:          # state created by the warm-up: back to "never stepped"
+                for k, v in cur_o["state"][pid].items():
+                    if torch.is_tensor(v):
+                        v.zero_()
 
     def learn(self, total_timesteps, log_interval=1, callback=None):
         if self._last_obs is None:

@@ -201,6 +201,9 @@ class SAC:
                         self._env_step_body(True, capturable=True)
                     self._env_graph = g
                 except Exception as e:
+                    if not getattr(self, "allow_eager_fallback", False):
+                        raise RuntimeError("SAC: CUDA-graph capture of the env step failed (set allow_eager_fallback or "
+                                           "use_cuda_graph=False to run eagerly)") from e
                     self.logs.append({"env_cuda_graph_disabled": repr(e)})
                     self._env_graph = False
                     torch.cuda.synchronize(self.device)
@@ -231,7 +234,10 @@ class SAC:
                     stats = self.train_step(capturable=True)
                     self._graph_stats = tuple(x.clone() for x in stats)
                 self._train_graph = g
-            except Exception as e:                     # capture is an optimisation, never a requirement
+            except Exception as e:
+                if not getattr(self, "allow_eager_fallback", False):
+                    raise RuntimeError("SAC: CUDA-graph capture of the gradient step failed (set allow_eager_fallback or "
+                                       "use_cuda_graph=False to run eagerly)") from e
                 self.logs.append({"cuda_graph_disabled": repr(e)})
                 self.use_cuda_graph = False
                 torch.cuda.synchronize(self.device)

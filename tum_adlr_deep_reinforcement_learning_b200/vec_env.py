@@ -35,6 +35,9 @@ class Box:
         self.shape = self.low.shape
         self.dtype = np.dtype(dtype)
 
+    def seed(self, seed=None):
+        return [seed]
+
     def sample(self):
         lo = np.where(np.isfinite(self.low) & (np.abs(self.low) < 1e30), self.low, -1.0)
         hi = np.where(np.isfinite(self.high) & (np.abs(self.high) < 1e30), self.high, 1.0)
