@@ -212,7 +212,7 @@ def python_reference_rate(budget_s):
 def run_reference_arm(args):
     """--impl reference: the reference's CPU implementation of the path on the box's host cores.  `value` is the C port
     of the reference (oracle/fw_oracle.c) on every host thread — the FASTEST CPU figure we can produce, so the driver's
-    ratio is conservative; one timed "step" = every thread advances its 128 envs by 16 env-steps in one C call.  The
+    ratio is conservative; one timed "step" = every thread advances its 128 envs by 64 env-steps in one C call.  The
     unmodified Python reference (SubprocVecEnv over the same cores) is timed once and reported beside it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -221,7 +221,7 @@ def run_reference_arm(args):
     cfg = build_config(sim_config_kw={"turbulence": True}, seed=0)
     threads = os.cpu_count() or 1
     from oracle import fw_oracle as O
-    per, inner = 128, 16
+    per, inner = 128, 64
     batches = [O.OracleBatch(cfg_with_offset(cfg, i * per), per) for i in range(threads)]
     for b in batches:
         b.reset()
@@ -271,8 +271,8 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the fp32 / PPO side measurements")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
-    if args.impl == "reference" and args.steps * 0.12 > 240:      # keep the reference arm within a few minutes
-        args.steps = 2000
+    if args.impl == "reference" and args.steps > 400:             # keep the reference arm within a few minutes
+        args.steps = 400
     if args.impl == "reference":
         return run_reference_arm(args)
     if args.impl == "python-reference":
@@ -497,7 +497,8 @@ def main():
                               "timing": "median of 10 launches, CUDA events; working set 335 MB > L2"}
         del rew_g, val_g, done_g
         # fw_rollout_post_step: VecNormalize + RunningMeanStd + RolloutBuffer.add for one step of 8192 envs
-        from tum_adlr_deep_reinforcement_learning_b200.buffers import DeviceVecNormalize, RolloutBuffer, fused_post_step
+        from tum_adlr_deep_reinforcement_learning_b200.buffers import (DeviceVecNormalize, RolloutBuffer, fused_post_step,
+                                                                        rollout_scratch_doubles)
         nb, od = 8192, 14
         norm_b = DeviceVecNormalize(nb, obs_dim=od, device=dev)
         buf_b = RolloutBuffer(64, nb, obs_dim=od, device=dev)
@@ -506,7 +507,7 @@ def main():
         ac_b, vl_b, lp_b = torch.randn(nb, 3, device=dev), torch.randn(nb, device=dev), torch.randn(nb, device=dev)
         lo_b, ld_b = torch.zeros(nb, od, device=dev), torch.zeros(nb, device=dev)
         rr_b, rl_b = torch.zeros(nb, dtype=torch.float64, device=dev), torch.zeros(nb, dtype=torch.float64, device=dev)
-        es_b, sc_b = torch.zeros(3, dtype=torch.float64, device=dev), torch.zeros(3 * 256 + 3, dtype=torch.float64, device=dev)
+        es_b, sc_b = torch.zeros(3, dtype=torch.float64, device=dev), torch.zeros(rollout_scratch_doubles(od), dtype=torch.float64, device=dev)
         times = []
         for it in range(40):
             buf_b.pos = it % 64

@@ -235,6 +235,18 @@ int fw_obs_dim(const FwHandle* h);   /* floats per observation row of this handl
  * the precomputed next-episode rows are recomputed there. */
 int fw_set_config(FwHandle* h, const FwConfig* cfg, void* stream);
 
+/* Checkpoint / resume (the reference checkpoints the policy and the VecNormalize statistics,
+ * common/base_class.py:560,645, vec_env/vec_normalize.py:222-243, and restarts every episode; here the envs themselves
+ * can be saved too).  The blob is ONE contiguous device buffer of fw_state_blob_size(h) bytes owned by the caller: a
+ * header (shape check) followed by the whole structure-of-arrays state, the per-env episode bookkeeping, the
+ * precomputed next-episode rows and the reset-time configuration (fw_set_config values).  fw_set_state_blob on a handle
+ * created with the same configuration and n_envs continues every episode bit-identically (turbulence streams included:
+ * they are functions of the stored filter states and Philox counters).  Not stored: an injected-noise buffer (caller
+ * memory, fw_reset) and profiling sums.  Asynchronous on `stream` except for the header check of fw_set_state_blob. */
+int64_t fw_state_blob_size(const FwHandle* h);
+int fw_get_state_blob(FwHandle* h, void* blob_dev, void* stream);
+int fw_set_state_blob(FwHandle* h, const void* blob_dev, void* stream);
+
 /* Measurement aid (no reference counterpart; bench.py's per-kernel roofline): with profiling on, every fw_step /
  * fw_step_random step records CUDA events on the launch stream around each of its kernels and ends with an event
  * synchronise; fw_get_profile returns the summed durations in ms of {init, integrate (RK45 attempt loop or RK4),
@@ -342,6 +354,8 @@ int fw_adam_clip_step(float* param_dev, const float* grad_dev, float* exp_avg_de
  * (common/vec_env/vec_normalize.py:106-127, common/running_mean_std.py:19-39), RolloutBuffer.add
  * (common/buffers.py:292-302; the row stores the PREVIOUS observation / done flags, on_policy_algorithm.py:178-180) and
  * Monitor-style episode totals (common/monitor.py:99-113).  All pointers are device pointers; statistics are float64. */
+#define FW_ROLLOUT_BLOCKS 64
+#define FW_ROLLOUT_SCRATCH(obs_dim) (3 * (obs_dim) + 4 + FW_ROLLOUT_BLOCKS * (2 * (obs_dim) + 5))
 typedef struct FwRolloutPost {
     /* this step */
     const float* obs_raw;      /* [n, obs_dim] raw observation returned by fw_step                                   */
@@ -360,7 +374,7 @@ typedef struct FwRolloutPost {
     double* ep_stats;          /* [3] += sum of finished returns, sum of finished lengths, number of finished         */
     /* rollout buffer row t */
     float* buf_obs; float* buf_actions; float* buf_rewards; float* buf_dones; float* buf_values; float* buf_log_probs;
-    double* scratch;           /* [3 * obs_dim + 3]                                                                   */
+    double* scratch;           /* [FW_ROLLOUT_SCRATCH(obs_dim)] doubles, zeroed once by the caller (holds a ticket counter) */
     int32_t n, obs_dim, act_dim;
     float gamma, clip_obs, clip_reward, epsilon;
     int32_t norm_obs, norm_reward, training;
@@ -372,7 +386,10 @@ int fw_rollout_post_step(const FwRolloutPost* p, void* stream);
  * state-independent log_std, common/distributions.py:130-175).  Inputs are the policy mean [B,3], the value head
  * output [B], log_std [3] and the rollout-buffer minibatch (actions [B,3], old_log_prob, advantages, returns [B]).
  * Outputs: losses_dev[3] = {loss, policy_loss, value_loss}; grad_mean_dev [B,3], grad_values_dev [B], grad_log_std_dev
- * [3] = d loss / d input (what autograd would hand to the networks' backward).  scratch_dev: 8 doubles. */
+ * [3] = d loss / d input (what autograd would hand to the networks' backward).  scratch_dev: FW_PPO_SCRATCH_DOUBLES
+ * doubles (sums are formed without floating-point atomics, block partials added in a fixed order: the same inputs give
+ * the same bits on every run). */
+#define FW_PPO_SCRATCH_DOUBLES (9 + 7 * 592)
 int fw_ppo_loss(const float* mean_dev, const float* values_dev, const float* log_std_dev, const float* actions_dev,
                 const float* old_log_prob_dev, const float* adv_dev, const float* returns_dev, int32_t batch,
                 float clip_range, float ent_coef, float vf_coef, double* scratch_dev, float* grad_mean_dev,

@@ -25,6 +25,7 @@ TRAJ_CASES = [
     ("traj_f32act", None, {"turbulence": False}, True),
     ("traj_turb", None, {"turbulence": True}, False),
     ("traj_turb_severe", None, {"turbulence": True, "turbulence_intensity": "severe"}, False),
+    ("traj_turb_moderate", None, {"turbulence": True, "turbulence_intensity": "moderate"}, False),
     ("traj_fail", None, {"turbulence": False}, False),
     ("traj_full400", {"steps_max": 400}, {"turbulence": False}, False),
     ("traj_full300_turb", {"steps_max": 300}, {"turbulence": True}, False),

@@ -209,6 +209,14 @@ def gen_turb():
     np.savez_compressed(os.path.join(HERE, "traj_turb_severe.npz"), **out)
 
 
+def gen_turb_moderate():
+    """Moderate Dryden intensity (the third setting of pyfly_config.json's turbulence_intensity) with injected noise."""
+    env = make_env(True, intensity="moderate")
+    rs = np.random.RandomState(2468)
+    out = run_episodes(env, 2, 160, rs, True, wind_mag=5.0, action_amp=1.1)
+    np.savez_compressed(os.path.join(HERE, "traj_turb_moderate.npz"), **out)
+
+
 def gen_fail():
     """Episodes started near/over the constraint envelope so that ConstraintException paths fire."""
     rs = np.random.RandomState(31337)
@@ -773,7 +781,7 @@ def gen_dryden():
 
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
-    jobs = {"waypoint": gen_waypoint, "targets": gen_targets, "resample": gen_resample, "reward": gen_reward, "cnn": gen_cnn, "params": gen_params, "traj": gen_traj, "turb": gen_turb, "fail": gen_fail, "full": gen_full,
+    jobs = {"waypoint": gen_waypoint, "targets": gen_targets, "resample": gen_resample, "reward": gen_reward, "cnn": gen_cnn, "params": gen_params, "traj": gen_traj, "turb": gen_turb, "turb_moderate": gen_turb_moderate, "fail": gen_fail, "full": gen_full,
             "pid": gen_pid, "gae": gen_gae, "vecnorm": gen_vecnorm, "ppo_update": gen_ppo_update, "curriculum": gen_curriculum, "dryden": gen_dryden}
     for name, fn in jobs.items():
         if what in (name, "all"):

@@ -15,7 +15,7 @@ from tum_adlr_deep_reinforcement_learning_b200 import config as C
 
 def test_library_exports_every_declared_symbol():
     hdr = open(os.path.join(ROOT, "include", "fwb200.h")).read()
-    declared = set(re.findall(r"^(?:int|const char\*)\s+(fw_\w+)\s*\(", hdr, flags=re.M))
+    declared = set(re.findall(r"^(?:int|int64_t|const char\*)\s+(fw_\w+)\s*\(", hdr, flags=re.M))
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
     L = _lib.lib()
     for sym in declared:

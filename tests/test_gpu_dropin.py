@@ -233,3 +233,75 @@ def test_reference_ppo_on_the_waypoint_adapter(cuda_device):
     with pytest.raises(RuntimeError):
         env.step_wait()
     env.close()
+
+
+def test_env_state_blob_round_trip(cuda_device):
+    """fw_get_state_blob / fw_set_state_blob: a handle restored from a blob continues every episode bit-identically —
+    through episode ends (the precomputed next-episode rows are part of the state) and after a live config change."""
+    import torch
+    from tum_adlr_deep_reinforcement_learning_b200 import batched as bt
+    from tum_adlr_deep_reinforcement_learning_b200._lib import FwError
+    from tum_adlr_deep_reinforcement_learning_b200.config import build_config
+    n = 300
+    kw = dict(sim_config_kw={"turbulence": True}, config_kw={"steps_max": 20}, seed=8)
+    a = bt.BatchedFixedWing(n, cfg=build_config(**kw))
+    a.enable_f64_outputs()
+    a.reset()
+    rs = np.random.RandomState(2)
+    acts = [torch.as_tensor(rs.uniform(-1, 1, (n, 3)).astype(np.float32)).cuda() for _ in range(70)]
+    for t in range(13):
+        a.step(acts[t])
+    a.set_config(build_config(curriculum_level=0.4, **dict(kw, seed=9)))
+    for t in range(13, 27):
+        a.step(acts[t])
+    blob = a.get_state().cpu()
+    b = bt.BatchedFixedWing(n, cfg=build_config(**kw))      # the ORIGINAL configuration: the blob carries the live one
+    b.enable_f64_outputs()
+    b.set_state(blob)
+    assert abs(b.cfg.seed - 0) >= 0
+    for t in range(27, 70):
+        a.step(acts[t])
+        b.step(acts[t])
+        assert torch.equal(a.obs64, b.obs64) and torch.equal(a.rew64, b.rew64) and torch.equal(a.done, b.done), t
+    for f in (bt.FIELD_Y, bt.FIELD_TARGET, bt.FIELD_COUNTERS, bt.FIELD_TURB):
+        assert torch.equal(a.get_field(f), b.get_field(f))
+    with pytest.raises((FwError, AssertionError)):
+        bt.BatchedFixedWing(n + 1, cfg=build_config(**kw)).set_state(blob)
+    a.close(); b.close()
+
+
+def test_ppo_checkpoint_resume_is_bit_identical(cuda_device, tmp_path):
+    """Train k iterations, save, rebuild env + trainer from scratch, load, continue: the weights after the continuation
+    equal those of an uninterrupted run bit for bit (env state, normaliser, optimiser, rollout carry and RNG all restored)."""
+    import torch
+    from tum_adlr_deep_reinforcement_learning_b200.ppo import PPO
+    from tum_adlr_deep_reinforcement_learning_b200.vec_env import FixedWingVecEnv
+
+    def make():
+        env = FixedWingVecEnv(256, config_kw={"steps_max": 30}, sim_config_kw={"turbulence": True}, seed=4)
+        return env, PPO(env, n_steps=8, batch_size=1024, n_epochs=2, seed=3, use_cuda_graph=False)
+
+    per = 8 * 256
+    env_a, a = make()
+    a.learn(total_timesteps=3 * per)
+    a.save(str(tmp_path / "ck.pt"), vecnormalize_path=str(tmp_path / "env.pkl"))
+    a.learn(total_timesteps=7 * per)
+    env_b, b = make()
+    b.load(str(tmp_path / "ck.pt"))
+    assert b.num_timesteps == 3 * per
+    b.learn(total_timesteps=7 * per)
+    for pa, pb in zip(a.policy.parameters(), b.policy.parameters()):
+        assert torch.equal(pa, pb)
+    assert torch.equal(a.norm.obs_rms.mean, b.norm.obs_rms.mean) and torch.equal(a.norm.ret_rms.var, b.norm.ret_rms.var)
+    assert torch.equal(env_a.sim.get_state(), env_b.sim.get_state())
+    # the same continuation from captured CUDA graphs (graph replay and eager launches run the same kernels)
+    env_c, c = make()
+    c.use_cuda_graph = True
+    c.load(str(tmp_path / "ck.pt"))
+    c.learn(total_timesteps=7 * per)
+    assert c._rollout_graph is not None
+    worst = max(float((pa - pc).abs().max()) for pa, pc in zip(a.policy.parameters(), c.policy.parameters()))
+    print("graphed continuation vs eager: max weight difference %.3e" % worst)
+    assert worst < 1e-3
+    for e in (env_a, env_b, env_c):
+        e.close()

@@ -124,20 +124,24 @@ def test_reset_distributions_and_wind(cuda_device):
     env.close()
 
 
-@pytest.mark.parametrize("precision,integrator,substeps,tol_step,tol_500", [
-    ("f32", "rk45", 0, 1e-4, None),      # same controller in float32: per-step deviation from the fp64 exact path
-    ("f64", "rk4", 4, 3e-3, 0.05),       # SURVEY §7 hard part 1: fixed step cannot beat the reference's own RK45 error
-    ("f32", "rk4", 4, 3e-3, 0.05),
+@pytest.mark.parametrize("precision,integrator,substeps,tol_step,tol_100,tol_500", [
+    # per-step | max over all envs after 100 steps | (median, 99th percentile, max) after 500 steps
+    ("f32", "rk45", 0, 1e-4, 5e-4, (2e-4, 3e-2, 3.0)),   # the same controller in float32
+    ("f64", "rk4", 4, 3e-3, 3e-2, (3e-3, 0.3, 5.0)),     # SURVEY §7 hard part 1: a fixed step cannot beat the reference's
+    ("f32", "rk4", 4, 3e-3, 3e-2, (3e-3, 0.3, 5.0)),     # own RK45 error (1e-4 per step)
 ])
-def test_fast_modes_at_their_stated_tolerance(precision, integrator, substeps, tol_step, tol_500, cuda_device):
-    """fp32 / fixed-step modes are NOT parity modes.  Stated tolerances (DESIGN.md "Modes"): per-step relative state
-    deviation from the fp64 exact path when both start from the same state, and bounded divergence of the
-    observation over 500 free-running steps under a smooth action sequence."""
+def test_fast_modes_at_their_stated_tolerance(precision, integrator, substeps, tol_step, tol_100, tol_500, cuda_device):
+    """fp32 / fixed-step modes are NOT parity modes.  Stated tolerances (DESIGN.md "Modes"), all with Dryden turbulence
+    ON: per-step relative state deviation from the fp64 exact path when both start from the same state, and bounded
+    divergence of the observation (roll, pitch, Va, p, q, r: rad, m/s, rad/s) over 500 free-running steps under a smooth
+    action sequence — the MAXIMUM over all 2048 envs after 100 steps, and median / 99th percentile / maximum after 500
+    (measured on a B200, tools/fast_mode_divergence.py: f32/rk45 3.5e-5 | 2.1e-5, 2.7e-3, 0.68; rk4x4 2.6e-3 | 2.7e-4,
+    3.7e-2, 0.36-1.1; the maximum is one of the ~13 % of envs about to depart under open-loop controls)."""
     import torch
     from tum_adlr_deep_reinforcement_learning_b200 import batched as bt
     from tum_adlr_deep_reinforcement_learning_b200.config import build_config
-    n = 512
-    kw = dict(sim_config_kw={"turbulence": False}, seed=5)
+    n = 2048
+    kw = dict(sim_config_kw={"turbulence": True}, seed=5)
     ref = bt.BatchedFixedWing(n, cfg=build_config(**kw))
     fast = bt.BatchedFixedWing(n, cfg=build_config(precision=precision, integrator=integrator,
                                                    rk4_substeps=max(substeps, 1), **kw))
@@ -154,22 +158,95 @@ def test_fast_modes_at_their_stated_tolerance(precision, integrator, substeps, t
     dev = np.abs(y1 - y0)[:, :16] / scale[:, :16]          # actuator RATES excluded (9e-2 abs is the reference's own
     print("\n[%s/%s] single-step max rel deviation %.2e" % (precision, integrator, dev.max()))   # RK45 error there)
     assert dev.max() < tol_step
-    # (b) 500 free-running steps, smooth (sinusoidal) actions
-    if tol_500 is not None:
-        worst = 0.0
-        for t in range(500):
-            ph = 0.02 * t
-            a = torch.as_tensor(np.stack([0.3 * np.sin(ph + rs.rand()) * np.ones(n), 0.3 * np.cos(ph) * np.ones(n),
-                                          0.5 * np.ones(n)], 1).astype(np.float32)).cuda()
-            ref.step(a, auto_reset=False)
-            fast.step(a, auto_reset=False)
-        o0, o1 = ref.obs64.cpu().numpy(), fast.obs64.cpu().numpy()
-        ok = ~(ref.done.cpu().numpy().astype(bool) | fast.done.cpu().numpy().astype(bool))
-        worst = np.median(np.abs(o1 - o0)[ok][:, :6].max(axis=1))
-        print("[%s/%s] median obs divergence after 500 steps %.3e" % (precision, integrator, worst))
-        assert worst < tol_500
+    # (b) 500 free-running steps, smooth (sinusoidal) actions, turbulence on; envs that terminated in either run drop out
+    alive = np.ones(n, bool)
+    for t in range(500):
+        ph = 0.02 * t
+        a = torch.as_tensor(np.stack([0.3 * np.sin(ph + rs.rand()) * np.ones(n), 0.3 * np.cos(ph) * np.ones(n),
+                                      0.5 * np.ones(n)], 1).astype(np.float32)).cuda()
+        ref.step(a, auto_reset=False)
+        fast.step(a, auto_reset=False)
+        alive &= ~(ref.done.cpu().numpy().astype(bool) | fast.done.cpu().numpy().astype(bool))
+        if t in (99, 499):
+            o0, o1 = ref.obs64.cpu().numpy()[alive], fast.obs64.cpu().numpy()[alive]
+            assert np.isfinite(o1).all() and np.isfinite(fast.get_field(bt.FIELD_Y).cpu().numpy()[alive]).all()
+            d = np.abs(o1 - o0)[:, :6].max(axis=1)
+            print("[%s/%s] step %d, %d envs alive: median %.2e p99 %.2e max %.2e" % (
+                precision, integrator, t + 1, alive.sum(), np.median(d), np.percentile(d, 99), d.max()))
+            if t == 99:
+                assert alive.sum() > 0.95 * n and d.max() < tol_100
+            else:
+                assert alive.sum() > 0.75 * n
+                assert np.median(d) < tol_500[0] and np.percentile(d, 99) < tol_500[1] and d.max() < tol_500[2]
     ref.close()
     fast.close()
+
+
+def test_streamed_dryden_matches_the_reference_tables(cuda_device):
+    """The reference simulates a whole episode of turbulence at reset (dryden.py:193-261, scipy lsim); the CUDA path
+    advances the six filters by one sample per env step.  With the fixture's unit noise injected, the sample the
+    integrator sees at step k must be column k of the reference's tables — all three intensities, both table lengths
+    (2000: the gym's parameterisation, 300: raw pyfly), and the 300-sample block restart of raw pyfly (two blocks)."""
+    import torch
+    from tum_adlr_deep_reinforcement_learning_b200 import batched as bt
+    from tum_adlr_deep_reinforcement_learning_b200.config import build_config
+    g = load_golden("dryden")
+    state = np.full((1, 21), np.nan)
+    state[0, :12] = [0.0, 0.03, 0.0, 0, 0, 0, 0, 0, -100.0, 19.0, 0.0, 0.5]
+    state[0, 18:] = 0.0
+    trim = torch.as_tensor([[-0.08, 0.0, 0.45]], dtype=torch.float32).cuda()      # elevons near neutral, half throttle
+
+    def run(env, noise, lin, ang, L):
+        env.reset(state=state, noise=noise[None])
+        worst = 0.0
+        for k in range(L):
+            t6 = env.get_field(bt.FIELD_TURB).cpu().numpy()[0]
+            ref6 = np.concatenate([lin[:, k], ang[:, k]])
+            worst = max(worst, float(np.abs(t6 - ref6).max()))
+            if k % 50 == 49:                       # the airframe flies open loop: put it back before it can depart
+                y = env.get_field(bt.FIELD_Y)
+                y[:, :7] = torch.as_tensor([1.0, 0, 0, 0, 0, 0, 0], dtype=torch.float64).cuda()
+                y[:, 10:13] = torch.as_tensor([19.0, 0.0, 0.5], dtype=torch.float64).cuda()
+                env.set_field(bt.FIELD_Y, y)
+            if k < L - 1:
+                env.step(trim, auto_reset=False)
+                assert not bool(env.done.cpu().numpy()[0]) or k == L - 2, k
+        return worst
+
+    for L in (2000, 300):
+        for inten in ("light", "moderate", "severe"):
+            tag = "L%d_%s" % (L, inten)
+            cfg = build_config(config_kw={"steps_max": L}, sim_config_kw={"turbulence": True, "turbulence_intensity": inten})
+            env = bt.BatchedFixedWing(1, cfg=cfg)
+            scale = max(1.0, float(np.abs(g[tag + "_lin"]).max()))
+            worst = run(env, g[tag + "_noise"], g[tag + "_lin"], g[tag + "_ang"], L)
+            env.close()
+            assert worst < 1e-12 * scale, (tag, worst)
+    # raw pyfly: tables of 300 samples re-simulated block after block (the waypoint env keeps pyfly's default length)
+    cfg = build_config(env_kind="waypoint", config_kw={"steps_max": 600},
+                       sim_config_kw={"turbulence": True, "turbulence_intensity": "moderate"})
+    assert cfg.turb_block_len == 300
+    env = bt.BatchedFixedWing(1, cfg=cfg)
+    tasks = np.zeros((1, 2, 15))
+    tasks[0, :, :3] = [[0.0, 0.0, -100.0], [1e6, 0.0, -100.0]]               # one leg, never reached: no teleport
+    tasks[0, :, 6] = 19.0
+    tasks[0, :, 12:] = 0.0
+    env.set_waypoint_tasks(tasks, [0])
+    noise = g["blocks_noise"]
+    env.reset(noise=noise[None])
+    worst = 0.0
+    for k in range(600):
+        t6 = env.get_field(bt.FIELD_TURB).cpu().numpy()[0]
+        worst = max(worst, float(np.abs(t6 - np.concatenate([g["blocks_lin"][:, k], g["blocks_ang"][:, k]])).max()))
+        if k % 50 == 49:
+            y = env.get_field(bt.FIELD_Y)
+            y[:, :7] = torch.as_tensor([1.0, 0, 0, 0, 0, 0, 0], dtype=torch.float64).cuda()
+            y[:, 10:13] = torch.as_tensor([19.0, 0.0, 0.5], dtype=torch.float64).cuda()
+            env.set_field(bt.FIELD_Y, y)
+        if k < 599:
+            env.step(torch.as_tensor([[0.0, 0.0, 0.45]], dtype=torch.float32).cuda(), auto_reset=False)
+    env.close()
+    assert worst < 1e-12 * max(1.0, float(np.abs(g["blocks_lin"]).max())), worst
 
 
 def test_ppo_plumbing_runs_and_improves_value_fit(cuda_device):
@@ -608,7 +685,8 @@ def test_fused_rollout_glue_matches_the_reference_fixture(cuda_device):
     run_ret = torch.zeros(N, dtype=torch.float64, device=dev)
     run_len = torch.zeros(N, dtype=torch.float64, device=dev)
     ep = torch.zeros(3, dtype=torch.float64, device=dev)
-    scratch = torch.zeros(3 * D + 3, dtype=torch.float64, device=dev)
+    from tum_adlr_deep_reinforcement_learning_b200.buffers import rollout_scratch_doubles
+    scratch = torch.zeros(rollout_scratch_doubles(D), dtype=torch.float64, device=dev)
     for t in range(T):
         fused_post_step(nm, buf, torch.as_tensor(g["obs_seq"][t + 1], device=dev), torch.as_tensor(g["rew_seq"][t], device=dev),
                         torch.as_tensor(g["done_seq"][t].astype(np.uint8), device=dev), torch.as_tensor(g["acts"][t], device=dev),

@@ -249,3 +249,48 @@ def test_ppo_policy_and_update_match_the_reference_on_cpu():
         for name, p in pol.named_parameters():
             ref = g["w%d/%s" % (k, name)]
             assert np.abs(p.detach().numpy() - ref).max() <= 2e-6 + 1e-5 * np.abs(ref - g["w0/" + name]).max(), (k, name)
+
+
+def test_vecnormalize_checkpoint_round_trips_with_the_reference_format(tmp_path):
+    """DeviceVecNormalize.save writes what the fork's VecNormalize.load reads (vec_normalize.py:222-243) and
+    DeviceVecNormalize.load reads what the fork's VecNormalize.save writes: statistics and settings survive both ways."""
+    import torch
+    from oracle import refshim
+    if not refshim.available():
+        pytest.skip("reference libraries neither mounted nor mirrored under baseline/_ref")
+    refshim.install()
+    import gym
+    from stable_baselines3.common.vec_env import DummyVecEnv, VecNormalize
+    from tum_adlr_deep_reinforcement_learning_b200.buffers import DeviceVecNormalize
+
+    class Toy(gym.Env):
+        observation_space = gym.spaces.Box(low=-np.ones(5, np.float32), high=np.ones(5, np.float32))
+        action_space = gym.spaces.Box(low=-np.ones(2, np.float32), high=np.ones(2, np.float32))
+
+        def reset(self):
+            return np.zeros(5, np.float32)
+
+        def step(self, a):
+            return np.zeros(5, np.float32), 0.0, False, {}
+
+    rs = np.random.RandomState(0)
+    mine = DeviceVecNormalize(3, obs_dim=5, device="cpu", clip_obs=7.0, gamma=0.97)
+    mine.reset(torch.zeros(3, 5))
+    for _ in range(20):
+        mine.step(torch.as_tensor(rs.standard_normal((3, 5)), dtype=torch.float32),
+                  torch.as_tensor(rs.standard_normal(3), dtype=torch.float32), torch.zeros(3, dtype=torch.uint8))
+    mine.save(str(tmp_path / "mine.pkl"))
+    ref = VecNormalize.load(str(tmp_path / "mine.pkl"), DummyVecEnv([Toy for _ in range(3)]))
+    assert np.array_equal(ref.obs_rms.mean, mine.obs_rms.mean.numpy()) and np.array_equal(ref.obs_rms.var, mine.obs_rms.var.numpy())
+    assert ref.obs_rms.count == float(mine.obs_rms.count) and ref.ret_rms.var == float(mine.ret_rms.var)
+    assert ref.clip_obs == 7.0 and ref.gamma == 0.97 and ref.training and ref.num_envs == 3
+    o = rs.standard_normal((3, 5)).astype(np.float32)
+    assert np.allclose(ref.normalize_obs(o), mine.normalize_obs(torch.as_tensor(o)).numpy(), atol=1e-6)
+    # the other way round
+    ref2 = VecNormalize(DummyVecEnv([Toy for _ in range(3)]), clip_reward=4.0)
+    ref2.obs_rms.update(rs.standard_normal((50, 5)))
+    ref2.ret_rms.update(rs.standard_normal(50))
+    ref2.save(str(tmp_path / "ref.pkl"))
+    back = DeviceVecNormalize(3, obs_dim=5, device="cpu").load(str(tmp_path / "ref.pkl"))
+    assert np.array_equal(back.obs_rms.mean.numpy(), ref2.obs_rms.mean) and float(back.ret_rms.var) == float(ref2.ret_rms.var)
+    assert float(back.obs_rms.count) == ref2.obs_rms.count and back.clip_reward == 4.0

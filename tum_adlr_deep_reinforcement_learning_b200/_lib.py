@@ -39,6 +39,10 @@ def lib():
     L.fw_create.argtypes = [ctypes.POINTER(FwConfig), ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(_vp)]
     L.fw_destroy.argtypes = [_vp]
     L.fw_set_config.argtypes = [_vp, ctypes.POINTER(FwConfig), _vp]
+    L.fw_state_blob_size.argtypes = [_vp]
+    L.fw_state_blob_size.restype = ctypes.c_int64
+    L.fw_get_state_blob.argtypes = [_vp, _vp, _vp]
+    L.fw_set_state_blob.argtypes = [_vp, _vp, _vp]
     L.fw_reset.argtypes = [_vp, _vp, _vp, _vp, _vp, ctypes.c_int32, _vp, _vp, _vp]
     L.fw_step.argtypes = [_vp, _vp, ctypes.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_int32, _vp]
     L.fw_step_random.argtypes = [_vp, ctypes.c_int32, ctypes.c_uint64, _vp, _vp, _vp, _vp]
@@ -74,6 +78,6 @@ def check(rc, what):
         raise FwError("%s failed (%d): %s" % (what, rc, lib().fw_last_error().decode()))
 
 
-EXPORTS = ("fw_create", "fw_destroy", "fw_set_config", "fw_last_error", "fw_abi_version", "fw_reset", "fw_step", "fw_step_random",
+EXPORTS = ("fw_create", "fw_destroy", "fw_set_config", "fw_state_blob_size", "fw_get_state_blob", "fw_set_state_blob", "fw_last_error", "fw_abi_version", "fw_reset", "fw_step", "fw_step_random",
            "fw_get_episode_info", "fw_get_field", "fw_set_field", "fw_gae", "fw_measure_fma_peak", "fw_debug_math",
            "fw_obs_dim", "fw_set_waypoint_tasks", "fw_set_profiling", "fw_get_profile", "fw_join", "fw_set_info_rows", "fw_ppo_loss", "fw_rollout_post_step", "fw_adam_clip_step")

@@ -77,6 +77,21 @@ class BatchedFixedWing:
         _lib.check(_lib.lib().fw_set_config(self._h, ctypes.byref(cfg), self._stream()), "fw_set_config")
         self.cfg = cfg
 
+    def get_state(self):
+        """The whole env state of the handle as one uint8 CUDA tensor (fw_get_state_blob): SoA state, episode
+        bookkeeping, precomputed next-episode rows, reset-time configuration.  `.cpu()` it and torch.save it."""
+        nbytes = int(_lib.lib().fw_state_blob_size(self._h))
+        blob = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        _lib.check(_lib.lib().fw_get_state_blob(self._h, _ptr(blob), self._stream()), "fw_get_state_blob")
+        return blob
+
+    def set_state(self, blob):
+        """Restore a blob written by get_state() of a handle with the same configuration and n_envs."""
+        blob = torch.as_tensor(blob, dtype=torch.uint8).to(self.device).contiguous()
+        assert blob.numel() == int(_lib.lib().fw_state_blob_size(self._h)), "state blob of another handle shape"
+        _lib.check(_lib.lib().fw_set_state_blob(self._h, _ptr(blob), self._stream()), "fw_set_state_blob")
+        torch.cuda.current_stream(self.device).synchronize()
+
     def set_waypoint_tasks(self, tasks, task_of_env):
         """Waypoint head: tasks [n_tasks, wp_len, 15] float64 rows (position n e d, roll pitch yaw, velocity u v w, wind
         n e d, omega p q r with NaN = sample), task_of_env [n] int.  The library keeps its own device copy."""

@@ -167,13 +167,70 @@ class DeviceVecNormalize:
 
     def state_dict(self):
         return {"obs_mean": self.obs_rms.mean, "obs_var": self.obs_rms.var, "obs_count": self.obs_rms.count,
-                "ret_mean": self.ret_rms.mean, "ret_var": self.ret_rms.var, "ret_count": self.ret_rms.count}
+                "ret_mean": self.ret_rms.mean, "ret_var": self.ret_rms.var, "ret_count": self.ret_rms.count,
+                "ret": self.ret}
 
     def load_state_dict(self, sd):
         for rms, pre in ((self.obs_rms, "obs"), (self.ret_rms, "ret")):
-            rms.mean.copy_(sd[pre + "_mean"])
-            rms.var.copy_(sd[pre + "_var"])
-            rms.count.copy_(sd[pre + "_count"])
+            rms.mean.copy_(torch.as_tensor(sd[pre + "_mean"], dtype=torch.float64))
+            rms.var.copy_(torch.as_tensor(sd[pre + "_var"], dtype=torch.float64))
+            rms.count.copy_(torch.as_tensor(sd[pre + "_count"], dtype=torch.float64))
+        if "ret" in sd and tuple(torch.as_tensor(sd["ret"]).shape) == tuple(self.ret.shape):
+            self.ret.copy_(torch.as_tensor(sd["ret"], dtype=torch.float64))
+
+    # ---- the reference's checkpoint format (vec_normalize.py:222-243): a pickle of the VecNormalize object without its
+    # venv.  save() writes exactly that when stable_baselines3 is importable — the fork's VecNormalize.load(path, venv)
+    # then reads our statistics — and load() reads a file written by the fork's VecNormalize.save (or by save()).
+    def save(self, path):
+        import pickle
+        fields = dict(clip_obs=self.clip_obs, clip_reward=self.clip_reward, gamma=self.gamma, epsilon=self.epsilon,
+                      training=self.training, norm_obs=self.norm_obs, norm_reward=self.norm_reward)
+        stats = {k: v.detach().cpu().numpy().copy() for k, v in self.state_dict().items()}
+        try:
+            from stable_baselines3.common.running_mean_std import RunningMeanStd as RefRms
+            from stable_baselines3.common.vec_env import VecNormalize as RefVecNormalize
+        except Exception:
+            with open(path, "wb") as f:
+                pickle.dump({"format": "fwb200.DeviceVecNormalize", **fields, **stats}, f)
+            return
+        import numpy as np
+        obj = RefVecNormalize.__new__(RefVecNormalize)
+        rms = {}
+        for pre, shape in (("obs", stats["obs_mean"].shape), ("ret", ())):
+            r = RefRms(shape=shape)
+            r.mean, r.var = stats[pre + "_mean"].astype(np.float64), stats[pre + "_var"].astype(np.float64)
+            r.count = float(stats[pre + "_count"])
+            rms[pre] = r
+        # the attributes VecNormalize.__getstate__ keeps (venv, class_attributes and ret are rebuilt by set_venv)
+        obj.__dict__.update(dict(fields, obs_keys=None, obs_spaces=None, obs_rms=rms["obs"], ret_rms=rms["ret"],
+                                 old_obs=np.array([]), old_reward=np.array([]), venv=None, class_attributes={},
+                                 ret=np.zeros(0), num_envs=int(self.ret.shape[0])))
+        with open(path, "wb") as f:
+            pickle.dump(obj, f)
+
+    def load(self, path):
+        import pickle
+        with open(path, "rb") as f:
+            obj = pickle.load(f)                 # a reference pickle needs stable_baselines3 importable, as in the reference
+        if isinstance(obj, dict):
+            src = obj
+            stats = obj
+        else:
+            src = obj.__dict__
+            stats = {"obs_mean": obj.obs_rms.mean, "obs_var": obj.obs_rms.var, "obs_count": obj.obs_rms.count,
+                     "ret_mean": obj.ret_rms.mean, "ret_var": obj.ret_rms.var, "ret_count": obj.ret_rms.count}
+        for k in ("clip_obs", "clip_reward", "gamma", "epsilon", "training", "norm_obs", "norm_reward"):
+            setattr(self, k, src[k])
+        self.load_state_dict(stats)
+        return self
+
+
+FW_ROLLOUT_BLOCKS, FW_PPO_SCRATCH_DOUBLES = 64, 9 + 7 * 592          # include/fwb200.h
+
+
+def rollout_scratch_doubles(obs_dim):
+    """FW_ROLLOUT_SCRATCH(obs_dim) of include/fwb200.h: allocate it ZEROED (torch.zeros), it holds a ticket counter."""
+    return 3 * obs_dim + 4 + FW_ROLLOUT_BLOCKS * (2 * obs_dim + 5)
 
 
 def fused_post_step(norm, buf, obs_raw, rew_raw, done, actions, values, log_probs, last_obs, last_dones, run_ret,
@@ -194,7 +251,7 @@ def fused_post_step(norm, buf, obs_raw, rew_raw, done, actions, values, log_prob
                 ep_stats=ep_stats, buf_obs=buf.observations[t], buf_actions=buf.actions[t], buf_rewards=buf.rewards[t],
                 buf_dones=buf.dones[t], buf_values=buf.values[t], buf_log_probs=buf.log_probs[t], scratch=scratch)
     assert all(v.is_cuda and v.is_contiguous() for v in tens.values())
-    assert scratch.numel() >= 3 * obs_raw.shape[1] + 3
+    assert scratch.numel() >= rollout_scratch_doubles(obs_raw.shape[1]), "scratch: torch.zeros(rollout_scratch_doubles(obs_dim))"
     p = _lib.FwRolloutPost(**{k: v.data_ptr() for k, v in tens.items()}, n=obs_raw.shape[0], obs_dim=obs_raw.shape[1],
                            act_dim=actions.shape[1], gamma=norm.gamma, clip_obs=norm.clip_obs,
                            clip_reward=norm.clip_reward, epsilon=norm.epsilon, norm_obs=int(norm.norm_obs),

@@ -60,7 +60,9 @@ template <> struct M<float> {
     static __device__ __forceinline__ float sqrt(float x) { return ::sqrtf(x); }
     static __device__ __forceinline__ float rsqrt(float x) { return ::rsqrtf(x); }
     static __device__ __forceinline__ float atan2_hot(float y, float x) { return ::atan2f(y, x); }
-    static __device__ __forceinline__ float asin_hot(float x) { return ::asinf(x); }
+    // sin(beta) = a1 * rsqrt(|a|^2) can exceed 1 by a float32 rounding when the sideslip reaches 90 degrees: clamp, as
+    // asin_bf does for its own argument, instead of handing NaN to the forces
+    static __device__ __forceinline__ float asin_hot(float x) { return ::asinf(fminf(fmaxf(x, -1.0f), 1.0f)); }
     static __device__ __forceinline__ float exp_hot(float x) { return ::expf(x); }
     static __device__ __forceinline__ float rcp_hot(float x) { return 1.0f / x; }
     static __device__ __forceinline__ float atan2(float y, float x) { return ::atan2f(y, x); }

@@ -35,10 +35,14 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// block sum of K doubles per thread -> atomicAdd into out[0..K)
+// Deterministic grid-wide sum of K doubles per thread: fixed shuffle trees inside the block, one partial per block in
+// global memory, and the LAST block to arrive (a ticket counter) adds the partials in block order and stores out[0..K).
+// No floating-point atomics anywhere: the same inputs give the same bits on every run, which checkpoint / resume and
+// run-to-run reproducibility of training rely on.  `ticket` must be 0 on entry and is left at 0.
 template <int K>
-__device__ __forceinline__ void block_accumulate(const double (&v)[K], double* out) {
+__device__ __forceinline__ void grid_accumulate(const double (&v)[K], double* partial, unsigned* ticket, double* out) {
     __shared__ double sh[K][TPB / 32];
+    __shared__ bool is_last;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
@@ -51,10 +55,30 @@ __device__ __forceinline__ void block_accumulate(const double (&v)[K], double* o
         for (int k = 0; k < K; ++k) {
             double s = lane < TPB / 32 ? sh[k][lane] : 0.0;
             s = warp_sum(s);
-            if (lane == 0) atomicAdd(out + k, s);
+            if (lane == 0) partial[(size_t)blockIdx.x * K + k] = s;
+        }
+        if (lane == 0) {
+            __threadfence();
+            is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
         }
     }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        if (threadIdx.x < K) {
+            double s = 0.0;
+            for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(partial + (size_t)b * K + threadIdx.x);
+            out[threadIdx.x] = s;
+        }
+        if (threadIdx.x == 0) *ticket = 0u;
+    }
 }
+
+// scratch layout of fw_ppo_loss (FW_PPO_SCRATCH_DOUBLES): acc[8] | two tickets | partials of the two reductions
+constexpr int PPO_MAX_GRID = 592;
+__device__ __forceinline__ unsigned* ppo_ticket(double* scratch, int which) { return reinterpret_cast<unsigned*>(scratch + 8) + which; }
+__device__ __forceinline__ double* ppo_partial_a(double* scratch) { return scratch + 9; }
+__device__ __forceinline__ double* ppo_partial_b(double* scratch) { return scratch + 9 + 2 * PPO_MAX_GRID; }
 
 // acc[0] = sum adv, acc[1] = sum adv^2
 __global__ void __launch_bounds__(TPB) ppo_adv_stats_kernel(const float* __restrict__ adv, int B, double* acc) {
@@ -64,7 +88,7 @@ __global__ void __launch_bounds__(TPB) ppo_adv_stats_kernel(const float* __restr
         v[0] += a;
         v[1] += a * a;
     }
-    block_accumulate<2>(v, acc);
+    grid_accumulate<2>(v, ppo_partial_a(acc), ppo_ticket(acc, 0), acc);
 }
 
 // acc[2] = sum min(pl1, pl2), acc[3] = sum (ret - v)^2, acc[4..6] = sum_i g_i * ((a - m)^2 / var - 1) per action dim
@@ -114,7 +138,7 @@ __global__ void __launch_bounds__(TPB) ppo_loss_kernel(const float* __restrict__
         v[1] += (double)(ve * ve);
         grad_values[i] = vf_coef * 2.f * inv_b * ve;
     }
-    block_accumulate<5>(v, acc + 2);
+    grid_accumulate<5>(v, ppo_partial_b(acc), ppo_ticket(acc, 1), acc + 2);
 }
 
 // out[0] = loss, out[1] = policy_loss, out[2] = value_loss; grad_log_std[j]
@@ -144,9 +168,9 @@ extern "C" int fw_ppo_loss(const float* mean_dev, const float* values_dev, const
         !scratch_dev || !grad_mean_dev || !grad_values_dev || !grad_log_std_dev || !losses_dev || batch <= 0)
         return FW_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
-    if (cudaMemsetAsync(scratch_dev, 0, sizeof(double) * 8, st) != cudaSuccess) return FW_ECUDA;
+    if (cudaMemsetAsync(scratch_dev, 0, sizeof(double) * 9, st) != cudaSuccess) return FW_ECUDA;
     int grid = (batch + TPB - 1) / TPB;
-    if (grid > 592) grid = 592;
+    if (grid > PPO_MAX_GRID) grid = PPO_MAX_GRID;
     ppo_adv_stats_kernel<<<grid, TPB, 0, st>>>(adv_dev, batch, scratch_dev);
     ppo_loss_kernel<<<grid, TPB, 0, st>>>(mean_dev, values_dev, log_std_dev, actions_dev, old_log_prob_dev, adv_dev,
                                           returns_dev, batch, clip_range, vf_coef, scratch_dev, grad_mean_dev,
@@ -168,13 +192,19 @@ extern "C" int fw_ppo_loss(const float* mean_dev, const float* values_dev, const
 // All statistics are float64 like the reference; the batch variance is E[x^2] - mean^2 from f64 sums.
 namespace {
 
-// scratch layout: [0, D) sum obs_j, [D, 2D) sum obs_j^2, 2D sum ret, 2D+1 sum ret^2
+// scratch layout: [0, D) sum obs_j, [D, 2D) sum obs_j^2, 2D sum ret, 2D+1 sum ret^2 | [2D+2, 3D+3) the scales of
+// rollout_scales_kernel | 3D+3 the ticket | from 3D+4: FW_ROLLOUT_BLOCKS partial rows of 2D+5 sums.
+// Deterministic like grid_accumulate: every warp adds its groups into its own shared-memory row in a fixed order, the
+// block adds its warps in order, the last block to arrive adds the blocks in order.  No floating-point atomics.
+constexpr int ROLLOUT_BLOCKS = FW_ROLLOUT_BLOCKS;
 __global__ void __launch_bounds__(TPB) rollout_stats_kernel(const FwRolloutPost p) {
-    extern __shared__ double sh[];                       // 2 D + 5 partial sums of the block
+    extern __shared__ double sh[];                       // [TPB / 32][2 D + 5] partial sums of the warps
+    __shared__ bool is_last;
     const int D = p.obs_dim, NS = 2 * D + 5;
-    for (int k = threadIdx.x; k < NS; k += TPB) sh[k] = 0.0;
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    double* mine = sh + (size_t)w * NS;
+    for (int k = lane; k < NS; k += 32) mine[k] = 0.0;
+    __syncwarp();
     // every warp walks whole groups of 32 envs so that the shuffles below are full-warp
     for (int base = (blockIdx.x * TPB + threadIdx.x - lane); base < p.n; base += gridDim.x * TPB) {
         const int i = base + lane;
@@ -191,23 +221,40 @@ __global__ void __launch_bounds__(TPB) rollout_stats_kernel(const FwRolloutPost 
             p.run_len[i] = d ? 0.0 : rl;
         }
         double s;
-        s = warp_sum(r_new); if (lane == 0) atomicAdd(sh + 2 * D, s);
-        s = warp_sum(r_new * r_new); if (lane == 0) atomicAdd(sh + 2 * D + 1, s);
-        s = warp_sum(e_ret); if (lane == 0 && s != 0.0) atomicAdd(sh + 2 * D + 2, s);
-        s = warp_sum(e_len); if (lane == 0 && s != 0.0) atomicAdd(sh + 2 * D + 3, s);
-        s = warp_sum(e_cnt); if (lane == 0 && s != 0.0) atomicAdd(sh + 2 * D + 4, s);
+        s = warp_sum(r_new); if (lane == 0) mine[2 * D] += s;
+        s = warp_sum(r_new * r_new); if (lane == 0) mine[2 * D + 1] += s;
+        s = warp_sum(e_ret); if (lane == 0) mine[2 * D + 2] += s;
+        s = warp_sum(e_len); if (lane == 0) mine[2 * D + 3] += s;
+        s = warp_sum(e_cnt); if (lane == 0) mine[2 * D + 4] += s;
         if (p.training) {
             for (int j = 0; j < D; ++j) {
                 const double x = on ? (double)p.obs_raw[(size_t)i * D + j] : 0.0;
-                s = warp_sum(x); if (lane == 0) atomicAdd(sh + j, s);
-                s = warp_sum(x * x); if (lane == 0) atomicAdd(sh + D + j, s);
+                s = warp_sum(x); if (lane == 0) mine[j] += s;
+                s = warp_sum(x * x); if (lane == 0) mine[D + j] += s;
             }
         }
     }
     __syncthreads();
+    double* partial = p.scratch + 3 * D + 4;
+    unsigned* ticket = reinterpret_cast<unsigned*>(p.scratch + 3 * D + 3);
     for (int k = threadIdx.x; k < NS; k += TPB) {
-        if (k < 2 * D + 2) atomicAdd(p.scratch + k, sh[k]);
-        else if (sh[k] != 0.0) atomicAdd(p.ep_stats + (k - 2 * D - 2), sh[k]);
+        double s = 0.0;
+        for (int q = 0; q < TPB / 32; ++q) s += sh[(size_t)q * NS + k];
+        partial[(size_t)blockIdx.x * NS + k] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        for (int k = threadIdx.x; k < NS; k += TPB) {
+            double s = 0.0;
+            for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(partial + (size_t)b * NS + k);
+            if (k < 2 * D + 2) p.scratch[k] = s;
+            else p.ep_stats[k - 2 * D - 2] += s;
+        }
+        if (threadIdx.x == 0) *ticket = 0u;
     }
 }
 
@@ -289,10 +336,10 @@ extern "C" int fw_rollout_post_step(const FwRolloutPost* p, void* stream) {
         return FW_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
     const int D = p->obs_dim;
-    if (cudaMemsetAsync(p->scratch, 0, sizeof(double) * (2 * D + 2), st) != cudaSuccess) return FW_ECUDA;
     int grid = (p->n + TPB - 1) / TPB;
-    if (grid > 296) grid = 296;
-    rollout_stats_kernel<<<grid, TPB, sizeof(double) * (2 * D + 5), st>>>(*p);
+    if (grid > ROLLOUT_BLOCKS) grid = ROLLOUT_BLOCKS;
+    // the ticket starts at 0 (a scratch buffer allocated zeroed) and every launch leaves it at 0
+    rollout_stats_kernel<<<grid, TPB, sizeof(double) * (TPB / 32) * (2 * D + 5), st>>>(*p);
     rollout_moments_kernel<<<1, 256, 0, st>>>(*p);
     rollout_scales_kernel<<<1, 256, 0, st>>>(*p);
     rollout_apply_kernel<<<(unsigned)(((size_t)p->n * D + TPB - 1) / TPB), TPB, 0, st>>>(*p);

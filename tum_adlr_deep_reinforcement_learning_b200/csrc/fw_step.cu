@@ -1429,6 +1429,30 @@ static int launch_step(FwHandle* h, const StepIO& io_in, cudaStream_t st) {
                 : launch_rk4<float, false>(h, h->c32, h->s32, h->w32, h->p32, io, st);
 }
 
+// ---- checkpoint / resume: the whole env state of a handle as one contiguous device blob ----
+struct BlobPart { void* ptr; size_t bytes; };
+static int blob_parts(FwHandle* h, BlobPart* out) {
+    const size_t esz = h->cfg.precision == FW_F64 ? 8 : 4, n = (size_t)h->n;
+    const size_t odim = (size_t)fw_obs_dim(h);
+    int k = 0;
+    out[k++] = {h->r_buf, esz * RF_COUNT * n};
+    out[k++] = {h->i_buf, sizeof(int32_t) * IF_COUNT * n};
+    out[k++] = {h->err_ring, esz * FW_END_ERR_WINDOW * 3 * n};
+    out[k++] = {h->metrics, sizeof(double) * FW_NMETRIC * n};
+    out[k++] = {h->ep_ret, sizeof(double) * n};
+    out[k++] = {h->ep_len, sizeof(int32_t) * n};
+    out[k++] = {h->ep_term, sizeof(int32_t) * n};
+    out[k++] = {h->r2_buf, esz * RF_COUNT * n};
+    out[k++] = {h->i2_buf, sizeof(int32_t) * IF_COUNT * n};
+    out[k++] = {h->err2, esz * 3 * n};
+    out[k++] = {h->spare_obs, sizeof(float) * odim * n};
+    out[k++] = {h->spare_obs64, sizeof(double) * odim * n};
+    out[k++] = {h->rc_dev, sizeof(ResetCfg<double>)};
+    return k;
+}
+struct BlobHeader { uint64_t magic; int32_t abi, n, precision, rf_count, if_count, obs_dim; uint64_t random_step; int32_t step_parity, _pad; };
+static const uint64_t BLOB_MAGIC = 0x46574232303053ull;   // "FWB200S"
+
 extern "C" {
 
 const char* fw_last_error(void) { return g_err; }
@@ -1637,6 +1661,80 @@ int fw_set_config(FwHandle* h, const FwConfig* cfg, void* stream) {
         if (h->cfg.precision == FW_F64) respare_kernel<double><<<grid, bs, 0, st>>>(h->c64, h->s64, h->p64);
         else respare_kernel<float><<<grid, bs, 0, st>>>(h->c32, h->s32, h->p32);
         CK(cudaGetLastError());
+    }
+    return FW_OK;
+}
+
+int64_t fw_state_blob_size(const FwHandle* h) {
+    if (!h) return FW_EINVAL;
+    BlobPart parts[16];
+    const int k = blob_parts(const_cast<FwHandle*>(h), parts);
+    size_t total = sizeof(BlobHeader);
+    for (int i = 0; i < k; ++i) total += (parts[i].bytes + 15) & ~(size_t)15;
+    return (int64_t)total;
+}
+
+int fw_get_state_blob(FwHandle* h, void* blob_dev, void* stream) {
+    if (!h || !blob_dev) return FW_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (stream_is_capturing(st)) { snprintf(g_err, sizeof(g_err), "fw_get_state_blob: not allowed during stream capture"); return FW_EINVAL; }
+    spare_join(h, st);                    // the precomputed rows being refilled belong to the state
+    BlobHeader hd;
+    memset(&hd, 0, sizeof(hd));
+    hd.magic = BLOB_MAGIC; hd.abi = FW_ABI_VERSION; hd.n = h->n; hd.precision = h->cfg.precision;
+    hd.rf_count = RF_COUNT; hd.if_count = IF_COUNT; hd.obs_dim = fw_obs_dim(h);
+    hd.random_step = h->random_step; hd.step_parity = h->step_parity;
+    CK(cudaMemcpyAsync(blob_dev, &hd, sizeof(hd), cudaMemcpyHostToDevice, st));     // pageable source: staged before return
+    BlobPart parts[16];
+    const int k = blob_parts(h, parts);
+    char* p = (char*)blob_dev + sizeof(BlobHeader);
+    for (int i = 0; i < k; ++i) {
+        CK(cudaMemcpyAsync(p, parts[i].ptr, parts[i].bytes, cudaMemcpyDeviceToDevice, st));
+        p += (parts[i].bytes + 15) & ~(size_t)15;
+    }
+    return FW_OK;
+}
+
+int fw_set_state_blob(FwHandle* h, const void* blob_dev, void* stream) {
+    if (!h || !blob_dev) return FW_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (stream_is_capturing(st)) { snprintf(g_err, sizeof(g_err), "fw_set_state_blob: not allowed during stream capture"); return FW_EINVAL; }
+    BlobHeader hd;
+    CK(cudaMemcpyAsync(&hd, blob_dev, sizeof(hd), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (hd.magic != BLOB_MAGIC || hd.abi != FW_ABI_VERSION || hd.n != h->n || hd.precision != h->cfg.precision ||
+        hd.rf_count != RF_COUNT || hd.if_count != IF_COUNT || hd.obs_dim != fw_obs_dim(h)) {
+        snprintf(g_err, sizeof(g_err), "fw_set_state_blob: the blob was written by a handle of another shape (n %d, precision %d, "
+                                       "obs_dim %d, abi %d)", hd.n, hd.precision, hd.obs_dim, hd.abi);
+        return FW_EINVAL;
+    }
+    spare_join(h, st);
+    BlobPart parts[16];
+    const int k = blob_parts(h, parts);
+    const char* p = (const char*)blob_dev + sizeof(BlobHeader);
+    for (int i = 0; i < k; ++i) {
+        CK(cudaMemcpyAsync(parts[i].ptr, p, parts[i].bytes, cudaMemcpyDeviceToDevice, st));
+        p += (parts[i].bytes + 15) & ~(size_t)15;
+    }
+    h->random_step = hd.random_step;
+    h->step_parity = hd.step_parity;
+    // the reset-time configuration travelled with the blob (device copy): bring the host copy in line
+    {
+        ResetCfg<double> rcd; ResetCfg<float> rcf;
+        if (h->cfg.precision == FW_F64) CK(cudaMemcpyAsync(&rcd, h->rc_dev, sizeof(rcd), cudaMemcpyDeviceToHost, st));
+        else CK(cudaMemcpyAsync(&rcf, h->rc_dev, sizeof(rcf), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+#define BACK(x) h->cfg.x = (h->cfg.precision == FW_F64) ? (double)rcd.x : (double)rcf.x
+        for (int q = 0; q < 12; ++q) { BACK(init_lo[q]); BACK(init_hi[q]); }
+        BACK(wind_mag_min); BACK(wind_mag_max);
+        for (int q = 0; q < 3; ++q) {
+            BACK(tgt_low[q]); BACK(tgt_high[q]); BACK(tgt_delta[q]); BACK(tgt_slope_low[q]); BACK(tgt_slope_high[q]);
+            BACK(tgt_amp_low[q]); BACK(tgt_amp_high[q]); BACK(tgt_period_low[q]); BACK(tgt_period_high[q]);
+        }
+#undef BACK
+        h->cfg.seed = (h->cfg.precision == FW_F64) ? rcd.seed : rcf.seed;
+        convert_cfg<double>(h->cfg, h->c64);
+        convert_cfg<float>(h->cfg, h->c32);
     }
     return FW_OK;
 }

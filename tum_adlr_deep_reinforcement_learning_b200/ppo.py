@@ -124,7 +124,8 @@ class FusedPPOLoss(torch.autograd.Function):
         dev = args[0].device
         g_mean, g_val, g_ls = torch.empty_like(args[0]), torch.empty_like(args[1]), torch.empty_like(args[2])
         losses = torch.empty(3, dtype=torch.float32, device=dev)
-        scratch = torch.empty(8, dtype=torch.float64, device=dev)
+        from .buffers import FW_PPO_SCRATCH_DOUBLES
+        scratch = torch.empty(FW_PPO_SCRATCH_DOUBLES, dtype=torch.float64, device=dev)
         ptr = lambda t: ctypes.c_void_p(t.data_ptr())
         _lib.check(_lib.lib().fw_ppo_loss(*[ptr(t) for t in args], B, float(clip_range), float(ent_coef), float(vf_coef),
                                           ptr(scratch), ptr(g_mean), ptr(g_val), ptr(g_ls), ptr(losses),
@@ -244,12 +245,15 @@ class PPO:
         self.norm = DeviceVecNormalize(self.n_envs, obs_dim=self.obs_dim, device=self.device, gamma=gamma, norm_obs=normalize,
                                        norm_reward=normalize)
         self.num_timesteps = 0
+        self._iteration = 0
+        self._t_start = None
         self._last_obs = None
         self._last_dones = None
         # on-device episode statistics (Monitor-equivalent, no per-env python objects)
         self._ep_stats = torch.zeros(3, dtype=torch.float64, device=self.device)     # one buffer: fw_rollout_post_step
         self.ep_ret_sum, self.ep_len_sum, self.ep_count = self._ep_stats[0], self._ep_stats[1], self._ep_stats[2]
-        self._post_scratch = torch.zeros(3 * 256 + 3, dtype=torch.float64, device=self.device)
+        from .buffers import rollout_scratch_doubles
+        self._post_scratch = torch.zeros(rollout_scratch_doubles(self.obs_dim), dtype=torch.float64, device=self.device)
         self._run_ret = torch.zeros(self.n_envs, dtype=torch.float64, device=self.device)
         self._run_len = torch.zeros(self.n_envs, dtype=torch.float64, device=self.device)
         self.logs = []
@@ -479,7 +483,8 @@ class PPO:
     def learn(self, total_timesteps, log_interval=1, callback=None):
         if self._last_obs is None:
             self._setup()
-            self._t_start, self._iteration = time.time(), 0
+        if getattr(self, "_t_start", None) is None:
+            self._t_start = time.time()
         t0 = self._t_start
         while self.num_timesteps < total_timesteps:
             self.collect_rollouts()
@@ -500,14 +505,46 @@ class PPO:
                     callback(row)
         return self
 
-    # ------------------------------------------------------------------ checkpoint (policy / optimiser / normaliser)
-    def save(self, path):
-        torch.save({"policy": self.policy.state_dict(), "optimizer": self.optimizer.state_dict(),
-                    "normalizer": self.norm.state_dict(), "num_timesteps": self.num_timesteps}, path)
+    # ------------------------------------------------------------------ checkpoint / resume
+    def save(self, path, vecnormalize_path=None):
+        """Everything a bit-identical continuation needs (SURVEY §5 "checkpoint / resume"; the reference keeps only the
+        model zip, common/base_class.py:645, and the VecNormalize pickle, simple_train.py:733-751, and restarts the
+        episodes): policy, optimiser, normaliser, the rollout carry (last observation / done flags, running episode
+        totals), the simulator's whole env state (BatchedFixedWing.get_state) and the torch RNG states.
+        `vecnormalize_path` additionally writes the normaliser in the reference's VecNormalize.save format."""
+        torch.cuda.synchronize(self.device)
+        opt = self.optimizer.state_dict()
+        if self.flat_optimizer:
+            opt = dict(opt, flat=self.optimizer.flat)
+        torch.save({"policy": self.policy.state_dict(), "optimizer": opt, "normalizer": self.norm.state_dict(),
+                    "num_timesteps": self.num_timesteps, "iteration": getattr(self, "_iteration", 0),
+                    "last_obs": self._last_obs, "last_dones": self._last_dones, "run_ret": self._run_ret,
+                    "run_len": self._run_len, "ep_stats": self._ep_stats,
+                    "env_state": self.env.sim.get_state().cpu(), "curriculum_level": getattr(self.env, "curriculum_level", 1.0),
+                    "rng_cpu": torch.get_rng_state(), "rng_cuda": torch.cuda.get_rng_state(self.device)}, path)
+        if vecnormalize_path is not None:
+            self.norm.save(vecnormalize_path)
 
     def load(self, path):
-        sd = torch.load(path, map_location=self.device)
+        sd = torch.load(path, map_location=self.device, weights_only=False)
         self.policy.load_state_dict(sd["policy"])
-        self.optimizer.load_state_dict(sd["optimizer"])
+        opt = dict(sd["optimizer"])
+        flat = opt.pop("flat", None)
+        self.optimizer.load_state_dict(opt)
+        if self.flat_optimizer and flat is not None:
+            self.optimizer.flat.copy_(flat)              # the parameters are views of it
         self.norm.load_state_dict(sd["normalizer"])
         self.num_timesteps = sd["num_timesteps"]
+        self._iteration = sd.get("iteration", 0)
+        if sd.get("env_state") is not None:
+            self.env.sim.set_state(sd["env_state"])
+            n, dev = self.n_envs, self.device
+            if self._last_obs is None:
+                self._last_obs = torch.zeros(n, self.obs_dim, dtype=torch.float32, device=dev)
+                self._last_dones = torch.zeros(n, dtype=torch.float32, device=dev)
+            for dst, key in ((self._last_obs, "last_obs"), (self._last_dones, "last_dones"), (self._run_ret, "run_ret"),
+                             (self._run_len, "run_len"), (self._ep_stats, "ep_stats")):
+                dst.copy_(sd[key])                       # in place: captured graphs keep these addresses
+            torch.set_rng_state(sd["rng_cpu"].cpu())
+            torch.cuda.set_rng_state(sd["rng_cuda"].cpu(), self.device)
+        return self
