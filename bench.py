@@ -528,6 +528,31 @@ def main():
                                             "note": "2.7 MB per call = 0.4 us at the HBM peak: three dependent launches, bound by "
                                                     "launch latency, not bandwidth; inside ppo.PPO they are replayed from a CUDA graph"}
 
+    # ---- the SAC replay ring (config C5 sizes: 1e6 rows, insert 1024, sample 4096) ----
+    if not args.no_extra:
+        from tum_adlr_deep_reinforcement_learning_b200.sac import ReplayBuffer
+        rbuf = ReplayBuffer(1_000_000, device=dev, seed=1)
+        rbuf.rows.normal_()
+        rbuf.size_dev.fill_(1_000_000); rbuf.pos, rbuf.full = 0, True
+        nrm = DeviceVecNormalize(1, obs_dim=14, device=dev)
+        o_i, a_i, r_i = torch.randn(1024, 14, device=dev), torch.randn(1024, 3, device=dev), torch.randn(1024, device=dev)
+        d_i = torch.zeros(1024, dtype=torch.uint8, device=dev)
+        t_ins, t_smp = [], []
+        for it in range(40):
+            flush.add_(1.0)
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record(); rbuf.add(o_i, o_i, a_i, r_i, d_i); e1.record(); rbuf.sample(4096, norm=nrm); e2.record()
+            torch.cuda.synchronize()
+            if it >= 8:
+                t_ins.append(e0.elapsed_time(e1)); t_smp.append(e1.elapsed_time(e2))
+        rowb = rbuf.row_floats * 4
+        for tag, ms_k, nbytes, what in (("replay_insert", float(np.median(t_ins)), 1024 * (rowb + 4 * 33), "1024 rows of %d B written + their sources read" % rowb),
+                                        ("replay_sample", float(np.median(t_smp)), 4096 * (rowb + 4 * 33), "4096 random rows of %d B read + the batch written" % rowb)):
+            gbs = nbytes / (ms_k * 1e-3) / 1e9
+            hbm_kernels[tag] = {"kernel": "fw_" + tag, "ms": ms_k, "bytes": nbytes, "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+                                "frac": gbs / hbm_peak, "note": what + "; two launches, bound by launch latency at these sizes"}
+        del rbuf
+
     # ---- PPO train env-steps/s (BASELINE.json second metric, config C4: 8192 envs/GPU, updates included) ----
     ppo = None
     if not args.no_extra:

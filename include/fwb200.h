@@ -395,6 +395,34 @@ int fw_ppo_loss(const float* mean_dev, const float* values_dev, const float* log
                 float clip_range, float ent_coef, float vf_coef, double* scratch_dev, float* grad_mean_dev,
                 float* grad_values_dev, float* grad_log_std_dev, float* losses_dev, void* stream);
 
+/* Replay ring of the off-policy (SAC) path in HBM.  Replaces ReplayBuffer.add / sample / _get_samples
+ * (stable_baselines3/common/buffers.py:146-256), widened from the reference's single env to n envs per insert.
+ * A transition is one packed row  obs[obs_dim] | next_obs[obs_dim] | action[act_dim] | reward | done(0/1)  padded to a
+ * multiple of four floats; the ring stores ORIGINAL observations and rewards and fw_replay_sample normalises with the
+ * statistics current at sample time, as the reference does (buffers.py:245-254, off_policy_algorithm.py:430-436).
+ * head_dev / size_dev / sample_calls_dev are device scalars (int64, zero-initialised by the caller) so that both calls
+ * can be captured in a CUDA graph.  Sample b of a call reads ring row floor(u * size), u = Philox4x32-10(seed; b, number of
+ * the call); indices_out_dev (nullable) receives the rows that were read. */
+#define FW_REPLAY_ROW_FLOATS(obs_dim, act_dim) ((2 * (obs_dim) + (act_dim) + 2 + 3) / 4 * 4)
+typedef struct FwReplay {
+    float* rows;               /* [capacity, row_floats], 16-byte aligned */
+    int64_t* head_dev;         /* next row to write */
+    int64_t* size_dev;         /* rows filled so far, <= capacity */
+    int64_t* sample_calls_dev; /* number of fw_replay_sample calls so far (Philox counter) */
+    int64_t capacity;
+    int32_t obs_dim, act_dim, row_floats, _pad;
+} FwReplay;
+typedef struct FwReplayNorm {  /* VecNormalize state used at sample time (vec_normalize.py:150-172); NULL pointers with flags 0 */
+    const double* obs_mean; const double* obs_var; const double* ret_var;
+    float clip_obs, clip_reward, epsilon;
+    int32_t norm_obs, norm_reward, _pad;
+} FwReplayNorm;
+int fw_replay_insert(const FwReplay* rb, const float* obs_dev, const float* next_obs_dev, const float* actions_dev,
+                     const float* rewards_dev, const uint8_t* dones_dev, int32_t n, void* stream);
+int fw_replay_sample(const FwReplay* rb, const FwReplayNorm* norm, int32_t batch, uint64_t seed, float* obs_out_dev,
+                     float* actions_out_dev, float* next_obs_out_dev, float* dones_out_dev, float* rewards_out_dev,
+                     int64_t* indices_out_dev, void* stream);
+
 /* Vector-pipe peak micro-benchmarks (dependent-chain-free FMA loops) used as roofline denominators by bench.py:
  * returns achieved TFLOP/s (2 flop per FMA) measured with CUDA events on `device`. */
 int fw_measure_fma_peak(int32_t device, int32_t precision, double* tflops_out);

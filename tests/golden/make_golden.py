@@ -730,6 +730,81 @@ def gen_ppo_update():
     np.savez_compressed(os.path.join(HERE, "ppo_update.npz"), **out)
 
 
+def gen_sac_update():
+    """Three gradient steps of the reference SAC.train() (sac/sac.py:177-269: squashed-Gaussian actor, twin critics,
+    automatic entropy coefficient, polyak 0.005, Adam lr 3e-4) on a hand-filled single-env replay buffer: the sampled row
+    indices, the unit normals behind both policy samples of every step, and all weights before / after each step.  A
+    second part records ReplayBuffer.sample with a VecNormalize env: normalisation at SAMPLE time (buffers.py:245-254)."""
+    import torch
+    from stable_baselines3 import SAC
+    from stable_baselines3.common.vec_env import VecNormalize
+    from stable_baselines3.common.vec_env.base_vec_env import VecEnv
+    D, B, CAP = 14, 64, 200
+    obs_space = refshim.Box(-np.inf * np.ones(D), np.inf * np.ones(D), dtype=np.float32)
+    act_space = refshim.Box(-np.ones(3), np.ones(3), dtype=np.float32)
+
+    class Scripted(VecEnv):
+        def __init__(self):
+            VecEnv.__init__(self, 1, obs_space, act_space)
+
+        def reset(self): return np.zeros((1, D), np.float32)
+        def step_async(self, actions): pass
+        def step_wait(self): return np.zeros((1, D), np.float32), np.zeros(1, np.float32), np.zeros(1, bool), [{}]
+        def close(self): pass
+        def get_attr(self, *a, **k): return [None]
+        def set_attr(self, *a, **k): pass
+        def env_method(self, *a, **k): return [None]
+        def seed(self, seed=None): return [None]
+
+    torch.manual_seed(0)
+    m = SAC("MlpPolicy", Scripted(), buffer_size=CAP, batch_size=B, learning_rate=3e-4, gamma=0.99, tau=0.005,
+            policy_kwargs=dict(net_arch=[64, 64]), device="cpu", verbose=0)     # 2 x 64 keeps the fixture small
+    rs = np.random.RandomState(11)
+    rb = m.replay_buffer
+    for k in range(150):
+        rb.add(rs.standard_normal((1, D)).astype(np.float32), rs.standard_normal((1, D)).astype(np.float32),
+               rs.uniform(-1, 1, (1, 3)).astype(np.float32), rs.standard_normal(1).astype(np.float32),
+               (rs.uniform(size=1) < 0.1).astype(np.float32))
+    out = dict(rb_obs=rb.observations[:150, 0].copy(), rb_next_obs=rb.next_observations[:150, 0].copy(),
+               rb_act=rb.actions[:150, 0].copy(), rb_rew=rb.rewards[:150, 0].copy(), rb_done=rb.dones[:150, 0].copy())
+
+    def weights(tag):
+        o = {}
+        for k, v in m.policy.state_dict().items():
+            o["%s/%s" % (tag, k)] = v.detach().numpy().copy()
+        o["%s/log_ent_coef" % tag] = m.log_ent_coef.detach().numpy().copy()
+        return o
+
+    picked = []
+    inner = rb._get_samples
+    rb._get_samples = lambda batch_inds, env=None: (picked.append(np.array(batch_inds)), inner(batch_inds, env=env))[1]
+    rec = []
+    alp = m.actor.action_log_prob
+    m.actor.action_log_prob = lambda obs: (lambda r: (rec.append((r[0].detach().numpy().copy(), r[1].detach().numpy().copy())), r)[1])(alp(obs))
+    m._current_progress_remaining = 1.0
+    out.update(weights("w0"))
+    for k in (1, 2, 3):
+        np.random.seed(50 + k)
+        torch.manual_seed(100 + k)
+        m.train(gradient_steps=1, batch_size=B)
+        # the two policy samples of the step draw their unit normals from the default generator, in this order
+        torch.manual_seed(100 + k)
+        out["eps_pi_%d" % k], out["eps_next_%d" % k] = torch.randn(B, 3).numpy(), torch.randn(B, 3).numpy()
+        out["idx_%d" % k] = picked[-1]
+        out["actions_pi_%d" % k], out["log_prob_%d" % k] = rec[-2]
+        out.update(weights("w%d" % k))
+    # sample-time normalisation
+    venv = VecNormalize(Scripted(), clip_obs=5.0, clip_reward=3.0)
+    venv.obs_rms.update(rs.standard_normal((300, D)) * 2 + 0.5)
+    venv.ret_rms.update(rs.standard_normal(300) * 4)
+    idx = rs.randint(0, 150, size=40)
+    smp = inner(idx, env=venv)
+    out.update(norm_idx=idx, norm_obs=smp.observations.numpy(), norm_next_obs=smp.next_observations.numpy(),
+               norm_rew=smp.rewards.numpy().reshape(-1), norm_done=smp.dones.numpy().reshape(-1), norm_act=smp.actions.numpy(),
+               norm_obs_mean=venv.obs_rms.mean, norm_obs_var=venv.obs_rms.var, norm_ret_var=np.float64(venv.ret_rms.var))
+    np.savez_compressed(os.path.join(HERE, "sac_update.npz"), **out)
+
+
 def gen_curriculum():
     """set_curriculum_level (fixed_wing.py:334-412) on the default config and on the dev config: initial-state
     ranges of the simulator and target ranges, for several levels."""
@@ -782,7 +857,7 @@ def gen_dryden():
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     jobs = {"waypoint": gen_waypoint, "targets": gen_targets, "resample": gen_resample, "reward": gen_reward, "cnn": gen_cnn, "params": gen_params, "traj": gen_traj, "turb": gen_turb, "turb_moderate": gen_turb_moderate, "fail": gen_fail, "full": gen_full,
-            "pid": gen_pid, "gae": gen_gae, "vecnorm": gen_vecnorm, "ppo_update": gen_ppo_update, "curriculum": gen_curriculum, "dryden": gen_dryden}
+            "pid": gen_pid, "gae": gen_gae, "vecnorm": gen_vecnorm, "ppo_update": gen_ppo_update, "sac_update": gen_sac_update, "curriculum": gen_curriculum, "dryden": gen_dryden}
     for name, fn in jobs.items():
         if what in (name, "all"):
             t0 = time.time()

@@ -732,3 +732,67 @@ def test_fused_ppo_update_matches_the_reference_fixture(cuda_device):
             ref = g["w%d/%s" % (k, name)]
             err = np.abs(p.detach().cpu().numpy() - ref).max()
             assert err <= 2e-6 + 1e-5 * np.abs(ref - g["w0/" + name]).max(), (k, name, err)
+
+
+def test_sac_update_matches_the_reference_on_gpu(cuda_device):
+    """The same three reference gradient steps as tests/test_host_parallel.py::test_sac_update_matches_the_reference_on_cpu,
+    on the device (split-K linears, capturable Adam): tests/golden/sac_update.npz."""
+    from test_host_parallel import _sac_check_steps, _sac_from_fixture
+    g = load_golden("sac_update")
+    _sac_check_steps(_sac_from_fixture(g, "w0", "cuda"), g, "cuda", tol_scale=2.0)
+
+
+def test_replay_kernels_against_the_reference_semantics(cuda_device):
+    """fw_replay_insert / fw_replay_sample: packed rows land where the tensor path puts them (wrap-around included), a
+    sampled batch is exactly rows[indices] normalised like the live reference's ReplayBuffer._get_samples under VecNormalize
+    (tests/golden/sac_update.npz), indices are uniform over the filled part and change from call to call, and both calls
+    replay from a CUDA graph with the device-side head / counter advancing."""
+    import torch
+    from tum_adlr_deep_reinforcement_learning_b200.buffers import DeviceVecNormalize
+    from tum_adlr_deep_reinforcement_learning_b200.sac import ReplayBuffer
+    g = load_golden("sac_update")
+    dev = torch.device("cuda")
+    t = lambda k: torch.as_tensor(g["rb_" + k]).to(dev)
+    rb, cpu = ReplayBuffer(150, device=dev, seed=3), ReplayBuffer(150, device="cpu")
+    for lo in range(0, 150, 50):
+        for b, d in ((rb, dev), (cpu, "cpu")):
+            b.add(*(t(k)[lo:lo + 50].to(d) for k in ("obs", "next_obs", "act", "rew")), t("done")[lo:lo + 50].to(d))
+    rb.add(t("obs")[:7] + 1, t("next_obs")[:7], t("act")[:7], t("rew")[:7], t("done")[:7])
+    cpu.add(*(x.cpu() for x in (t("obs")[:7] + 1, t("next_obs")[:7], t("act")[:7], t("rew")[:7], t("done")[:7])))
+    assert torch.equal(rb.rows.cpu(), cpu.rows) and int(rb.head_dev) == 7 and int(rb.size_dev) == 150 and rb.pos == 7
+    norm = DeviceVecNormalize(1, device=dev, clip_obs=5.0, clip_reward=3.0)
+    norm.load_state_dict({"obs_mean": g["norm_obs_mean"], "obs_var": g["norm_obs_var"], "obs_count": 1.0,
+                          "ret_mean": 0.0, "ret_var": g["norm_ret_var"], "ret_count": 1.0})
+    obs, act, nxt, done, rew = rb.sample(4096, norm=norm)
+    idx = rb.last_indices.clone()
+    assert int(idx.min()) >= 0 and int(idx.max()) < 150
+    nc = DeviceVecNormalize(1, device="cpu", clip_obs=5.0, clip_reward=3.0)
+    nc.load_state_dict({k: v.cpu() for k, v in norm.state_dict().items()})
+    ro, ra, rn, rd, rr = cpu.sample(4096, norm=nc, indices=idx.cpu())
+    assert np.allclose(obs.cpu().numpy(), ro.numpy(), atol=1e-6) and np.allclose(nxt.cpu().numpy(), rn.numpy(), atol=1e-6)
+    assert np.allclose(rew.cpu().numpy(), rr.numpy(), atol=1e-6) and torch.equal(act.cpu(), ra) and torch.equal(done.cpu(), rd)
+    counts = np.bincount(idx.cpu().numpy(), minlength=150)
+    assert counts.min() > 0 and abs(counts.std() - np.sqrt(4096 / 150)) < 2.5        # Poisson-like spread, no hole
+    rb.sample(4096, norm=norm)
+    assert not torch.equal(rb.last_indices, idx) and int(rb.calls_dev) == 2
+    # reference fixture rows through the kernel's normalisation: batch == ring in order
+    fx = ReplayBuffer(150, device=dev)
+    fx.add(t("obs"), t("next_obs"), t("act"), t("rew"), t("done"))
+    o2 = fx.sample(2000, norm=norm)
+    pick = fx.last_indices.cpu().numpy()
+    sel = [int(np.flatnonzero(pick == i)[0]) for i in g["norm_idx"] if (pick == i).any()]
+    want = [k for k, i in enumerate(g["norm_idx"]) if (pick == i).any()]
+    assert len(want) > 30
+    assert np.allclose(o2[0].cpu().numpy()[sel], g["norm_obs"][want], atol=1e-6)
+    assert np.allclose(o2[4].cpu().numpy()[sel], g["norm_rew"][want], atol=1e-6)
+    # captured in a CUDA graph: head and sample counter advance on the device with every replay
+    gr = torch.cuda.CUDAGraph()
+    src = [x.clone() for x in (t("obs")[:10], t("next_obs")[:10], t("act")[:10], t("rew")[:10], t("done")[:10])]
+    torch.cuda.synchronize()
+    with torch.cuda.graph(gr):
+        rb.add(*src, advance_host=False)
+        out = rb.sample(256, norm=norm)
+    h0, c0 = int(rb.head_dev), int(rb.calls_dev)
+    gr.replay(); first = rb.last_indices.clone(); gr.replay()
+    torch.cuda.synchronize()
+    assert int(rb.head_dev) == (h0 + 20) % 150 and int(rb.calls_dev) == c0 + 2 and not torch.equal(first, rb.last_indices)

@@ -123,8 +123,8 @@ def test_replay_buffer_ring_semantics():
     # slots 0,1 were overwritten by transitions 10, 11; the rest still hold 2..9
     assert buf.observations[:, 0].tolist() == [10, 11, 2, 3, 4, 5, 6, 7, 8, 9]
     assert buf.next_observations[0, 0].item() == 110 and buf.dones[1].item() == 1.0
-    g = torch.Generator().manual_seed(0)
-    o, a, no, d, r = buf.sample(256, generator=g)
+    torch.manual_seed(0)
+    o, a, no, d, r = buf.sample(256)
     assert o.shape == (256, 2) and set(o[:, 0].tolist()) <= set(range(2, 12))
     assert torch.equal(no, o + 100) and torch.equal(r, o[:, 0])
     small = ReplayBuffer(100, obs_dim=2, action_dim=1, device="cpu")
@@ -294,3 +294,108 @@ def test_vecnormalize_checkpoint_round_trips_with_the_reference_format(tmp_path)
     back = DeviceVecNormalize(3, obs_dim=5, device="cpu").load(str(tmp_path / "ref.pkl"))
     assert np.array_equal(back.obs_rms.mean.numpy(), ref2.obs_rms.mean) and float(back.ret_rms.var) == float(ref2.ret_rms.var)
     assert float(back.obs_rms.count) == ref2.obs_rms.count and back.clip_reward == 4.0
+
+
+def _sac_from_fixture(g, tag, device):
+    """sac.SAC (2 x 64 networks) with the reference SACPolicy weights of snapshot `tag` (tests/golden/sac_update.npz)."""
+    import types
+    import torch
+    from tum_adlr_deep_reinforcement_learning_b200 import sac as S
+
+    env = types.SimpleNamespace(device=torch.device(device), num_envs=1, sim=types.SimpleNamespace(obs_dim=14))
+    real_mlp = S._mlp
+    S._mlp = lambda inp, out, hidden=(64, 64): real_mlp(inp, out, (64, 64))
+    try:
+        algo = S.SAC(env, buffer_size=256, batch_size=64, normalize=False, use_cuda_graph=False)
+    finally:
+        S._mlp = real_mlp
+    _sac_load(algo, g, tag)
+    return algo
+
+
+def _sac_ref_weights(g, tag):
+    """name -> array for (actor.net, critic.qs, critic_target.qs, log_ent_coef) in sac.py's layout: the reference keeps
+    mu / log_std as two Linear heads (sac/policies.py:95-107), sac.Actor one Linear whose output is chunked in two."""
+    t = lambda k: g["%s/%s" % (tag, k)]
+    out = {}
+    for i, j in ((0, 0), (2, 2)):
+        out["actor.net.%d.weight" % j], out["actor.net.%d.bias" % j] = t("actor.latent_pi.%d.weight" % i), t("actor.latent_pi.%d.bias" % i)
+    out["actor.net.4.weight"] = np.concatenate([t("actor.mu.weight"), t("actor.log_std.weight")])
+    out["actor.net.4.bias"] = np.concatenate([t("actor.mu.bias"), t("actor.log_std.bias")])
+    for net in ("critic", "critic_target"):
+        for q in (0, 1):
+            for layer in (0, 2, 4):
+                for leaf in ("weight", "bias"):
+                    out["%s.qs.%d.%d.%s" % (net, q, layer, leaf)] = t("%s.qf%d.%d.%s" % (net, q, layer, leaf))
+    out["log_ent_coef"] = t("log_ent_coef")
+    return out
+
+
+def _sac_named(algo):
+    import itertools
+    return dict(itertools.chain((("actor." + k, v) for k, v in algo.actor.named_parameters()),
+                                (("critic." + k, v) for k, v in algo.critic.named_parameters()),
+                                (("critic_target." + k, v) for k, v in algo.critic_target.named_parameters()),
+                                [("log_ent_coef", algo.log_ent_coef)]))
+
+
+def _sac_load(algo, g, tag):
+    import torch
+    ref = _sac_ref_weights(g, tag)
+    with torch.no_grad():
+        for k, p in _sac_named(algo).items():
+            p.copy_(torch.as_tensor(ref[k]).reshape(p.shape))
+
+
+def _sac_check_steps(algo, g, device, tol_scale=1.0):
+    import torch
+    dev = torch.device(device)
+    rows = {k: torch.as_tensor(g["rb_" + k]).to(dev) for k in ("obs", "next_obs", "act", "rew", "done")}
+    w0 = _sac_ref_weights(g, "w0")
+    for k in (1, 2, 3):
+        idx = torch.as_tensor(g["idx_%d" % k]).to(dev)
+        batch = (rows["obs"][idx], rows["act"][idx], rows["next_obs"][idx], rows["done"][idx], rows["rew"][idx])
+        noise = (torch.as_tensor(g["eps_pi_%d" % k]).to(dev), torch.as_tensor(g["eps_next_%d" % k]).to(dev))
+        if k == 1:
+            with torch.no_grad():
+                a_pi, logp = algo.actor(batch[0], eps=noise[0])
+            assert np.allclose(a_pi.cpu().numpy(), g["actions_pi_1"], atol=2e-6)
+            assert np.allclose(logp.cpu().numpy(), g["log_prob_1"].reshape(-1), atol=2e-5)
+        algo.train_step(batch=batch, noise=noise)
+        ref = _sac_ref_weights(g, "w%d" % k)
+        for name, p in _sac_named(algo).items():
+            got = p.detach().cpu().numpy().reshape(ref[name].shape)
+            step = np.abs(ref[name] - w0[name]).max()
+            assert np.abs(got - ref[name]).max() <= tol_scale * (2e-6 + 2e-3 * step), (k, name, np.abs(got - ref[name]).max(), step)
+
+
+def test_sac_update_matches_the_reference_on_cpu():
+    """sac.SAC.train_step against three gradient steps of the live reference's SAC.train() (sac/sac.py:177-269;
+    tests/golden/sac_update.npz: same sampled rows, same unit normals): actor, both critics, the polyak-averaged targets and
+    the entropy coefficient after every step."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sac_update.npz"))
+    _sac_check_steps(_sac_from_fixture(g, "w0", "cpu"), g, "cpu")
+
+
+def test_replay_ring_semantics_on_cpu():
+    """ReplayBuffer (tensor path): packed rows, wrap-around insert, and sample-time normalisation equal to the live
+    reference's ReplayBuffer._get_samples under a VecNormalize env (buffers.py:245-254)."""
+    import torch
+    from tum_adlr_deep_reinforcement_learning_b200.buffers import DeviceVecNormalize
+    from tum_adlr_deep_reinforcement_learning_b200.sac import ReplayBuffer
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sac_update.npz"))
+    rb = ReplayBuffer(150, device="cpu")
+    t = lambda k: torch.as_tensor(g["rb_" + k])
+    for lo in range(0, 150, 50):
+        rb.add(t("obs")[lo:lo + 50], t("next_obs")[lo:lo + 50], t("act")[lo:lo + 50], t("rew")[lo:lo + 50], t("done")[lo:lo + 50])
+    assert rb.full and rb.pos == 0 and int(rb.size_dev) == 150 and int(rb.head_dev) == 0
+    assert torch.equal(rb.observations, t("obs")) and torch.equal(rb.dones, t("done"))
+    norm = DeviceVecNormalize(1, device="cpu", clip_obs=5.0, clip_reward=3.0)
+    norm.load_state_dict({"obs_mean": g["norm_obs_mean"], "obs_var": g["norm_obs_var"], "obs_count": 1.0,
+                          "ret_mean": 0.0, "ret_var": g["norm_ret_var"], "ret_count": 1.0})
+    obs, act, nxt, done, rew = rb.sample(40, norm=norm, indices=torch.as_tensor(g["norm_idx"]))
+    assert np.allclose(obs.numpy(), g["norm_obs"], atol=1e-6) and np.allclose(nxt.numpy(), g["norm_next_obs"], atol=1e-6)
+    assert np.allclose(rew.numpy(), g["norm_rew"], atol=1e-6) and np.array_equal(done.numpy(), g["norm_done"])
+    assert np.array_equal(act.numpy(), g["norm_act"])
+    rb.add(t("obs")[:7] + 1, t("next_obs")[:7], t("act")[:7], t("rew")[:7], t("done")[:7])      # wraps over the oldest rows
+    assert rb.pos == 7 and torch.equal(rb.observations[:7], t("obs")[:7] + 1) and torch.equal(rb.observations[7:], t("obs")[7:])

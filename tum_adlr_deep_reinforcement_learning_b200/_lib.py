@@ -21,6 +21,20 @@ class FwRolloutPost(ctypes.Structure):
          ("norm_obs", ctypes.c_int32), ("norm_reward", ctypes.c_int32), ("training", ctypes.c_int32)])
 
 
+class FwReplay(ctypes.Structure):
+    """Mirror of FwReplay in include/fwb200.h."""
+    _fields_ = [("rows", ctypes.c_void_p), ("head_dev", ctypes.c_void_p), ("size_dev", ctypes.c_void_p),
+                ("sample_calls_dev", ctypes.c_void_p), ("capacity", ctypes.c_int64), ("obs_dim", ctypes.c_int32),
+                ("act_dim", ctypes.c_int32), ("row_floats", ctypes.c_int32), ("_pad", ctypes.c_int32)]
+
+
+class FwReplayNorm(ctypes.Structure):
+    """Mirror of FwReplayNorm in include/fwb200.h."""
+    _fields_ = [("obs_mean", ctypes.c_void_p), ("obs_var", ctypes.c_void_p), ("ret_var", ctypes.c_void_p),
+                ("clip_obs", ctypes.c_float), ("clip_reward", ctypes.c_float), ("epsilon", ctypes.c_float),
+                ("norm_obs", ctypes.c_int32), ("norm_reward", ctypes.c_int32), ("_pad", ctypes.c_int32)]
+
+
 class FwError(RuntimeError):
     pass
 
@@ -57,6 +71,13 @@ def lib():
     L.fw_ppo_loss.argtypes = [_vp] * 7 + [ctypes.c_int32, ctypes.c_float, ctypes.c_float, ctypes.c_float] + [_vp] * 6
     L.fw_rollout_post_step.argtypes = [ctypes.POINTER(FwRolloutPost), _vp]
     L.fw_adam_clip_step.argtypes = [_vp] * 5 + [ctypes.c_int32] + [ctypes.c_float] * 5 + [_vp]
+    L.fw_replay_insert.argtypes = [ctypes.POINTER(FwReplay), _vp, _vp, _vp, _vp, _vp, ctypes.c_int32, _vp]
+    L.fw_replay_sample.argtypes = [ctypes.POINTER(FwReplay), ctypes.POINTER(FwReplayNorm), ctypes.c_int32, ctypes.c_uint64,
+                                   _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+    L.fw_replay_size.restype = ctypes.c_int
+    L.fw_replay_norm_size.restype = ctypes.c_int
+    if L.fw_replay_size() != ctypes.sizeof(FwReplay) or L.fw_replay_norm_size() != ctypes.sizeof(FwReplayNorm):
+        raise FwError("FwReplay / FwReplayNorm layout mismatch between _lib.py and include/fwb200.h")
     L.fw_join.argtypes = [_vp, _vp]
     L.fw_set_info_rows.argtypes = [_vp, _vp, ctypes.c_int32]
     L.fw_set_profiling.argtypes = [_vp, ctypes.c_int32]
@@ -80,4 +101,4 @@ def check(rc, what):
 
 EXPORTS = ("fw_create", "fw_destroy", "fw_set_config", "fw_state_blob_size", "fw_get_state_blob", "fw_set_state_blob", "fw_last_error", "fw_abi_version", "fw_reset", "fw_step", "fw_step_random",
            "fw_get_episode_info", "fw_get_field", "fw_set_field", "fw_gae", "fw_measure_fma_peak", "fw_debug_math",
-           "fw_obs_dim", "fw_set_waypoint_tasks", "fw_set_profiling", "fw_get_profile", "fw_join", "fw_set_info_rows", "fw_ppo_loss", "fw_rollout_post_step", "fw_adam_clip_step")
+           "fw_obs_dim", "fw_set_waypoint_tasks", "fw_set_profiling", "fw_get_profile", "fw_join", "fw_set_info_rows", "fw_ppo_loss", "fw_rollout_post_step", "fw_adam_clip_step", "fw_replay_insert", "fw_replay_sample")

@@ -23,53 +23,48 @@ LOG_STD_MIN, LOG_STD_MAX = -20.0, 2.0
 
 
 class ReplayBuffer:
-    def __init__(self, capacity, obs_dim=14, action_dim=3, device="cuda"):
-        self.capacity = int(capacity)
+    """The replay ring in HBM behind fw_replay_insert / fw_replay_sample (csrc/fw_replay.cu): one packed row per
+    transition, ORIGINAL observations and rewards stored, normalisation with the current VecNormalize statistics at
+    sample time (buffers.py:245-254), ring head / fill level / Philox sample counter on the device (CUDA-graph safe).
+    On a CPU device (tests) the same layout and semantics run as tensor ops."""
+
+    def __init__(self, capacity, obs_dim=14, action_dim=3, device="cuda", seed=0):
+        self.capacity, self.obs_dim, self.action_dim = int(capacity), int(obs_dim), int(action_dim)
         self.device = torch.device(device)
         d = self.device
-        self.observations = torch.zeros(self.capacity, obs_dim, dtype=torch.float32, device=d)
-        self.next_observations = torch.zeros(self.capacity, obs_dim, dtype=torch.float32, device=d)
-        self.actions = torch.zeros(self.capacity, action_dim, dtype=torch.float32, device=d)
-        self.rewards = torch.zeros(self.capacity, dtype=torch.float32, device=d)
-        self.dones = torch.zeros(self.capacity, dtype=torch.float32, device=d)
-        self.pos = 0
-        self.full = False
-        self.size_dev = torch.zeros((), dtype=torch.float32, device=d)
-        self.pos_dev = torch.zeros((), dtype=torch.long, device=d)
-        self._arange = None
+        self.row_floats = (2 * self.obs_dim + self.action_dim + 2 + 3) // 4 * 4
+        self.rows = torch.zeros(self.capacity, self.row_floats, dtype=torch.float32, device=d)
+        self.head_dev = torch.zeros((), dtype=torch.long, device=d)
+        self.size_dev = torch.zeros((), dtype=torch.long, device=d)
+        self.calls_dev = torch.zeros((), dtype=torch.long, device=d)
+        self.seed = int(seed)
+        self.pos, self.full = 0, False               # host mirror of the ring head (advance_host)
+        self.last_indices = None
+        self._c = None
+
+    # views of the packed rows, reference names (buffers.py:176-184)
+    @property
+    def observations(self):
+        return self.rows[:, :self.obs_dim]
+
+    @property
+    def next_observations(self):
+        return self.rows[:, self.obs_dim:2 * self.obs_dim]
+
+    @property
+    def actions(self):
+        return self.rows[:, 2 * self.obs_dim:2 * self.obs_dim + self.action_dim]
+
+    @property
+    def rewards(self):
+        return self.rows[:, 2 * self.obs_dim + self.action_dim]
+
+    @property
+    def dones(self):
+        return self.rows[:, 2 * self.obs_dim + self.action_dim + 1]
 
     def size(self):
         return self.capacity if self.full else self.pos
-
-    def add(self, obs, next_obs, action, reward, done):
-        """Batched insert of n transitions (one per env) at the ring head, wrapping around the end."""
-        n = obs.shape[0]
-        assert n <= self.capacity
-        first = min(n, self.capacity - self.pos)
-        for dst, src in ((self.observations, obs), (self.next_observations, next_obs), (self.actions, action),
-                         (self.rewards, reward), (self.dones, done.to(torch.float32))):
-            dst[self.pos:self.pos + first].copy_(src[:first])
-            if first < n:
-                dst[:n - first].copy_(src[first:])
-        self.pos += n
-        if self.pos >= self.capacity:
-            self.full = True
-            self.pos -= self.capacity
-        self.size_dev.fill_(float(self.size()))
-        self.pos_dev.fill_(self.pos)
-
-    def add_capturable(self, obs, next_obs, action, reward, done):
-        """add() with the ring head read from / advanced on the device (`pos_dev`), as one scatter per array: usable
-        inside a captured CUDA graph.  The caller mirrors the advance on the host with advance_host(n)."""
-        n = obs.shape[0]
-        if self._arange is None or self._arange.numel() != n:
-            self._arange = torch.arange(n, device=self.device)
-        idx = (self.pos_dev + self._arange) % self.capacity
-        for dst, src in ((self.observations, obs), (self.next_observations, next_obs), (self.actions, action),
-                         (self.rewards, reward), (self.dones, done.to(torch.float32))):
-            dst.index_copy_(0, idx, src)
-        self.pos_dev.add_(n).remainder_(self.capacity)
-        self.size_dev.add_(float(n)).clamp_(max=float(self.capacity))
 
     def advance_host(self, n):
         self.pos += n
@@ -77,17 +72,77 @@ class ReplayBuffer:
             self.full = True
             self.pos -= self.capacity
 
-    def sample(self, batch_size, generator=None):
-        idx = torch.randint(0, self.size(), (batch_size,), device=self.device, generator=generator)
-        return (self.observations[idx], self.actions[idx], self.next_observations[idx], self.dones[idx],
-                self.rewards[idx])
+    def _struct(self):
+        if self._c is None:
+            from . import _lib
+            self._c = _lib.FwReplay(rows=self.rows.data_ptr(), head_dev=self.head_dev.data_ptr(),
+                                    size_dev=self.size_dev.data_ptr(), sample_calls_dev=self.calls_dev.data_ptr(),
+                                    capacity=self.capacity, obs_dim=self.obs_dim, act_dim=self.action_dim,
+                                    row_floats=self.row_floats)
+        return self._c
 
-    def sample_capturable(self, batch_size):
-        """Uniform sample whose range is read from a device scalar (`size_dev`, kept current by add()): usable inside a
-        captured CUDA graph, where a python-side size would be frozen at capture time."""
-        idx = (torch.rand(batch_size, device=self.device) * self.size_dev).long().clamp_(max=self.capacity - 1)
-        return (self.observations[idx], self.actions[idx], self.next_observations[idx], self.dones[idx],
-                self.rewards[idx])
+    def add(self, obs, next_obs, action, reward, done, advance_host=True):
+        """Batched insert of n transitions (one per env) at the ring head, wrapping around the end.  advance_host=False
+        when the call is being captured into / replayed from a CUDA graph: the caller then mirrors every replay with
+        advance_host(n)."""
+        n = obs.shape[0]
+        assert n <= self.capacity
+        if self.device.type == "cuda":
+            import ctypes
+            from . import _lib
+            t = [obs.contiguous(), next_obs.contiguous(), action.contiguous(), reward.contiguous(),
+                 done.to(torch.uint8).contiguous()]
+            assert all(x.is_cuda for x in t) and all(x.dtype == torch.float32 for x in t[:4])
+            self._keep = t
+            _lib.check(_lib.lib().fw_replay_insert(ctypes.byref(self._struct()), *[ctypes.c_void_p(x.data_ptr()) for x in t],
+                                                   n, ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)),
+                       "fw_replay_insert")
+        else:
+            idx = (self.head_dev + torch.arange(n)) % self.capacity
+            row = torch.zeros(n, self.row_floats)
+            D, A = self.obs_dim, self.action_dim
+            row[:, :D], row[:, D:2 * D], row[:, 2 * D:2 * D + A] = obs, next_obs, action
+            row[:, 2 * D + A], row[:, 2 * D + A + 1] = reward, done.to(torch.float32)
+            self.rows.index_copy_(0, idx, row)
+            self.head_dev.add_(n).remainder_(self.capacity)
+            self.size_dev.add_(n).clamp_(max=self.capacity)
+        if advance_host:
+            self.advance_host(n)
+
+    def sample(self, batch_size, norm=None, indices=None):
+        """(observations, actions, next_observations, dones, rewards) of batch_size uniformly drawn transitions;
+        `norm` (DeviceVecNormalize) normalises observations and rewards with its CURRENT statistics.  `indices`
+        (tests) replaces the draw."""
+        D, A = self.obs_dim, self.action_dim
+        if self.device.type == "cuda" and indices is None:
+            import ctypes
+            from . import _lib
+            dev = self.device
+            out = [torch.empty(batch_size, D, device=dev), torch.empty(batch_size, A, device=dev),
+                   torch.empty(batch_size, D, device=dev), torch.empty(batch_size, device=dev),
+                   torch.empty(batch_size, device=dev)]
+            self.last_indices = torch.empty(batch_size, dtype=torch.long, device=dev)
+            nm = _lib.FwReplayNorm()
+            if norm is not None:
+                nm.obs_mean, nm.obs_var = norm.obs_rms.mean.data_ptr(), norm.obs_rms.var.data_ptr()
+                nm.ret_var = norm.ret_rms.var.data_ptr()
+                nm.clip_obs, nm.clip_reward, nm.epsilon = norm.clip_obs, norm.clip_reward, norm.epsilon
+                nm.norm_obs, nm.norm_reward = int(norm.norm_obs), int(norm.norm_reward)
+            p = lambda x: ctypes.c_void_p(x.data_ptr())
+            _lib.check(_lib.lib().fw_replay_sample(ctypes.byref(self._struct()), ctypes.byref(nm), batch_size, self.seed,
+                                                   p(out[0]), p(out[1]), p(out[2]), p(out[3]), p(out[4]),
+                                                   p(self.last_indices),
+                                                   ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
+                       "fw_replay_sample")
+            return tuple(out)
+        if indices is None:
+            indices = torch.randint(0, self.size(), (batch_size,), device=self.device)
+        self.last_indices = indices
+        r = self.rows[indices]
+        obs, nxt, rew = r[:, :D], r[:, D:2 * D], r[:, 2 * D + A]
+        if norm is not None:
+            obs, nxt, rew = norm.normalize_obs(obs), norm.normalize_obs(nxt), norm.normalize_reward(rew)
+        return obs, r[:, 2 * D:2 * D + A], nxt, r[:, 2 * D + A + 1], rew
 
 
 def _mlp(inp, out, hidden=(256, 256)):
@@ -106,11 +161,12 @@ class Actor(nn.Module):
         self.net = _mlp(obs_dim, 2 * action_dim, hidden)
         self.action_dim = action_dim
 
-    def forward(self, obs, deterministic=False):
+    def forward(self, obs, deterministic=False, eps=None):
+        """`eps`: the unit normals of the reparameterised sample (tests inject the reference's draws)."""
         mean, log_std = self.net(obs).chunk(2, dim=-1)
         log_std = log_std.clamp(LOG_STD_MIN, LOG_STD_MAX)
         std = log_std.exp()
-        u = mean if deterministic else mean + std * torch.randn_like(mean)
+        u = mean if deterministic else mean + std * (torch.randn_like(mean) if eps is None else eps)
         a = torch.tanh(u)
         # log prob of the squashed Gaussian (SquashedDiagGaussianDistribution, common/distributions.py)
         logp = (-0.5 * ((u - mean) / std).pow(2) - log_std - 0.5 * math.log(2 * math.pi)).sum(-1)
@@ -131,8 +187,9 @@ class Critic(nn.Module):
 class SAC:
     def __init__(self, env, buffer_size=1_000_000, batch_size=4096, gradient_steps=2, learning_starts=10_000,
                  learning_rate=3e-4, gamma=0.99, tau=0.005, target_entropy="auto", normalize=True, seed=0,
-                 use_cuda_graph=True):
+                 use_cuda_graph=True, allow_eager_fallback=False):
         self.env, self.device, self.n_envs = env, env.device, env.num_envs
+        self.allow_eager_fallback = bool(allow_eager_fallback)
         self.batch_size, self.gradient_steps, self.learning_starts = batch_size, gradient_steps, learning_starts
         self.gamma, self.tau = gamma, tau
         torch.manual_seed(seed)
@@ -152,7 +209,8 @@ class SAC:
         self._graph_stats = None
         self._env_graph = None
         self._env_warm = 0
-        self.buffer = ReplayBuffer(buffer_size, obs_dim=od, device=self.device)
+        self.buffer = ReplayBuffer(buffer_size, obs_dim=od, device=self.device, seed=seed)
+        self._last_obs_raw = None
         self.norm = DeviceVecNormalize(self.n_envs, obs_dim=od, device=self.device, gamma=gamma, norm_obs=normalize,
                                        norm_reward=normalize)
         self.num_timesteps = 0
@@ -174,11 +232,11 @@ class SAC:
         self.ep_ret_sum.add_((self._run_ret * d).sum())
         self.ep_count.add_(d.sum())
         self._run_ret.masked_fill_(d, 0.0)
-        obs, rew = self.norm.step(obs_raw, rew_raw, done)
-        if capturable:
-            self.buffer.add_capturable(self._last_obs, obs, actions, rew, done)
-        else:
-            self.buffer.add(self._last_obs, obs, actions, rew, done)
+        obs, _ = self.norm.step(obs_raw, rew_raw, done)
+        # the ring keeps the ORIGINAL observation and reward (off_policy_algorithm.py:430-436); they are normalised with
+        # the statistics current when a batch is drawn (buffers.py:245-254)
+        self.buffer.add(self._last_obs_raw, obs_raw, actions, rew_raw, done, advance_host=not capturable)
+        self._last_obs_raw.copy_(obs_raw)
         self._last_obs.copy_(obs)
 
     def _env_step(self):
@@ -245,18 +303,18 @@ class SAC:
         self._train_graph.replay()
         return self._graph_stats
 
-    def train_step(self, capturable=False):
-        """One gradient step of sac.py:196-256 on a device-sampled batch."""
-        obs, act, next_obs, done, rew = (self.buffer.sample_capturable(self.batch_size) if capturable
-                                         else self.buffer.sample(self.batch_size))
-        a_pi, logp = self.actor(obs)
+    def train_step(self, capturable=False, batch=None, noise=(None, None)):
+        """One gradient step of sac.py:196-256 on a device-sampled batch.  `batch` / `noise` (tests): a given
+        (obs, actions, next_obs, dones, rewards) tuple and the unit normals of the two policy samples."""
+        obs, act, next_obs, done, rew = batch if batch is not None else self.buffer.sample(self.batch_size, norm=self.norm)
+        a_pi, logp = self.actor(obs, eps=noise[0])
         ent_coef = self.log_ent_coef.exp().detach()
         ent_loss = -(self.log_ent_coef * (logp + self.target_entropy).detach()).mean()
         self.ent_opt.zero_grad(set_to_none=not capturable)
         ent_loss.backward()
         self.ent_opt.step()
         with torch.no_grad():
-            na, nlogp = self.actor(next_obs)
+            na, nlogp = self.actor(next_obs, eps=noise[1])
             q_next = torch.min(*self.critic_target(next_obs, na)) - ent_coef * nlogp
             target = rew + (1 - done) * self.gamma * q_next
         q1, q2 = self.critic(obs, act)
@@ -277,7 +335,9 @@ class SAC:
 
     def learn(self, total_timesteps, log_every=50, callback=None):
         if self._last_obs is None:
-            self._last_obs = self.norm.reset(self.env.reset_tensor()).clone()
+            raw = self.env.reset_tensor()
+            self._last_obs_raw = raw.clone()
+            self._last_obs = self.norm.reset(raw).clone()
             self._t_start, self._it = time.time(), 0
         while self.num_timesteps < total_timesteps:
             self._env_step()
