@@ -423,6 +423,30 @@ int fw_replay_sample(const FwReplay* rb, const FwReplayNorm* norm, int32_t batch
                      float* actions_out_dev, float* next_obs_out_dev, float* dones_out_dev, float* rewards_out_dev,
                      int64_t* indices_out_dev, void* stream);
 
+/* The PPO gradient all-reduce (one mean of the flattened 42 KB policy gradient per optimiser step, the only
+ * collective of the path) fused with clip_grad_norm_ + Adam (ppo/ppo.py:212-214) in ONE single-block kernel per rank over
+ * NVLink peer memory: each rank's buffer is mapped by its peers through CUDA IPC, ranks signal and wait through flag words
+ * in each other's buffers, every rank pushes its gradient into the peers' buffers, adds the slots in rank order
+ * (bit-identical replicas) and applies the update.  Replaces ncclAllReduce + a divide + fw_adam_clip_step.  One process per GPU on ONE node:
+ *   fw_comm_create   allocates the rank's buffer (flags + 2 x world slots of n_floats: every peer pushes into its slot)
+ *   fw_comm_export   -> FW_COMM_HANDLE_BYTES bytes to hand to every peer (e.g. torch.distributed.all_gather)
+ *   fw_comm_connect  handles of ALL ranks, world x FW_COMM_HANDLE_BYTES bytes in rank order (the own entry is ignored)
+ *   fw_comm_allreduce_adam   grad_dev is replaced by the mean gradient; then as fw_adam_clip_step.  Asynchronous on `stream`,
+ *                    capturable; every rank must make the same sequence of calls.  A peer that does not arrive within ~2 s
+ *                    sets the error word (fw_comm_error returns 1) instead of hanging the GPU. */
+#define FW_COMM_MAX_WORLD 8
+#define FW_COMM_HANDLE_BYTES 64
+typedef struct FwComm FwComm;
+int fw_comm_create(int32_t n_floats, int32_t world, int32_t rank, int32_t device, FwComm** out);
+int fw_comm_export(FwComm* c, void* handle64);
+int fw_comm_connect(FwComm* c, const void* handles);
+int fw_comm_allreduce_adam(FwComm* c, float* param_dev, float* grad_dev, float* exp_avg_dev, float* exp_avg_sq_dev,
+                           float* step_dev, int32_t n, float lr, float beta1, float beta2, float eps, float max_norm,
+                           void* stream);
+int fw_comm_error(FwComm* c);
+int fw_comm_destroy(FwComm* c);
+const char* fw_comm_last_error(void);
+
 /* Vector-pipe peak micro-benchmarks (dependent-chain-free FMA loops) used as roofline denominators by bench.py:
  * returns achieved TFLOP/s (2 flop per FMA) measured with CUDA events on `device`. */
 int fw_measure_fma_peak(int32_t device, int32_t precision, double* tflops_out);

@@ -305,3 +305,24 @@ def test_ppo_checkpoint_resume_is_bit_identical(cuda_device, tmp_path):
     assert worst < 1e-3
     for e in (env_a, env_b, env_c):
         e.close()
+
+
+def test_peer_allreduce_adam_on_two_gpus(cuda_device):
+    """fw_comm_allreduce_adam (gradient mean over NVLink peer memory + clip + Adam in one kernel) against
+    ncclAllReduce + divide + fw_adam_clip_step: bit-identical parameters on 2 ranks over 30 steps, replicas identical,
+    capturable in a CUDA graph (tools/comm_test.py under torchrun).  Needs two GPUs; skipped otherwise."""
+    import json
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tools", "comm_test.py")],
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300, cwd=root)
+    lines = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
+    assert res.returncode == 0 and lines, res.stdout[-2000:]
+    out = json.loads(lines[-1])
+    assert out["world"] == 2 and out["max_param_diff"] == 0.0

@@ -78,6 +78,13 @@ def lib():
     L.fw_replay_norm_size.restype = ctypes.c_int
     if L.fw_replay_size() != ctypes.sizeof(FwReplay) or L.fw_replay_norm_size() != ctypes.sizeof(FwReplayNorm):
         raise FwError("FwReplay / FwReplayNorm layout mismatch between _lib.py and include/fwb200.h")
+    L.fw_comm_create.argtypes = [ctypes.c_int32] * 4 + [ctypes.POINTER(_vp)]
+    L.fw_comm_export.argtypes = [_vp, _vp]
+    L.fw_comm_connect.argtypes = [_vp, _vp]
+    L.fw_comm_allreduce_adam.argtypes = [_vp] * 6 + [ctypes.c_int32] + [ctypes.c_float] * 5 + [_vp]
+    L.fw_comm_error.argtypes = [_vp]
+    L.fw_comm_destroy.argtypes = [_vp]
+    L.fw_comm_last_error.restype = ctypes.c_char_p
     L.fw_join.argtypes = [_vp, _vp]
     L.fw_set_info_rows.argtypes = [_vp, _vp, ctypes.c_int32]
     L.fw_set_profiling.argtypes = [_vp, ctypes.c_int32]
@@ -101,4 +108,5 @@ def check(rc, what):
 
 EXPORTS = ("fw_create", "fw_destroy", "fw_set_config", "fw_state_blob_size", "fw_get_state_blob", "fw_set_state_blob", "fw_last_error", "fw_abi_version", "fw_reset", "fw_step", "fw_step_random",
            "fw_get_episode_info", "fw_get_field", "fw_set_field", "fw_gae", "fw_measure_fma_peak", "fw_debug_math",
-           "fw_obs_dim", "fw_set_waypoint_tasks", "fw_set_profiling", "fw_get_profile", "fw_join", "fw_set_info_rows", "fw_ppo_loss", "fw_rollout_post_step", "fw_adam_clip_step", "fw_replay_insert", "fw_replay_sample")
+           "fw_obs_dim", "fw_set_waypoint_tasks", "fw_set_profiling", "fw_get_profile", "fw_join", "fw_set_info_rows", "fw_ppo_loss", "fw_rollout_post_step", "fw_adam_clip_step", "fw_replay_insert", "fw_replay_sample", "fw_comm_create", "fw_comm_export", "fw_comm_connect",
+           "fw_comm_allreduce_adam", "fw_comm_error", "fw_comm_destroy", "fw_comm_last_error")

@@ -5,7 +5,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfwb200.so")
-SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("fw_step.cu", "fw_gae.cu", "fw_ppo.cu", "fw_replay.cu")]
+SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("fw_step.cu", "fw_gae.cu", "fw_ppo.cu", "fw_replay.cu", "fw_comm.cu")]
 HEADERS = [os.path.join(_HERE, "csrc", "fw_device.cuh"), os.path.join(_HERE, "csrc", "fw_math.cuh"), os.path.join(os.path.dirname(_HERE), "include", "fwb200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-shared"]

@@ -166,10 +166,56 @@ class FlatAdam:
     def zero_grad(self, set_to_none=False):
         self.grad.zero_()
 
+    def enable_peer_allreduce(self, dist):
+        """Data-parallel runs on one node: step() becomes fw_comm_allreduce_adam — gradient mean over all ranks (NVLink
+        peer memory, ranks added in rank order), clip and Adam in ONE launch instead of ncclAllReduce + divide + step.
+        Returns False (and changes nothing) when the peers' buffers cannot be mapped."""
+        import ctypes
+        from . import _lib
+        world, rank = dist.get_world_size(), dist.get_rank()
+        if world < 2 or world > 8:
+            return False
+        L = _lib.lib()
+        h = ctypes.c_void_p()
+        dev = self.flat.device
+        rc = L.fw_comm_create(self.flat.numel(), world, rank, dev.index if dev.index is not None else 0, ctypes.byref(h))
+        mine = ctypes.create_string_buffer(64)
+        if rc == 0:
+            rc = L.fw_comm_export(h, mine)
+        # every rank must take the same branch: exchange (status, handle) and agree
+        payload = torch.tensor([1 if rc == 0 else 0] + list(mine.raw), dtype=torch.uint8, device=dev)
+        gathered = [torch.empty_like(payload) for _ in range(world)]
+        dist.all_gather(gathered, payload)
+        ok = all(int(g[0]) == 1 for g in gathered)
+        if ok:
+            blob = b"".join(bytes(g[1:].cpu().tolist()) for g in gathered)
+            rc = L.fw_comm_connect(h, ctypes.c_char_p(blob))
+            flag = torch.tensor([1 if rc == 0 else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            ok = int(flag.item()) == 1
+        if not ok:
+            if h:
+                L.fw_comm_destroy(h)
+            return False
+        self._comm = h
+        return True
+
+    def comm_error(self):
+        """True when a peer failed to arrive inside fw_comm_allreduce_adam (checked by the trainer once per iteration)."""
+        from . import _lib
+        return bool(getattr(self, "_comm", None)) and _lib.lib().fw_comm_error(self._comm) == 1
+
     def step(self):
         import ctypes
         from . import _lib
         ptr = lambda t: ctypes.c_void_p(t.data_ptr())
+        if getattr(self, "_comm", None):
+            _lib.check(_lib.lib().fw_comm_allreduce_adam(self._comm, ptr(self.flat), ptr(self.grad), ptr(self.exp_avg),
+                                                         ptr(self.exp_avg_sq), ptr(self.step_count), self.flat.numel(),
+                                                         self.lr, self.betas[0], self.betas[1], self.eps, self.max_grad_norm,
+                                                         ctypes.c_void_p(torch.cuda.current_stream(self.flat.device).cuda_stream)),
+                       "fw_comm_allreduce_adam")
+            return
         _lib.check(_lib.lib().fw_adam_clip_step(ptr(self.flat), ptr(self.grad), ptr(self.exp_avg), ptr(self.exp_avg_sq),
                                                 ptr(self.step_count), self.flat.numel(), self.lr, self.betas[0],
                                                 self.betas[1], self.eps, self.max_grad_norm, ctypes.c_void_p(
@@ -237,6 +283,10 @@ class PPO:
         else:
             self.optimizer = torch.optim.Adam(self.policy.parameters(), lr=learning_rate, eps=1e-5,
                                               capturable=self.use_cuda_graph)
+        # data parallel on one node: fuse the gradient all-reduce into the optimiser kernel over NVLink peer memory
+        self.peer_allreduce = False
+        if self.flat_optimizer and self.world > 1 and os.environ.get("FWB200_PPO_PEER_ALLREDUCE", "1") != "0":
+            self.peer_allreduce = self.optimizer.enable_peer_allreduce(dist)
         self._rollout_graph = None
         self._train_graph = None
         self._eager_rollouts = 0
@@ -386,10 +436,10 @@ class PPO:
         self.optimizer.zero_grad(set_to_none=False)
         loss.backward()
         if self.flat_optimizer:
-            if self.dist is not None and self.world > 1:       # the gradient already is one flat buffer
-                self.dist.all_reduce(self.optimizer.grad)
+            if self.dist is not None and self.world > 1 and not self.peer_allreduce:
+                self.dist.all_reduce(self.optimizer.grad)      # the gradient already is one flat buffer
                 self.optimizer.grad.div_(self.world)
-            self.optimizer.step()                              # clip_grad_norm_ + Adam in one launch
+            self.optimizer.step()                              # (peer all-reduce +) clip_grad_norm_ + Adam in one launch
             return policy_loss.detach(), value_loss.detach()
         if self.dist is not None and self.world > 1:
             allreduce_gradients(self._params, self.dist, self.world)
