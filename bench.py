@@ -183,13 +183,28 @@ def python_reference_worker(budget_s):
         venv.step(rs.uniform(-1, 1, (C, 3)))
     k = 0
     t0 = time.perf_counter()
-    while time.perf_counter() - t0 < 0.6 * budget_s or k < 20:
+    while time.perf_counter() - t0 < 0.45 * budget_s or k < 20:
         venv.step(rs.uniform(-1, 1, (C, 3)))
         k += 1
     dt = time.perf_counter() - t0
+    # the fork's PPO on the same SubprocVecEnv (BASELINE.md §3 "PPO CPU baseline"), bounded: 2 rollouts of 128 steps per
+    # worker instead of SB3's 2048 (the rate is env-bound: 97 % of the wall-clock is env.step), default batch 64, 10 epochs
+    ppo_rate, ppo_note = None, None
+    try:
+        import torch
+        from stable_baselines3 import PPO
+        torch.set_num_threads(max(1, C // 2))
+        n_steps = 128
+        model = PPO("MlpPolicy", venv, n_steps=n_steps, batch_size=64, n_epochs=10, device="cpu", verbose=0)
+        t1 = time.perf_counter()
+        model.learn(total_timesteps=2 * n_steps * C)
+        ppo_rate = model.num_timesteps / (time.perf_counter() - t1)
+        ppo_note = "PPO('MlpPolicy', SubprocVecEnv x %d, n_steps=%d, batch_size=64, n_epochs=10, device=cpu).learn(%d steps)" % (C, n_steps, model.num_timesteps)
+    except Exception as e:                                   # reported, never fatal for the env figure
+        ppo_note = "fork PPO baseline failed: %r" % (e,)
     venv.close()
     print(json.dumps({"value": C * k / dt, "unit": UNIT, "cores": C, "workers": C, "kind": "reference",
-                      "single_env_value": single,
+                      "single_env_value": single, "ppo_train_value": ppo_rate, "ppo_train_sample": ppo_note,
                       "sample": "SubprocVecEnv(start_method=fork) of %d x FixedWingAircraft(fixed_wing_config.json), turbulence "
                                 "light, U(-1,1)^3 actions, %d timed vec steps (%.1f s); single env: %d steps" % (C, k, dt, n1)}))
 
