@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define FW_ABI_VERSION 8
+#define FW_ABI_VERSION 9
 
 #define FW_NY 19        /* ODE state: quat[4] omega[3] pos[3] vel[3] act_value[3] act_rate[3]  (pyfly.py:1372-1389) */
 #define FW_NOBS 14      /* default observation vector (fixed_wing_config.json "observation.states")               */
@@ -37,6 +37,7 @@ extern "C" {
 #define FW_OBS_LEN_MAX 5       /* observation.length (rows of history)                                            */
 #define FW_NOBS_MAX (FW_OBS_ENTRIES_MAX * FW_OBS_LEN_MAX)
 #define FW_REW_FACTORS_MAX 12
+#define FW_NPARAM 48    /* aircraft parameters mass .. C_n_delta_r of FwConfig, in that order                             */
 #define FW_NACT 3       /* elevator, aileron, throttle (fixed_wing_config.json "action.states")                   */
 #define FW_NSTATE_INJECT 21 /* roll pitch yaw p q r pn pe pd u v w | er el thr | er_dot el_dot thr_dot | wind n e d */
 #define FW_NMETRIC 28   /* see FwMetricIndex                                                                      */
@@ -214,6 +215,18 @@ typedef struct FwConfig {
     /* ---- counter-based RNG (Philox4x32-10) for auto-reset and turbulence noise ---- */
     uint64_t seed;
     int64_t env_id_offset;                /* global id of env 0 of this handle (sharding: rank*n_envs) */
+
+    /* ---- per-episode aircraft-parameter randomisation: the gym config's "simulator.model" block
+     * (FixedWingAircraft.sample_simulator_parameters, fixed_wing.py:748-813).  Index i = position in the aircraft
+     * parameter block above (mass = 0 ... C_n_delta_r = 47).  At every reset an enabled parameter whose original value
+     * is not 0 is re-drawn around par_orig[i]: N(orig, par_var[i]) clipped to [orig - par_clip[i], orig + par_clip[i]]
+     * (NaN = no clip; min > max collapses to the max like np.clip), or U(orig - var, orig + var).  par_var / par_clip
+     * arrive already scaled for var_type "relative" (var * |orig|, clip * orig — sign kept, as the reference does).
+     * Jx, Jy, Jz, Jxz and the aspect ratio stay at their construction-time values inside the dynamics (pyfly computes
+     * the inertia terms once, pyfly.py:1086-1119).  model_on selects kernels that read per-env parameters. ---- */
+    int32_t model_on, model_uniform;
+    int32_t par_enabled[FW_NPARAM];
+    double par_orig[FW_NPARAM], par_var[FW_NPARAM], par_clip[FW_NPARAM];
 } FwConfig;
 
 typedef struct FwHandle FwHandle;
@@ -330,7 +343,8 @@ enum FwField {
     FW_FIELD_TURB = 6,       /* [n,6]  turbulence sample used by the NEXT step (lin3, ang3)   */
     FW_FIELD_COUNTERS = 7,   /* [n,4]  int32: steps_count, steps_for_target, sim_step, episode*/
     FW_FIELD_NFEV = 8,       /* [n,2]  int32: RHS evaluations, RK attempts of the last step   */
-    FW_FIELD_COUNT = 9
+    FW_FIELD_PARAMS = 9,     /* [n,FW_NPARAM] f64 aircraft parameters of the running episode (model_on handles only) */
+    FW_FIELD_COUNT = 10
 };
 int fw_get_field(FwHandle* h, int32_t field, void* out_dev, void* stream);
 int fw_set_field(FwHandle* h, int32_t field, const void* in_dev, void* stream);

@@ -79,6 +79,7 @@ typedef struct FwoEnv {
     int last_nfev, last_natt;
     uint64_t episode;
     uint64_t ep_seed;      /* Philox key of the running episode: cfg.seed when it was reset (fwo_set_config) */
+    double Jy0;            /* self.I[1, 1], fixed at construction (pyfly.py:1086-1096): parameter randomisation never reaches it */
     int64_t env_id;
 } FwoEnv;
 
@@ -99,7 +100,7 @@ void fwo_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4
 /* Stream layout shared with the CUDA path (DESIGN.md "RNG"): counter = (env_id lo32, episode lo32, purpose|env hi,
  * block); two 53-bit uniforms per block. */
 enum { FWO_RNG_RESET = 0, FWO_RNG_NOISE = 1, FWO_RNG_RESAMPLE = 2, FWO_RNG_ACTION = 3, FWO_RNG_OBS = 4,
-       FWO_RNG_OBS_INIT = 5 };
+       FWO_RNG_OBS_INIT = 5, FWO_RNG_MODEL = 6 };
 
 static void rng_block(uint64_t seed, int64_t env_id, uint64_t episode, uint32_t purpose, uint32_t block,
                       uint32_t out[4]) {
@@ -294,7 +295,7 @@ static int dynamics(FwoEnv* e, int t_positive, const double* y, double* dy) {
     /* ---- _f_omega_dot (pyfly.py:1659-1683) ---- */
     const double* g = e->gam;
     dy[4] = g[1] * P * Q - g[2] * Q * Rr + g[3] * tau[0] + g[4] * tau[2];
-    dy[5] = g[5] * P * Rr - g[6] * (P * P - Rr * Rr) + tau[1] / c->Jy;
+    dy[5] = g[5] * P * Rr - g[6] * (P * P - Rr * Rr) + tau[1] / e->Jy0;
     dy[6] = g[7] * P * Q - g[1] * Q * Rr + g[4] * tau[0] + g[8] * tau[2];
     /* ---- _f_p_dot (pyfly.py:1706-1737) ---- */
     double T[3][3] = {
@@ -979,6 +980,7 @@ FwoEnv* fwo_create(const FwConfig* cfg, int64_t env_id) {
     FwoEnv* e = (FwoEnv*)calloc(1, sizeof(FwoEnv));
     e->cfg = *cfg;
     gammas(e);
+    e->Jy0 = e->cfg.Jy;
     int L = cfg->steps_max + 2;
     e->turb_len = cfg->steps_max > 0 ? cfg->steps_max : 1;
     e->turb = (double*)calloc((size_t)6 * e->turb_len, sizeof(double));
@@ -998,6 +1000,41 @@ void fwo_destroy(FwoEnv* e) {
     free(e->turb); free(e->act_hist); free(e->cmd_hist); free(e->err_hist); free(e->goal_hist);
     free(e->st_hist); free(e->tgt_hist); free(e);
 }
+
+/* sample_simulator_parameters, the "model" block (fixed_wing.py:758-800): every enabled aircraft parameter whose
+ * original value is not 0 is re-drawn around the original at every reset.  The parameters are the 48 doubles of
+ * FwConfig from `mass` on (this env's private copy of the config is what dynamics() reads; pyfly's _forces reads
+ * self.params on every call).  Draw i of the episode: Philox block i of purpose MODEL — two uniforms, Box-Muller cosine
+ * branch for the gaussian, the first uniform for the uniform distribution. */
+static void sample_model_params(FwoEnv* e) {
+    FwConfig* c = &e->cfg;
+    if (!c->model_on) return;
+    double* par = &c->mass;
+    for (int i = 0; i < FW_NPARAM; ++i) {
+        if (!c->par_enabled[i]) continue;
+        const double orig = c->par_orig[i];
+        if (orig == 0) continue;
+        uint32_t r[4];
+        rng_block(e->ep_seed, e->env_id, e->episode, FWO_RNG_MODEL, (uint32_t)i, r);
+        const double u1 = u53(r[0], r[1]), u2 = u53(r[2], r[3]);
+        double v;
+        if (c->model_uniform) {
+            const double lo = orig - c->par_var[i], hi = orig + c->par_var[i];
+            v = lo + (hi - lo) * u1;
+        } else {
+            const double z = sqrt(-2.0 * log(1.0 - u1)) * cos(6.283185307179586476925 * u2);
+            v = orig + c->par_var[i] * z;
+            if (!isnan(c->par_clip[i])) {       /* np.clip(v, orig - clip, orig + clip) = minimum(maximum(v, lo), hi) */
+                const double lo = orig - c->par_clip[i], hi = orig + c->par_clip[i];
+                v = fmin(fmax(v, lo), hi);
+            }
+        }
+        par[i] = v;
+    }
+}
+/* the aircraft parameters of the running episode (tests: inject the reference's draws / read ours back) */
+void fwo_set_params(FwoEnv* e, const double* par48) { memcpy(&e->cfg.mass, par48, sizeof(double) * FW_NPARAM); }
+void fwo_get_params(const FwoEnv* e, double* par48) { memcpy(par48, &e->cfg.mass, sizeof(double) * FW_NPARAM); }
 
 /* turbulence for the whole episode (pyfly.py:870-871 -> dryden.simulate) */
 static void gen_turbulence(FwoEnv* e, const double* noise, int noise_len) {
@@ -1160,6 +1197,7 @@ void fwo_reset(FwoEnv* e, const double* state, const double* target, const doubl
     for (int k = 0; k < 3; ++k) { e->prev_shaping[k] = 0; e->has_prev_shaping[k] = 0; }
     push_state_history(e);          /* Variable.reset: history = [value] (pyfly.py:89-104) */
     e->ep_return = 0; e->term_code = 0;
+    sample_model_params(e);         /* fixed_wing.py:437: after simulator.reset, before sample_target */
     /* sample_target, then injected targets override (fixed_wing.py:443-450) */
     double u12[12];
     target_draws(e, FWO_RNG_RESET, 8, u12);          /* blocks 8..13 of the reset stream (0..7: state and wind) */
@@ -1319,7 +1357,12 @@ FwoEnv* fwo_batch_env(FwoBatch* b, int i) { return b->envs[i]; }
 
 /* set_curriculum_level / seed on a live env (fixed_wing.py:324-412): the new ranges and seed serve every later reset
  * and target resampling; the running episode keeps its state, turbulence table and Philox key (ep_seed). */
-void fwo_set_config(FwoEnv* e, const FwConfig* cfg) { e->cfg = *cfg; }
+void fwo_set_config(FwoEnv* e, const FwConfig* cfg) {
+    double par[FW_NPARAM];
+    memcpy(par, &e->cfg.mass, sizeof(par));      /* the running episode keeps its aircraft parameters */
+    e->cfg = *cfg;
+    if (cfg->model_on) memcpy(&e->cfg.mass, par, sizeof(par));
+}
 void fwo_batch_set_config(FwoBatch* b, const FwConfig* cfg) {
     for (int i = 0; i < b->n; ++i) fwo_set_config(b->envs[i], cfg);
 }

@@ -55,6 +55,8 @@ def lib():
         L.fwo_batch_destroy.argtypes = [ctypes.c_void_p]
         L.fwo_batch_set_config.argtypes = [ctypes.c_void_p, ctypes.POINTER(FwConfig)]
         L.fwo_set_config.argtypes = [ctypes.c_void_p, ctypes.POINTER(FwConfig)]
+        L.fwo_set_params.argtypes = [ctypes.c_void_p, _dp]
+        L.fwo_get_params.argtypes = [ctypes.c_void_p, _dp]
         L.fwo_batch_env.restype = ctypes.c_void_p
         L.fwo_batch_env.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.fwo_batch_reset.argtypes = [ctypes.c_void_p, _dp]
@@ -117,6 +119,15 @@ class OracleEnv:
         return dict(y=y, euler=eu, vab=vab, cmd=cmd, target=tgt, wind=wind, steps_count=int(cnt[0]),
                     steps_for_target=int(cnt[1]), sim_step=int(cnt[2]), episode=int(cnt[3]), nfev=int(cnt[4]),
                     natt=int(cnt[5]))
+
+    def set_params(self, par48):
+        """Aircraft parameters (mass .. C_n_delta_r, FwConfig order) of the running episode."""
+        lib().fwo_set_params(self._h, _p(np.ascontiguousarray(par48, dtype=np.float64)))
+
+    def params(self):
+        out = np.zeros(48)
+        lib().fwo_get_params(self._h, _p(out))
+        return out
 
     def metrics(self):
         m = np.zeros(FW_NMETRIC)
@@ -211,6 +222,12 @@ class OracleBatch:
         a = np.ascontiguousarray(actions, dtype=np.float32)
         lib().fwo_batch_step(self._h, _p(a, _fp), _p(self.obs), _p(self.rew), _p(self.done, _u8p))
         return self.obs, self.rew, self.done
+
+    def params(self):
+        out = np.zeros((self.n, 48))
+        for i in range(self.n):
+            lib().fwo_get_params(lib().fwo_batch_env(self._h, i), _p(out[i]))
+        return out
 
     def counters(self):
         nfev, natt = np.zeros(self.n, np.int32), np.zeros(self.n, np.int32)

@@ -153,3 +153,19 @@ def moving_targets_env_config():
     cfg["target"]["states"] = MOVING_TARGETS
     cfg["steps_max"] = 150
     return cfg
+
+
+MODEL_BLOCK = {"var_type": "relative", "var": 0.1, "clip": 0.15, "distribution": "gaussian",
+               "parameters": [{"name": "C_L_alpha"}, {"name": "C_m_q"}, {"name": "mass", "var": 0.05}, {"name": "C_D_p"},
+                              {"name": "k_motor"}, {"name": "C_l_p"}, {"name": "C_n_r", "clip": 0.05}, {"name": "C_Y_beta"},
+                              {"name": "S_prop"}, {"name": "b"}, {"name": "c"}, {"name": "M", "var": 0.02}, {"name": "e"},
+                              {"name": "Jx"}, {"name": "C_L_0"}, {"name": "C_D_q"}]}
+
+
+def model_env_config(distribution="gaussian"):
+    """The default gym config plus the simulator.model block the fixtures traj_model_*.npz were recorded with
+    (tests/golden/make_golden.py gen_model)."""
+    from tum_adlr_deep_reinforcement_learning_b200.config import default_env_config
+    cfg = default_env_config()
+    cfg["simulator"]["model"] = dict(MODEL_BLOCK, distribution=distribution)
+    return cfg

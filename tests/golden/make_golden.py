@@ -103,7 +103,7 @@ def scenario_arrays(st, tgt):
 
 
 def run_episodes(env, n_ep, n_steps, rs, turbulence, wind_mag, action_amp, hard=False, noise_len=None,
-                 metrics=False, f32_actions=False):
+                 metrics=False, f32_actions=False, after_reset=None):
     """Roll `n_ep` injected episodes; every record has a leading [episode, step] shape."""
     rec = {k: [] for k in ("init_state", "init_target", "actions", "y", "euler", "vab", "cmd", "target", "obs",
                            "reward", "done", "nfev", "term", "obs0", "y0", "euler0", "vab0", "n_valid")}
@@ -118,6 +118,8 @@ def run_episodes(env, n_ep, n_steps, rs, turbulence, wind_mag, action_amp, hard=
             noise = rs.standard_normal((4, L))
             kw["turbulence_noise"] = noise
         obs0 = env.reset(state=dict(st), target=dict(tgt), **kw)
+        if after_reset is not None:
+            rec.setdefault("params", []).append(after_reset(env))
         s_arr, t_arr = scenario_arrays(st, tgt)
         rec["init_state"].append(s_arr)
         rec["init_target"].append(t_arr)
@@ -215,6 +217,57 @@ def gen_turb_moderate():
     rs = np.random.RandomState(2468)
     out = run_episodes(env, 2, 160, rs, True, wind_mag=5.0, action_amp=1.1)
     np.savez_compressed(os.path.join(HERE, "traj_turb_moderate.npz"), **out)
+
+
+MODEL_BLOCK = {"var_type": "relative", "var": 0.1, "clip": 0.15, "distribution": "gaussian",
+               "parameters": [{"name": "C_L_alpha"}, {"name": "C_m_q"}, {"name": "mass", "var": 0.05}, {"name": "C_D_p"},
+                              {"name": "k_motor"}, {"name": "C_l_p"}, {"name": "C_n_r", "clip": 0.05}, {"name": "C_Y_beta"},
+                              {"name": "S_prop"}, {"name": "b"}, {"name": "c"}, {"name": "M", "var": 0.02}, {"name": "e"},
+                              {"name": "Jx"}, {"name": "C_L_0"}, {"name": "C_D_q"}]}
+AERO_NAMES = ("mass Jx Jy Jz Jxz S_wing b c S_prop C_prop k_motor k_T_P k_Omega e M a_0 "
+              "C_L_0 C_L_alpha C_L_q C_L_delta_e C_D_p C_D_q C_D_beta1 C_D_beta2 C_D_delta_e "
+              "C_m_0 C_m_alpha C_m_q C_m_delta_e C_m_fp C_Y_0 C_Y_beta C_Y_p C_Y_r C_Y_delta_a C_Y_delta_r "
+              "C_l_0 C_l_beta C_l_p C_l_r C_l_delta_a C_l_delta_r C_n_0 C_n_beta C_n_p C_n_r C_n_delta_a C_n_delta_r").split()
+
+
+class CyclingDraws:
+    """Stand-in for the env-level RandomState while sample_simulator_parameters runs: normal(loc, scale) walks a fixed
+    list of standard-normal values (one of them far enough out to hit the clip), uniform() a fixed list of fractions."""
+    Z = (0.7, -1.3, 2.5, -0.2, 1.1, -2.2, 0.05, 1.9)
+    U = (0.625, 0.1, 0.9, 0.4)
+
+    def __init__(self):
+        self.kz = self.ku = 0
+
+    def normal(self, loc=0.0, scale=1.0):
+        z = self.Z[self.kz % len(self.Z)]
+        self.kz += 1
+        return loc + scale * z
+
+    def uniform(self, low=0.0, high=1.0):
+        u = self.U[self.ku % len(self.U)]
+        self.ku += 1
+        return low + u * (high - low)
+
+
+def gen_model():
+    """Per-episode aircraft-parameter randomisation (the gym config's simulator.model block,
+    FixedWingAircraft.sample_simulator_parameters fixed_wing.py:748-813): the parameters the reference draws at every
+    reset (env RNG replaced by fixed draws) and the trajectories flown with them; gaussian with clip, then uniform."""
+    import tempfile
+    cfg = json.load(open(refshim.GYM_CONFIG))
+    for dist in ("gaussian", "uniform"):
+        cfg["simulator"]["model"] = dict(MODEL_BLOCK, distribution=dist)
+        with tempfile.NamedTemporaryFile("w", suffix=".json", delete=False) as f:
+            json.dump(cfg, f)
+        env = make_env(True, config_path=f.name)
+        env.np_random = CyclingDraws()
+        rs = np.random.RandomState(515 + len(dist))
+        out = run_episodes(env, 3, 150, rs, True, wind_mag=4.0, action_amp=1.1,
+                           after_reset=lambda e: np.array([e.simulator.params[k] for k in AERO_NAMES], dtype=np.float64))
+        os.unlink(f.name)
+        np.savez_compressed(os.path.join(HERE, "traj_model_%s.npz" % dist), **out)
+        print(dist, "C_L_alpha", out["params"][:, AERO_NAMES.index("C_L_alpha")], "C_n_r", out["params"][:, AERO_NAMES.index("C_n_r")])
 
 
 def gen_fail():
@@ -856,7 +909,7 @@ def gen_dryden():
 
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
-    jobs = {"waypoint": gen_waypoint, "targets": gen_targets, "resample": gen_resample, "reward": gen_reward, "cnn": gen_cnn, "params": gen_params, "traj": gen_traj, "turb": gen_turb, "turb_moderate": gen_turb_moderate, "fail": gen_fail, "full": gen_full,
+    jobs = {"waypoint": gen_waypoint, "targets": gen_targets, "resample": gen_resample, "reward": gen_reward, "cnn": gen_cnn, "params": gen_params, "traj": gen_traj, "turb": gen_turb, "turb_moderate": gen_turb_moderate, "model": gen_model, "fail": gen_fail, "full": gen_full,
             "pid": gen_pid, "gae": gen_gae, "vecnorm": gen_vecnorm, "ppo_update": gen_ppo_update, "sac_update": gen_sac_update, "curriculum": gen_curriculum, "dryden": gen_dryden}
     for name, fn in jobs.items():
         if what in (name, "all"):

@@ -144,13 +144,14 @@ def test_spaces_match_the_reference():
     assert np.array_equal(g["default_act_high"], np.full(3, f32max, np.float32))
 
 
-def test_simulator_randomisation_blocks_are_refused():
-    """sample_simulator_parameters (fixed_wing.py:748-813): a `simulator.model` block (aircraft-parameter
-    randomisation) or any simulator key other than `states` must raise, not be dropped silently."""
+def test_simulator_randomisation_blocks():
+    """sample_simulator_parameters (fixed_wing.py:748-813): a `simulator.model` block (aircraft-parameter randomisation)
+    is flattened into FwConfig; any other simulator key than `states` / `model` must raise, not be dropped silently."""
     env = C.default_env_config()
-    env["simulator"]["model"] = {"var_type": "relative", "var": 0.1, "parameters": [{"name": "C_L_alpha"}]}
-    with pytest.raises(NotImplementedError):
-        C.build_config(env_cfg=env)
+    env["simulator"]["model"] = {"var_type": "relative", "var": 0.1, "parameters": [{"name": "C_L_alpha"}, {"name": "C_m_q", "clip": 0.05}]}
+    c = C.build_config(env_cfg=env)                    # aircraft-parameter randomisation is supported (model_on handles)
+    assert c.model_on == 1 and c.par_enabled[17] == 1 and np.isclose(c.par_var[17], 0.1 * c.C_L_alpha) and np.isnan(c.par_clip[17])
+    assert np.isclose(c.par_clip[27], 0.05 * c.C_m_q) and c.par_clip[27] < 0           # sic: relative clip keeps the sign
     env = C.default_env_config()
     env["simulator"]["turbulence_intensity"] = {"values": ["light", "severe"]}
     with pytest.raises(NotImplementedError):

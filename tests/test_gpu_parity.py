@@ -361,3 +361,68 @@ def test_full_size_batch_properties(cuda_device):
         sums.append(float(acc))
         big.close()
     assert sums[0] == sums[1]
+
+
+@pytest.mark.parametrize("dist", ["gaussian", "uniform"])
+def test_aircraft_parameter_randomisation(dist, cuda_device):
+    """simulator.model (FixedWingAircraft.sample_simulator_parameters, fixed_wing.py:748-813) on the CUDA path:
+    (a) with the parameters the LIVE reference drew at each reset injected (FW_FIELD_PARAMS), the reference's
+        trajectories are reproduced with identical RK45 decisions (tests/golden/traj_model_*.npz);
+    (b) the device's own Philox draws equal the oracle's, parameter for parameter, through auto-resets, and the two then
+        fly the same trajectories; a handle without the block refuses FW_FIELD_PARAMS."""
+    import torch
+    from conftest import model_env_config
+    from oracle import fw_oracle as O
+    from tum_adlr_deep_reinforcement_learning_b200 import batched as bt
+    from tum_adlr_deep_reinforcement_learning_b200._lib import FwError
+    from tum_adlr_deep_reinforcement_learning_b200.config import build_config
+    g = load_golden("traj_model_" + dist)
+    E, T = g["actions"].shape[:2]
+    cfg = build_config(env_cfg=model_env_config(dist), sim_config_kw={"turbulence": True})
+    env = bt.BatchedFixedWing(E, cfg=cfg)
+    env.enable_f64_outputs()
+    env.reset(state=g["init_state"], target=g["init_target"], noise=g["noise"])
+    assert np.abs(env.obs64.cpu().numpy() - g["obs0"]).max() < 1e-12
+    env.set_field(bt.FIELD_PARAMS, g["params"])
+    assert np.array_equal(env.get_field(bt.FIELD_PARAMS).cpu().numpy(), g["params"])
+    alive = np.ones(E, bool)
+    for t in range(T):
+        env.step(torch.as_tensor(g["actions"][:, t]).cuda().contiguous(), auto_reset=False)
+        y, obs = env.get_field(bt.FIELD_Y).cpu().numpy(), env.obs64.cpu().numpy()
+        nf = env.get_field(bt.FIELD_NFEV).cpu().numpy()[:, 0]
+        for ep in np.flatnonzero(alive):
+            if t >= int(g["n_valid"][ep]):
+                alive[ep] = False
+                continue
+            assert nf[ep] == int(g["nfev"][ep, t]), (ep, t)
+            assert (np.abs(y[ep] - g["y"][ep, t]) / np.maximum(1, np.abs(g["y"][ep, t]))).max() < 1e-9, (ep, t)
+            assert (np.abs(obs[ep] - g["obs"][ep, t]) / np.maximum(1, np.abs(g["obs"][ep, t]))).max() < 1e-9, (ep, t)
+    env.close()
+    # (b) own sampling against the oracle, across episode ends
+    n = 512
+    cfg2 = build_config(env_cfg=model_env_config(dist), sim_config_kw={"turbulence": True}, config_kw={"steps_max": 12}, seed=21)
+    env = bt.BatchedFixedWing(n, cfg=cfg2)
+    env.enable_f64_outputs()
+    env.reset()
+    ob = O.OracleBatch(cfg2, n)
+    ob.reset()
+    rs = np.random.RandomState(3)
+    for t in range(30):
+        pr = ob.params()
+        assert (np.abs(env.get_field(bt.FIELD_PARAMS).cpu().numpy() - pr) / np.maximum(1e-30, np.abs(pr))).max() < 1e-12, t
+        a = rs.uniform(-1, 1, (n, 3)).astype(np.float32)
+        env.step(torch.as_tensor(a).cuda())
+        o_ref, r_ref, d_ref = ob.step(a)
+        assert np.array_equal(env.done.cpu().numpy(), d_ref), t
+        assert (np.abs(env.obs64.cpu().numpy() - o_ref) / np.maximum(1.0, np.abs(o_ref))).max() < 1e-9, t
+    first = ob.params()
+    assert len(np.unique(first[:, 17])) > 0.8 * n                      # C_L_alpha: every env its own draw
+    blob = env.get_state()
+    twin = bt.BatchedFixedWing(n, cfg=cfg2)
+    twin.set_state(blob)
+    assert torch.equal(twin.get_field(bt.FIELD_PARAMS), env.get_field(bt.FIELD_PARAMS))     # the blob carries them
+    env.close(); twin.close()
+    plain = bt.BatchedFixedWing(4, cfg=build_config())
+    with pytest.raises(FwError):
+        plain.get_field(bt.FIELD_PARAMS)
+    plain.close()

@@ -51,6 +51,46 @@ def test_oracle_reproduces_live_reference_trajectories(name, cfg_kw, sim_kw, f32
             assert ln == int(g["n_valid"][ep])
 
 
+@pytest.mark.parametrize("dist", ["gaussian", "uniform"])
+def test_oracle_aircraft_parameter_randomisation(dist):
+    """simulator.model (fixed_wing.py:748-813): with the parameters the live reference drew at every reset injected, the
+    oracle flies the reference's trajectories (identical RK45 decisions); its own Philox draws follow the configured
+    distribution: unlisted parameters and parameters whose original is 0 stay put, the clip holds (a negative original
+    turns the relative clip inside out and pins the value at orig + clip, as np.clip does), Jx changes nothing."""
+    from conftest import model_env_config
+    g = load_golden("traj_model_" + dist)
+    cfg = build_config(env_cfg=model_env_config(dist), sim_config_kw={"turbulence": True})
+    assert cfg.model_on == 1 and cfg.model_uniform == int(dist == "uniform")
+    for ep in range(g["actions"].shape[0]):
+        env = O.OracleEnv(cfg)
+        obs = env.reset(g["init_state"][ep], g["init_target"][ep], g["noise"][ep])
+        assert np.abs(obs - g["obs0"][ep]).max() < 1e-12
+        own = env.params()
+        env.set_params(g["params"][ep])
+        for t in range(int(g["n_valid"][ep])):
+            obs, rew, done, term = env.step(g["actions"][ep, t])
+            s = env.get()
+            assert done == bool(g["done"][ep, t]) and s["nfev"] == int(g["nfev"][ep, t]), (ep, t)
+            assert _rel(s["y"], g["y"][ep, t]).max() < 1e-9 and _rel(obs, g["obs"][ep, t]).max() < 1e-9, (ep, t)
+        nominal = np.array([cfg.par_orig[i] for i in range(48)])
+        on = np.array([bool(cfg.par_enabled[i]) for i in range(48)])
+        assert np.array_equal(own[~on], nominal[~on])
+        assert own[21] == nominal[21] == 0.0                       # C_D_q: listed, original 0 -> never drawn
+        assert abs(own[45] - (nominal[45] + 0.05 * nominal[45])) < 1e-15 or dist == "uniform"    # C_n_r pinned by the clip
+    # distribution of the oracle's own draws
+    batch = O.OracleBatch(cfg, 4000)
+    batch.reset()
+    P_ = batch.params()
+    i = 17                                                             # C_L_alpha: var 0.1 |orig|, clip 0.15 orig
+    o = cfg.par_orig[i]
+    if dist == "gaussian":
+        assert abs(P_[:, i].mean() - o) < 0.01 * o and P_[:, i].min() >= o * 0.85 - 1e-12 and P_[:, i].max() <= o * 1.15 + 1e-12
+        assert 0.08 * o < P_[:, i].std() < 0.1 * o                     # N(o, 0.1 o) clipped at 1.5 sigma
+    else:
+        assert abs(P_[:, i].mean() - o) < 0.01 * o and abs(P_[:, i].std() - 0.2 * o / np.sqrt(12)) < 0.005 * o
+        assert P_[:, i].min() >= 0.9 * o and P_[:, i].max() <= 1.1 * o
+
+
 def test_dryden_matches_reference_for_all_intensities():
     g = load_golden("dryden")
     for L in (2000, 300):

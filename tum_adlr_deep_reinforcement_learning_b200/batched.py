@@ -10,10 +10,11 @@ import torch
 from . import _lib
 from .config import (FW_NMETRIC, FW_NOBS, FW_NSTATE_INJECT, FW_NY, build_config)
 
-FIELD_Y, FIELD_EULER, FIELD_VAB, FIELD_WIND, FIELD_TARGET, FIELD_CMD, FIELD_TURB, FIELD_COUNTERS, FIELD_NFEV = range(9)
+FIELD_Y, FIELD_EULER, FIELD_VAB, FIELD_WIND, FIELD_TARGET, FIELD_CMD, FIELD_TURB, FIELD_COUNTERS, FIELD_NFEV, FIELD_PARAMS = range(10)
 _FIELD_SHAPE = {FIELD_Y: (FW_NY, torch.float64), FIELD_EULER: (3, torch.float64), FIELD_VAB: (3, torch.float64),
                 FIELD_WIND: (3, torch.float64), FIELD_TARGET: (3, torch.float64), FIELD_CMD: (3, torch.float64),
-                FIELD_TURB: (6, torch.float64), FIELD_COUNTERS: (4, torch.int32), FIELD_NFEV: (2, torch.int32)}
+                FIELD_TURB: (6, torch.float64), FIELD_COUNTERS: (4, torch.int32), FIELD_NFEV: (2, torch.int32),
+                FIELD_PARAMS: (48, torch.float64)}
 
 
 def _ptr(t):

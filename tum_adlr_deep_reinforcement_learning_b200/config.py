@@ -20,7 +20,7 @@ import numpy as np
 
 _DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
 
-FW_ABI_VERSION = 8
+FW_ABI_VERSION = 9
 FW_NY, FW_NOBS, FW_NACT, FW_NSTATE_INJECT, FW_NMETRIC = 19, 14, 3, 21, 28
 FW_F64, FW_F32 = 0, 1
 FW_INT_RK45_SCIPY, FW_INT_RK4_FIXED = 0, 1
@@ -81,7 +81,9 @@ class FwConfig(ctypes.Structure):
            ("obs_kind", _i * 16), ("obs_idx", _i * 16), ("obs_window", _i * 16), ("obs_norm_flag", _i * 16),
            ("obs_mean", _d * 16), ("obs_var", _d * 16), ("obs_init_noise", _d),
            ("env_kind", _i), ("turb_block_len", _i), ("wp_goal_bound", _d * 3), ("wp_rew_range", _d * 3),
-           ("seed", ctypes.c_uint64), ("env_id_offset", ctypes.c_int64)])
+           ("seed", ctypes.c_uint64), ("env_id_offset", ctypes.c_int64),
+           ("model_on", _i), ("model_uniform", _i), ("par_enabled", _i * 48), ("par_orig", _d * 48), ("par_var", _d * 48),
+           ("par_clip", _d * 48)])
 
 
 def _var(name, **kw):
@@ -317,12 +319,12 @@ def build_config(env_cfg=None, sim_cfg=None, config_kw=None, sim_config_kw=None,
     env, sim = resolve_configs(env_cfg, sim_cfg, config_kw, sim_config_kw, env_kind)
     waypoint = env_kind == "waypoint"
     for key in env.get("simulator", {}):
-        # sample_simulator_parameters (fixed_wing.py:748-813) re-draws aircraft parameters ("model") or simulator
-        # attributes (any other key) at every reset; that is not implemented: refuse it instead of silently flying the
-        # nominal airframe
-        if key != "states":
-            raise NotImplementedError("simulator.%s: per-episode simulator / aircraft-parameter randomisation "
-                                      "(fixed_wing.py:748-813)" % key)
+        # sample_simulator_parameters (fixed_wing.py:748-813) re-draws aircraft parameters ("model", supported below) or
+        # simulator attributes (any other key, e.g. a list of turbulence intensities) at every reset; the latter is not
+        # implemented: refuse it instead of silently ignoring it
+        if key not in ("states", "model"):
+            raise NotImplementedError("simulator.%s: per-episode randomisation of simulator attributes "
+                                      "(fixed_wing.py:801-813)" % key)
     P = load_aircraft_parameters() if params is None else dict(params)
 
     c = FwConfig()
@@ -602,6 +604,35 @@ def build_config(env_cfg=None, sim_cfg=None, config_kw=None, sim_config_kw=None,
         c.wp_goal_bound[k], c.wp_rew_range[k] = 0.5, 6.0
     c.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
     c.env_id_offset = int(env_id_offset)
+    # ---- simulator.model: per-episode aircraft-parameter randomisation (fixed_wing.py:758-800) ----
+    model = env.get("simulator", {}).get("model")
+    for i, name in enumerate(_AERO):
+        c.par_orig[i] = getattr(c, name)
+        c.par_clip[i] = float("nan")
+    if model is not None:
+        if waypoint:
+            raise NotImplementedError("simulator.model with the waypoint env")
+        dist = model.get("distribution", "gaussian")
+        if dist not in ("gaussian", "uniform"):
+            raise ValueError("Unexpected distribution type {}".format(dist))
+        c.model_on, c.model_uniform = 1, int(dist == "uniform")
+        relative = model["var_type"] == "relative"
+        for prm in model["parameters"]:
+            key = "e_oswald" if prm["name"] == "e" else prm["name"]
+            if key not in _AERO:
+                if prm["name"] in P:        # C_D_0, C_D_alpha1/2, r_cg, ...: in x8_param.mat, read by nothing in the dynamics
+                    continue
+                raise KeyError(prm["name"])
+            i = _AERO.index(key)
+            orig = prm.get("original")
+            orig = getattr(c, key) if orig is None else float(orig)
+            var = float(prm.get("var", model["var"]))
+            clip = prm.get("clip", model.get("clip"))
+            if relative:
+                var *= abs(orig)
+                clip = None if clip is None else clip * orig      # sic: not abs (fixed_wing.py:785-786)
+            c.par_enabled[i], c.par_orig[i], c.par_var[i] = 1, orig, var
+            c.par_clip[i] = float("nan") if clip is None else float(clip)
     return c
 
 

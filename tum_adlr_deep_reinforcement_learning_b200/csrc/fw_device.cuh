@@ -97,6 +97,8 @@ template <typename T> struct DCfg {
     T C_n_0, C_n_beta, C_n_p, C_n_r, C_n_delta_a, C_n_delta_r;
     T gam[9];
     T half_rho, mg, prop_k /* 0.5 rho S_prop C_prop */, inv_pi_e_ar, inv_Jy, inv_mass, exp_M_a0;
+    T g_;        // gravity (per-env mg when aircraft parameters are randomised)
+    int model_on;
     T dt, elevon_min, elevon_max, elevon_dot_max, w0sq, two_zeta_w0, inv_tau, throttle_min, throttle_max;
     T omega_con_min[3], omega_con_max[3], va_value_min, va_con_max;
     T init_lo[12], init_hi[12], wind_mag_min, wind_mag_max, turb_noise_scale;
@@ -132,6 +134,9 @@ template <typename T> struct ResetCfg {
     T tgt_low[3], tgt_high[3], tgt_delta[3];
     T tgt_slope_low[3], tgt_slope_high[3], tgt_amp_low[3], tgt_amp_high[3], tgt_period_low[3], tgt_period_high[3];
     unsigned long long seed;
+    // simulator.model (fixed_wing.py:758-800): which aircraft parameters are re-drawn at every reset, and how
+    int model_uniform, par_enabled[FW_NPARAM];
+    double par_orig[FW_NPARAM], par_var[FW_NPARAM], par_clip[FW_NPARAM];
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -174,6 +179,20 @@ enum IField {
     IF_COUNT = 50
 };
 
+// Per-env aircraft parameters (model_on handles): S.par holds, per env, the FW_NPARAM base parameters in FwConfig order
+// followed by the PD_COUNT values the RHS actually reads (base parameters and what convert_cfg derives from them).
+#define FW_RHS_PARAMS(X) X(S_wing) X(b) X(c) X(k_motor) X(k_T_P) X(k_Omega) X(M_) X(a_0) X(C_L_0) X(C_L_alpha) X(C_L_q) \
+    X(C_L_delta_e) X(C_D_p) X(C_D_q) X(C_D_beta1) X(C_D_beta2) X(C_D_delta_e) X(C_m_0) X(C_m_alpha) X(C_m_q) X(C_m_delta_e) \
+    X(C_m_fp) X(C_Y_0) X(C_Y_beta) X(C_Y_p) X(C_Y_r) X(C_Y_delta_a) X(C_l_0) X(C_l_beta) X(C_l_p) X(C_l_r) X(C_l_delta_a) \
+    X(C_n_0) X(C_n_beta) X(C_n_p) X(C_n_r) X(C_n_delta_a) X(mg) X(inv_mass) X(prop_k) X(inv_pi_e_ar) X(exp_M_a0)
+enum RhsParam {
+#define X(name) PD_##name,
+    FW_RHS_PARAMS(X)
+#undef X
+    PD_COUNT
+};
+#define FW_PAR_FIELDS (FW_NPARAM + PD_COUNT)
+
 template <typename T> struct Soa {
     T* r;              // [RF_COUNT][n]
     int32_t* i;        // [IF_COUNT][n]
@@ -189,6 +208,7 @@ template <typename T> struct Soa {
     const int32_t* wp_task_of_env;
     int wp_n_tasks, wp_len;
     const ResetCfg<T>* rc;       // device memory (fw_set_config)
+    T* par;                      // [FW_PAR_FIELDS][n] per-env aircraft parameters, or nullptr (model off)
 };
 
 // the Philox key of env's running episode
@@ -200,7 +220,7 @@ template <typename T> __device__ __forceinline__ unsigned long long env_seed(con
 // ---------------------------------------------------------------------------------------------------------------
 // Philox4x32-10 counter-based RNG (Salmon et al. SC'11).  Stream layout (identical in oracle/fw_oracle.c):
 //   key = seed;  counter = (env_id lo32, episode lo32, purpose << 28 | env_id hi bits, block)
-enum { RNG_RESET = 0, RNG_NOISE = 1, RNG_RESAMPLE = 2, RNG_ACTION = 3, RNG_OBS = 4, RNG_OBS_INIT = 5 };
+enum { RNG_RESET = 0, RNG_NOISE = 1, RNG_RESAMPLE = 2, RNG_ACTION = 3, RNG_OBS = 4, RNG_OBS_INIT = 5, RNG_MODEL = 6 };
 
 __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
 #pragma unroll
@@ -281,9 +301,12 @@ __device__ __forceinline__ void rot_euler_apply(T phi, T th, T psi, const T v[3]
 // PyFly._dynamics with _forces inlined.  `first` = the t == 0 call of solve_ivp (no state write-back, pyfly.py:1461):
 // constraint checks are skipped and elevator/aileron come from `elev0/ail0` (they are 0 right after a reset because
 // disabled ControlVariables reset to 0, pyfly.py:359-363).  Returns 0 or a FwTermCode.
-template <typename T, bool TURB>
+// PE: the aircraft parameters come from the env's column of S.par (`pe` = S.par + env, stride `pn`) instead of the
+// warp-uniform constant bank; with PE = false PRM(x) is c.x exactly as before.
+template <typename T, bool TURB, bool PE = false>
 __device__ __forceinline__ int rhs(const DCfg<T>& c, const DynCtx<T>& x, const T (&y)[FW_NY], bool first, T elev0,
-                                   T ail0, T (&dy)[FW_NY]) {
+                                   T ail0, T (&dy)[FW_NY], const T* pe = nullptr, int pn = 0) {
+#define PRM(name) (PE ? __ldg(pe + (size_t)(FW_NPARAM + PD_##name) * pn) : c.name)
     const T e0 = y[0], e1 = y[1], e2 = y[2], e3 = y[3];
     const T P = y[4], Q = y[5], R = y[6];
     const T u = y[10], v = y[11], w = y[12];
@@ -327,44 +350,44 @@ __device__ __forceinline__ int rhs(const DCfg<T>& c, const DynCtx<T>& x, const T
     if (!(s_all > (T)0)) Va = (T)0;             // rsqrt(0) = inf: keep Va = 0 like sqrt(0)
     if (Va < c.va_value_min) { Va = c.va_value_min; inv2Va = (T)1 / ((T)2 * Va); }
 
-    const T pre = c.half_rho * (Va * Va) * c.S_wing;
-    const T fgx = c.mg * ((T)2 * (e1 * e3 - e2 * e0)), fgy = c.mg * ((T)2 * (e2 * e3 + e1 * e0));
-    const T fgz = c.mg * (e3 * e3 + e0 * e0 - e1 * e1 - e2 * e2);
-    const T CLlin = c.C_L_0 + c.C_L_alpha * alpha;
+    const T pre = c.half_rho * (Va * Va) * PRM(S_wing);
+    const T fgx = PRM(mg) * ((T)2 * (e1 * e3 - e2 * e0)), fgy = PRM(mg) * ((T)2 * (e2 * e3 + e1 * e0));
+    const T fgz = PRM(mg) * (e3 * e3 + e0 * e0 - e1 * e1 - e2 * e2);
+    const T CLlin = PRM(C_L_0) + PRM(C_L_alpha) * alpha;
     T sigma;
     if (sizeof(T) == 8) {
         // sigma = (1 + e1 + e2) / ((1 + e1)(1 + e2)), e1 = exp(-M(a - a0)), e2 = exp(M(a + a0))  (pyfly.py:1541-1543).
         // With E = exp(M a), C = exp(M a0): e1 = C / E, e2 = C E, and multiplying through by E gives the same value
         // from ONE exponential and ONE division, all terms positive (no cancellation): |a| <= pi keeps E^2 < 1e137.
-        const T E = M<T>::exp_hot(c.M_ * alpha);
-        sigma = (E + c.exp_M_a0 + c.exp_M_a0 * (E * E)) * M<T>::rcp_hot((E + c.exp_M_a0) * ((T)1 + c.exp_M_a0 * E));
+        const T E = M<T>::exp_hot(PRM(M_) * alpha);
+        sigma = (E + PRM(exp_M_a0) + PRM(exp_M_a0) * (E * E)) * M<T>::rcp_hot((E + PRM(exp_M_a0)) * ((T)1 + PRM(exp_M_a0) * E));
     } else {
         // overflow-safe in fp32: sigma = 1 - s(-M(a-a0)) s(M(a+a0)), s = logistic
-        const T g1 = M<T>::exp(c.M_ * (alpha - c.a_0)), g2 = M<T>::exp(-c.M_ * (alpha + c.a_0));
+        const T g1 = M<T>::exp(PRM(M_) * (alpha - PRM(a_0))), g2 = M<T>::exp(-PRM(M_) * (alpha + PRM(a_0)));
         sigma = (T)1 - (T)1 / (((T)1 + g1) * ((T)1 + g2));
     }
     const T sg = sgn(alpha);
     const T C_L = ((T)1 - sigma) * CLlin + sigma * ((T)2 * sg * (sa * sa) * ca);
-    const T lift = pre * (C_L + c.C_L_q * c.c * inv2Va * q + c.C_L_delta_e * elevator);
-    const T C_Da = c.C_D_p + ((T)1 - sigma) * (CLlin * CLlin) * c.inv_pi_e_ar + sigma * ((T)2 * sg * (sa * sa * sa));
-    const T C_Db = c.C_D_beta1 * beta + c.C_D_beta2 * (beta * beta);
-    const T drag = pre * (C_Da + C_Db + c.C_D_q * c.c * inv2Va * q + c.C_D_delta_e * (elevator * elevator));
-    const T C_m = ((T)1 - sigma) * (c.C_m_0 + c.C_m_alpha * alpha) + sigma * (c.C_m_fp * sg * (sa * sa));
-    const T bq = c.b * inv2Va;
-    const T m_ = pre * c.c * (C_m + c.C_m_q * bq * q + c.C_m_delta_e * elevator);   // sic: b (pyfly.py:1579)
-    const T fy = pre * (c.C_Y_0 + c.C_Y_beta * beta + c.C_Y_p * bq * p + c.C_Y_r * bq * r + c.C_Y_delta_a * aileron);
-    const T l_ = pre * c.b * (c.C_l_0 + c.C_l_beta * beta + c.C_l_p * bq * p + c.C_l_r * bq * r + c.C_l_delta_a * aileron);
-    const T n_ = pre * c.b * (c.C_n_0 + c.C_n_beta * beta + c.C_n_p * bq * p + c.C_n_r * bq * r + c.C_n_delta_a * aileron);
+    const T lift = pre * (C_L + PRM(C_L_q) * PRM(c) * inv2Va * q + PRM(C_L_delta_e) * elevator);
+    const T C_Da = PRM(C_D_p) + ((T)1 - sigma) * (CLlin * CLlin) * PRM(inv_pi_e_ar) + sigma * ((T)2 * sg * (sa * sa * sa));
+    const T C_Db = PRM(C_D_beta1) * beta + PRM(C_D_beta2) * (beta * beta);
+    const T drag = pre * (C_Da + C_Db + PRM(C_D_q) * PRM(c) * inv2Va * q + PRM(C_D_delta_e) * (elevator * elevator));
+    const T C_m = ((T)1 - sigma) * (PRM(C_m_0) + PRM(C_m_alpha) * alpha) + sigma * (PRM(C_m_fp) * sg * (sa * sa));
+    const T bq = PRM(b) * inv2Va;
+    const T m_ = pre * PRM(c) * (C_m + PRM(C_m_q) * bq * q + PRM(C_m_delta_e) * elevator);   // sic: b (pyfly.py:1579)
+    const T fy = pre * (PRM(C_Y_0) + PRM(C_Y_beta) * beta + PRM(C_Y_p) * bq * p + PRM(C_Y_r) * bq * r + PRM(C_Y_delta_a) * aileron);
+    const T l_ = pre * PRM(b) * (PRM(C_l_0) + PRM(C_l_beta) * beta + PRM(C_l_p) * bq * p + PRM(C_l_r) * bq * r + PRM(C_l_delta_a) * aileron);
+    const T n_ = pre * PRM(b) * (PRM(C_n_0) + PRM(C_n_beta) * beta + PRM(C_n_p) * bq * p + PRM(C_n_r) * bq * r + PRM(C_n_delta_a) * aileron);
     // f_aero = R_euler(0, alpha, beta) . [-drag, fy, -lift]  (pyfly.py:1617-1620; phi = 0 -> sin 0, cos 1)
     const T s0 = -drag, s1 = fy, s2 = -lift;
     const T fax = ca * cb * s0 + ca * sb * s1 + (-sa) * s2;
     const T fay = (-sb) * s0 + cb * s1;
     const T faz = sa * cb * s0 + sa * sb * s1 + ca * s2;
-    const T Vd = Va + thr * (c.k_motor - Va);
-    const T fprop = c.prop_k * Vd * (Vd - Va);
-    const T kt = c.k_Omega * thr;
+    const T Vd = Va + thr * (PRM(k_motor) - Va);
+    const T fprop = PRM(prop_k) * Vd * (Vd - Va);
+    const T kt = PRM(k_Omega) * thr;
     const T fx = fprop + fgx + fax, fyb = fgy + fay, fz = fgz + faz;
-    const T tx = l_ + (-c.k_T_P * (kt * kt)), ty = m_, tz = n_;
+    const T tx = l_ + (-PRM(k_T_P) * (kt * kt)), ty = m_, tz = n_;
 
     // _f_attitude_dot uses the STATE omega (not turbulence corrected) (pyfly.py:1466,1476)
     dy[0] = (T)0.5 * (-P * e1 - Q * e2 - R * e3);
@@ -378,9 +401,9 @@ __device__ __forceinline__ int rhs(const DCfg<T>& c, const DynCtx<T>& x, const T
     dy[7] = (e1 * e1 + e0 * e0 - e2 * e2 - e3 * e3) * u + (T)2 * (e1 * e2 - e3 * e0) * v + (T)2 * (e1 * e3 + e2 * e0) * w;
     dy[8] = (T)2 * (e1 * e2 + e3 * e0) * u + (e2 * e2 + e0 * e0 - e1 * e1 - e3 * e3) * v + (T)2 * (e2 * e3 - e1 * e0) * w;
     dy[9] = (T)2 * (e1 * e3 - e2 * e0) * u + (T)2 * (e2 * e3 + e1 * e0) * v + (e3 * e3 + e0 * e0 - e1 * e1 - e2 * e2) * w;
-    dy[10] = R * v - Q * w + fx * c.inv_mass;
-    dy[11] = P * w - R * u + fyb * c.inv_mass;
-    dy[12] = Q * u - P * v + fz * c.inv_mass;
+    dy[10] = R * v - Q * w + fx * PRM(inv_mass);
+    dy[11] = P * w - R * u + fyb * PRM(inv_mass);
+    dy[12] = Q * u - P * v + fz * PRM(inv_mass);
     // Actuation.rhs (pyfly.py:519-543): elevons 2nd order on clipped value/rate, throttle 1st order
     dy[13] = erd;
     dy[14] = eld;
@@ -389,6 +412,7 @@ __device__ __forceinline__ int rhs(const DCfg<T>& c, const DynCtx<T>& x, const T
     dy[17] = el * (-c.w0sq) + x.cmd[1] * c.w0sq + eld * (-c.two_zeta_w0);
     dy[18] = (T)0;
     return 0;
+#undef PRM
 }
 
 // Dormand-Prince 5(4) tableau (scipy rk.py class RK45) as "evaluation rows": row r gives the coefficients of the
@@ -433,16 +457,16 @@ __device__ __forceinline__ float ld_again(const float* p) {
 }
 
 // ys enters holding y0 (which is also at ysrc[i * n]); f0 is written to f0dst[i * n] (i < FW_NK).
-template <typename T, bool TURB>
+template <typename T, bool TURB, bool PE = false>
 __device__ __forceinline__ int rk45_init(const DCfg<T>& c, const DynCtx<T>& x, T (&ys)[FW_NY], const T* ysrc, T* f0dst,
-                                         int n, T elev0, T ail0, T& h_abs) {
+                                         int n, T elev0, T ail0, T& h_abs, const T* pe = nullptr) {
     const T rtol = c.rtol, atol = c.atol, t_bound = c.dt;
     T dyv[FW_NY];
     T d1 = 0, h0 = 0;
     int rc = 0;
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
-        rc = rhs<T, TURB>(c, x, ys, pass == 0, elev0, ail0, dyv);
+        rc = rhs<T, TURB, PE>(c, x, ys, pass == 0, elev0, ail0, dyv, pe, n);
         if (rc) return rc;
         if (pass == 0) {
             T s0 = 0, s1 = 0;
@@ -486,9 +510,9 @@ template <typename T> __device__ __forceinline__ T ulp10(T t) {   // min_step = 
 
 // classical RK4 x substeps, register resident (throughput mode; same RHS with its clip/constraint side effects),
 // also one loop around one RHS instance.
-template <typename T, bool TURB>
+template <typename T, bool TURB, bool PE = false>
 __device__ __forceinline__ int solve_rk4(const DCfg<T>& c, const DynCtx<T>& x, T (&y)[FW_NY], T elev0, T ail0,
-                                         int& nfev, int& natt) {
+                                         int& nfev, int& natt, const T* pe = nullptr, int pn = 0) {
     const int n = c.rk4_substeps > 0 ? c.rk4_substeps : 1;
     const T h = c.dt / (T)n;
     T k[FW_NY], acc[FW_NK], ys[FW_NY];
@@ -506,7 +530,7 @@ __device__ __forceinline__ int solve_rk4(const DCfg<T>& c, const DynCtx<T>& x, T
 #pragma unroll
         for (int i = 0; i < FW_NK; ++i) ys[i] = y[i] + cs * k[i];
         ys[18] = y[18];
-        rc = rhs<T, TURB>(c, x, ys, e == 0, elev0, ail0, k);
+        rc = rhs<T, TURB, PE>(c, x, ys, e == 0, elev0, ail0, k, pe, pn);
         nfev++;
         if (rc) break;
         const T w = (st == 1 || st == 2) ? (T)2 : (T)1;
@@ -958,6 +982,61 @@ __device__ __noinline__ void generic_observation(const DCfg<T>& c, const Soa<T>&
     }
 }
 
+// What the RHS reads, from the FW_NPARAM base parameters of one env (FwConfig order: mass 0, S_wing 5, b 6, c 7, S_prop 8,
+// C_prop 9, k_motor 10, k_T_P 11, k_Omega 12, e 13, M 14, a_0 15, C_L_0 16 ...): the same expressions convert_cfg uses for
+// the warp-uniform constants.  Jx..Jxz and the aspect ratio keep their construction-time values (pyfly.py:1086-1119).
+template <typename T>
+__device__ __forceinline__ void write_env_params(const DCfg<T>& c, const Soa<T>& S, int env, const double (&bp)[FW_NPARAM]) {
+    const int n = S.n;
+    T* p = S.par + env;
+#pragma unroll 1
+    for (int i = 0; i < FW_NPARAM; ++i) p[(size_t)i * n] = (T)bp[i];
+    T* d = p + (size_t)FW_NPARAM * n;
+    d[(size_t)PD_S_wing * n] = (T)bp[5]; d[(size_t)PD_b * n] = (T)bp[6]; d[(size_t)PD_c * n] = (T)bp[7];
+    d[(size_t)PD_k_motor * n] = (T)bp[10]; d[(size_t)PD_k_T_P * n] = (T)bp[11]; d[(size_t)PD_k_Omega * n] = (T)bp[12];
+    d[(size_t)PD_M_ * n] = (T)bp[14]; d[(size_t)PD_a_0 * n] = (T)bp[15];
+#pragma unroll 1
+    for (int k = 0; k < 19; ++k) d[(size_t)(PD_C_L_0 + k) * n] = (T)bp[16 + k];            // C_L_0 .. C_Y_delta_a (16 .. 34)
+#pragma unroll 1
+    for (int k = 0; k < 5; ++k) d[(size_t)(PD_C_l_0 + k) * n] = (T)bp[36 + k];             // C_l_0 .. C_l_delta_a
+#pragma unroll 1
+    for (int k = 0; k < 5; ++k) d[(size_t)(PD_C_n_0 + k) * n] = (T)bp[42 + k];             // C_n_0 .. C_n_delta_a
+    d[(size_t)PD_mg * n] = (T)(bp[0] * (double)c.g_);
+    d[(size_t)PD_inv_mass * n] = (T)(1.0 / bp[0]);
+    d[(size_t)PD_prop_k * n] = (T)((double)c.half_rho * bp[8] * bp[9]);
+    d[(size_t)PD_inv_pi_e_ar * n] = (T)(1.0 / (3.14159265358979323846 * bp[13] * (double)c.ar));
+    d[(size_t)PD_exp_M_a0 * n] = (T)::exp(bp[14] * bp[15]);
+}
+static_assert(PD_C_Y_delta_a - PD_C_L_0 == 18 && PD_C_l_delta_a - PD_C_l_0 == 4 && PD_C_n_delta_a - PD_C_n_0 == 4, "parameter blocks");
+
+// sample_simulator_parameters, "model" block (fixed_wing.py:758-800), same Philox stream as oracle sample_model_params
+template <typename T>
+__device__ __noinline__ void sample_env_params(const DCfg<T>& c, const Soa<T>& S, int env, unsigned long long seed,
+                                               long long gid, unsigned long long episode) {
+    const ResetCfg<T>& rc = *S.rc;
+    double bp[FW_NPARAM];
+#pragma unroll 1
+    for (int i = 0; i < FW_NPARAM; ++i) {
+        const double orig = rc.par_orig[i];
+        double v = orig;
+        if (rc.par_enabled[i] && orig != 0.0) {
+            const uint4 r = rng_block(seed, gid, episode, RNG_MODEL, (uint32_t)i);
+            const double u1 = u53(r.x, r.y), u2 = u53(r.z, r.w);
+            if (rc.model_uniform) {
+                const double lo = orig - rc.par_var[i], hi = orig + rc.par_var[i];
+                v = lo + (hi - lo) * u1;
+            } else {
+                v = orig + rc.par_var[i] * (::sqrt(-2.0 * ::log(1.0 - u1)) * ::cos(6.283185307179586476925 * u2));
+                if (!::isnan(rc.par_clip[i])) v = ::fmin(::fmax(v, orig - rc.par_clip[i]), orig + rc.par_clip[i]);
+            }
+        } else if (!rc.par_enabled[i]) {
+            v = orig;
+        }
+        bp[i] = v;
+    }
+    write_env_params<T>(c, S, env, bp);
+}
+
 // FixedWingAircraft.reset -> PyFly.reset for one env; writes the full SoA row and the reset observation.
 template <typename T>
 __device__ void reset_env(const DCfg<T>& c, const Soa<T>& S, int env, const double* state_in, const double* target_in,
@@ -1030,6 +1109,7 @@ __device__ void reset_env(const DCfg<T>& c, const Soa<T>& S, int env, const doub
     for (int i = 0; i < 9; ++i) y[4 + i] = s12[3 + i];
 #pragma unroll
     for (int i = 0; i < 6; ++i) y[13 + i] = a6[i];
+    if (S.par) sample_env_params<T>(c, S, env, seed, gid, episode);     // fixed_wing.py:442, before sample_target
     // targets (fixed_wing.py:443-450)
     T u12[12], tgt[3], tp[15];
     int tcls[3];

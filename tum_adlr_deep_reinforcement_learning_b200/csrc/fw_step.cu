@@ -64,6 +64,7 @@ __device__ __forceinline__ Soa<T> spare_view(const Spare<T>& P, int env) {
     L.r += (size_t)env * (RF_COUNT - 1);
     L.i += (size_t)env * (IF_COUNT - 1);
     L.err_ring += (size_t)env * 2;
+    if (L.par) L.par += (size_t)env * (FW_PAR_FIELDS - 1);
     L.n = 1;
     return L;
 }
@@ -114,6 +115,8 @@ __device__ __forceinline__ void take_spare_warp(const Soa<T>& S, const Spare<T>&
             }
         }
         if (rank < 3) S.err_ring[(size_t)rank * n + e] = P.S2.err_ring[(size_t)e * 3 + rank];
+        if (S.par)          // the next episode's aircraft parameters (simulator.model)
+            for (int f = rank; f < FW_PAR_FIELDS; f += width) S.par[(size_t)f * n + e] = P.S2.par[(size_t)e * FW_PAR_FIELDS + f];
         for (int q = rank; q < odim; q += width) {
             if (obs) obs[(size_t)e * odim + q] = P.obs[(size_t)e * odim + q];
             if (obs64) obs64[(size_t)e * odim + q] = P.obs64[(size_t)e * odim + q];
@@ -264,7 +267,7 @@ __device__ __forceinline__ void load_dyn(const DCfg<T>& c, const Soa<T>& S, cons
 }
 
 // ---- kernel A0: RungeKutta.__init__ + select_initial_step for every env, lock step ----
-template <typename T, bool TURB>
+template <typename T, bool TURB, bool PE>
 __global__ void __launch_bounds__(128, 4) rk45_init_kernel(const __grid_constant__ DCfg<T> c, const Soa<T> S, const StepIO io,
                                                         const Scratch<T> W, int attempt_threads, int32_t* done_count) {
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
@@ -278,7 +281,8 @@ __global__ void __launch_bounds__(128, 4) rk45_init_kernel(const __grid_constant
     T y[FW_NY], h_abs = 0, elev0, ail0;
     DynCtx<T> x;
     load_dyn<T, TURB>(c, S, io, env, y, x, elev0, ail0);
-    const int rc = rk45_init<T, TURB>(c, x, y, S.r + (size_t)RF_Y * n + env, W.f0 + env, n, elev0, ail0, h_abs);
+    const int rc = rk45_init<T, TURB, PE>(c, x, y, S.r + (size_t)RF_Y * n + env, W.f0 + env, n, elev0, ail0, h_abs,
+                                          PE ? S.par + env : nullptr);
     W.hinit[env] = h_abs;
 #pragma unroll
     for (int k = 0; k < 3; ++k) { W.cmd[k * n + env] = x.cmd[k]; W.turb[k * n + env] = x.tl[k]; W.turb[(3 + k) * n + env] = x.ta[k]; }
@@ -288,7 +292,7 @@ __global__ void __launch_bounds__(128, 4) rk45_init_kernel(const __grid_constant
 }
 
 // ---- kernel A1: the attempt loop, persistent lanes pulling envs from a queue ----
-template <typename T, bool TURB, int NT>
+template <typename T, bool TURB, int NT, bool PE>
 __global__ void __maxnreg__(255) rk45_attempt_kernel(const __grid_constant__ DCfg<T> c, const Soa<T> S,
                                                           const Scratch<T> W) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -388,7 +392,7 @@ __global__ void __maxnreg__(255) rk45_attempt_kernel(const __grid_constant__ DCf
                 for (int k = 0; k < 3; ++k) ys[7 + k] = y[7 + k] + posB[k] * h;     // == y_new at row 6; unused before
                 ys[18] = y[18];
             }
-            const int r2 = rhs<T, TURB>(c, x, ys, false, (T)0, (T)0, dyv);
+            const int r2 = rhs<T, TURB, PE>(c, x, ys, false, (T)0, (T)0, dyv, PE ? S.par + (env < n ? env : 0) : nullptr, n);
             if (run && rc == 0) {
                 nfev++;
                 if (r2) rc = r2;
@@ -460,7 +464,7 @@ __global__ void __maxnreg__(255) rk45_attempt_kernel(const __grid_constant__ DCf
 }
 
 // ---- fixed-step modes: lock-step integrate kernel (no adaptivity, no divergence to rebalance) ----
-template <typename T, bool TURB>
+template <typename T, bool TURB, bool PE>
 __global__ void __launch_bounds__(128) rk4_kernel(const __grid_constant__ DCfg<T> c, const Soa<T> S, const StepIO io,
                                                   const Scratch<T> W, int32_t* done_count) {
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
@@ -474,7 +478,7 @@ __global__ void __launch_bounds__(128) rk4_kernel(const __grid_constant__ DCfg<T
     DynCtx<T> x;
     load_dyn<T, TURB>(c, S, io, env, y, x, elev0, ail0);
     int nfev = 0, natt = 0;
-    const int rc = solve_rk4<T, TURB>(c, x, y, elev0, ail0, nfev, natt);
+    const int rc = solve_rk4<T, TURB, PE>(c, x, y, elev0, ail0, nfev, natt, PE ? S.par + env : nullptr, n);
 #pragma unroll
     for (int i = 0; i < FW_NY; ++i) W.ytmp[i * n + env] = y[i];
 #pragma unroll
@@ -1127,6 +1131,17 @@ __global__ void field_copy_kernel(const __grid_constant__ DCfg<T> c, Soa<T> S, i
         case FW_FIELD_NFEV:
             if (!to_soa) { di[(size_t)env * 2] = ii[IF_NFEV * n]; di[(size_t)env * 2 + 1] = ii[IF_NATT * n]; }
             break;
+        case FW_FIELD_PARAMS:
+            if (S.par) {
+                if (to_soa) {
+                    double bp[FW_NPARAM];
+                    for (int k = 0; k < FW_NPARAM; ++k) bp[k] = d[(size_t)env * FW_NPARAM + k];
+                    write_env_params<T>(c, S, env, bp);
+                } else {
+                    for (int k = 0; k < FW_NPARAM; ++k) d[(size_t)env * FW_NPARAM + k] = (double)S.par[(size_t)k * n + env];
+                }
+            }
+            break;
         default: break;
     }
 }
@@ -1187,6 +1202,8 @@ template <typename T> static void convert_cfg(const FwConfig& f, DCfg<T>& d) {
     }
     d.half_rho = (T)(0.5 * f.rho);
     d.mg = (T)(f.mass * f.g);
+    d.g_ = (T)f.g;
+    d.model_on = f.model_on;
     d.prop_k = (T)(0.5 * f.rho * f.S_prop * f.C_prop);
     d.inv_pi_e_ar = (T)(1.0 / (3.14159265358979323846 * f.e_oswald * (f.b * f.b / f.S_wing)));
     d.inv_Jy = (T)(1.0 / f.Jy);
@@ -1247,6 +1264,10 @@ template <typename T> static void convert_reset_cfg(const FwConfig& f, ResetCfg<
     }
 #undef CP
     d.seed = f.seed;
+    d.model_uniform = f.model_uniform;
+    for (int i = 0; i < FW_NPARAM; ++i) {
+        d.par_enabled[i] = f.par_enabled[i]; d.par_orig[i] = f.par_orig[i]; d.par_var[i] = f.par_var[i]; d.par_clip[i] = f.par_clip[i];
+    }
 }
 
 // the FwConfig fields fw_set_config may change on a live handle (everything ResetCfg carries); used to check that
@@ -1259,6 +1280,9 @@ static void blank_reset_fields(FwConfig& f) {
     memset(f.tgt_amp_low, 0, sizeof(f.tgt_amp_low)); memset(f.tgt_amp_high, 0, sizeof(f.tgt_amp_high));
     memset(f.tgt_period_low, 0, sizeof(f.tgt_period_low)); memset(f.tgt_period_high, 0, sizeof(f.tgt_period_high));
     f.seed = 0;
+    f.model_uniform = 0;
+    memset(f.par_enabled, 0, sizeof(f.par_enabled)); memset(f.par_orig, 0, sizeof(f.par_orig));
+    memset(f.par_var, 0, sizeof(f.par_var)); memset(f.par_clip, 0, sizeof(f.par_clip));
 }
 
 }  // namespace fw
@@ -1277,6 +1301,7 @@ struct FwHandle {
     void* w_real; int32_t* w_int;          // scratch between the kernels of one step
     double* wp_tasks; int32_t* wp_task_of_env;   // waypoint head: device copies of the task table
     void* rc_dev;                          // ResetCfg<T> in device memory (fw_set_config rewrites it)
+    void* par_buf; void* par2_buf;         // per-env aircraft parameters and their next-episode rows (model_on)
     Scratch<double> w64;
     Scratch<float> w32;
     int sm_count, att_blocks_per_sm;
@@ -1362,10 +1387,10 @@ static void spare_refill(FwHandle* h, const DCfg<T>& c, const Spare<T>& P, cudaS
 }
 
 // One env step = init kernel -> persistent attempt kernel -> head kernel (RK45), or rk4 kernel -> head kernel.
-template <typename T, bool TURB, int NT>
+template <typename T, bool TURB, int NT, bool PE>
 static int launch_rk45(FwHandle* h, const DCfg<T>& c, const Soa<T>& S, const Scratch<T>& W, const Spare<T>& P, const StepIO& io, cudaStream_t st) {
     const size_t smem = (size_t)6 * FW_NS * NT * sizeof(T);
-    auto k = rk45_attempt_kernel<T, TURB, NT>;
+    auto k = rk45_attempt_kernel<T, TURB, NT, PE>;
     // per handle: function attributes and occupancy belong to the handle's device (one handle runs one instantiation)
     if (!h->att_blocks_per_sm) {
         CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1378,7 +1403,7 @@ static int launch_rk45(FwHandle* h, const DCfg<T>& c, const Soa<T>& S, const Scr
     const int g0 = (h->n + 127) / 128, g0h = (h->n + 63) / 64;
     prof_mark(h, 0, st);
     const int par = h->step_parity;
-    rk45_init_kernel<T, TURB><<<g0, 128, 0, st>>>(c, S, io, W, grid * NT, P.count + par);
+    rk45_init_kernel<T, TURB, PE><<<g0, 128, 0, st>>>(c, S, io, W, grid * NT, P.count + par);
     prof_mark(h, 1, st);
     k<<<grid, NT, smem, st>>>(c, S, W);
     prof_mark(h, 2, st);
@@ -1393,12 +1418,12 @@ static int launch_rk45(FwHandle* h, const DCfg<T>& c, const Soa<T>& S, const Scr
     prof_collect(h, true);
     return FW_OK;
 }
-template <typename T, bool TURB>
+template <typename T, bool TURB, bool PE>
 static int launch_rk4(FwHandle* h, const DCfg<T>& c, const Soa<T>& S, const Scratch<T>& W, const Spare<T>& P, const StepIO& io, cudaStream_t st) {
     const int g0 = (h->n + 127) / 128, g0h = (h->n + 63) / 64;
     prof_mark(h, 1, st);
     const int par = h->step_parity;
-    rk4_kernel<T, TURB><<<g0, 128, 0, st>>>(c, S, io, W, P.count + par);
+    rk4_kernel<T, TURB, PE><<<g0, 128, 0, st>>>(c, S, io, W, P.count + par);
     prof_mark(h, 2, st);
     spare_join(h, st);
     if (h->cfg.env_kind == FW_ENV_WAYPOINT) waypoint_head_kernel<T, TURB><<<g0, 128, 0, st>>>(c, S, io, W);
@@ -1416,18 +1441,23 @@ static int launch_step(FwHandle* h, const StepIO& io_in, cudaStream_t st) {
     StepIO io = io_in;
     io.info = io.auto_reset ? h->info_rows : nullptr;
     io.info_cap = h->info_cap;
-    const bool turb = h->cfg.turbulence != 0, rk45 = h->cfg.integrator == FW_INT_RK45_SCIPY;
-    if (h->cfg.precision == FW_F64) {
-        if (rk45) return turb ? launch_rk45<double, true, NT_RK45_F64>(h, h->c64, h->s64, h->w64, h->p64, io, st)
-                              : launch_rk45<double, false, NT_RK45_F64>(h, h->c64, h->s64, h->w64, h->p64, io, st);
-        return turb ? launch_rk4<double, true>(h, h->c64, h->s64, h->w64, h->p64, io, st)
-                    : launch_rk4<double, false>(h, h->c64, h->s64, h->w64, h->p64, io, st);
-    }
-    if (rk45) return turb ? launch_rk45<float, true, NT_RK45_F32>(h, h->c32, h->s32, h->w32, h->p32, io, st)
-                          : launch_rk45<float, false, NT_RK45_F32>(h, h->c32, h->s32, h->w32, h->p32, io, st);
-    return turb ? launch_rk4<float, true>(h, h->c32, h->s32, h->w32, h->p32, io, st)
-                : launch_rk4<float, false>(h, h->c32, h->s32, h->w32, h->p32, io, st);
+    const bool turb = h->cfg.turbulence != 0, rk45 = h->cfg.integrator == FW_INT_RK45_SCIPY, pe = h->cfg.model_on != 0;
+    // per-env aircraft parameters (simulator.model) select their own instantiations; the default path is untouched
+#define FW_DISPATCH(T, c, s, w, p, NT)                                                                                  \
+    do {                                                                                                                \
+        if (rk45) {                                                                                                     \
+            if (pe) return turb ? launch_rk45<T, true, NT, true>(h, c, s, w, p, io, st) : launch_rk45<T, false, NT, true>(h, c, s, w, p, io, st);   \
+            return turb ? launch_rk45<T, true, NT, false>(h, c, s, w, p, io, st) : launch_rk45<T, false, NT, false>(h, c, s, w, p, io, st);         \
+        }                                                                                                               \
+        if (pe) return turb ? launch_rk4<T, true, true>(h, c, s, w, p, io, st) : launch_rk4<T, false, true>(h, c, s, w, p, io, st);                 \
+        return turb ? launch_rk4<T, true, false>(h, c, s, w, p, io, st) : launch_rk4<T, false, false>(h, c, s, w, p, io, st);                       \
+    } while (0)
+    if (h->cfg.precision == FW_F64) FW_DISPATCH(double, h->c64, h->s64, h->w64, h->p64, NT_RK45_F64);
+    FW_DISPATCH(float, h->c32, h->s32, h->w32, h->p32, NT_RK45_F32);
+#undef FW_DISPATCH
 }
+
+extern "C" int fw_obs_dim(const FwHandle* h);
 
 // ---- checkpoint / resume: the whole env state of a handle as one contiguous device blob ----
 struct BlobPart { void* ptr; size_t bytes; };
@@ -1448,6 +1478,7 @@ static int blob_parts(FwHandle* h, BlobPart* out) {
     out[k++] = {h->spare_obs, sizeof(float) * odim * n};
     out[k++] = {h->spare_obs64, sizeof(double) * odim * n};
     out[k++] = {h->rc_dev, sizeof(ResetCfg<double>)};
+    if (h->par_buf) { out[k++] = {h->par_buf, esz * FW_PAR_FIELDS * n}; out[k++] = {h->par2_buf, esz * FW_PAR_FIELDS * n}; }
     return k;
 }
 struct BlobHeader { uint64_t magic; int32_t abi, n, precision, rf_count, if_count, obs_dim; uint64_t random_step; int32_t step_parity, _pad; };
@@ -1566,8 +1597,8 @@ int fw_create(const FwConfig* cfg, int32_t n_envs, int32_t device, FwHandle** ou
     CK(cudaMemset(h->ep_ret, 0, sizeof(double) * n));
     CK(cudaMemset(h->ep_len, 0, sizeof(int32_t) * n));
     CK(cudaMemset(h->ep_term, 0, sizeof(int32_t) * n));
-    h->s64 = Soa<double>{(double*)h->r_buf, h->i_buf, (double*)h->err_ring, h->metrics, h->ep_ret, h->ep_len, h->ep_term, nullptr, 0, n_envs, nullptr, nullptr, 0, 0, nullptr};
-    h->s32 = Soa<float>{(float*)h->r_buf, h->i_buf, (float*)h->err_ring, h->metrics, h->ep_ret, h->ep_len, h->ep_term, nullptr, 0, n_envs, nullptr, nullptr, 0, 0, nullptr};
+    h->s64 = Soa<double>{(double*)h->r_buf, h->i_buf, (double*)h->err_ring, h->metrics, h->ep_ret, h->ep_len, h->ep_term, nullptr, 0, n_envs, nullptr, nullptr, 0, 0, nullptr, nullptr};
+    h->s32 = Soa<float>{(float*)h->r_buf, h->i_buf, (float*)h->err_ring, h->metrics, h->ep_ret, h->ep_len, h->ep_term, nullptr, 0, n_envs, nullptr, nullptr, 0, 0, nullptr, nullptr};
     {
         CK(cudaMalloc(&h->rc_dev, sizeof(ResetCfg<double>)));
         if (cfg->precision == FW_F64) {
@@ -1579,6 +1610,13 @@ int fw_create(const FwConfig* cfg, int32_t n_envs, int32_t device, FwHandle** ou
         }
         h->s64.rc = (const ResetCfg<double>*)h->rc_dev;
         h->s32.rc = (const ResetCfg<float>*)h->rc_dev;
+        if (cfg->model_on) {
+            CK(cudaMalloc(&h->par_buf, esz * FW_PAR_FIELDS * n));
+            CK(cudaMalloc(&h->par2_buf, esz * FW_PAR_FIELDS * n));
+            CK(cudaMemset(h->par_buf, 0, esz * FW_PAR_FIELDS * n));
+            CK(cudaMemset(h->par2_buf, 0, esz * FW_PAR_FIELDS * n));
+            h->s64.par = (double*)h->par_buf; h->s32.par = (float*)h->par_buf;
+        }
     }
     {
         const int odim = fw_obs_dim(h);
@@ -1595,7 +1633,9 @@ int fw_create(const FwConfig* cfg, int32_t n_envs, int32_t device, FwHandle** ou
         CK(cudaMemset(h->spare_obs64, 0, sizeof(double) * odim * n));
         CK(cudaMemset(h->done_list, 0, sizeof(int32_t) * (2 * n + 2)));
         h->p64.S2 = h->s64; h->p64.S2.r = (double*)h->r2_buf; h->p64.S2.i = h->i2_buf; h->p64.S2.err_ring = (double*)h->err2;
+        h->p64.S2.par = (double*)h->par2_buf;
         h->p32.S2 = h->s32; h->p32.S2.r = (float*)h->r2_buf; h->p32.S2.i = h->i2_buf; h->p32.S2.err_ring = (float*)h->err2;
+        h->p32.S2.par = (float*)h->par2_buf;
         h->p64.obs = h->p32.obs = h->spare_obs;
         h->p64.obs64 = h->p32.obs64 = h->spare_obs64;
         h->p64.list = h->p32.list = h->done_list;
@@ -1620,7 +1660,7 @@ int fw_destroy(FwHandle* h) {
     cudaDeviceSynchronize();
     cudaFree(h->r_buf); cudaFree(h->i_buf); cudaFree(h->err_ring); cudaFree(h->metrics);
     cudaFree(h->ep_ret); cudaFree(h->ep_len); cudaFree(h->ep_term); cudaFree(h->w_real); cudaFree(h->w_int);
-    cudaFree(h->wp_tasks); cudaFree(h->wp_task_of_env); cudaFree(h->rc_dev);
+    cudaFree(h->wp_tasks); cudaFree(h->wp_task_of_env); cudaFree(h->rc_dev); cudaFree(h->par_buf); cudaFree(h->par2_buf);
     cudaFree(h->r2_buf); cudaFree(h->i2_buf); cudaFree(h->err2); cudaFree(h->spare_obs); cudaFree(h->spare_obs64);
     cudaFree(h->done_list);
     if (h->side) cudaStreamDestroy(h->side);
@@ -1795,6 +1835,10 @@ int fw_get_episode_info(FwHandle* h, int32_t* term_code_dev, double* metrics_dev
 
 static int field_copy(FwHandle* h, int32_t field, void* buf, int to_soa, void* stream) {
     if (!h || !buf || field < 0 || field >= FW_FIELD_COUNT) return FW_EINVAL;
+    if (field == FW_FIELD_PARAMS && !h->par_buf) {
+        snprintf(g_err, sizeof(g_err), "FW_FIELD_PARAMS: the handle was created without simulator.model (model_on = 0)");
+        return FW_EINVAL;
+    }
     const int bs = 128, grid = (h->n + bs - 1) / bs;
     if (h->cfg.precision == FW_F64) field_copy_kernel<double><<<grid, bs, 0, (cudaStream_t)stream>>>(h->c64, h->s64, field, buf, to_soa);
     else field_copy_kernel<float><<<grid, bs, 0, (cudaStream_t)stream>>>(h->c32, h->s32, field, buf, to_soa);
