@@ -553,6 +553,9 @@ class PPO:
                 self.logs.append(row)
                 if callback is not None:
                     callback(row)
+        if self.peer_allreduce and self.optimizer.comm_error():
+            raise RuntimeError("fw_comm_allreduce_adam: a peer rank did not arrive within the time limit; the replicas are "
+                               "no longer in step")
         return self
 
     # ------------------------------------------------------------------ checkpoint / resume
