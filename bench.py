@@ -306,6 +306,15 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the env step has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
+        # the ranks of one box share its host cores: give every rank its own slice, so that the e2e leg (python + pinned
+        # copies per step in every process) is not scheduled on top of its neighbours
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cores) // world)
+            mine = cores[local * per:(local + 1) * per] or cores
+            os.sched_setaffinity(0, mine)
+        except (AttributeError, OSError):
+            pass
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     n, K, W = args.envs_per_gpu, args.steps, args.warmup
