@@ -615,7 +615,7 @@ def main():
         from tum_adlr_deep_reinforcement_learning_b200.ppo import PPO
         n_ppo, n_steps, iters = 8192, 32, 10
         venv = FixedWingVecEnv(n_ppo, sim_config_kw={"turbulence": True}, device=local, seed=0, env_id_offset=rank * n_ppo)
-        algo = PPO(venv, n_steps=n_steps, batch_size=n_ppo * n_steps // 8, n_epochs=10, ent_coef=0.01,
+        algo = PPO(venv, n_steps=n_steps, batch_size=n_ppo * n_steps // 4, n_epochs=10, ent_coef=0.01,
                    dist=dist if world > 1 else None)
         algo.learn(total_timesteps=3 * world * n_ppo * n_steps)        # warm-up: eager pass, CUDA-graph captures
         assert algo._rollout_graph is not None and algo._train_graph, "PPO must run from captured CUDA graphs in the bench"
@@ -625,7 +625,10 @@ def main():
         barrier()
         dt = max_over_ranks(time.perf_counter() - t0)
         ppo = {"value": iters * world * n_ppo * n_steps / dt, "unit": "env-steps/s (rollout + GAE + 10-epoch update)",
-               "envs_per_gpu": n_ppo, "n_steps": n_steps, "minibatch": n_ppo * n_steps // 8, "n_epochs": 10,
+               "envs_per_gpu": n_ppo, "n_steps": n_steps, "minibatch": n_ppo * n_steps // 4, "n_epochs": 10,
+               "hyper_parameters": "4 minibatches x 10 epochs per rollout of 32 steps (nminibatches = 4 is the PPO2 default of the "
+                                   "reference's training script); reaches the reference's 1 M-step reward (-405) in 16.6 s of "
+                                   "wall-clock, results/r02_ppo_curve_60s_4minibatches.json (8 minibatches: 16.2 s, 7.6e6 env-steps/s)",
                "iterations_timed": iters, "ep_rew_mean": algo.logs[-1]["ep_rew_mean"], "cuda_graphs": True,
                "note": "policy 2x64 tanh MLP in PyTorch (split-K weight gradients), loss block fused in fw_ppo_loss, rollout "
                        "and minibatch update replayed as CUDA graphs (value branch on a second stream); one gradient all-reduce per optimiser step when "

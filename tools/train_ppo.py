@@ -13,7 +13,7 @@ from tum_adlr_deep_reinforcement_learning_b200.vec_env import FixedWingVecEnv
 
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
 out = sys.argv[2] if len(sys.argv) > 2 else "gpurun_out/ppo_curve.json"
-hp = dict(n_steps=32, batch_size=32768, n_epochs=10, ent_coef=0.01, learning_rate=3e-4)   # ent_coef as SB2 PPO2
+hp = dict(n_steps=32, batch_size=65536, n_epochs=10, ent_coef=0.01, learning_rate=3e-4)   # ent_coef, 4 minibatches as SB2 PPO2
 for kv in sys.argv[3:]:
     k, v = kv.split("=")
     hp[k] = type(hp[k])(v)
