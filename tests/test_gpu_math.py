@@ -30,3 +30,7 @@ def test_hot_loop_math_within_2_ulp(cuda_device):
     nz = ref != 0
     assert _ulp_err(got[nz], ref[nz]).max() <= 2.0
     assert np.all(got[~nz] == 0)
+    # 1/sqrt(x) on the range of |airspeed|^2 and of the asin argument reduction (normal range, x > 0)
+    x = np.concatenate([np.exp(rs.uniform(np.log(1e-12), np.log(1e12), n)), [1.0, 4.0, 0.25, 400.0]])
+    got = debug_math(3, torch.as_tensor(x).cuda()).cpu().numpy()
+    assert _ulp_err(got, 1.0 / np.sqrt(x)).max() <= 2.0

@@ -35,6 +35,7 @@ template <> struct M<double> {
     static __device__ __forceinline__ double log(double x) { return ::log(x); }
     static __device__ __forceinline__ double sqrt(double x) { return ::sqrt(x); }
     static __device__ __forceinline__ double rsqrt(double x) { return ::rsqrt(x); }
+    static __device__ __forceinline__ double rsqrt_hot(double x) { return rsqrt_fast(x); }
     // straight-line versions for the RHS hot loop (fw_math.cuh)
     static __device__ __forceinline__ double atan2_hot(double y, double x) { return atan2_bf(y, x); }
     static __device__ __forceinline__ double asin_hot(double x) { return asin_bf(x); }
@@ -59,6 +60,7 @@ template <> struct M<float> {
     static __device__ __forceinline__ float log(float x) { return ::logf(x); }
     static __device__ __forceinline__ float sqrt(float x) { return ::sqrtf(x); }
     static __device__ __forceinline__ float rsqrt(float x) { return ::rsqrtf(x); }
+    static __device__ __forceinline__ float rsqrt_hot(float x) { return ::rsqrtf(x); }
     static __device__ __forceinline__ float atan2_hot(float y, float x) { return ::atan2f(y, x); }
     // sin(beta) = a1 * rsqrt(|a|^2) can exceed 1 by a float32 rounding when the sideslip reaches 90 degrees: clamp, as
     // asin_bf does for its own argument, instead of handing NaN to the forces
@@ -310,11 +312,15 @@ __device__ __forceinline__ int rhs(const DCfg<T>& c, const DynCtx<T>& x, const T
     const T e0 = y[0], e1 = y[1], e2 = y[2], e3 = y[3];
     const T P = y[4], Q = y[5], R = y[6];
     const T u = y[10], v = y[11], w = y[12];
+    // Constraint violations are carried as a code to the end instead of returning early: the RHS
+    // stays ONE basic block, so the scheduler can interleave its independent chains; a failing env's derivatives are
+    // never used (the caller stops at rc != 0), and the first violation in evaluation order wins as before.
+    int rc_con = 0;
     if (!first) {
         // _set_states_from_ode_solution(save=False): ConstraintException on p, q, r (pyfly.py:1872-1874)
-        if (P < c.omega_con_min[0] || P > c.omega_con_max[0]) return FW_TERM_OMEGA_P;
-        if (Q < c.omega_con_min[1] || Q > c.omega_con_max[1]) return FW_TERM_OMEGA_Q;
-        if (R < c.omega_con_min[2] || R > c.omega_con_max[2]) return FW_TERM_OMEGA_R;
+        if (R < c.omega_con_min[2] || R > c.omega_con_max[2]) rc_con = FW_TERM_OMEGA_R;
+        if (Q < c.omega_con_min[1] || Q > c.omega_con_max[1]) rc_con = FW_TERM_OMEGA_Q;
+        if (P < c.omega_con_min[0] || P > c.omega_con_max[0]) rc_con = FW_TERM_OMEGA_P;
     }
     // Actuation.set_states: the RHS sees CLIPPED actuator values / rates (pyfly.py:471-492, 312-328)
     const T er = clip(y[13], c.elevon_min, c.elevon_max), el = clip(y[14], c.elevon_min, c.elevon_max);
@@ -335,13 +341,13 @@ __device__ __forceinline__ int rhs(const DCfg<T>& c, const DynCtx<T>& x, const T
     // airspeed triangle.  One reciprocal square root per length: Va = s * rsqrt(s) and 1/Va = rsqrt(s) are within
     // 1-2 ulp of the reference's sqrt / divide, far inside the 1e-9 parity bar, and cost a third of sqrt + 3 divides.
     const T s_xz = a0 * a0 + a2 * a2, s_all = a0 * a0 + a1 * a1 + a2 * a2;
-    const T inv_Va_raw = M<T>::rsqrt(s_all), inv_rxz = M<T>::rsqrt(s_xz);
+    const T inv_Va_raw = M<T>::rsqrt_hot(s_all), inv_rxz = M<T>::rsqrt_hot(s_xz);
     T Va = s_all * inv_Va_raw;
     const T rxz = s_xz * inv_rxz;
     const T alpha = M<T>::atan2_hot(a2, a0);
     const T sb = a1 * inv_Va_raw;               // == sin(beta): beta = asin(a1 / Va) (pyfly.py:1848)
     const T beta = M<T>::asin_hot(sb);
-    if (c.va_con_max > (T)0 && Va > c.va_con_max) return FW_TERM_VA;
+    if (rc_con == 0 && c.va_con_max > (T)0 && Va > c.va_con_max) rc_con = FW_TERM_VA;
     // sin/cos of alpha = atan2(a2, a0) and cos of beta = asin(a1/Va) follow from the triangle without any
     // trigonometric evaluation (identical up to rounding): sin a = a2/r, cos a = a0/r, cos b = r/Va, r = |(a0, a2)|
     const T sa = (s_xz > (T)0) ? a2 * inv_rxz : (T)0, ca = (s_xz > (T)0) ? a0 * inv_rxz : (T)1;
@@ -411,7 +417,7 @@ __device__ __forceinline__ int rhs(const DCfg<T>& c, const DynCtx<T>& x, const T
     dy[16] = er * (-c.w0sq) + x.cmd[0] * c.w0sq + erd * (-c.two_zeta_w0);
     dy[17] = el * (-c.w0sq) + x.cmd[1] * c.w0sq + eld * (-c.two_zeta_w0);
     dy[18] = (T)0;
-    return 0;
+    return rc_con;
 #undef PRM
 }
 
@@ -434,6 +440,10 @@ template <typename T> __device__ __noinline__ T pow_ni(T x, T y) { return M<T>::
 
 #define FW_NK 18   // ODE components that evolve: d/dt of y[18] (throttle rate state) is identically 0
 #define FW_NS 15   // of those, components whose stage derivatives are stored (all but position y[7..9])
+#define FW_NP 8    // ... held in shared memory as pairs (the last pair is half empty)
+template <typename T> struct Vec2;
+template <> struct Vec2<double> { typedef double2 type; };
+template <> struct Vec2<float> { typedef float2 type; };
 
 // scipy.integrate.solve_ivp(fun, (0, dt), y0) with RK45 defaults (pyfly.py:1393-1395) is split over two kernels:
 //

@@ -203,6 +203,7 @@ __global__ void debug_math_kernel(int op, const double* x, const double* y, doub
     if (i >= n) return;
     if (op == 0) out[i] = fw::exp_bf(x[i]);
     else if (op == 1) out[i] = fw::asin_bf(x[i]);
+    else if (op == 3) out[i] = fw::rsqrt_fast(x[i]);
     else out[i] = fw::atan2_bf(y[i], x[i]);
 }
 

@@ -12,6 +12,36 @@
 
 namespace fw {
 
+// Polynomial coefficients live in constant memory: as 64-bit immediates every coefficient costs
+// two UMOV / IMAD.MOV issue slots on sm_100a (11 % of the RHS instruction stream, profiles/r01_v7); from the constant
+// bank two coefficients arrive with one LDCU.128.
+// (non-const on purpose: a const table with a visible initialiser is folded back into immediates)
+#define FW_TAB static __device__ __constant__ double
+FW_TAB EXP_PE[7] = {1.0 / 479001600.0, 1.0 / 3628800.0, 1.0 / 40320.0, 1.0 / 720.0, 1.0 / 24.0, 0.5, 1.0};
+FW_TAB EXP_PO[7] = {1.0 / 6227020800.0, 1.0 / 39916800.0, 1.0 / 362880.0, 1.0 / 5040.0, 1.0 / 120.0, 1.0 / 6.0, 1.0};
+FW_TAB ASIN_PE[7] = {-0.01924167174674304, 0.0030448799094556773, 0.009621842970100282, 0.01396378001220357,
+                     0.02237215744350722, 0.044642857142551895, 0.16666666666666666};
+FW_TAB ASIN_PO[7] = {0.02961201126495512, 0.019554513336123378, 0.009319560794767446, 0.011566459612121669,
+                     0.017352816540325496, 0.03038194447553234, 0.07500000000000118};
+FW_TAB ATAN_PE[6] = {-0.034570561981427744, -0.05230454270650244, -0.06666424885738255, -0.09090908753500877,
+                     -0.14285714285659828, -0.3333333333333333};
+FW_TAB ATAN_PO[6] = {0.016285756855221028, 0.04551593220626549, 0.05878928997834775, 0.07692296375032143,
+                     0.11111111105155447, 0.19999999999999804};
+
+// 1/sqrt(x) for normal-range x > 0: hardware seed (rsqrt.approx.ftz.f64, ~2^-21) and ONE third-order correction
+// r (1 + e/2 + 3 e^2 / 8), e = 1 - x r^2 (truncation 5/16 e^3 < 2^-60): ~1 ulp like ::rsqrt, but straight-line — the
+// library version carries a slow-path CALL for denormals / specials that splits the RHS into basic blocks the scheduler
+// cannot interleave across.  x = 0 gives inf (as ::rsqrt); denormal x is flushed to 0 (callers guard with selects).
+__device__ __forceinline__ double rsqrt_fast(double x) {
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    const double t = x * r;
+    const double e = fma(-t, r, 1.0);
+    const double p = fma(0.375, e, 0.5);
+    const double w = r * e;
+    return fma(w, p, r);
+}
+
 // exp(x) for |x| <= 700: n = rint(x log2 e), r = x - n ln2 (two-term Cody-Waite), Taylor degree 13 on |r| <= 0.3466
 // (truncation 4e-18), scaled by 2^n through the exponent field.
 __device__ __forceinline__ double exp_bf(double x) {
@@ -21,20 +51,9 @@ __device__ __forceinline__ double exp_bf(double x) {
     r = fma(-n, 1.90821492927058770002e-10, r);
     const double r2 = r * r;
     // even / odd Horner halves of sum r^k / k!
-    double pe = 1.0 / 479001600.0;                 // 1/12!
-    pe = fma(pe, r2, 1.0 / 3628800.0);             // 1/10!
-    pe = fma(pe, r2, 1.0 / 40320.0);
-    pe = fma(pe, r2, 1.0 / 720.0);
-    pe = fma(pe, r2, 1.0 / 24.0);
-    pe = fma(pe, r2, 0.5);
-    pe = fma(pe, r2, 1.0);
-    double po = 1.0 / 6227020800.0;                // 1/13!
-    po = fma(po, r2, 1.0 / 39916800.0);            // 1/11!
-    po = fma(po, r2, 1.0 / 362880.0);
-    po = fma(po, r2, 1.0 / 5040.0);
-    po = fma(po, r2, 1.0 / 120.0);
-    po = fma(po, r2, 1.0 / 6.0);
-    po = fma(po, r2, 1.0);
+    double pe = EXP_PE[0], po = EXP_PO[0];
+#pragma unroll
+    for (int k = 1; k < 7; ++k) { pe = fma(pe, r2, EXP_PE[k]); po = fma(po, r2, EXP_PO[k]); }
     const double p = fma(po, r, pe);
     const int ni = (int)n;
     return __hiloint2double(__double2hiint(p) + ni * 1048576, __double2loint(p));
@@ -58,7 +77,7 @@ __device__ __forceinline__ double asin_bf(double x) {
     const double ax = fabs(x);
     const bool big = ax > 0.5;
     const double z = big ? (1.0 - ax) * 0.5 : x * x;
-    const double rs = ::rsqrt(z);
+    const double rs = rsqrt_fast(z);
     double sq = z * rs;                                   // ~sqrt(z)
     double corr = fma(-sq, sq, z) * (0.5 * rs);           // sqrt(z) - sq to first order
     if (!(z > 0.0)) { sq = 0.0; corr = 0.0; }
@@ -66,20 +85,9 @@ __device__ __forceinline__ double asin_bf(double x) {
     const double cv = big ? corr : 0.0;
     const double z2 = z * z;
     double pe, po;
-    pe = -0.01924167174674304;
-    pe = fma(pe, z2, 0.0030448799094556773);
-    pe = fma(pe, z2, 0.009621842970100282);
-    pe = fma(pe, z2, 0.01396378001220357);
-    pe = fma(pe, z2, 0.02237215744350722);
-    pe = fma(pe, z2, 0.044642857142551895);
-    pe = fma(pe, z2, 0.16666666666666666);
-    po = 0.02961201126495512;
-    po = fma(po, z2, 0.019554513336123378);
-    po = fma(po, z2, 0.009319560794767446);
-    po = fma(po, z2, 0.011566459612121669);
-    po = fma(po, z2, 0.017352816540325496);
-    po = fma(po, z2, 0.03038194447553234);
-    po = fma(po, z2, 0.07500000000000118);
+    pe = ASIN_PE[0]; po = ASIN_PO[0];
+#pragma unroll
+    for (int k = 1; k < 7; ++k) { pe = fma(pe, z2, ASIN_PE[k]); po = fma(po, z2, ASIN_PO[k]); }
     const double g = fma(po, z, pe);
     const double pp = sv + fma(sv * z, g, cv);
     const double res = big ? 1.57079632679489655800e+00 - (2.0 * pp - 6.12323399573676603587e-17) : pp;
@@ -100,18 +108,9 @@ __device__ __forceinline__ double atan2_bf(double y, double x) {
     const double z = t * t;
     const double z2 = z * z;
     double pe, po;
-    pe = -0.034570561981427744;
-    pe = fma(pe, z2, -0.05230454270650244);
-    pe = fma(pe, z2, -0.06666424885738255);
-    pe = fma(pe, z2, -0.09090908753500877);
-    pe = fma(pe, z2, -0.14285714285659828);
-    pe = fma(pe, z2, -0.3333333333333333);
-    po = 0.016285756855221028;
-    po = fma(po, z2, 0.04551593220626549);
-    po = fma(po, z2, 0.05878928997834775);
-    po = fma(po, z2, 0.07692296375032143);
-    po = fma(po, z2, 0.11111111105155447);
-    po = fma(po, z2, 0.19999999999999804);
+    pe = ATAN_PE[0]; po = ATAN_PO[0];
+#pragma unroll
+    for (int k = 1; k < 6; ++k) { pe = fma(pe, z2, ATAN_PE[k]); po = fma(po, z2, ATAN_PO[k]); }
     const double q = fma(po, z, pe);
     double a = fma(t * z, q, t);
     if (big) a = 7.85398163397448278999e-01 + (a + 3.06161699786838301793e-17);        // + pi/4

@@ -296,11 +296,16 @@ template <typename T, bool TURB, int NT, bool PE>
 __global__ void __maxnreg__(255) rk45_attempt_kernel(const __grid_constant__ DCfg<T> c, const Soa<T> S,
                                                           const Scratch<T> W) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T* K = reinterpret_cast<T*>(smem_raw) + threadIdx.x;
     // Stage storage holds FW_NS = 15 components: position (y[7..9]) never feeds back into the RHS, so its stage
     // inputs are never needed and its two quadratures (sum B_j K_j for y_new, sum E_j K_j for the error estimate) are
     // carried in registers, accumulated in the same j order as the stored components.
-#define KS(s, cc) K[((s) * FW_NS + (cc)) * NT]
+    // Layout: components in PAIRS, KV[(stage * FW_NP + pair) * NT + lane] = (component 2 pair, 2 pair + 1): one
+    // 16-byte (f64) access per lane moves two values, consecutive lanes are consecutive -> conflict-free LDS.128 / STS.128.
+    typedef typename Vec2<T>::type V2;
+    V2* KV = reinterpret_cast<V2*>(smem_raw) + threadIdx.x;
+    T* K = reinterpret_cast<T*>(KV);
+#define KP(s, pp) KV[((s) * FW_NP + (pp)) * NT]
+#define KS(s, cc) K[(((s) * FW_NP + ((cc) >> 1)) * NT) * 2 + ((cc) & 1)]
 #define KC(cc) ((cc) < 7 ? (cc) : (cc) + 3)       /* stored slot -> ODE component */
     const int n = S.n;
     const T rtol = c.rtol, atol = c.atol, t_bound = c.dt;
@@ -377,15 +382,23 @@ __global__ void __maxnreg__(255) rk45_attempt_kernel(const __grid_constant__ DCf
 #pragma unroll 1
         for (int row = 1; row <= 6; ++row) {
             {
-                T acc[FW_NS];
+                // sum_{j < row} A[row][j] K_j, j ascending.  The j loop stays rolled: written out for every j behind
+                // warp-uniform tests of `row` it needs 255 registers + 330 B of spills and the kernel is 25 % slower (measured).
+                T acc[2 * FW_NP];
 #pragma unroll
-                for (int cc = 0; cc < FW_NS; ++cc) acc[cc] = 0;
-#pragma unroll 1
-                for (int j = 0; j < row; ++j) {
-                    const T a = (T)RK_ROW[row][j];
-#pragma unroll
-                    for (int cc = 0; cc < FW_NS; ++cc) acc[cc] += KS(j, cc) * a;
+                for (int cc = 0; cc < 2 * FW_NP; ++cc) acc[cc] = 0;
+#define FW_TERM(j)                                                                      \
+                {                                                                       \
+                    const T a = (T)RK_ROW[row][j];                                      \
+                    _Pragma("unroll") for (int pp = 0; pp < FW_NP; ++pp) {              \
+                        const V2 kv = KP(j, pp);                                        \
+                        acc[2 * pp] += kv.x * a;                                        \
+                        if (2 * pp + 1 < FW_NS) acc[2 * pp + 1] += kv.y * a;            \
+                    }                                                                   \
                 }
+#pragma unroll 1
+                for (int j = 0; j < row; ++j) FW_TERM(j)
+#undef FW_TERM
 #pragma unroll
                 for (int cc = 0; cc < FW_NS; ++cc) ys[KC(cc)] = y[KC(cc)] + acc[cc] * h;
 #pragma unroll
@@ -398,7 +411,12 @@ __global__ void __maxnreg__(255) rk45_attempt_kernel(const __grid_constant__ DCf
                 if (r2) rc = r2;
                 else if (row < 6) {
 #pragma unroll
-                    for (int cc = 0; cc < FW_NS; ++cc) KS(row, cc) = dyv[KC(cc)];
+                    for (int pp = 0; pp < FW_NP; ++pp) {
+                        V2 kv;
+                        kv.x = dyv[KC(2 * pp)];
+                        kv.y = (2 * pp + 1 < FW_NS) ? dyv[KC(2 * pp + 1)] : (T)0;
+                        KP(row, pp) = kv;
+                    }
                     const T bj = (T)RK_ROW[6][row], ej = (T)RK_E[row];
 #pragma unroll
                     for (int k = 0; k < 3; ++k) { posB[k] += dyv[7 + k] * bj; posE[k] += dyv[7 + k] * ej; }
@@ -461,6 +479,7 @@ __global__ void __maxnreg__(255) rk45_attempt_kernel(const __grid_constant__ DCf
     }
 #undef KC
 #undef KS
+#undef KP
 }
 
 // ---- fixed-step modes: lock-step integrate kernel (no adaptivity, no divergence to rebalance) ----
@@ -1336,8 +1355,8 @@ static void prof_collect(FwHandle* h, bool has_init) {
     h->prof_steps += 1;
 }
 
-static const int NT_RK45_F64 = 32;     // 6*15*32*8 = 23040 B of stage storage per one-warp block: 9 blocks / SM
-static const int NT_RK45_F32 = 64;     // 6*15*64*4 = 23040 B
+static const int NT_RK45_F64 = 32;     // 6*16*32*8 = 24576 B of stage storage per one-warp block: 8 blocks / SM fit
+static const int NT_RK45_F32 = 64;     // 6*16*64*4 = 24576 B
 static const int W_REAL_FIELDS = FW_NK + 1 + 3 + 6 + FW_NY;   // f0, hinit, cmd, turb, ytmp
 
 template <typename T> static Scratch<T> make_scratch(void* real, int32_t* ints, size_t n) {
@@ -1389,7 +1408,7 @@ static void spare_refill(FwHandle* h, const DCfg<T>& c, const Spare<T>& P, cudaS
 // One env step = init kernel -> persistent attempt kernel -> head kernel (RK45), or rk4 kernel -> head kernel.
 template <typename T, bool TURB, int NT, bool PE>
 static int launch_rk45(FwHandle* h, const DCfg<T>& c, const Soa<T>& S, const Scratch<T>& W, const Spare<T>& P, const StepIO& io, cudaStream_t st) {
-    const size_t smem = (size_t)6 * FW_NS * NT * sizeof(T);
+    const size_t smem = (size_t)6 * FW_NP * 2 * NT * sizeof(T);
     auto k = rk45_attempt_kernel<T, TURB, NT, PE>;
     // per handle: function attributes and occupancy belong to the handle's device (one handle runs one instantiation)
     if (!h->att_blocks_per_sm) {
