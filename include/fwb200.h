@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define FW_ABI_VERSION 9
+#define FW_ABI_VERSION 10
 
 #define FW_NY 19        /* ODE state: quat[4] omega[3] pos[3] vel[3] act_value[3] act_rate[3]  (pyfly.py:1372-1389) */
 #define FW_NOBS 14      /* default observation vector (fixed_wing_config.json "observation.states")               */
@@ -81,10 +81,12 @@ enum FwEnvKind {
 /* observation entry kinds (fixed_wing.py:1149-1234) and the state indices an entry of kind STATE may name */
 /* general reward engine (fixed_wing.py:941-1111): factor classes/types and function classes */
 enum FwRewFactor { FW_RF_STATE_ERROR = 0, FW_RF_STATE_VALUE, FW_RF_ACTION_VALUE, FW_RF_ACTION_DELTA, FW_RF_ACTION_BOUND,
-                   FW_RF_SUCCESS, FW_RF_STEP, FW_RF_GOAL_PER_STATE, FW_RF_GOAL_ALL };
+                   FW_RF_SUCCESS, FW_RF_STEP, FW_RF_GOAL_PER_STATE, FW_RF_GOAL_ALL,
+                   FW_RF_STATE_INT_ERROR /* "int_error": windowed error integral, fixed_wing.py:1003-1012 */ };
 enum FwRewFunction { FW_FN_LINEAR = 0, FW_FN_EXPONENTIAL = 1, FW_FN_QUADRATIC = 2 };
 
-enum FwObsKind { FW_OBS_STATE = 0, FW_OBS_TARGET_ABS = 1, FW_OBS_TARGET_REL = 2, FW_OBS_ACTION = 3 };
+enum FwObsKind { FW_OBS_STATE = 0, FW_OBS_TARGET_ABS = 1, FW_OBS_TARGET_REL = 2, FW_OBS_ACTION = 3,
+                 FW_OBS_TARGET_INT = 4 /* value "integrator": windowed error integral, fixed_wing.py:1165-1180 */ };
 enum FwObsState { FW_S_ROLL = 0, FW_S_PITCH, FW_S_VA, FW_S_OMEGA_P, FW_S_OMEGA_Q, FW_S_OMEGA_R, FW_S_ALPHA, FW_S_BETA };
 
 enum FwTargetClass { FW_TGT_CONSTANT = 0, FW_TGT_COMPENSATE = 1, FW_TGT_LINEAR = 2, FW_TGT_SINUSOIDAL = 3 };   /* fixed_wing.py:1375-1452 */
@@ -227,6 +229,17 @@ typedef struct FwConfig {
     int32_t model_on, model_uniform;
     int32_t par_enabled[FW_NPARAM];
     double par_orig[FW_NPARAM], par_var[FW_NPARAM], par_clip[FW_NPARAM];
+
+    /* ---- error integrals and strided observation rows (fixed_wing.py:83, 1003-1012, 1129-1138, 1165-1180) ----
+     * integration_window W: the "int_error" reward value is sum(history["error"][-W:]) padded with (W - steps) copies of
+     * the first error while the episode is younger than W — and, python slicing being what it is, the sum of the WHOLE
+     * history for W == 0, the value every config of the reference tree carries.  The "integrator" observation of the row
+     * with lag i is sum(history["error"][-W-i:-i]) + (W - (steps - i)) * history["error"][0] while steps - i < W; the
+     * reset observation reads the history of the episode that just ENDED (the new one is installed after the
+     * observation is taken, fixed_wing.py:453-460), or error * W on the very first reset.  Errors live in the 50-deep
+     * ring of the end_error metric: W + lag_max <= FW_END_ERR_WINDOW - 1.
+     * obs_step s: row k of the observation has lag 1 + k s (range(1, length * s, s)); lag_max <= 5. ---- */
+    int32_t integration_window, obs_step;
 } FwConfig;
 
 typedef struct FwHandle FwHandle;
@@ -466,7 +479,7 @@ const char* fw_comm_last_error(void);
 int fw_measure_fma_peak(int32_t device, int32_t precision, double* tflops_out);
 
 /* Diagnostic: evaluates the straight-line FP64 math of the RHS hot loop elementwise (op 0: exp(x), 1: asin(x),
- * 2: atan2(y, x)); used by the tests to bound their error against the host libm. */
+ * 2: atan2(y, x), 3: 1/sqrt(x)); used by the tests to bound their error against the host libm. */
 int fw_debug_math(int32_t op, const double* x_dev, const double* y_dev, double* out_dev, int32_t n, void* stream);
 
 #ifdef __cplusplus

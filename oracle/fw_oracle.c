@@ -65,6 +65,9 @@ typedef struct FwoEnv {
     double* act_hist;  int n_act;  int act_is_f32;   /* history["action"], raw */
     double* cmd_hist;  int n_cmd;                    /* elevator/aileron/throttle .history["command"], [t][3] */
     double* err_hist;  int n_err;                    /* history["error"], [t][3] */
+    int obs_hist_n;    /* length of the history["error"] the observation sees: the running episode's in step(), the ENDED
+                          episode's inside reset() (self.history is replaced after the reset observation, fixed_wing.py:453-460) */
+    int has_history;   /* self.history is not None: false until the first reset has completed */
     uint8_t* goal_hist; int n_goal;                  /* history["goal"], [t][4] roll pitch Va all */
     double* st_hist;   int n_st;                     /* state .history of roll pitch Va p q r alpha beta, [t][8] */
     double* tgt_hist;  int n_tgt;                    /* history["target"], [t][3] */
@@ -712,6 +715,20 @@ static double window_feature_f32(const double* hist, int lo, int hi, int col, in
     return (double)s;
 }
 
+/* np.sum(history["error"][name][start:stop]), absolute indices clamped to [0, n] like a python slice; n = len(history) */
+static double err_slice_sum(const FwoEnv* e, int n, int k, int start, int stop) {
+    if (start < 0) start = 0;
+    if (stop < 0) stop = 0;
+    if (start > n) start = n;
+    if (stop > n) stop = n;
+    if (stop <= start) return 0.0;
+    double* tmp = (double*)malloc(sizeof(double) * (size_t)(stop - start));
+    for (int t = start; t < stop; ++t) tmp[t - start] = e->err_hist[(size_t)t * 3 + k];
+    const double s = np_sum_f64(tmp, stop - start);
+    free(tmp);
+    return s;
+}
+
 /* get_observation (fixed_wing.py:1113-1262), general layout: obs_len rows (newest first) of obs_n entries, entry kinds
  * state / target absolute / target relative / action, history rows clamped to the episode start with the
  * `init_noise` offset, optional (val - mean) / var normalisation. */
@@ -721,7 +738,9 @@ static void get_observation_generic(const FwoEnv* e, double* obs) {
     const double cur_state[8] = {e->h_roll, e->h_pitch, e->h_Va, e->h_omega[0], e->h_omega[1], e->h_omega[2],
                                  e->h_alpha, e->h_beta};
     const double actval[3] = {e->elev, e->ail, e->act_val[2]};
-    for (int i = 1; i <= L; ++i) {
+    const int W = c->integration_window, ostep = c->obs_step > 0 ? c->obs_step : 1;
+    for (int row = 0; row < L; ++row) {
+        const int i = 1 + row * ostep;        /* range(1, length * step, step) (fixed_wing.py:1129-1138) */
         int ie = i;
         double init_noise = 0;
         if (i > e->steps_count) {
@@ -750,6 +769,15 @@ static void get_observation_generic(const FwoEnv* e, double* obs) {
                 case FW_OBS_TARGET_REL:
                     val = (ie == 1) ? get_error(e, idx) : e->err_hist[(size_t)(e->n_err - ie) * 3 + idx];
                     break;
+                case FW_OBS_TARGET_INT:       /* fixed_wing.py:1165-1180 */
+                    if (!e->has_history) val = get_error(e, idx) * W;
+                    else {
+                        const int n = e->obs_hist_n;
+                        /* history[-W - i : -i]: a python slice (W + i > n clamps to the start) */
+                        val = err_slice_sum(e, n, idx, n - W - ie < 0 ? 0 : n - W - ie, n - ie);
+                        if (e->steps_count - ie < W) val += (W - (e->steps_count - ie)) * e->err_hist[idx];
+                    }
+                    break;
                 default: {
                     if (e->steps_count - ie < 0) {
                         val = actval[idx];
@@ -766,7 +794,7 @@ static void get_observation_generic(const FwoEnv* e, double* obs) {
             }
             val += init_noise;
             if (c->obs_normalize && c->obs_norm_flag[k]) { val -= c->obs_mean[k]; val /= c->obs_var[k]; }
-            obs[(i - 1) * n + k] = val;
+            obs[row * n + k] = val;
         }
     }
     add_obs_noise(e, obs, L * n);
@@ -854,6 +882,12 @@ static double get_reward_generic(FwoEnv* e, const double action[3], int success)
         switch (c->rew_class[i]) {
             case FW_RF_STATE_ERROR: val = get_error(e, c->rew_idx[i]); break;
             case FW_RF_STATE_VALUE: val = states[c->rew_idx[i]]; break;
+            case FW_RF_STATE_INT_ERROR: {     /* fixed_wing.py:1003-1012; [-0:] is the whole list */
+                const int W = c->integration_window, n = e->n_err;
+                val = err_slice_sum(e, n, c->rew_idx[i], (W == 0 || W > n) ? 0 : n - W, n);
+                if (e->steps_count < W) val += (W - e->steps_count) * e->err_hist[c->rew_idx[i]];
+                break;
+            }
             case FW_RF_ACTION_VALUE:
                 if (e->act_is_f32) { float sacc = 0; for (int j = 0; j < 3; ++j) sacc += fabsf((float)action[j]); val = sacc; }
                 else for (int j = 0; j < 3; ++j) val += fabs(action[j]);
@@ -1192,6 +1226,7 @@ void fwo_reset(FwoEnv* e, const double* state, const double* target, const doubl
     }
     e->h_roll = e->roll; e->h_pitch = e->pitch; e->h_Va = e->Va; e->h_alpha = e->alpha; e->h_beta = e->beta;
     for (int i = 0; i < 3; ++i) e->h_omega[i] = e->omega[i];
+    e->obs_hist_n = e->n_err;       /* the reset observation still sees the ended episode's error history */
     e->n_act = 0; e->n_cmd = 0; e->n_err = 0; e->n_goal = 0; e->act_is_f32 = 0;
     e->n_st = 0; e->n_tgt = 0;
     for (int k = 0; k < 3; ++k) { e->prev_shaping[k] = 0; e->has_prev_shaping[k] = 0; }
@@ -1209,6 +1244,7 @@ void fwo_reset(FwoEnv* e, const double* state, const double* target, const doubl
     get_observation(e, obs);
     for (int k = 0; k < 3; ++k) { e->err_hist[k] = get_error(e, k); e->tgt_hist[k] = e->target[k]; }
     e->n_err = 1; e->n_tgt = 1;
+    e->has_history = 1; e->obs_hist_n = 1;
     goal_status(e, e->goal_hist);
     e->n_goal = 1;
 }
@@ -1264,6 +1300,7 @@ void fwo_step(FwoEnv* e, const double action[3], int action_is_f32, double obs[F
             e->tgt_hist[(size_t)e->n_tgt * 3 + k] = e->target[k];
         }
         e->n_err++; e->n_tgt++;
+        e->obs_hist_n = e->n_err;
         get_observation(e, obs);
     } else {
         d = 1;

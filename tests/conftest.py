@@ -169,3 +169,24 @@ def model_env_config(distribution="gaussian"):
     cfg = default_env_config()
     cfg["simulator"]["model"] = dict(MODEL_BLOCK, distribution=distribution)
     return cfg
+
+
+def integrator_env_config(W, L, step):
+    """The configs of tests/golden/make_golden.py:gen_integrator: `integration_window` W, observation rows at lags
+    1, 1 + step, ..., "integrator" target entries and "int_error" reward factors."""
+    from tum_adlr_deep_reinforcement_learning_b200.config import default_env_config
+    cfg = default_env_config()
+    cfg["integration_window"] = W
+    ob = cfg["observation"]
+    ob["length"], ob["step"], ob["shape"] = L, step, "vector"
+    ob["states"] = [s_ for s_ in ob["states"] if s_["name"] not in ("alpha", "beta")]
+    for name in ("roll", "pitch", "Va"):
+        ob["states"].append({"name": name, "type": "target", "value": "integrator"})
+    for name, sc in zip(("roll", "pitch", "Va"), (40.0, 25.0, 300.0)):
+        cfg["reward"]["factors"].append({"name": name, "class": "state", "type": "int_error", "function_class": "linear",
+                                         "scaling": sc, "shaping": False, "max": 2.0, "sign": -1})
+    cfg["steps_max"] = 60
+    return cfg
+
+
+INTEGRATOR_CASES = [("traj_integrator_w4", 4, 3, 2), ("traj_integrator_w0", 0, 1, 1)]

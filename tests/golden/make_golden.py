@@ -1,7 +1,7 @@
 """Generate the golden fixtures in this directory by running the UNMODIFIED reference where it lies.
 
 TEST INFRASTRUCTURE — run here (the build container, where /root/reference is mounted), never on the
-GPU box.  Usage:  python tests/golden/make_golden.py [params|traj|turb|fail|full|pid|gae|vecnorm|ppo_update|curriculum|dryden|all]
+GPU box.  Usage:  python tests/golden/make_golden.py [integrator|params|traj|turb|fail|full|pid|gae|vecnorm|ppo_update|curriculum|dryden|all]
 
 Everything is recorded through the reference's public surface:
   FixedWingAircraft.reset(state=, target=, turbulence_noise=) / .step(action)
@@ -370,6 +370,40 @@ MOVING_TARGETS = [
     {"name": "pitch", "convert_to_radians": True, "low": -25, "high": 25, "delta": 45, "class": "sinusoidal",
      "amplitude_low": 3, "amplitude_high": 9, "period_low": 60, "period_high": 140, "bound": 5},
     {"name": "Va", "low": 15, "high": 28, "delta": 6, "class": "compensate", "bound": 2}]
+
+
+def integrator_env_config(cfg, W, L, step):
+    """Default config + error integrals: `integration_window` W, observation rows with lags 1, 1 + step, ... carrying the
+    default entries (without alpha / beta) and "integrator" targets, and "int_error" reward factors (general engine)."""
+    cfg["integration_window"] = W
+    ob = cfg["observation"]
+    ob["length"], ob["step"], ob["shape"] = L, step, "vector"
+    ob["states"] = [s_ for s_ in ob["states"] if s_["name"] not in ("alpha", "beta")]      # 12 + 3 entries (max 16)
+    for name in TARGET_KEYS:
+        ob["states"].append({"name": name, "type": "target", "value": "integrator"})
+    for name, sc in zip(TARGET_KEYS, (40.0, 25.0, 300.0)):
+        cfg["reward"]["factors"].append({"name": name, "class": "state", "type": "int_error", "function_class": "linear",
+                                         "scaling": sc, "shaping": False, "max": 2.0, "sign": -1})
+    cfg["steps_max"] = 60
+    return cfg
+
+
+def gen_integrator():
+    """`integrator` observations and `int_error` rewards (fixed_wing.py:1003-1012, 1165-1180) with a window of 4 and rows
+    at lags 1 / 3 / 5 (observation.step 2), and with the window of 0 every config of the reference tree carries (the sum
+    then runs over the WHOLE history).  ONE env object per fixture across all episodes: the reset observation of an
+    integrator entry reads the error history of the episode that just ended."""
+    import tempfile
+    for tag, W, L, step in (("w4", 4, 3, 2), ("w0", 0, 1, 1)):
+        cfg = integrator_env_config(json.load(open(refshim.GYM_CONFIG)), W, L, step)
+        with tempfile.NamedTemporaryFile("w", suffix=".json", delete=False) as f:
+            json.dump(cfg, f)
+        env = make_env(False, config_path=f.name)
+        env.np_random = FixedDraws()
+        rs = np.random.RandomState(515 + W)
+        out = run_episodes(env, 5, 45, rs, False, wind_mag=3.0, action_amp=1.4)
+        np.savez_compressed(os.path.join(HERE, "traj_integrator_%s.npz" % tag), **out)
+        print(tag, "obs dim", out["obs"].shape[-1], "n_valid", out["n_valid"], "reward range", out["reward"].min(), out["reward"].max())
 
 
 def gen_targets():
@@ -909,7 +943,7 @@ def gen_dryden():
 
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
-    jobs = {"waypoint": gen_waypoint, "targets": gen_targets, "resample": gen_resample, "reward": gen_reward, "cnn": gen_cnn, "params": gen_params, "traj": gen_traj, "turb": gen_turb, "turb_moderate": gen_turb_moderate, "model": gen_model, "fail": gen_fail, "full": gen_full,
+    jobs = {"integrator": gen_integrator, "waypoint": gen_waypoint, "targets": gen_targets, "resample": gen_resample, "reward": gen_reward, "cnn": gen_cnn, "params": gen_params, "traj": gen_traj, "turb": gen_turb, "turb_moderate": gen_turb_moderate, "model": gen_model, "fail": gen_fail, "full": gen_full,
             "pid": gen_pid, "gae": gen_gae, "vecnorm": gen_vecnorm, "ppo_update": gen_ppo_update, "sac_update": gen_sac_update, "curriculum": gen_curriculum, "dryden": gen_dryden}
     for name, fn in jobs.items():
         if what in (name, "all"):

@@ -64,13 +64,22 @@ def test_overrides_follow_reference_semantics():
 
 def test_unsupported_configs_fail_loudly():
     with pytest.raises(NotImplementedError):
-        C.build_config(config_kw={"observation": {"step": 2}})
-    with pytest.raises(NotImplementedError):
         C.build_config(config_kw={"target": {"states": {0: {"class": "attitude_angular"}}}})
     with pytest.raises(NotImplementedError):
-        C.build_config(config_kw={"reward": {"factors": {0: {"type": "int_error"}}}})
-    with pytest.raises(NotImplementedError):
         C.build_config(config_kw={"observation": {"states": {0: {"name": "position_n"}}}})
+    with pytest.raises(NotImplementedError):      # rows reach 1 + 2 * 3 = 7 steps back: the history rings hold 5
+        C.build_config(config_kw={"observation": {"step": 3, "length": 3}})
+    with pytest.raises(NotImplementedError):      # window + lag beyond the 50-deep error ring
+        C.build_config(config_kw={"integration_window": 49, "reward": {"factors": {0: {"type": "int_error"}}}})
+
+
+def test_error_integral_and_strided_row_configs_build():
+    c = C.build_config(config_kw={"observation": {"step": 2, "length": 3}})
+    assert (c.obs_generic, c.obs_len, c.obs_step) == (1, 3, 2)
+    c = C.build_config(config_kw={"integration_window": 7, "reward": {"factors": {0: {"type": "int_error"}}},
+                                  "observation": {"states": {6: {"value": "integrator"}}}})
+    assert c.rew_generic == 1 and c.rew_class[0] == 9 and c.integration_window == 7
+    assert c.obs_generic == 1 and c.obs_kind[6] == 4 and c.obs_idx[6] == 0
 
 
 def test_general_env_head_configs_build():

@@ -245,6 +245,52 @@ def test_general_reward_engine(cuda_device):
     env.close()
 
 
+def test_error_integrals_and_strided_observation_rows(cuda_device):
+    """`integrator` observation entries, `int_error` reward factors (fixed_wing.py:1003-1012, 1165-1180) and
+    observation.step = 2 on the CUDA path: (a) the live-reference fixtures replayed on a ONE-env handle across episodes —
+    the reset observation of an integrator entry reads the error history of the episode that just ended (error * window
+    on the very first reset); (b) 512 envs with Philox resets, turbulence and auto-reset against the oracle, where the
+    value of the ended episode is added to the precomputed next-episode observation."""
+    import torch
+    from conftest import INTEGRATOR_CASES, integrator_env_config
+    from oracle import fw_oracle as O
+    from tum_adlr_deep_reinforcement_learning_b200 import batched as bt
+    from tum_adlr_deep_reinforcement_learning_b200.config import build_config
+    for name, W, L, step in INTEGRATOR_CASES:
+        g = load_golden(name)
+        cfg = build_config(env_cfg=integrator_env_config(W, L, step), sim_config_kw={"turbulence": False}, obs_init_noise=0.25)
+        env = bt.BatchedFixedWing(1, cfg=cfg)
+        assert env.obs_dim == L * 15
+        env.enable_f64_outputs()
+        for ep in range(g["actions"].shape[0]):
+            env.reset(state=g["init_state"][ep:ep + 1], target=g["init_target"][ep:ep + 1])
+            assert np.abs(env.obs64.cpu().numpy()[0] - g["obs0"][ep]).max() < 1e-12, (name, ep)
+            for t in range(int(g["n_valid"][ep])):
+                env.step(torch.as_tensor(g["actions"][ep:ep + 1, t]).cuda().contiguous(), auto_reset=False)
+                assert _rel(env.obs64.cpu().numpy()[0], g["obs"][ep, t]).max() < RTOL_F64, (name, ep, t)
+                r = float(env.rew64.cpu().numpy()[0])
+                assert abs(r - g["reward"][ep, t]) < 1e-9 * max(1.0, abs(g["reward"][ep, t])), (name, ep, t)
+        env.close()
+        ecfg = integrator_env_config(W, L, step)
+        ecfg["steps_max"] = 14
+        cfg = build_config(env_cfg=ecfg, sim_config_kw={"turbulence": True}, seed=33)
+        n = 512
+        env = bt.BatchedFixedWing(n, cfg=cfg)
+        env.enable_f64_outputs()
+        env.reset()
+        ob = O.OracleBatch(cfg, n)
+        assert _rel(env.obs64.cpu().numpy(), ob.reset()).max() < 1e-12
+        rs = np.random.RandomState(5)
+        for t in range(40):                       # almost three episodes of 14 steps, plus early failures
+            a = rs.uniform(-1.5, 1.5, (n, 3)).astype(np.float32)
+            env.step(torch.as_tensor(a).cuda(), auto_reset=True)
+            o_ref, r_ref, d_ref = ob.step(a)
+            assert np.array_equal(env.done.cpu().numpy(), d_ref), (name, t)
+            assert _rel(env.obs64.cpu().numpy(), o_ref).max() < RTOL_F64, (name, t)
+            assert _rel(env.rew64.cpu().numpy(), r_ref).max() < RTOL_F64, (name, t)
+        env.close()
+
+
 def test_moving_target_classes(cuda_device):
     """linear / sinusoidal targets on the CUDA path: the live-reference fixture (fixed draws), then Philox sampling with
     on_success = "new" resampling against the oracle."""

@@ -232,6 +232,27 @@ def test_oracle_general_reward_engine():
                 assert done == bool(g["done"][ep, t])
 
 
+def test_oracle_error_integrals_and_strided_observation_rows():
+    """`integrator` observation entries, `int_error` reward factors (fixed_wing.py:1003-1012, 1165-1180) and
+    observation.step = 2 against live-reference runs: window 4 with rows at lags 1 / 3 / 5, and the window of 0 that every
+    config of the reference tree carries (the reward integral then runs over the whole history).  ONE env object across
+    the episodes: the reset observation reads the error history of the episode that just ended (None on the first)."""
+    from conftest import INTEGRATOR_CASES, integrator_env_config
+    for name, W, L, step in INTEGRATOR_CASES:
+        g = load_golden(name)
+        cfg = build_config(env_cfg=integrator_env_config(W, L, step), sim_config_kw={"turbulence": False}, obs_init_noise=0.25)
+        assert cfg.obs_generic == 1 and cfg.rew_generic == 1 and (cfg.obs_len, cfg.obs_n, cfg.obs_step) == (L, 15, step)
+        env = O.OracleEnv(cfg)
+        for ep in range(g["actions"].shape[0]):
+            obs = env.reset(g["init_state"][ep], g["init_target"][ep])
+            assert np.abs(obs - g["obs0"][ep]).max() < 1e-12, (name, ep)
+            for t in range(int(g["n_valid"][ep])):
+                obs, rew, done, term = env.step(g["actions"][ep, t])
+                assert _rel(obs, g["obs"][ep, t]).max() < 1e-9, (name, ep, t)
+                assert abs(rew - g["reward"][ep, t]) < 1e-9 * max(1.0, abs(g["reward"][ep, t])), (name, ep, t)
+                assert done == bool(g["done"][ep, t])
+
+
 def test_oracle_moving_target_classes():
     """Target classes linear / sinusoidal with Va compensate on a sinusoidal pitch target, against a live-reference run
     whose env-level RNG was replaced by fixed draws u (tests/golden/make_golden.py:gen_targets)."""

@@ -20,7 +20,7 @@ import numpy as np
 
 _DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
 
-FW_ABI_VERSION = 9
+FW_ABI_VERSION = 10
 FW_NY, FW_NOBS, FW_NACT, FW_NSTATE_INJECT, FW_NMETRIC = 19, 14, 3, 21, 28
 FW_F64, FW_F32 = 0, 1
 FW_INT_RK45_SCIPY, FW_INT_RK4_FIXED = 0, 1
@@ -83,7 +83,7 @@ class FwConfig(ctypes.Structure):
            ("env_kind", _i), ("turb_block_len", _i), ("wp_goal_bound", _d * 3), ("wp_rew_range", _d * 3),
            ("seed", ctypes.c_uint64), ("env_id_offset", ctypes.c_int64),
            ("model_on", _i), ("model_uniform", _i), ("par_enabled", _i * 48), ("par_orig", _d * 48), ("par_var", _d * 48),
-           ("par_clip", _d * 48)])
+           ("par_clip", _d * 48), ("integration_window", _i), ("obs_step", _i)])
 
 
 def _var(name, **kw):
@@ -508,6 +508,8 @@ def build_config(env_cfg=None, sim_cfg=None, config_kw=None, sim_config_kw=None,
             c.rew_window[i] = int(f.get("window_size", 0) or 0)
             if cls == "state" and typ == "error":
                 c.rew_class[i], c.rew_idx[i] = 0, TARGET_STATES.index(f["name"])
+            elif cls == "state" and typ == "int_error":
+                c.rew_class[i], c.rew_idx[i] = 9, TARGET_STATES.index(f["name"])
             elif cls == "state" and typ == "value":
                 if f["name"] not in state_names:
                     raise NotImplementedError("reward on state %r" % f["name"])
@@ -537,12 +539,22 @@ def build_config(env_cfg=None, sim_cfg=None, config_kw=None, sim_config_kw=None,
     obs = env["observation"]
     noise = obs.get("noise") or {}
     c.obs_noise_mean, c.obs_noise_std = float(noise.get("mean", 0) or 0), float(noise.get("var", 0) or 0)
-    if obs.get("step", 1) != 1:
-        raise NotImplementedError("observation.step != 1")
     L = int(obs.get("length", 1))
+    ostep = int(obs.get("step", 1) or 1)
     states = obs["states"]
     if L > 5 or len(states) > 16:
         raise NotImplementedError("observation.length > 5 or more than 16 entries per row")
+    # row k has lag 1 + k * step (range(1, length * step, step), fixed_wing.py:1129-1138); history rows reach 5 steps back
+    lag_max = 1 + (L - 1) * ostep
+    if ostep < 1 or lag_max > 5:
+        raise NotImplementedError("observation rows reach %d steps back (length %d, step %d): at most 5" % (lag_max, L, ostep))
+    c.obs_step = ostep
+    W = int(env.get("integration_window", 0) or 0)
+    c.integration_window = W
+    uses_int = any(s_["type"] == "target" and s_.get("value") == "integrator" for s_ in states) or any(
+        f.get("class") == "state" and f.get("type") == "int_error" for f in rew["factors"])
+    if uses_int and (W < 0 or W + lag_max > 49):
+        raise NotImplementedError("integration_window %d + observation lag %d exceed the 50-deep error ring" % (W, lag_max))
     names = [(s_["name"], s_["type"]) for s_ in states]
     default_layout = [("roll", "state"), ("pitch", "state"), ("Va", "state"), ("omega_p", "state"),
                       ("omega_q", "state"), ("omega_r", "state"), ("roll", "target"), ("pitch", "target"),
@@ -550,7 +562,7 @@ def build_config(env_cfg=None, sim_cfg=None, config_kw=None, sim_config_kw=None,
                       ("aileron", "action"), ("throttle", "action")]
     c.obs_normalize = int(bool(obs.get("normalize", False)))
     c.obs_len, c.obs_n = L, len(states)
-    c.obs_generic = int(not (L == 1 and names == default_layout and not c.obs_normalize
+    c.obs_generic = int(not (L == 1 and ostep == 1 and names == default_layout and not c.obs_normalize
                              and all(s_.get("value", "absolute") == "absolute" for s_ in states if s_["type"] == "target")))
     c.obs_init_noise = float("nan") if obs_init_noise is None else float(obs_init_noise)
     state_idx = {"roll": 0, "pitch": 1, "Va": 2, "omega_p": 3, "omega_q": 4, "omega_r": 5, "alpha": 6, "beta": 7}
@@ -565,9 +577,9 @@ def build_config(env_cfg=None, sim_cfg=None, config_kw=None, sim_config_kw=None,
             c.obs_kind[e], c.obs_idx[e] = 0, state_idx[s_["name"]]
         elif kind == "target":
             value = s_.get("value", "absolute")
-            if value not in ("absolute", "relative"):
-                raise NotImplementedError("target observation value %r" % value)
-            c.obs_kind[e], c.obs_idx[e] = (1 if value == "absolute" else 2), TARGET_STATES.index(s_["name"])
+            if value not in ("absolute", "relative", "integrator"):
+                raise ValueError("Unexpected observation variable target value type: %r" % value)
+            c.obs_kind[e], c.obs_idx[e] = {"absolute": 1, "relative": 2, "integrator": 4}[value], TARGET_STATES.index(s_["name"])
         elif kind == "action":
             c.obs_kind[e], c.obs_idx[e] = 3, act_names.index(s_["name"])
             c.obs_window[e] = int(s_.get("window_size", 1))
@@ -592,7 +604,7 @@ def build_config(env_cfg=None, sim_cfg=None, config_kw=None, sim_config_kw=None,
         c.obs_var[e] = s_["var"] if s_.get("var") is not None else ((hi - lo) / 16 if finite else 1.0)
         c.obs_norm_flag[e] = int(bool(s_.get("norm", True)))
     c.obs_act_window = max(windows)
-    if max(c.obs_act_window, c.rew_delta_window) + (L - 1) > 9:
+    if max(c.obs_act_window, c.rew_delta_window) + (lag_max - 1) > 9:
         raise NotImplementedError("action windows + observation length exceed the 8-deep action ring")
     c.rise_low, c.rise_high = 0.1, 0.9
     for m in env.get("metrics", []):

@@ -123,6 +123,7 @@ template <typename T> struct DCfg {
     int obs_generic, obs_len, obs_n, obs_normalize;
     int obs_kind[FW_OBS_ENTRIES_MAX], obs_idx[FW_OBS_ENTRIES_MAX], obs_window[FW_OBS_ENTRIES_MAX], obs_norm_flag[FW_OBS_ENTRIES_MAX];
     T obs_mean[FW_OBS_ENTRIES_MAX], obs_var[FW_OBS_ENTRIES_MAX], obs_init_noise;
+    int integration_window, obs_step, obs_has_int;
     unsigned long long seed;
     long long env_id_offset;
 };
@@ -827,6 +828,27 @@ __device__ __forceinline__ void write_obs(const T* o, int dim, int env, float* o
     if (obs64) for (int j = 0; j < dim; ++j) obs64[(size_t)env * dim + j] = (double)o[j];
 }
 
+// sum of history["error"][name][start:stop] (absolute entry indices, clamped like a python slice to [0, len]) from the
+// 50-deep error ring of the end_error metric, oldest first.  Callers keep stop - start + lag below the ring depth.
+template <typename T>
+__device__ __noinline__ T err_ring_sum(const Soa<T>& S, int env, int k, int start, int stop, int len) {
+    if (start < 0) start = 0;
+    if (stop > len) stop = len;
+    T s = 0;
+#pragma unroll 1
+    for (int t = start; t < stop; ++t) s += S.err_ring[(size_t)((t % FW_END_ERR_WINDOW) * 3 + k) * S.n + env];
+    return s;
+}
+
+// The value an "integrator" observation entry takes in the reset observation that follows an episode whose error history
+// has `len` entries and first entry e0: every row is clamped to lag 1 with steps_count = 0 (fixed_wing.py:1141-1180), so
+// sum(history[-W-1:-1]) + (W + 1) * history[0].
+template <typename T>
+__device__ __forceinline__ T integrator_reset_value(const DCfg<T>& c, const Soa<T>& S, int env, int k, int len, T e0) {
+    const int W = c.integration_window;
+    return err_ring_sum<T>(S, env, k, len - W - 1, len - 1, len) + (T)(W + 1) * e0;
+}
+
 // get_reward (fixed_wing.py:941-1111), the general engine: any list of factors with linear / exponential / quadratic
 // function classes, shaping and plain parts per term, absolute or potential form.  Out of line: the default factor
 // family has its own straight-line code in the head kernel.
@@ -842,7 +864,16 @@ __device__ __noinline__ T generic_reward(const DCfg<T>& c, const Soa<T>& S, int 
         const int cls = c.rew_class[i];
         if (cls == FW_RF_STATE_ERROR) val = eg[c.rew_idx[i]];
         else if (cls == FW_RF_STATE_VALUE) val = st8[c.rew_idx[i]];
-        else if (cls == FW_RF_ACTION_VALUE) {
+        else if (cls == FW_RF_STATE_INT_ERROR) {
+            // history["error"] holds `steps` entries here (this step's is appended after the reward); [-0:] is the whole
+            // list, whose sum the metrics already carry (fixed_wing.py:1003-1012)
+            const int W = c.integration_window, k = c.rew_idx[i];
+            if (W == 0) val = S.r[(RF_ESUM + k) * n + env];
+            else {
+                val = err_ring_sum<T>(S, env, k, steps - W, steps, steps);
+                if (steps < W) val += (T)(W - steps) * S.r[(RF_E0 + k) * n + env];
+            }
+        } else if (cls == FW_RF_ACTION_VALUE) {
             if (act_f32) { float sa = 0.f; for (int j = 0; j < 3; ++j) sa += fabsf((float)a_raw[j]); val = (T)sa; }
             else for (int j = 0; j < 3; ++j) val += M<T>::fabs(a_raw[j]);
         } else if (cls == FW_RF_ACTION_DELTA) {
@@ -923,7 +954,8 @@ template <typename T>
 __device__ __noinline__ void generic_observation(const DCfg<T>& c, const Soa<T>& S, int env, int steps, bool push,
                                                  const T (&cur)[14] /* 8 states, 3 targets, 3 errors */,
                                                  const T (&a_raw)[3], bool act_f32, const T (&cmd_in)[3],
-                                                 const T (&actval)[3], unsigned long long episode, T* o) {
+                                                 const T (&actval)[3], unsigned long long episode, T* o,
+                                                 const T* int_reset /* reset observation: integrator values, else null */) {
     const int n = S.n, L = c.obs_len, ne = c.obs_n;
     T* r = S.r + env;
     T hist[4][14], gact[24], gcmd[24];
@@ -933,8 +965,10 @@ __device__ __noinline__ void generic_observation(const DCfg<T>& c, const Soa<T>&
 #pragma unroll 1
     for (int k = 0; k < 24; ++k) { gact[k] = r[(RF_GACT + k) * n]; gcmd[k] = r[(RF_GCMD + k) * n]; }
     const int N = steps;                                     // number of actions so far, the current one included
+    const int hist_len = steps + (push ? 1 : 0);             // len(history["error"]) the observation sees
 #pragma unroll 1
-    for (int i = 1; i <= L; ++i) {
+    for (int row = 0; row < L; ++row) {
+        const int i = 1 + row * c.obs_step;                  // range(1, length * step, step) (fixed_wing.py:1129-1138)
         int ie = i;
         T init_noise = 0;
         if (i > steps) {
@@ -953,7 +987,14 @@ __device__ __noinline__ void generic_observation(const DCfg<T>& c, const Soa<T>&
         for (int k = 0; k < ne; ++k) {
             const int idx = c.obs_idx[k], kind = c.obs_kind[k];
             T val;
-            if (kind != FW_OBS_ACTION) {
+            if (kind == FW_OBS_TARGET_INT) {
+                if (int_reset) val = int_reset[idx];
+                else {
+                    const int W = c.integration_window;
+                    val = err_ring_sum<T>(S, env, idx, hist_len - W - ie, hist_len - ie, hist_len);
+                    if (steps - ie < W) val += (T)(W - (steps - ie)) * r[(RF_E0 + idx) * n];
+                }
+            } else if (kind != FW_OBS_ACTION) {
                 const int q = (kind == FW_OBS_STATE) ? idx : (kind == FW_OBS_TARGET_ABS ? 8 + idx : 11 + idx);
                 val = (ie == 1) ? cur[q] : hist[ie - 2][q];
             } else if (steps - ie < 0) {
@@ -977,7 +1018,7 @@ __device__ __noinline__ void generic_observation(const DCfg<T>& c, const Soa<T>&
             }
             val += init_noise;
             if (c.obs_normalize && c.obs_norm_flag[k]) { val -= c.obs_mean[k]; val /= c.obs_var[k]; }
-            o[(i - 1) * ne + k] = val;
+            o[row * ne + k] = val;
         }
     }
     if (c.obs_noise_std > (T)0 || c.obs_noise_mean != (T)0) add_obs_noise<T>(c, env_seed(S, env), c.env_id_offset + env, episode, steps, o, L * ne);
@@ -990,6 +1031,25 @@ __device__ __noinline__ void generic_observation(const DCfg<T>& c, const Soa<T>&
         for (int k = 23; k >= 3; --k) { r[(RF_GACT + k) * n] = gact[k - 3]; r[(RF_GCMD + k) * n] = gcmd[k - 3]; }
         for (int j = 0; j < 3; ++j) { r[(RF_GACT + j) * n] = a_raw[j]; r[(RF_GCMD + j) * n] = cmd_in[j]; }
     }
+}
+
+// Adds the integrator values of the ended episode to the precomputed reset observation of `env` (whose integrator
+// entries were computed as 0): (0 - mean) / var + v / var for a normalised entry, every row alike.
+template <typename T, typename SpareT>
+__device__ __noinline__ void patch_integrator_reset_obs(const DCfg<T>& c, const SpareT& P, int env, int odim,
+                                                        const T (&v)[3], float* obs, double* obs64) {
+#pragma unroll 1
+    for (int row = 0; row < c.obs_len; ++row)
+#pragma unroll 1
+        for (int k = 0; k < c.obs_n; ++k) {
+            if (c.obs_kind[k] != FW_OBS_TARGET_INT) continue;
+            double add = (double)v[c.obs_idx[k]];
+            if (c.obs_normalize && c.obs_norm_flag[k]) add /= (double)c.obs_var[k];
+            const size_t q = (size_t)env * odim + row * c.obs_n + k;
+            const double val = P.obs64[q] + add;
+            if (obs) obs[q] = (float)val;
+            if (obs64) obs64[q] = val;
+        }
 }
 
 // What the RHS reads, from the FW_NPARAM base parameters of one env (FwConfig order: mass 0, S_wing 5, b 6, c 7, S_prop 8,
@@ -1050,9 +1110,22 @@ __device__ __noinline__ void sample_env_params(const DCfg<T>& c, const Soa<T>& S
 // FixedWingAircraft.reset -> PyFly.reset for one env; writes the full SoA row and the reset observation.
 template <typename T>
 __device__ void reset_env(const DCfg<T>& c, const Soa<T>& S, int env, const double* state_in, const double* target_in,
-                          float* obs, double* obs64) {
+                          float* obs, double* obs64, bool live = false) {
     const int n = S.n;
     const unsigned long long episode = (unsigned long long)(uint32_t)S.i[IF_EPISODE * n + env] + 1ull;
+    // `live`: S is the running env (fw_reset), not a precomputed next-episode row.  The reset observation's "integrator"
+    // entries read the error history of the episode that is being replaced (fixed_wing.py:453-460, 1165-1180): taken
+    // from the live ring before the row is rewritten; a precomputed row carries 0 there and head_kernel adds the value
+    // when the row is consumed.  An env that was never reset has no history: error * window, filled in below.
+    T int_reset[3] = {0, 0, 0};
+    const bool int_none = live && episode == 1ull;
+    if (live && c.obs_generic && c.obs_has_int && !int_none) {
+        const int steps_prev = S.i[IF_STEPS * n + env];
+        const int failed = steps_prev > 0 && S.ep_term[env] >= FW_TERM_OMEGA_P;        // a failed step appends no error entry
+        const int len = steps_prev + (failed ? 0 : 1);
+#pragma unroll 1
+        for (int k = 0; k < 3; ++k) int_reset[k] = integrator_reset_value<T>(c, S, env, k, len, S.r[(RF_E0 + k) * n + env]);
+    }
     const long long gid = c.env_id_offset + env;
     const ResetCfg<T>& rc = *S.rc;
     const unsigned long long seed = rc.seed;
@@ -1201,7 +1274,9 @@ __device__ void reset_env(const DCfg<T>& c, const Soa<T>& S, int env, const doub
         for (int k = 0; k < 24; ++k) { r[(RF_GACT + k) * n] = 0; r[(RF_GCMD + k) * n] = 0; }
         T og[FW_NOBS_MAX];
         const T zero3[3] = {0, 0, 0};
-        generic_observation<T>(c, S, env, 0, false, cur, zero3, false, zero3, av, episode, og);
+        if (int_none)
+            for (int k = 0; k < 3; ++k) int_reset[k] = e[k] * (T)c.integration_window;
+        generic_observation<T>(c, S, env, 0, false, cur, zero3, false, zero3, av, episode, og, int_reset);
         write_obs(og, obs_dim(c), env, obs, obs64);
         return;
     }

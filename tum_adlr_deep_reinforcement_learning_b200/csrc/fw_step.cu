@@ -139,7 +139,7 @@ __global__ void reset_kernel(const __grid_constant__ DCfg<T> c, const Soa<T> S, 
     if (env >= S.n) return;
     if (mask && !mask[env]) return;
     if (c.env_kind == FW_ENV_WAYPOINT) { wp_reset_env<T>(c, S, env, obs, obs64); return; }
-    reset_env<T>(c, S, env, state_in, target_in, obs, obs64);
+    reset_env<T>(c, S, env, state_in, target_in, obs, obs64, true);
     if (P.on) make_spare<T>(c, S, P, env);
 }
 
@@ -868,7 +868,7 @@ __global__ void __launch_bounds__(64, 8) head_kernel(const __grid_constant__ DCf
         const T cur[14] = {roll, pitch, Va, om_obs[0], om_obs[1], om_obs[2], alpha, beta, tgt[0], tgt[1], tgt[2],
                            e_cur[0], e_cur[1], e_cur[2]};
         const T actval[3] = {(y[13] + y[14]) / (T)2, (-y[13] + y[14]) / (T)2, y[15]};
-        generic_observation<T>(c, S, env, steps, !fail, cur, a_raw, act_f32, cmd_in, actval, episode, og);
+        generic_observation<T>(c, S, env, steps, !fail, cur, a_raw, act_f32, cmd_in, actval, episode, og, (const T*)nullptr);
         obs_out = og;
         odim = c.obs_len * c.obs_n;
     }
@@ -937,7 +937,22 @@ __global__ void __launch_bounds__(64, 8) head_kernel(const __grid_constant__ DCf
     // side stream while the next step integrates)
     const bool take = done && io.auto_reset;
     if (take && io.term_obs) write_obs(obs_out, odim, env, io.term_obs, (double*)nullptr);
+    // "integrator" observation entries of the RESET observation read the error history of the episode that just ended
+    // (fixed_wing.py:453-460, 1165-1180): the precomputed row holds them as 0 and they are added here from the live ring
+    T int_reset[3] = {0, 0, 0};
+    if constexpr (GENERIC) {
+        if (take && c.obs_has_int) {
+#pragma unroll 1
+            for (int k = 0; k < 3; ++k) int_reset[k] = integrator_reset_value<T>(c, S, env, k, n_err, e0v[k]);
+        }
+    }
     take_spare_warp<T>(S, P, take, env, odim, io.obs, io.obs64);
+    if constexpr (GENERIC) {
+        if (c.obs_has_int) {
+            __syncwarp(__activemask());          // the cooperative copy of the reset observation is done
+            if (take) patch_integrator_reset_obs<T>(c, P, env, odim, int_reset, io.obs, io.obs64);
+        }
+    }
     if (take) {
         P.list[(size_t)parity * n + atomicAdd(P.count + parity, 1)] = env;
         if (io.info) {
@@ -1267,6 +1282,10 @@ template <typename T> static void convert_cfg(const FwConfig& f, DCfg<T>& d) {
         d.obs_kind[k] = f.obs_kind[k]; d.obs_idx[k] = f.obs_idx[k]; d.obs_window[k] = f.obs_window[k];
         d.obs_norm_flag[k] = f.obs_norm_flag[k]; CP(obs_mean[k]); CP(obs_var[k]);
     }
+    d.integration_window = f.integration_window;
+    d.obs_step = f.obs_step > 0 ? f.obs_step : 1;
+    d.obs_has_int = 0;
+    for (int k = 0; k < f.obs_n && f.obs_generic; ++k) d.obs_has_int |= (f.obs_kind[k] == FW_OBS_TARGET_INT);
 #undef CP
     d.seed = f.seed;
     d.env_id_offset = f.env_id_offset;
