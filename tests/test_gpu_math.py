@@ -18,14 +18,17 @@ def test_hot_loop_math_within_2_ulp(cuda_device):
     x = np.concatenate([rs.uniform(-160, 160, n // 2), rs.uniform(-2, 2, n // 2)])          # M * alpha, |alpha| <= pi
     got = debug_math(0, torch.as_tensor(x).cuda()).cpu().numpy()
     assert _ulp_err(got, np.exp(x)).max() <= 2.0
+    assert np.array_equal(got, debug_math(4, torch.as_tensor(x).cuda()).cpu().numpy())      # immediate-coefficient build
     x = np.concatenate([rs.uniform(-0.5, 0.5, n // 2), rs.uniform(-1, 1, n // 2), [0.0, 0.5, -0.5, 1.0, -1.0, 1e-300]])
     got = debug_math(1, torch.as_tensor(x).cuda()).cpu().numpy()
+    assert np.array_equal(got, debug_math(5, torch.as_tensor(x).cuda()).cpu().numpy())
     ref = np.arcsin(x)
     nz = ref != 0
     assert _ulp_err(got[nz], ref[nz]).max() <= 2.0 and np.all(got[~nz] == 0)
     xs = np.concatenate([rs.uniform(-30, 30, n), rs.standard_normal(n) * 1e-3, [0.0, 1.0, -1.0, 0.0, -2.0, 3.0]])
     ys = np.concatenate([rs.uniform(-30, 30, n), rs.uniform(-30, 30, n), [0.0, 0.0, 0.0, 2.0, 0.0, 3.0]])
     got = debug_math(2, torch.as_tensor(xs).cuda(), torch.as_tensor(ys).cuda()).cpu().numpy()
+    assert np.array_equal(got, debug_math(6, torch.as_tensor(xs).cuda(), torch.as_tensor(ys).cuda()).cpu().numpy())
     ref = np.arctan2(ys, xs)
     nz = ref != 0
     assert _ulp_err(got[nz], ref[nz]).max() <= 2.0

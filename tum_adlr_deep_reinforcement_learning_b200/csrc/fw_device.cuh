@@ -37,9 +37,9 @@ template <> struct M<double> {
     static __device__ __forceinline__ double rsqrt(double x) { return ::rsqrt(x); }
     static __device__ __forceinline__ double rsqrt_hot(double x) { return rsqrt_fast(x); }
     // straight-line versions for the RHS hot loop (fw_math.cuh)
-    static __device__ __forceinline__ double atan2_hot(double y, double x) { return atan2_bf(y, x); }
-    static __device__ __forceinline__ double asin_hot(double x) { return asin_bf(x); }
-    static __device__ __forceinline__ double exp_hot(double x) { return exp_bf(x); }
+    template <bool CT = true> static __device__ __forceinline__ double atan2_hot(double y, double x) { return atan2_bf<CT>(y, x); }
+    template <bool CT = true> static __device__ __forceinline__ double asin_hot(double x) { return asin_bf<CT>(x); }
+    template <bool CT = true> static __device__ __forceinline__ double exp_hot(double x) { return exp_bf<CT>(x); }
     static __device__ __forceinline__ double rcp_hot(double x) { return rcp_fast(x); }
     static __device__ __forceinline__ double atan2(double y, double x) { return ::atan2(y, x); }
     static __device__ __forceinline__ double asin(double x) { return ::asin(x); }
@@ -61,11 +61,11 @@ template <> struct M<float> {
     static __device__ __forceinline__ float sqrt(float x) { return ::sqrtf(x); }
     static __device__ __forceinline__ float rsqrt(float x) { return ::rsqrtf(x); }
     static __device__ __forceinline__ float rsqrt_hot(float x) { return ::rsqrtf(x); }
-    static __device__ __forceinline__ float atan2_hot(float y, float x) { return ::atan2f(y, x); }
+    template <bool CT = true> static __device__ __forceinline__ float atan2_hot(float y, float x) { return ::atan2f(y, x); }
     // sin(beta) = a1 * rsqrt(|a|^2) can exceed 1 by a float32 rounding when the sideslip reaches 90 degrees: clamp, as
     // asin_bf does for its own argument, instead of handing NaN to the forces
-    static __device__ __forceinline__ float asin_hot(float x) { return ::asinf(fminf(fmaxf(x, -1.0f), 1.0f)); }
-    static __device__ __forceinline__ float exp_hot(float x) { return ::expf(x); }
+    template <bool CT = true> static __device__ __forceinline__ float asin_hot(float x) { return ::asinf(fminf(fmaxf(x, -1.0f), 1.0f)); }
+    template <bool CT = true> static __device__ __forceinline__ float exp_hot(float x) { return ::expf(x); }
     static __device__ __forceinline__ float rcp_hot(float x) { return 1.0f / x; }
     static __device__ __forceinline__ float atan2(float y, float x) { return ::atan2f(y, x); }
     static __device__ __forceinline__ float asin(float x) { return ::asinf(x); }
@@ -306,7 +306,7 @@ __device__ __forceinline__ void rot_euler_apply(T phi, T th, T psi, const T v[3]
 // disabled ControlVariables reset to 0, pyfly.py:359-363).  Returns 0 or a FwTermCode.
 // PE: the aircraft parameters come from the env's column of S.par (`pe` = S.par + env, stride `pn`) instead of the
 // warp-uniform constant bank; with PE = false PRM(x) is c.x exactly as before.
-template <typename T, bool TURB, bool PE = false>
+template <typename T, bool TURB, bool PE = false, bool CT = true>
 __device__ __forceinline__ int rhs(const DCfg<T>& c, const DynCtx<T>& x, const T (&y)[FW_NY], bool first, T elev0,
                                    T ail0, T (&dy)[FW_NY], const T* pe = nullptr, int pn = 0) {
 #define PRM(name) (PE ? __ldg(pe + (size_t)(FW_NPARAM + PD_##name) * pn) : c.name)
@@ -345,9 +345,9 @@ __device__ __forceinline__ int rhs(const DCfg<T>& c, const DynCtx<T>& x, const T
     const T inv_Va_raw = M<T>::rsqrt_hot(s_all), inv_rxz = M<T>::rsqrt_hot(s_xz);
     T Va = s_all * inv_Va_raw;
     const T rxz = s_xz * inv_rxz;
-    const T alpha = M<T>::atan2_hot(a2, a0);
+    const T alpha = M<T>::template atan2_hot<CT>(a2, a0);
     const T sb = a1 * inv_Va_raw;               // == sin(beta): beta = asin(a1 / Va) (pyfly.py:1848)
-    const T beta = M<T>::asin_hot(sb);
+    const T beta = M<T>::template asin_hot<CT>(sb);
     if (rc_con == 0 && c.va_con_max > (T)0 && Va > c.va_con_max) rc_con = FW_TERM_VA;
     // sin/cos of alpha = atan2(a2, a0) and cos of beta = asin(a1/Va) follow from the triangle without any
     // trigonometric evaluation (identical up to rounding): sin a = a2/r, cos a = a0/r, cos b = r/Va, r = |(a0, a2)|
@@ -366,7 +366,7 @@ __device__ __forceinline__ int rhs(const DCfg<T>& c, const DynCtx<T>& x, const T
         // sigma = (1 + e1 + e2) / ((1 + e1)(1 + e2)), e1 = exp(-M(a - a0)), e2 = exp(M(a + a0))  (pyfly.py:1541-1543).
         // With E = exp(M a), C = exp(M a0): e1 = C / E, e2 = C E, and multiplying through by E gives the same value
         // from ONE exponential and ONE division, all terms positive (no cancellation): |a| <= pi keeps E^2 < 1e137.
-        const T E = M<T>::exp_hot(PRM(M_) * alpha);
+        const T E = M<T>::template exp_hot<CT>(PRM(M_) * alpha);
         sigma = (E + PRM(exp_M_a0) + PRM(exp_M_a0) * (E * E)) * M<T>::rcp_hot((E + PRM(exp_M_a0)) * ((T)1 + PRM(exp_M_a0) * E));
     } else {
         // overflow-safe in fp32: sigma = 1 - s(-M(a-a0)) s(M(a+a0)), s = logistic
@@ -477,7 +477,7 @@ __device__ __forceinline__ int rk45_init(const DCfg<T>& c, const DynCtx<T>& x, T
     int rc = 0;
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
-        rc = rhs<T, TURB, PE>(c, x, ys, pass == 0, elev0, ail0, dyv, pe, n);
+        rc = rhs<T, TURB, PE, false>(c, x, ys, pass == 0, elev0, ail0, dyv, pe, n);
         if (rc) return rc;
         if (pass == 0) {
             T s0 = 0, s1 = 0;
@@ -831,7 +831,7 @@ __device__ __forceinline__ void write_obs(const T* o, int dim, int env, float* o
 // sum of history["error"][name][start:stop] (absolute entry indices, clamped like a python slice to [0, len]) from the
 // 50-deep error ring of the end_error metric, oldest first.  Callers keep stop - start + lag below the ring depth.
 template <typename T>
-__device__ __noinline__ T err_ring_sum(const Soa<T>& S, int env, int k, int start, int stop, int len) {
+__device__ __forceinline__ T err_ring_sum(const Soa<T>& S, int env, int k, int start, int stop, int len) {
     if (start < 0) start = 0;
     if (stop > len) stop = len;
     T s = 0;

@@ -28,6 +28,22 @@ FW_TAB ATAN_PE[6] = {-0.034570561981427744, -0.05230454270650244, -0.06666424885
 FW_TAB ATAN_PO[6] = {0.016285756855221028, 0.04551593220626549, 0.05878928997834775, 0.07692296375032143,
                      0.11111111105155447, 0.19999999999999804};
 
+// The same coefficients as compile-time constants (folded into immediates): the one-wave init kernel runs every RHS
+// once per launch with a cold constant cache and a 128-register budget, where the table loads cost 1.7 us and 140 B of spills.
+#define FW_IMM static __device__ const double
+FW_IMM EXP_PE_I[7] = {1.0 / 479001600.0, 1.0 / 3628800.0, 1.0 / 40320.0, 1.0 / 720.0, 1.0 / 24.0, 0.5, 1.0};
+FW_IMM EXP_PO_I[7] = {1.0 / 6227020800.0, 1.0 / 39916800.0, 1.0 / 362880.0, 1.0 / 5040.0, 1.0 / 120.0, 1.0 / 6.0, 1.0};
+FW_IMM ASIN_PE_I[7] = {-0.01924167174674304, 0.0030448799094556773, 0.009621842970100282, 0.01396378001220357,
+                     0.02237215744350722, 0.044642857142551895, 0.16666666666666666};
+FW_IMM ASIN_PO_I[7] = {0.02961201126495512, 0.019554513336123378, 0.009319560794767446, 0.011566459612121669,
+                     0.017352816540325496, 0.03038194447553234, 0.07500000000000118};
+FW_IMM ATAN_PE_I[6] = {-0.034570561981427744, -0.05230454270650244, -0.06666424885738255, -0.09090908753500877,
+                     -0.14285714285659828, -0.3333333333333333};
+FW_IMM ATAN_PO_I[6] = {0.016285756855221028, 0.04551593220626549, 0.05878928997834775, 0.07692296375032143,
+                     0.11111111105155447, 0.19999999999999804};
+
+#define FW_COEF(name, k) (CT ? name[k] : name##_I[k])
+
 // 1/sqrt(x) for normal-range x > 0: hardware seed (rsqrt.approx.ftz.f64, ~2^-21) and ONE third-order correction
 // r (1 + e/2 + 3 e^2 / 8), e = 1 - x r^2 (truncation 5/16 e^3 < 2^-60): ~1 ulp like ::rsqrt, but straight-line — the
 // library version carries a slow-path CALL for denormals / specials that splits the RHS into basic blocks the scheduler
@@ -44,16 +60,16 @@ __device__ __forceinline__ double rsqrt_fast(double x) {
 
 // exp(x) for |x| <= 700: n = rint(x log2 e), r = x - n ln2 (two-term Cody-Waite), Taylor degree 13 on |r| <= 0.3466
 // (truncation 4e-18), scaled by 2^n through the exponent field.
-__device__ __forceinline__ double exp_bf(double x) {
+template <bool CT = true> __device__ __forceinline__ double exp_bf(double x) {
     const double t = x * 1.4426950408889634074;
     const double n = (t + 6755399441055744.0) - 6755399441055744.0;       // rint via the 1.5 * 2^52 trick
     double r = fma(-n, 6.93147180369123816490e-01, x);
     r = fma(-n, 1.90821492927058770002e-10, r);
     const double r2 = r * r;
     // even / odd Horner halves of sum r^k / k!
-    double pe = EXP_PE[0], po = EXP_PO[0];
+    double pe = FW_COEF(EXP_PE, 0), po = FW_COEF(EXP_PO, 0);
 #pragma unroll
-    for (int k = 1; k < 7; ++k) { pe = fma(pe, r2, EXP_PE[k]); po = fma(po, r2, EXP_PO[k]); }
+    for (int k = 1; k < 7; ++k) { pe = fma(pe, r2, FW_COEF(EXP_PE, k)); po = fma(po, r2, FW_COEF(EXP_PO, k)); }
     const double p = fma(po, r, pe);
     const int ni = (int)n;
     return __hiloint2double(__double2hiint(p) + ni * 1048576, __double2loint(p));
@@ -73,7 +89,7 @@ __device__ __forceinline__ double rcp_fast(double x) {
 // asin(x), |x| <= 1, straight line.  |x| <= 1/2: x + x z g(z), z = x^2.  Otherwise asin = pi/2 - 2 asin(sqrt((1-|x|)/2))
 // with the same polynomial on z = (1-|x|)/2; the square root comes from rsqrt plus its exact residual (fma) so that the
 // doubled term keeps ~1 ulp.  Worst error 1.6 ulp (tools/gen_math_coeffs.py grid; tests/test_gpu_math.py).
-__device__ __forceinline__ double asin_bf(double x) {
+template <bool CT = true> __device__ __forceinline__ double asin_bf(double x) {
     const double ax = fabs(x);
     const bool big = ax > 0.5;
     const double z = big ? (1.0 - ax) * 0.5 : x * x;
@@ -85,9 +101,9 @@ __device__ __forceinline__ double asin_bf(double x) {
     const double cv = big ? corr : 0.0;
     const double z2 = z * z;
     double pe, po;
-    pe = ASIN_PE[0]; po = ASIN_PO[0];
+    pe = FW_COEF(ASIN_PE, 0); po = FW_COEF(ASIN_PO, 0);
 #pragma unroll
-    for (int k = 1; k < 7; ++k) { pe = fma(pe, z2, ASIN_PE[k]); po = fma(po, z2, ASIN_PO[k]); }
+    for (int k = 1; k < 7; ++k) { pe = fma(pe, z2, FW_COEF(ASIN_PE, k)); po = fma(po, z2, FW_COEF(ASIN_PO, k)); }
     const double g = fma(po, z, pe);
     const double pp = sv + fma(sv * z, g, cv);
     const double res = big ? 1.57079632679489655800e+00 - (2.0 * pp - 6.12323399573676603587e-17) : pp;
@@ -97,7 +113,7 @@ __device__ __forceinline__ double asin_bf(double x) {
 // atan2(y, x): one reciprocal.  m = min/max of |x|, |y|; if m > tan(pi/8) the argument is folded with
 // atan(m) = pi/4 + atan((m - 1)/(m + 1)) which is formed directly as (mn - mx)/(mn + mx); then |t| <= tan(pi/8) and
 // atan(t) = t + t w q(w), w = t^2.  Octant / quadrant fix-ups are selects with hi/lo split constants.
-__device__ __forceinline__ double atan2_bf(double y, double x) {
+template <bool CT = true> __device__ __forceinline__ double atan2_bf(double y, double x) {
     const double ax = fabs(x), ay = fabs(y);
     const double mx = fmax(ax, ay), mn = fmin(ax, ay);
     const bool big = mn > 0.41421356237309503 * mx;
@@ -108,9 +124,9 @@ __device__ __forceinline__ double atan2_bf(double y, double x) {
     const double z = t * t;
     const double z2 = z * z;
     double pe, po;
-    pe = ATAN_PE[0]; po = ATAN_PO[0];
+    pe = FW_COEF(ATAN_PE, 0); po = FW_COEF(ATAN_PO, 0);
 #pragma unroll
-    for (int k = 1; k < 6; ++k) { pe = fma(pe, z2, ATAN_PE[k]); po = fma(po, z2, ATAN_PO[k]); }
+    for (int k = 1; k < 6; ++k) { pe = fma(pe, z2, FW_COEF(ATAN_PE, k)); po = fma(po, z2, FW_COEF(ATAN_PO, k)); }
     const double q = fma(po, z, pe);
     double a = fma(t * z, q, t);
     if (big) a = 7.85398163397448278999e-01 + (a + 3.06161699786838301793e-17);        // + pi/4

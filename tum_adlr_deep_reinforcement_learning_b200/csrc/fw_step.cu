@@ -743,7 +743,7 @@ __global__ void __launch_bounds__(64, 8) head_kernel(const __grid_constant__ DCf
                     (double)gcnt[k] / (double)c.streak_req >= (double)c.streak_fraction) settle[k] = idx;
             }
             if (steps_tgt >= c.streak_req && (double)gcnt[3] / (double)c.streak_req >= (double)c.streak_fraction) {
-                if (c.rew_generic) {                       // goal_achieved_on_step (fixed_wing.py:546-547)
+                if (GENERIC && c.rew_generic) {            // goal_achieved_on_step (fixed_wing.py:546-547)
                     success_on_step = ii[IF_GOAL_ACHIEVED * n] == 0;
                     ii[IF_GOAL_ACHIEVED * n] = 1;
                 }
@@ -753,7 +753,7 @@ __global__ void __launch_bounds__(64, 8) head_kernel(const __grid_constant__ DCf
         }
         // reward (fixed_wing.py:941-1111, default factor family)
         T val = 0;
-        if (c.rew_generic) {
+        if (GENERIC && c.rew_generic) {
             const T st8[8] = {roll, pitch, Va, y[4], y[5], y[6], alpha, beta};
             val = generic_reward<T>(c, S, env, eg, st8, a_raw, act_f32, aring, n_prev, steps, gbits, success_on_step);
         } else {
@@ -785,13 +785,13 @@ __global__ void __launch_bounds__(64, 8) head_kernel(const __grid_constant__ DCf
         // target resample / advance (fixed_wing.py:569-580, 1363-1471)
         int tcls[3] = {c.tgt_class[0], c.tgt_class[1], c.tgt_class[2]};
         T tp[15];
-        if (c.tgt_moving) {
+        if (GENERIC && c.tgt_moving) {
 #pragma unroll
             for (int k = 0; k < 15; ++k) tp[k] = r[(RF_TPROP + k) * n];
 #pragma unroll
             for (int k = 0; k < 3; ++k) tcls[k] = ii[(IF_TCLS + k) * n];
         }
-        if (resample || (c.resample_every > 0 && steps_tgt >= c.resample_every)) {
+        if (GENERIC && (resample || (c.resample_every > 0 && steps_tgt >= c.resample_every))) {
             T u12[12];
             target_draws<T>(c, env_seed(S, env), c.env_id_offset + env, episode, RNG_RESAMPLE, (uint32_t)(steps * 8), u12);
             sample_target<T>(c, *S.rc, roll, pitch, Va, steps, u12, tgt, tcls, tp);
@@ -804,7 +804,7 @@ __global__ void __launch_bounds__(64, 8) head_kernel(const __grid_constant__ DCf
             }
         }
         const T tgt_pitch_cur = tgt[1];
-        if (c.tgt_moving) {
+        if (GENERIC && c.tgt_moving) {
             const T TWO_PI = (T)6.283185307179586476925286766559;
 #pragma unroll
             for (int k = 0; k < 2; ++k) {          // roll, pitch (Va is constant or compensate)
@@ -819,7 +819,7 @@ __global__ void __launch_bounds__(64, 8) head_kernel(const __grid_constant__ DCf
         if (tcls[2] == FW_TGT_COMPENSATE) {
             // the Va law sees the pitch target itself, or the bias of a sinusoidal one (fixed_wing.py:1381-1384); every
             // new value is computed from the targets BEFORE this step's advance
-            const T pitch_tar = (c.tgt_moving && tcls[1] == FW_TGT_SINUSOIDAL) ? tp[13] : tgt_pitch_cur, va_t = tgt[2];
+            const T pitch_tar = (GENERIC && c.tgt_moving && tcls[1] == FW_TGT_SINUSOIDAL) ? tp[13] : tgt_pitch_cur, va_t = tgt[2];
             const T D2R = (T)(3.141592653589793238462643383279502884 / 180.0);
             if (pitch_tar <= (T)-2.5 * D2R) {
                 const T va_end = (T)28.434 - (T)40.0841 * pitch_tar;
@@ -858,12 +858,12 @@ __global__ void __launch_bounds__(64, 8) head_kernel(const __grid_constant__ DCf
                                             : delta_feature<T>(cmd_in[j], cring, j, np_, false);
     }
 
-    if (!GENERIC && (c.obs_noise_std > (T)0 || c.obs_noise_mean != (T)0))
+    if (!(GENERIC && c.obs_generic) && (c.obs_noise_std > (T)0 || c.obs_noise_mean != (T)0))
         add_obs_noise<T>(c, env_seed(S, env), c.env_id_offset + env, episode, steps, obs_v, FW_NOBS);
     T og[GENERIC ? FW_NOBS_MAX : 1];
     const T* obs_out = obs_v;
     int odim = FW_NOBS;
-    if constexpr (GENERIC) {
+    if (GENERIC && c.obs_generic) {
         const T e_cur[3] = {fail ? err_roll(tgt[0], roll) : e_new[0], fail ? tgt[1] - pitch : e_new[1], fail ? tgt[2] - Va : e_new[2]};
         const T cur[14] = {roll, pitch, Va, om_obs[0], om_obs[1], om_obs[2], alpha, beta, tgt[0], tgt[1], tgt[2],
                            e_cur[0], e_cur[1], e_cur[2]};
@@ -1424,6 +1424,16 @@ static void spare_refill(FwHandle* h, const DCfg<T>& c, const Spare<T>& P, cudaS
     if (h->refill_captured) spare_join(h, st);
 }
 
+// head_kernel<.., GENERIC = false> is the straight-line head of the default task family (default observation row, default
+// reward family, constant / compensate targets, no resampling); everything else — general observation layout, general
+// reward engine, moving targets, periodic or on-success resampling — lives in the GENERIC instantiation only, so that
+// its cold code does not cost the default kernel registers (782 -> 1006 B of spills and +5 us when it did).
+static inline bool head_generic(const FwConfig& f) {
+    bool moving = false;
+    for (int k = 0; k < 3; ++k) moving |= (f.tgt_class[k] == FW_TGT_LINEAR || f.tgt_class[k] == FW_TGT_SINUSOIDAL);
+    return f.obs_generic || f.rew_generic || moving || f.resample_every > 0 || f.on_success == FW_SUCCESS_NEW;
+}
+
 // One env step = init kernel -> persistent attempt kernel -> head kernel (RK45), or rk4 kernel -> head kernel.
 template <typename T, bool TURB, int NT, bool PE>
 static int launch_rk45(FwHandle* h, const DCfg<T>& c, const Soa<T>& S, const Scratch<T>& W, const Spare<T>& P, const StepIO& io, cudaStream_t st) {
@@ -1447,7 +1457,7 @@ static int launch_rk45(FwHandle* h, const DCfg<T>& c, const Soa<T>& S, const Scr
     prof_mark(h, 2, st);
     spare_join(h, st);
     if (h->cfg.env_kind == FW_ENV_WAYPOINT) waypoint_head_kernel<T, TURB><<<g0, 128, 0, st>>>(c, S, io, W);
-    else if (h->cfg.obs_generic) head_kernel<T, TURB, true><<<g0h, 64, 0, st>>>(c, S, io, W, P, par);
+    else if (head_generic(h->cfg)) head_kernel<T, TURB, true><<<g0h, 64, 0, st>>>(c, S, io, W, P, par);
     else head_kernel<T, TURB, false><<<g0h, 64, 0, st>>>(c, S, io, W, P, par);
     CK(cudaGetLastError());
     prof_mark(h, 3, st);
@@ -1465,7 +1475,7 @@ static int launch_rk4(FwHandle* h, const DCfg<T>& c, const Soa<T>& S, const Scra
     prof_mark(h, 2, st);
     spare_join(h, st);
     if (h->cfg.env_kind == FW_ENV_WAYPOINT) waypoint_head_kernel<T, TURB><<<g0, 128, 0, st>>>(c, S, io, W);
-    else if (h->cfg.obs_generic) head_kernel<T, TURB, true><<<g0h, 64, 0, st>>>(c, S, io, W, P, par);
+    else if (head_generic(h->cfg)) head_kernel<T, TURB, true><<<g0h, 64, 0, st>>>(c, S, io, W, P, par);
     else head_kernel<T, TURB, false><<<g0h, 64, 0, st>>>(c, S, io, W, P, par);
     CK(cudaGetLastError());
     prof_mark(h, 3, st);
