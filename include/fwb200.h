@@ -43,6 +43,8 @@ extern "C" {
 #define FW_NMETRIC 28   /* see FwMetricIndex                                                                      */
 #define FW_ACT_WINDOW_MAX 8
 #define FW_END_ERR_WINDOW 50   /* fixed_wing.py:1666 */
+#define FW_NMETRIC_ANG 24      /* attitude_angular: avg_error, total_error, end_error, rise_time, overshoot, success,
+                                  settling_time, success_time_frac x (omega_p, omega_q, omega_r), metric-major */
 
 enum FwError {
     FW_OK = 0,
@@ -240,6 +242,16 @@ typedef struct FwConfig {
      * ring of the end_error metric: W + lag_max <= FW_END_ERR_WINDOW - 1.
      * obs_step s: row k of the observation has lag 1 + k s (range(1, length * s, s)); lag_max <= 5. ---- */
     int32_t integration_window, obs_step;
+
+    /* ---- target class "attitude_angular" (fixed_wing.py:671-675, 741-746, 1455-1460, 1558-1642): omega_p, omega_q,
+     * omega_r become target states 3, 4, 5 whose targets _attitude_to_angular_rates derives every step from the roll /
+     * pitch errors and the previous rate targets.  They take part in the goal status (ang_bound, raw units: the
+     * reference keeps the raw props of these states, no degree conversion; inf = no bound), in reward factors and
+     * observation entries that name them (index 3 + a), in info["target"] and in the per-state metrics
+     * (FW_NMETRIC_ANG values behind the 28 of the base states).  All three or none. ---- */
+    int32_t ang_on, _pad_ang;
+    double ang_max_vel[3];                /* props "max_vel", default radians(180) */
+    double ang_bound[3];
 } FwConfig;
 
 typedef struct FwHandle FwHandle;
@@ -341,6 +353,11 @@ int fw_step_random(FwHandle* h, int32_t k_steps, uint64_t action_seed, float* ob
 
 /* Per-env info on done: term_code [n] int32, metrics [n, FW_NMETRIC] f64, episode return/length (Monitor,
  * common/monitor.py:99-113).  Valid for envs whose done flag was set by the most recent fw_step. */
+/* attitude_angular configs: the FW_NMETRIC_ANG per-state metrics of omega_p / omega_q / omega_r [n, FW_NMETRIC_ANG] f64
+ * (avg_error, total_error, end_error, rise_time, overshoot, success, settling_time, success_time_frac x 3 states,
+ * metric-major; get_metric, fixed_wing.py:1644-1736), valid like fw_get_episode_info.  FW_EINVAL for other configs. */
+int fw_get_episode_info_angular(FwHandle* h, double* metrics_ang_dev, void* stream);
+
 int fw_get_episode_info(FwHandle* h, int32_t* term_code_dev, double* metrics_dev, double* ep_return_dev,
                         int32_t* ep_length_dev, void* stream);
 
@@ -357,7 +374,8 @@ enum FwField {
     FW_FIELD_COUNTERS = 7,   /* [n,4]  int32: steps_count, steps_for_target, sim_step, episode*/
     FW_FIELD_NFEV = 8,       /* [n,2]  int32: RHS evaluations, RK attempts of the last step   */
     FW_FIELD_PARAMS = 9,     /* [n,FW_NPARAM] f64 aircraft parameters of the running episode (model_on handles only) */
-    FW_FIELD_COUNT = 10
+    FW_FIELD_ATARGET = 10,   /* [n,3]  omega_p omega_q omega_r rate targets (attitude_angular configs; zeros otherwise) */
+    FW_FIELD_COUNT = 11
 };
 int fw_get_field(FwHandle* h, int32_t field, void* out_dev, void* stream);
 int fw_set_field(FwHandle* h, int32_t field, const void* in_dev, void* stream);

@@ -71,6 +71,10 @@ typedef struct FwoEnv {
     uint8_t* goal_hist; int n_goal;                  /* history["goal"], [t][4] roll pitch Va all */
     double* st_hist;   int n_st;                     /* state .history of roll pitch Va p q r alpha beta, [t][8] */
     double* tgt_hist;  int n_tgt;                    /* history["target"], [t][3] */
+    /* target class attitude_angular: omega_p/q/r as target states 3..5 (same row counts as the base histories) */
+    double atarget[3];
+    double* aerr_hist; double* atgt_hist; uint8_t* agoal_hist;   /* [t][3] each */
+    double ametrics[FW_NMETRIC_ANG];
     double prev_shaping[3]; int has_prev_shaping[3];   /* self.prev_shaping per function class (None after reset) */
     int goal_achieved;                                /* self.goal_achieved: set once, never cleared by reset */
     /* ---- waypoint head (simple_train.py:197-702) ---- */
@@ -574,6 +578,7 @@ static float np_sum_f32(const float* a, int n) {
 /* _get_error (fixed_wing.py:1318-1344): roll has wrap=True (pyfly_config.json) -> _get_angle_dist(target, value) */
 static double py_mod(double a, double b) { double m = fmod(a, b); if (m != 0 && ((m < 0) != (b < 0))) m += b; return m; }
 static double get_error(const FwoEnv* e, int k) {
+    if (k >= 3) return e->atarget[k - 3] - e->omega[k - 3];      /* omega states do not wrap */
     if (k == 0) {
         double dist = py_mod(e->roll - e->target[0] + M_PI, 2 * M_PI) - M_PI;
         if (dist < -M_PI) dist += 2 * M_PI;
@@ -582,9 +587,42 @@ static double get_error(const FwoEnv* e, int k) {
     return e->target[k] - (k == 1 ? e->pitch : e->Va);
 }
 
+/* per angular state (attitude_angular targets with a bound take part in "all", fixed_wing.py:1346-1361) */
+static void goal_status_ang(const FwoEnv* e, uint8_t ga[3]) {
+    for (int a = 0; a < 3; ++a) ga[a] = e->cfg.ang_on ? (fabs(get_error(e, 3 + a)) <= e->cfg.ang_bound[a]) : 1;
+}
 static void goal_status(const FwoEnv* e, uint8_t g[4]) {
     g[3] = 1;
     for (int k = 0; k < 3; ++k) { g[k] = fabs(get_error(e, k)) <= e->cfg.tgt_bound[k]; g[3] &= g[k]; }
+    if (e->cfg.ang_on) { uint8_t ga[3]; goal_status_ang(e, ga); g[3] &= ga[0] & ga[1] & ga[2]; }
+}
+
+/* _attitude_to_angular_rates (fixed_wing.py:1558-1642) for omega state a (0 p, 1 q, 2 r): reads the CURRENT targets and
+ * simulator values; the `damping = 0.05` branches are overwritten unconditionally in the reference (kept so). */
+static double attitude_to_angular_rate(const FwoEnv* e, int a) {
+    const FwConfig* c = &e->cfg;
+    const double max_vel = c->ang_max_vel[a];
+    const double roll_angle = e->roll, pitch_angle = e->pitch;
+    const double roll_error = get_error(e, 0), pitch_error = get_error(e, 1);
+    const double q_w = cos(roll_angle), r_w = sin(roll_angle);
+    const double max_pitch_change = max_vel * c->dt * (q_w + r_w);
+    double res, damping;
+    if (a == 0) {
+        damping = fabs(roll_error / (0.5 * M_PI));
+        const double q_roll = sin(roll_angle) * tan(pitch_angle) * e->atarget[1] * c->dt;
+        const double r_roll = cos(roll_angle) * tan(pitch_angle) * e->atarget[2] * c->dt;
+        res = clipd(-(roll_error - q_roll - r_roll) / c->dt, -max_vel, max_vel);
+    } else if (a == 1) {
+        damping = fabs(pitch_error / (0.5 * M_PI));
+        if (max_pitch_change > fabs(pitch_error)) res = -pitch_error / (2 * q_w);
+        else res = sgn(q_w) * max_vel * sgn(pitch_error);
+    } else {
+        damping = fabs(pitch_error / (0.5 * M_PI));
+        if (max_pitch_change > fabs(pitch_error)) res = pitch_error / r_w;
+        else res = -sgn(r_w) * max_vel * sgn(pitch_error);
+    }
+    if (isnan(damping)) damping = 0.05; else damping = fmin(1.0, damping);
+    return clipd(e->atarget[a] + (res * damping - e->atarget[a]) * 1 / 20, -max_vel, max_vel);
 }
 
 /* sample_target (fixed_wing.py:654-746).  u12: four U[0,1) draws per target state in the order the reference consumes
@@ -617,6 +655,14 @@ static void sample_target(FwoEnv* e, const double u12[12]) {
         }
         e->target[k] = initial;
     }
+    if (c->ang_on) {
+        /* fixed_wing.py:671-675, 741-746: the three are set to 0, then ALL re-derived from those zeros (the dict
+         * comprehension is evaluated before the update) */
+        double v[3];
+        e->atarget[0] = e->atarget[1] = e->atarget[2] = 0;
+        for (int a = 0; a < 3; ++a) v[a] = attitude_to_angular_rate(e, a);
+        for (int a = 0; a < 3; ++a) e->atarget[a] = v[a];
+    }
 }
 
 /* the twelve draws of one target sampling: Philox (purpose, block base) or the test override */
@@ -634,6 +680,8 @@ static void target_draws(const FwoEnv* e, uint32_t purpose, uint32_t block0, dou
 static void next_target(FwoEnv* e) {
     const FwConfig* c = &e->cfg;
     double res[3] = {e->target[0], e->target[1], e->target[2]};
+    double ares[3] = {0, 0, 0};
+    if (c->ang_on) for (int a = 0; a < 3; ++a) ares[a] = attitude_to_angular_rate(e, a);   /* every value from the OLD targets */
     for (int k = 0; k < 3; ++k) {
         if (e->tcls[k] == FW_TGT_LINEAR) res[k] = e->target[k] + e->t_slope[k] * c->dt;
         else if (e->tcls[k] == FW_TGT_SINUSOIDAL)
@@ -660,6 +708,7 @@ static void next_target(FwoEnv* e) {
     /* wrap of roll targets beyond pi (fixed_wing.py:1465-1469) */
     if (fabs(res[0]) > M_PI) res[0] = sgn(res[0]) * (py_mod(fabs(res[0]), M_PI) - M_PI);
     for (int k = 0; k < 3; ++k) e->target[k] = res[k];
+    if (c->ang_on) for (int a = 0; a < 3; ++a) e->atarget[a] = ares[a];
 }
 
 /* sum(|diff|) of one column of the trailing `window` rows of hist[n][3], accumulated in float32
@@ -723,7 +772,7 @@ static double err_slice_sum(const FwoEnv* e, int n, int k, int start, int stop) 
     if (stop > n) stop = n;
     if (stop <= start) return 0.0;
     double* tmp = (double*)malloc(sizeof(double) * (size_t)(stop - start));
-    for (int t = start; t < stop; ++t) tmp[t - start] = e->err_hist[(size_t)t * 3 + k];
+    for (int t = start; t < stop; ++t) tmp[t - start] = k < 3 ? e->err_hist[(size_t)t * 3 + k] : e->aerr_hist[(size_t)t * 3 + k - 3];
     const double s = np_sum_f64(tmp, stop - start);
     free(tmp);
     return s;
@@ -764,10 +813,12 @@ static void get_observation_generic(const FwoEnv* e, double* obs) {
                     val = (ie == 1) ? cur_state[idx] : e->st_hist[(size_t)(e->n_st - ie) * 8 + idx];
                     break;
                 case FW_OBS_TARGET_ABS:
-                    val = (ie == 1) ? e->target[idx] : e->tgt_hist[(size_t)(e->n_tgt - ie) * 3 + idx];
+                    if (idx >= 3) val = (ie == 1) ? e->atarget[idx - 3] : e->atgt_hist[(size_t)(e->n_tgt - ie) * 3 + idx - 3];
+                    else val = (ie == 1) ? e->target[idx] : e->tgt_hist[(size_t)(e->n_tgt - ie) * 3 + idx];
                     break;
                 case FW_OBS_TARGET_REL:
-                    val = (ie == 1) ? get_error(e, idx) : e->err_hist[(size_t)(e->n_err - ie) * 3 + idx];
+                    if (idx >= 3) val = (ie == 1) ? get_error(e, idx) : e->aerr_hist[(size_t)(e->n_err - ie) * 3 + idx - 3];
+                    else val = (ie == 1) ? get_error(e, idx) : e->err_hist[(size_t)(e->n_err - ie) * 3 + idx];
                     break;
                 case FW_OBS_TARGET_INT:       /* fixed_wing.py:1165-1180 */
                     if (!e->has_history) val = get_error(e, idx) * W;
@@ -775,7 +826,8 @@ static void get_observation_generic(const FwoEnv* e, double* obs) {
                         const int n = e->obs_hist_n;
                         /* history[-W - i : -i]: a python slice (W + i > n clamps to the start) */
                         val = err_slice_sum(e, n, idx, n - W - ie < 0 ? 0 : n - W - ie, n - ie);
-                        if (e->steps_count - ie < W) val += (W - (e->steps_count - ie)) * e->err_hist[idx];
+                        if (e->steps_count - ie < W)
+                            val += (W - (e->steps_count - ie)) * (idx < 3 ? e->err_hist[idx] : e->aerr_hist[idx - 3]);
                     }
                     break;
                 default: {
@@ -885,7 +937,8 @@ static double get_reward_generic(FwoEnv* e, const double action[3], int success)
             case FW_RF_STATE_INT_ERROR: {     /* fixed_wing.py:1003-1012; [-0:] is the whole list */
                 const int W = c->integration_window, n = e->n_err;
                 val = err_slice_sum(e, n, c->rew_idx[i], (W == 0 || W > n) ? 0 : n - W, n);
-                if (e->steps_count < W) val += (W - e->steps_count) * e->err_hist[c->rew_idx[i]];
+                if (e->steps_count < W)
+                    val += (W - e->steps_count) * (c->rew_idx[i] < 3 ? e->err_hist[c->rew_idx[i]] : e->aerr_hist[c->rew_idx[i] - 3]);
                 break;
             }
             case FW_RF_ACTION_VALUE:
@@ -921,9 +974,12 @@ static double get_reward_generic(FwoEnv* e, const double action[3], int success)
                 val = success ? (c->rew_value_timesteps[i] ? (double)(c->steps_max - e->steps_count) : c->rew_value[i]) : 0;
                 break;
             case FW_RF_STEP: val = c->rew_value[i]; break;
-            case FW_RF_GOAL_PER_STATE:
-                for (int k = 0; k < 3; ++k) val += g[k] ? c->rew_value[i] / 3 : 0;
+            case FW_RF_GOAL_PER_STATE: {      /* value / len(self.target) per achieved state (fixed_wing.py:1038-1044) */
+                const int nt = c->ang_on ? 6 : 3;
+                for (int k = 0; k < 3; ++k) val += g[k] ? c->rew_value[i] / nt : 0;
+                if (c->ang_on) { uint8_t ga[3]; goal_status_ang(e, ga); for (int a = 0; a < 3; ++a) val += ga[a] ? c->rew_value[i] / nt : 0; }
                 break;
+            }
             case FW_RF_GOAL_ALL: val += g[3] ? c->rew_value[i] : 0; break;
         }
         /* values derived from a float32 action array stay float32 through the function class (numpy keeps the array
@@ -957,33 +1013,58 @@ static double get_reward_generic(FwoEnv* e, const double action[3], int success)
 }
 
 /* get_metric x9 (fixed_wing.py:1644-1736) computed from the full histories exactly as the reference does */
+/* the five error metrics of ONE target state from its error history hist[t * 3 + col] (fixed_wing.py:1655-1730) */
+static void state_error_metrics(const FwoEnv* e, const double* hist, int col, double out5[5]) {
+    const FwConfig* c = &e->cfg;
+    const int ne = e->n_err;
+    double e0 = hist[col], sum = 0, sabs = 0, vmin = INFINITY, vmax = -INFINITY;
+    for (int t = 0; t < ne; ++t) {
+        double v = hist[t * 3 + col];
+        sum += v; sabs += fabs(v); vmin = fmin(vmin, v); vmax = fmax(vmax, v);
+    }
+    out5[0] = (fabs(e0) >= 0.01) ? fabs((sum / ne) / e0) : NAN;
+    out5[1] = sabs;
+    int lo = ne - FW_END_ERR_WINDOW < 0 ? 0 : ne - FW_END_ERR_WINDOW;
+    double s50 = 0;
+    for (int t = lo; t < ne; ++t) s50 += hist[t * 3 + col];
+    out5[2] = fabs(s50 / (ne - lo));
+    /* rise_time: reverse scan (fixed_wing.py:1702-1719) */
+    double rise_end = NAN, rise_start = NAN, low_lim = fabs(c->rise_low * e0), high_lim = fabs(c->rise_high * e0);
+    for (int j = 1; j < ne; ++j) {
+        double er = fabs(hist[(ne - 1 - j) * 3 + col]), prev = fabs(hist[(ne - j) * 3 + col]);
+        if (er >= low_lim && prev < low_lim) rise_end = e->steps_count - j;
+        if (er >= high_lim && prev < high_lim) rise_start = e->steps_count - j;
+    }
+    out5[3] = rise_end - rise_start;
+    /* overshoot (fixed_wing.py:1722-1730) */
+    double opp = (e0 > 0) ? vmin : vmax;
+    out5[4] = (sgn(opp) == sgn(e0)) ? NAN : fabs(opp / e0);
+}
+
+/* success / settling_time (fixed_wing.py:1684-1699), success_time_frac (:1733-1734) of one goal column */
+static void goal_metrics(const FwoEnv* e, const uint8_t* gh, int stride, int col, double out3[3]) {
+    const FwConfig* c = &e->cfg;
+    const int ng = e->n_goal;
+    int cnt = 0, total = 0, settle = -1;
+    for (int t = 0; t < ng; ++t) {
+        cnt += gh[t * stride + col];
+        total += gh[t * stride + col];
+        if (t >= c->streak_req) cnt -= gh[(t - c->streak_req) * stride + col];
+        if (settle < 0 && t + 1 >= c->streak_req && (double)cnt / c->streak_req >= c->streak_fraction) settle = t;
+    }
+    out3[0] = settle >= 0;
+    out3[1] = settle >= 0 ? (double)settle : NAN;
+    out3[2] = (double)total / ng;
+}
+
 static void compute_metrics(FwoEnv* e) {
     const FwConfig* c = &e->cfg;
     double* m = e->metrics;
-    int ne = e->n_err, ng = e->n_goal;
     for (int k = 0; k < 3; ++k) {
-        double e0 = e->err_hist[k], sum = 0, sabs = 0, vmin = INFINITY, vmax = -INFINITY;
-        for (int t = 0; t < ne; ++t) {
-            double v = e->err_hist[t * 3 + k];
-            sum += v; sabs += fabs(v); vmin = fmin(vmin, v); vmax = fmax(vmax, v);
-        }
-        m[FW_M_AVG_ERROR + k] = (fabs(e0) >= 0.01) ? fabs((sum / ne) / e0) : NAN;
-        m[FW_M_TOTAL_ERROR + k] = sabs;
-        int lo = ne - FW_END_ERR_WINDOW < 0 ? 0 : ne - FW_END_ERR_WINDOW;
-        double s50 = 0;
-        for (int t = lo; t < ne; ++t) s50 += e->err_hist[t * 3 + k];
-        m[FW_M_END_ERROR + k] = fabs(s50 / (ne - lo));
-        /* rise_time: reverse scan (fixed_wing.py:1702-1719) */
-        double rise_end = NAN, rise_start = NAN, low_lim = fabs(c->rise_low * e0), high_lim = fabs(c->rise_high * e0);
-        for (int j = 1; j < ne; ++j) {
-            double er = fabs(e->err_hist[(ne - 1 - j) * 3 + k]), prev = fabs(e->err_hist[(ne - j) * 3 + k]);
-            if (er >= low_lim && prev < low_lim) rise_end = e->steps_count - j;
-            if (er >= high_lim && prev < high_lim) rise_start = e->steps_count - j;
-        }
-        m[FW_M_RISE_TIME + k] = rise_end - rise_start;
-        /* overshoot (fixed_wing.py:1722-1730) */
-        double opp = (e0 > 0) ? vmin : vmax;
-        m[FW_M_OVERSHOOT + k] = (sgn(opp) == sgn(e0)) ? NAN : fabs(opp / e0);
+        double o[5];
+        state_error_metrics(e, e->err_hist, k, o);
+        m[FW_M_AVG_ERROR + k] = o[0]; m[FW_M_TOTAL_ERROR + k] = o[1]; m[FW_M_END_ERROR + k] = o[2];
+        m[FW_M_RISE_TIME + k] = o[3]; m[FW_M_OVERSHOOT + k] = o[4];
     }
     /* control_variation (fixed_wing.py:1670-1680) */
     {
@@ -992,18 +1073,18 @@ static void compute_metrics(FwoEnv* e) {
             for (int j = 0; j < 3; ++j) s += fabs(e->cmd_hist[t * 3 + j] - e->cmd_hist[(t - 1) * 3 + j]);
         m[FW_M_CONTROL_VARIATION] = s / (3 * c->dt * (e->n_cmd - 1));
     }
-    /* success / settling_time (fixed_wing.py:1684-1699), success_time_frac (:1733-1734) */
     for (int k = 0; k < 4; ++k) {
-        int cnt = 0, total = 0, settle = -1;
-        for (int t = 0; t < ng; ++t) {
-            cnt += e->goal_hist[t * 4 + k];
-            total += e->goal_hist[t * 4 + k];
-            if (t >= c->streak_req) cnt -= e->goal_hist[(t - c->streak_req) * 4 + k];
-            if (settle < 0 && t + 1 >= c->streak_req && (double)cnt / c->streak_req >= c->streak_fraction) settle = t;
-        }
-        m[FW_M_SUCCESS + k] = settle >= 0;
-        m[FW_M_SETTLING_TIME + k] = settle >= 0 ? (double)settle : NAN;
-        m[FW_M_SUCCESS_TIME_FRAC + k] = (double)total / ng;
+        double o[3];
+        goal_metrics(e, e->goal_hist, 4, k, o);
+        m[FW_M_SUCCESS + k] = o[0]; m[FW_M_SETTLING_TIME + k] = o[1]; m[FW_M_SUCCESS_TIME_FRAC + k] = o[2];
+    }
+    /* attitude_angular: the same metrics for omega_p/q/r, metric-major (FW_NMETRIC_ANG) */
+    if (c->ang_on) for (int a = 0; a < 3; ++a) {
+        double o[5], g3[3];
+        state_error_metrics(e, e->aerr_hist, a, o);
+        goal_metrics(e, e->agoal_hist, 3, a, g3);
+        for (int q = 0; q < 5; ++q) e->ametrics[q * 3 + a] = o[q];
+        for (int q = 0; q < 3; ++q) e->ametrics[15 + q * 3 + a] = g3[q];
     }
 }
 
@@ -1024,6 +1105,9 @@ FwoEnv* fwo_create(const FwConfig* cfg, int64_t env_id) {
     e->goal_hist = (uint8_t*)calloc((size_t)4 * L, 1);
     e->st_hist = (double*)calloc((size_t)8 * L, sizeof(double));
     e->tgt_hist = (double*)calloc((size_t)3 * L, sizeof(double));
+    e->aerr_hist = (double*)calloc((size_t)3 * L, sizeof(double));
+    e->atgt_hist = (double*)calloc((size_t)3 * L, sizeof(double));
+    e->agoal_hist = (uint8_t*)calloc((size_t)3 * L, 1);
     e->env_id = env_id;
     e->episode = 0;
     return e;
@@ -1032,7 +1116,7 @@ FwoEnv* fwo_create(const FwConfig* cfg, int64_t env_id) {
 void fwo_destroy(FwoEnv* e) {
     if (!e) return;
     free(e->turb); free(e->act_hist); free(e->cmd_hist); free(e->err_hist); free(e->goal_hist);
-    free(e->st_hist); free(e->tgt_hist); free(e);
+    free(e->st_hist); free(e->tgt_hist); free(e->aerr_hist); free(e->atgt_hist); free(e->agoal_hist); free(e);
 }
 
 /* sample_simulator_parameters, the "model" block (fixed_wing.py:758-800): every enabled aircraft parameter whose
@@ -1243,9 +1327,11 @@ void fwo_reset(FwoEnv* e, const double* state, const double* target, const doubl
     }
     get_observation(e, obs);
     for (int k = 0; k < 3; ++k) { e->err_hist[k] = get_error(e, k); e->tgt_hist[k] = e->target[k]; }
+    if (c->ang_on) for (int a = 0; a < 3; ++a) { e->aerr_hist[a] = get_error(e, 3 + a); e->atgt_hist[a] = e->atarget[a]; }
     e->n_err = 1; e->n_tgt = 1;
     e->has_history = 1; e->obs_hist_n = 1;
     goal_status(e, e->goal_hist);
+    goal_status_ang(e, e->agoal_hist);
     e->n_goal = 1;
 }
 
@@ -1276,6 +1362,7 @@ void fwo_step(FwoEnv* e, const double action[3], int action_is_f32, double obs[F
         int resample = 0, success_on_step = 0;
         if (c->streak_req > 0) {
             goal_status(e, e->goal_hist + (size_t)e->n_goal * 4);
+            goal_status_ang(e, e->agoal_hist + (size_t)e->n_goal * 3);
             e->n_goal++;
             if (e->steps_for_target >= c->streak_req) {
                 int cnt = 0;
@@ -1298,6 +1385,10 @@ void fwo_step(FwoEnv* e, const double action[3], int action_is_f32, double obs[F
         for (int k = 0; k < 3; ++k) {
             e->err_hist[(size_t)e->n_err * 3 + k] = get_error(e, k);
             e->tgt_hist[(size_t)e->n_tgt * 3 + k] = e->target[k];
+            if (c->ang_on) {
+                e->aerr_hist[(size_t)e->n_err * 3 + k] = get_error(e, 3 + k);
+                e->atgt_hist[(size_t)e->n_tgt * 3 + k] = e->atarget[k];
+            }
         }
         e->n_err++; e->n_tgt++;
         e->obs_hist_n = e->n_err;
@@ -1326,6 +1417,10 @@ void fwo_get(const FwoEnv* e, double y[NY], double euler[3], double vab[3], doub
     counters[3] = (int32_t)e->episode; counters[4] = e->last_nfev; counters[5] = e->last_natt;
 }
 
+void fwo_get_angular(const FwoEnv* e, double atarget[3], double ametrics[FW_NMETRIC_ANG]) {
+    for (int a = 0; a < 3; ++a) atarget[a] = e->atarget[a];
+    for (int q = 0; q < FW_NMETRIC_ANG; ++q) ametrics[q] = e->ametrics[q];
+}
 void fwo_get_metrics(const FwoEnv* e, double metrics[FW_NMETRIC], double* ep_return, int32_t* ep_len, int32_t* term) {
     memcpy(metrics, e->metrics, sizeof(e->metrics));
     *ep_return = e->ep_return; *ep_len = e->steps_count; *term = e->term_code;

@@ -42,6 +42,7 @@ def lib():
                                ctypes.POINTER(ctypes.c_int)]
         L.fwo_get.argtypes = [ctypes.c_void_p, _dp, _dp, _dp, _dp, _dp, _dp, _i32p]
         L.fwo_get_metrics.argtypes = [ctypes.c_void_p, _dp, _dp, _i32p, _i32p]
+        L.fwo_get_angular.argtypes = [ctypes.c_void_p, _dp, _dp]
         L.fwo_turbulence.restype = _dp
         L.fwo_turbulence.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int)]
         L.fwo_rhs.argtypes = [ctypes.POINTER(FwConfig), _dp, _dp, _dp, _dp, _dp]
@@ -110,6 +111,12 @@ class OracleEnv:
         done, term = ctypes.c_int(), ctypes.c_int()
         lib().fwo_step(self._h, _p(a), int(f32), _p(obs), ctypes.byref(rew), ctypes.byref(done), ctypes.byref(term))
         return obs, rew.value, bool(done.value), term.value
+
+    def angular(self):
+        """(rate targets omega_p/q/r, the 24 attitude_angular metrics of the last finished episode)."""
+        at, am = np.zeros(3), np.zeros(24)
+        lib().fwo_get_angular(self._h, _p(at), _p(am))
+        return at, am
 
     def get(self):
         y, eu, vab, cmd, tgt, wind = (np.zeros(FW_NY), np.zeros(3), np.zeros(3), np.zeros(3), np.zeros(3),
@@ -222,6 +229,12 @@ class OracleBatch:
         a = np.ascontiguousarray(actions, dtype=np.float32)
         lib().fwo_batch_step(self._h, _p(a, _fp), _p(self.obs), _p(self.rew), _p(self.done, _u8p))
         return self.obs, self.rew, self.done
+
+    def env_angular(self, i):
+        """(rate targets, the 24 attitude_angular metrics of the last finished episode) of env i."""
+        at, am = np.zeros(3), np.zeros(24)
+        lib().fwo_get_angular(lib().fwo_batch_env(self._h, i), _p(at), _p(am))
+        return at, am
 
     def params(self):
         out = np.zeros((self.n, 48))

@@ -190,3 +190,44 @@ def integrator_env_config(W, L, step):
 
 
 INTEGRATOR_CASES = [("traj_integrator_w4", 4, 3, 2), ("traj_integrator_w0", 0, 1, 1)]
+
+
+def angular_env_config():
+    """The config of tests/golden/make_golden.py:gen_angular: target class attitude_angular on omega_p/q/r with bounds,
+    observed, rewarded and part of the success streak."""
+    from tum_adlr_deep_reinforcement_learning_b200.config import default_env_config
+    cfg = default_env_config()
+    names = ("omega_p", "omega_q", "omega_r")
+    for name, bound in zip(names, (0.6, 0.4, 0.5)):
+        cfg["target"]["states"].append({"name": name, "class": "attitude_angular", "bound": bound})
+    cfg["target"]["states"][-1]["max_vel"] = 2.5
+    ob = cfg["observation"]
+    ob["states"] = [s_ for s_ in ob["states"] if s_["name"] not in ("alpha", "beta")]
+    for name in names:
+        ob["states"].append({"name": name, "type": "target", "value": "absolute"})
+    ob["states"].append({"name": "omega_q", "type": "target", "value": "relative"})
+    for name, sc in zip(names, (6.0, 5.0, 4.0)):
+        cfg["reward"]["factors"].append({"name": name, "class": "state", "type": "error", "function_class": "linear",
+                                         "scaling": sc, "shaping": False, "max": 0.5, "sign": -1})
+    cfg["reward"]["factors"].append({"name": "goal", "class": "goal", "type": "per_state", "value": 0.6,
+                                     "function_class": "linear", "scaling": 1, "shaping": False, "sign": 1})
+    cfg["steps_max"] = 50
+    cfg["target"]["success_streak_req"] = 5
+    cfg["target"]["success_streak_fraction"] = 0.6
+    for s_, b in zip(cfg["target"]["states"][:3], (70, 45, 14)):
+        s_["bound"] = b
+    return cfg
+
+
+def angular_metric_rows(metrics28, metrics24):
+    """The fixture's 52-value row (5 error metrics x 6 states | 3 goal metrics x (6 states + all) | control_variation)
+    from the C-ABI layout: 28 base metrics (FwMetricIndex) + 24 angular ones (metric-major)."""
+    m, a = np.asarray(metrics28, dtype=np.float64), np.asarray(metrics24, dtype=np.float64)
+    row = []
+    base_off = {"avg_error": 13, "total_error": 10, "end_error": 25, "rise_time": 0, "overshoot": 7}     # FwMetricIndex
+    for q, name in enumerate(("avg_error", "total_error", "end_error", "rise_time", "overshoot")):
+        row += list(m[base_off[name]:base_off[name] + 3]) + list(a[q * 3:q * 3 + 3])
+    for q, off in enumerate((17, 3, 21)):              # success, settling_time, success_time_frac: roll pitch Va all
+        row += list(m[off:off + 3]) + list(a[15 + q * 3:15 + q * 3 + 3]) + [m[off + 3]]
+    row.append(m[16])
+    return np.array(row)

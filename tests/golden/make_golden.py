@@ -1,7 +1,7 @@
 """Generate the golden fixtures in this directory by running the UNMODIFIED reference where it lies.
 
 TEST INFRASTRUCTURE — run here (the build container, where /root/reference is mounted), never on the
-GPU box.  Usage:  python tests/golden/make_golden.py [integrator|params|traj|turb|fail|full|pid|gae|vecnorm|ppo_update|curriculum|dryden|all]
+GPU box.  Usage:  python tests/golden/make_golden.py [angular|integrator|params|traj|turb|fail|full|pid|gae|vecnorm|ppo_update|curriculum|dryden|all]
 
 Everything is recorded through the reference's public surface:
   FixedWingAircraft.reset(state=, target=, turbulence_noise=) / .step(action)
@@ -404,6 +404,86 @@ def gen_integrator():
         out = run_episodes(env, 5, 45, rs, False, wind_mag=3.0, action_amp=1.4)
         np.savez_compressed(os.path.join(HERE, "traj_integrator_%s.npz" % tag), **out)
         print(tag, "obs dim", out["obs"].shape[-1], "n_valid", out["n_valid"], "reward range", out["reward"].min(), out["reward"].max())
+
+
+ANG_KEYS = ["omega_p", "omega_q", "omega_r"]
+
+
+def angular_env_config(cfg):
+    """Default config + target class attitude_angular (fixed_wing.py:671-675, 1455-1460, 1558-1642): omega_p/q/r as
+    derived target states with bounds, observed (absolute and relative), rewarded (error factors, goal per_state) and
+    part of the success streak; short episodes with a wide streak so that goals fire."""
+    for name, bound in zip(ANG_KEYS, (0.6, 0.4, 0.5)):
+        cfg["target"]["states"].append({"name": name, "class": "attitude_angular", "bound": bound})
+    cfg["target"]["states"][-1]["max_vel"] = 2.5
+    ob = cfg["observation"]
+    ob["states"] = [s_ for s_ in ob["states"] if s_["name"] not in ("alpha", "beta")]
+    for name in ANG_KEYS:
+        ob["states"].append({"name": name, "type": "target", "value": "absolute"})
+    ob["states"].append({"name": "omega_q", "type": "target", "value": "relative"})
+    for name, sc in zip(ANG_KEYS, (6.0, 5.0, 4.0)):
+        cfg["reward"]["factors"].append({"name": name, "class": "state", "type": "error", "function_class": "linear",
+                                         "scaling": sc, "shaping": False, "max": 0.5, "sign": -1})
+    cfg["reward"]["factors"].append({"name": "goal", "class": "goal", "type": "per_state", "value": 0.6,
+                                     "function_class": "linear", "scaling": 1, "shaping": False, "sign": 1})
+    cfg["steps_max"] = 50
+    cfg["target"]["success_streak_req"] = 5
+    cfg["target"]["success_streak_fraction"] = 0.6
+    for s_, b in zip(cfg["target"]["states"][:3], (70, 45, 14)):
+        s_["bound"] = b
+    return cfg
+
+
+def gen_angular():
+    """Target class attitude_angular against the live reference: six target states.  The env RNG is replaced by fixed draws
+    (the rate targets sampled at reset derive from the SAMPLED roll / pitch targets, before the injected ones override
+    them, fixed_wing.py:441-450): u = 0.625, fed to our side as rng_u_override."""
+    import tempfile
+    cfg = angular_env_config(json.load(open(refshim.GYM_CONFIG)))
+    with tempfile.NamedTemporaryFile("w", suffix=".json", delete=False) as f:
+        json.dump(cfg, f)
+    env = make_env(False, config_path=f.name)
+    env.np_random = FixedDraws()
+    rs = np.random.RandomState(909)
+    n_ep, n_steps = 5, 50
+    keys6 = TARGET_KEYS + ANG_KEYS
+    rec = {k: [] for k in ("init_state", "init_target", "obs0", "target0", "actions", "obs", "reward", "done", "term",
+                           "target", "n_valid")}
+    mrec = []
+    for ep in range(n_ep):
+        st, tgt = random_scenario(rs, 3.0, False)
+        obs0 = env.reset(state=dict(st), target=dict(tgt))
+        s_arr, t_arr = scenario_arrays(st, tgt)
+        rec["init_state"].append(s_arr), rec["init_target"].append(t_arr)
+        rec["obs0"].append(np.array(obs0, dtype=np.float64))
+        rec["target0"].append(np.array([env.target[k] for k in keys6], dtype=np.float64))
+        er = {k: [] for k in ("actions", "obs", "reward", "done", "term", "target")}
+        n_valid = n_steps
+        for t in range(n_steps):
+            a = rs.uniform(-1.3, 1.3, 3)
+            obs, rew, done, info = env.step(a)
+            er["actions"].append(a), er["obs"].append(np.array(obs, dtype=np.float64)), er["reward"].append(float(rew))
+            er["done"].append(bool(done)), er["term"].append(term_code(info.get("termination", "")))
+            er["target"].append(np.array([env.target[k] for k in keys6], dtype=np.float64))
+            if done:
+                n_valid = t + 1
+                row = []
+                for name in ("avg_error", "total_error", "end_error", "rise_time", "overshoot"):
+                    row += [float(info[name][k]) for k in keys6]
+                for name in ("success", "settling_time", "success_time_frac"):
+                    row += [float(info[name][k]) for k in keys6 + ["all"]]
+                row.append(float(info["control_variation"]["all"]))
+                mrec.append(row)
+                break
+        rec["n_valid"].append(n_valid)
+        for k, v in er.items():
+            arr = np.array(v)
+            rec[k].append(np.pad(arr, [(0, n_steps - arr.shape[0])] + [(0, 0)] * (arr.ndim - 1)))
+    out = {k: np.array(v) for k, v in rec.items()}
+    out["metrics52"] = np.array(mrec)        # 5 x 6 error metrics | 3 x 7 goal metrics | control_variation
+    np.savez_compressed(os.path.join(HERE, "traj_angular.npz"), **out)
+    print("n_valid", out["n_valid"], "terms", [int(out["term"][e, out["n_valid"][e] - 1]) for e in range(n_ep)],
+          "reward range", out["reward"].min(), out["reward"].max(), "metric rows", out["metrics52"].shape)
 
 
 def gen_targets():
@@ -943,7 +1023,7 @@ def gen_dryden():
 
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
-    jobs = {"integrator": gen_integrator, "waypoint": gen_waypoint, "targets": gen_targets, "resample": gen_resample, "reward": gen_reward, "cnn": gen_cnn, "params": gen_params, "traj": gen_traj, "turb": gen_turb, "turb_moderate": gen_turb_moderate, "model": gen_model, "fail": gen_fail, "full": gen_full,
+    jobs = {"angular": gen_angular, "integrator": gen_integrator, "waypoint": gen_waypoint, "targets": gen_targets, "resample": gen_resample, "reward": gen_reward, "cnn": gen_cnn, "params": gen_params, "traj": gen_traj, "turb": gen_turb, "turb_moderate": gen_turb_moderate, "model": gen_model, "fail": gen_fail, "full": gen_full,
             "pid": gen_pid, "gae": gen_gae, "vecnorm": gen_vecnorm, "ppo_update": gen_ppo_update, "sac_update": gen_sac_update, "curriculum": gen_curriculum, "dryden": gen_dryden}
     for name, fn in jobs.items():
         if what in (name, "all"):

@@ -63,14 +63,40 @@ def test_overrides_follow_reference_semantics():
 
 
 def test_unsupported_configs_fail_loudly():
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(NotImplementedError):      # attitude_angular is defined for omega_p / omega_q / omega_r, all three
         C.build_config(config_kw={"target": {"states": {0: {"class": "attitude_angular"}}}})
+    env = C.default_env_config()
+    env["target"]["states"].append({"name": "omega_p", "class": "attitude_angular"})
+    with pytest.raises(NotImplementedError):
+        C.build_config(env_cfg=env)
     with pytest.raises(NotImplementedError):
         C.build_config(config_kw={"observation": {"states": {0: {"name": "position_n"}}}})
     with pytest.raises(NotImplementedError):      # rows reach 1 + 2 * 3 = 7 steps back: the history rings hold 5
         C.build_config(config_kw={"observation": {"step": 3, "length": 3}})
     with pytest.raises(NotImplementedError):      # window + lag beyond the 50-deep error ring
         C.build_config(config_kw={"integration_window": 49, "reward": {"factors": {0: {"type": "int_error"}}}})
+
+
+def test_attitude_angular_config_builds():
+    env = C.default_env_config()
+    for name, bound in zip(("omega_p", "omega_q", "omega_r"), (0.5, None, 0.25)):
+        st = {"name": name, "class": "attitude_angular"}
+        if bound is not None:
+            st["bound"] = bound
+        env["target"]["states"].append(st)
+    env["target"]["states"][3]["max_vel"] = 2.0
+    env["observation"]["states"][6] = {"name": "omega_r", "type": "target", "value": "relative"}
+    env["reward"]["factors"].append({"name": "omega_q", "class": "state", "type": "error", "function_class": "linear",
+                                     "scaling": 2.0, "shaping": False, "sign": -1})
+    c = C.build_config(env_cfg=env)
+    assert c.ang_on == 1 and c.rew_generic == 1 and c.obs_generic == 1
+    assert c.ang_max_vel[0] == 2.0 and np.isclose(c.ang_max_vel[1], np.pi) and c.ang_bound[0] == 0.5 and np.isinf(c.ang_bound[1])
+    assert (c.obs_kind[6], c.obs_idx[6]) == (2, 5) and c.rew_class[c.rew_n - 1] == 0 and c.rew_idx[c.rew_n - 1] == 4
+    env["reward"]["factors"].append({"name": "goal", "class": "goal", "type": "per_state", "value": 1.0,
+                                     "function_class": "linear", "scaling": 1, "shaping": False, "sign": 1})
+    with pytest.raises(KeyError):                 # the reference indexes the goal history of EVERY target state there
+        C.build_config(env_cfg=env)
+    assert C.build_config().ang_on == 0
 
 
 def test_error_integral_and_strided_row_configs_build():

@@ -96,6 +96,42 @@ def test_vecenv_contract_terminal_obs_and_autoreset(cuda_device):
     venv.close()
 
 
+def test_vecenv_info_dicts_with_attitude_angular_targets(cuda_device):
+    """The VecEnv surface of an attitude_angular config: info["target"] and get_attr("target") carry six target states,
+    and the metric dicts of a finished episode carry the rate targets' entries (values = the oracle's, key order =
+    the reference's: roll, pitch, Va, omega_p, omega_q, omega_r[, all])."""
+    from conftest import angular_env_config
+    from oracle import fw_oracle as O
+    from tum_adlr_deep_reinforcement_learning_b200.vec_env import FixedWingVecEnv
+    ecfg = angular_env_config()
+    ecfg["steps_max"] = 12
+    n = 64
+    venv = FixedWingVecEnv(n, config_path=ecfg, sim_config_kw={"turbulence": True}, seed=5, info_mode="compat")
+    ob = O.OracleBatch(venv.cfg, n)
+    venv.reset(); ob.reset()
+    rs = np.random.RandomState(2)
+    names6 = ["roll", "pitch", "Va", "omega_p", "omega_q", "omega_r"]
+    seen = 0
+    for t in range(13):
+        a = rs.uniform(-1, 1, (n, 3)).astype(np.float32)
+        obs, rew, done, infos = venv.step(a)
+        o_ref, r_ref, d_ref = ob.step(a)
+        assert np.array_equal(done, d_ref.astype(bool))
+        for i in np.flatnonzero(done):
+            info = infos[i]
+            ref24 = ob.env_angular(int(i))[1]
+            assert list(info["total_error"].keys()) == names6 and list(info["success"].keys()) == names6 + ["all"]
+            assert abs(info["total_error"]["omega_q"] - ref24[3 + 1]) < 1e-9 * max(1.0, abs(ref24[4]))
+            assert info["success"]["omega_r"] == bool(ref24[15 + 2])
+            assert abs(info["success_time_frac"]["omega_p"] - ref24[21]) < 1e-12
+            seen += 1
+        assert list(infos[0]["target"].keys()) == names6
+    assert seen >= n
+    tg = venv.get_attr("target", [0, 1])
+    assert list(tg[0].keys()) == names6
+    venv.close()
+
+
 def test_reset_distributions_and_wind(cuda_device):
     """Philox resets draw from the reference's ranges: uniform init states, wind magnitude <= 8,
     targets inside [low, high] and within delta of the current state."""

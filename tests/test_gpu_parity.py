@@ -291,6 +291,64 @@ def test_error_integrals_and_strided_observation_rows(cuda_device):
         env.close()
 
 
+def test_attitude_angular_targets(cuda_device):
+    """Target class attitude_angular on the CUDA path (omega_p/q/r as derived target states: observations, error and goal
+    rewards, success streak, per-state metrics): (a) the live-reference fixture on a ONE-env handle, (b) 512 envs with
+    Philox resets, turbulence, on_success = "new" resampling and auto-reset against the oracle, metrics included."""
+    import torch
+    from conftest import angular_env_config, angular_metric_rows, close_or_both_nan
+    from oracle import fw_oracle as O
+    from tum_adlr_deep_reinforcement_learning_b200 import batched as bt
+    from tum_adlr_deep_reinforcement_learning_b200.config import build_config
+    g = load_golden("traj_angular")
+    cfg = build_config(env_cfg=angular_env_config(), sim_config_kw={"turbulence": False}, rng_u_override=0.625)
+    env = bt.BatchedFixedWing(1, cfg=cfg)
+    assert env.obs_dim == 16
+    env.enable_f64_outputs()
+    row = 0
+    for ep in range(g["actions"].shape[0]):
+        env.reset(state=g["init_state"][ep:ep + 1], target=g["init_target"][ep:ep + 1])
+        assert np.abs(env.obs64.cpu().numpy()[0] - g["obs0"][ep]).max() < 1e-12, ep
+        assert np.abs(env.get_field(bt.FIELD_ATARGET).cpu().numpy()[0] - g["target0"][ep, 3:]).max() < 1e-12
+        for t in range(int(g["n_valid"][ep])):
+            env.step(torch.as_tensor(g["actions"][ep:ep + 1, t]).cuda().contiguous(), auto_reset=False)
+            assert _rel(env.obs64.cpu().numpy()[0], g["obs"][ep, t]).max() < RTOL_F64, (ep, t)
+            r = float(env.rew64.cpu().numpy()[0])
+            assert abs(r - g["reward"][ep, t]) < 1e-9 * max(1.0, abs(g["reward"][ep, t])), (ep, t)
+            assert _rel(env.get_field(bt.FIELD_ATARGET).cpu().numpy()[0], g["target"][ep, t, 3:]).max() < RTOL_F64, (ep, t)
+            assert bool(env.done.cpu().numpy()[0]) == bool(g["done"][ep, t])
+        if bool(g["done"][ep, int(g["n_valid"][ep]) - 1]):
+            term, m28, ret, ln = env.episode_info()
+            ours = angular_metric_rows(m28.cpu().numpy()[0], env.episode_info_angular().cpu().numpy()[0])
+            assert close_or_both_nan(ours, g["metrics52"][row], 1e-9, 1e-12).all(), (ep, ours, g["metrics52"][row])
+            row += 1
+    env.close()
+    ecfg = angular_env_config()
+    ecfg["steps_max"] = 25
+    ecfg["target"]["on_success"] = "new"
+    cfg = build_config(env_cfg=ecfg, sim_config_kw={"turbulence": True}, seed=77)
+    n = 512
+    env = bt.BatchedFixedWing(n, cfg=cfg)
+    env.enable_f64_outputs()
+    env.reset()
+    ob = O.OracleBatch(cfg, n)
+    assert _rel(env.obs64.cpu().numpy(), ob.reset()).max() < 1e-12
+    rs = np.random.RandomState(6)
+    for t in range(60):
+        a = rs.uniform(-1.4, 1.4, (n, 3)).astype(np.float32)
+        env.step(torch.as_tensor(a).cuda(), auto_reset=True)
+        o_ref, r_ref, d_ref = ob.step(a)
+        assert np.array_equal(env.done.cpu().numpy(), d_ref), t
+        assert _rel(env.obs64.cpu().numpy(), o_ref).max() < RTOL_F64, t
+        assert _rel(env.rew64.cpu().numpy(), r_ref).max() < RTOL_F64, t
+        if d_ref.any():
+            am = env.episode_info_angular().cpu().numpy()
+            for i in np.flatnonzero(d_ref)[:8]:
+                ref = ob.env_angular(int(i))[1]
+                assert close_or_both_nan(am[i], ref, 1e-9, 1e-12).all(), (t, i, am[i], ref)
+    env.close()
+
+
 def test_moving_target_classes(cuda_device):
     """linear / sinusoidal targets on the CUDA path: the live-reference fixture (fixed draws), then Philox sampling with
     on_success = "new" resampling against the oracle."""

@@ -253,6 +253,34 @@ def test_oracle_error_integrals_and_strided_observation_rows():
                 assert done == bool(g["done"][ep, t])
 
 
+def test_oracle_attitude_angular_targets():
+    """Target class attitude_angular (fixed_wing.py:671-675, 1455-1460, 1558-1642): omega_p/q/r as derived target states
+    in observations, error and goal rewards, the success streak and the per-state metrics, against a live-reference run
+    (env RNG replaced by fixed draws, u = 0.625: the rate targets sampled at reset derive from the SAMPLED attitude
+    targets before the injected ones override them)."""
+    from conftest import angular_env_config, angular_metric_rows, close_or_both_nan
+    g = load_golden("traj_angular")
+    cfg = build_config(env_cfg=angular_env_config(), sim_config_kw={"turbulence": False}, rng_u_override=0.625)
+    assert cfg.ang_on == 1 and cfg.rew_generic == 1 and cfg.obs_generic == 1 and cfg.obs_n == 16
+    env = O.OracleEnv(cfg)
+    row = 0
+    for ep in range(g["actions"].shape[0]):
+        obs = env.reset(g["init_state"][ep], g["init_target"][ep])
+        assert np.abs(obs - g["obs0"][ep]).max() < 1e-12, ep
+        assert np.abs(env.angular()[0] - g["target0"][ep, 3:]).max() < 1e-12, ep
+        for t in range(int(g["n_valid"][ep])):
+            obs, rew, done, term = env.step(g["actions"][ep, t])
+            assert _rel(obs, g["obs"][ep, t]).max() < 1e-9, (ep, t)
+            assert abs(rew - g["reward"][ep, t]) < 1e-9 * max(1.0, abs(g["reward"][ep, t])), (ep, t)
+            assert _rel(env.angular()[0], g["target"][ep, t, 3:]).max() < 1e-9, (ep, t)
+            assert done == bool(g["done"][ep, t]) and (not done or term == int(g["term"][ep, t]))
+        if done:
+            ours = angular_metric_rows(env.metrics()[0], env.angular()[1])
+            assert close_or_both_nan(ours, g["metrics52"][row], 1e-9, 1e-12).all(), (ep, ours, g["metrics52"][row])
+            row += 1
+    assert row == len(g["metrics52"])
+
+
 def test_oracle_moving_target_classes():
     """Target classes linear / sinusoidal with Va compensate on a sinusoidal pitch target, against a live-reference run
     whose env-level RNG was replaced by fixed draws u (tests/golden/make_golden.py:gen_targets)."""

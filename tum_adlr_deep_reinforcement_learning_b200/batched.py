@@ -10,11 +10,11 @@ import torch
 from . import _lib
 from .config import (FW_NMETRIC, FW_NOBS, FW_NSTATE_INJECT, FW_NY, build_config)
 
-FIELD_Y, FIELD_EULER, FIELD_VAB, FIELD_WIND, FIELD_TARGET, FIELD_CMD, FIELD_TURB, FIELD_COUNTERS, FIELD_NFEV, FIELD_PARAMS = range(10)
+FIELD_Y, FIELD_EULER, FIELD_VAB, FIELD_WIND, FIELD_TARGET, FIELD_CMD, FIELD_TURB, FIELD_COUNTERS, FIELD_NFEV, FIELD_PARAMS, FIELD_ATARGET = range(11)
 _FIELD_SHAPE = {FIELD_Y: (FW_NY, torch.float64), FIELD_EULER: (3, torch.float64), FIELD_VAB: (3, torch.float64),
                 FIELD_WIND: (3, torch.float64), FIELD_TARGET: (3, torch.float64), FIELD_CMD: (3, torch.float64),
                 FIELD_TURB: (6, torch.float64), FIELD_COUNTERS: (4, torch.int32), FIELD_NFEV: (2, torch.int32),
-                FIELD_PARAMS: (48, torch.float64)}
+                FIELD_PARAMS: (48, torch.float64), FIELD_ATARGET: (3, torch.float64)}
 
 
 def _ptr(t):
@@ -182,6 +182,16 @@ class BatchedFixedWing:
         _lib.check(_lib.lib().fw_get_episode_info(self._h, _ptr(term), _ptr(metrics), _ptr(ret), _ptr(length),
                                                   self._stream()), "fw_get_episode_info")
         return term, metrics, ret, length
+
+    def episode_info_angular(self):
+        """attitude_angular configs: [n, 24] float64 device tensor of the omega_p/q/r metrics (avg_error, total_error,
+        end_error, rise_time, overshoot, success, settling_time, success_time_frac x 3, metric-major) of the envs whose
+        done flag was set by the last step."""
+        if getattr(self, "_ang_buf", None) is None:
+            self._ang_buf = torch.zeros(self.n, 24, dtype=torch.float64, device=self.device)
+        _lib.check(_lib.lib().fw_get_episode_info_angular(self._h, _ptr(self._ang_buf), self._stream()),
+                   "fw_get_episode_info_angular")
+        return self._ang_buf
 
     def episode_info_rows(self, idx):
         """Rows `idx` (LongTensor on the device) of (metrics | return | length | term_code | terminal observation) as

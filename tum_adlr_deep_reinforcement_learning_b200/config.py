@@ -26,6 +26,8 @@ FW_F64, FW_F32 = 0, 1
 FW_INT_RK45_SCIPY, FW_INT_RK4_FIXED = 0, 1
 TERM_NAMES = {0: None, 1: "steps", 2: "success", 10: "omega_p", 11: "omega_q", 12: "omega_r", 13: "Va"}
 TARGET_STATES = ("roll", "pitch", "Va")
+ANGULAR_TARGET_STATES = ("omega_p", "omega_q", "omega_r")      # target class attitude_angular: target states 3, 4, 5
+ALL_TARGET_STATES = TARGET_STATES + ANGULAR_TARGET_STATES
 GOAL_STATES = ("roll", "pitch", "Va", "all")
 INIT_STATES = ("roll", "pitch", "yaw", "omega_p", "omega_q", "omega_r", "position_n", "position_e", "position_d",
                "velocity_u", "velocity_v", "velocity_w")
@@ -83,7 +85,17 @@ class FwConfig(ctypes.Structure):
            ("env_kind", _i), ("turb_block_len", _i), ("wp_goal_bound", _d * 3), ("wp_rew_range", _d * 3),
            ("seed", ctypes.c_uint64), ("env_id_offset", ctypes.c_int64),
            ("model_on", _i), ("model_uniform", _i), ("par_enabled", _i * 48), ("par_orig", _d * 48), ("par_var", _d * 48),
-           ("par_clip", _d * 48), ("integration_window", _i), ("obs_step", _i)])
+           ("par_clip", _d * 48), ("integration_window", _i), ("obs_step", _i),
+           ("ang_on", _i), ("_pad_ang", _i), ("ang_max_vel", _d * 3), ("ang_bound", _d * 3)])
+
+
+def _target_index(name, c):
+    """Index of a target state: roll, pitch, Va = 0..2; omega_p/q/r = 3..5 when the config carries attitude_angular targets."""
+    if name in TARGET_STATES:
+        return TARGET_STATES.index(name)
+    if name in ANGULAR_TARGET_STATES and c.ang_on:
+        return 3 + ANGULAR_TARGET_STATES.index(name)
+    raise KeyError("%r is not a target state of this config" % name)
 
 
 def _var(name, **kw):
@@ -405,6 +417,19 @@ def build_config(env_cfg=None, sim_cfg=None, config_kw=None, sim_config_kw=None,
         c.action_bounds_min[j] = act.get("scale_low", -1) * (mult or 0)
     tgt = env["target"]
     tstates = {s["name"]: s for s in tgt["states"]}
+    # target class attitude_angular (fixed_wing.py:671-675, 741-746): omega_p/q/r as derived target states.  The reference
+    # needs all three (sample_target fills all three, _attitude_to_angular_rates reads the props of each)
+    ang = [n_ for n_ in ANGULAR_TARGET_STATES if n_ in tstates]
+    extra = [n_ for n_ in tstates if n_ not in ALL_TARGET_STATES]
+    if extra:
+        raise NotImplementedError("target states %r" % extra)
+    if ang and (len(ang) != 3 or any(tstates[n_].get("class") != "attitude_angular" for n_ in ang)):
+        raise NotImplementedError("omega_p / omega_q / omega_r targets: all three, of class attitude_angular")
+    c.ang_on = int(bool(ang))
+    for a, n_ in enumerate(ANGULAR_TARGET_STATES):
+        p_ = tstates.get(n_, {})
+        c.ang_max_vel[a] = float(p_.get("max_vel", np.radians(180)))
+        c.ang_bound[a] = np.inf if p_.get("bound") is None else float(p_["bound"])      # raw props: no degree conversion
     for k, name in enumerate(TARGET_STATES):
         s = tstates[name]
         rad = s.get("convert_to_radians", False)
@@ -431,7 +456,7 @@ def build_config(env_cfg=None, sim_cfg=None, config_kw=None, sim_config_kw=None,
         c.tgt_bound[k] = np.inf if bound is None else bound
         cls = s.get("class", "constant")
         if cls not in ("constant", "compensate", "linear", "sinusoidal"):
-            raise NotImplementedError("target class %r (SURVEY §8f 'next' row 1)" % cls)
+            raise NotImplementedError("target class %r for state %r" % (cls, name))
         if cls == "compensate" and name != "Va":
             raise NotImplementedError("target class compensate is only defined for Va (fixed_wing.py:1432-1435)")
         c.tgt_class[k] = {"constant": 0, "compensate": 1, "linear": 2, "sinusoidal": 3}[cls]
@@ -473,6 +498,7 @@ def build_config(env_cfg=None, sim_cfg=None, config_kw=None, sim_config_kw=None,
             simple = simple and key not in seen
         seen.add(key)
         default_family = default_family and simple
+    default_family = default_family and not c.ang_on      # angular targets live in the general env head only
     c.rew_generic = int(not default_family)
     if default_family:
         for f in rew["factors"]:
@@ -507,9 +533,9 @@ def build_config(env_cfg=None, sim_cfg=None, config_kw=None, sim_config_kw=None,
             c.rew_sign[i] = float(np.sign(f.get("sign", -1)))
             c.rew_window[i] = int(f.get("window_size", 0) or 0)
             if cls == "state" and typ == "error":
-                c.rew_class[i], c.rew_idx[i] = 0, TARGET_STATES.index(f["name"])
+                c.rew_class[i], c.rew_idx[i] = 0, _target_index(f["name"], c)
             elif cls == "state" and typ == "int_error":
-                c.rew_class[i], c.rew_idx[i] = 9, TARGET_STATES.index(f["name"])
+                c.rew_class[i], c.rew_idx[i] = 9, _target_index(f["name"], c)
             elif cls == "state" and typ == "value":
                 if f["name"] not in state_names:
                     raise NotImplementedError("reward on state %r" % f["name"])
@@ -529,6 +555,9 @@ def build_config(env_cfg=None, sim_cfg=None, config_kw=None, sim_config_kw=None,
                 c.rew_value[i] = 0.0 if f["value"] == "timesteps" else float(f["value"])
             elif cls == "step":
                 c.rew_class[i], c.rew_value[i] = 6, float(f["value"])
+            elif cls == "goal" and typ == "per_state" and c.ang_on and not all(np.isfinite(c.ang_bound[a]) for a in range(3)):
+                # the reference indexes history["goal"][state] for EVERY target state here (fixed_wing.py:1038-1044)
+                raise KeyError("goal per_state reward needs a bound on every target state, omega_p / omega_q / omega_r included")
             elif cls == "goal" and typ in ("per_state", "all"):
                 c.rew_class[i], c.rew_value[i] = (7 if typ == "per_state" else 8), float(f["value"])
             else:
@@ -579,7 +608,7 @@ def build_config(env_cfg=None, sim_cfg=None, config_kw=None, sim_config_kw=None,
             value = s_.get("value", "absolute")
             if value not in ("absolute", "relative", "integrator"):
                 raise ValueError("Unexpected observation variable target value type: %r" % value)
-            c.obs_kind[e], c.obs_idx[e] = {"absolute": 1, "relative": 2, "integrator": 4}[value], TARGET_STATES.index(s_["name"])
+            c.obs_kind[e], c.obs_idx[e] = {"absolute": 1, "relative": 2, "integrator": 4}[value], _target_index(s_["name"], c)
         elif kind == "action":
             c.obs_kind[e], c.obs_idx[e] = 3, act_names.index(s_["name"])
             c.obs_window[e] = int(s_.get("window_size", 1))

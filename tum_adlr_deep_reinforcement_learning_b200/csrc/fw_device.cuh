@@ -124,6 +124,8 @@ template <typename T> struct DCfg {
     int obs_kind[FW_OBS_ENTRIES_MAX], obs_idx[FW_OBS_ENTRIES_MAX], obs_window[FW_OBS_ENTRIES_MAX], obs_norm_flag[FW_OBS_ENTRIES_MAX];
     T obs_mean[FW_OBS_ENTRIES_MAX], obs_var[FW_OBS_ENTRIES_MAX], obs_init_noise;
     int integration_window, obs_step, obs_has_int;
+    int ang_on;                          // target class attitude_angular: omega_p/q/r are target states 3..5
+    T ang_max_vel[3], ang_bound[3];
     unsigned long long seed;
     long long env_id_offset;
 };
@@ -164,7 +166,11 @@ enum RField {
     RF_GCMD = 170,            // 8 x 3
     RF_PREV_SHAPING = 194,    // 3: prev_shaping per function class of the general reward engine (NaN = None)
     RF_TPROP = 197,           // 15: slope3 amplitude3 period3 phase3 bias3 of moving targets (tgt_moving only)
-    RF_COUNT = 212
+    // target class attitude_angular only (ang_on): the rate targets of omega_p/q/r and their error statistics
+    RF_ATGT = 212,            // 3
+    RF_AE0 = 215, RF_AESUM = 218, RF_AEABS = 221, RF_AEMIN = 224, RF_AEMAX = 227, RF_AEPREV = 230,   // 3 each
+    RF_AHIST = 233,           // 4 older rows of (3 rate targets, 3 rate errors) for observation rows with a lag
+    RF_COUNT = 257
 };
 enum IField {
     IF_STEPS = 0, IF_STEPS_TGT, IF_EPISODE, IF_SIM_STEP,
@@ -179,7 +185,10 @@ enum IField {
     IF_TCLS = 44,             // 3: per-env target class (an injected target forces constant, fixed_wing.py:446-450)
     IF_GOAL_ACHIEVED = 43,    // self.goal_achieved: set by the first success, never cleared (fixed_wing.py:81, 546-547)
     IF_SEED_LO = 48, IF_SEED_HI = 49,   // Philox key of the running episode = ResetCfg.seed when the episode was reset
-    IF_COUNT = 50
+    // attitude_angular only: goal rings / counters / rise indices of omega_p/q/r (same meaning as the base ones)
+    IF_AGOAL_RING = 50,       // 3 states x 4 words
+    IF_AGOAL_CNT = 62, IF_AGOAL_TOTAL = 65, IF_ASETTLE = 68, IF_ARISE_LO = 71, IF_ARISE_HI = 74,   // 3 each
+    IF_COUNT = 77
 };
 
 // Per-env aircraft parameters (model_on handles): S.par holds, per env, the FW_NPARAM base parameters in FwConfig order
@@ -212,6 +221,8 @@ template <typename T> struct Soa {
     int wp_n_tasks, wp_len;
     const ResetCfg<T>* rc;       // device memory (fw_set_config)
     T* par;                      // [FW_PAR_FIELDS][n] per-env aircraft parameters, or nullptr (model off)
+    T* err_ring_a;               // [FW_END_ERR_WINDOW * 3][n] error ring of omega_p/q/r, or nullptr (no attitude_angular targets)
+    double* metrics_a;           // [n][FW_NMETRIC_ANG] (written on done), or nullptr
 };
 
 // the Philox key of env's running episode
@@ -828,21 +839,135 @@ __device__ __forceinline__ void write_obs(const T* o, int dim, int env, float* o
     if (obs64) for (int j = 0; j < dim; ++j) obs64[(size_t)env * dim + j] = (double)o[j];
 }
 
+// ---------------- target class attitude_angular (fixed_wing.py:671-675, 741-746, 1455-1460, 1558-1642) ----------------
+// _attitude_to_angular_rates for omega state a (0 p, 1 q, 2 r) from the CURRENT roll / pitch errors, attitude and rate
+// targets.  The reference's `damping = 0.05` branches are overwritten unconditionally (kept so); divisions by cos / sin of
+// the roll angle are unguarded there and here.
+template <typename T>
+__device__ __noinline__ T attitude_to_angular_rate(const DCfg<T>& c, int a, T roll, T pitch, T roll_err, T pitch_err,
+                                                   const T (&atgt)[3]) {
+    const T max_vel = c.ang_max_vel[a], HALF_PI = (T)(0.5 * 3.141592653589793238462643383279502884);
+    T r_w, q_w;
+    M<T>::sincos(roll, &r_w, &q_w);
+    const T max_pitch_change = max_vel * c.dt * (q_w + r_w);
+    T res, damping;
+    if (a == 0) {
+        damping = M<T>::fabs(roll_err / HALF_PI);
+        const T tp = (T)::tan((double)pitch);
+        const T q_roll = r_w * tp * atgt[1] * c.dt, r_roll = q_w * tp * atgt[2] * c.dt;
+        res = clip(-(roll_err - q_roll - r_roll) / c.dt, -max_vel, max_vel);
+    } else if (a == 1) {
+        damping = M<T>::fabs(pitch_err / HALF_PI);
+        if (max_pitch_change > M<T>::fabs(pitch_err)) res = -pitch_err / ((T)2 * q_w);
+        else res = sgn(q_w) * max_vel * sgn(pitch_err);
+    } else {
+        damping = M<T>::fabs(pitch_err / HALF_PI);
+        if (max_pitch_change > M<T>::fabs(pitch_err)) res = pitch_err / r_w;
+        else res = -sgn(r_w) * max_vel * sgn(pitch_err);
+    }
+    if (M<T>::isnan(damping)) damping = (T)0.05; else damping = M<T>::fmin((T)1, damping);
+    return clip(atgt[a] + (res * damping - atgt[a]) * (T)1 / (T)20, -max_vel, max_vel);
+}
+
+// the three rate targets from the same inputs (every value from the OLD targets, like the dict the reference builds
+// before it assigns, fixed_wing.py:609-612); from_zero: sample_target's re-derivation from zeroed rate targets (:671-746)
+template <typename T>
+__device__ __noinline__ void angular_targets(const DCfg<T>& c, T roll, T pitch, T roll_err, T pitch_err, bool from_zero,
+                                             T (&atgt)[3]) {
+    T old[3] = {atgt[0], atgt[1], atgt[2]};
+    if (from_zero) old[0] = old[1] = old[2] = 0;
+#pragma unroll 1
+    for (int a = 0; a < 3; ++a) atgt[a] = attitude_to_angular_rate<T>(c, a, roll, pitch, roll_err, pitch_err, old);
+}
+
+// goal ring / streak bookkeeping of the three rate targets for history["goal"] entry `idx` (the code of the base states
+// in head_kernel, on the IF_AGOAL_* fields)
+template <typename T>
+__device__ __noinline__ void angular_goal_update(const DCfg<T>& c, const Soa<T>& S, int env, int idx, const int (&ga)[3]) {
+    const int n = S.n;
+    int32_t* ii = S.i + env;
+    const int w = (idx & 127) >> 5, b = idx & 31, idx_old = idx - c.streak_req;
+#pragma unroll 1
+    for (int a = 0; a < 3; ++a) {
+        int32_t* ring = ii + (IF_AGOAL_RING + 4 * a) * n;
+        int cnt = ii[(IF_AGOAL_CNT + a) * n], tot = ii[(IF_AGOAL_TOTAL + a) * n], settle = ii[(IF_ASETTLE + a) * n];
+        if (idx_old >= 0) cnt -= (ring[((idx_old & 127) >> 5) * n] >> (idx_old & 31)) & 1;
+        uint32_t word = (uint32_t)ring[w * n];
+        word = (word & ~(1u << b)) | ((uint32_t)ga[a] << b);
+        ring[w * n] = (int32_t)word;
+        cnt += ga[a]; tot += ga[a];
+        if (settle < 0 && idx + 1 >= c.streak_req && (double)cnt / (double)c.streak_req >= (double)c.streak_fraction) settle = idx;
+        ii[(IF_AGOAL_CNT + a) * n] = cnt; ii[(IF_AGOAL_TOTAL + a) * n] = tot; ii[(IF_ASETTLE + a) * n] = settle;
+    }
+}
+
+// streamed error statistics of the rate targets for the new history["error"] entry (index n_err), as for the base states
+template <typename T>
+__device__ __noinline__ void angular_stats_update(const DCfg<T>& c, const Soa<T>& S, int env, int n_err, const T (&ea)[3]) {
+    const int n = S.n;
+    T* r = S.r + env;
+    int32_t* ii = S.i + env;
+#pragma unroll 1
+    for (int a = 0; a < 3; ++a) {
+        const T e0 = r[(RF_AE0 + a) * n], v = ea[a], av = M<T>::fabs(v), prev = r[(RF_AEPREV + a) * n];
+        const T low_lim = M<T>::fabs(c.rise_low * e0), high_lim = M<T>::fabs(c.rise_high * e0);
+        if (ii[(IF_ARISE_LO + a) * n] < 0 && prev >= low_lim && av < low_lim) ii[(IF_ARISE_LO + a) * n] = n_err - 1;
+        if (ii[(IF_ARISE_HI + a) * n] < 0 && prev >= high_lim && av < high_lim) ii[(IF_ARISE_HI + a) * n] = n_err - 1;
+        r[(RF_AESUM + a) * n] += v; r[(RF_AEABS + a) * n] += av;
+        r[(RF_AEMIN + a) * n] = M<T>::fmin(r[(RF_AEMIN + a) * n], v); r[(RF_AEMAX + a) * n] = M<T>::fmax(r[(RF_AEMAX + a) * n], v);
+        r[(RF_AEPREV + a) * n] = av;
+        S.err_ring_a[(size_t)((n_err % FW_END_ERR_WINDOW) * 3 + a) * n + env] = v;
+    }
+}
+
+// the 24 metrics of the rate targets at the end of an episode (get_metric, fixed_wing.py:1644-1736; metric-major)
+template <typename T>
+__device__ __noinline__ void angular_metrics(const DCfg<T>& c, const Soa<T>& S, int env, int n_err, int n_goal, int off) {
+    const int n = S.n;
+    const T* r = S.r + env;
+    const int32_t* ii = S.i + env;
+    double* m = S.metrics_a + (size_t)env * FW_NMETRIC_ANG;
+    const int end_cnt = n_err < FW_END_ERR_WINDOW ? n_err : FW_END_ERR_WINDOW;
+#pragma unroll 1
+    for (int a = 0; a < 3; ++a) {
+        const T e0 = r[(RF_AE0 + a) * n];
+        T s50 = 0;
+#pragma unroll 1
+        for (int t = n_err - end_cnt; t < n_err; ++t) s50 += S.err_ring_a[(size_t)((t % FW_END_ERR_WINDOW) * 3 + a) * n + env];
+        m[0 + a] = (M<T>::fabs(e0) >= (T)0.01) ? (double)M<T>::fabs((r[(RF_AESUM + a) * n] / (T)n_err) / e0) : CUDART_NAN;
+        m[3 + a] = (double)r[(RF_AEABS + a) * n];
+        m[6 + a] = (double)M<T>::fabs(s50 / (T)end_cnt);
+        const int lo = ii[(IF_ARISE_LO + a) * n], hi = ii[(IF_ARISE_HI + a) * n];
+        m[9 + a] = (lo >= 0 ? (double)(lo + off) : CUDART_NAN) - (hi >= 0 ? (double)(hi + off) : CUDART_NAN);
+        const T opp = (e0 > (T)0) ? r[(RF_AEMIN + a) * n] : r[(RF_AEMAX + a) * n];
+        m[12 + a] = (sgn(opp) == sgn(e0)) ? CUDART_NAN : (double)M<T>::fabs(opp / e0);
+        const int settle = ii[(IF_ASETTLE + a) * n];
+        m[15 + a] = settle >= 0 ? 1.0 : 0.0;
+        m[18 + a] = settle >= 0 ? (double)settle : CUDART_NAN;
+        m[21 + a] = (double)ii[(IF_AGOAL_TOTAL + a) * n] / (double)n_goal;
+    }
+}
+
 // sum of history["error"][name][start:stop] (absolute entry indices, clamped like a python slice to [0, len]) from the
 // 50-deep error ring of the end_error metric, oldest first.  Callers keep stop - start + lag below the ring depth.
 template <typename T>
 __device__ __forceinline__ T err_ring_sum(const Soa<T>& S, int env, int k, int start, int stop, int len) {
     if (start < 0) start = 0;
     if (stop > len) stop = len;
+    const T* ring = k < 3 ? S.err_ring : S.err_ring_a;         // target states 3..5: the rate targets' own ring
+    const int kk = k < 3 ? k : k - 3;
     T s = 0;
 #pragma unroll 1
-    for (int t = start; t < stop; ++t) s += S.err_ring[(size_t)((t % FW_END_ERR_WINDOW) * 3 + k) * S.n + env];
+    for (int t = start; t < stop; ++t) s += ring[(size_t)((t % FW_END_ERR_WINDOW) * 3 + kk) * S.n + env];
     return s;
 }
 
 // The value an "integrator" observation entry takes in the reset observation that follows an episode whose error history
 // has `len` entries and first entry e0: every row is clamped to lag 1 with steps_count = 0 (fixed_wing.py:1141-1180), so
 // sum(history[-W-1:-1]) + (W + 1) * history[0].
+__device__ __forceinline__ int e0_field(int k) { return k < 3 ? RF_E0 + k : RF_AE0 + k - 3; }
+__device__ __forceinline__ int esum_field(int k) { return k < 3 ? RF_ESUM + k : RF_AESUM + k - 3; }
+
 template <typename T>
 __device__ __forceinline__ T integrator_reset_value(const DCfg<T>& c, const Soa<T>& S, int env, int k, int len, T e0) {
     const int W = c.integration_window;
@@ -853,9 +978,9 @@ __device__ __forceinline__ T integrator_reset_value(const DCfg<T>& c, const Soa<
 // function classes, shaping and plain parts per term, absolute or potential form.  Out of line: the default factor
 // family has its own straight-line code in the head kernel.
 template <typename T>
-__device__ __noinline__ T generic_reward(const DCfg<T>& c, const Soa<T>& S, int env, const T (&eg)[3], const T (&st8)[8],
+__device__ __noinline__ T generic_reward(const DCfg<T>& c, const Soa<T>& S, int env, const T (&eg)[6], const T (&st8)[8],
                                          const T (&a_raw)[3], bool act_f32, const T* aring, int n_prev, int steps,
-                                         const int (&gbits)[4], bool success) {
+                                         const int (&gbits)[7] /* roll pitch Va all omega_p omega_q omega_r */, bool success) {
     const int n = S.n;
     T val_t[3] = {0, 0, 0}, shp_t[3] = {0, 0, 0};
 #pragma unroll 1
@@ -868,10 +993,10 @@ __device__ __noinline__ T generic_reward(const DCfg<T>& c, const Soa<T>& S, int 
             // history["error"] holds `steps` entries here (this step's is appended after the reward); [-0:] is the whole
             // list, whose sum the metrics already carry (fixed_wing.py:1003-1012)
             const int W = c.integration_window, k = c.rew_idx[i];
-            if (W == 0) val = S.r[(RF_ESUM + k) * n + env];
+            if (W == 0) val = S.r[esum_field(k) * n + env];
             else {
                 val = err_ring_sum<T>(S, env, k, steps - W, steps, steps);
-                if (steps < W) val += (T)(W - steps) * S.r[(RF_E0 + k) * n + env];
+                if (steps < W) val += (T)(W - steps) * S.r[e0_field(k) * n + env];
             }
         } else if (cls == FW_RF_ACTION_VALUE) {
             if (act_f32) { float sa = 0.f; for (int j = 0; j < 3; ++j) sa += fabsf((float)a_raw[j]); val = (T)sa; }
@@ -909,8 +1034,10 @@ __device__ __noinline__ T generic_reward(const DCfg<T>& c, const Soa<T>& S, int 
         } else if (cls == FW_RF_SUCCESS) {
             val = success ? (c.rew_value_timesteps[i] ? (T)(c.steps_max - steps) : c.rew_value[i]) : (T)0;
         } else if (cls == FW_RF_STEP) val = c.rew_value[i];
-        else if (cls == FW_RF_GOAL_PER_STATE) {
-            for (int k = 0; k < 3; ++k) val += gbits[k] ? c.rew_value[i] / (T)3 : (T)0;
+        else if (cls == FW_RF_GOAL_PER_STATE) {          // value / len(self.target) per achieved state
+            const T nt = c.ang_on ? (T)6 : (T)3;
+            for (int k = 0; k < 3; ++k) val += gbits[k] ? c.rew_value[i] / nt : (T)0;
+            if (c.ang_on) for (int k = 4; k < 7; ++k) val += gbits[k] ? c.rew_value[i] / nt : (T)0;
         } else if (cls == FW_RF_GOAL_ALL) val = gbits[3] ? c.rew_value[i] : (T)0;
         // values derived from a float32 action array stay float32 through the function class
         const bool f32v = act_f32 && (cls == FW_RF_ACTION_DELTA || cls == FW_RF_ACTION_VALUE);
@@ -955,7 +1082,8 @@ __device__ __noinline__ void generic_observation(const DCfg<T>& c, const Soa<T>&
                                                  const T (&cur)[14] /* 8 states, 3 targets, 3 errors */,
                                                  const T (&a_raw)[3], bool act_f32, const T (&cmd_in)[3],
                                                  const T (&actval)[3], unsigned long long episode, T* o,
-                                                 const T* int_reset /* reset observation: integrator values, else null */) {
+                                                 const T* int_reset /* reset observation: integrator values (6), else null */,
+                                                 const T* acur = nullptr /* attitude_angular: 3 rate targets, 3 rate errors */) {
     const int n = S.n, L = c.obs_len, ne = c.obs_n;
     T* r = S.r + env;
     T hist[4][14], gact[24], gcmd[24];
@@ -992,8 +1120,12 @@ __device__ __noinline__ void generic_observation(const DCfg<T>& c, const Soa<T>&
                 else {
                     const int W = c.integration_window;
                     val = err_ring_sum<T>(S, env, idx, hist_len - W - ie, hist_len - ie, hist_len);
-                    if (steps - ie < W) val += (T)(W - (steps - ie)) * r[(RF_E0 + idx) * n];
+                    if (steps - ie < W) val += (T)(W - (steps - ie)) * r[e0_field(idx) * n];
                 }
+            } else if (kind != FW_OBS_ACTION && idx >= 3 && (kind == FW_OBS_TARGET_ABS || kind == FW_OBS_TARGET_REL)) {
+                // a rate target (attitude_angular) or its error: current values, or the row of RF_AHIST
+                const int q = (kind == FW_OBS_TARGET_ABS ? 0 : 3) + idx - 3;
+                val = (ie == 1) ? acur[q] : r[(RF_AHIST + (ie - 2) * 6 + q) * n];
             } else if (kind != FW_OBS_ACTION) {
                 const int q = (kind == FW_OBS_STATE) ? idx : (kind == FW_OBS_TARGET_ABS ? 8 + idx : 11 + idx);
                 val = (ie == 1) ? cur[q] : hist[ie - 2][q];
@@ -1022,6 +1154,12 @@ __device__ __noinline__ void generic_observation(const DCfg<T>& c, const Soa<T>&
         }
     }
     if (c.obs_noise_std > (T)0 || c.obs_noise_mean != (T)0) add_obs_noise<T>(c, env_seed(S, env), c.env_id_offset + env, episode, steps, o, L * ne);
+    if (push && acur) {
+#pragma unroll 1
+        for (int k = 3; k >= 1; --k)
+            for (int q = 0; q < 6; ++q) r[(RF_AHIST + k * 6 + q) * n] = r[(RF_AHIST + (k - 1) * 6 + q) * n];
+        for (int q = 0; q < 6; ++q) r[(RF_AHIST + q) * n] = acur[q];
+    }
     if (push) {
 #pragma unroll 1
         for (int k = 3; k >= 1; --k)
@@ -1037,7 +1175,7 @@ __device__ __noinline__ void generic_observation(const DCfg<T>& c, const Soa<T>&
 // entries were computed as 0): (0 - mean) / var + v / var for a normalised entry, every row alike.
 template <typename T, typename SpareT>
 __device__ __noinline__ void patch_integrator_reset_obs(const DCfg<T>& c, const SpareT& P, int env, int odim,
-                                                        const T (&v)[3], float* obs, double* obs64) {
+                                                        const T (&v)[6], float* obs, double* obs64) {
 #pragma unroll 1
     for (int row = 0; row < c.obs_len; ++row)
 #pragma unroll 1
@@ -1117,14 +1255,14 @@ __device__ void reset_env(const DCfg<T>& c, const Soa<T>& S, int env, const doub
     // entries read the error history of the episode that is being replaced (fixed_wing.py:453-460, 1165-1180): taken
     // from the live ring before the row is rewritten; a precomputed row carries 0 there and head_kernel adds the value
     // when the row is consumed.  An env that was never reset has no history: error * window, filled in below.
-    T int_reset[3] = {0, 0, 0};
+    T int_reset[6] = {0, 0, 0, 0, 0, 0};
     const bool int_none = live && episode == 1ull;
     if (live && c.obs_generic && c.obs_has_int && !int_none) {
         const int steps_prev = S.i[IF_STEPS * n + env];
         const int failed = steps_prev > 0 && S.ep_term[env] >= FW_TERM_OMEGA_P;        // a failed step appends no error entry
         const int len = steps_prev + (failed ? 0 : 1);
 #pragma unroll 1
-        for (int k = 0; k < 3; ++k) int_reset[k] = integrator_reset_value<T>(c, S, env, k, len, S.r[(RF_E0 + k) * n + env]);
+        for (int k = 0; k < (c.ang_on ? 6 : 3); ++k) int_reset[k] = integrator_reset_value<T>(c, S, env, k, len, S.r[e0_field(k) * n + env]);
     }
     const long long gid = c.env_id_offset + env;
     const ResetCfg<T>& rc = *S.rc;
@@ -1200,6 +1338,9 @@ __device__ void reset_env(const DCfg<T>& c, const Soa<T>& S, int env, const doub
     for (int k = 0; k < 15; ++k) tp[k] = 0;
     target_draws<T>(c, seed, gid, episode, RNG_RESET, 8u, u12);       // blocks 8..13 of the reset stream (0..7: state, wind)
     sample_target<T>(c, rc, roll, pitch, Va, 0, u12, tgt, tcls, tp);
+    // attitude_angular: the rate targets derive from the SAMPLED attitude targets, before injected ones override them
+    T atgt[3] = {0, 0, 0};
+    if (c.ang_on) angular_targets<T>(c, roll, pitch, err_roll(tgt[0], roll), tgt[1] - pitch, true, atgt);
     if (target_in) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -1235,6 +1376,26 @@ __device__ void reset_env(const DCfg<T>& c, const Soa<T>& S, int env, const doub
         S.err_ring[(size_t)(0 * 3 + k) * n + env] = e[k];
         gbits[k] = M<T>::fabs(e[k]) <= c.tgt_bound[k];
         gbits[3] &= gbits[k];
+    }
+    T ea[3] = {0, 0, 0};
+    if (c.ang_on) {
+#pragma unroll 1
+        for (int a = 0; a < 3; ++a) {
+            ea[a] = atgt[a] - y[4 + a];
+            const int ga = M<T>::fabs(ea[a]) <= c.ang_bound[a];
+            gbits[3] &= ga;
+            r[(RF_ATGT + a) * n] = atgt[a];
+            r[(RF_AE0 + a) * n] = ea[a]; r[(RF_AESUM + a) * n] = ea[a]; r[(RF_AEABS + a) * n] = M<T>::fabs(ea[a]);
+            r[(RF_AEMIN + a) * n] = ea[a]; r[(RF_AEMAX + a) * n] = ea[a]; r[(RF_AEPREV + a) * n] = M<T>::fabs(ea[a]);
+            S.err_ring_a[(size_t)a * n + env] = ea[a];
+            ii[(IF_AGOAL_RING + 4 * a) * n] = ga;
+            ii[(IF_AGOAL_RING + 4 * a + 1) * n] = 0; ii[(IF_AGOAL_RING + 4 * a + 2) * n] = 0; ii[(IF_AGOAL_RING + 4 * a + 3) * n] = 0;
+            ii[(IF_AGOAL_CNT + a) * n] = ga; ii[(IF_AGOAL_TOTAL + a) * n] = ga;
+            ii[(IF_ASETTLE + a) * n] = (c.streak_req == 1 && (double)ga >= (double)c.streak_fraction) ? 0 : -1;
+            ii[(IF_ARISE_LO + a) * n] = -1; ii[(IF_ARISE_HI + a) * n] = -1;
+        }
+        for (int q = 0; q < 3; ++q) { r[(RF_AHIST + q) * n] = atgt[q]; r[(RF_AHIST + 3 + q) * n] = ea[q]; }
+        for (int q = 6; q < 24; ++q) r[(RF_AHIST + q) * n] = 0;
     }
     r[RF_EP_RET * n] = 0;
 #pragma unroll
@@ -1275,8 +1436,9 @@ __device__ void reset_env(const DCfg<T>& c, const Soa<T>& S, int env, const doub
         T og[FW_NOBS_MAX];
         const T zero3[3] = {0, 0, 0};
         if (int_none)
-            for (int k = 0; k < 3; ++k) int_reset[k] = e[k] * (T)c.integration_window;
-        generic_observation<T>(c, S, env, 0, false, cur, zero3, false, zero3, av, episode, og, int_reset);
+            for (int k = 0; k < 3; ++k) { int_reset[k] = e[k] * (T)c.integration_window; int_reset[3 + k] = ea[k] * (T)c.integration_window; }
+        const T acur[6] = {atgt[0], atgt[1], atgt[2], ea[0], ea[1], ea[2]};
+        generic_observation<T>(c, S, env, 0, false, cur, zero3, false, zero3, av, episode, og, int_reset, c.ang_on ? acur : nullptr);
         write_obs(og, obs_dim(c), env, obs, obs64);
         return;
     }

@@ -64,6 +64,7 @@ __device__ __forceinline__ Soa<T> spare_view(const Spare<T>& P, int env) {
     L.r += (size_t)env * (RF_COUNT - 1);
     L.i += (size_t)env * (IF_COUNT - 1);
     L.err_ring += (size_t)env * 2;
+    if (L.err_ring_a) L.err_ring_a += (size_t)env * 2;
     if (L.par) L.par += (size_t)env * (FW_PAR_FIELDS - 1);
     L.n = 1;
     return L;
@@ -115,6 +116,7 @@ __device__ __forceinline__ void take_spare_warp(const Soa<T>& S, const Spare<T>&
             }
         }
         if (rank < 3) S.err_ring[(size_t)rank * n + e] = P.S2.err_ring[(size_t)e * 3 + rank];
+        if (rank < 3 && S.err_ring_a) S.err_ring_a[(size_t)rank * n + e] = P.S2.err_ring_a[(size_t)e * 3 + rank];
         if (S.par)          // the next episode's aircraft parameters (simulator.model)
             for (int f = rank; f < FW_PAR_FIELDS; f += width) S.par[(size_t)f * n + e] = P.S2.par[(size_t)e * FW_PAR_FIELDS + f];
         for (int q = rank; q < odim; q += width) {
@@ -713,7 +715,13 @@ __global__ void __launch_bounds__(64, 8) head_kernel(const __grid_constant__ DCf
     T e_new[3] = {0, 0, 0};
     T reward;
     T obs_v[FW_NOBS];
-    int gbits[4] = {0, 0, 0, 0};
+    int gbits[7] = {0, 0, 0, 0, 1, 1, 1};       // roll pitch Va all | omega_p omega_q omega_r (attitude_angular)
+    T atgt[3] = {0, 0, 0}, ea_new[3] = {0, 0, 0};
+    const bool ang = GENERIC && c.ang_on;
+    if (ang) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) atgt[a] = r[(RF_ATGT + a) * n];
+    }
     int gcnt[4], gtot[4], settle[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -721,12 +729,18 @@ __global__ void __launch_bounds__(64, 8) head_kernel(const __grid_constant__ DCf
     }
     if (!fail) {
         // goal status with the CURRENT target (fixed_wing.py:536-560)
-        const T eg[3] = {err_roll(tgt[0], roll), tgt[1] - pitch, tgt[2] - Va};
-        bool resample = false, success_on_step = false;
+        const T eg[6] = {err_roll(tgt[0], roll), tgt[1] - pitch, tgt[2] - Va, atgt[0] - y[4], atgt[1] - y[5], atgt[2] - y[6]};
+        bool resample = false, success_on_step = false, resampled = false;
         if (c.streak_req > 0) {
             gbits[3] = 1;
 #pragma unroll
             for (int k = 0; k < 3; ++k) { gbits[k] = M<T>::fabs(eg[k]) <= c.tgt_bound[k]; gbits[3] &= gbits[k]; }
+            if (ang) {              // bounded rate targets take part in "all" (fixed_wing.py:1346-1361)
+#pragma unroll
+                for (int a = 0; a < 3; ++a) { gbits[4 + a] = M<T>::fabs(eg[3 + a]) <= c.ang_bound[a]; gbits[3] &= gbits[4 + a]; }
+                const int ga[3] = {gbits[4], gbits[5], gbits[6]};
+                angular_goal_update<T>(c, S, env, steps, ga);
+            }
             const int idx = steps;                 // index of this entry in history["goal"] (entry 0 = reset)
             const int w = (idx & 127) >> 5, b = idx & 31;
             const int idx_old = idx - c.streak_req;
@@ -796,12 +810,20 @@ __global__ void __launch_bounds__(64, 8) head_kernel(const __grid_constant__ DCf
             target_draws<T>(c, env_seed(S, env), c.env_id_offset + env, episode, RNG_RESAMPLE, (uint32_t)(steps * 8), u12);
             sample_target<T>(c, *S.rc, roll, pitch, Va, steps, u12, tgt, tcls, tp);
             steps_tgt = 0;
+            resampled = true;
             if (c.tgt_moving) {
 #pragma unroll
                 for (int k = 0; k < 15; ++k) r[(RF_TPROP + k) * n] = tp[k];
 #pragma unroll
                 for (int k = 0; k < 3; ++k) ii[(IF_TCLS + k) * n] = tcls[k];
             }
+        }
+        if (ang) {
+            // rate targets: re-derived from zero by a resample (sample_target), then advanced — every value from the
+            // targets BEFORE this step's advance (fixed_wing.py:574-580, 1455-1460)
+            const T er = err_roll(tgt[0], roll), ep = tgt[1] - pitch;
+            if (resampled) angular_targets<T>(c, roll, pitch, er, ep, true, atgt);
+            angular_targets<T>(c, roll, pitch, er, ep, false, atgt);
         }
         const T tgt_pitch_cur = tgt[1];
         if (GENERIC && c.tgt_moving) {
@@ -839,6 +861,7 @@ __global__ void __launch_bounds__(64, 8) head_kernel(const __grid_constant__ DCf
             if (M<T>::fabs(tgt[0]) > PI) tgt[0] = sgn(tgt[0]) * (py_mod(M<T>::fabs(tgt[0]), PI) - PI);
         }
         e_new[0] = err_roll(tgt[0], roll); e_new[1] = tgt[1] - pitch; e_new[2] = tgt[2] - Va;
+        if (ang) { ea_new[0] = atgt[0] - y[4]; ea_new[1] = atgt[1] - y[5]; ea_new[2] = atgt[2] - y[6]; }
     } else {
         done = true;
         term = fail;
@@ -868,7 +891,10 @@ __global__ void __launch_bounds__(64, 8) head_kernel(const __grid_constant__ DCf
         const T cur[14] = {roll, pitch, Va, om_obs[0], om_obs[1], om_obs[2], alpha, beta, tgt[0], tgt[1], tgt[2],
                            e_cur[0], e_cur[1], e_cur[2]};
         const T actval[3] = {(y[13] + y[14]) / (T)2, (-y[13] + y[14]) / (T)2, y[15]};
-        generic_observation<T>(c, S, env, steps, !fail, cur, a_raw, act_f32, cmd_in, actval, episode, og, (const T*)nullptr);
+        const T acur[6] = {atgt[0], atgt[1], atgt[2], fail ? atgt[0] - om_obs[0] : ea_new[0], fail ? atgt[1] - om_obs[1] : ea_new[1],
+                           fail ? atgt[2] - om_obs[2] : ea_new[2]};
+        generic_observation<T>(c, S, env, steps, !fail, cur, a_raw, act_f32, cmd_in, actval, episode, og, (const T*)nullptr,
+                               ang ? acur : (const T*)nullptr);
         obs_out = og;
         odim = c.obs_len * c.obs_n;
     }
@@ -896,6 +922,7 @@ __global__ void __launch_bounds__(64, 8) head_kernel(const __grid_constant__ DCf
             r[(RF_EPREV + k) * n] = ea;
             S.err_ring[(size_t)((n_err % FW_END_ERR_WINDOW) * 3 + k) * n + env] = e_new[k];
         }
+        if (ang) angular_stats_update<T>(c, S, env, n_err, ea_new);
         n_err += 1;
     }
 
@@ -927,6 +954,7 @@ __global__ void __launch_bounds__(64, 8) head_kernel(const __grid_constant__ DCf
         }
         S.ep_ret[env] = (double)ep_ret;
         S.ep_len[env] = steps;
+        if (ang) angular_metrics<T>(c, S, env, n_err, n_goal, off);
     }
     S.ep_term[env] = term;
     if (io.rew) io.rew[env] = (float)reward;
@@ -939,11 +967,12 @@ __global__ void __launch_bounds__(64, 8) head_kernel(const __grid_constant__ DCf
     if (take && io.term_obs) write_obs(obs_out, odim, env, io.term_obs, (double*)nullptr);
     // "integrator" observation entries of the RESET observation read the error history of the episode that just ended
     // (fixed_wing.py:453-460, 1165-1180): the precomputed row holds them as 0 and they are added here from the live ring
-    T int_reset[3] = {0, 0, 0};
+    T int_reset[6] = {0, 0, 0, 0, 0, 0};
     if constexpr (GENERIC) {
         if (take && c.obs_has_int) {
 #pragma unroll 1
-            for (int k = 0; k < 3; ++k) int_reset[k] = integrator_reset_value<T>(c, S, env, k, n_err, e0v[k]);
+            for (int k = 0; k < (c.ang_on ? 6 : 3); ++k)
+                int_reset[k] = integrator_reset_value<T>(c, S, env, k, n_err, k < 3 ? e0v[k < 3 ? k : 0] : r[(RF_AE0 + k - 3) * n]);
         }
     }
     take_spare_warp<T>(S, P, take, env, odim, io.obs, io.obs64);
@@ -985,6 +1014,10 @@ __global__ void __launch_bounds__(64, 8) head_kernel(const __grid_constant__ DCf
 #pragma unroll
         for (int i = 0; i < FW_NY; ++i) r[(RF_Y + i) * n] = y[i];
         r[RF_ROLL * n] = roll; r[RF_PITCH * n] = pitch; r[RF_VA * n] = Va; r[RF_ALPHA * n] = alpha; r[RF_BETA * n] = beta;
+    }
+    if (ang) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) r[(RF_ATGT + a) * n] = atgt[a];
     }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -1145,6 +1178,7 @@ __global__ void field_copy_kernel(const __grid_constant__ DCfg<T> c, Soa<T> S, i
         case FW_FIELD_VAB: rw(RF_VA, 3, 0, 3); break;
         case FW_FIELD_WIND: rw(RF_WIND, 3, 0, 3); break;
         case FW_FIELD_TARGET: rw(RF_TGT, 3, 0, 3); break;
+        case FW_FIELD_ATARGET: rw(RF_ATGT, 3, 0, 3); break;
         case FW_FIELD_CMD: rw(RF_CMD_RING, 3, 0, 3); break;
         case FW_FIELD_TURB:
             if (!to_soa) {
@@ -1282,6 +1316,8 @@ template <typename T> static void convert_cfg(const FwConfig& f, DCfg<T>& d) {
         d.obs_kind[k] = f.obs_kind[k]; d.obs_idx[k] = f.obs_idx[k]; d.obs_window[k] = f.obs_window[k];
         d.obs_norm_flag[k] = f.obs_norm_flag[k]; CP(obs_mean[k]); CP(obs_var[k]);
     }
+    d.ang_on = f.ang_on;
+    for (int k = 0; k < 3; ++k) { CP(ang_max_vel[k]); CP(ang_bound[k]); }
     d.integration_window = f.integration_window;
     d.obs_step = f.obs_step > 0 ? f.obs_step : 1;
     d.obs_has_int = 0;
@@ -1335,6 +1371,7 @@ struct FwHandle {
     Soa<double> s64;
     Soa<float> s32;
     void* r_buf; int32_t* i_buf; void* err_ring;
+    void* err_ring_a; void* err2a; double* metrics_a;     // attitude_angular targets only (else nullptr)
     double* metrics; double* ep_ret; int32_t* ep_len; int32_t* ep_term;
     void* w_real; int32_t* w_int;          // scratch between the kernels of one step
     double* wp_tasks; int32_t* wp_task_of_env;   // waypoint head: device copies of the task table
@@ -1431,7 +1468,7 @@ static void spare_refill(FwHandle* h, const DCfg<T>& c, const Spare<T>& P, cudaS
 static inline bool head_generic(const FwConfig& f) {
     bool moving = false;
     for (int k = 0; k < 3; ++k) moving |= (f.tgt_class[k] == FW_TGT_LINEAR || f.tgt_class[k] == FW_TGT_SINUSOIDAL);
-    return f.obs_generic || f.rew_generic || moving || f.resample_every > 0 || f.on_success == FW_SUCCESS_NEW;
+    return f.obs_generic || f.rew_generic || moving || f.resample_every > 0 || f.on_success == FW_SUCCESS_NEW || f.ang_on;
 }
 
 // One env step = init kernel -> persistent attempt kernel -> head kernel (RK45), or rk4 kernel -> head kernel.
@@ -1517,6 +1554,11 @@ static int blob_parts(FwHandle* h, BlobPart* out) {
     out[k++] = {h->i_buf, sizeof(int32_t) * IF_COUNT * n};
     out[k++] = {h->err_ring, esz * FW_END_ERR_WINDOW * 3 * n};
     out[k++] = {h->metrics, sizeof(double) * FW_NMETRIC * n};
+    if (h->err_ring_a) {
+        out[k++] = {h->err_ring_a, esz * FW_END_ERR_WINDOW * 3 * n};
+        out[k++] = {h->err2a, esz * 3 * n};
+        out[k++] = {h->metrics_a, sizeof(double) * FW_NMETRIC_ANG * n};
+    }
     out[k++] = {h->ep_ret, sizeof(double) * n};
     out[k++] = {h->ep_len, sizeof(int32_t) * n};
     out[k++] = {h->ep_term, sizeof(int32_t) * n};
@@ -1645,8 +1687,18 @@ int fw_create(const FwConfig* cfg, int32_t n_envs, int32_t device, FwHandle** ou
     CK(cudaMemset(h->ep_ret, 0, sizeof(double) * n));
     CK(cudaMemset(h->ep_len, 0, sizeof(int32_t) * n));
     CK(cudaMemset(h->ep_term, 0, sizeof(int32_t) * n));
-    h->s64 = Soa<double>{(double*)h->r_buf, h->i_buf, (double*)h->err_ring, h->metrics, h->ep_ret, h->ep_len, h->ep_term, nullptr, 0, n_envs, nullptr, nullptr, 0, 0, nullptr, nullptr};
-    h->s32 = Soa<float>{(float*)h->r_buf, h->i_buf, (float*)h->err_ring, h->metrics, h->ep_ret, h->ep_len, h->ep_term, nullptr, 0, n_envs, nullptr, nullptr, 0, 0, nullptr, nullptr};
+    h->s64 = Soa<double>{(double*)h->r_buf, h->i_buf, (double*)h->err_ring, h->metrics, h->ep_ret, h->ep_len, h->ep_term, nullptr, 0, n_envs, nullptr, nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr};
+    h->s32 = Soa<float>{(float*)h->r_buf, h->i_buf, (float*)h->err_ring, h->metrics, h->ep_ret, h->ep_len, h->ep_term, nullptr, 0, n_envs, nullptr, nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr};
+    if (cfg->ang_on) {
+        CK(cudaMalloc(&h->err_ring_a, esz * FW_END_ERR_WINDOW * 3 * n));
+        CK(cudaMalloc(&h->err2a, esz * 3 * n));
+        CK(cudaMalloc((void**)&h->metrics_a, sizeof(double) * FW_NMETRIC_ANG * n));
+        CK(cudaMemset(h->err_ring_a, 0, esz * FW_END_ERR_WINDOW * 3 * n));
+        CK(cudaMemset(h->err2a, 0, esz * 3 * n));
+        CK(cudaMemset(h->metrics_a, 0, sizeof(double) * FW_NMETRIC_ANG * n));
+        h->s64.err_ring_a = (double*)h->err_ring_a; h->s32.err_ring_a = (float*)h->err_ring_a;
+        h->s64.metrics_a = h->s32.metrics_a = h->metrics_a;
+    }
     {
         CK(cudaMalloc(&h->rc_dev, sizeof(ResetCfg<double>)));
         if (cfg->precision == FW_F64) {
@@ -1682,8 +1734,10 @@ int fw_create(const FwConfig* cfg, int32_t n_envs, int32_t device, FwHandle** ou
         CK(cudaMemset(h->done_list, 0, sizeof(int32_t) * (2 * n + 2)));
         h->p64.S2 = h->s64; h->p64.S2.r = (double*)h->r2_buf; h->p64.S2.i = h->i2_buf; h->p64.S2.err_ring = (double*)h->err2;
         h->p64.S2.par = (double*)h->par2_buf;
+        h->p64.S2.err_ring_a = (double*)h->err2a;
         h->p32.S2 = h->s32; h->p32.S2.r = (float*)h->r2_buf; h->p32.S2.i = h->i2_buf; h->p32.S2.err_ring = (float*)h->err2;
         h->p32.S2.par = (float*)h->par2_buf;
+        h->p32.S2.err_ring_a = (float*)h->err2a;
         h->p64.obs = h->p32.obs = h->spare_obs;
         h->p64.obs64 = h->p32.obs64 = h->spare_obs64;
         h->p64.list = h->p32.list = h->done_list;
@@ -1707,6 +1761,7 @@ int fw_destroy(FwHandle* h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     cudaFree(h->r_buf); cudaFree(h->i_buf); cudaFree(h->err_ring); cudaFree(h->metrics);
+    cudaFree(h->err_ring_a); cudaFree(h->err2a); cudaFree(h->metrics_a);
     cudaFree(h->ep_ret); cudaFree(h->ep_len); cudaFree(h->ep_term); cudaFree(h->w_real); cudaFree(h->w_int);
     cudaFree(h->wp_tasks); cudaFree(h->wp_task_of_env); cudaFree(h->rc_dev); cudaFree(h->par_buf); cudaFree(h->par2_buf);
     cudaFree(h->r2_buf); cudaFree(h->i2_buf); cudaFree(h->err2); cudaFree(h->spare_obs); cudaFree(h->spare_obs64);
@@ -1755,7 +1810,7 @@ int fw_set_config(FwHandle* h, const FwConfig* cfg, void* stream) {
 
 int64_t fw_state_blob_size(const FwHandle* h) {
     if (!h) return FW_EINVAL;
-    BlobPart parts[16];
+    BlobPart parts[24];
     const int k = blob_parts(const_cast<FwHandle*>(h), parts);
     size_t total = sizeof(BlobHeader);
     for (int i = 0; i < k; ++i) total += (parts[i].bytes + 15) & ~(size_t)15;
@@ -1773,7 +1828,7 @@ int fw_get_state_blob(FwHandle* h, void* blob_dev, void* stream) {
     hd.rf_count = RF_COUNT; hd.if_count = IF_COUNT; hd.obs_dim = fw_obs_dim(h);
     hd.random_step = h->random_step; hd.step_parity = h->step_parity;
     CK(cudaMemcpyAsync(blob_dev, &hd, sizeof(hd), cudaMemcpyHostToDevice, st));     // pageable source: staged before return
-    BlobPart parts[16];
+    BlobPart parts[24];
     const int k = blob_parts(h, parts);
     char* p = (char*)blob_dev + sizeof(BlobHeader);
     for (int i = 0; i < k; ++i) {
@@ -1797,7 +1852,7 @@ int fw_set_state_blob(FwHandle* h, const void* blob_dev, void* stream) {
         return FW_EINVAL;
     }
     spare_join(h, st);
-    BlobPart parts[16];
+    BlobPart parts[24];
     const int k = blob_parts(h, parts);
     const char* p = (const char*)blob_dev + sizeof(BlobHeader);
     for (int i = 0; i < k; ++i) {
@@ -1868,6 +1923,13 @@ int fw_step_random(FwHandle* h, int32_t k_steps, uint64_t action_seed, float* ob
         int rc = launch_step(h, io, (cudaStream_t)stream);
         if (rc) return rc;
     }
+    return FW_OK;
+}
+
+int fw_get_episode_info_angular(FwHandle* h, double* metrics_ang_dev, void* stream) {
+    if (!h || !metrics_ang_dev) return FW_EINVAL;
+    if (!h->metrics_a) { snprintf(g_err, sizeof(g_err), "fw_get_episode_info_angular: the config has no attitude_angular targets"); return FW_EINVAL; }
+    CK(cudaMemcpyAsync(metrics_ang_dev, h->metrics_a, sizeof(double) * FW_NMETRIC_ANG * h->n, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return FW_OK;
 }
 

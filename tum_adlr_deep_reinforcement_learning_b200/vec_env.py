@@ -22,7 +22,7 @@ import numpy as np
 import torch
 
 from . import batched as bt
-from .config import (GOAL_STATES, METRIC_LAYOUT, TARGET_STATES, TERM_NAMES, build_config, observation_bounds,
+from .config import (ANGULAR_TARGET_STATES, GOAL_STATES, METRIC_LAYOUT, TARGET_STATES, TERM_NAMES, build_config, observation_bounds,
                      resolve_configs)
 
 
@@ -309,8 +309,8 @@ class FixedWingVecEnv(_VecEnvSurface):
         if attr_name == "fw_config":
             return [self.cfg for _ in idx]
         if attr_name == "target":
-            t = self.sim.get_field(bt.FIELD_TARGET).cpu().numpy()
-            return [dict(zip(TARGET_STATES, map(float, t[i]))) for i in idx]
+            t = self._targets_host()
+            return [dict(zip(self._target_names(), map(float, t[i]))) for i in idx]
         if attr_name == "steps_count":
             c = self.sim.get_field(bt.FIELD_COUNTERS).cpu().numpy()
             return [int(c[i, 0]) for i in idx]
@@ -409,8 +409,8 @@ class FixedWingVecEnv(_VecEnvSurface):
                     else np.zeros((0, 31 + self.sim.obs_dim)))
         waypoint = self.cfg.env_kind != 0
         if compat:
-            tgt = self.sim.get_field(bt.FIELD_TARGET).cpu().numpy()
-            names = ("position_n", "position_e", "position_d") if waypoint else TARGET_STATES
+            tgt = self._targets_host()
+            names = ("position_n", "position_e", "position_d") if waypoint else self._target_names()
             infos = [{"target": dict(zip(names, map(float, tgt[i])))} for i in range(n)]
         now = round(time.time() - self._t_start, 6)
         term_obs_all = rows[:, 31:].astype(np.float32)
@@ -424,9 +424,44 @@ class FixedWingVecEnv(_VecEnvSurface):
                 # fixed_wing.py:626 reports the finished episode's target; it sits in terminal_observation[6:9]
                 info["target"] = dict(zip(TARGET_STATES, term_obs[6:9].tolist()))
             infos[i] = info
+        if getattr(self.cfg, "ang_on", 0) and len(done_idx):
+            self._merge_angular_metrics(infos, done_idx)
         if not compat:
             self._lazy_dirty = done_idx.tolist()
         return infos
+
+    # ---- target class attitude_angular: omega_p / omega_q / omega_r are target states too (fixed_wing.py:671-746) ----
+    def _target_names(self):
+        return TARGET_STATES + ANGULAR_TARGET_STATES if getattr(self.cfg, "ang_on", 0) else TARGET_STATES
+
+    def _targets_host(self):
+        t = self.sim.get_field(bt.FIELD_TARGET).cpu().numpy()
+        if getattr(self.cfg, "ang_on", 0):
+            t = np.concatenate([t, self.sim.get_field(bt.FIELD_ATARGET).cpu().numpy()], axis=1)
+        return t
+
+    def _merge_angular_metrics(self, infos, done_idx):
+        """The per-state metric dicts of a finished episode get the entries of the rate targets (get_metric iterates every
+        target state, fixed_wing.py:1644-1736; goal metrics only for states with a bound), in the reference's key order."""
+        am = self.sim.episode_info_angular().index_select(
+            0, torch.as_tensor(np.asarray(done_idx), dtype=torch.long, device=self.device)).cpu().numpy()
+        bounded = [a for a in range(3) if np.isfinite(self.cfg.ang_bound[a])]
+        err_names = ("avg_error", "total_error", "end_error", "rise_time", "overshoot")
+        goal_names = ("success", "settling_time", "success_time_frac")
+        for row, i in zip(am, np.asarray(done_idx).tolist()):
+            info = infos[i]
+            for q, name in enumerate(err_names):
+                if name in info:
+                    info[name].update({ANGULAR_TARGET_STATES[a]: float(row[q * 3 + a]) for a in range(3)})
+            for q, name in enumerate(goal_names):
+                if name in info:
+                    d = info[name]
+                    allv = d.pop("all", None)
+                    for a in bounded:
+                        v = float(row[15 + q * 3 + a])
+                        d[ANGULAR_TARGET_STATES[a]] = bool(v) if name == "success" else v
+                    if allv is not None:
+                        d["all"] = allv
 
 
 def state_dict_to_row(state):
