@@ -346,6 +346,12 @@ def test_attitude_angular_targets(cuda_device):
             for i in np.flatnonzero(d_ref)[:8]:
                 ref = ob.env_angular(int(i))[1]
                 assert close_or_both_nan(am[i], ref, 1e-9, 1e-12).all(), (t, i, am[i], ref)
+        if t == 30:                 # checkpoint: the state blob carries the rate targets' rings and metrics
+            blob = env.get_state()
+            env.close()
+            env = bt.BatchedFixedWing(n, cfg=cfg)
+            env.enable_f64_outputs()
+            env.set_state(blob)
     env.close()
 
 

@@ -77,6 +77,9 @@ __device__ __forceinline__ Soa<T> spare_view(const Spare<T>& P, int env) {
 template <typename T>
 __device__ __forceinline__ void take_spare_warp(const Soa<T>& S, const Spare<T>& P, bool mine, int env, int odim,
                                                 float* obs, double* obs64) {
+    // fields in use: the attitude_angular block at the end of both field lists only when the config has such targets
+    // (212 real fields are ONE pass of 8 x 32 loads per lane, 257 would be two)
+    const int n_rf = S.err_ring_a ? (int)RF_COUNT : (int)RF_ATGT, n_if = S.err_ring_a ? (int)IF_COUNT : (int)IF_AGOAL_RING;
     const unsigned act = __activemask();
     unsigned dm = __ballot_sync(act, mine);
     if (!dm) return;
@@ -92,26 +95,26 @@ __device__ __forceinline__ void take_spare_warp(const Soa<T>& S, const Spare<T>&
             const T* src = P.S2.r + (size_t)e * RF_COUNT;
             T* dst = S.r + e;
 #pragma unroll 1
-            for (int f0 = rank; f0 < RF_COUNT; f0 += 8 * width) {
+            for (int f0 = rank; f0 < n_rf; f0 += 8 * width) {
                 T tmp[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) tmp[j] = (f0 + j * width < RF_COUNT) ? src[f0 + j * width] : (T)0;
+                for (int j = 0; j < 8; ++j) tmp[j] = (f0 + j * width < n_rf) ? src[f0 + j * width] : (T)0;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) if (f0 + j * width < RF_COUNT) dst[(size_t)(f0 + j * width) * n] = tmp[j];
+                for (int j = 0; j < 8; ++j) if (f0 + j * width < n_rf) dst[(size_t)(f0 + j * width) * n] = tmp[j];
             }
         }
         {
             const int32_t* src = P.S2.i + (size_t)e * IF_COUNT;
             int32_t* dst = S.i + e;
 #pragma unroll 1
-            for (int f0 = rank; f0 < IF_COUNT; f0 += 2 * width) {
+            for (int f0 = rank; f0 < n_if; f0 += 2 * width) {
                 int32_t tmp[2];
 #pragma unroll
-                for (int j = 0; j < 2; ++j) tmp[j] = (f0 + j * width < IF_COUNT) ? src[f0 + j * width] : 0;
+                for (int j = 0; j < 2; ++j) tmp[j] = (f0 + j * width < n_if) ? src[f0 + j * width] : 0;
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
                     const int f = f0 + j * width;
-                    if (f < IF_COUNT && f != IF_GOAL_ACHIEVED && f != IF_NFEV && f != IF_NATT) dst[(size_t)f * n] = tmp[j];
+                    if (f < n_if && f != IF_GOAL_ACHIEVED && f != IF_NFEV && f != IF_NATT) dst[(size_t)f * n] = tmp[j];
                 }
             }
         }
