@@ -207,9 +207,12 @@ class OracleBatch:
         self.done = np.zeros(n, np.uint8)
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().fwo_batch_destroy(self._h)
-            self._h = None
+        try:                                   # module globals may be gone at interpreter shutdown
+            if getattr(self, "_h", None):
+                lib().fwo_batch_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
 
     def set_waypoint_tasks(self, tasks, task_of_env):
         self._tasks = np.ascontiguousarray(tasks, dtype=np.float64)

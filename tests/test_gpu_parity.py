@@ -355,6 +355,45 @@ def test_attitude_angular_targets(cuda_device):
     env.close()
 
 
+def test_attitude_angular_targets_with_the_default_observation_and_reward(cuda_device):
+    """The default observation row and reward family plus three rate targets (one without a bound): the general head
+    instantiation with obs_generic = 0, against the oracle — done flags (the bounded rate targets gate the success
+    streak), observations, rewards and the rate targets' metrics."""
+    import torch
+    from conftest import close_or_both_nan
+    from oracle import fw_oracle as O
+    from tum_adlr_deep_reinforcement_learning_b200 import batched as bt
+    from tum_adlr_deep_reinforcement_learning_b200.config import build_config, default_env_config
+    ecfg = default_env_config()
+    for name, b in zip(("omega_p", "omega_q", "omega_r"), (0.6, None, 0.5)):
+        st = {"name": name, "class": "attitude_angular"}
+        if b is not None:
+            st["bound"] = b
+        ecfg["target"]["states"].append(st)
+    ecfg["steps_max"] = 20
+    cfg = build_config(env_cfg=ecfg, sim_config_kw={"turbulence": True}, seed=11)
+    assert (cfg.obs_generic, cfg.rew_generic, cfg.ang_on) == (0, 1, 1)
+    n = 512
+    env = bt.BatchedFixedWing(n, cfg=cfg)
+    env.enable_f64_outputs()
+    env.reset()
+    ob = O.OracleBatch(cfg, n)
+    assert np.abs(env.obs64.cpu().numpy() - ob.reset()).max() < 1e-12
+    rs = np.random.RandomState(1)
+    for t in range(50):
+        a = rs.uniform(-1.3, 1.3, (n, 3)).astype(np.float32)
+        env.step(torch.as_tensor(a).cuda())
+        o_ref, r_ref, d_ref = ob.step(a)
+        assert np.array_equal(env.done.cpu().numpy(), d_ref), t
+        assert _rel(env.obs64.cpu().numpy(), o_ref).max() < RTOL_F64, t
+        assert _rel(env.rew64.cpu().numpy(), r_ref).max() < RTOL_F64, t
+        if d_ref.any():
+            am = env.episode_info_angular().cpu().numpy()
+            for i in np.flatnonzero(d_ref)[:4]:
+                assert close_or_both_nan(am[i], ob.env_angular(int(i))[1], 1e-9, 1e-12).all(), (t, i)
+    env.close()
+
+
 def test_moving_target_classes(cuda_device):
     """linear / sinusoidal targets on the CUDA path: the live-reference fixture (fixed draws), then Philox sampling with
     on_success = "new" resampling against the oracle."""
