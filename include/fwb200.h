@@ -497,7 +497,8 @@ const char* fw_comm_last_error(void);
 int fw_measure_fma_peak(int32_t device, int32_t precision, double* tflops_out);
 
 /* Diagnostic: evaluates the straight-line FP64 math of the RHS hot loop elementwise (op 0: exp(x), 1: asin(x),
- * 2: atan2(y, x), 3: 1/sqrt(x), 4..6: ops 0..2 built with immediate instead of constant-bank coefficients); used by the tests to bound their error against the host libm. */
+ * 2: atan2(y, x), 3: 1/sqrt(x), 4..6: ops 0..2 built with immediate instead of constant-bank coefficients, 7: log(x),
+ * 8 / 9: x^y as exp(y log x), constant-bank / immediate build); used by the tests to bound their error against the host libm. */
 int fw_debug_math(int32_t op, const double* x_dev, const double* y_dev, double* out_dev, int32_t n, void* stream);
 
 #ifdef __cplusplus

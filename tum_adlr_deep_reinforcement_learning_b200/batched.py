@@ -239,7 +239,7 @@ def measure_fma_peak(device=0, precision="f64"):
 
 
 def debug_math(op, x, y=None):
-    """Elementwise evaluation of the RHS hot-loop math (0 exp, 1 asin, 2 atan2(y, x), 3 rsqrt) on float64 CUDA tensors."""
+    """Elementwise evaluation of the RHS hot-loop math (0 exp, 1 asin, 2 atan2(y, x), 3 rsqrt, 4..6 immediate-coefficient builds of 0..2, 7 log, 8 / 9 x^y) on float64 CUDA tensors."""
     x = x.contiguous()
     out = torch.empty_like(x)
     st = ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)

@@ -41,6 +41,7 @@ template <> struct M<double> {
     template <bool CT = true> static __device__ __forceinline__ double asin_hot(double x) { return asin_bf<CT>(x); }
     template <bool CT = true> static __device__ __forceinline__ double exp_hot(double x) { return exp_bf<CT>(x); }
     static __device__ __forceinline__ double rcp_hot(double x) { return rcp_fast(x); }
+    template <bool CT = true> static __device__ __forceinline__ double pow_hot(double x, double p) { return pow_hot_bf<CT>(x, p); }
     static __device__ __forceinline__ double atan2(double y, double x) { return ::atan2(y, x); }
     static __device__ __forceinline__ double asin(double x) { return ::asin(x); }
     static __device__ __forceinline__ double pow(double x, double y) { return ::pow(x, y); }
@@ -67,6 +68,7 @@ template <> struct M<float> {
     template <bool CT = true> static __device__ __forceinline__ float asin_hot(float x) { return ::asinf(fminf(fmaxf(x, -1.0f), 1.0f)); }
     template <bool CT = true> static __device__ __forceinline__ float exp_hot(float x) { return ::expf(x); }
     static __device__ __forceinline__ float rcp_hot(float x) { return 1.0f / x; }
+    template <bool CT = true> static __device__ __forceinline__ float pow_hot(float x, float p) { return ::powf(x, p); }
     static __device__ __forceinline__ float atan2(float y, float x) { return ::atan2f(y, x); }
     static __device__ __forceinline__ float asin(float x) { return ::asinf(x); }
     static __device__ __forceinline__ float pow(float x, float y) { return ::powf(x, y); }
@@ -518,7 +520,7 @@ __device__ __forceinline__ int rk45_init(const DCfg<T>& c, const DynCtx<T>& x, T
             const T d2 = (M<T>::sqrt(s2) / M<T>::sqrt((T)FW_NY)) / h0;
             T h1;
             if (d1 <= (T)1e-15 && d2 <= (T)1e-15) h1 = M<T>::fmax((T)1e-6, h0 * (T)1e-3);
-            else h1 = pow_ni<T>((T)0.01 / M<T>::fmax(d1, d2), (T)0.2);
+            else h1 = M<T>::template pow_hot<false>((T)0.01 / M<T>::fmax(d1, d2), (T)0.2);
             h_abs = M<T>::fmin(M<T>::fmin((T)100 * h0, h1), t_bound);
         }
     }

@@ -207,6 +207,9 @@ __global__ void debug_math_kernel(int op, const double* x, const double* y, doub
     else if (op == 4) out[i] = fw::exp_bf<false>(x[i]);            // 4..6: the immediate-coefficient instantiations
     else if (op == 5) out[i] = fw::asin_bf<false>(x[i]);
     else if (op == 6) out[i] = fw::atan2_bf<false>(y[i], x[i]);
+    else if (op == 7) out[i] = fw::log_bf<true>(x[i]);
+    else if (op == 8) out[i] = fw::pow_hot_bf<true>(x[i], y[i]);              // x^y
+    else if (op == 9) out[i] = fw::pow_hot_bf<false>(x[i], y[i]);
     else out[i] = fw::atan2_bf(y[i], x[i]);
 }
 
@@ -304,7 +307,7 @@ int fw_gae(const float* rew_dev, const float* val_dev, const float* done_dev, co
 }
 
 int fw_debug_math(int32_t op, const double* x_dev, const double* y_dev, double* out_dev, int32_t n, void* stream) {
-    if (!x_dev || !out_dev || n <= 0 || op < 0 || op > 6 || ((op == 2 || op == 6) && !y_dev)) return FW_EINVAL;
+    if (!x_dev || !out_dev || n <= 0 || op < 0 || op > 9 || ((op == 2 || op == 6 || op == 8 || op == 9) && !y_dev)) return FW_EINVAL;
     debug_math_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(op, x_dev, y_dev, out_dev, n);
     return cudaGetLastError() == cudaSuccess ? FW_OK : FW_ECUDA;
 }

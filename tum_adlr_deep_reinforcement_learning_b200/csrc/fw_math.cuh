@@ -75,6 +75,34 @@ template <bool CT = true> __device__ __forceinline__ double exp_bf(double x) {
     return __hiloint2double(__double2hiint(p) + ni * 1048576, __double2loint(p));
 }
 
+// log(x) for normal-range x > 0 (callers clamp), straight line: x = 2^k m with m in [sqrt(1/2), sqrt(2)), f = m - 1,
+// s = f / (2 + f), log(1 + f) = f - hfsq + s (hfsq + R(s^2)) with the degree-7 minimax R of fdlibm's e_log.c
+// (|error| < 2^-58.45 there), result k ln2_hi + (log(1 + f) + k ln2_lo): < 1 ulp (tests/test_gpu_math.py).
+FW_TAB LOG_LG[7] = {6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01, 2.222219843214978396e-01,
+                    1.818357216161805012e-01, 1.531383769920937332e-01, 1.479819860511658591e-01};
+FW_IMM LOG_LG_I[7] = {6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01, 2.222219843214978396e-01,
+                      1.818357216161805012e-01, 1.531383769920937332e-01, 1.479819860511658591e-01};
+__device__ __forceinline__ double rcp_fast(double x);
+template <bool CT = true> __device__ __forceinline__ double log_bf(double x) {
+    int hx = __double2hiint(x);
+    const int lx = __double2loint(x);
+    int k = (hx >> 20) - 1023;
+    hx &= 0x000fffff;
+    const int i = (hx + 0x95f64) & 0x100000;          // m >= sqrt(2): halve it, k + 1
+    k += i >> 20;
+    const double m = __hiloint2double(hx | (i ^ 0x3ff00000), lx);
+    const double f = m - 1.0;
+    const double s = f * rcp_fast(2.0 + f);
+    const double z = s * s, w = z * z;
+    double t1 = FW_COEF(LOG_LG, 5), t2 = FW_COEF(LOG_LG, 6);
+    t1 = fma(t1, w, FW_COEF(LOG_LG, 3)); t2 = fma(t2, w, FW_COEF(LOG_LG, 4));
+    t1 = fma(t1, w, FW_COEF(LOG_LG, 1)); t2 = fma(t2, w, FW_COEF(LOG_LG, 2));
+    t2 = fma(t2, w, FW_COEF(LOG_LG, 0));
+    const double R = fma(t1, w, 0.0) + t2 * z;        // Lg2 w + Lg4 w^2 + Lg6 w^3  +  z (Lg1 + Lg3 w + Lg5 w^2 + Lg7 w^3)
+    const double hfsq = 0.5 * f * f, dk = (double)k;
+    return dk * 6.93147180369123816490e-01 - ((hfsq - (s * (hfsq + R) + dk * 1.90821492927058770002e-10)) - f);
+}
+
 // 1/x for normal-range x: hardware seed (rcp.approx.ftz.f64, ~2^-23) + two Newton steps -> ~1 ulp, 6 instructions
 // instead of the ~35 of an IEEE-rounded division with its special-case fix-ups.
 __device__ __forceinline__ double rcp_fast(double x) {
@@ -133,6 +161,16 @@ template <bool CT = true> __device__ __forceinline__ double atan2_bf(double y, d
     if (ay > ax) a = 1.57079632679489655800e+00 - (a - 6.12323399573676603587e-17);    // pi/2 - a
     if (x < 0.0) a = 3.14159265358979311600e+00 - (a - 1.22464679914735317723e-16);    // pi - a
     return copysign(a, y);
+}
+
+// x^p for x > 0 as exp(p log x), x clamped into [1e-300, 1e300]: the step-size controller's err^-0.2 and the initial
+// step's (0.01 / d)^0.2 (scipy rk.py:139-166, common.py:118-126), where the library pow is a ~300-instruction call once
+// per attempt.  |p log x| <= 140 keeps the result within ~8 ulp of pow (tests/test_gpu_math.py); both uses then pass
+// through min / max against constants, and the parity suite sees identical step-size decisions on every fixture step.
+template <bool CT = true> __device__ __forceinline__ double pow_hot_bf(double x, double p) {
+    const double xc = fmin(fmax(x, 1e-300), 1e300);
+    const double r = exp_bf<CT>(p * log_bf<CT>(xc));
+    return (x != x) ? x : r;                       // NaN in, NaN out (the clamp would swallow it)
 }
 
 }  // namespace fw

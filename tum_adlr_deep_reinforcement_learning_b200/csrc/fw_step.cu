@@ -449,7 +449,7 @@ __global__ void __maxnreg__(255) rk45_attempt_kernel(const __grid_constant__ DCf
                 }
                 const T err = M<T>::sqrt(errsq) / M<T>::sqrt((T)FW_NY);
                 // err == 0: pow(0, -0.2) = inf -> min(10, inf) = MAX_FACTOR, the same as scipy's special case
-                const T pf = (T)0.9 * pow_ni<T>(err, (T)-0.2);
+                const T pf = (T)0.9 * M<T>::template pow_hot<true>(err, (T)-0.2);
                 if (err < (T)1) {
                     T factor = (err == (T)0) ? (T)10 : M<T>::fmin((T)10, pf);
                     if (rejected) factor = M<T>::fmin((T)1, factor);
