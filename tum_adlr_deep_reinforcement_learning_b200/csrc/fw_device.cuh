@@ -293,6 +293,7 @@ template <typename T> __device__ __noinline__ T asin_ni(T a) { return M<T>::asin
 template <typename T> __device__ __noinline__ void sincos_ni(T a, T* sn, T* cs) { M<T>::sincos(a, sn, cs); }
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // per-step dynamics context that is constant during one integration
 template <typename T> struct DynCtx {
