@@ -681,10 +681,11 @@ def test_flat_adam_matches_torch_adam_with_clipping(cuda_device):
 
 
 def test_ppo_on_other_observation_layouts(cuda_device):
-    """PPO takes the observation width from the env: the waypoint env head (12 raw states) and the reference's
-    CNN-controller layout (5 x 12 matrix flattened) both run rollouts + updates through the fused paths and graphs."""
+    """PPO takes the observation width from the env: the waypoint env head (12 raw states), the reference's
+    CNN-controller layout (5 x 12 matrix flattened) and an attitude_angular config (16 entries, six target states) all run
+    rollouts + updates through the fused paths and graphs."""
     import torch
-    from conftest import cnn_env_config
+    from conftest import angular_env_config, cnn_env_config
     from tum_adlr_deep_reinforcement_learning_b200.ppo import PPO
     from tum_adlr_deep_reinforcement_learning_b200.vec_env import FixedWingVecEnv, WaypointVecEnv
     tasks = np.full((2, 4, 15), np.nan)
@@ -695,8 +696,9 @@ def test_ppo_on_other_observation_layouts(cuda_device):
             tasks[t, w, 6:9] = [18.0, 0.0, 0.0]
             tasks[t, w, 9:12] = 0.0
     envs = [WaypointVecEnv(512, tasks, sim_config_kw={"turbulence": False}),
-            FixedWingVecEnv(512, config_path=cnn_env_config(), sim_config_kw={"turbulence": False})]
-    for env, dim in zip(envs, (12, 60)):
+            FixedWingVecEnv(512, config_path=cnn_env_config(), sim_config_kw={"turbulence": False}),
+            FixedWingVecEnv(512, config_path=angular_env_config(), sim_config_kw={"turbulence": True})]
+    for env, dim in zip(envs, (12, 60, 16)):
         assert env.sim.obs_dim == dim
         algo = PPO(env, n_steps=8, batch_size=2048, n_epochs=2)
         algo.learn(total_timesteps=4 * 8 * 512)              # eager rollout, then captured graphs
