@@ -655,13 +655,9 @@ __global__ void __launch_bounds__(64, 8) head_kernel(const __grid_constant__ DCf
     if (env >= n) return;
     T* r = S.r + env;
     int32_t* ii = S.i + env;
-    // The episode-statistics fields, goal rings and action rings are read late, behind stores the compiler may not hoist
-    // them above (12 % of the kernel's samples sat on those loads): their lines are fetched into L1 now, without holding
-    // registers for them (hoisting the loads themselves costs 1.4 KB of spills and is slower).  64.5 -> 62.3 us.
-#pragma unroll
-    for (int f = RF_E0; f <= RF_EP_RET; ++f) prefetch_l1(r + (size_t)f * n);
-#pragma unroll
-    for (int f = IF_RISE_LO; f < IF_RISE_LO + 6; ++f) prefetch_l1(ii + (size_t)f * n);
+    // The goal-ring words are read late, behind stores the compiler may not hoist them above: their lines are fetched
+    // into L1 now, without holding registers for them.  (The episode-statistics fields were prefetched here too until
+    // their loads moved ahead of the observation section, below.)
 #pragma unroll
     for (int f = IF_GOAL_RING; f < IF_GOAL_RING + 28; ++f) prefetch_l1(ii + (size_t)f * n);
     int fail = W.fail[env];
@@ -880,6 +876,17 @@ __global__ void __launch_bounds__(64, 8) head_kernel(const __grid_constant__ DCf
         reward = c.step_fail_timesteps ? (T)(steps - c.steps_max) : c.step_fail_value;
     }
 
+    // The episode-statistics fields are loaded HERE, ahead of the observation section: behind its stores their round trip
+    // was exposed in full (11 % of the kernel's samples on the first use, profiles/r02_v9_stall_lines.txt)
+    T esum[3], eabs[3], emin[3], emax[3], e0v[3], eprev[3];
+    int rise_lo[3], rise_hi[3];
+    const T ep_ret_prev = r[RF_EP_RET * n];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        e0v[k] = r[(RF_E0 + k) * n]; esum[k] = r[(RF_ESUM + k) * n]; eabs[k] = r[(RF_EABS + k) * n];
+        emin[k] = r[(RF_EMIN + k) * n]; emax[k] = r[(RF_EMAX + k) * n]; eprev[k] = r[(RF_EPREV + k) * n];
+        rise_lo[k] = ii[(IF_RISE_LO + k) * n]; rise_hi[k] = ii[(IF_RISE_HI + k) * n];
+    }
     // ---------------- observation (fixed_wing.py:1113-1262) ----------------
     obs_v[0] = roll; obs_v[1] = pitch; obs_v[2] = Va;
     obs_v[3] = om_obs[0]; obs_v[4] = om_obs[1]; obs_v[5] = om_obs[2];
@@ -912,20 +919,12 @@ __global__ void __launch_bounds__(64, 8) head_kernel(const __grid_constant__ DCf
     }
 
     // ---------------- streamed episode statistics (fixed_wing.py:1644-1736) ----------------
-    T esum[3], eabs[3], emin[3], emax[3], e0v[3];
-    int rise_lo[3], rise_hi[3];
-    const T ep_ret = r[RF_EP_RET * n] + reward;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        e0v[k] = r[(RF_E0 + k) * n]; esum[k] = r[(RF_ESUM + k) * n]; eabs[k] = r[(RF_EABS + k) * n];
-        emin[k] = r[(RF_EMIN + k) * n]; emax[k] = r[(RF_EMAX + k) * n];
-        rise_lo[k] = ii[(IF_RISE_LO + k) * n]; rise_hi[k] = ii[(IF_RISE_HI + k) * n];
-    }
+    const T ep_ret = ep_ret_prev + reward;
     int n_err = steps_before + 1;           // entries in history["error"] before this step
     if (!fail) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            const T ea = M<T>::fabs(e_new[k]), prev = r[(RF_EPREV + k) * n];
+            const T ea = M<T>::fabs(e_new[k]), prev = eprev[k];
             const T low_lim = M<T>::fabs(c.rise_low * e0v[k]), high_lim = M<T>::fabs(c.rise_high * e0v[k]);
             if (rise_lo[k] < 0 && prev >= low_lim && ea < low_lim) rise_lo[k] = n_err - 1;
             if (rise_hi[k] < 0 && prev >= high_lim && ea < high_lim) rise_hi[k] = n_err - 1;
