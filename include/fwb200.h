@@ -317,6 +317,13 @@ int fw_set_waypoint_tasks(FwHandle* h, const double* tasks_dev, int32_t n_tasks,
                           const int32_t* task_of_env_dev, void* stream);
 const char* fw_last_error(void);
 int fw_abi_version(void);
+/* sizeof() of the structs a binding has to mirror field by field (FwConfig, FwRolloutPost, FwReplay, FwReplayNorm), as the
+ * library was compiled: a ctypes / cgo / JNI stub compares them with its own layout at load time and refuses a mismatch
+ * (tum_adlr_deep_reinforcement_learning_b200/_lib.py does). */
+int fw_config_size(void);
+int fw_rollout_post_size(void);
+int fw_replay_size(void);
+int fw_replay_norm_size(void);
 
 /* Replaces: FixedWingAircraft.reset(state, target, turbulence_noise) (fixed_wing.py:414-481 -> pyfly.py:1262-1311).
  *  mask_dev        [n] uint8, nullable (NULL = all envs): which envs to reset.

@@ -109,4 +109,5 @@ def check(rc, what):
 EXPORTS = ("fw_create", "fw_destroy", "fw_set_config", "fw_state_blob_size", "fw_get_state_blob", "fw_set_state_blob", "fw_last_error", "fw_abi_version", "fw_reset", "fw_step", "fw_step_random", "fw_get_episode_info_angular",
            "fw_get_episode_info", "fw_get_field", "fw_set_field", "fw_gae", "fw_measure_fma_peak", "fw_debug_math",
            "fw_obs_dim", "fw_set_waypoint_tasks", "fw_set_profiling", "fw_get_profile", "fw_join", "fw_set_info_rows", "fw_ppo_loss", "fw_rollout_post_step", "fw_adam_clip_step", "fw_replay_insert", "fw_replay_sample", "fw_comm_create", "fw_comm_export", "fw_comm_connect",
-           "fw_comm_allreduce_adam", "fw_comm_error", "fw_comm_destroy", "fw_comm_last_error")
+           "fw_comm_allreduce_adam", "fw_comm_error", "fw_comm_destroy", "fw_comm_last_error",
+           "fw_config_size", "fw_rollout_post_size", "fw_replay_size", "fw_replay_norm_size")
