@@ -387,8 +387,10 @@ __global__ void __maxnreg__(255) rk45_attempt_kernel(const __grid_constant__ DCf
 #pragma unroll 1
         for (int row = 1; row <= 6; ++row) {
             {
-                // sum_{j < row} A[row][j] K_j, j ascending.  The j loop stays rolled: written out for every j behind
+                // sum_{j < row} A[row][j] K_j, j ascending.  The j loop stays a loop: written out for every j behind
                 // warp-uniform tests of `row` it needs 255 registers + 330 B of spills and the kernel is 25 % slower (measured).
+                // Two terms per trip put 16 LDS.128 in flight ahead of 30 FMAs (same FMA order per component): 154.6 ->
+                // 150.4 us in the A/B; 3 / 4 / 6 terms per trip 151.6 / 152.2 / 152.7, explicit ping-pong prefetch 159-162.
                 T acc[2 * FW_NP];
 #pragma unroll
                 for (int cc = 0; cc < 2 * FW_NP; ++cc) acc[cc] = 0;
@@ -401,7 +403,7 @@ __global__ void __maxnreg__(255) rk45_attempt_kernel(const __grid_constant__ DCf
                         if (2 * pp + 1 < FW_NS) acc[2 * pp + 1] += kv.y * a;            \
                     }                                                                   \
                 }
-#pragma unroll 1
+#pragma unroll 2
                 for (int j = 0; j < row; ++j) FW_TERM(j)
 #undef FW_TERM
 #pragma unroll
