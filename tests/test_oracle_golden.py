@@ -358,3 +358,21 @@ def test_oracle_waypoint_env_head():
             obs, rew, done, term = env.step(g["actions_%d" % t][k])
             assert _rel(obs, g["obs_%d" % t][k]).max() < 1e-9, (t, k)
             assert abs(rew - g["reward_%d" % t][k]) < 1e-9 and done == bool(g["done_%d" % t][k])
+
+
+def test_oracle_against_the_live_reference_on_fresh_episodes():
+    """Where the reference can be imported (the build container, or its mirror baseline/_ref), tools/oracle_sweep.py draws
+    NEW episodes in nine categories (calm / windy / out-of-range initial states, clipped and f32 actions, the three
+    turbulence intensities), steps the live reference (fixed_wing.py:483-652) and the oracle side by side and applies the
+    checks of the fixture test above: exact done / termination / RK45 RHS count, <= 1e-9 relative elsewhere.  In its own
+    process: the reference needs the fabricated gym / matplotlib modules of oracle/refshim."""
+    import os
+    import subprocess
+    import sys
+    from oracle import refshim
+    if not refshim.available():
+        pytest.skip("reference libraries neither mounted nor mirrored under baseline/_ref")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "tools", "oracle_sweep.py"), "2", "50", "31337"],
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert res.returncode == 0 and "MISMATCHES: 0" in res.stdout, res.stdout[-2000:]
