@@ -244,3 +244,30 @@ def test_vecenv_classes_are_sb3_vecenvs():
         assert hasattr(V.FixedWingVecEnv, name), name
     import gym.spaces
     assert isinstance(V.make_box([0.0], [1.0]), gym.spaces.Box)
+
+
+def test_every_config_file_shipped_with_the_reference():
+    """Every fixed_wing_config*.json in the reference tree, by path: the live ones (gym_fixed_wing/, its examples and
+    model folders, magpy/__old's attitude configs) build; the archived position-target experiments under magpy/__old are
+    refused loudly (target states outside roll / pitch / Va / the rates), never half-applied.  Needs the reference tree
+    (build container); skipped elsewhere."""
+    import glob
+    import json
+    base = "/root/reference/magpie"
+    files = sorted(glob.glob(os.path.join(base, "**", "fixed_wing_config*.json"), recursive=True))
+    if not files:
+        pytest.skip("reference tree not mounted")
+    built, refused = [], []
+    for f in files:
+        try:
+            json.load(open(f))
+        except json.JSONDecodeError:
+            continue                              # fixed_wing_config-commented.json is documentation, not JSON
+        try:
+            C.build_config(env_cfg=f)
+            built.append(os.path.relpath(f, base))
+        except NotImplementedError as e:
+            assert "position_" in str(e), (f, e)
+            refused.append(os.path.relpath(f, base))
+    assert len(built) >= 9 and all("__old" in r for r in refused), (built, refused)
+    assert not any("__old" in b and "pos" in b for b in built)
