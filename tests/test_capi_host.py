@@ -271,3 +271,62 @@ def test_every_config_file_shipped_with_the_reference():
             refused.append(os.path.relpath(f, base))
     assert len(built) >= 9 and all("__old" in r for r in refused), (built, refused)
     assert not any("__old" in b and "pos" in b for b in built)
+
+
+def test_spaces_of_every_shipped_config_match_the_live_reference():
+    """observation_space / action_space of the adapters (config.observation_space_bounds / action_space_bounds) against
+    `FixedWingAircraft(...)` of the live reference (fixed_wing.py:92-258) for every config file it ships, plain and with
+    overrides that change the layout (length 3 vector, length 2 matrix, numeric / state-derived action bounds): low,
+    high, shape and dtype identical.  Needs the reference tree; skipped elsewhere."""
+    import glob
+    import json
+    import warnings
+    from oracle import refshim
+    base = "/root/reference/magpie"
+    files = sorted(glob.glob(os.path.join(base, "**", "fixed_wing_config*.json"), recursive=True))
+    if not files or not refshim.available():
+        pytest.skip("reference tree not mounted")
+    refshim.install()
+    from gym_fixed_wing.fixed_wing import FixedWingAircraft
+    variants = ((None, None),
+                ({"observation": {"length": 3, "shape": "vector"}}, {"turbulence": True}),
+                ({"observation": {"length": 2, "shape": "matrix"}}, None),
+                ({"action": {"states": {0: {"high": None, "low": None}, 1: {"high": 0.3, "low": -0.2}}}}, None))
+    checked = 0
+    for f in files:
+        try:
+            json.load(open(f))
+        except json.JSONDecodeError:
+            continue
+        for kw, skw in variants:
+            try:
+                C.build_config(env_cfg=f, config_kw=kw, sim_config_kw=skw)
+            except NotImplementedError:
+                continue
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                ref = FixedWingAircraft(f, config_kw=kw, sim_config_kw=skw)
+            env, sim = C.resolve_configs(f, None, kw, skw)
+            lo, hi = C.observation_space_bounds(env, sim)
+            assert lo.dtype == ref.observation_space.low.dtype and lo.shape == ref.observation_space.shape, (f, kw)
+            assert np.array_equal(lo, ref.observation_space.low) and np.array_equal(hi, ref.observation_space.high), (f, kw)
+            alo, ahi = C.action_space_bounds(env, sim)
+            assert np.array_equal(alo, ref.action_space.low) and np.array_equal(ahi, ref.action_space.high), (f, kw)
+            checked += 1
+    assert checked >= 36
+
+
+def test_matrix_observation_space_without_the_reference():
+    """The CNN-controller layout (tests/conftest.cnn_env_config): a [5, 12] Box whose rows repeat the per-entry bounds;
+    the numbers are the ones the live-reference test above pins (roll +-pi, Va [pyfly's value_min 1e-6, 60], relative targets unbounded,
+    action windows at the actuator limits)."""
+    from conftest import cnn_env_config
+    env, sim = C.resolve_configs(cnn_env_config(), None, None, None)
+    lo, hi = C.observation_space_bounds(env, sim)
+    assert lo.shape == hi.shape == (5, 12) and lo.dtype == np.float32
+    assert np.array_equal(lo[0], lo[4]) and np.isclose(hi[0, 0], np.pi) and hi[0, 2] == 60 and lo[0, 2] == np.float32(1e-6)
+    f32max = np.finfo(np.float32).max
+    assert np.all(hi[:, 6:9] == f32max) and np.all(lo[:, 6:9] == -f32max)
+    assert np.allclose(lo[0, 9:], [np.radians(-30), np.radians(-32.5), 0]) and np.allclose(hi[0, 9:], [np.radians(35), np.radians(32.5), 1])
+    alo, ahi = C.action_space_bounds(*C.resolve_configs(None, None, None, None))
+    assert np.all(ahi == f32max) and np.all(alo == -f32max)             # the default config says "max" (fixed_wing.py:218)

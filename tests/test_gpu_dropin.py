@@ -235,6 +235,37 @@ def test_reference_ppo_on_the_waypoint_adapter(cuda_device):
     env.close()
 
 
+def test_matrix_observation_layout_through_the_numpy_edge(cuda_device):
+    """The CNN-controller config (observation.shape "matrix", length 5): the adapter's Box is [5, 12] with the reference's
+    per-entry bounds (tests/test_capi_host.py pins them to the live reference) and reset / step / env_method("reset") /
+    terminal_observation hand out [.., 5, 12] arrays — the row-major view of the flat rows the kernels write (which
+    tests/test_gpu_parity.py pins to the live-reference fixture traj_cnn_obs.npz)."""
+    from conftest import cnn_env_config
+    from tum_adlr_deep_reinforcement_learning_b200.vec_env import FixedWingVecEnv
+    ecfg = cnn_env_config()
+    ecfg["steps_max"] = 6
+    n = 64
+    env = FixedWingVecEnv(n, config_path=ecfg, sim_config_kw={"turbulence": False}, seed=5)
+    assert env.observation_space.shape == (5, 12) and env.action_space.shape == (3,)
+    assert np.isclose(env.observation_space.high[0, 0], np.pi) and env.observation_space.high[3, 2] == 60
+    obs = env.reset()
+    assert obs.shape == (n, 5, 12) and obs.dtype == np.float32
+    assert np.array_equal(obs.reshape(n, 60), env.sim.obs.cpu().numpy())
+    rs = np.random.RandomState(0)
+    ends = 0
+    for t in range(8):
+        obs, rew, done, infos = env.step(rs.uniform(-1, 1, (n, 3)).astype(np.float32))
+        assert obs.shape == (n, 5, 12) and rew.shape == (n,) and done.shape == (n,)
+        assert np.array_equal(obs.reshape(n, 60), env.sim.obs.cpu().numpy())
+        for i in np.flatnonzero(done):
+            assert infos[i]["terminal_observation"].shape == (5, 12)
+            ends += 1
+    assert ends >= n                                            # steps_max 6: every env finished once
+    one = env.env_method("reset", indices=[3])[0]
+    assert one.shape == (5, 12)
+    env.close()
+
+
 def test_env_state_blob_round_trip(cuda_device):
     """fw_get_state_blob / fw_set_state_blob: a handle restored from a blob continues every episode bit-identically —
     through episode ends (the precomputed next-episode rows are part of the state) and after a live config change."""

@@ -683,9 +683,93 @@ def obs_dim(cfg):
     return cfg.obs_len * cfg.obs_n if cfg.obs_generic else FW_NOBS
 
 
+def _simulator_limits(sim):
+    """name -> {value_min, value_max, constraint_min, constraint_max} of the pyfly states as PyFly.__init__ leaves them
+    (Variable.__init__ degree conversion pyfly.py:61-64; elevator / aileron limits from the elevons, Actuation.finalize
+    pyfly.py:599-623) — before the gym config's simulator overrides, which set_curriculum_level applies after the spaces
+    are built (fixed_wing.py:412)."""
+    var = {}
+    for v in sim["variables"]:
+        v = dict(v)
+        if v.get("convert_to_radians"):
+            for k in ("value_min", "value_max", "constraint_min", "constraint_max"):
+                if v.get(k) is not None:
+                    v[k] = float(np.radians(v[k]))
+        var[v["name"]] = v
+    if "elevon_right" in var and "elevon_left" in var:
+        er, el = var["elevon_right"], var["elevon_left"]
+        if None not in (er.get("value_min"), er.get("value_max"), el.get("value_min"), el.get("value_max")):
+            var["elevator"] = {"value_min": (er["value_min"] + el["value_min"]) / 2,
+                               "value_max": (er["value_max"] + el["value_max"]) / 2}
+            var["aileron"] = {"value_min": (-er["value_max"] + el["value_min"]) / 2,
+                              "value_max": (-er["value_min"] + el["value_max"]) / 2}
+    return var
+
+
+def _state_limit(var, name, lim, sign):
+    st = var.get(name, {})
+    if st.get("value_" + lim) is not None:
+        return st["value_" + lim]
+    if st.get("constraint_" + lim) is not None:
+        return st["constraint_" + lim]
+    return sign * float(np.finfo(np.float32).max)
+
+
+def action_space_bounds(env, sim):
+    """(low, high) of `FixedWingAircraft.action_space`, float32 (fixed_wing.py:199-258): per action state "max" ->
+    +-float32 max, absent -> the simulator state's limit, else the number given."""
+    f32max = float(np.finfo(np.float32).max)
+    var = _simulator_limits(sim)
+    lo, hi = [], []
+    for a in env["action"]["states"]:
+        h, l = a.get("high"), a.get("low")
+        hi.append(f32max if h == "max" else _state_limit(var, a["name"], "max", 1.0) if h is None else h)
+        lo.append(-f32max if l == "max" else _state_limit(var, a["name"], "min", -1.0) if l is None else l)
+    return np.array(lo, dtype=np.float64).astype(np.float32), np.array(hi, dtype=np.float64).astype(np.float32)
+
+
+def observation_space_bounds(env, sim):
+    """(low, high) of `FixedWingAircraft.observation_space` for ANY observation layout, float32 and shaped like the
+    reference's Box: [n] per entry, tiled `length` times for shape "vector", [length, n] for shape "matrix"
+    (fixed_wing.py:92-140, 178-190, 245-247).  `env` / `sim`: the reference-format dicts of resolve_configs.  An entry's
+    bound is its own "low" / "high" (degrees converted if it says so), else the simulator state's value limit, else its
+    constraint, else +-float32 max; a relative target spans high - low either way when both are finite.  The reference
+    builds the space BEFORE set_curriculum_level applies the gym config's simulator overrides (fixed_wing.py:412), so
+    the simulator limits are pyfly_config's own (_simulator_limits)."""
+    f32max = float(np.finfo(np.float32).max)
+    var = _simulator_limits(sim)
+
+    def bound(o, key, lim, sign):
+        b = o.get(key)
+        if b is None:
+            return _state_limit(var, o["name"], lim, sign)
+        return float(np.radians(b)) if o.get("convert_to_radians", False) else b
+
+    lo, hi = [], []
+    for o in env["observation"]["states"]:
+        high, low = bound(o, "high", "max", 1.0), bound(o, "low", "min", -1.0)
+        if o["type"] == "target" and o.get("value") == "relative":
+            if high != f32max and low != -f32max:
+                high, low = high - low, low - high
+            else:
+                high, low = f32max, -f32max
+        hi.append(high)
+        lo.append(low)
+    L = int(env["observation"].get("length", 1))
+    if L > 1:
+        shape = env["observation"].get("shape", "vector")
+        if shape == "vector":
+            lo, hi = lo * L, hi * L
+        elif shape == "matrix":
+            lo, hi = [lo] * L, [hi] * L
+        else:
+            raise ValueError("observation.shape %r (fixed_wing.py:178-192)" % (shape,))
+    return np.array(lo, dtype=np.float64).astype(np.float32), np.array(hi, dtype=np.float64).astype(np.float32)
+
+
 def observation_bounds(env_cfg=None, cfg=None):
-    """observation_space low/high (fixed_wing.py:92-140) for the default 14-vector; a general layout reports
-    unbounded boxes of its own shape."""
+    """observation_space low/high (fixed_wing.py:92-140) of the default 14-vector from the flattened config alone (the
+    adapters use observation_space_bounds, which covers every layout); a general layout reports unbounded boxes."""
     if cfg is not None and cfg.obs_generic:
         f32max = float(np.finfo(np.float32).max)
         return (np.full(obs_dim(cfg), -f32max, np.float32), np.full(obs_dim(cfg), f32max, np.float32))

@@ -22,8 +22,8 @@ import numpy as np
 import torch
 
 from . import batched as bt
-from .config import (ANGULAR_TARGET_STATES, GOAL_STATES, METRIC_LAYOUT, TARGET_STATES, TERM_NAMES, build_config, observation_bounds,
-                     resolve_configs)
+from .config import (ANGULAR_TARGET_STATES, GOAL_STATES, METRIC_LAYOUT, TARGET_STATES, TERM_NAMES, action_space_bounds,
+                     build_config, observation_space_bounds, resolve_configs)
 
 
 class Box:
@@ -184,9 +184,12 @@ class FixedWingVecEnv(_VecEnvSurface):
         self.env_config, self.sim_config = resolve_configs(config_path, sim_config_path, config_kw, sim_config_kw)
         self.sim = bt.BatchedFixedWing(int(num_envs), cfg=self.cfg, device=device)
         self.device = self.sim.device
-        lo, hi = observation_bounds(cfg=self.cfg)
-        f32max = np.finfo(np.float32).max
-        self._init_vecenv(num_envs, make_box(lo, hi), make_box(np.full(3, -f32max), np.full(3, f32max)))
+        # the reference's own spaces for any layout (fixed_wing.py:92-258): per-entry bounds, [length, n] for
+        # observation.shape "matrix" — the numpy edge hands out observations in that shape (views of the flat rows the
+        # kernels write, which are the row-major matrix); the tensor fast path stays flat
+        lo, hi = observation_space_bounds(self.env_config, self.sim_config)
+        assert lo.size == self.sim.obs_dim, (lo.shape, self.sim.obs_dim)
+        self._init_vecenv(num_envs, make_box(lo, hi), make_box(*action_space_bounds(self.env_config, self.sim_config)))
         self.curriculum_level = 1.0
         self._init_host_edge(info_mode, copy_outputs)
 
@@ -206,7 +209,8 @@ class FixedWingVecEnv(_VecEnvSurface):
         self._out = [bt.unpack_outputs(b, n, self.sim.obs_dim) for b in self._out_pin]
         self._info_np = ([b[self.sim.info_offset:].view(torch.float64).numpy() for b in self._out_pin]
                          if self.sim.info_cap else None)
-        self._out_np = [(o.numpy(), r.numpy(), d.numpy().view(np.bool_)) for o, r, d in self._out]
+        oshape = (n,) + tuple(self.observation_space.shape)
+        self._out_np = [(o.numpy().reshape(oshape), r.numpy(), d.numpy().view(np.bool_)) for o, r, d in self._out]
         self._flip = 0
         # touch the done-path once so that CUDA's lazy module loading does not land on the first finished episode
         self.sim.episode_info_rows(torch.zeros(1, dtype=torch.long, device=self.device))
@@ -360,7 +364,7 @@ class FixedWingVecEnv(_VecEnvSurface):
             self.sim.enable_f64_outputs()
         self.sim.reset(mask=mask, state=st, target=tg, noise=noise)
         obs = self.sim.obs64.cpu().numpy()
-        return [obs[i].copy() for i in idx]
+        return [obs[i].reshape(self.observation_space.shape).copy() for i in idx]
 
     # ------------------------------------------------------------------ info dicts
     _done_info = staticmethod(_done_info)
@@ -413,7 +417,7 @@ class FixedWingVecEnv(_VecEnvSurface):
             names = ("position_n", "position_e", "position_d") if waypoint else self._target_names()
             infos = [{"target": dict(zip(names, map(float, tgt[i])))} for i in range(n)]
         now = round(time.time() - self._t_start, 6)
-        term_obs_all = rows[:, 31:].astype(np.float32)
+        term_obs_all = rows[:, 31:].astype(np.float32).reshape((-1,) + tuple(self.observation_space.shape))
         generic = bool(self.cfg.obs_generic)
         for j, (row, i) in enumerate(zip(rows[:, :31].tolist(), done_idx.tolist())):
             term_obs = term_obs_all[j]
@@ -524,7 +528,7 @@ class FixedWingAircraft:
         f64 = a.dtype != np.float32
         t = torch.as_tensor(a.reshape(1, 3), dtype=torch.float64 if f64 else torch.float32).to(self._v.device)
         self._v.sim.step(t.contiguous(), auto_reset=False)
-        obs = self._v.sim.obs64.cpu().numpy()[0].copy()
+        obs = self._v.sim.obs64.cpu().numpy()[0].reshape(self.observation_space.shape).copy()
         rew = float(self._v.sim.rew64.cpu().numpy()[0])
         done = bool(self._v.sim.done.cpu().numpy()[0])
         if done:
