@@ -582,8 +582,7 @@ class WaypointVecEnv(FixedWingVecEnv):
             task_of_env = np.arange(int(num_envs)) % self.tasks.shape[0]
         self.task_of_env = np.asarray(task_of_env, dtype=np.int32)
         self.sim.set_waypoint_tasks(self.tasks, self.task_of_env)
-        f32max = np.finfo(np.float32).max
-        self._init_vecenv(num_envs, make_box(np.full(12, -f32max), np.full(12, f32max)),
+        self._init_vecenv(num_envs, make_box(np.full(12, -np.inf), np.full(12, np.inf)),     # simple_train.py:267-273
                           make_box(np.array([-1, -1, 0]), np.array([1, 1, 1])))          # simple_train.py:275-279
         self.curriculum_level = 1.0
         self._init_host_edge(info_mode, copy_outputs)
