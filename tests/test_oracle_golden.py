@@ -363,8 +363,9 @@ def test_oracle_waypoint_env_head():
 def test_oracle_against_the_live_reference_on_fresh_episodes():
     """Where the reference can be imported (the build container, or its mirror baseline/_ref), tools/oracle_sweep.py draws
     NEW episodes in nine categories (calm / windy / out-of-range initial states, clipped and f32 actions, the three
-    turbulence intensities), steps the live reference (fixed_wing.py:483-652) and the oracle side by side and applies the
-    checks of the fixture test above: exact done / termination / RK45 RHS count, <= 1e-9 relative elsewhere.  In its own
+    turbulence intensities) and then under EVERY config file the reference ships (general observation layouts, reward
+    variants), steps the live reference (fixed_wing.py:483-652) and the oracle side by side and applies the checks of
+    the fixture test above: exact done / termination / RK45 RHS count, <= 1e-9 relative elsewhere.  In its own
     process: the reference needs the fabricated gym / matplotlib modules of oracle/refshim."""
     import os
     import subprocess
