@@ -38,8 +38,9 @@ CASES = [  # name, turbulence, intensity, wind_mag, action_amp, hard, f32 action
 
 # A config without rate constraints (fixed_wing_config_dev.json, scale_space false) lets the model blow up in finite time:
 # in the reference the body rates pass 100 rad/s, then the state climbs from 1e4 to 1e154 within a dozen steps (16 000 RHS
-# evaluations per step — the oracle counts the same 16 580 —, numpy overflow warnings).  Round-off differences are amplified without bound there, so an episode is compared up to the step
-# at which the REFERENCE state (position aside) exceeds BLOWUP and counted in `blown`; up to that step the usual bounds hold.
+# evaluations per step — the oracle counts the same 16 580 —, numpy overflow warnings).  Round-off differences are
+# amplified without bound there, so an episode is compared up to the step at which the REFERENCE state (position aside)
+# exceeds BLOWUP and counted in `blown`; up to that step the usual bounds hold.
 BLOWUP = 200.0
 blown = 0
 
